@@ -1,0 +1,261 @@
+/*
+ * tpt.h — C ABI of the B200 renderer backend (libtpt.so).
+ *
+ * This is the drop-in boundary underneath the reference's C++ host API.  The
+ * reference has no FFI of its own; what it has is one call,
+ *     Renderer::Render(std::string, const Scene&, int spp, int thread_count, bool bdpt)
+ *     (reference Renderer.hpp:11, Renderer.cpp:68-127)
+ * which runs FillBufferThread (Renderer.cpp:32-63) over all pixels and, inside
+ * it, PathTrace (PathTracer.cpp:44) or BDPT (BDPT.cpp:282).  Every entry point
+ * below replaces one piece of that path; the piece is cited next to it.
+ *
+ * Conventions: plain pointers and sizes, no C++ or torch types, no exceptions
+ * across the boundary.  Every function returns a TptStatus (0 = ok); the text of
+ * the last failure on the calling thread is available from tpt_last_error().
+ * The caller owns every host buffer it passes in.  Handles are opaque.
+ * There is no CPU fallback: without a CUDA device every call that computes
+ * returns TPT_ERR_NO_DEVICE.
+ */
+#ifndef TPT_H
+#define TPT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TPT_ABI_VERSION 1
+
+typedef enum TptStatus {
+    TPT_OK = 0,
+    TPT_ERR_INVALID = 1,     /* bad argument / malformed scene description */
+    TPT_ERR_NO_DEVICE = 2,   /* no usable CUDA device (there is no CPU path)  */
+    TPT_ERR_CUDA = 3,        /* a CUDA runtime call or kernel failed         */
+    TPT_ERR_OOM = 4
+} TptStatus;
+
+typedef struct TptVec3 { float x, y, z; } TptVec3;
+
+/* FaceCulling, reference Object.hpp:14-18 (same numeric values). */
+enum { TPT_CULL_BACK = 0, TPT_CULL_FRONT = 1, TPT_NO_CULL = 2 };
+
+/* MaterialType, reference Material.hpp:11-13 (same numeric values). */
+enum { TPT_MAT_DIELETRIC = 0, TPT_MAT_METAL = 1, TPT_MAT_TRANSPARENT = 2 };
+
+/* Material, reference Material.hpp:15-44: the fields the path reads. */
+typedef struct TptMaterial {
+    int32_t type;
+    TptVec3 emission;   /* m_emission */
+    TptVec3 Kd;
+    float   ior_d;
+    TptVec3 ior_m;
+    TptVec3 ior_m_k;
+    float   rough;
+} TptMaterial;
+
+/* BVHBuildNode, reference BVH.hpp:80-95, array layout (BVH_NODE_ARRAY_LAYOUT).
+ * left/right index the same array (-1 = none).  object: -1 for an interior
+ * node; in top_nodes[] the index into objects[]; in mesh_nodes[] the index of
+ * the triangle inside its mesh. */
+typedef struct TptNode {
+    TptVec3 bmin, bmax;
+    int32_t left, right;
+    int32_t object;
+    float   area;
+} TptNode;
+
+/* Triangle, reference Triangle.hpp:15-50: fields as computed by the host
+ * constructor (Triangle.hpp:18-25) — copied, never recomputed on the device. */
+typedef struct TptTriangle {
+    TptVec3 v0, v1, v2, e1, e2, normal;
+    float   area;
+} TptTriangle;
+
+/* Sphere, reference Sphere.hpp:12-32. */
+typedef struct TptSphere {
+    TptVec3 center;
+    float   radius, radius2, area;
+} TptSphere;
+
+/* One entry of Scene::objects (Scene.hpp:27), in Scene::Add order. */
+enum { TPT_OBJ_MESH = 0, TPT_OBJ_SPHERE = 1 };
+typedef struct TptObject {
+    int32_t kind;        /* TPT_OBJ_MESH | TPT_OBJ_SPHERE                         */
+    int32_t material;    /* index into materials[]                                */
+    int32_t first_prim;  /* mesh: first triangle in tris[]; sphere: index in spheres[] */
+    int32_t n_prims;     /* mesh: triangle count; sphere: 1                       */
+    int32_t first_node;  /* mesh: first node of its BVH in mesh_nodes[] (its root) */
+    int32_t n_nodes;     /* mesh: node count; sphere: 0                           */
+    float   area;        /* MeshTriangle::area / Sphere::area                     */
+    TptVec3 bmin, bmax;  /* Object::GetBounds()                                   */
+} TptObject;
+
+/* Flattened Scene (reference Scene.hpp:13-39 plus everything it points to).
+ * Global primitive ids used by every entry point: triangle i of tris[] has id
+ * i; sphere j has id n_tris + j. */
+typedef struct TptSceneDesc {
+    int32_t width, height;
+    double  fov;
+    TptVec3 eye;
+    TptVec3 background;
+    int32_t n_objects;    const TptObject*   objects;
+    int32_t n_top_nodes;  const TptNode*     top_nodes;   /* Scene::bvh->nodes           */
+    int32_t n_mesh_nodes; const TptNode*     mesh_nodes;  /* all MeshTriangle::bvh->nodes */
+    int32_t n_tris;       const TptTriangle* tris;
+    int32_t n_spheres;    const TptSphere*   spheres;
+    int32_t n_materials;  const TptMaterial* materials;
+    int32_t n_emissive;   const int32_t*     emissive_objects; /* Scene::m_emissionObjects */
+} TptSceneDesc;
+
+typedef struct TptScene TptScene;
+
+/* Integrator selection.  PT_SHIPPED is PathTrace exactly as the reference
+ * compiles (stray `break` at PathTracer.cpp:109: camera hit + direct light);
+ * PT_FULL is the same function with that line removed (the README PT images);
+ * BDPT is BDPT() (BDPT.cpp:282). */
+enum { TPT_MODE_PT_SHIPPED = 0, TPT_MODE_PT_FULL = 1, TPT_MODE_BDPT = 2 };
+
+/* Seeding.  REF: ResetRandom(pixel+1) once per pixel, the spp of a pixel drawn
+ * one after another from that stream (Renderer.cpp:42-53) — images converge to
+ * the reference's sample by sample.  SPLIT: the stream of (pixel, rank) starts
+ * from a hashed seed, for spp-split multi-GPU runs (statistical parity only). */
+enum { TPT_SEED_REF = 0, TPT_SEED_SPLIT = 1 };
+
+/* How the frame is shared between `world` cooperating calls (one per GPU). */
+enum {
+    TPT_PART_ALL = 0,        /* this call renders every pixel (spp is this call's share) */
+    TPT_PART_INTERLEAVE = 1  /* pixels i with i % world == rank, like Renderer.cpp:38    */
+};
+
+/* Scheduling of the work on the device. */
+enum {
+    TPT_PIPE_WAVEFRONT = 0,  /* queues: generate / extend / shade / connect / accumulate */
+    TPT_PIPE_MEGAKERNEL = 1  /* one thread per pixel, whole sample; validation path      */
+};
+
+typedef struct TptRenderParams {
+    int32_t mode;        /* TPT_MODE_*                                               */
+    int32_t spp;         /* samples this call renders per pixel                      */
+    int32_t spp_total;   /* the 1/spp weight of Renderer.cpp:49,51 (0 = same as spp) */
+    int32_t seed_mode;   /* TPT_SEED_*                                               */
+    int32_t partition;   /* TPT_PART_*                                               */
+    int32_t rank, world; /* 0,1 for a single GPU                                     */
+    int32_t pipeline;    /* TPT_PIPE_*                                               */
+    int32_t flags;       /* TPT_FLAG_*                                               */
+} TptRenderParams;
+
+enum {
+    TPT_FLAG_REF_TRAVERSAL = 1, /* no t-pruning: visit exactly the nodes BVH.cpp:103-143 visits */
+    TPT_FLAG_COUNT_VISITS  = 2  /* fill node_visits / prim_tests in TptStats (slower)           */
+};
+
+typedef struct TptStats {
+    uint64_t samples;      /* (pixel, spp) pairs rendered by this call                     */
+    uint64_t ref_rays;     /* the reference's "Rays" line: PathTracer.cpp:126 / BDPT.cpp:288 */
+    uint64_t traced_rays;  /* BVH queries issued: scene-level + light-object probes        */
+    uint64_t node_visits;  /* with TPT_FLAG_COUNT_VISITS                                   */
+    uint64_t prim_tests;   /* with TPT_FLAG_COUNT_VISITS                                   */
+    uint64_t launches;     /* kernels launched by this call                                */
+    double   device_ms;    /* CUDA-event time of the kernels, first launch to last         */
+    double   h2d_ms, d2h_ms;
+} TptStats;
+
+/* ---- lifetime ---------------------------------------------------------- */
+
+int         tpt_abi_version(void);
+const char* tpt_last_error(void);
+/* Number of usable CUDA devices (0 when there is none). */
+int         tpt_device_count(void);
+
+/* Replaces Scene::BuildBVH's product (Scene.cpp:11-19) + the MeshTriangle BVHs
+ * (Triangle.cpp:69-74) as a device-resident, 128-bit packed scene on `device`. */
+int tpt_scene_create(const TptSceneDesc* desc, int device, TptScene** out);
+int tpt_scene_destroy(TptScene* scene);
+
+/* ---- the exact tier ----------------------------------------------------- */
+
+/* Scene::Intersect / BVHAccel::Intersect (Scene.cpp:21-35, BVH.cpp:103-143) for
+ * a batch of rays.  org/dir: n*3 floats; cull: n bytes (TPT_CULL_*).
+ * Outputs (any may be NULL): prim_id (-1 = miss), t (Intersection::distance),
+ * coords and normal (n*3 floats, zero on a miss).  Host buffers. */
+int tpt_intersect_batch(TptScene* scene, const float* org, const float* dir,
+                        const uint8_t* cull, size_t n, int32_t flags,
+                        int32_t* prim_id, double* t, float* coords, float* normal,
+                        TptStats* stats);
+
+/* Same, on buffers already resident on the scene's device; asynchronous on
+ * `stream` (a cudaStream_t, NULL = default stream). */
+int tpt_intersect_batch_device(TptScene* scene, const float* d_org, const float* d_dir,
+                               const uint8_t* d_cull, size_t n, int32_t flags,
+                               int32_t* d_prim_id, double* d_t, float* d_coords,
+                               float* d_normal, void* stream);
+
+/* Scene::ShadowCheck(Vector3f light, Vector3f x, cull) (Scene.cpp:37-48).
+ * from/to: n*3 floats, shadowed: n bytes. */
+int tpt_shadow_batch(TptScene* scene, const float* from, const float* to,
+                     const uint8_t* cull, size_t n, uint8_t* shadowed);
+
+/* ---- the render path ----------------------------------------------------- */
+
+/* Renderer::Render's timed region (Renderer.cpp:76-117) without the JPEG write:
+ * out_rgb (host, width*height*3 floats) receives framebuffer[i] — radiance plus
+ * merged light-splat buffer, already weighted by 1/spp_total. */
+int tpt_render(TptScene* scene, const TptRenderParams* params, float* out_rgb,
+               TptStats* stats);
+
+/* The same work leaving this call's partial sums on the device:
+ * d_accum is 2*width*height*3 floats, [radiance | splat], already weighted by
+ * 1/spp_total, to be summed over ranks (one NCCL reduce) and then merged by
+ * tpt_finalize_device.  Asynchronous on `stream`. */
+int tpt_render_device(TptScene* scene, const TptRenderParams* params, float* d_accum,
+                      void* stream, TptStats* stats);
+size_t tpt_accum_floats(const TptScene* scene);
+
+/* Renderer.cpp:98-114 (emission-buffer merge) as one epilogue kernel:
+ * d_out[i] = radiance[i] + splat[i].  With d_rgb8 != NULL it also applies
+ * SaveFloatImageToJpg's tonemap (SceneRenderingHelper.cpp:57-66). */
+int tpt_finalize_device(TptScene* scene, const float* d_accum, float* d_out_rgb,
+                        uint8_t* d_rgb8, void* stream);
+
+/* ---- per-function entry points (parity tests against the oracle) --------- */
+
+/* XorShift32 / GetRandomFloat (global.cpp:5-22): n draws from ResetRandom(seed). */
+int tpt_rng_batch(uint32_t seed, size_t n, uint32_t* states, float* floats);
+
+/* Material::evalGivenSample / pdf / fresnel (Material.cpp:11-72, 105-147,
+ * 221-252) on n independent (wo, wi, normal) triples for material `mat`. */
+int tpt_material_eval_batch(TptScene* scene, int32_t mat, const float* wo, const float* wi,
+                            const float* nrm, int32_t combine_cosine, size_t n, float* out_rgb);
+int tpt_material_pdf_batch(TptScene* scene, int32_t mat, const float* wo, const float* nrm,
+                           const float* wi, size_t n, float* out_pdf);
+int tpt_material_fresnel_batch(TptScene* scene, int32_t mat, const float* I, const float* nrm,
+                               size_t n, float* out_rgb);
+/* Material::sample (Material.cpp:150-214) from ResetRandom(seeds[i]). */
+int tpt_material_sample_batch(TptScene* scene, int32_t mat, const float* wo, const float* nrm,
+                              const uint32_t* seeds, size_t n, float* out_wi, float* out_pdf,
+                              uint32_t* out_state);
+
+/* A BDPT subpath vertex as the integrators store it (BDPT.hpp:16-21). */
+typedef struct TptPathVertex {
+    TptVec3 x, N;
+    int32_t prim;     /* global primitive id, -1 = none (camera / background)   */
+    int32_t type;     /* PTVertex::Type: 0 Background 1 Intermediate 2 Light 3 Camera */
+    float   pdf;
+    TptVec3 alpha;
+} TptPathVertex;
+
+/* BDPTPath::PathWeight (BDPT.cpp:173-259) for explicit subpaths: for each of the
+ * n path pairs (cam_count[i] camera vertices at cam + 16*i, light_count[i] light
+ * vertices at light + 16*i) every strategy (s = 1..cam_count, t = 0..light_count,
+ * s + t >= 2) is evaluated; weights holds 16*17*3 floats per pair, strategy (s,t)
+ * at ((s-1)*17 + t)*3, already clamped at zero like BDPT.cpp:299. */
+int tpt_bdpt_pathweight_batch(TptScene* scene, const TptPathVertex* cam, const int32_t* cam_count,
+                              const TptPathVertex* light, const int32_t* light_count,
+                              size_t n, float* weights);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TPT_H */
