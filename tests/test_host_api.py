@@ -1,0 +1,67 @@
+"""The product's host API (Scene / MeshTriangle / Sphere / BVHAccel, host/tpt_api.hpp) builds,
+node for node and bit for bit, the trees the reference builds — the tree shape is the tie
+order of the closest-hit query."""
+import numpy as np
+import pytest
+
+from conftest import desc_from_golden, golden
+from oracle import bindings as B
+
+SCENES = ["standard", "smooth", "silver", "refractive", "occlusion", "bunny"]
+
+
+@pytest.mark.parametrize("scene", SCENES)
+def test_flattened_scene_matches_reference_trees(tpt, scene):
+    hs = tpt.HostScene(scene, 784, 784)
+    mine = B.desc_arrays(B.SceneDesc.from_buffer_copy(bytes(hs.desc)))
+    ref_desc, keep = desc_from_golden(scene)
+    theirs = B.desc_arrays(ref_desc)
+    assert mine["header"] == theirs["header"]
+    for key in ("objects", "top_nodes", "mesh_nodes", "tris", "spheres", "materials", "emissive"):
+        assert mine[key].shape == theirs[key].shape, key
+        assert (mine[key] == theirs[key]).all(), key
+
+
+@pytest.mark.skipif(not B.have_ref(), reason="compiled reference not present")
+@pytest.mark.parametrize("scene", ["standard", "occlusion"])
+def test_golden_flat_files_are_the_reference(scene):
+    chk, d = B.ref_scene(scene, 784, 784)
+    a, b = B.desc_arrays(d), B.desc_arrays(desc_from_golden(scene)[0])
+    for key in a:
+        assert (np.asarray(a[key]) == np.asarray(b[key])).all() if key != "header" else a[key] == b[key]
+
+
+def test_scene_sizes(tpt):
+    """Sizes quoted in SURVEY.md section 8."""
+    d = tpt.HostScene("standard", 784, 784).desc
+    assert (d.n_tris, d.n_top_nodes, d.n_mesh_nodes, d.n_objects, d.n_emissive) == (32, 11, 58, 6, 1)
+    d = tpt.HostScene("refractive", 784, 784).desc
+    assert (d.n_spheres, d.n_top_nodes) == (1, 13)
+    d = tpt.HostScene("occlusion", 784, 784).desc
+    assert d.n_tris == 36
+
+
+def test_obj_reader_variants(tpt, tmp_path):
+    """v/vt/vn index forms, negative indices and a polygon face."""
+    import os
+    box = tmp_path / "cornellbox"
+    os.makedirs(box)
+    tpt.ensure_models()
+    import shutil
+    for f in os.listdir(os.path.join(tpt.MODELS_DIR, "cornellbox")):
+        shutil.copy(os.path.join(tpt.MODELS_DIR, "cornellbox", f), box / f)
+    # rewrite two meshes with other index syntaxes that describe the same triangles
+    def verts(name):
+        return [l for l in open(os.path.join(tpt.MODELS_DIR, "cornellbox", name)).read().splitlines() if l.startswith("v ")]
+    # left.obj is "f 1 2 3 / f 1 3 4": slashed forms and negative (relative) indices
+    (box / "left.obj").write_text("# comment\n" + "\n".join(verts("left.obj")) +
+                                  "\nvn 0 1 0\nvt 0 0\nf 1/1/1 2//1 -2\nf -4 3/1 4\n")
+    # light.obj is the same fan: one quad face
+    (box / "light.obj").write_text("\n".join(verts("light.obj")) + "\n\nf 1 2 3 4\n")
+    sa = tpt.HostScene("standard", 64, 64, models_dir=str(tmp_path))   # keep alive: desc points into it
+    sb = tpt.HostScene("standard", 64, 64)
+    a, b = sa.desc, sb.desc
+    assert a.n_tris == b.n_tris
+    ta = B.desc_arrays(B.SceneDesc.from_buffer_copy(bytes(a)))["tris"]
+    tb = B.desc_arrays(B.SceneDesc.from_buffer_copy(bytes(b)))["tris"]
+    assert (ta == tb).all()

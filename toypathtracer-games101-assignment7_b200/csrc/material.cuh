@@ -1,0 +1,234 @@
+// material.cuh — GGX / Lambert / Fresnel sampling and evaluation on the device
+// (shading tier of vec.cuh).  Function by function it follows reference
+// Material.cpp, GGX.hpp and SampleHelperFunctions.{hpp,cpp}; the float/double
+// promotions of each expression are kept (DotProduct is double and narrowed where
+// the reference assigns it to a float), including the safe-divide pdf semantics.
+#pragma once
+
+#include "traverse.cuh"
+
+// ---- SampleHelperFunctions -------------------------------------------------------
+TPT_DEV f3 reflect_dir(f3 I, f3 N) {                      // Reflect, .cpp:21-25
+    I = -I;
+    const float k = (float)(2 * dotd(I, N));
+    return I - k * N;
+}
+TPT_DEV f3 refract_dir(f3 I, f3 N, float ior) {           // Refract, .cpp:37-48 (zero vector on TIR)
+    I = -I;
+    float cosi = (float)std_clampd(dotd(I, N), -1.0, 1.0);
+    float etai = 1, etat = ior;
+    f3 n = N;
+    if (cosi < 0) { cosi = -cosi; } else { float s = etai; etai = etat; etat = s; n = -N; }
+    const float eta = etai / etat;
+    const float k = 1 - eta * eta * (1 - cosi * cosi);
+    if (k < 0) return mk3(0.0f);
+    return x_normalize(eta * I + (eta * cosi - sqrtf(k)) * n);
+}
+TPT_DEV f3 any_perpendicular(f3 i) {                       // AnyPerpendicular, .cpp:51-67
+    if (i.z == 0.0f) {
+        if (i.y == 0.0f) return mk3(0.0f, 1.0f, 0.0f);
+        return x_normalize(mk3(1.0f, -i.x / i.y, 0.0f));
+    }
+    return x_normalize(mk3(0.0f, 1.0f, -1.0f * i.y / i.z));
+}
+TPT_DEV f3 to_world(f3 a, f3 N) {                          // TransformVectorToWorld, .hpp:46-54
+    const f3 tangent = any_perpendicular(N);
+    const f3 bitangent = x_cross(N, tangent);
+    return mk3(a.x * tangent.x + a.y * bitangent.x + a.z * N.x,
+               a.x * tangent.y + a.y * bitangent.y + a.z * N.y,
+               a.x * tangent.z + a.y * bitangent.z + a.z * N.z);
+}
+TPT_DEV f3 half_dir(f3 N, f3 wi, f3 wo, float matIor, float nl, float nv) {   // GetHalfDir, .hpp:79-102
+    if (nl == 0.0f || nv == 0.0f) return mk3(0.0f);
+    f3 h;
+    if (nl * nv > 0.0f) {
+        h = x_normalize(wi + wo);
+        if (nv < 0.0f) h = -h;
+    } else {
+        if (nv < 0.0f) h = -x_normalize(matIor * wo + wi);
+        else h = -x_normalize(wo + wi * matIor);
+    }
+    return h;
+}
+TPT_DEV float cosine_pdf(f3 N, f3 wi) { return saturate_f(dotf(wi, N)) / TPT_PI; }   // .hpp:118-120
+TPT_DEV f3 cosine_sample(uint32_t& rng, f3 N, float* pdf) {                            // .hpp:105-115
+    const float u1 = rng_float(rng);
+    const float r = sqrtf(u1);
+    const float theta = 2 * TPT_PI * rng_float(rng);
+    float sn, cs;
+    sincosf(theta, &sn, &cs);
+    const float x = r * cs, y = r * sn;
+    const f3 wi = x_normalize(to_world(mk3(x, y, sqrtf(1.0f - u1)), N));
+    *pdf = (float)(dotd(wi, N) / (double)TPT_PI);   // double / float -> double, then narrowed
+    return wi;
+}
+
+// ---- GGX.hpp ----------------------------------------------------------------------
+TPT_DEV float ggx_visibility(float vn, float vh, float roughness) {   // Visibility, :8-14
+    if (vh * vn <= 0.0f) return 0.0f;
+    const float vh2 = vh * vh;
+    const float tan2 = (1.0f - vh2) / vh2;
+    return 2.0f / (1 + sqrtf(1.0f + roughness * roughness * tan2));
+}
+TPT_DEV float ggx_term(float ndoth, float roughness) {                 // GGXTerm, :17-30
+    const float a2 = roughness * roughness;
+    const float c2 = ndoth * ndoth;
+    const float c4 = c2 * c2;
+    const float tan2 = (1.0f - c2) / c2;
+    float den = a2 + tan2;
+    den = den * den;
+    return a2 / (TPT_PI * c4 * den);
+}
+TPT_DEV float ggx_half_pdf(f3 n, f3 h, float roughness) {              // GGXHalfPDF, :33-35
+    const double a = fabs(dotd(n, h));
+    return (float)((double)ggx_term((float)a, roughness) * a);
+}
+TPT_DEV f3 ggx_sample_h(uint32_t& rng, f3 N, float roughness) {        // SampleGGXSpecularH, :46-59
+    const float d1 = rng_float(rng), d2 = rng_float(rng);
+    const float theta = atan2f(roughness * sqrtf(d1), sqrtf(1.0f - d1));
+    const float phi = 2.0f * TPT_PI * d2;
+    float st, ct, sp, cp;
+    sincosf(theta, &st, &ct);
+    sincosf(phi, &sp, &cp);
+    return x_normalize(to_world(mk3(st * cp, st * sp, ct), N));
+}
+
+// ---- Material.cpp -----------------------------------------------------------------
+TPT_DEV f3 mat_fresnel(const Mat& m, f3 I, f3 N) {                     // fresnel, :221-252
+    if (m.type == 1) {   // Metal: conductor approximation, per channel
+        const float cosTheta = dotf(I, N);
+        const float cosTheta2 = cosTheta * cosTheta;
+        const f3 TwoEtaCosTheta = (m.ior_m * 2.0f) * cosTheta;
+        const f3 t0 = m.ior_m * m.ior_m + m.ior_m_k * m.ior_m_k;
+        const f3 t1 = t0 * cosTheta2;
+        const f3 Rs = (t0 - TwoEtaCosTheta + mk3(cosTheta2)) / (t0 + TwoEtaCosTheta + mk3(cosTheta2));
+        const f3 Rp = (t1 - TwoEtaCosTheta + mk3(1.0f)) / (t1 + TwoEtaCosTheta + mk3(1.0f));
+        return 0.5f * (Rp + Rs);
+    }
+    I = -I;
+    float cosi = (float)std_clampd(dotd(I, N), -1., 1.);
+    float etai = 1, etat = m.ior_d;
+    if (cosi > 0) { float s = etai; etai = etat; etat = s; }
+    const float sint = etai / etat * sqrtf(std_max(0.f, 1 - cosi * cosi));
+    if (sint >= 1) return mk3(1.0f);
+    const float cost = sqrtf(std_max(0.f, 1 - sint * sint));
+    cosi = fabsf(cosi);
+    const float Rs = ((etat * cosi) - (etai * cost)) / ((etat * cosi) + (etai * cost));
+    const float Rp = ((etai * cosi) - (etat * cost)) / ((etai * cosi) + (etat * cost));
+    return mk3((Rs * Rs + Rp * Rp) / 2);
+}
+
+// evalGivenSample, :11-72: f * cos (or f when combineCosineTerm is false)
+TPT_DEV f3 mat_eval(const Mat& m, f3 wo, f3 wi, f3 N, bool combineCosineTerm) {
+    const float nl = dotf(N, wi);
+    const float nv = dotf(N, wo);
+    if (nl == 0.0f || nv == 0.0f) return mk3(0.0f);
+    const f3 h = half_dir(N, wi, wo, m.ior_d, nl, nv);
+    const float nh = dotf(N, h);
+    const float lh = dotf(wi, h);
+    const float vh = dotf(wo, h);
+    const float D = ggx_term(nh, m.rough);
+    const float G = ggx_visibility(nv, vh, m.rough) * ggx_visibility(nl, lh, m.rough);
+    const f3 f = mat_fresnel(m, wi, h);
+    if (nl * nv > 0.0f) {   // reflection
+        f3 specular = mk3(0.0f);
+        if (G != 0.0f) {
+            specular = ((D * f) * G) / (4.0f * fabsf(nv));
+            if (!combineCosineTerm) specular = specular / fabsf(nl);
+        }
+        f3 diffuse = mk3(0.0f);
+        if (m.type == 0) {  // Dieletric
+            diffuse = (m.Kd * (mk3(1.0f) - f)) / TPT_PI;
+            if (combineCosineTerm) diffuse = diffuse * saturate_f(nl);
+        }
+        return diffuse + specular;
+    }
+    if (m.type != 2) return mk3(0.0f);   // refraction only through Transparent
+    float ior_i, ior_o;
+    if (nv < 0.0f) { ior_i = 1.0f; ior_o = m.ior_d; } else { ior_i = m.ior_d; ior_o = 1.0f; }
+    float partA = fabsf(vh) * fabsf(lh) / fabsf(nv);
+    if (!combineCosineTerm) partA /= fabsf(nl);
+    const float partB = ior_o * ior_o * (1.0f - f.x) * G * D;
+    if (partA * partB == 0.0f) return mk3(0.0f);
+    float partC = ior_i * lh + ior_o * vh;
+    partC *= partC;
+    return mk3(partA * partB / partC);
+}
+
+// pdf, :105-147
+TPT_DEV float mat_pdf(const Mat& m, f3 w_o, f3 n, f3 w_i) {
+    const float nv = dotf(n, w_o), nl = dotf(n, w_i);
+    if (nv == 0.0f || nl == 0.0f) return 0.0f;
+    const f3 h = half_dir(n, w_i, w_o, m.ior_d, nl, nv);
+    const float pdf_h = ggx_half_pdf(n, h, m.rough);
+    const float vh = dotf(w_o, h);
+    const float abs_vh = fabsf(vh);
+    if (nv * nl < 0.0f) {
+        if (m.type != 2) return 0.0f;
+        const f3 f = mat_fresnel(m, w_o, h);
+        const float lh = dotf(w_i, h);
+        const float ior_i = (nl < 0.0f) ? m.ior_d : 1.0f;    // GetInsideOutsideIOR, .hpp:57-73
+        const float ior_o = (nv < 0.0f) ? m.ior_d : 1.0f;
+        const float den = (ior_i * lh + ior_o * vh);
+        const float jaco = safe_div(ior_o * ior_o * abs_vh, (den * den));
+        return pdf_h * (1.0f - f.x) * jaco;
+    } else if (nv * nl > 0.0f) {
+        const float jaco = safe_div(1.0f, (4.0f * abs_vh));
+        if (m.type == 1) return pdf_h * jaco;
+        if (m.type == 0) return (cosine_pdf(n, w_i) + pdf_h * jaco) * 0.5f;
+        const f3 f = mat_fresnel(m, w_o, h);
+        return pdf_h * f.x * jaco;
+    }
+    return 0.0f;
+}
+
+// sample, :150-214.  RNG draws: 2 for H, then Dieletric 1 (+2 on the diffuse branch),
+// Transparent 1, Metal 0 — same order as the reference.
+TPT_DEV f3 mat_sample(const Mat& m, uint32_t& rng, f3 w_o, f3 n, float* pdf) {
+    f3 H = ggx_sample_h(rng, n, m.rough);
+    const f3 w_i_s = reflect_dir(w_o, H);
+    float pdf_h = ggx_half_pdf(n, H, m.rough);
+    const float vn = dotf(w_o, n);
+    float vh = dotf(w_o, H);
+    float abs_vh = fabsf(vh);
+    float jaco_reflect = safe_div(1.0f, (4.0f * abs_vh));
+    if (m.type == 1) {
+        *pdf = pdf_h * jaco_reflect;
+        if (vn * dotf(w_i_s, n) < 0.0f) *pdf = 0.0f;
+        return w_i_s;
+    }
+    if (m.type == 0) {
+        if (rng_float(rng) < 0.5f) {   // specular lobe
+            const float pdf_d = cosine_pdf(n, w_i_s);
+            *pdf = (pdf_h * jaco_reflect + pdf_d) * 0.5f;
+            if (vn * dotf(w_i_s, n) < 0.0f) *pdf = 0.0f;
+            return w_i_s;
+        }
+        float pdf_d;
+        const f3 w_i_d = cosine_sample(rng, n, &pdf_d);
+        H = x_normalize(w_i_d + w_o);
+        vh = dotf(w_o, H);
+        abs_vh = fabsf(vh);
+        pdf_h = ggx_half_pdf(n, H, m.rough);
+        jaco_reflect = safe_div(1.0f, (4.0f * abs_vh));
+        *pdf = (pdf_h * jaco_reflect + pdf_d) * 0.5f;
+        if (vn * dotf(w_i_d, n) < 0.0f) *pdf = 0.0f;
+        return w_i_d;
+    }
+    const f3 f = mat_fresnel(m, w_o, H);
+    if (rng_float(rng) < f.x) {
+        *pdf = pdf_h * f.x * jaco_reflect;
+        if (vn * dotf(w_i_s, n) < 0.0f) *pdf = 0.0f;
+        return w_i_s;
+    }
+    const f3 w_i_refract = refract_dir(w_o, H, m.ior_d);
+    const float nl = dotf(n, w_i_refract);
+    const float ior_i = (nl < 0.0f) ? m.ior_d : 1.0f;
+    const float ior_o = (vn < 0.0f) ? m.ior_d : 1.0f;
+    const float lh = dotf(w_i_refract, H);
+    const float den = (ior_i * lh + ior_o * vh);
+    const float jaco_refract = safe_div(ior_o * ior_o * abs_vh, (den * den));
+    *pdf = pdf_h * (1.0f - f.x) * jaco_refract;
+    if (vn * dotf(w_i_refract, n) > 0.0f) *pdf = 0.0f;
+    return w_i_refract;
+}

@@ -1,0 +1,700 @@
+// tpt.cu — libtpt.so: the C ABI of include/tpt.h, the device scene builder, the
+// exact-tier batch kernels, the per-function parity kernels and the one-thread-
+// per-pixel validation renderer.  The wavefront pipeline lives in wavefront.cu.
+//
+// There is no CPU path in this library: without a CUDA device every computing
+// entry point fails with TPT_ERR_NO_DEVICE.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "integrators.cuh"
+#include "tpt_internal.h"
+
+// ------------------------------------------------------------------ error plumbing
+static thread_local std::string g_last_error;
+void tpt_set_error(const std::string& msg) { g_last_error = msg; }
+bool tpt_cuda_ok(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    tpt_set_error(std::string(what) + ": " + cudaGetErrorString(e));
+    return false;
+}
+
+extern "C" int tpt_abi_version(void) { return TPT_ABI_VERSION; }
+extern "C" const char* tpt_last_error(void) { return g_last_error.c_str(); }
+extern "C" int tpt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+static int require_device(int device) {
+    const int n = tpt_device_count();
+    if (n <= 0) { tpt_set_error("no CUDA device available (libtpt has no CPU fallback)"); return TPT_ERR_NO_DEVICE; }
+    if (device < 0 || device >= n) { tpt_set_error("device index out of range"); return TPT_ERR_INVALID; }
+    TPT_CUDA(cudaSetDevice(device));
+    return TPT_OK;
+}
+
+// ------------------------------------------------------------------ scene builder
+namespace {
+
+struct HostBuild {
+    const TptSceneDesc* d;
+    std::vector<float4> nodes;       // 2 per node
+    std::vector<DevObject> objs;
+    std::string err;
+
+    static float as_f(int v) { float f; std::memcpy(&f, &v, 4); return f; }
+
+    int push(const TptVec3& lo, const TptVec3& hi, int prim) {
+        const int self = (int)nodes.size() / 2;
+        nodes.push_back(make_float4(lo.x, lo.y, lo.z, as_f(prim)));
+        nodes.push_back(make_float4(hi.x, hi.y, hi.z, as_f(self + 1)));
+        return self;
+    }
+    void set_miss(int node) { nodes[2 * node + 1].w = as_f((int)nodes.size() / 2); }
+
+    // the reference pops `right` first (BVH.cpp:137-138,121): right subtree precedes left
+    bool emit_mesh(const TptObject& o, int local, int depth) {
+        if (local < 0 || local >= o.n_nodes || depth > 128) { err = "malformed mesh BVH"; return false; }
+        const TptNode& n = d->mesh_nodes[o.first_node + local];
+        if (n.object >= 0) {
+            if (n.object >= o.n_prims) { err = "mesh BVH leaf outside its mesh"; return false; }
+            push(n.bmin, n.bmax, o.first_prim + n.object);
+            return true;
+        }
+        const int self = push(n.bmin, n.bmax, -1);
+        if (!emit_mesh(o, n.right, depth + 1) || !emit_mesh(o, n.left, depth + 1)) return false;
+        set_miss(self);
+        return true;
+    }
+    bool emit_top(int idx, int depth) {
+        if (idx < 0 || idx >= d->n_top_nodes || depth > 128) { err = "malformed top-level BVH"; return false; }
+        const TptNode& n = d->top_nodes[idx];
+        if (n.object >= 0) {
+            if (n.object >= d->n_objects) { err = "top-level leaf outside objects[]"; return false; }
+            const TptObject& o = d->objects[n.object];
+            DevObject& dev = objs[n.object];
+            if (o.kind == TPT_OBJ_SPHERE) {
+                dev.root = push(n.bmin, n.bmax, d->n_tris + o.first_prim);
+                dev.end = dev.root + 1;
+                return true;
+            }
+            if (o.n_nodes <= 0) { err = "mesh without a BVH"; return false; }
+            // The leaf box (MeshTriangle::bounding_box) and the mesh root box are the same
+            // numbers for a mesh built by the host API; then one slab test stands for both.
+            const TptNode& mr = d->mesh_nodes[o.first_node];
+            const bool same = std::memcmp(&mr.bmin, &n.bmin, sizeof(TptVec3)) == 0 &&
+                              std::memcmp(&mr.bmax, &n.bmax, sizeof(TptVec3)) == 0;
+            int gate = -1;
+            if (!same) gate = push(n.bmin, n.bmax, -1);
+            dev.root = (int)nodes.size() / 2;
+            if (!emit_mesh(o, 0, depth + 1)) return false;
+            dev.end = (int)nodes.size() / 2;
+            if (gate >= 0) set_miss(gate);
+            return true;
+        }
+        const int self = push(n.bmin, n.bmax, -1);
+        if (!emit_top(n.right, depth + 1) || !emit_top(n.left, depth + 1)) return false;
+        set_miss(self);
+        return true;
+    }
+};
+
+template <class T> int upload(TptScene* s, const std::vector<T>& host, const T** dev) {
+    void* p = nullptr;
+    const size_t bytes = std::max<size_t>(host.size() * sizeof(T), 16);
+    TPT_CUDA(cudaMalloc(&p, bytes));
+    s->allocs.push_back(p);
+    TPT_CUDA(cudaMemset(p, 0, bytes));
+    if (!host.empty()) TPT_CUDA(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *dev = reinterpret_cast<const T*>(p);
+    return TPT_OK;
+}
+
+}  // namespace
+
+extern "C" int tpt_scene_create(const TptSceneDesc* d, int device, TptScene** out) {
+    if (!d || !out) { tpt_set_error("null argument"); return TPT_ERR_INVALID; }
+    *out = nullptr;
+    if (d->width <= 0 || d->height <= 0 || d->n_objects <= 0 || d->n_top_nodes <= 0 || d->n_materials <= 0 ||
+        !d->objects || !d->top_nodes || !d->materials) {
+        tpt_set_error("scene description is empty or incomplete");
+        return TPT_ERR_INVALID;
+    }
+    HostBuild hb;
+    hb.d = d;
+    hb.objs.assign(d->n_objects, DevObject());
+    for (int k = 0; k < d->n_objects; ++k) {
+        const TptObject& o = d->objects[k];
+        DevObject& dev = hb.objs[k];
+        std::memset(&dev, 0, sizeof dev);
+        if (o.material < 0 || o.material >= d->n_materials) { tpt_set_error("object material out of range"); return TPT_ERR_INVALID; }
+        dev.kind = o.kind; dev.material = o.material; dev.first_prim = o.first_prim; dev.n_prims = o.n_prims;
+        dev.root = dev.end = -1; dev.lroot = o.first_node; dev.area = o.area;
+        if (o.kind == TPT_OBJ_MESH) {
+            if (o.first_prim < 0 || o.first_prim + o.n_prims > d->n_tris || o.first_node < 0 ||
+                o.first_node + o.n_nodes > d->n_mesh_nodes || o.n_nodes <= 0) {
+                tpt_set_error("mesh ranges out of bounds");
+                return TPT_ERR_INVALID;
+            }
+            dev.root_area = d->mesh_nodes[o.first_node].area;
+        } else if (o.kind == TPT_OBJ_SPHERE) {
+            if (o.first_prim < 0 || o.first_prim >= d->n_spheres) { tpt_set_error("sphere index out of bounds"); return TPT_ERR_INVALID; }
+            dev.root_area = d->spheres[o.first_prim].area;
+        } else { tpt_set_error("unknown object kind"); return TPT_ERR_INVALID; }
+    }
+    if (!hb.emit_top(0, 0)) { tpt_set_error(hb.err); return TPT_ERR_INVALID; }
+    for (int k = 0; k < d->n_objects; ++k)
+        if (hb.objs[k].root < 0) { tpt_set_error("an object is not reachable from the top-level BVH"); return TPT_ERR_INVALID; }
+
+    std::vector<float4> tris, tverts, spheres, mats;
+    std::vector<DevLightNode> lnodes(d->n_mesh_nodes);
+    for (int k = 0; k < d->n_objects; ++k) {
+        const TptObject& o = d->objects[k];
+        if (o.kind != TPT_OBJ_MESH) continue;
+        for (int j = 0; j < o.n_nodes; ++j) {
+            const TptNode& n = d->mesh_nodes[o.first_node + j];
+            DevLightNode& l = lnodes[o.first_node + j];
+            l.left = n.left; l.right = n.right; l.area = n.area;
+            l.tri = n.object >= 0 ? o.first_prim + n.object : -1;
+        }
+    }
+    std::vector<int> triMat(d->n_tris, 0), triObj(d->n_tris, 0);
+    for (int k = 0; k < d->n_objects; ++k)
+        if (d->objects[k].kind == TPT_OBJ_MESH)
+            for (int j = 0; j < d->objects[k].n_prims; ++j) {
+                triMat[d->objects[k].first_prim + j] = d->objects[k].material;
+                triObj[d->objects[k].first_prim + j] = k;
+            }
+    for (int p = 0; p < d->n_tris; ++p) {
+        const TptTriangle& t = d->tris[p];
+        tris.push_back(make_float4(t.v0.x, t.v0.y, t.v0.z, HostBuild::as_f(triMat[p])));
+        tris.push_back(make_float4(t.e1.x, t.e1.y, t.e1.z, t.area));
+        tris.push_back(make_float4(t.e2.x, t.e2.y, t.e2.z, HostBuild::as_f(triObj[p])));
+        tris.push_back(make_float4(t.normal.x, t.normal.y, t.normal.z, 0.0f));
+        tverts.push_back(make_float4(t.v1.x, t.v1.y, t.v1.z, 0.0f));
+        tverts.push_back(make_float4(t.v2.x, t.v2.y, t.v2.z, 0.0f));
+    }
+    std::vector<int> sphMat(d->n_spheres, 0), sphObj(d->n_spheres, 0);
+    for (int k = 0; k < d->n_objects; ++k)
+        if (d->objects[k].kind == TPT_OBJ_SPHERE) {
+            sphMat[d->objects[k].first_prim] = d->objects[k].material;
+            sphObj[d->objects[k].first_prim] = k;
+        }
+    for (int j = 0; j < d->n_spheres; ++j) {
+        const TptSphere& s = d->spheres[j];
+        spheres.push_back(make_float4(s.center.x, s.center.y, s.center.z, s.radius));
+        spheres.push_back(make_float4(s.radius2, s.area, HostBuild::as_f(sphMat[j]), HostBuild::as_f(sphObj[j])));
+    }
+    for (int m = 0; m < d->n_materials; ++m) {
+        const TptMaterial& t = d->materials[m];
+        const int emissive = (t.emission.x > 0.0f || t.emission.y > 0.0f || t.emission.z > 0.0f) ? 1 : 0;   // Material.hpp:29-32
+        mats.push_back(make_float4(t.emission.x, t.emission.y, t.emission.z, HostBuild::as_f(t.type)));
+        mats.push_back(make_float4(t.Kd.x, t.Kd.y, t.Kd.z, t.rough));
+        mats.push_back(make_float4(t.ior_m.x, t.ior_m.y, t.ior_m.z, t.ior_d));
+        mats.push_back(make_float4(t.ior_m_k.x, t.ior_m_k.y, t.ior_m_k.z, HostBuild::as_f(emissive)));
+    }
+    std::vector<int> emissive(d->emissive_objects, d->emissive_objects + d->n_emissive);
+    for (int e : emissive)
+        if (e < 0 || e >= d->n_objects) { tpt_set_error("emissive object index out of range"); return TPT_ERR_INVALID; }
+
+    int rc = require_device(device);
+    if (rc != TPT_OK) return rc;
+
+    TptScene* s = new TptScene;
+    s->device = device;
+    s->n_prims = d->n_tris + d->n_spheres;
+    SceneView& v = s->view;
+    std::memset(&v, 0, sizeof v);
+    rc = upload(s, hb.nodes, &v.nodes);
+    if (rc == TPT_OK) rc = upload(s, tris, &v.tris);
+    if (rc == TPT_OK) rc = upload(s, tverts, &v.tverts);
+    if (rc == TPT_OK) rc = upload(s, spheres, &v.spheres);
+    if (rc == TPT_OK) rc = upload(s, mats, &v.mats);
+    if (rc == TPT_OK) rc = upload(s, hb.objs, &v.objs);
+    if (rc == TPT_OK) rc = upload(s, lnodes, &v.lnodes);
+    if (rc == TPT_OK) rc = upload(s, emissive, &v.emissive);
+    if (rc == TPT_OK && !tpt_cuda_ok(cudaMalloc(&s->d_stats, STAT_COUNT * sizeof(unsigned long long)), "cudaMalloc stats")) rc = TPT_ERR_CUDA;
+    if (rc != TPT_OK) { tpt_scene_destroy(s); return rc; }
+    v.n_nodes = (int)hb.nodes.size() / 2; v.n_tris = d->n_tris; v.n_spheres = d->n_spheres;
+    v.n_mats = d->n_materials; v.n_objs = d->n_objects; v.n_lnodes = d->n_mesh_nodes; v.n_emissive = d->n_emissive;
+    v.width = d->width; v.height = d->height;
+    // CalculateScale(fov) with the reference's promotions (SceneRenderingHelper.cpp:12-14, global.hpp:9)
+    {
+        const float fov = (float)d->fov;
+        const float half = (float)(fov * 0.5);
+        const float rad = (float)((double)(half * 3.141592653589793f) / 180.0);
+        v.scale = (float)std::tan((double)rad);
+    }
+    v.aspect = (float)(d->width / d->height);
+    v.eye = make_float3(d->eye.x, d->eye.y, d->eye.z);
+    v.background = make_float3(d->background.x, d->background.y, d->background.z);
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    s->num_sms = prop.multiProcessorCount;
+    s->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    const unsigned need = scene_stage_bytes(v);
+    v.stage_bytes = need <= 40u * 1024u ? need : 0u;   // larger scenes are read through L1/L2
+    *out = s;
+    return TPT_OK;
+}
+
+extern "C" int tpt_scene_destroy(TptScene* s) {
+    if (!s) return TPT_OK;
+    cudaSetDevice(s->device);
+    wavefront_destroy(s);
+    for (void* p : s->allocs) cudaFree(p);
+    if (s->d_stats) cudaFree(s->d_stats);
+    delete s;
+    return TPT_OK;
+}
+
+extern "C" size_t tpt_accum_floats(const TptScene* s) { return s ? (size_t)s->view.width * s->view.height * 6 : 0; }
+
+// ------------------------------------------------------------------ small helpers
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) { return tpt_cuda_ok(cudaMalloc(&p, std::max<size_t>(bytes, 16)), "cudaMalloc") ? TPT_OK : TPT_ERR_CUDA; }
+    int from_host(const void* h, size_t bytes) {
+        int rc = alloc(bytes);
+        if (rc != TPT_OK) return rc;
+        if (bytes) TPT_CUDA(cudaMemcpy(p, h, bytes, cudaMemcpyHostToDevice));
+        return TPT_OK;
+    }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+TPT_DEV f3 ld3(const float* p, size_t i) { return mk3(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
+TPT_DEV void st3(float* p, size_t i, f3 v) { p[3 * i] = v.x; p[3 * i + 1] = v.y; p[3 * i + 2] = v.z; }
+
+__device__ inline void flush_counters(const Ctx& c, unsigned long long ref_rays, unsigned long long samples,
+                                      unsigned long long* stats) {
+    // one atomic per warp and counter
+    unsigned long long v[6] = {ref_rays, c.scene_rays, c.probe_rays, c.cnt.node_visits, c.cnt.prim_tests, samples};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        unsigned long long x = v[k];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) == 0 && x) atomicAdd(stats + k, x);
+    }
+}
+
+TPT_DEV Ctx make_ctx(const SceneView& sc, bool prune) {
+    Ctx c;
+    c.sc = sc; c.prune = prune;
+    c.cnt.node_visits = 0; c.cnt.prim_tests = 0; c.scene_rays = 0; c.probe_rays = 0;
+    return c;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ exact-tier kernels
+extern __shared__ __align__(16) unsigned char tpt_smem[];
+
+// Persistent grid-stride closest-hit over a ray batch (Scene::Intersect).
+template <bool COUNT>
+__global__ void __launch_bounds__(256) k_intersect(SceneView g, const float* __restrict__ org,
+                                                   const float* __restrict__ dir, const uint8_t* __restrict__ cull,
+                                                   size_t n, int prune, int32_t* prim, double* t, float* coords,
+                                                   float* normal, unsigned long long* stats) {
+    Ctx c = make_ctx(stage_scene(g, tpt_smem), prune != 0);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const DRay r = make_ray(ld3(org, i), ld3(dir, i));
+        DHit h;
+        trace_scene<COUNT>(c, r, cull[i], &h);
+        if (prim) prim[i] = h.prim;
+        if (t) t[i] = h.prim >= 0 ? h.t : 0.0;
+        if (coords) st3(coords, i, h.coords);
+        if (normal) st3(normal, i, h.normal);
+    }
+    if (stats) flush_counters(c, 0, 0, stats);
+}
+
+__global__ void __launch_bounds__(256) k_shadow(SceneView g, const float* __restrict__ from,
+                                                const float* __restrict__ to, const uint8_t* __restrict__ cull,
+                                                size_t n, uint8_t* out) {
+    Ctx c = make_ctx(stage_scene(g, tpt_smem), true);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = trace_shadow<false>(c, ld3(from, i), ld3(to, i), cull[i]) ? 1 : 0;
+}
+
+static int launch_grid(const TptScene* s, size_t n) {
+    const size_t blocks = (n + 255) / 256;
+    const size_t cap = (size_t)s->num_sms * 8;     // 8 resident 256-thread CTAs per SM
+    return (int)std::max<size_t>(1, std::min(blocks, cap));
+}
+
+extern "C" int tpt_intersect_batch_device(TptScene* s, const float* d_org, const float* d_dir, const uint8_t* d_cull,
+                                          size_t n, int32_t flags, int32_t* d_prim, double* d_t, float* d_coords,
+                                          float* d_normal, void* stream) {
+    if (!s) { tpt_set_error("null scene"); return TPT_ERR_INVALID; }
+    if (n == 0) return TPT_OK;
+    TPT_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int prune = (flags & TPT_FLAG_REF_TRAVERSAL) ? 0 : 1;
+    const int grid = launch_grid(s, n);
+    if (flags & TPT_FLAG_COUNT_VISITS)
+        k_intersect<true><<<grid, 256, s->view.stage_bytes, st>>>(s->view, d_org, d_dir, d_cull, n, prune, d_prim, d_t,
+                                                                  d_coords, d_normal, s->d_stats);
+    else
+        k_intersect<false><<<grid, 256, s->view.stage_bytes, st>>>(s->view, d_org, d_dir, d_cull, n, prune, d_prim, d_t,
+                                                                   d_coords, d_normal, s->d_stats);
+    TPT_CUDA(cudaGetLastError());
+    return TPT_OK;
+}
+
+static void read_stats(TptScene* s, TptStats* stats) {
+    unsigned long long h[STAT_COUNT] = {0};
+    cudaMemcpy(h, s->d_stats, sizeof h, cudaMemcpyDeviceToHost);
+    stats->ref_rays = h[STAT_REF_RAYS];
+    stats->traced_rays = h[STAT_SCENE_RAYS] + h[STAT_PROBE_RAYS];
+    stats->node_visits = h[STAT_NODE_VISITS];
+    stats->prim_tests = h[STAT_PRIM_TESTS];
+    stats->samples = h[STAT_SAMPLES];
+}
+
+extern "C" int tpt_intersect_batch(TptScene* s, const float* org, const float* dir, const uint8_t* cull, size_t n,
+                                   int32_t flags, int32_t* prim_id, double* t, float* coords, float* normal,
+                                   TptStats* stats) {
+    if (!s || (n && (!org || !dir || !cull))) { tpt_set_error("null argument"); return TPT_ERR_INVALID; }
+    TPT_CUDA(cudaSetDevice(s->device));
+    if (stats) std::memset(stats, 0, sizeof *stats);
+    if (n == 0) return TPT_OK;
+    DevBuf dorg, ddir, dcull, dprim, dt, dco, dno;
+    int rc;
+    if ((rc = dorg.from_host(org, n * 12)) || (rc = ddir.from_host(dir, n * 12)) || (rc = dcull.from_host(cull, n))) return rc;
+    if (prim_id && (rc = dprim.alloc(n * 4))) return rc;
+    if (t && (rc = dt.alloc(n * 8))) return rc;
+    if (coords && (rc = dco.alloc(n * 12))) return rc;
+    if (normal && (rc = dno.alloc(n * 12))) return rc;
+    TPT_CUDA(cudaMemset(s->d_stats, 0, STAT_COUNT * sizeof(unsigned long long)));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, 0);
+    rc = tpt_intersect_batch_device(s, dorg.as<float>(), ddir.as<float>(), dcull.as<uint8_t>(), n, flags,
+                                    dprim.as<int32_t>(), dt.as<double>(), dco.as<float>(), dno.as<float>(), nullptr);
+    cudaEventRecord(e1, 0);
+    if (rc == TPT_OK && !tpt_cuda_ok(cudaDeviceSynchronize(), "k_intersect")) rc = TPT_ERR_CUDA;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (rc != TPT_OK) return rc;
+    if (prim_id) TPT_CUDA(cudaMemcpy(prim_id, dprim.p, n * 4, cudaMemcpyDeviceToHost));
+    if (t) TPT_CUDA(cudaMemcpy(t, dt.p, n * 8, cudaMemcpyDeviceToHost));
+    if (coords) TPT_CUDA(cudaMemcpy(coords, dco.p, n * 12, cudaMemcpyDeviceToHost));
+    if (normal) TPT_CUDA(cudaMemcpy(normal, dno.p, n * 12, cudaMemcpyDeviceToHost));
+    if (stats) { read_stats(s, stats); stats->device_ms = ms; stats->launches = 1; }
+    return TPT_OK;
+}
+
+extern "C" int tpt_shadow_batch(TptScene* s, const float* from, const float* to, const uint8_t* cull, size_t n,
+                                uint8_t* shadowed) {
+    if (!s || (n && (!from || !to || !cull || !shadowed))) { tpt_set_error("null argument"); return TPT_ERR_INVALID; }
+    TPT_CUDA(cudaSetDevice(s->device));
+    if (n == 0) return TPT_OK;
+    DevBuf a, b, c, o;
+    int rc;
+    if ((rc = a.from_host(from, n * 12)) || (rc = b.from_host(to, n * 12)) || (rc = c.from_host(cull, n)) || (rc = o.alloc(n))) return rc;
+    k_shadow<<<launch_grid(s, n), 256, s->view.stage_bytes>>>(s->view, a.as<float>(), b.as<float>(), c.as<uint8_t>(), n, o.as<uint8_t>());
+    TPT_CUDA(cudaGetLastError());
+    TPT_CUDA(cudaDeviceSynchronize());
+    TPT_CUDA(cudaMemcpy(shadowed, o.p, n, cudaMemcpyDeviceToHost));
+    return TPT_OK;
+}
+
+// ------------------------------------------------------------------ per-function parity kernels
+__global__ void k_rng(uint32_t seed, size_t n, uint32_t* states, float* floats) {
+    if (blockIdx.x || threadIdx.x) return;
+    uint32_t s = seed;
+    for (size_t i = 0; i < n; ++i) {
+        const float f = rng_float(s);
+        if (states) states[i] = s;
+        if (floats) floats[i] = f;
+    }
+}
+extern "C" int tpt_rng_batch(uint32_t seed, size_t n, uint32_t* states, float* floats) {
+    int rc = require_device(0);
+    if (rc != TPT_OK) return rc;
+    DevBuf ds, df;
+    if ((rc = ds.alloc(n * 4)) || (rc = df.alloc(n * 4))) return rc;
+    k_rng<<<1, 32>>>(seed, n, ds.as<uint32_t>(), df.as<float>());
+    TPT_CUDA(cudaGetLastError());
+    TPT_CUDA(cudaDeviceSynchronize());
+    if (states) TPT_CUDA(cudaMemcpy(states, ds.p, n * 4, cudaMemcpyDeviceToHost));
+    if (floats) TPT_CUDA(cudaMemcpy(floats, df.p, n * 4, cudaMemcpyDeviceToHost));
+    return TPT_OK;
+}
+
+enum { MATOP_EVAL = 0, MATOP_PDF = 1, MATOP_FRESNEL = 2, MATOP_SAMPLE = 3 };
+__global__ void __launch_bounds__(256) k_material(SceneView g, int op, int mat, const float* a, const float* b,
+                                                  const float* c3, const uint32_t* seeds, int combine, size_t n,
+                                                  float* out3, float* out1, uint32_t* out_state) {
+    const SceneView sc = stage_scene(g, tpt_smem);
+    const Mat m = load_mat(sc, mat);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        if (op == MATOP_EVAL) st3(out3, i, mat_eval(m, ld3(a, i), ld3(b, i), ld3(c3, i), combine != 0));   // wo, wi, N
+        else if (op == MATOP_PDF) out1[i] = mat_pdf(m, ld3(a, i), ld3(b, i), ld3(c3, i));                   // wo, N, wi
+        else if (op == MATOP_FRESNEL) st3(out3, i, mat_fresnel(m, ld3(a, i), ld3(b, i)));                   // I, N
+        else {
+            uint32_t s = seeds[i];
+            float pdf;
+            st3(out3, i, mat_sample(m, s, ld3(a, i), ld3(b, i), &pdf));                                     // wo, N
+            out1[i] = pdf;
+            if (out_state) out_state[i] = s;
+        }
+    }
+}
+static int material_batch(TptScene* s, int op, int mat, const float* a, const float* b, const float* c,
+                          const uint32_t* seeds, int combine, size_t n, float* out3, float* out1, uint32_t* out_state) {
+    if (!s) { tpt_set_error("null scene"); return TPT_ERR_INVALID; }
+    if (mat < 0 || mat >= s->view.n_mats) { tpt_set_error("material index out of range"); return TPT_ERR_INVALID; }
+    TPT_CUDA(cudaSetDevice(s->device));
+    if (n == 0) return TPT_OK;
+    DevBuf da, db, dc, dsd, d3, d1, dst;
+    int rc;
+    if ((rc = da.from_host(a, n * 12)) || (rc = db.from_host(b, n * 12))) return rc;
+    if (c && (rc = dc.from_host(c, n * 12))) return rc;
+    if (seeds && (rc = dsd.from_host(seeds, n * 4))) return rc;
+    if ((rc = d3.alloc(n * 12)) || (rc = d1.alloc(n * 4)) || (rc = dst.alloc(n * 4))) return rc;
+    k_material<<<launch_grid(s, n), 256, s->view.stage_bytes>>>(s->view, op, mat, da.as<float>(), db.as<float>(), dc.as<float>(),
+                                                              dsd.as<uint32_t>(), combine, n, d3.as<float>(), d1.as<float>(), dst.as<uint32_t>());
+    TPT_CUDA(cudaGetLastError());
+    TPT_CUDA(cudaDeviceSynchronize());
+    if (out3) TPT_CUDA(cudaMemcpy(out3, d3.p, n * 12, cudaMemcpyDeviceToHost));
+    if (out1) TPT_CUDA(cudaMemcpy(out1, d1.p, n * 4, cudaMemcpyDeviceToHost));
+    if (out_state) TPT_CUDA(cudaMemcpy(out_state, dst.p, n * 4, cudaMemcpyDeviceToHost));
+    return TPT_OK;
+}
+extern "C" int tpt_material_eval_batch(TptScene* s, int32_t mat, const float* wo, const float* wi, const float* nrm,
+                                       int32_t combine, size_t n, float* out) {
+    return material_batch(s, MATOP_EVAL, mat, wo, wi, nrm, nullptr, combine, n, out, nullptr, nullptr);
+}
+extern "C" int tpt_material_pdf_batch(TptScene* s, int32_t mat, const float* wo, const float* nrm, const float* wi,
+                                      size_t n, float* out) {
+    return material_batch(s, MATOP_PDF, mat, wo, nrm, wi, nullptr, 0, n, nullptr, out, nullptr);
+}
+extern "C" int tpt_material_fresnel_batch(TptScene* s, int32_t mat, const float* I, const float* nrm, size_t n, float* out) {
+    return material_batch(s, MATOP_FRESNEL, mat, I, nrm, nullptr, nullptr, 0, n, out, nullptr, nullptr);
+}
+extern "C" int tpt_material_sample_batch(TptScene* s, int32_t mat, const float* wo, const float* nrm, const uint32_t* seeds,
+                                         size_t n, float* out_wi, float* out_pdf, uint32_t* out_state) {
+    if (!seeds) { tpt_set_error("null seeds"); return TPT_ERR_INVALID; }
+    return material_batch(s, MATOP_SAMPLE, mat, wo, nrm, nullptr, seeds, 0, n, out_wi, out_pdf, out_state);
+}
+
+// PathWeight over explicit subpaths: one thread per (pair, s, t).
+TPT_DEV PVert to_pvert(const TptPathVertex& v) {
+    PVert p;
+    p.x = mk3(v.x.x, v.x.y, v.x.z); p.N = mk3(v.N.x, v.N.y, v.N.z);
+    p.prim = v.prim; p.type = v.type; p.pdf = v.pdf; p.alpha = mk3(v.alpha.x, v.alpha.y, v.alpha.z);
+    return p;
+}
+__global__ void __launch_bounds__(256) k_pathweight(SceneView g, const TptPathVertex* cam, const int32_t* camCount,
+                                                    const TptPathVertex* light, const int32_t* lightCount, size_t n,
+                                                    float* weights) {
+    Ctx c = make_ctx(stage_scene(g, tpt_smem), true);
+    const size_t total = n * 16 * 17;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t pair = i / (16 * 17);
+        const int st = (int)(i % (16 * 17)), s = st / 17 + 1, t = st % 17;
+        f3 w = mk3(0.0f);
+        if (s <= camCount[pair] && t <= lightCount[pair] && s + t >= 2) {
+            const TptPathVertex* cp = cam + 16 * pair;
+            const TptPathVertex* lp = light + 16 * pair;
+            auto camA = [&](int k) { return to_pvert(cp[k]); };
+            auto lightA = [&](int k) { return to_pvert(lp[k]); };
+            w = path_weight<false>(c, camA, s, lightA, t);
+        }
+        st3(weights, i, w);
+    }
+}
+extern "C" int tpt_bdpt_pathweight_batch(TptScene* s, const TptPathVertex* cam, const int32_t* cam_count,
+                                         const TptPathVertex* light, const int32_t* light_count, size_t n,
+                                         float* weights) {
+    if (!s || (n && (!cam || !cam_count || !light || !light_count || !weights))) { tpt_set_error("null argument"); return TPT_ERR_INVALID; }
+    TPT_CUDA(cudaSetDevice(s->device));
+    if (n == 0) return TPT_OK;
+    DevBuf dc, dcc, dl, dlc, dw;
+    int rc;
+    if ((rc = dc.from_host(cam, n * 16 * sizeof(TptPathVertex))) || (rc = dcc.from_host(cam_count, n * 4)) ||
+        (rc = dl.from_host(light, n * 16 * sizeof(TptPathVertex))) || (rc = dlc.from_host(light_count, n * 4)) ||
+        (rc = dw.alloc(n * 16 * 17 * 12))) return rc;
+    k_pathweight<<<launch_grid(s, n * 16 * 17), 256, s->view.stage_bytes>>>(
+        s->view, dc.as<TptPathVertex>(), dcc.as<int32_t>(), dl.as<TptPathVertex>(), dlc.as<int32_t>(), n, dw.as<float>());
+    TPT_CUDA(cudaGetLastError());
+    TPT_CUDA(cudaDeviceSynchronize());
+    TPT_CUDA(cudaMemcpy(weights, dw.p, n * 16 * 17 * 12, cudaMemcpyDeviceToHost));
+    return TPT_OK;
+}
+
+// ------------------------------------------------------------------ validation renderer
+// One thread per pixel runs FillBufferThread's loop body (Renderer.cpp:40-53) start
+// to finish.  Divergent by construction; it exists to validate the integrators and
+// as the yardstick the wavefront pipeline is measured against.
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_render_mega(SceneView g, RenderArgs a, float* radiance, float* splat,
+                                                     unsigned long long* stats) {
+    Ctx c = make_ctx(stage_scene(g, tpt_smem), a.prune != 0);
+    const SceneView& sc = c.sc;
+    const int npix = sc.width * sc.height;
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    int pixel = slot;
+    if (a.partition == TPT_PART_INTERLEAVE) pixel = slot * a.world + a.rank;
+    unsigned long long ref_rays = 0, samples = 0;
+    if (pixel < npix) {
+        uint32_t rng = tpt_pixel_seed(a.seed_mode, (uint32_t)pixel, (uint32_t)a.rank);
+        const float inv_spp = 1.0f / a.spp_total;
+        const DRay primary = make_ray(mk3(sc.eye.x, sc.eye.y, sc.eye.z), pixel_ray(sc, pixel % sc.width, pixel / sc.width));
+        f3 acc = mk3(0.0f);
+        for (int k = 0; k < a.spp; ++k) {
+            f3 L;
+            if (a.mode == TPT_MODE_BDPT) {
+                PVert cam[MAX_BDPT_PATH_LENGTH], light[MAX_BDPT_PATH_LENGTH];
+                DHit h;
+                trace_scene<COUNT>(c, primary, 0, &h);
+                camera_path_head(sc, h, cam);
+                const int nc = fill_path<COUNT>(c, rng, cam);
+                const LightStart ls = light_path_head(sc, rng, sc.emissive[0], light);
+                trace_scene<COUNT>(c, make_ray(light[0].x, ls.w_i), 0, &h);
+                int nl = 2;
+                if (light_path_first_hit(ls, h, light)) nl = fill_path<COUNT>(c, rng, light);
+                ref_rays += nc + nl;                                   // BDPT.cpp:288
+                auto camA = [&](int i) { return cam[i]; };
+                auto lightA = [&](int i) { return light[i]; };
+                L = mk3(0.0f);
+                for (int s = 1; s <= nc; ++s)
+                    for (int t = 0; t <= nl; ++t) {
+                        if (s + t < 2) continue;
+                        const f3 w = path_weight<COUNT>(c, camA, s, lightA, t);
+                        if (s > 1) L += w;
+                        else splat_to_image(sc, light[t - 1].x, w, splat);
+                    }
+            } else {
+                int bounces;
+                L = path_trace<COUNT>(c, rng, primary, a.mode == TPT_MODE_PT_FULL, &bounces);
+                ref_rays += bounces;                                   // PathTracer.cpp:126
+            }
+            acc += inv_spp * L;                                        // Renderer.cpp:49,51
+            samples++;
+        }
+        st3(radiance, pixel, acc);
+    }
+    flush_counters(c, ref_rays, samples, stats);
+}
+
+// emissionBuffer[i] * 1.0f / spp (Renderer.cpp:58-60)
+__global__ void k_scale(float* buf, size_t n, float spp) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        buf[i] = buf[i] * 1.0f / spp;
+}
+
+// framebuffer[j] += emissionBuffers[i][j] (Renderer.cpp:106-113) and, optionally, the
+// tonemap of SaveFloatImageToJpg (SceneRenderingHelper.cpp:62-64), in one pass.
+__global__ void k_finalize(const float* __restrict__ accum, size_t n3, float* out, uint8_t* rgb8) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = accum[i] + accum[n3 + i];
+        if (out) out[i] = v;
+        if (rgb8) rgb8[i] = (uint8_t)(255 * powf(std_clamp(v, 0.f, 1.f), 0.6f));
+    }
+}
+
+extern "C" int tpt_finalize_device(TptScene* s, const float* d_accum, float* d_out_rgb, uint8_t* d_rgb8, void* stream) {
+    if (!s || !d_accum) { tpt_set_error("null argument"); return TPT_ERR_INVALID; }
+    TPT_CUDA(cudaSetDevice(s->device));
+    const size_t n3 = (size_t)s->view.width * s->view.height * 3;
+    k_finalize<<<launch_grid(s, n3), 256, 0, (cudaStream_t)stream>>>(d_accum, n3, d_out_rgb, d_rgb8);
+    TPT_CUDA(cudaGetLastError());
+    return TPT_OK;
+}
+
+static int check_params(const TptScene* s, const TptRenderParams* p, RenderArgs* a) {
+    if (!s || !p) { tpt_set_error("null argument"); return TPT_ERR_INVALID; }
+    if (p->mode < TPT_MODE_PT_SHIPPED || p->mode > TPT_MODE_BDPT) { tpt_set_error("unknown mode"); return TPT_ERR_INVALID; }
+    if (p->spp <= 0) { tpt_set_error("spp must be positive"); return TPT_ERR_INVALID; }
+    const int world = p->world > 0 ? p->world : 1;
+    if (p->rank < 0 || p->rank >= world) { tpt_set_error("rank outside world"); return TPT_ERR_INVALID; }
+    if (p->mode == TPT_MODE_BDPT && s->view.n_emissive == 0) { tpt_set_error("BDPT needs an emissive object (BDPT.cpp:287)"); return TPT_ERR_INVALID; }
+    a->mode = p->mode; a->spp = p->spp; a->spp_total = p->spp_total > 0 ? p->spp_total : p->spp;
+    a->seed_mode = p->seed_mode; a->partition = p->partition; a->rank = p->rank; a->world = world;
+    a->prune = (p->flags & TPT_FLAG_REF_TRAVERSAL) ? 0 : 1;
+    a->count_visits = (p->flags & TPT_FLAG_COUNT_VISITS) ? 1 : 0;
+    return TPT_OK;
+}
+
+extern "C" int tpt_render_device(TptScene* s, const TptRenderParams* p, float* d_accum, void* stream, TptStats* stats) {
+    RenderArgs a;
+    int rc = check_params(s, p, &a);
+    if (rc != TPT_OK) return rc;
+    if (!d_accum) { tpt_set_error("null accumulation buffer"); return TPT_ERR_INVALID; }
+    TPT_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n3 = (size_t)s->view.width * s->view.height * 3;
+    float* d_radiance = d_accum;
+    float* d_splat = d_accum + n3;
+    unsigned long long launches = 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (stats) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
+    TPT_CUDA(cudaMemsetAsync(d_accum, 0, 2 * n3 * sizeof(float), st));
+    TPT_CUDA(cudaMemsetAsync(s->d_stats, 0, STAT_COUNT * sizeof(unsigned long long), st));
+    if (p->pipeline == TPT_PIPE_MEGAKERNEL) {
+        const int npix = s->view.width * s->view.height;
+        const int slots = a.partition == TPT_PART_INTERLEAVE ? (npix + a.world - 1) / a.world : npix;
+        const int grid = (slots + 127) / 128;
+        if (a.count_visits) k_render_mega<true><<<grid, 128, s->view.stage_bytes, st>>>(s->view, a, d_radiance, d_splat, s->d_stats);
+        else k_render_mega<false><<<grid, 128, s->view.stage_bytes, st>>>(s->view, a, d_radiance, d_splat, s->d_stats);
+        TPT_CUDA(cudaGetLastError());
+        launches += 1;
+    } else {
+        rc = wavefront_render(s, a, d_radiance, d_splat, st, &launches);
+        if (rc != TPT_OK) return rc;
+    }
+    if (a.mode == TPT_MODE_BDPT) {
+        k_scale<<<launch_grid(s, n3), 256, 0, st>>>(d_splat, n3, (float)a.spp_total);
+        TPT_CUDA(cudaGetLastError());
+        launches += 1;
+    }
+    if (stats) {
+        cudaEventRecord(e1, st);
+        TPT_CUDA(cudaEventSynchronize(e1));
+        std::memset(stats, 0, sizeof *stats);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        read_stats(s, stats);
+        stats->device_ms = ms;
+        stats->launches = launches;
+    }
+    return TPT_OK;
+}
+
+extern "C" int tpt_render(TptScene* s, const TptRenderParams* p, float* out_rgb, TptStats* stats) {
+    if (!s || !out_rgb) { tpt_set_error("null argument"); return TPT_ERR_INVALID; }
+    TPT_CUDA(cudaSetDevice(s->device));
+    const size_t n3 = (size_t)s->view.width * s->view.height * 3;
+    DevBuf accum, out;
+    int rc;
+    if ((rc = accum.alloc(2 * n3 * sizeof(float))) || (rc = out.alloc(n3 * sizeof(float)))) return rc;
+    TptStats local;
+    rc = tpt_render_device(s, p, accum.as<float>(), nullptr, &local);
+    if (rc != TPT_OK) return rc;
+    rc = tpt_finalize_device(s, accum.as<float>(), out.as<float>(), nullptr, nullptr);
+    if (rc != TPT_OK) return rc;
+    local.launches += 1;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, 0);
+    TPT_CUDA(cudaMemcpy(out_rgb, out.p, n3 * sizeof(float), cudaMemcpyDeviceToHost));
+    cudaEventRecord(e1, 0);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    local.d2h_ms = ms;
+    if (stats) *stats = local;
+    return TPT_OK;
+}

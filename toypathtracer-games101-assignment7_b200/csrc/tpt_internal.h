@@ -1,0 +1,49 @@
+// tpt_internal.h — host-side state shared by the translation units of libtpt.so.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "scene.cuh"
+#include "tpt.h"
+
+struct WavefrontState;   // wavefront.cu
+
+struct TptScene {
+    int device = 0;
+    SceneView view;                 // pointers address device memory
+    std::vector<void*> allocs;      // everything cudaMalloc'ed for the scene arrays
+    int n_prims = 0;
+    int num_sms = 0;
+    int smem_optin = 0;             // max opt-in dynamic shared memory per block
+    unsigned long long* d_stats = nullptr;   // 8 counters, see STAT_*
+    WavefrontState* wf = nullptr;   // lazily created work buffers of the wavefront pipeline
+};
+
+enum { STAT_REF_RAYS = 0, STAT_SCENE_RAYS, STAT_PROBE_RAYS, STAT_NODE_VISITS, STAT_PRIM_TESTS, STAT_SAMPLES, STAT_COUNT = 8 };
+
+struct RenderArgs {
+    int mode, spp, spp_total;
+    int seed_mode, partition, rank, world;
+    int prune, count_visits;
+};
+
+void tpt_set_error(const std::string& msg);
+bool tpt_cuda_ok(cudaError_t e, const char* what);
+#define TPT_CUDA(call) do { if (!tpt_cuda_ok((call), #call)) return TPT_ERR_CUDA; } while (0)
+
+// Per-pixel stream seed.  REF: pixel + 1 (Renderer.cpp:42).  SPLIT: a hash of
+// (pixel, rank) that is never zero (XorShift32 is stuck at zero).
+__host__ __device__ inline uint32_t tpt_pixel_seed(int seed_mode, uint32_t pixel, uint32_t rank) {
+    if (seed_mode == TPT_SEED_REF) return pixel + 1u;
+    uint32_t h = pixel * 0x9E3779B1u + (rank + 1u) * 0x85EBCA77u;
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+    return h ? h : 0x6D2B79F5u;
+}
+
+// wavefront.cu
+int wavefront_render(TptScene* scene, const RenderArgs& a, float* d_radiance, float* d_splat,
+                     cudaStream_t stream, unsigned long long* launches);
+void wavefront_destroy(TptScene* scene);

@@ -1,0 +1,210 @@
+// traverse.cuh — the exact tier: ray setup, slab test, triangle / sphere tests and
+// the closest-hit walk over the threaded node array of scene.cuh.
+#pragma once
+
+#include "scene.cuh"
+
+// ---- RNG: XorShift32 / GetRandomFloat, reference global.cpp:5-22 ------------------
+TPT_DEV uint32_t rng_next(uint32_t& s) {
+    uint32_t x = s;
+    x ^= x << 13; x ^= x >> 17; x ^= x << 15;
+    s = x;
+    return x;
+}
+// (float)((double)x / 0xffffffff).  x * (1/4294967295.0) rounded to float gives the
+// same float for every one of the 2^32 inputs (oracle/check_rng_scale.c proves it
+// exhaustively), and a DMUL is ~10x cheaper than the IEEE double division.
+TPT_DEV float rng_float(uint32_t& s) {
+    return (float)((double)rng_next(s) * 2.3283064370807974e-10);
+}
+
+struct DRay {
+    f3 o, d, inv;
+};
+TPT_DEV DRay make_ray(f3 o, f3 d) {        // Ray::Ray, Ray.hpp:11-15
+    DRay r; r.o = o; r.d = d; r.inv = x_rcp(d);
+    return r;
+}
+
+struct DHit {
+    double t;     // Intersection::distance
+    int prim;     // -1 = miss
+    f3 coords, normal;
+};
+
+struct TravCounters {
+    unsigned node_visits, prim_tests;
+};
+
+// Bounds3::IntersectP, reference Bounds3.hpp:92-115.  nmin_out is the entry
+// parameter it ends with (>= FLT_MIN), used only for conservative pruning.
+TPT_DEV bool slab_test(const float4 lo, const float4 hi, const DRay& r, float* nmin_out) {
+    float nmin = FLT_MIN, nmax = FLT_MAX;
+    {
+        float t1 = __fmul_rn(__fsub_rn(lo.x, r.o.x), r.inv.x), t2 = __fmul_rn(__fsub_rn(hi.x, r.o.x), r.inv.x);
+        if (t1 > t2) { float s = t1; t1 = t2; t2 = s; }
+        nmin = std_max(nmin, t1); nmax = std_min(nmax, t2);
+    }
+    {
+        float t1 = __fmul_rn(__fsub_rn(lo.y, r.o.y), r.inv.y), t2 = __fmul_rn(__fsub_rn(hi.y, r.o.y), r.inv.y);
+        if (t1 > t2) { float s = t1; t1 = t2; t2 = s; }
+        nmin = std_max(nmin, t1); nmax = std_min(nmax, t2);
+    }
+    {
+        float t1 = __fmul_rn(__fsub_rn(lo.z, r.o.z), r.inv.z), t2 = __fmul_rn(__fsub_rn(hi.z, r.o.z), r.inv.z);
+        if (t1 > t2) { float s = t1; t1 = t2; t2 = s; }
+        nmin = std_max(nmin, t1); nmax = std_min(nmax, t2);
+    }
+    *nmin_out = nmin;
+    return nmax > 0.0f && nmin <= nmax;
+}
+
+// Triangle::GetIntersection, reference Triangle.cpp:77-118.  Returns true and fills
+// *t on a hit; the hit point / normal are produced by the caller for the winner only.
+TPT_DEV bool triangle_test(const SceneView& sc, int prim, const DRay& r, int cull, double* t_out) {
+    const f3 normal = mk3(sc.tris[4 * prim + 3]);
+    if (cull == 0) {            // CullBack
+        if (dotd(r.d, normal) > 0) return false;
+    } else if (cull == 1) {     // CullFront
+        if (dotd(r.d, normal) < 0) return false;
+    }
+    const f3 e2 = mk3(sc.tris[4 * prim + 2]);
+    const f3 e1 = mk3(sc.tris[4 * prim + 1]);
+    const f3 pvec = x_cross(r.d, e2);
+    const double det = dotd(e1, pvec);
+    if (fabs(det) < (double)TPT_EPSILON) return false;
+    const double det_inv = 1. / det;
+    const f3 tvec = x_sub(r.o, mk3(sc.tris[4 * prim]));
+    const double u = dotd(tvec, pvec) * det_inv;
+    if (u < 0 || u > 1) return false;
+    const f3 qvec = x_cross(tvec, e1);
+    const double v = dotd(r.d, qvec) * det_inv;
+    if (v < 0 || u + v > 1) return false;
+    const double t = dotd(e2, qvec) * det_inv;
+    if (t < 0.0) return false;
+    *t_out = t;
+    return true;
+}
+
+// SolveQuadratic (SampleHelperFunctions.cpp:4-18) + Sphere::GetIntersection (Sphere.cpp:4-41).
+TPT_DEV bool sphere_test(const SceneView& sc, int sphere, const DRay& r, int cull, float* t_out) {
+    const float4 s0 = sc.spheres[2 * sphere], s1 = sc.spheres[2 * sphere + 1];
+    const f3 L = x_sub(r.o, mk3(s0));
+    // a, b, c are formed in double and narrowed to float at the SolveQuadratic call
+    const float a = (float)dotd(r.d, r.d);
+    const float b = (float)(2.0 * dotd(r.d, L));
+    const float c = (float)(dotd(L, L) - (double)s1.x);
+    const double discr = (double)b * b - 4.0 * a * c;
+    float x0, x1;
+    if (discr < 0) return false;
+    else if (discr == 0) x0 = x1 = (float)(-0.5 * b / a);
+    else {
+        const float q = (b > 0) ? (float)(-0.5 * (b + sqrt(discr))) : (float)(-0.5 * (b - sqrt(discr)));
+        x0 = __fdiv_rn(q, a);
+        x1 = __fdiv_rn(c, q);
+    }
+    if (x0 > x1) { float s = x0; x0 = x1; x1 = s; }
+    float t_kept;
+    if (cull == 0) t_kept = x0;
+    else if (cull == 1) t_kept = x1;
+    else t_kept = (x0 <= 0) ? x1 : x0;
+    if (!(t_kept > 0.0f)) return false;
+    *t_out = t_kept;
+    return true;
+}
+
+// Closest hit over nodes [first, end) — BVHAccel::Intersect (BVH.cpp:103-143) with
+// the mesh BVHs grafted in (Triangle.hpp:64-73).  With `prune` a subtree whose slab
+// entry lies beyond the best hit so far is skipped; the margin keeps every subtree
+// that could still hold a hit at t <= best (float slab vs double triangle t), so the
+// winner is the reference's.  COUNT fills visit counters (reference semantics when
+// prune is off).
+template <bool COUNT>
+TPT_DEV void closest_hit_range(const SceneView& sc, const DRay& r, int cull, int first, int end,
+                               bool prune, DHit* hit, TravCounters* cnt) {
+    double best_t = 0.0;
+    int best = -1;
+    float prune_t = FLT_MAX;
+    int i = first;
+    while (i < end) {
+        const float4 n0 = sc.nodes[2 * i], n1 = sc.nodes[2 * i + 1];
+        if (COUNT) cnt->node_visits++;
+        float nmin;
+        bool in = slab_test(n0, n1, r, &nmin);
+        if (nmin > prune_t) in = false;   // prune_t stays FLT_MAX unless pruning
+        if (!in) { i = __float_as_int(n1.w); continue; }
+        const int prim = __float_as_int(n0.w);
+        if (prim >= 0) {
+            if (COUNT) cnt->prim_tests++;
+            double t;
+            bool ok;
+            if (prim < sc.n_tris) {
+                ok = triangle_test(sc, prim, r, cull, &t);
+            } else {
+                float ts;
+                ok = sphere_test(sc, prim - sc.n_tris, r, cull, &ts);
+                t = (double)ts;    // Intersection::distance = t_kept, Sphere.cpp:39
+            }
+            if (ok && (best < 0 || best_t > t)) {   // strict: first visited wins ties, BVH.cpp:131
+                best = prim; best_t = t;
+                if (prune) prune_t = (float)t * 1.0001f + 1e-3f;
+            }
+        }
+        i = i + 1;   // leaf: its miss link is i+1 too
+    }
+    hit->prim = best;
+    hit->t = best_t;
+    if (best < 0) {
+        hit->coords = mk3(0.0f); hit->normal = mk3(0.0f);
+    } else if (best < sc.n_tris) {
+        hit->coords = x_madd(r.o, r.d, (float)best_t);            // Triangle.cpp:111
+        hit->normal = mk3(sc.tris[4 * best + 3]);                  // stored normal, never flipped
+    } else {
+        hit->coords = x_madd(r.o, r.d, (float)best_t);            // Sphere.cpp:34 (t_kept is a float)
+        hit->normal = x_normalize(x_sub(hit->coords, mk3(sc.spheres[2 * (best - sc.n_tris)])));
+    }
+}
+
+// Scene::Intersect, Scene.cpp:21-35
+template <bool COUNT>
+TPT_DEV void scene_intersect(const SceneView& sc, const DRay& r, int cull, bool prune, DHit* hit, TravCounters* cnt) {
+    closest_hit_range<COUNT>(sc, r, cull, 0, sc.n_nodes, prune, hit, cnt);
+}
+
+// Object::GetIntersection on one scene object (the PT light probes, PathTracer.cpp:15,93,100)
+// A MeshTriangle runs its own BVH from its root (root slab test included); a Sphere
+// is tested directly, without its bounding box (Sphere.cpp:4).
+template <bool COUNT>
+TPT_DEV void object_intersect(const SceneView& sc, int obj, const DRay& r, int cull, bool prune, DHit* hit,
+                              TravCounters* cnt) {
+    const DevObject o = sc.objs[obj];
+    if (o.kind == 1) {
+        float ts;
+        if (COUNT) cnt->prim_tests++;
+        if (sphere_test(sc, o.first_prim, r, cull, &ts)) {
+            hit->prim = sc.n_tris + o.first_prim;
+            hit->t = (double)ts;
+            hit->coords = x_madd(r.o, r.d, ts);
+            hit->normal = x_normalize(x_sub(hit->coords, mk3(sc.spheres[2 * o.first_prim])));
+        } else {
+            hit->prim = -1; hit->t = 0.0; hit->coords = mk3(0.0f); hit->normal = mk3(0.0f);
+        }
+        return;
+    }
+    closest_hit_range<COUNT>(sc, r, cull, o.root, o.end, prune, hit, cnt);
+}
+
+// Scene::ShadowCheck(Vector3f lightCoords, Vector3f x, cull), Scene.cpp:37-48:
+// the ray leaves `from` toward `to`; shadowed iff the closest hit is more than
+// (squared distance - 1) short of `to`.
+template <bool COUNT>
+TPT_DEV bool shadow_check(const SceneView& sc, f3 from, f3 to, int cull, bool prune, TravCounters* cnt) {
+    const f3 d0 = x_sub(from, to);
+    const double lightDistanceSqr = dotd(d0, d0);
+    const DRay r = make_ray(from, x_normalize(x_sub(to, from)));
+    DHit h;
+    scene_intersect<COUNT>(sc, r, cull, prune, &h, cnt);
+    if (h.prim < 0) return false;
+    const f3 d1 = x_sub(h.coords, from);
+    return dotd(d1, d1) < lightDistanceSqr - 1.0;
+}

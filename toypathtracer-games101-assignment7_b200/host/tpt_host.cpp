@@ -1,0 +1,352 @@
+// tpt_host.cpp — host side of the B200 backend: OBJ reading, the median-split BVH
+// build (tree shape = tie order, so it follows reference BVH.cpp:30-99 exactly),
+// Renderer::Render as flatten -> tpt_render (GPU) -> report -> image file, the
+// README scene scripts, and a small C surface for the Python tests and bench.
+#include "tpt_api.hpp"
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+
+#include "flatten.hpp"
+#include "tpt.h"
+#include "tpt_host.h"
+
+const float EPSILON = 1e-4;
+
+// ---------------------------------------------------------------- BVH build
+BVHAccel::BVHAccel(std::vector<Object*> p, int maxPrims, SplitMethod method)
+    : maxPrimsInNode(std::min(255, maxPrims)), splitMethod(method), primitives(std::move(p)) {
+    if (!primitives.empty()) recursiveBuild(primitives);
+}
+
+namespace {
+template <int AXIS> bool CentroidLess(Object* a, Object* b) {
+    return a->GetBounds().Centroid()[AXIS] < b->GetBounds().Centroid()[AXIS];
+}
+}  // namespace
+
+BVHNodeIndex BVHAccel::recursiveBuild(std::vector<Object*> objs) {
+    const BVHNodeIndex self = (BVHNodeIndex)nodes.size();
+    nodes.emplace_back();
+    if (objs.size() == 1) {
+        BVHBuildNode& n = nodes[self];
+        n.bounds = objs[0]->GetBounds();
+        n.object = objs[0];
+        n.area = objs[0]->getArea();
+        return self;
+    }
+    std::vector<Object*> lo, hi;
+    if (objs.size() == 2) {
+        lo.push_back(objs[0]);
+        hi.push_back(objs[1]);
+    } else {
+        Bounds3 centroids;
+        for (Object* o : objs) centroids = Union(centroids, o->GetBounds().Centroid());
+        // std::sort, not stable_sort: ties must fall where the reference's fall
+        switch (centroids.maxExtent()) {
+            case 0: std::sort(objs.begin(), objs.end(), CentroidLess<0>); break;
+            case 1: std::sort(objs.begin(), objs.end(), CentroidLess<1>); break;
+            default: std::sort(objs.begin(), objs.end(), CentroidLess<2>); break;
+        }
+        auto mid = objs.begin() + (objs.size() / 2);
+        lo.assign(objs.begin(), mid);
+        hi.assign(mid, objs.end());
+    }
+    const BVHNodeIndex l = recursiveBuild(lo);   // left subtree gets the lower indices
+    const BVHNodeIndex r = recursiveBuild(hi);
+    BVHBuildNode& n = nodes[self];
+    n.left = l;
+    n.right = r;
+    n.bounds = Union(nodes[l].bounds, nodes[r].bounds);
+    n.area = nodes[l].area + nodes[r].area;
+    return self;
+}
+
+// ---------------------------------------------------------------- meshes
+namespace {
+
+// "12", "12/3", "12//4", "-1" -> 0-based position index
+bool ParseFaceIndex(const std::string& tok, size_t nPositions, size_t* out) {
+    char* end = nullptr;
+    long v = std::strtol(tok.c_str(), &end, 10);
+    if (end == tok.c_str() || v == 0) return false;
+    long idx = v > 0 ? v - 1 : (long)nPositions + v;
+    if (idx < 0 || (size_t)idx >= nPositions) return false;
+    *out = (size_t)idx;
+    return true;
+}
+
+bool ReadObjFaces(const std::string& path, std::vector<Vector3f>* faceVertices) {
+    std::ifstream in(path);
+    if (!in.is_open()) return false;
+    std::vector<Vector3f> positions;
+    std::string line;
+    while (std::getline(in, line)) {
+        std::istringstream ls(line);
+        std::string tag;
+        if (!(ls >> tag)) continue;
+        if (tag == "v") {
+            std::string a, b, c;
+            if (!(ls >> a >> b >> c)) return false;
+            positions.emplace_back(std::strtof(a.c_str(), nullptr), std::strtof(b.c_str(), nullptr),
+                                   std::strtof(c.c_str(), nullptr));
+        } else if (tag == "f") {
+            std::vector<size_t> idx;
+            std::string tok;
+            while (ls >> tok) {
+                size_t i;
+                if (!ParseFaceIndex(tok, positions.size(), &i)) return false;
+                idx.push_back(i);
+            }
+            for (size_t k = 1; k + 1 < idx.size(); ++k) {   // triangles as-is; polygons as a fan
+                faceVertices->push_back(positions[idx[0]]);
+                faceVertices->push_back(positions[idx[k]]);
+                faceVertices->push_back(positions[idx[k + 1]]);
+            }
+        }
+    }
+    return true;
+}
+
+}  // namespace
+
+MeshTriangle::MeshTriangle(const std::string& filename, Material* m_) : Object(m_) {
+    std::vector<Vector3f> fv;
+    if (!ReadObjFaces(filename, &fv) || fv.empty()) {
+        std::fprintf(stderr, "MeshTriangle: cannot read triangles from '%s'\n", filename.c_str());
+        return;   // an empty mesh; Scene::BuildBVH / the flattener report it
+    }
+    Build(fv);
+}
+
+MeshTriangle::MeshTriangle(const float* xyz, size_t numTriangles, Material* m_) : Object(m_) {
+    std::vector<Vector3f> fv;
+    for (size_t i = 0; i < numTriangles * 3; ++i) fv.emplace_back(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    if (!fv.empty()) Build(fv);
+}
+
+void MeshTriangle::Build(const std::vector<Vector3f>& fv) {
+    const float big = std::numeric_limits<float>::max();
+    Vector3f lo(big, big, big), hi(-big, -big, -big);
+    triangles.reserve(fv.size() / 3);
+    for (size_t i = 0; i + 2 < fv.size(); i += 3) {
+        for (int j = 0; j < 3; ++j) {
+            const Vector3f& v = fv[i + j];
+            lo = Vector3f(std::min(lo.x, v.x), std::min(lo.y, v.y), std::min(lo.z, v.z));
+            hi = Vector3f(std::max(hi.x, v.x), std::max(hi.y, v.y), std::max(hi.z, v.z));
+        }
+        triangles.emplace_back(fv[i], fv[i + 1], fv[i + 2], m);
+    }
+    bounding_box = Bounds3(lo, hi);
+    std::vector<Object*> ptrs;
+    area = 0;
+    for (Triangle& t : triangles) {
+        ptrs.push_back(&t);
+        area += t.area;
+    }
+    bvh = new BVHAccel(ptrs);
+}
+
+// ---------------------------------------------------------------- Scene
+void Scene::BuildBVH() {
+    bvh = new BVHAccel(objects, 1, BVHAccel::SplitMethod::NAIVE);
+    m_emissionObjects.clear();
+    for (Object* o : objects)
+        if (o->hasEmit()) m_emissionObjects.push_back(o);
+}
+
+// ---------------------------------------------------------------- image output
+namespace {
+bool EndsWith(const std::string& s, const char* suffix) {
+    size_t n = std::strlen(suffix);
+    return s.size() >= n && s.compare(s.size() - n, n, suffix) == 0;
+}
+unsigned char Tonemap(float v) {   // reference SceneRenderingHelper.cpp:62-64
+    return (unsigned char)(255 * std::pow(std::clamp(v, 0.f, 1.f), 0.6f));
+}
+}  // namespace
+
+void SaveFloatImageToJpg(std::vector<Vector3f> framebuffer, int width, int height, std::string path) {
+    if (EndsWith(path, ".pfm") || EndsWith(path, ".f32")) {
+        std::ofstream out(path, std::ios::binary);
+        if (EndsWith(path, ".pfm")) out << "PF\n" << width << " " << height << "\n-1.0\n";
+        for (int i = 0; i < width * height; ++i) out.write((const char*)&framebuffer[i].x, 3 * sizeof(float));
+        return;
+    }
+    if (!EndsWith(path, ".ppm")) path += ".ppm";   // no JPEG encoder in this backend
+    std::ofstream out(path, std::ios::binary);
+    out << "P6\n" << width << " " << height << "\n255\n";
+    for (int i = 0; i < width * height; ++i) {
+        unsigned char c[3] = {Tonemap(framebuffer[i].x), Tonemap(framebuffer[i].y), Tonemap(framebuffer[i].z)};
+        out.write((const char*)c, 3);
+    }
+}
+
+// ---------------------------------------------------------------- Renderer
+void Renderer::Render(std::string outputFileName, const Scene& scene, int spp, int /*thread_count*/, bool bdpt) {
+    if (!quiet) std::cout << (bdpt ? "Tracing mode: Bidirectional Ptah Tracing" : "Tracing mode: Path tracing") << std::endl;
+    tpt::FlatScene flat;
+    std::string err;
+    if (!tpt::FlattenScene<Scene, MeshTriangle, Sphere, Triangle>(scene, &flat, &err)) {
+        std::cerr << "Renderer::Render: " << err << std::endl;
+        return;
+    }
+    TptSceneDesc desc = flat.desc();
+    TptScene* dev = nullptr;
+    if (tpt_scene_create(&desc, device, &dev) != TPT_OK) {
+        std::cerr << "Renderer::Render: " << tpt_last_error() << std::endl;
+        return;
+    }
+    if (!quiet) std::cout << "SPP: " << spp << "\n";
+    TptRenderParams p;
+    std::memset(&p, 0, sizeof p);
+    p.mode = bdpt ? TPT_MODE_BDPT : (pt_full ? TPT_MODE_PT_FULL : TPT_MODE_PT_SHIPPED);
+    p.spp = spp;
+    p.world = 1;
+    TptStats st;
+    std::memset(&st, 0, sizeof st);
+    std::vector<float> rgb((size_t)scene.width * scene.height * 3);
+    auto start = std::chrono::system_clock::now();
+    int rc = tpt_render(dev, &p, rgb.data(), &st);
+    auto stop = std::chrono::system_clock::now();
+    tpt_scene_destroy(dev);
+    if (rc != TPT_OK) {
+        std::cerr << "Renderer::Render: " << tpt_last_error() << std::endl;
+        return;
+    }
+    framebuffer.assign((size_t)scene.width * scene.height, Vector3f());
+    for (size_t i = 0; i < framebuffer.size(); ++i) framebuffer[i] = Vector3f(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
+    seconds = std::chrono::duration<double>(stop - start).count();
+    refRays = st.ref_rays;
+    tracedRays = st.traced_rays;
+    if (!quiet) {
+        // the reference's report (Renderer.cpp:116-124); counters are 64-bit here
+        auto ms = std::chrono::duration_cast<std::chrono::milliseconds>(stop - start).count();
+        std::cout << std::endl << "Render complete: \n";
+        std::cout << "Time taken: " << std::chrono::duration_cast<std::chrono::hours>(stop - start).count() << " hours\n";
+        std::cout << "          : " << std::chrono::duration_cast<std::chrono::minutes>(stop - start).count() << " minutes\n";
+        std::cout << "          : " << std::chrono::duration_cast<std::chrono::seconds>(stop - start).count() << " seconds\n";
+        std::cout << "Rays: " << st.ref_rays << std::endl;
+        std::cout << "Rays Per Second: " << (float)st.ref_rays / 1e3f / (ms > 0 ? ms : 1) << "MRays" << std::endl;
+        std::cout << "Traced rays: " << st.traced_rays << "  device ms: " << st.device_ms << std::endl;
+    }
+    if (!outputFileName.empty()) SaveFloatImageToJpg(framebuffer, scene.width, scene.height, outputFileName);
+}
+
+// ---------------------------------------------------------------- scene scripts
+struct TpthScene {
+    std::unique_ptr<Scene> scene;
+    std::vector<std::unique_ptr<Material>> materials;
+    std::vector<std::unique_ptr<Object>> objects;
+    tpt::FlatScene flat;
+    std::string error;
+};
+
+namespace {
+Material* AddMaterial(TpthScene* h, MaterialType t, Vector3f e = Vector3f(0.0f)) {
+    h->materials.emplace_back(new Material(t, e));
+    return h->materials.back().get();
+}
+Object* AddMesh(TpthScene* h, const std::string& path, Material* m) {
+    h->objects.emplace_back(new MeshTriangle(path, m));
+    h->scene->Add(h->objects.back().get());
+    return h->objects.back().get();
+}
+}  // namespace
+
+extern "C" {
+
+// The five README scenes (reference main.cpp:49-103 with the edits of SURVEY.md F6)
+// and the Cornell + bunny fixture of BASELINE config 4.
+TpthScene* tpth_scene_build(const char* sceneName, const char* modelsDir, int width, int height) {
+    const std::string name(sceneName), dir(modelsDir);
+    auto h = new TpthScene;
+    h->scene.reset(new Scene(width, height));
+    Scene& scene = *h->scene;
+    scene.eyePos = Vector3f(278, 278, -800);
+    scene.backgroundColor = 0.0f;
+
+    Material* red = AddMaterial(h, Dieletric);
+    red->Kd = Vector3f(0.63f, 0.065f, 0.05f);
+    Material* green = AddMaterial(h, Dieletric);
+    green->Kd = Vector3f(0.14f, 0.45f, 0.091f);
+    Material* white = AddMaterial(h, Dieletric);
+    white->Kd = Vector3f(0.725f, 0.71f, 0.68f);
+    white->SetSmoothness(name == "smooth" ? .9f : .1f);
+    Material* light = AddMaterial(h, Dieletric,
+        8.0f * Vector3f(0.747f + 0.058f, 0.747f + 0.258f, 0.747f) +
+        15.6f * Vector3f(0.740f + 0.287f, 0.740f + 0.160f, 0.740f) +
+        18.4f * Vector3f(0.737f + 0.642f, 0.737f + 0.159f, 0.737f));
+    light->Kd = Vector3f(0.65f);
+    Material* silver = AddMaterial(h, Metal);
+    silver->ior_m = Vector3f(0.041000f, 0.53285f, 0.049317f);
+    silver->ior_m_k = Vector3f(4.8025f, 3.4101f, 2.8545f);
+    silver->SetSmoothness(1.f);
+    Material* glass = AddMaterial(h, Transparent);
+    glass->ior_d = 1.5f;
+    glass->SetSmoothness(.9f);
+
+    Material* walls = name == "silver" ? silver : white;
+    const std::string box = dir + "/cornellbox/";
+    if (name == "bunny") {
+        AddMesh(h, box + "floor.obj", walls);
+        AddMesh(h, dir + "/bunny/bunny_x1500.obj", walls);
+        AddMesh(h, box + "left.obj", red);
+        AddMesh(h, box + "right.obj", green);
+        AddMesh(h, box + "light.obj", light);
+    } else if (name == "standard" || name == "smooth" || name == "silver" || name == "refractive" ||
+               name == "occlusion") {
+        AddMesh(h, box + "floor.obj", walls);
+        AddMesh(h, box + "shortbox.obj", walls);
+        AddMesh(h, box + "tallbox.obj", walls);
+        AddMesh(h, box + "left.obj", red);
+        AddMesh(h, box + "right.obj", green);
+        AddMesh(h, box + "light.obj", light);
+        if (name == "refractive") {
+            h->objects.emplace_back(new Sphere(Vector3f(278.0f, 278.0f, 200.0f), 50.0f, glass));
+            scene.Add(h->objects.back().get());
+        }
+        if (name == "occlusion") AddMesh(h, box + "lightocculuder.obj", white);
+    } else {
+        h->error = "unknown scene '" + name + "'";
+        return h;
+    }
+    for (Object* o : scene.objects) {
+        auto* mesh = dynamic_cast<MeshTriangle*>(o);
+        if (mesh && mesh->triangles.empty()) {
+            h->error = "a mesh of scene '" + name + "' could not be read from " + dir;
+            return h;
+        }
+    }
+    scene.BuildBVH();
+    if (!tpt::FlattenScene<Scene, MeshTriangle, Sphere, Triangle>(scene, &h->flat, &h->error)) return h;
+    return h;
+}
+
+const char* tpth_scene_error(const TpthScene* h) { return h->error.empty() ? nullptr : h->error.c_str(); }
+void tpth_scene_desc(const TpthScene* h, TptSceneDesc* out) { *out = h->flat.desc(); }
+void tpth_scene_destroy(TpthScene* h) { delete h; }
+
+// Renderer::Render on a built scene; returns 0 on success.  out_rgb may be NULL.
+int tpth_render(TpthScene* h, const char* outputFile, int spp, int bdpt, int ptFull, int device,
+                float* out_rgb, double* seconds) {
+    Renderer r;
+    r.pt_full = ptFull != 0;
+    r.device = device;
+    r.quiet = true;
+    r.Render(outputFile ? outputFile : "", *h->scene, spp, 1, bdpt != 0);
+    if (r.framebuffer.empty()) return 1;
+    if (out_rgb)
+        for (size_t i = 0; i < r.framebuffer.size(); ++i) {
+            out_rgb[3 * i] = r.framebuffer[i].x; out_rgb[3 * i + 1] = r.framebuffer[i].y; out_rgb[3 * i + 2] = r.framebuffer[i].z;
+        }
+    if (seconds) *seconds = r.seconds;
+    return 0;
+}
+
+}  // extern "C"
