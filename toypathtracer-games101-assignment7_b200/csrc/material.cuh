@@ -3,6 +3,10 @@
 // Material.cpp, GGX.hpp and SampleHelperFunctions.{hpp,cpp}; the float/double
 // promotions of each expression are kept (DotProduct is double and narrowed where
 // the reference assigns it to a float), including the safe-divide pdf semantics.
+// Expressions of the form 1 - x*x cancel catastrophically for the near-specular
+// materials (rough 0.002 / 0.01: 1 - cos^2 is a handful of ulps of cos^2), so an FMA
+// there would change D and G by percents, not ulps; those are written with the
+// never-contracted intrinsics and round exactly like the reference.
 #pragma once
 
 #include "traverse.cuh"
@@ -20,7 +24,7 @@ TPT_DEV f3 refract_dir(f3 I, f3 N, float ior) {           // Refract, .cpp:37-48
     f3 n = N;
     if (cosi < 0) { cosi = -cosi; } else { float s = etai; etai = etat; etat = s; n = -N; }
     const float eta = etai / etat;
-    const float k = 1 - eta * eta * (1 - cosi * cosi);
+    const float k = __fsub_rn(1.0f, __fmul_rn(__fmul_rn(eta, eta), __fsub_rn(1.0f, __fmul_rn(cosi, cosi))));
     if (k < 0) return mk3(0.0f);
     return x_normalize(eta * I + (eta * cosi - sqrtf(k)) * n);
 }
@@ -66,18 +70,18 @@ TPT_DEV f3 cosine_sample(uint32_t& rng, f3 N, float* pdf) {                     
 // ---- GGX.hpp ----------------------------------------------------------------------
 TPT_DEV float ggx_visibility(float vn, float vh, float roughness) {   // Visibility, :8-14
     if (vh * vn <= 0.0f) return 0.0f;
-    const float vh2 = vh * vh;
-    const float tan2 = (1.0f - vh2) / vh2;
-    return 2.0f / (1 + sqrtf(1.0f + roughness * roughness * tan2));
+    const float vh2 = __fmul_rn(vh, vh);
+    const float tan2 = __fsub_rn(1.0f, vh2) / vh2;
+    return 2.0f / (1 + sqrtf(__fadd_rn(1.0f, __fmul_rn(__fmul_rn(roughness, roughness), tan2))));
 }
 TPT_DEV float ggx_term(float ndoth, float roughness) {                 // GGXTerm, :17-30
-    const float a2 = roughness * roughness;
-    const float c2 = ndoth * ndoth;
-    const float c4 = c2 * c2;
-    const float tan2 = (1.0f - c2) / c2;
-    float den = a2 + tan2;
-    den = den * den;
-    return a2 / (TPT_PI * c4 * den);
+    const float a2 = __fmul_rn(roughness, roughness);
+    const float c2 = __fmul_rn(ndoth, ndoth);
+    const float c4 = __fmul_rn(c2, c2);
+    const float tan2 = __fsub_rn(1.0f, c2) / c2;
+    float den = __fadd_rn(a2, tan2);
+    den = __fmul_rn(den, den);
+    return a2 / __fmul_rn(__fmul_rn(TPT_PI, c4), den);
 }
 TPT_DEV float ggx_half_pdf(f3 n, f3 h, float roughness) {              // GGXHalfPDF, :33-35
     const double a = fabs(dotd(n, h));
@@ -109,12 +113,13 @@ TPT_DEV f3 mat_fresnel(const Mat& m, f3 I, f3 N) {                     // fresne
     float cosi = (float)std_clampd(dotd(I, N), -1., 1.);
     float etai = 1, etat = m.ior_d;
     if (cosi > 0) { float s = etai; etai = etat; etat = s; }
-    const float sint = etai / etat * sqrtf(std_max(0.f, 1 - cosi * cosi));
+    const float sint = etai / etat * sqrtf(std_max(0.f, __fsub_rn(1.0f, __fmul_rn(cosi, cosi))));
     if (sint >= 1) return mk3(1.0f);
-    const float cost = sqrtf(std_max(0.f, 1 - sint * sint));
+    const float cost = sqrtf(std_max(0.f, __fsub_rn(1.0f, __fmul_rn(sint, sint))));
     cosi = fabsf(cosi);
-    const float Rs = ((etat * cosi) - (etai * cost)) / ((etat * cosi) + (etai * cost));
-    const float Rp = ((etai * cosi) - (etat * cost)) / ((etai * cosi) + (etat * cost));
+    const float tc = __fmul_rn(etat, cosi), ic = __fmul_rn(etai, cost), ii = __fmul_rn(etai, cosi), tt = __fmul_rn(etat, cost);
+    const float Rs = __fsub_rn(tc, ic) / __fadd_rn(tc, ic);
+    const float Rp = __fsub_rn(ii, tt) / __fadd_rn(ii, tt);
     return mk3((Rs * Rs + Rp * Rp) / 2);
 }
 
