@@ -148,7 +148,14 @@ typedef struct TptRenderParams {
 
 enum {
     TPT_FLAG_REF_TRAVERSAL = 1, /* no t-pruning: visit exactly the nodes BVH.cpp:103-143 visits */
-    TPT_FLAG_COUNT_VISITS  = 2  /* fill node_visits / prim_tests in TptStats (slower)           */
+    TPT_FLAG_COUNT_VISITS  = 2, /* fill node_visits / prim_tests in TptStats (slower)           */
+    TPT_FLAG_KERNEL_TIMES  = 4  /* CUDA-event time of every launch, summed per kernel class     */
+};
+
+/* Kernel classes of the wavefront pipeline (indices into TptStats.kernel_ms). */
+enum {
+    TPT_K_GENERATE = 0, TPT_K_SHADE = 1, TPT_K_EXTEND = 2, TPT_K_EXPAND = 3,
+    TPT_K_CONNECT = 4, TPT_K_SHADOW = 5, TPT_K_MIS = 6, TPT_K_ACCUMULATE = 7, TPT_K_COUNT = 8
 };
 
 typedef struct TptStats {
@@ -160,6 +167,10 @@ typedef struct TptStats {
     uint64_t launches;     /* kernels launched by this call                                */
     double   device_ms;    /* CUDA-event time of the kernels, first launch to last         */
     double   h2d_ms, d2h_ms;
+    uint64_t extend_rays;  /* rays traced by the extend kernels (subset of traced_rays)     */
+    uint64_t shadow_rays;  /* rays traced by the shadow kernels                            */
+    double   kernel_ms[8];       /* with TPT_FLAG_KERNEL_TIMES: summed launch durations    */
+    uint64_t kernel_launches[8]; /* launches per kernel class                              */
 } TptStats;
 
 /* ---- lifetime ---------------------------------------------------------- */

@@ -1,0 +1,30 @@
+#!/usr/bin/env python3
+"""Summarise an .ncu-rep (captured with --set full) as one CSV row per profiled launch:
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/rNN_summary.csv"""
+import csv
+import subprocess
+import sys
+
+KEYS = ["Kernel Name", "gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__inst_executed.sum",
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__pcsamp_warps_issue_stalled_long_scoreboard", "smsp__pcsamp_warps_issue_stalled_no_instructions",
+        "smsp__pcsamp_warps_issue_stalled_wait", "smsp__pcsamp_warps_issue_stalled_short_scoreboard",
+        "smsp__pcsamp_warps_issue_stalled_branch_resolving", "smsp__pcsamp_warps_issue_stalled_math_pipe_throttle"]
+
+raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr, units, data = rows[0], rows[1], rows[2:]
+keys = [k for k in KEYS if k in hdr]
+out = open(sys.argv[2], "w") if len(sys.argv) > 2 else sys.stdout
+w = csv.writer(out)
+w.writerow(keys)
+w.writerow([units[hdr.index(k)] for k in keys])
+for r in data:
+    w.writerow([r[hdr.index(k)].split("(")[0].replace("<unnamed>::", "") if k == "Kernel Name" else r[hdr.index(k)] for k in keys])

@@ -27,7 +27,8 @@ CULL_BACK, CULL_FRONT, NO_CULL = 0, 1, 2
 SEED_REF, SEED_SPLIT = 0, 1
 PART_ALL, PART_INTERLEAVE = 0, 1
 PIPE_WAVEFRONT, PIPE_MEGAKERNEL = 0, 1
-FLAG_REF_TRAVERSAL, FLAG_COUNT_VISITS = 1, 2
+FLAG_REF_TRAVERSAL, FLAG_COUNT_VISITS, FLAG_KERNEL_TIMES = 1, 2, 4
+KERNEL_NAMES = ("generate", "shade", "extend", "expand", "connect", "shadow", "mis", "accumulate")
 SCENES = ("standard", "smooth", "silver", "refractive", "occlusion", "bunny")
 
 
@@ -60,10 +61,15 @@ class RenderParams(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("ref_rays", C.c_uint64), ("traced_rays", C.c_uint64),
                 ("node_visits", C.c_uint64), ("prim_tests", C.c_uint64), ("launches", C.c_uint64),
-                ("device_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double)]
+                ("device_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
+                ("extend_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
+                ("kernel_ms", C.c_double * 8), ("kernel_launches", C.c_uint64 * 8)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["kernel_ms"] = dict(zip(KERNEL_NAMES, list(self.kernel_ms)))
+        d["kernel_launches"] = dict(zip(KERNEL_NAMES, list(self.kernel_launches)))
+        return d
 
 
 PATHVERTEX_DTYPE = np.dtype([("x", np.float32, 3), ("N", np.float32, 3), ("prim", np.int32),

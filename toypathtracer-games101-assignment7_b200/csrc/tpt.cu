@@ -356,6 +356,8 @@ static void read_stats(TptScene* s, TptStats* stats) {
     stats->node_visits = h[STAT_NODE_VISITS];
     stats->prim_tests = h[STAT_PRIM_TESTS];
     stats->samples = h[STAT_SAMPLES];
+    stats->shadow_rays = h[STAT_SHADOW_RAYS];
+    stats->extend_rays = h[STAT_SCENE_RAYS] - h[STAT_SHADOW_RAYS];
 }
 
 extern "C" int tpt_intersect_batch(TptScene* s, const float* org, const float* dir, const uint8_t* cull, size_t n,
@@ -623,6 +625,7 @@ static int check_params(const TptScene* s, const TptRenderParams* p, RenderArgs*
     a->seed_mode = p->seed_mode; a->partition = p->partition; a->rank = p->rank; a->world = world;
     a->prune = (p->flags & TPT_FLAG_REF_TRAVERSAL) ? 0 : 1;
     a->count_visits = (p->flags & TPT_FLAG_COUNT_VISITS) ? 1 : 0;
+    a->kernel_times = (p->flags & TPT_FLAG_KERNEL_TIMES) ? 1 : 0;
     return TPT_OK;
 }
 
@@ -637,21 +640,26 @@ extern "C" int tpt_render_device(TptScene* s, const TptRenderParams* p, float* d
     float* d_radiance = d_accum;
     float* d_splat = d_accum + n3;
     unsigned long long launches = 0;
+    KernelTimer timer;
+    timer.on = a.kernel_times != 0 && stats != nullptr;
+    timer.stream = st;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (stats) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
     TPT_CUDA(cudaMemsetAsync(d_accum, 0, 2 * n3 * sizeof(float), st));
     TPT_CUDA(cudaMemsetAsync(s->d_stats, 0, STAT_COUNT * sizeof(unsigned long long), st));
-    if (p->pipeline == TPT_PIPE_MEGAKERNEL) {
+    // PathTrace has no queue pipeline yet: both pipeline values run the per-pixel kernel for the PT modes
+    if (p->pipeline == TPT_PIPE_MEGAKERNEL || a.mode != TPT_MODE_BDPT) {
         const int npix = s->view.width * s->view.height;
-        const int slots = a.partition == TPT_PART_INTERLEAVE ? (npix + a.world - 1) / a.world : npix;
+        const int slots = a.partition == TPT_PART_INTERLEAVE ? (npix - a.rank + a.world - 1) / a.world : npix;
         const int grid = (slots + 127) / 128;
         if (a.count_visits) k_render_mega<true><<<grid, 128, s->view.stage_bytes, st>>>(s->view, a, d_radiance, d_splat, s->d_stats);
         else k_render_mega<false><<<grid, 128, s->view.stage_bytes, st>>>(s->view, a, d_radiance, d_splat, s->d_stats);
         TPT_CUDA(cudaGetLastError());
         launches += 1;
     } else {
-        rc = wavefront_render(s, a, d_radiance, d_splat, st, &launches);
+        rc = wavefront_render(s, a, d_radiance, d_splat, st, &timer);
         if (rc != TPT_OK) return rc;
+        for (int k = 0; k < 8; ++k) launches += timer.launches[k];
     }
     if (a.mode == TPT_MODE_BDPT) {
         k_scale<<<launch_grid(s, n3), 256, 0, st>>>(d_splat, n3, (float)a.spp_total);
@@ -668,6 +676,8 @@ extern "C" int tpt_render_device(TptScene* s, const TptRenderParams* p, float* d
         read_stats(s, stats);
         stats->device_ms = ms;
         stats->launches = launches;
+        timer.collect();
+        for (int k = 0; k < 8; ++k) { stats->kernel_ms[k] = timer.ms[k]; stats->kernel_launches[k] = timer.launches[k]; }
     }
     return TPT_OK;
 }

@@ -22,12 +22,45 @@ struct TptScene {
     WavefrontState* wf = nullptr;   // lazily created work buffers of the wavefront pipeline
 };
 
-enum { STAT_REF_RAYS = 0, STAT_SCENE_RAYS, STAT_PROBE_RAYS, STAT_NODE_VISITS, STAT_PRIM_TESTS, STAT_SAMPLES, STAT_COUNT = 8 };
+enum { STAT_REF_RAYS = 0, STAT_SCENE_RAYS, STAT_PROBE_RAYS, STAT_NODE_VISITS, STAT_PRIM_TESTS, STAT_SAMPLES, STAT_SHADOW_RAYS, STAT_COUNT = 8 };
 
 struct RenderArgs {
     int mode, spp, spp_total;
     int seed_mode, partition, rank, world;
-    int prune, count_visits;
+    int prune, count_visits, kernel_times;
+};
+
+// CUDA-event stopwatch around individual launches (TPT_FLAG_KERNEL_TIMES).
+struct KernelTimer {
+    bool on = false;
+    cudaStream_t stream = nullptr;
+    std::vector<cudaEvent_t> pool;
+    std::vector<int> kinds;
+    size_t used = 0;
+    double ms[8] = {0};
+    unsigned long long launches[8] = {0};
+    void begin(int kind) {
+        launches[kind]++;
+        if (!on) return;
+        if (used + 2 > pool.size()) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); pool.push_back(a); pool.push_back(b); }
+        kinds.push_back(kind);
+        cudaEventRecord(pool[used], stream);
+    }
+    void end() {
+        if (!on) return;
+        cudaEventRecord(pool[used + 1], stream);
+        used += 2;
+    }
+    void collect() {   // after the stream has been synchronised
+        for (size_t i = 0; i < kinds.size(); ++i) {
+            float t = 0;
+            cudaEventElapsedTime(&t, pool[2 * i], pool[2 * i + 1]);
+            ms[kinds[i]] += t;
+        }
+        kinds.clear();
+        used = 0;
+    }
+    ~KernelTimer() { for (cudaEvent_t e : pool) cudaEventDestroy(e); }
 };
 
 void tpt_set_error(const std::string& msg);
@@ -45,5 +78,5 @@ __host__ __device__ inline uint32_t tpt_pixel_seed(int seed_mode, uint32_t pixel
 
 // wavefront.cu
 int wavefront_render(TptScene* scene, const RenderArgs& a, float* d_radiance, float* d_splat,
-                     cudaStream_t stream, unsigned long long* launches);
+                     cudaStream_t stream, KernelTimer* timer);
 void wavefront_destroy(TptScene* scene);

@@ -1,8 +1,562 @@
-// wavefront.cu — placeholder until the queue pipeline lands (next commit).
+// wavefront.cu — the BDPT render path as wavefront queues (DESIGN.md "Wavefront").
+//
+// One SLOT per pixel keeps that pixel's XorShift32 stream, so the spp of a pixel
+// run one after another exactly as FillBufferThread draws them (Renderer.cpp:42-53)
+// while all pixels advance in parallel.  Every iteration of the host loop runs
+//
+//   k_shade    per active slot: finish the vertex its last ray produced (area pdf,
+//              Russian roulette, throughput), move through the sample's state
+//              machine (camera subpath -> light subpath -> sample complete -> next
+//              sample) and BSDF-sample the next direction; emits one ray per slot
+//   k_extend   closest hit for those rays (persistent threads, scene in shared memory)
+//   k_expand   completed samples -> one work item per strategy (s,t)
+//   k_connect  unweighted contribution of each strategy; queues a shadow ray or
+//              passes the item straight to the MIS queue
+//   k_shadow   visibility rays; survivors go to the MIS queue
+//   k_mis      power-heuristic weight of the surviving strategies
+//   k_accumulate  per completed sample: ordered sum of its strategies into the pixel,
+//              3x3 tent splats of the s = 1 strategies
+//
+// Queues are compacted with warp ballots + one atomic per warp (wf_append); a slot
+// that finished its spp simply stops re-entering the active queue, so late
+// iterations cost only what is still alive.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+#include "integrators.cuh"
 #include "tpt_internal.h"
 
-int wavefront_render(TptScene*, const RenderArgs&, float*, float*, cudaStream_t, unsigned long long*) {
-    tpt_set_error("wavefront pipeline not built yet");
-    return TPT_ERR_INVALID;
+extern __shared__ __align__(16) unsigned char tpt_smem[];
+
+namespace {
+
+// ---- per-iteration device counters ------------------------------------------------
+struct WfCounters {
+    unsigned n_active[2];      // active queue lengths (double buffered)
+    unsigned long long done_pairs;   // (done count << 40) | pair count, allocated together
+    unsigned n_shadow, n_mis;
+    unsigned n_retired;        // slots that rendered all their spp
+    unsigned pad;
+};
+
+// ---- slot state ----------------------------------------------------------------------
+// info bits: [0] path (0 camera, 1 light)  [1..4] i = index of the last stored vertex
+//            [5..9] count  [10] pending ray  [11] light-first ray  [12] rr pass
+//            [13] waiting for pair space  [14] light-0 buffer parity  [16..20] nc of this sample
+#define INFO_PATH(i) ((i) & 1u)
+#define INFO_I(i) (((i) >> 1) & 15u)
+#define INFO_COUNT(i) (((i) >> 5) & 31u)
+#define INFO_PENDING (1u << 10)
+#define INFO_LIGHT_FIRST (1u << 11)
+#define INFO_RR_PASS (1u << 12)
+#define INFO_WAIT (1u << 13)
+#define INFO_PARITY (1u << 14)
+#define INFO_NC(i) (((i) >> 16) & 31u)
+TPT_DEV unsigned make_info(unsigned path, unsigned i, unsigned count, unsigned flags, unsigned nc) {
+    return path | (i << 1) | (count << 5) | flags | (nc << 16);
 }
-void wavefront_destroy(TptScene*) {}
+
+struct WfBuffers {
+    int S;                     // slots
+    // path store: vertex k of slot s at [k * S + s]
+    float4 *camA, *camB, *camC;        // A = {x, pdf}  B = {N, asfloat(pack(prim,type))}  C = {alpha, 0}
+    float4 *lightA, *lightB, *lightC;  // index 0 unused here: light vertex 0 lives in l0* (two parities)
+    float4 *l0A, *l0B, *l0C;           // [parity * S + s]
+    uint32_t* rng;
+    unsigned* info;
+    unsigned* spp_done;
+    float4 *ray_o, *ray_d, *pend;      // {o, asfloat(cull)} {d, srpdf} {alpha factor, 0}
+    float4* hit;                       // {coords, asfloat(prim)}
+    int* active[2];
+    // completed samples of this iteration
+    int* done_slot;
+    unsigned* done_info;               // nc | nl << 8 | parity << 16
+    unsigned* done_off;
+    // strategies
+    unsigned long long pair_cap;
+    uint2* pair_rec;                   // {done index, s | t << 8}
+    float4* pair_val;
+    unsigned *shadow_q, *mis_q;
+    WfCounters* ctr;
+};
+
+TPT_DEV int pack_pt(int prim, int type) { return ((prim + 1) << 2) | type; }
+TPT_DEV int unpack_prim(int p) { return (p >> 2) - 1; }
+TPT_DEV int unpack_type(int p) { return p & 3; }
+
+TPT_DEV void store_vertex(float4* A, float4* B, float4* C, size_t at, const PVert& v) {
+    A[at] = make_float4(v.x.x, v.x.y, v.x.z, v.pdf);
+    B[at] = make_float4(v.N.x, v.N.y, v.N.z, __int_as_float(pack_pt(v.prim, v.type)));
+    C[at] = make_float4(v.alpha.x, v.alpha.y, v.alpha.z, 0.0f);
+}
+TPT_DEV PVert load_vertex(const float4* A, const float4* B, const float4* C, size_t at, bool alpha) {
+    const float4 a = A[at], b = B[at];
+    PVert v;
+    v.x = mk3(a); v.pdf = a.w; v.N = mk3(b);
+    const int p = __float_as_int(b.w);
+    v.prim = unpack_prim(p); v.type = unpack_type(p);
+    v.alpha = alpha ? mk3(C[at]) : mk3(0.0f);
+    return v;
+}
+TPT_DEV PVert camera_vertex(const SceneView& sc) {
+    PVert v;
+    v.type = VT_CAMERA; v.x = mk3(sc.eye.x, sc.eye.y, sc.eye.z); v.N = mk3(0.0f); v.prim = -1;
+    v.pdf = CAMERA_ZERO_PDF; v.alpha = mk3(1.0f);
+    return v;
+}
+
+struct CamPath {
+    const WfBuffers& b; const SceneView& sc; int slot;
+    TPT_DEV PVert operator()(int k) const {
+        if (k == 0) return camera_vertex(sc);
+        return load_vertex(b.camA, b.camB, b.camC, (size_t)k * b.S + slot, true);
+    }
+};
+struct LightPath {
+    const WfBuffers& b; int slot; int parity;
+    TPT_DEV PVert operator()(int k) const {
+        if (k == 0) return load_vertex(b.l0A, b.l0B, b.l0C, (size_t)parity * b.S + slot, true);
+        return load_vertex(b.lightA, b.lightB, b.lightC, (size_t)k * b.S + slot, true);
+    }
+};
+
+// Warp-aggregated queue append: one atomicAdd per warp, order inside the warp kept.
+TPT_DEV unsigned wf_append(unsigned* counter, bool want) {
+    const unsigned mask = __ballot_sync(0xffffffffu, want);
+    if (mask == 0) return 0;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned leader = __ffs(mask) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + __popc(mask & ((1u << lane) - 1u));
+}
+
+TPT_DEV f3 hit_normal(const SceneView& sc, int prim, f3 coords) {
+    if (prim < sc.n_tris) return mk3(sc.tris[4 * prim + 3]);
+    return x_normalize(x_sub(coords, mk3(sc.spheres[2 * (prim - sc.n_tris)])));
+}
+
+__device__ inline void flush_stats(unsigned long long ref_rays, unsigned long long scene_rays,
+                                   unsigned long long samples, unsigned long long* stats,
+                                   unsigned long long shadow_rays = 0) {
+    unsigned long long v[4] = {ref_rays, scene_rays, samples, shadow_rays};
+    const int idx[4] = {STAT_REF_RAYS, STAT_SCENE_RAYS, STAT_SAMPLES, STAT_SHADOW_RAYS};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        unsigned long long x = v[k];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) == 0 && x) atomicAdd(stats + idx[k], x);
+    }
+}
+
+// ---- generate: primary ray + hit, once per pixel (the primary ray is the same for every
+// sample: no jitter, Renderer.cpp:46) -----------------------------------------------------
+__global__ void __launch_bounds__(256) k_generate(SceneView g, RenderArgs a, WfBuffers b, unsigned long long* stats) {
+    const SceneView sc = stage_scene(g, tpt_smem);
+    unsigned long long rays = 0;
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < b.S; slot += gridDim.x * blockDim.x) {
+        const int pixel = a.partition == TPT_PART_INTERLEAVE ? slot * a.world + a.rank : slot;   // < npix by the choice of S
+        const DRay r = make_ray(mk3(sc.eye.x, sc.eye.y, sc.eye.z), pixel_ray(sc, pixel % sc.width, pixel / sc.width));
+        DHit h;
+        scene_intersect<false>(sc, r, 0, a.prune != 0, &h, nullptr);
+        rays++;
+        PVert cam[2];
+        camera_path_head(sc, h, cam);
+        store_vertex(b.camA, b.camB, b.camC, (size_t)1 * b.S + slot, cam[1]);
+        b.rng[slot] = tpt_pixel_seed(a.seed_mode, (uint32_t)pixel, (uint32_t)a.rank);
+        b.spp_done[slot] = 0;
+        b.info[slot] = make_info(0, 1, 2, 0, 0);
+        b.active[0][slot] = slot;
+    }
+    flush_stats(0, rays, 0, stats);
+}
+
+// ---- shade: the per-slot state machine ----------------------------------------------------
+__global__ void __launch_bounds__(256) k_shade(SceneView g, RenderArgs a, WfBuffers b, int cur, unsigned long long* stats) {
+    const SceneView sc = stage_scene(g, tpt_smem);
+    const unsigned n = b.ctr->n_active[cur];
+    const int* list = b.active[cur];
+    int* next_list = b.active[cur ^ 1];
+    unsigned long long ref_rays = 0, samples = 0;
+    const unsigned total = (n + 31u) & ~31u;     // whole warps enter the loop (ballots below)
+    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+        const bool live = q < n;
+        const int slot = live ? list[q] : 0;
+        bool keep = false;        // slot stays in the active queue
+        unsigned info = 0;
+        if (live) {
+            info = b.info[slot];
+            uint32_t rng = b.rng[slot];
+            unsigned path = INFO_PATH(info), i = INFO_I(info), count = INFO_COUNT(info), nc = INFO_NC(info);
+            unsigned parity = (info & INFO_PARITY) ? 1u : 0u;
+            bool path_done = false;
+            bool waiting = (info & INFO_WAIT) != 0;
+            float4* A = path ? b.lightA : b.camA;
+            float4* B = path ? b.lightB : b.camB;
+            float4* C = path ? b.lightC : b.camC;
+
+            if (info & INFO_PENDING) {
+                // ---- the vertex the traced ray produced (SampleNextVertex tail + FillPath body)
+                const float4 hr = b.hit[slot];
+                DHit h;
+                h.prim = __float_as_int(hr.w); h.coords = mk3(hr); h.t = 0.0;
+                h.normal = h.prim >= 0 ? hit_normal(sc, h.prim, h.coords) : mk3(0.0f);
+                PVert nv = vertex_from_hit(h);
+                const float4 rd = b.ray_d[slot], pa = b.pend[slot];
+                const float srpdf = rd.w;
+                const f3 afac = mk3(pa);
+                if (info & INFO_LIGHT_FIRST) {
+                    const PVert v0 = load_vertex(b.l0A, b.l0B, b.l0C, (size_t)parity * b.S + slot, false);
+                    nv.pdf = srpdf_to_area(srpdf, v0.x, v0.N, VT_LIGHT, nv.x, nv.N, nv.type);
+                    nv.alpha = afac;                       // SafeDivide(verts[0].alpha, pdf1), or 0 when pdf1 == 0
+                    store_vertex(A, B, C, (size_t)1 * b.S + slot, nv);
+                    i = 1; count = 2;
+                    if (srpdf == 0.0f && nv.type == VT_BACKGROUND) path_done = true;   // BDPT.cpp:85-88
+                } else {
+                    const PVert L = i == 0 ? camera_vertex(sc) : load_vertex(A, B, C, (size_t)i * b.S + slot, true);
+                    nv.pdf = srpdf_to_area(srpdf, L.x, L.N, L.type, nv.x, nv.N, nv.type);
+                    const float rrProb = i > 4 ? .8f : 1.f;
+                    if (!(info & INFO_RR_PASS) || nv.pdf == 0.0f) {
+                        path_done = true;                  // BDPT.cpp:106-111: vertex i+1 is not part of the path
+                    } else {
+                        nv.pdf = nv.pdf * rrProb;
+                        nv.alpha = (L.alpha * afac) / rrProb;
+                        store_vertex(A, B, C, (size_t)(i + 1) * b.S + slot, nv);
+                        count++; i++;
+                    }
+                }
+            }
+
+            // ---- advance until a ray is emitted, the slot has to wait, or it retires
+            unsigned flags = 0;
+            bool emitted = false;
+            for (int guard = 0; guard < 6 && !emitted; ++guard) {
+                if (!path_done && !waiting) {
+                    // top of the FillPath loop for vertex i (BDPT.cpp:98-104)
+                    const PVert V = load_vertex(A, B, C, (size_t)i * b.S + slot, false);
+                    if (i >= MAX_BDPT_PATH_LENGTH - 1 || V.type == VT_BACKGROUND) { path_done = true; continue; }
+                    f3 prev_x;
+                    if (i == 1) prev_x = path ? mk3(b.l0A[(size_t)parity * b.S + slot]) : mk3(sc.eye.x, sc.eye.y, sc.eye.z);
+                    else prev_x = mk3(A[(size_t)(i - 1) * b.S + slot]);
+                    const f3 w_o = x_normalize(prev_x - V.x);
+                    const NextSample s = sample_next_dir(sc, rng, V.N, V.prim, w_o);
+                    const float rrProb = i > 4 ? .8f : 1.f;
+                    const bool rr_pass = !(rng_float(rng) > rrProb);
+                    b.ray_o[slot] = make_float4(V.x.x, V.x.y, V.x.z, __int_as_float(s.cull));
+                    b.ray_d[slot] = make_float4(s.w_i.x, s.w_i.y, s.w_i.z, s.srpdf);
+                    b.pend[slot] = make_float4(s.alpha.x, s.alpha.y, s.alpha.z, 0.0f);
+                    flags = INFO_PENDING | (rr_pass ? INFO_RR_PASS : 0u);
+                    emitted = true;
+                } else if (path == 0 && !waiting) {
+                    // camera subpath complete -> GenerateLightPath head (BDPT.cpp:61-77)
+                    nc = count;
+                    parity ^= 1u;                          // the finished sample's light vertex 0 stays readable
+                    PVert v0[1];
+                    const LightStart ls = light_path_head(sc, rng, sc.emissive[0], v0);
+                    store_vertex(b.l0A, b.l0B, b.l0C, (size_t)parity * b.S + slot, v0[0]);
+                    const f3 afac = ls.pdf1 != 0.0f ? safe_div(v0[0].alpha, ls.pdf1) : mk3(0.0f);
+                    b.ray_o[slot] = make_float4(v0[0].x.x, v0[0].x.y, v0[0].x.z, __int_as_float(0));
+                    b.ray_d[slot] = make_float4(ls.w_i.x, ls.w_i.y, ls.w_i.z, ls.pdf1);
+                    b.pend[slot] = make_float4(afac.x, afac.y, afac.z, 0.0f);
+                    path = 1; i = 0; count = 1; path_done = false;
+                    A = b.lightA; B = b.lightB; C = b.lightC;
+                    flags = INFO_PENDING | INFO_LIGHT_FIRST;
+                    emitted = true;
+                } else {
+                    // light subpath complete -> the sample is complete: reserve its strategies
+                    const unsigned nl = count;
+                    const unsigned npairs = nc * (nl + 1) - 1;
+                    const unsigned long long old = atomicAdd(&b.ctr->done_pairs, (1ull << 40) | npairs);
+                    const unsigned long long off = old & ((1ull << 40) - 1);
+                    const unsigned di = (unsigned)(old >> 40);
+                    if (off + npairs > b.pair_cap) {
+                        // no room left this iteration: leave a void record (its range is marked
+                        // invalid by k_expand) and complete the sample in a later iteration
+                        b.done_slot[di] = -1;
+                        b.done_info[di] = npairs;
+                        b.done_off[di] = off < b.pair_cap ? (unsigned)off : 0xffffffffu;
+                        waiting = true; path_done = true;
+                        flags = INFO_WAIT;
+                        break;
+                    }
+                    b.done_slot[di] = slot;
+                    b.done_info[di] = nc | (nl << 8) | (parity << 16);
+                    b.done_off[di] = (unsigned)off;
+                    ref_rays += nc + nl;                   // BDPT.cpp:288
+                    samples++;
+                    waiting = false;
+                    const unsigned done = b.spp_done[slot] + 1;
+                    b.spp_done[slot] = done;
+                    if ((int)done >= a.spp) {              // all samples of this pixel drawn
+                        atomicAdd(&b.ctr->n_retired, 1u);
+                        flags = 0; path = 0; i = 1; count = 2; nc = 0;
+                        goto retire;
+                    }
+                    // next sample: camera subpath restarts at the cached primary hit
+                    path = 0; i = 1; count = 2; nc = 0; path_done = false;
+                    A = b.camA; B = b.camB; C = b.camC;
+                }
+            }
+            keep = true;
+        retire:
+            b.rng[slot] = rng;
+            info = make_info(path, i, count, flags | (parity ? INFO_PARITY : 0u), nc);
+            b.info[slot] = info;
+        }
+        const unsigned at = wf_append(&b.ctr->n_active[cur ^ 1], keep);
+        if (keep) next_list[at] = slot;
+    }
+    flush_stats(ref_rays, 0, samples, stats);
+}
+
+// ---- extend: closest hit for the rays of the active slots --------------------------------
+__global__ void __launch_bounds__(256) k_extend(SceneView g, RenderArgs a, WfBuffers b, int cur, unsigned long long* stats) {
+    const SceneView sc = stage_scene(g, tpt_smem);
+    const unsigned n = b.ctr->n_active[cur];
+    const int* list = b.active[cur];
+    unsigned long long rays = 0;
+    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const int slot = list[q];
+        if (!(b.info[slot] & INFO_PENDING)) continue;
+        const float4 o = b.ray_o[slot], d = b.ray_d[slot];
+        DHit h;
+        scene_intersect<false>(sc, make_ray(mk3(o), mk3(d)), __float_as_int(o.w), a.prune != 0, &h, nullptr);
+        rays++;
+        b.hit[slot] = make_float4(h.coords.x, h.coords.y, h.coords.z, __int_as_float(h.prim));
+    }
+    flush_stats(0, rays, 0, stats);
+}
+
+// ---- expand: one work item per strategy of every completed sample ------------------------
+__global__ void __launch_bounds__(256) k_expand(WfBuffers b) {
+    const unsigned n_done = (unsigned)(b.ctr->done_pairs >> 40);
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned di = warp; di < n_done; di += nwarps) {
+        const unsigned inf = b.done_info[di], off = b.done_off[di];
+        if (b.done_slot[di] < 0) {          // void record: invalidate the part of its range below the cap
+            if (off != 0xffffffffu)
+                for (unsigned long long k = off + lane; k < b.pair_cap && k < (unsigned long long)off + inf; k += 32)
+                    b.pair_rec[k] = make_uint2(0xffffffffu, 0u);
+            continue;
+        }
+        const unsigned nc = inf & 255u, nl = (inf >> 8) & 255u;
+        const unsigned np = nc * (nl + 1) - 1;
+        // strategy order of the reference loops (BDPT.cpp:290-313): s outer, t inner, (1,0) skipped
+        for (unsigned k = lane; k < np; k += 32) {
+            const unsigned j = k + 1;
+            const unsigned s = j / (nl + 1) + 1, t = j % (nl + 1);
+            b.pair_rec[off + k] = make_uint2(di, s | (t << 8));
+        }
+    }
+}
+
+// ---- connect: unweighted contribution, shadow-ray / MIS queueing --------------------------
+__global__ void __launch_bounds__(256) k_connect(SceneView g, WfBuffers b) {
+    const SceneView sc = stage_scene(g, tpt_smem);
+    const unsigned long long np_all = b.ctr->done_pairs & ((1ull << 40) - 1);
+    const unsigned n = (unsigned)(np_all < b.pair_cap ? np_all : b.pair_cap);
+    const unsigned total = (n + 31u) & ~31u;
+    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
+        bool to_shadow = false, to_mis = false;
+        if (p < n && b.pair_rec[p].x != 0xffffffffu) {
+            const uint2 rec = b.pair_rec[p];
+            const unsigned inf = b.done_info[rec.x];
+            const int slot = b.done_slot[rec.x];
+            const int s = rec.y & 255u, t = rec.y >> 8;
+            const CamPath cam{b, sc, slot};
+            const LightPath light{b, slot, (int)((inf >> 16) & 1u)};
+            int needs_shadow;
+            const f3 u = connect_unweighted(sc, cam, s, light, t, &needs_shadow);
+            const bool zero = u.x == 0.0f && u.y == 0.0f && u.z == 0.0f;
+            b.pair_val[p] = make_float4(u.x, u.y, u.z, __int_as_float(needs_shadow));
+            to_shadow = !zero && needs_shadow != 0;
+            to_mis = !zero && needs_shadow == 0;
+        }
+        const unsigned as = wf_append(&b.ctr->n_shadow, to_shadow);
+        if (to_shadow) b.shadow_q[as] = p;
+        const unsigned am = wf_append(&b.ctr->n_mis, to_mis);
+        if (to_mis) b.mis_q[am] = p;
+    }
+}
+
+// ---- shadow: Scene::ShadowCheck for the queued connections -------------------------------
+__global__ void __launch_bounds__(256) k_shadow_q(SceneView g, RenderArgs a, WfBuffers b, unsigned long long* stats) {
+    const SceneView sc = stage_scene(g, tpt_smem);
+    const unsigned n = b.ctr->n_shadow;
+    const unsigned total = (n + 31u) & ~31u;
+    unsigned long long rays = 0;
+    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+        bool visible = false;
+        unsigned p = 0;
+        if (q < n) {
+            p = b.shadow_q[q];
+            const uint2 rec = b.pair_rec[p];
+            const unsigned inf = b.done_info[rec.x];
+            const int slot = b.done_slot[rec.x];
+            const int s = rec.y & 255u, t = rec.y >> 8;
+            const f3 from = s == 1 ? mk3(sc.eye.x, sc.eye.y, sc.eye.z) : mk3(b.camA[(size_t)(s - 1) * b.S + slot]);
+            const f3 to = t == 1 ? mk3(b.l0A[(size_t)((inf >> 16) & 1u) * b.S + slot]) : mk3(b.lightA[(size_t)(t - 1) * b.S + slot]);
+            const int kind = __float_as_int(b.pair_val[p].w);
+            visible = !shadow_check<false>(sc, from, to, kind == 2 ? 1 : 0, a.prune != 0, nullptr);
+            rays++;
+            if (!visible) b.pair_val[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+        const unsigned am = wf_append(&b.ctr->n_mis, visible);
+        if (visible) b.mis_q[am] = p;
+    }
+    flush_stats(0, rays, 0, stats, rays);
+}
+
+// ---- mis: power-heuristic weight of the surviving strategies ------------------------------
+__global__ void __launch_bounds__(256) k_mis(SceneView g, WfBuffers b) {
+    const SceneView sc = stage_scene(g, tpt_smem);
+    const unsigned n = b.ctr->n_mis;
+    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const unsigned p = b.mis_q[q];
+        const uint2 rec = b.pair_rec[p];
+        const unsigned inf = b.done_info[rec.x];
+        const int slot = b.done_slot[rec.x];
+        const int s = rec.y & 255u, t = rec.y >> 8;
+        const CamPath cam{b, sc, slot};
+        const LightPath light{b, slot, (int)((inf >> 16) & 1u)};
+        const float4 v = b.pair_val[p];
+        f3 w = mk3(v);
+        // a Background end returns before any weighting (BDPT.cpp:180-185)
+        const int endType = s == 1 ? VT_CAMERA : unpack_type(__float_as_int(b.camB[(size_t)(s - 1) * b.S + slot].w));
+        if (endType != VT_BACKGROUND) w = w / mis_denominator(sc, cam, s, light, t);
+        b.pair_val[p] = make_float4(std_max(w.x, 0.0f), std_max(w.y, 0.0f), std_max(w.z, 0.0f), 0.0f);   // BDPT.cpp:299
+    }
+}
+
+// ---- accumulate: ordered per-sample sum + light-tracing splats ----------------------------
+__global__ void __launch_bounds__(256) k_accumulate(SceneView g, RenderArgs a, WfBuffers b, float* radiance, float* splat) {
+    const SceneView sc = stage_scene(g, tpt_smem);
+    const unsigned n_done = (unsigned)(b.ctr->done_pairs >> 40);
+    const float inv_spp = 1.0f / a.spp_total;
+    for (unsigned di = blockIdx.x * blockDim.x + threadIdx.x; di < n_done; di += gridDim.x * blockDim.x) {
+        const unsigned inf = b.done_info[di], off = b.done_off[di];
+        const int slot = b.done_slot[di];
+        if (slot < 0) continue;             // void record (no pair space this iteration)
+        const unsigned nc = inf & 255u, nl = (inf >> 8) & 255u, parity = (inf >> 16) & 1u;
+        f3 result = mk3(0.0f);
+        unsigned k = 0;
+        for (unsigned s = 1; s <= nc; ++s)
+            for (unsigned t = 0; t <= nl; ++t) {
+                if (s + t < 2) continue;
+                const f3 w = mk3(b.pair_val[off + k]);
+                k++;
+                if (s > 1) result += w;                          // BDPT.cpp:301-303
+                else {                                           // BDPT.cpp:304-311
+                    const f3 lx = t == 1 ? mk3(b.l0A[(size_t)parity * b.S + slot]) : mk3(b.lightA[(size_t)(t - 1) * b.S + slot]);
+                    splat_to_image(sc, lx, w, splat);
+                }
+            }
+        const int pixel = a.partition == TPT_PART_INTERLEAVE ? slot * a.world + a.rank : slot;
+        float* px = radiance + 3 * (size_t)pixel;
+        px[0] += inv_spp * result.x; px[1] += inv_spp * result.y; px[2] += inv_spp * result.z;   // Renderer.cpp:49
+    }
+}
+
+__global__ void k_reset_iteration(WfCounters* c, int next) {
+    c->n_active[next] = 0;
+    c->done_pairs = 0;
+    c->n_shadow = 0;
+    c->n_mis = 0;
+}
+
+}  // namespace
+
+// ---- host side -------------------------------------------------------------------------------
+struct WavefrontState {
+    int S = 0;
+    WfBuffers b;
+    std::vector<void*> allocs;
+    unsigned* h_flag = nullptr;     // pinned: [0] n_active, [1] n_retired
+};
+
+static int wf_alloc(TptScene* s, int S) {
+    if (s->wf && s->wf->S == S) return TPT_OK;
+    wavefront_destroy(s);
+    WavefrontState* w = new WavefrontState;
+    s->wf = w;
+    w->S = S;
+    std::memset(&w->b, 0, sizeof w->b);
+    WfBuffers& b = w->b;
+    b.S = S;
+    auto get = [&](size_t bytes, void** out) -> bool {
+        void* p = nullptr;
+        if (!tpt_cuda_ok(cudaMalloc(&p, std::max<size_t>(bytes, 16)), "cudaMalloc(wavefront)")) return false;
+        w->allocs.push_back(p);
+        *out = p;
+        return true;
+    };
+    const size_t V = (size_t)MAX_BDPT_PATH_LENGTH * S * sizeof(float4);
+    const size_t F4 = (size_t)S * sizeof(float4);
+    b.pair_cap = (unsigned long long)S * 48ull;
+    if (b.pair_cap > 0x7fffffffull) b.pair_cap = 0x7fffffffull;
+    bool ok = get(V, (void**)&b.camA) && get(V, (void**)&b.camB) && get(V, (void**)&b.camC) &&
+              get(V, (void**)&b.lightA) && get(V, (void**)&b.lightB) && get(V, (void**)&b.lightC) &&
+              get(2 * F4, (void**)&b.l0A) && get(2 * F4, (void**)&b.l0B) && get(2 * F4, (void**)&b.l0C) &&
+              get((size_t)S * 4, (void**)&b.rng) && get((size_t)S * 4, (void**)&b.info) &&
+              get((size_t)S * 4, (void**)&b.spp_done) && get(F4, (void**)&b.ray_o) && get(F4, (void**)&b.ray_d) &&
+              get(F4, (void**)&b.pend) && get(F4, (void**)&b.hit) && get((size_t)S * 4, (void**)&b.active[0]) &&
+              get((size_t)S * 4, (void**)&b.active[1]) && get((size_t)S * 4, (void**)&b.done_slot) &&
+              get((size_t)S * 4, (void**)&b.done_info) && get((size_t)S * 4, (void**)&b.done_off) &&
+              get(b.pair_cap * sizeof(uint2), (void**)&b.pair_rec) && get(b.pair_cap * sizeof(float4), (void**)&b.pair_val) &&
+              get(b.pair_cap * 4, (void**)&b.shadow_q) && get(b.pair_cap * 4, (void**)&b.mis_q) &&
+              get(sizeof(WfCounters), (void**)&b.ctr);
+    if (ok && !tpt_cuda_ok(cudaMallocHost((void**)&w->h_flag, 64), "cudaMallocHost")) ok = false;
+    if (!ok) { wavefront_destroy(s); return TPT_ERR_OOM; }
+    return TPT_OK;
+}
+
+void wavefront_destroy(TptScene* s) {
+    if (!s || !s->wf) return;
+    for (void* p : s->wf->allocs) cudaFree(p);
+    if (s->wf->h_flag) cudaFreeHost(s->wf->h_flag);
+    delete s->wf;
+    s->wf = nullptr;
+}
+
+int wavefront_render(TptScene* s, const RenderArgs& a, float* d_radiance, float* d_splat, cudaStream_t st,
+                     KernelTimer* tm) {
+    if (a.mode != TPT_MODE_BDPT) { tpt_set_error("wavefront_render handles BDPT only"); return TPT_ERR_INVALID; }
+    const int npix = s->view.width * s->view.height;
+    const int S = a.partition == TPT_PART_INTERLEAVE ? (npix - a.rank + a.world - 1) / a.world : npix;   // pixels i with i % world == rank
+    int rc = wf_alloc(s, S);
+    if (rc != TPT_OK) return rc;
+    WavefrontState* w = s->wf;
+    WfBuffers& b = w->b;
+    const unsigned smem = s->view.stage_bytes;
+    const int grid = std::max(1, std::min((S + 255) / 256, s->num_sms * 8));
+    const int pgrid = s->num_sms * 8;      // strategy kernels: persistent, sized to the machine
+    WfCounters init;
+    std::memset(&init, 0, sizeof init);
+    init.n_active[0] = (unsigned)S;
+    TPT_CUDA(cudaMemcpyAsync(b.ctr, &init, sizeof init, cudaMemcpyHostToDevice, st));
+    tm->begin(TPT_K_GENERATE); k_generate<<<grid, 256, smem, st>>>(s->view, a, b, s->d_stats); tm->end();
+    int cur = 0;
+    // every sample needs at least 2 iterations; 31 is the longest a sample can take
+    const long long max_iters = (long long)a.spp * 32 + 8;
+    for (long long it = 0; it < max_iters; ++it) {
+        k_reset_iteration<<<1, 1, 0, st>>>(b.ctr, cur ^ 1);
+        tm->begin(TPT_K_SHADE); k_shade<<<grid, 256, smem, st>>>(s->view, a, b, cur, s->d_stats); tm->end();
+        tm->begin(TPT_K_EXTEND); k_extend<<<grid, 256, smem, st>>>(s->view, a, b, cur ^ 1, s->d_stats); tm->end();
+        tm->begin(TPT_K_EXPAND); k_expand<<<pgrid, 256, 0, st>>>(b); tm->end();
+        tm->begin(TPT_K_CONNECT); k_connect<<<pgrid, 256, smem, st>>>(s->view, b); tm->end();
+        tm->begin(TPT_K_SHADOW); k_shadow_q<<<pgrid, 256, smem, st>>>(s->view, a, b, s->d_stats); tm->end();
+        tm->begin(TPT_K_MIS); k_mis<<<pgrid, 256, smem, st>>>(s->view, b); tm->end();
+        tm->begin(TPT_K_ACCUMULATE); k_accumulate<<<grid, 256, smem, st>>>(s->view, a, b, d_radiance, d_splat); tm->end();
+        cur ^= 1;
+        if ((it & 7) == 7 || it + 1 == max_iters) {
+            TPT_CUDA(cudaMemcpyAsync(w->h_flag, &b.ctr->n_active[cur], sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            TPT_CUDA(cudaStreamSynchronize(st));
+            if (w->h_flag[0] == 0) break;
+        }
+    }
+    TPT_CUDA(cudaGetLastError());
+    return TPT_OK;
+}
