@@ -66,6 +66,21 @@ def test_pt_is_deterministic_and_pipelines_agree(tpt):
     s.close()
 
 
+@pytest.mark.parametrize("scene", ["standard", "refractive", "silver", "occlusion"])
+def test_bdpt_pipelines_agree_per_pixel(tpt, scene):
+    """The wavefront pipeline (queues, shared-suffix MIS, atomics) and the per-pixel validation kernel
+    (the reference's loops, brute-force MIS) draw the same streams and must produce the same image up
+    to float summation order — a per-pixel check, far tighter than the statistical tolerance."""
+    s = gpu_scene(scene, 96, 96)
+    a, sa = s.render("bdpt", 6, pipeline=tpt.PIPE_WAVEFRONT)
+    b, sb = s.render("bdpt", 6, pipeline=tpt.PIPE_MEGAKERNEL)
+    assert sa["ref_rays"] == sb["ref_rays"]                      # identical subpaths
+    err = np.abs(a - b) / (np.abs(b) + 1e-3)
+    assert np.percentile(err, 99.9) < 1e-3, np.percentile(err, 99.9)
+    assert np.allclose(a.mean((0, 1)), b.mean((0, 1)), rtol=1e-4)
+    s.close()
+
+
 def test_pixel_interleave_partition_is_exact(tpt):
     """Renderer.cpp:38 striding across `world` calls: the union of the stripes is the 1-GPU image
     (PT bit for bit; BDPT up to the float-add order of the splats)."""

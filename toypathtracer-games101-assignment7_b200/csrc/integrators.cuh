@@ -287,13 +287,12 @@ TPT_DEV bool light_path_first_hit(const LightStart& s, const DHit& h, PVert* ver
     return true;
 }
 
-// PathVertex::EvalPdfOnSolidAngle (BDPT.cpp:332-351) followed by SrpdfToAreaPdf and
-// the Russian-roulette factor — the pdf BDPTPath::Append (BDPT.cpp:141-166) gives the
-// vertex v when it is appended behind L (whose predecessor is at pre_x) as vertex
-// number `count` of the temporary path.
-TPT_DEV float append_pdf(const SceneView& sc, const PVert& L, int Ltype, f3 pre_x, const PVert& v, int count) {
+// PathVertex::EvalPdfOnSolidAngle (BDPT.cpp:332-351) followed by SrpdfToAreaPdf: the
+// area pdf BDPTPath::Append (BDPT.cpp:141-161) gives the vertex v when it is appended
+// behind L (whose predecessor is at pre_x), before the Russian-roulette factor.
+TPT_DEV float append_pdf_base(const SceneView& sc, const PVert& L, int Ltype, f3 pre_x, f3 vx, f3 vN, int vtype) {
     float distSqr;
-    const f3 w = x_normalize_len2(v.x - L.x, &distSqr);
+    const f3 w = x_normalize_len2(vx - L.x, &distSqr);
     const f3 NL = Ltype == VT_CAMERA ? mk3(0.0f, 0.0f, 1.0f) : L.N;
     const float cosine = (float)fabs(dotd(w, NL));
     float srpdf;
@@ -306,8 +305,12 @@ TPT_DEV float append_pdf(const SceneView& sc, const PVert& L, int Ltype, f3 pre_
         srpdf = safe_div(mat_pdf(mat, wo, NL, w), cosine);
     }
     const float cos1 = Ltype == VT_CAMERA ? 1.0f : (float)fabs(dotd(w, L.N));
-    const float cos2 = v.type == VT_CAMERA ? 1.0f : (float)fabs(dotd(-w, v.N));
-    float pdf = srpdf * fabsf(cos1 * cos2 / distSqr);
+    const float cos2 = vtype == VT_CAMERA ? 1.0f : (float)fabs(dotd(-w, vN));
+    return srpdf * fabsf(cos1 * cos2 / distSqr);
+}
+// ... and with it: vertex number `count` of the temporary path (BDPT.cpp:162-165).
+TPT_DEV float append_pdf(const SceneView& sc, const PVert& L, int Ltype, f3 pre_x, const PVert& v, int count) {
+    float pdf = append_pdf_base(sc, L, Ltype, pre_x, v.x, v.N, v.type);
     pdf *= count > 4 ? .8f : 1.f;
     return pdf;
 }
@@ -402,6 +405,68 @@ TPT_DEV float mis_denominator(const SceneView& sc, const CamPath& cam, int s, co
             den += cur * cur;
             if (cur == 0.0f) break;
             P = L; L = v; count++;
+        }
+    }
+    return den;
+}
+
+// The same denominator with the suffixes shared between strategies.  From the third
+// appended vertex on, the pdf Append computes depends only on three consecutive vertices
+// of the DONOR subpath (and on the Russian-roulette threshold): appending light[i] behind
+// light[i+1] whose predecessor is light[i+2] is the same for every (s,t) with t >= i+3.
+// Those "reverse" pdfs are computed once per vertex when the subpath is generated
+// (rev = append_pdf_base); a strategy then evaluates at most four pdfs of its own and
+// walks the stored ratios, multiplying in the reference's order so the floats agree.
+// camAux(i) / lightAux(i) return {original pdf of vertex i, reverse pdf towards vertex i}.
+template <class CamPath, class LightPath, class CamAux, class LightAux>
+TPT_DEV float mis_denominator_shared(const SceneView& sc, const CamPath& cam, int s, const LightPath& light, int t,
+                                     const CamAux& camAux, const LightAux& lightAux) {
+    float den = 1.0f;
+    const PVert z = cam(s - 1);                       // camera subpath end
+    PVert zp = z;                                     // its predecessor (unused for s == 1)
+    if (s >= 2) zp = cam(s - 2);
+    PVert y = z, yp = z;                              // light subpath end and its predecessor
+    if (t >= 1) { y = light(t - 1); yp = y; }
+    if (t >= 2) yp = light(t - 2);
+    if (t >= 1) {   // camera subpath extended by light[t-1], ..., light[0]
+        int count = s;
+        float cur = safe_div(append_pdf(sc, z, z.type, zp.x, y, count), y.pdf);
+        den += cur * cur;
+        count++;
+        if (cur != 0.0f && t >= 2) {
+            cur *= safe_div(append_pdf(sc, y, y.type, z.x, yp, count), yp.pdf);
+            den += cur * cur;
+            count++;
+            for (int i = t - 3; i >= 0 && cur != 0.0f; --i) {
+                const float2 aux = lightAux(i);
+                cur *= safe_div(aux.y * (count > 4 ? .8f : 1.f), aux.x);
+                den += cur * cur;
+                count++;
+            }
+        }
+    }
+    {   // light subpath extended by cam[s-1], ..., cam[0]
+        int count = t;
+        float cur;
+        if (t == 0) {
+            // Append to an empty path (BDPT.cpp:127-139): pdf = the primitive's own 1/area (quirk Q15)
+            cur = safe_div(prim_pdf(sc, z.prim), z.pdf);
+        } else {
+            cur = safe_div(append_pdf(sc, y, y.type, yp.x, z, count), z.pdf);
+        }
+        den += cur * cur;
+        count++;
+        if (cur != 0.0f && s >= 2) {
+            // behind cam[s-1] (re-typed Light when it started the path), predecessor light[t-1]
+            cur *= safe_div(append_pdf(sc, z, t == 0 ? VT_LIGHT : z.type, y.x, zp, count), zp.pdf);
+            den += cur * cur;
+            count++;
+            for (int i = s - 3; i >= 0 && cur != 0.0f; --i) {
+                const float2 aux = camAux(i);
+                cur *= safe_div(aux.y * (count > 4 ? .8f : 1.f), aux.x);
+                den += cur * cur;
+                count++;
+            }
         }
     }
     return den;

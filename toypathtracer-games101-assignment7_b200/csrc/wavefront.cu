@@ -13,9 +13,8 @@
 //   k_connect  unweighted contribution of each strategy; queues a shadow ray or
 //              passes the item straight to the MIS queue
 //   k_shadow   visibility rays; survivors go to the MIS queue
-//   k_mis      power-heuristic weight of the surviving strategies
-//   k_accumulate  per completed sample: ordered sum of its strategies into the pixel,
-//              3x3 tent splats of the s = 1 strategies
+//   k_mis      power-heuristic weight of the surviving strategies, accumulated into the
+//              pixel (s > 1) or splatted with the 3x3 tent (s = 1): the accumulate stage
 //
 // Queues are compacted with warp ballots + one atomic per warp (wf_append); a slot
 // that finished its spp simply stops re-entering the active queue, so late
@@ -121,6 +120,23 @@ struct LightPath {
     }
 };
 
+// {original area pdf of vertex i, reverse pdf towards vertex i (C.w, written by k_shade)}
+struct CamAux {
+    const WfBuffers& b; int slot;
+    TPT_DEV float2 operator()(int i) const {
+        const size_t at = (size_t)i * b.S + slot;
+        return make_float2(i == 0 ? CAMERA_ZERO_PDF : b.camA[at].w, b.camC[at].w);
+    }
+};
+struct LightAux {
+    const WfBuffers& b; int slot; int parity;
+    TPT_DEV float2 operator()(int i) const {
+        if (i == 0) { const size_t at = (size_t)parity * b.S + slot; return make_float2(b.l0A[at].w, b.l0C[at].w); }
+        const size_t at = (size_t)i * b.S + slot;
+        return make_float2(b.lightA[at].w, b.lightC[at].w);
+    }
+};
+
 // Warp-aggregated queue append: one atomicAdd per warp, order inside the warp kept.
 TPT_DEV unsigned wf_append(unsigned* counter, bool want) {
     const unsigned mask = __ballot_sync(0xffffffffu, want);
@@ -174,6 +190,12 @@ __global__ void __launch_bounds__(256) k_generate(SceneView g, RenderArgs a, WfB
 }
 
 // ---- shade: the per-slot state machine ----------------------------------------------------
+// Written in three phases so that the expensive code has ONE call site that all lanes of
+// a warp reach together: (1) finish the vertex the last ray produced, (2) walk the cheap
+// state machine until the slot knows what it does next, (3) BSDF-sample (or start the
+// light subpath) and emit the ray.
+enum { ACT_NONE = 0, ACT_EXTEND = 1, ACT_LIGHT = 2 };
+
 __global__ void __launch_bounds__(256) k_shade(SceneView g, RenderArgs a, WfBuffers b, int cur, unsigned long long* stats) {
     const SceneView sc = stage_scene(g, tpt_smem);
     const unsigned n = b.ctr->n_active[cur];
@@ -185,38 +207,41 @@ __global__ void __launch_bounds__(256) k_shade(SceneView g, RenderArgs a, WfBuff
         const bool live = q < n;
         const int slot = live ? list[q] : 0;
         bool keep = false;        // slot stays in the active queue
-        unsigned info = 0;
+        int action = ACT_NONE;
+        unsigned path = 0, i = 0, count = 0, nc = 0, parity = 0, flags = 0;
+        uint32_t rng = 0;
         if (live) {
-            info = b.info[slot];
-            uint32_t rng = b.rng[slot];
-            unsigned path = INFO_PATH(info), i = INFO_I(info), count = INFO_COUNT(info), nc = INFO_NC(info);
-            unsigned parity = (info & INFO_PARITY) ? 1u : 0u;
-            bool path_done = false;
+            const unsigned info = b.info[slot];
+            rng = b.rng[slot];
+            path = INFO_PATH(info); i = INFO_I(info); count = INFO_COUNT(info); nc = INFO_NC(info);
+            parity = (info & INFO_PARITY) ? 1u : 0u;
             bool waiting = (info & INFO_WAIT) != 0;
-            float4* A = path ? b.lightA : b.camA;
-            float4* B = path ? b.lightB : b.camB;
-            float4* C = path ? b.lightC : b.camC;
+            bool path_done = waiting;     // a waiting slot sits on a finished light subpath
+            int cur_type = -1;            // type of vertex i, when known without a load
 
+            // ---- phase 1: the vertex the traced ray produced (SampleNextVertex tail + FillPath body)
             if (info & INFO_PENDING) {
-                // ---- the vertex the traced ray produced (SampleNextVertex tail + FillPath body)
+                float4* A = path ? b.lightA : b.camA;
+                float4* B = path ? b.lightB : b.camB;
+                float4* C = path ? b.lightC : b.camC;
+                const bool lf = (info & INFO_LIGHT_FIRST) != 0;
                 const float4 hr = b.hit[slot];
                 DHit h;
                 h.prim = __float_as_int(hr.w); h.coords = mk3(hr); h.t = 0.0;
                 h.normal = h.prim >= 0 ? hit_normal(sc, h.prim, h.coords) : mk3(0.0f);
                 PVert nv = vertex_from_hit(h);
-                const float4 rd = b.ray_d[slot], pa = b.pend[slot];
-                const float srpdf = rd.w;
-                const f3 afac = mk3(pa);
-                if (info & INFO_LIGHT_FIRST) {
-                    const PVert v0 = load_vertex(b.l0A, b.l0B, b.l0C, (size_t)parity * b.S + slot, false);
-                    nv.pdf = srpdf_to_area(srpdf, v0.x, v0.N, VT_LIGHT, nv.x, nv.N, nv.type);
+                const float srpdf = b.ray_d[slot].w;
+                const f3 afac = mk3(b.pend[slot]);
+                // the vertex the ray left from: light vertex 0 for the first light ray, else vertex i
+                const PVert L = lf ? load_vertex(b.l0A, b.l0B, b.l0C, (size_t)parity * b.S + slot, false)
+                                   : load_vertex(A, B, C, (size_t)i * b.S + slot, true);
+                nv.pdf = srpdf_to_area(srpdf, L.x, L.N, L.type, nv.x, nv.N, nv.type);
+                if (lf) {
                     nv.alpha = afac;                       // SafeDivide(verts[0].alpha, pdf1), or 0 when pdf1 == 0
                     store_vertex(A, B, C, (size_t)1 * b.S + slot, nv);
                     i = 1; count = 2;
                     if (srpdf == 0.0f && nv.type == VT_BACKGROUND) path_done = true;   // BDPT.cpp:85-88
                 } else {
-                    const PVert L = i == 0 ? camera_vertex(sc) : load_vertex(A, B, C, (size_t)i * b.S + slot, true);
-                    nv.pdf = srpdf_to_area(srpdf, L.x, L.N, L.type, nv.x, nv.N, nv.type);
                     const float rrProb = i > 4 ? .8f : 1.f;
                     if (!(info & INFO_RR_PASS) || nv.pdf == 0.0f) {
                         path_done = true;                  // BDPT.cpp:106-111: vertex i+1 is not part of the path
@@ -224,86 +249,113 @@ __global__ void __launch_bounds__(256) k_shade(SceneView g, RenderArgs a, WfBuff
                         nv.pdf = nv.pdf * rrProb;
                         nv.alpha = (L.alpha * afac) / rrProb;
                         store_vertex(A, B, C, (size_t)(i + 1) * b.S + slot, nv);
+                        // reverse pdf towards vertex i-1: it is appended behind vertex i whose
+                        // predecessor is the new vertex i+1 (mis_denominator_shared reads it)
+                        {
+                            f3 tx, tN = mk3(0.0f);
+                            int tt;
+                            float* dst;
+                            if (i >= 2) {
+                                const size_t at = (size_t)(i - 1) * b.S + slot;
+                                const float4 ta = A[at], tb = B[at];
+                                tx = mk3(ta); tN = mk3(tb); tt = unpack_type(__float_as_int(tb.w));
+                                dst = &C[at].w;
+                            } else if (path) {
+                                const size_t at = (size_t)parity * b.S + slot;
+                                const float4 ta = b.l0A[at], tb = b.l0B[at];
+                                tx = mk3(ta); tN = mk3(tb); tt = VT_LIGHT;
+                                dst = &b.l0C[at].w;
+                            } else {
+                                tx = mk3(sc.eye.x, sc.eye.y, sc.eye.z); tt = VT_CAMERA;
+                                dst = &b.camC[slot].w;
+                            }
+                            *dst = append_pdf_base(sc, L, L.type, nv.x, tx, tN, tt);
+                        }
                         count++; i++;
                     }
                 }
+                cur_type = nv.type;
             }
 
-            // ---- advance until a ray is emitted, the slot has to wait, or it retires
-            unsigned flags = 0;
-            bool emitted = false;
-            for (int guard = 0; guard < 6 && !emitted; ++guard) {
-                if (!path_done && !waiting) {
-                    // top of the FillPath loop for vertex i (BDPT.cpp:98-104)
-                    const PVert V = load_vertex(A, B, C, (size_t)i * b.S + slot, false);
-                    if (i >= MAX_BDPT_PATH_LENGTH - 1 || V.type == VT_BACKGROUND) { path_done = true; continue; }
-                    f3 prev_x;
-                    if (i == 1) prev_x = path ? mk3(b.l0A[(size_t)parity * b.S + slot]) : mk3(sc.eye.x, sc.eye.y, sc.eye.z);
-                    else prev_x = mk3(A[(size_t)(i - 1) * b.S + slot]);
-                    const f3 w_o = x_normalize(prev_x - V.x);
-                    const NextSample s = sample_next_dir(sc, rng, V.N, V.prim, w_o);
-                    const float rrProb = i > 4 ? .8f : 1.f;
-                    const bool rr_pass = !(rng_float(rng) > rrProb);
-                    b.ray_o[slot] = make_float4(V.x.x, V.x.y, V.x.z, __int_as_float(s.cull));
-                    b.ray_d[slot] = make_float4(s.w_i.x, s.w_i.y, s.w_i.z, s.srpdf);
-                    b.pend[slot] = make_float4(s.alpha.x, s.alpha.y, s.alpha.z, 0.0f);
-                    flags = INFO_PENDING | (rr_pass ? INFO_RR_PASS : 0u);
-                    emitted = true;
-                } else if (path == 0 && !waiting) {
-                    // camera subpath complete -> GenerateLightPath head (BDPT.cpp:61-77)
-                    nc = count;
-                    parity ^= 1u;                          // the finished sample's light vertex 0 stays readable
-                    PVert v0[1];
-                    const LightStart ls = light_path_head(sc, rng, sc.emissive[0], v0);
-                    store_vertex(b.l0A, b.l0B, b.l0C, (size_t)parity * b.S + slot, v0[0]);
-                    const f3 afac = ls.pdf1 != 0.0f ? safe_div(v0[0].alpha, ls.pdf1) : mk3(0.0f);
-                    b.ray_o[slot] = make_float4(v0[0].x.x, v0[0].x.y, v0[0].x.z, __int_as_float(0));
-                    b.ray_d[slot] = make_float4(ls.w_i.x, ls.w_i.y, ls.w_i.z, ls.pdf1);
-                    b.pend[slot] = make_float4(afac.x, afac.y, afac.z, 0.0f);
-                    path = 1; i = 0; count = 1; path_done = false;
-                    A = b.lightA; B = b.lightB; C = b.lightC;
-                    flags = INFO_PENDING | INFO_LIGHT_FIRST;
-                    emitted = true;
-                } else {
-                    // light subpath complete -> the sample is complete: reserve its strategies
-                    const unsigned nl = count;
-                    const unsigned npairs = nc * (nl + 1) - 1;
-                    const unsigned long long old = atomicAdd(&b.ctr->done_pairs, (1ull << 40) | npairs);
-                    const unsigned long long off = old & ((1ull << 40) - 1);
-                    const unsigned di = (unsigned)(old >> 40);
-                    if (off + npairs > b.pair_cap) {
-                        // no room left this iteration: leave a void record (its range is marked
-                        // invalid by k_expand) and complete the sample in a later iteration
-                        b.done_slot[di] = -1;
-                        b.done_info[di] = npairs;
-                        b.done_off[di] = off < b.pair_cap ? (unsigned)off : 0xffffffffu;
-                        waiting = true; path_done = true;
-                        flags = INFO_WAIT;
-                        break;
-                    }
-                    b.done_slot[di] = slot;
-                    b.done_info[di] = nc | (nl << 8) | (parity << 16);
-                    b.done_off[di] = (unsigned)off;
-                    ref_rays += nc + nl;                   // BDPT.cpp:288
-                    samples++;
-                    waiting = false;
-                    const unsigned done = b.spp_done[slot] + 1;
-                    b.spp_done[slot] = done;
-                    if ((int)done >= a.spp) {              // all samples of this pixel drawn
-                        atomicAdd(&b.ctr->n_retired, 1u);
-                        flags = 0; path = 0; i = 1; count = 2; nc = 0;
-                        goto retire;
-                    }
-                    // next sample: camera subpath restarts at the cached primary hit
-                    path = 0; i = 1; count = 2; nc = 0; path_done = false;
-                    A = b.camA; B = b.camB; C = b.camC;
-                }
-            }
+            // ---- phase 2: state machine, cheap steps only
             keep = true;
-        retire:
+            for (int guard = 0; guard < 6; ++guard) {
+                if (!path_done) {
+                    // top of the FillPath loop for vertex i (BDPT.cpp:98-99)
+                    if (cur_type < 0) cur_type = unpack_type(__float_as_int((path ? b.lightB : b.camB)[(size_t)i * b.S + slot].w));
+                    if (i >= MAX_BDPT_PATH_LENGTH - 1 || cur_type == VT_BACKGROUND) { path_done = true; continue; }
+                    action = ACT_EXTEND;
+                    break;
+                }
+                if (path == 0) { action = ACT_LIGHT; break; }   // camera subpath complete
+                // light subpath complete -> the sample is complete: reserve its strategies
+                const unsigned nl = count;
+                const unsigned npairs = nc * (nl + 1) - 1;
+                const unsigned long long old = atomicAdd(&b.ctr->done_pairs, (1ull << 40) | npairs);
+                const unsigned long long off = old & ((1ull << 40) - 1);
+                const unsigned di = (unsigned)(old >> 40);
+                if (off + npairs > b.pair_cap) {
+                    // no room left this iteration: leave a void record (its range is marked
+                    // invalid by k_expand) and complete the sample in a later iteration
+                    b.done_slot[di] = -1;
+                    b.done_info[di] = npairs;
+                    b.done_off[di] = off < b.pair_cap ? (unsigned)off : 0xffffffffu;
+                    flags = INFO_WAIT;
+                    break;
+                }
+                b.done_slot[di] = slot;
+                b.done_info[di] = nc | (nl << 8) | (parity << 16);
+                b.done_off[di] = (unsigned)off;
+                ref_rays += nc + nl;                       // BDPT.cpp:288
+                samples++;
+                const unsigned done = b.spp_done[slot] + 1;
+                b.spp_done[slot] = done;
+                path = 0; i = 1; count = 2; nc = 0; path_done = false; cur_type = -1;
+                if ((int)done >= a.spp) {                  // all samples of this pixel drawn: the slot retires
+                    atomicAdd(&b.ctr->n_retired, 1u);
+                    keep = false;
+                    break;
+                }
+                // next sample: the camera subpath restarts at the cached primary hit
+            }
+        }
+
+        // ---- phase 3: the one expensive step of this iteration
+        __syncwarp();   // every lane of the warp runs this loop body the same number of times (`total`)
+        if (action == ACT_EXTEND) {
+            const float4* A = path ? b.lightA : b.camA;
+            const float4* B = path ? b.lightB : b.camB;
+            const float4 va = A[(size_t)i * b.S + slot], vb = B[(size_t)i * b.S + slot];
+            const f3 Vx = mk3(va), VN = mk3(vb);
+            const int Vprim = unpack_prim(__float_as_int(vb.w));
+            f3 prev_x;
+            if (i == 1) prev_x = path ? mk3(b.l0A[(size_t)parity * b.S + slot]) : mk3(sc.eye.x, sc.eye.y, sc.eye.z);
+            else prev_x = mk3(A[(size_t)(i - 1) * b.S + slot]);
+            const f3 w_o = x_normalize(prev_x - Vx);
+            const NextSample s = sample_next_dir(sc, rng, VN, Vprim, w_o);
+            const float rrProb = i > 4 ? .8f : 1.f;
+            const bool rr_pass = !(rng_float(rng) > rrProb);      // drawn even when rrProb == 1 (quirk Q16)
+            b.ray_o[slot] = make_float4(Vx.x, Vx.y, Vx.z, __int_as_float(s.cull));
+            b.ray_d[slot] = make_float4(s.w_i.x, s.w_i.y, s.w_i.z, s.srpdf);
+            b.pend[slot] = make_float4(s.alpha.x, s.alpha.y, s.alpha.z, 0.0f);
+            flags = INFO_PENDING | (rr_pass ? INFO_RR_PASS : 0u);
+        } else if (action == ACT_LIGHT) {
+            // GenerateLightPath head (BDPT.cpp:61-77)
+            nc = count;
+            parity ^= 1u;                                  // the finished sample's light vertex 0 stays readable
+            PVert v0[1];
+            const LightStart ls = light_path_head(sc, rng, sc.emissive[0], v0);
+            store_vertex(b.l0A, b.l0B, b.l0C, (size_t)parity * b.S + slot, v0[0]);
+            const f3 afac = ls.pdf1 != 0.0f ? safe_div(v0[0].alpha, ls.pdf1) : mk3(0.0f);
+            b.ray_o[slot] = make_float4(v0[0].x.x, v0[0].x.y, v0[0].x.z, __int_as_float(0));
+            b.ray_d[slot] = make_float4(ls.w_i.x, ls.w_i.y, ls.w_i.z, ls.pdf1);
+            b.pend[slot] = make_float4(afac.x, afac.y, afac.z, 0.0f);
+            path = 1; i = 0; count = 1;
+            flags = INFO_PENDING | INFO_LIGHT_FIRST;
+        }
+        if (live) {
             b.rng[slot] = rng;
-            info = make_info(path, i, count, flags | (parity ? INFO_PARITY : 0u), nc);
-            b.info[slot] = info;
+            b.info[slot] = make_info(path, i, count, flags | (parity ? INFO_PARITY : 0u), nc);
         }
         const unsigned at = wf_append(&b.ctr->n_active[cur ^ 1], keep);
         if (keep) next_list[at] = slot;
@@ -371,7 +423,7 @@ __global__ void __launch_bounds__(256) k_connect(SceneView g, WfBuffers b) {
             int needs_shadow;
             const f3 u = connect_unweighted(sc, cam, s, light, t, &needs_shadow);
             const bool zero = u.x == 0.0f && u.y == 0.0f && u.z == 0.0f;
-            b.pair_val[p] = make_float4(u.x, u.y, u.z, __int_as_float(needs_shadow));
+            if (!zero) b.pair_val[p] = make_float4(u.x, u.y, u.z, __int_as_float(needs_shadow));
             to_shadow = !zero && needs_shadow != 0;
             to_mis = !zero && needs_shadow == 0;
         }
@@ -391,72 +443,60 @@ __global__ void __launch_bounds__(256) k_shadow_q(SceneView g, RenderArgs a, WfB
     for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
         bool visible = false;
         unsigned p = 0;
-        if (q < n) {
+        const bool live = q < n;
+        f3 from = mk3(0.0f), to = mk3(0.0f, 0.0f, 1.0f);
+        int kind = 1;
+        if (live) {
             p = b.shadow_q[q];
             const uint2 rec = b.pair_rec[p];
             const unsigned inf = b.done_info[rec.x];
             const int slot = b.done_slot[rec.x];
             const int s = rec.y & 255u, t = rec.y >> 8;
-            const f3 from = s == 1 ? mk3(sc.eye.x, sc.eye.y, sc.eye.z) : mk3(b.camA[(size_t)(s - 1) * b.S + slot]);
-            const f3 to = t == 1 ? mk3(b.l0A[(size_t)((inf >> 16) & 1u) * b.S + slot]) : mk3(b.lightA[(size_t)(t - 1) * b.S + slot]);
-            const int kind = __float_as_int(b.pair_val[p].w);
-            visible = !shadow_check<false>(sc, from, to, kind == 2 ? 1 : 0, a.prune != 0, nullptr);
+            from = s == 1 ? mk3(sc.eye.x, sc.eye.y, sc.eye.z) : mk3(b.camA[(size_t)(s - 1) * b.S + slot]);
+            to = t == 1 ? mk3(b.l0A[(size_t)((inf >> 16) & 1u) * b.S + slot]) : mk3(b.lightA[(size_t)(t - 1) * b.S + slot]);
+            kind = __float_as_int(b.pair_val[p].w);
             rays++;
-            if (!visible) b.pair_val[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         }
+        if (live) visible = !shadow_check<false>(sc, from, to, kind == 2 ? 1 : 0, a.prune != 0, nullptr);
         const unsigned am = wf_append(&b.ctr->n_mis, visible);
         if (visible) b.mis_q[am] = p;
     }
     flush_stats(0, rays, 0, stats, rays);
 }
 
-// ---- mis: power-heuristic weight of the surviving strategies ------------------------------
-__global__ void __launch_bounds__(256) k_mis(SceneView g, WfBuffers b) {
+// ---- mis + accumulate: power-heuristic weight of the surviving strategies, added to the
+// pixel (s > 1, BDPT.cpp:301-303 + Renderer.cpp:49) or splatted with the 3x3 tent (s == 1,
+// BDPT.cpp:304-311).  Sums are formed with float atomics: their order is not the
+// reference's loop order (neither is the reference's own splat merge across threads).
+__global__ void __launch_bounds__(256) k_mis(SceneView g, RenderArgs a, WfBuffers b, float* radiance, float* splat) {
     const SceneView sc = stage_scene(g, tpt_smem);
     const unsigned n = b.ctr->n_mis;
+    const float inv_spp = 1.0f / a.spp_total;
     for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
         const unsigned p = b.mis_q[q];
         const uint2 rec = b.pair_rec[p];
         const unsigned inf = b.done_info[rec.x];
         const int slot = b.done_slot[rec.x];
         const int s = rec.y & 255u, t = rec.y >> 8;
+        const int parity = (int)((inf >> 16) & 1u);
         const CamPath cam{b, sc, slot};
-        const LightPath light{b, slot, (int)((inf >> 16) & 1u)};
-        const float4 v = b.pair_val[p];
-        f3 w = mk3(v);
+        const LightPath light{b, slot, parity};
+        f3 w = mk3(b.pair_val[p]);
         // a Background end returns before any weighting (BDPT.cpp:180-185)
         const int endType = s == 1 ? VT_CAMERA : unpack_type(__float_as_int(b.camB[(size_t)(s - 1) * b.S + slot].w));
-        if (endType != VT_BACKGROUND) w = w / mis_denominator(sc, cam, s, light, t);
-        b.pair_val[p] = make_float4(std_max(w.x, 0.0f), std_max(w.y, 0.0f), std_max(w.z, 0.0f), 0.0f);   // BDPT.cpp:299
-    }
-}
-
-// ---- accumulate: ordered per-sample sum + light-tracing splats ----------------------------
-__global__ void __launch_bounds__(256) k_accumulate(SceneView g, RenderArgs a, WfBuffers b, float* radiance, float* splat) {
-    const SceneView sc = stage_scene(g, tpt_smem);
-    const unsigned n_done = (unsigned)(b.ctr->done_pairs >> 40);
-    const float inv_spp = 1.0f / a.spp_total;
-    for (unsigned di = blockIdx.x * blockDim.x + threadIdx.x; di < n_done; di += gridDim.x * blockDim.x) {
-        const unsigned inf = b.done_info[di], off = b.done_off[di];
-        const int slot = b.done_slot[di];
-        if (slot < 0) continue;             // void record (no pair space this iteration)
-        const unsigned nc = inf & 255u, nl = (inf >> 8) & 255u, parity = (inf >> 16) & 1u;
-        f3 result = mk3(0.0f);
-        unsigned k = 0;
-        for (unsigned s = 1; s <= nc; ++s)
-            for (unsigned t = 0; t <= nl; ++t) {
-                if (s + t < 2) continue;
-                const f3 w = mk3(b.pair_val[off + k]);
-                k++;
-                if (s > 1) result += w;                          // BDPT.cpp:301-303
-                else {                                           // BDPT.cpp:304-311
-                    const f3 lx = t == 1 ? mk3(b.l0A[(size_t)parity * b.S + slot]) : mk3(b.lightA[(size_t)(t - 1) * b.S + slot]);
-                    splat_to_image(sc, lx, w, splat);
-                }
+        if (endType != VT_BACKGROUND)
+            w = w / mis_denominator_shared(sc, cam, s, light, t, CamAux{b, slot}, LightAux{b, slot, parity});
+        w = mk3(std_max(w.x, 0.0f), std_max(w.y, 0.0f), std_max(w.z, 0.0f));   // BDPT.cpp:299
+        if (s > 1) {
+            if (w.x != 0.0f || w.y != 0.0f || w.z != 0.0f) {
+                const int pixel = a.partition == TPT_PART_INTERLEAVE ? slot * a.world + a.rank : slot;
+                float* px = radiance + 3 * (size_t)pixel;
+                atomicAdd(px, inv_spp * w.x); atomicAdd(px + 1, inv_spp * w.y); atomicAdd(px + 2, inv_spp * w.z);
             }
-        const int pixel = a.partition == TPT_PART_INTERLEAVE ? slot * a.world + a.rank : slot;
-        float* px = radiance + 3 * (size_t)pixel;
-        px[0] += inv_spp * result.x; px[1] += inv_spp * result.y; px[2] += inv_spp * result.z;   // Renderer.cpp:49
+        } else {
+            const f3 lx = t == 1 ? mk3(b.l0A[(size_t)parity * b.S + slot]) : mk3(b.lightA[(size_t)(t - 1) * b.S + slot]);
+            splat_to_image(sc, lx, w, splat);
+        }
     }
 }
 
@@ -548,8 +588,7 @@ int wavefront_render(TptScene* s, const RenderArgs& a, float* d_radiance, float*
         tm->begin(TPT_K_EXPAND); k_expand<<<pgrid, 256, 0, st>>>(b); tm->end();
         tm->begin(TPT_K_CONNECT); k_connect<<<pgrid, 256, smem, st>>>(s->view, b); tm->end();
         tm->begin(TPT_K_SHADOW); k_shadow_q<<<pgrid, 256, smem, st>>>(s->view, a, b, s->d_stats); tm->end();
-        tm->begin(TPT_K_MIS); k_mis<<<pgrid, 256, smem, st>>>(s->view, b); tm->end();
-        tm->begin(TPT_K_ACCUMULATE); k_accumulate<<<grid, 256, smem, st>>>(s->view, a, b, d_radiance, d_splat); tm->end();
+        tm->begin(TPT_K_MIS); k_mis<<<pgrid, 256, smem, st>>>(s->view, a, b, d_radiance, d_splat); tm->end();
         cur ^= 1;
         if ((it & 7) == 7 || it + 1 == max_iters) {
             TPT_CUDA(cudaMemcpyAsync(w->h_flag, &b.ctr->n_active[cur], sizeof(unsigned), cudaMemcpyDeviceToHost, st));
