@@ -108,7 +108,7 @@ TPT_DEV f3 light_sample_dir(Ctx& c, int light, uint32_t& rng, f3 x, float* pdf) 
     object_sample(c.sc, light, rng, &pos);
     f3 w_i = pos.coords - x;
     const float lightDistanceSqr = dotf(w_i, w_i);
-    w_i = x_normalize(w_i);
+    w_i = s_normalize(w_i);
     const float rawpdf = object_pdf(c.sc, light);
     const float costhetap = dotf(pos.normal, -w_i);
     *pdf = (float)((double)rawpdf * lightDistanceSqr / fabsf(costhetap));
@@ -190,7 +190,7 @@ TPT_DEV f3 path_trace(Ctx& c, uint32_t& rng, DRay ray, bool full, int* outBounce
 // SrpdfToAreaPdf, SampleHelperFunctions.hpp:122-131
 TPT_DEV float srpdf_to_area(float srpdf, f3 x1, f3 N1, int type1, f3 x2, f3 N2, int type2) {
     float distSqr;
-    const f3 w = x_normalize_len2(x2 - x1, &distSqr);
+    const f3 w = s_normalize_len2(x2 - x1, &distSqr);
     const float cos1 = type1 == VT_CAMERA ? 1.0f : (float)fabs(dotd(w, N1));
     const float cos2 = type2 == VT_CAMERA ? 1.0f : (float)fabs(dotd(-w, N2));
     return srpdf * fabsf(cos1 * cos2 / distSqr);
@@ -234,7 +234,7 @@ TPT_DEV int fill_path(Ctx& c, uint32_t& rng, PVert* verts) {
     int count = 2;
     for (int i = 1; i < MAX_BDPT_PATH_LENGTH - 1; i++) {
         if (verts[i].type == VT_BACKGROUND) break;
-        const f3 w_o = x_normalize(verts[i - 1].x - verts[i].x);
+        const f3 w_o = s_normalize(verts[i - 1].x - verts[i].x);
         const NextSample s = sample_next_dir(c.sc, rng, verts[i].N, verts[i].prim, w_o);
         DHit h;
         trace_scene<COUNT>(c, make_ray(verts[i].x, s.w_i), s.cull, &h);
@@ -292,7 +292,7 @@ TPT_DEV bool light_path_first_hit(const LightStart& s, const DHit& h, PVert* ver
 // behind L (whose predecessor is at pre_x), before the Russian-roulette factor.
 TPT_DEV float append_pdf_base(const SceneView& sc, const PVert& L, int Ltype, f3 pre_x, f3 vx, f3 vN, int vtype) {
     float distSqr;
-    const f3 w = x_normalize_len2(vx - L.x, &distSqr);
+    const f3 w = s_normalize_len2(vx - L.x, &distSqr);
     const f3 NL = Ltype == VT_CAMERA ? mk3(0.0f, 0.0f, 1.0f) : L.N;
     const float cosine = (float)fabs(dotd(w, NL));
     float srpdf;
@@ -300,7 +300,7 @@ TPT_DEV float append_pdf_base(const SceneView& sc, const PVert& L, int Ltype, f3
     else if (Ltype == VT_CAMERA) srpdf = CAMERA_RAY_PDF;
     else if (cosine == 0.0f) srpdf = 0.0f;
     else {
-        const f3 wo = x_normalize(pre_x - L.x);
+        const f3 wo = s_normalize(pre_x - L.x);
         const Mat mat = load_mat(sc, prim_material(sc, L.prim));
         srpdf = safe_div(mat_pdf(mat, wo, NL, w), cosine);
     }
@@ -319,7 +319,7 @@ TPT_DEV float append_pdf(const SceneView& sc, const PVert& L, int Ltype, f3 pre_
 TPT_DEV f3 vertex_bsdf(const SceneView& sc, const PVert& v, f3 pre_x, f3 dir) {
     if (v.type == VT_LIGHT || v.type == VT_CAMERA) return mk3(1.0f);
     const Mat mat = load_mat(sc, prim_material(sc, v.prim));
-    return mat_eval(mat, x_normalize(pre_x - v.x), dir, vert_normal(v), false);
+    return mat_eval(mat, s_normalize(pre_x - v.x), dir, vert_normal(v), false);
 }
 
 // Scene::ShadowCheck(const PTVertex& v1, const PTVertex& v2), Scene.cpp:50-83.
@@ -348,14 +348,14 @@ TPT_DEV f3 connect_unweighted(const SceneView& sc, const CamPath& cam, int s, co
         if (z1.prim < 0) return mk3(0.0f);
         const Mat mat = load_mat(sc, prim_material(sc, z1.prim));
         if (dotd(mat.emission, mat.emission) == 0.0) return mk3(0.0f);
-        const f3 w_i = x_normalize(cam(s - 2).x - z1.x);
+        const f3 w_i = s_normalize(cam(s - 2).x - z1.x);
         const f3 c_st = mat.emission * (float)dotd(vert_normal(z1), w_i);
         return (mk3(1.0f) * z1.alpha) * c_st;
     }
     const PVert y = light(t - 1);
     if (y.type == VT_BACKGROUND) return mk3(0.0f);
     float distSqr;
-    const f3 dir_ltoc = x_normalize_len2(z1.x - y.x, &distSqr);
+    const f3 dir_ltoc = s_normalize_len2(z1.x - y.x, &distSqr);
     *needs_shadow = shadow_query_kind(sc, z1, y);
     const f3 fl = vertex_bsdf(sc, y, t >= 2 ? light(t - 2).x : mk3(0.0f), dir_ltoc);
     const f3 fc = vertex_bsdf(sc, z1, s >= 2 ? cam(s - 2).x : mk3(0.0f), -dir_ltoc);
@@ -490,7 +490,7 @@ TPT_DEV f3 path_weight(Ctx& c, const CamPath& cam, int s, const LightPath& light
 // for the light vertex at `light_x`, with the reference's `height` stride (quirk Q5).
 TPT_DEV void splat_to_image(const SceneView& sc, f3 light_x, f3 value, float* splat) {
     if (value.x == 0.0f && value.y == 0.0f && value.z == 0.0f) return;   // adding zeros
-    f3 d = x_normalize(light_x - mk3(sc.eye.x, sc.eye.y, sc.eye.z));
+    f3 d = s_normalize(light_x - mk3(sc.eye.x, sc.eye.y, sc.eye.z));
     d = d / d.z;
     const float u = (-d.x / sc.scale / sc.aspect + 1.0f) * 0.5f;
     const float v = (-d.y / sc.scale + 1.0f) * 0.5f;

@@ -126,22 +126,21 @@ TPT_DEV void closest_hit_range(const SceneView& sc, const DRay& r, int cull, int
     int best = -1;
     float prune_t = FLT_MAX;
     int i = first;
-    while (i < end) {
+    while (i < end) {     // one back edge, no `continue`: the warp reconverges every iteration
         const float4 n0 = sc.nodes[2 * i], n1 = sc.nodes[2 * i + 1];
         if (COUNT) cnt->node_visits++;
         float nmin;
-        bool in = slab_test(n0, n1, r, &nmin);
-        if (nmin > prune_t) in = false;   // prune_t stays FLT_MAX unless pruning
-        if (!in) { i = __float_as_int(n1.w); continue; }
+        const bool in = slab_test(n0, n1, r, &nmin) && !(nmin > prune_t);   // prune_t stays FLT_MAX unless pruning
         const int prim = __float_as_int(n0.w);
-        if (prim >= 0) {
+        i = in ? i + 1 : __float_as_int(n1.w);       // descend (a leaf's miss link is i+1 too) or skip the subtree
+        if (in && prim >= 0) {
             if (COUNT) cnt->prim_tests++;
-            double t;
+            double t = 0.0;
             bool ok;
             if (prim < sc.n_tris) {
                 ok = triangle_test(sc, prim, r, cull, &t);
             } else {
-                float ts;
+                float ts = 0.0f;
                 ok = sphere_test(sc, prim - sc.n_tris, r, cull, &ts);
                 t = (double)ts;    // Intersection::distance = t_kept, Sphere.cpp:39
             }
@@ -150,7 +149,6 @@ TPT_DEV void closest_hit_range(const SceneView& sc, const DRay& r, int cull, int
                 if (prune) prune_t = (float)t * 1.0001f + 1e-3f;
             }
         }
-        i = i + 1;   // leaf: its miss link is i+1 too
     }
     hit->prim = best;
     hit->t = best_t;
@@ -197,14 +195,55 @@ TPT_DEV void object_intersect(const SceneView& sc, int obj, const DRay& r, int c
 // Scene::ShadowCheck(Vector3f lightCoords, Vector3f x, cull), Scene.cpp:37-48:
 // the ray leaves `from` toward `to`; shadowed iff the closest hit is more than
 // (squared distance - 1) short of `to`.
+//
+// With `prune` this is an any-hit query: the hit point o + fl(t)*d moves away from o
+// monotonically with t (every rounding involved is monotone), so "the CLOSEST hit lies
+// within the limit" is the same statement as "SOME hit lies within the limit".  The walk
+// therefore stops at the first hit inside the limit and never enters a box that starts
+// beyond the target.  Without `prune` it is the reference's closest-hit form.
 template <bool COUNT>
 TPT_DEV bool shadow_check(const SceneView& sc, f3 from, f3 to, int cull, bool prune, TravCounters* cnt) {
     const f3 d0 = x_sub(from, to);
     const double lightDistanceSqr = dotd(d0, d0);
+    const double limit = lightDistanceSqr - 1.0;
     const DRay r = make_ray(from, x_normalize(x_sub(to, from)));
-    DHit h;
-    scene_intersect<COUNT>(sc, r, cull, prune, &h, cnt);
-    if (h.prim < 0) return false;
-    const f3 d1 = x_sub(h.coords, from);
-    return dotd(d1, d1) < lightDistanceSqr - 1.0;
+    if (!prune) {
+        DHit h;
+        scene_intersect<COUNT>(sc, r, cull, false, &h, cnt);
+        if (h.prim < 0) return false;
+        const f3 d1 = x_sub(h.coords, from);
+        return dotd(d1, d1) < limit;
+    }
+    // a hit at parameter t >= |to - from| cannot be inside the limit; boxes entered later are skipped
+    const float reach = __fsqrt_rn((float)lightDistanceSqr) * 1.0001f + 1e-3f;
+    // one loop, one back edge, one exit: the lanes of a warp stay together (an early `return`
+    // inside the loop splits the warp into groups that walk the rest of the tree one by one)
+    int i = 0;
+    const int end = sc.n_nodes;
+    bool found = false;
+    while (i < end && !found) {
+        const float4 n0 = sc.nodes[2 * i], n1 = sc.nodes[2 * i + 1];
+        if (COUNT) cnt->node_visits++;
+        float nmin;
+        const bool in = slab_test(n0, n1, r, &nmin) && !(nmin > reach);
+        const int prim = __float_as_int(n0.w);
+        i = in ? i + 1 : __float_as_int(n1.w);
+        if (in && prim >= 0) {
+            if (COUNT) cnt->prim_tests++;
+            float tf = 0.0f;
+            bool ok;
+            if (prim < sc.n_tris) {
+                double t = 0.0;
+                ok = triangle_test(sc, prim, r, cull, &t);
+                tf = (float)t;
+            } else {
+                ok = sphere_test(sc, prim - sc.n_tris, r, cull, &tf);
+            }
+            if (ok) {
+                const f3 d1 = x_sub(x_madd(r.o, r.d, tf), from);
+                found = dotd(d1, d1) < limit;
+            }
+        }
+    }
+    return found;
 }

@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(256) k_shade(SceneView g, RenderArgs a, WfBuff
             f3 prev_x;
             if (i == 1) prev_x = path ? mk3(b.l0A[(size_t)parity * b.S + slot]) : mk3(sc.eye.x, sc.eye.y, sc.eye.z);
             else prev_x = mk3(A[(size_t)(i - 1) * b.S + slot]);
-            const f3 w_o = x_normalize(prev_x - Vx);
+            const f3 w_o = s_normalize(prev_x - Vx);
             const NextSample s = sample_next_dir(sc, rng, VN, Vprim, w_o);
             const float rrProb = i > 4 ? .8f : 1.f;
             const bool rr_pass = !(rng_float(rng) > rrProb);      // drawn even when rrProb == 1 (quirk Q16)
