@@ -348,7 +348,7 @@ TPT_DEV f3 connect_unweighted(const SceneView& sc, const CamPath& cam, int s, co
         if (z1.prim < 0) return mk3(0.0f);
         const Mat mat = load_mat(sc, prim_material(sc, z1.prim));
         if (dotd(mat.emission, mat.emission) == 0.0) return mk3(0.0f);
-        const f3 w_i = s_normalize(cam(s - 2).x - z1.x);
+        const f3 w_i = s_normalize(cam.pos(s - 2) - z1.x);
         const f3 c_st = mat.emission * (float)dotd(vert_normal(z1), w_i);
         return (mk3(1.0f) * z1.alpha) * c_st;
     }
@@ -357,8 +357,8 @@ TPT_DEV f3 connect_unweighted(const SceneView& sc, const CamPath& cam, int s, co
     float distSqr;
     const f3 dir_ltoc = s_normalize_len2(z1.x - y.x, &distSqr);
     *needs_shadow = shadow_query_kind(sc, z1, y);
-    const f3 fl = vertex_bsdf(sc, y, t >= 2 ? light(t - 2).x : mk3(0.0f), dir_ltoc);
-    const f3 fc = vertex_bsdf(sc, z1, s >= 2 ? cam(s - 2).x : mk3(0.0f), -dir_ltoc);
+    const f3 fl = vertex_bsdf(sc, y, t >= 2 ? light.pos(t - 2) : mk3(0.0f), dir_ltoc);
+    const f3 fc = vertex_bsdf(sc, z1, s >= 2 ? cam.pos(s - 2) : mk3(0.0f), -dir_ltoc);
     const float g = (float)fabs(dotd(vert_normal(y), dir_ltoc) * dotd(vert_normal(z1), -dir_ltoc) / (double)distSqr);
     const f3 c_st = (fl * fc) * g;
     return (y.alpha * z1.alpha) * c_st;

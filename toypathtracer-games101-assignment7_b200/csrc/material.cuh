@@ -89,10 +89,13 @@ TPT_DEV float ggx_half_pdf(f3 n, f3 h, float roughness) {              // GGXHal
 }
 TPT_DEV f3 ggx_sample_h(uint32_t& rng, f3 N, float roughness) {        // SampleGGXSpecularH, :46-59
     const float d1 = rng_float(rng), d2 = rng_float(rng);
-    const float theta = atan2f(roughness * sqrtf(d1), sqrtf(1.0f - d1));
+    // theta = atan2(rough * sqrt(d1), sqrt(1 - d1)); only its sine and cosine are used, and those
+    // are the two legs over the hypotenuse — no atan2 / sincos round trip (same values to an ulp)
+    const float ly = roughness * sqrtf(d1), lx = sqrtf(1.0f - d1);
+    const float hyp = sqrtf(lx * lx + ly * ly);
+    const float st = ly / hyp, ct = lx / hyp;
     const float phi = 2.0f * TPT_PI * d2;
-    float st, ct, sp, cp;
-    sincosf(theta, &st, &ct);
+    float sp, cp;
     sincosf(phi, &sp, &cp);
     return s_normalize(to_world(mk3(st * cp, st * sp, ct), N));
 }

@@ -85,6 +85,7 @@ __device__ inline SceneView stage_scene(const SceneView& g, unsigned char* smem)
     auto put = [&](const void* src, unsigned bytes) -> const float4* {
         const unsigned n = (bytes + 15u) / 16u;
         const float4* from = reinterpret_cast<const float4*>(src);
+#pragma unroll 1
         for (unsigned i = threadIdx.x; i < n; i += blockDim.x) dst[off + i] = __ldg(from + i);
         const float4* at = dst + off;
         off += n;

@@ -490,12 +490,20 @@ extern "C" int tpt_material_sample_batch(TptScene* s, int32_t mat, const float* 
 }
 
 // PathWeight over explicit subpaths: one thread per (pair, s, t).
+TPT_DEV PVert to_pvert(const PVert& v) { return v; }
 TPT_DEV PVert to_pvert(const TptPathVertex& v) {
     PVert p;
     p.x = mk3(v.x.x, v.x.y, v.x.z); p.N = mk3(v.N.x, v.N.y, v.N.z);
     p.prim = v.prim; p.type = v.type; p.pdf = v.pdf; p.alpha = mk3(v.alpha.x, v.alpha.y, v.alpha.z);
     return p;
 }
+// A subpath held as a plain array (the validation kernel's local arrays, the ABI's TptPathVertex).
+template <class V> struct ArrayPath {
+    const V* v;
+    TPT_DEV PVert operator()(int k) const { return to_pvert(v[k]); }
+    TPT_DEV f3 pos(int k) const { return to_pvert(v[k]).x; }
+};
+
 __global__ void __launch_bounds__(256) k_pathweight(SceneView g, const TptPathVertex* cam, const int32_t* camCount,
                                                     const TptPathVertex* light, const int32_t* lightCount, size_t n,
                                                     float* weights) {
@@ -508,8 +516,7 @@ __global__ void __launch_bounds__(256) k_pathweight(SceneView g, const TptPathVe
         if (s <= camCount[pair] && t <= lightCount[pair] && s + t >= 2) {
             const TptPathVertex* cp = cam + 16 * pair;
             const TptPathVertex* lp = light + 16 * pair;
-            auto camA = [&](int k) { return to_pvert(cp[k]); };
-            auto lightA = [&](int k) { return to_pvert(lp[k]); };
+            const ArrayPath<TptPathVertex> camA{cp}, lightA{lp};
             w = path_weight<false>(c, camA, s, lightA, t);
         }
         st3(weights, i, w);
@@ -566,8 +573,7 @@ __global__ void __launch_bounds__(128) k_render_mega(SceneView g, RenderArgs a, 
                 int nl = 2;
                 if (light_path_first_hit(ls, h, light)) nl = fill_path<COUNT>(c, rng, light);
                 ref_rays += nc + nl;                                   // BDPT.cpp:288
-                auto camA = [&](int i) { return cam[i]; };
-                auto lightA = [&](int i) { return light[i]; };
+                const ArrayPath<PVert> camA{cam}, lightA{light};
                 L = mk3(0.0f);
                 for (int s = 1; s <= nc; ++s)
                     for (int t = 0; t <= nl; ++t) {

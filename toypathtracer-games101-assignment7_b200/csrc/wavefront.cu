@@ -28,6 +28,10 @@
 
 extern __shared__ __align__(16) unsigned char tpt_smem[];
 
+#ifndef WF_MIN_BLOCKS
+#define WF_MIN_BLOCKS 4   // resident 256-thread CTAs per SM the shading kernels are compiled for
+#endif
+
 namespace {
 
 // ---- per-iteration device counters ------------------------------------------------
@@ -42,7 +46,8 @@ struct WfCounters {
 // ---- slot state ----------------------------------------------------------------------
 // info bits: [0] path (0 camera, 1 light)  [1..4] i = index of the last stored vertex
 //            [5..9] count  [10] pending ray  [11] light-first ray  [12] rr pass
-//            [13] waiting for pair space  [14] light-0 buffer parity  [16..20] nc of this sample
+//            [13] waiting for pair space  [14] light-0 buffer parity  [15] ray left from cam[1]
+//            [16..20] nc of this sample
 #define INFO_PATH(i) ((i) & 1u)
 #define INFO_I(i) (((i) >> 1) & 15u)
 #define INFO_COUNT(i) (((i) >> 5) & 31u)
@@ -51,6 +56,7 @@ struct WfCounters {
 #define INFO_RR_PASS (1u << 12)
 #define INFO_WAIT (1u << 13)
 #define INFO_PARITY (1u << 14)
+#define INFO_FROM_C1 (1u << 15)
 #define INFO_NC(i) (((i) >> 16) & 31u)
 TPT_DEV unsigned make_info(unsigned path, unsigned i, unsigned count, unsigned flags, unsigned nc) {
     return path | (i << 1) | (count << 5) | flags | (nc << 16);
@@ -65,8 +71,11 @@ struct WfBuffers {
     uint32_t* rng;
     unsigned* info;
     unsigned* spp_done;
-    float4 *ray_o, *ray_d, *pend;      // {o, asfloat(cull)} {d, srpdf} {alpha factor, 0}
+    float4 *ray_o, *ray_d, *pend;      // {o, asfloat(cull), cull < 0: no ray} {d, srpdf} {alpha factor, 0}
     float4* hit;                       // {coords, asfloat(prim)}
+    // rolling window: the vertex the pending ray left from (cur) and the one before it (prv), indexed
+    // by slot alone so that k_shade can issue every load of an iteration at once
+    float4 *curA, *curB, *curC, *prvA, *prvB;
     int* active[2];
     // completed samples of this iteration
     int* done_slot;
@@ -74,7 +83,7 @@ struct WfBuffers {
     unsigned* done_off;
     // strategies
     unsigned long long pair_cap;
-    uint2* pair_rec;                   // {done index, s | t << 8}
+    uint2* pair_rec;                   // {slot, s | t << 8 | parity << 16}; slot 0xffffffff = void
     float4* pair_val;
     unsigned *shadow_q, *mis_q;
     WfCounters* ctr;
@@ -105,20 +114,30 @@ TPT_DEV PVert camera_vertex(const SceneView& sc) {
     return v;
 }
 
-struct CamPath {
+// Path-store views.  ALPHA = false skips the third 128-bit word (throughput), which the
+// MIS weights never read.
+template <bool ALPHA> struct CamPathT {
     const WfBuffers& b; const SceneView& sc; int slot;
     TPT_DEV PVert operator()(int k) const {
         if (k == 0) return camera_vertex(sc);
-        return load_vertex(b.camA, b.camB, b.camC, (size_t)k * b.S + slot, true);
+        return load_vertex(b.camA, b.camB, b.camC, (size_t)k * b.S + slot, ALPHA);
+    }
+    TPT_DEV f3 pos(int k) const {
+        return k == 0 ? mk3(sc.eye.x, sc.eye.y, sc.eye.z) : mk3(b.camA[(size_t)k * b.S + slot]);
     }
 };
-struct LightPath {
+template <bool ALPHA> struct LightPathT {
     const WfBuffers& b; int slot; int parity;
     TPT_DEV PVert operator()(int k) const {
-        if (k == 0) return load_vertex(b.l0A, b.l0B, b.l0C, (size_t)parity * b.S + slot, true);
-        return load_vertex(b.lightA, b.lightB, b.lightC, (size_t)k * b.S + slot, true);
+        if (k == 0) return load_vertex(b.l0A, b.l0B, b.l0C, (size_t)parity * b.S + slot, ALPHA);
+        return load_vertex(b.lightA, b.lightB, b.lightC, (size_t)k * b.S + slot, ALPHA);
+    }
+    TPT_DEV f3 pos(int k) const {
+        return k == 0 ? mk3(b.l0A[(size_t)parity * b.S + slot]) : mk3(b.lightA[(size_t)k * b.S + slot]);
     }
 };
+typedef CamPathT<true> CamPath;
+typedef LightPathT<true> LightPath;
 
 // {original area pdf of vertex i, reverse pdf towards vertex i (C.w, written by k_shade)}
 struct CamAux {
@@ -196,13 +215,23 @@ __global__ void __launch_bounds__(256) k_generate(SceneView g, RenderArgs a, WfB
 // light subpath) and emit the ray.
 enum { ACT_NONE = 0, ACT_EXTEND = 1, ACT_LIGHT = 2 };
 
-__global__ void __launch_bounds__(256) k_shade(SceneView g, RenderArgs a, WfBuffers b, int cur, unsigned long long* stats) {
+TPT_DEV PVert unpack_vertex(const float4 a, const float4 b, const float4 c) {
+    PVert v;
+    v.x = mk3(a); v.pdf = a.w; v.N = mk3(b);
+    const int p = __float_as_int(b.w);
+    v.prim = unpack_prim(p); v.type = unpack_type(p);
+    v.alpha = mk3(c);
+    return v;
+}
+
+__global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_shade(SceneView g, RenderArgs a, WfBuffers b, int cur, unsigned long long* stats) {
     const SceneView sc = stage_scene(g, tpt_smem);
     const unsigned n = b.ctr->n_active[cur];
     const int* list = b.active[cur];
     int* next_list = b.active[cur ^ 1];
     unsigned long long ref_rays = 0, samples = 0;
     const unsigned total = (n + 31u) & ~31u;     // whole warps enter the loop (ballots below)
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
         const bool live = q < n;
         const int slot = live ? list[q] : 0;
@@ -210,14 +239,24 @@ __global__ void __launch_bounds__(256) k_shade(SceneView g, RenderArgs a, WfBuff
         int action = ACT_NONE;
         unsigned path = 0, i = 0, count = 0, nc = 0, parity = 0, flags = 0;
         uint32_t rng = 0;
+        // the vertex the next ray leaves from (V) and its predecessor's position, kept in registers
+        float4 VA = zero4, VB = zero4, c1A = zero4, c1B = zero4;
+        f3 prev_x = mk3(0.0f);
+        bool path_done = false, completing = false, fresh = false;
         if (live) {
+            // ---- every load of this iteration, issued together (all addressed by the slot alone)
             const unsigned info = b.info[slot];
             rng = b.rng[slot];
+            const float4 hr = b.hit[slot], rd = b.ray_d[slot], pa = b.pend[slot];
+            const float4 cA = b.curA[slot], cB = b.curB[slot], cC = b.curC[slot];
+            const float4 pA = b.prvA[slot], pB = b.prvB[slot];
+            c1A = b.camA[(size_t)b.S + slot]; c1B = b.camB[(size_t)b.S + slot];
+
             path = INFO_PATH(info); i = INFO_I(info); count = INFO_COUNT(info); nc = INFO_NC(info);
             parity = (info & INFO_PARITY) ? 1u : 0u;
-            bool waiting = (info & INFO_WAIT) != 0;
-            bool path_done = waiting;     // a waiting slot sits on a finished light subpath
-            int cur_type = -1;            // type of vertex i, when known without a load
+            const bool waiting = (info & INFO_WAIT) != 0;
+            path_done = waiting;          // a waiting slot sits on a finished light subpath
+            int cur_type = -1;            // type of vertex i, when known
 
             // ---- phase 1: the vertex the traced ray produced (SampleNextVertex tail + FillPath body)
             if (info & INFO_PENDING) {
@@ -225,16 +264,15 @@ __global__ void __launch_bounds__(256) k_shade(SceneView g, RenderArgs a, WfBuff
                 float4* B = path ? b.lightB : b.camB;
                 float4* C = path ? b.lightC : b.camC;
                 const bool lf = (info & INFO_LIGHT_FIRST) != 0;
-                const float4 hr = b.hit[slot];
+                const bool c1 = (info & INFO_FROM_C1) != 0;
                 DHit h;
                 h.prim = __float_as_int(hr.w); h.coords = mk3(hr); h.t = 0.0;
                 h.normal = h.prim >= 0 ? hit_normal(sc, h.prim, h.coords) : mk3(0.0f);
                 PVert nv = vertex_from_hit(h);
-                const float srpdf = b.ray_d[slot].w;
-                const f3 afac = mk3(b.pend[slot]);
-                // the vertex the ray left from: light vertex 0 for the first light ray, else vertex i
-                const PVert L = lf ? load_vertex(b.l0A, b.l0B, b.l0C, (size_t)parity * b.S + slot, false)
-                                   : load_vertex(A, B, C, (size_t)i * b.S + slot, true);
+                const float srpdf = rd.w;
+                const f3 afac = mk3(pa);
+                // L: the vertex the ray left from; T: the vertex before it (target of the reverse pdf)
+                const PVert L = c1 ? unpack_vertex(c1A, c1B, make_float4(1.f, 1.f, 1.f, 0.f)) : unpack_vertex(cA, cB, cC);
                 nv.pdf = srpdf_to_area(srpdf, L.x, L.N, L.type, nv.x, nv.N, nv.type);
                 if (lf) {
                     nv.alpha = afac;                       // SafeDivide(verts[0].alpha, pdf1), or 0 when pdf1 == 0
@@ -251,94 +289,108 @@ __global__ void __launch_bounds__(256) k_shade(SceneView g, RenderArgs a, WfBuff
                         store_vertex(A, B, C, (size_t)(i + 1) * b.S + slot, nv);
                         // reverse pdf towards vertex i-1: it is appended behind vertex i whose
                         // predecessor is the new vertex i+1 (mis_denominator_shared reads it)
-                        {
-                            f3 tx, tN = mk3(0.0f);
-                            int tt;
-                            float* dst;
-                            if (i >= 2) {
-                                const size_t at = (size_t)(i - 1) * b.S + slot;
-                                const float4 ta = A[at], tb = B[at];
-                                tx = mk3(ta); tN = mk3(tb); tt = unpack_type(__float_as_int(tb.w));
-                                dst = &C[at].w;
-                            } else if (path) {
-                                const size_t at = (size_t)parity * b.S + slot;
-                                const float4 ta = b.l0A[at], tb = b.l0B[at];
-                                tx = mk3(ta); tN = mk3(tb); tt = VT_LIGHT;
-                                dst = &b.l0C[at].w;
-                            } else {
-                                tx = mk3(sc.eye.x, sc.eye.y, sc.eye.z); tt = VT_CAMERA;
-                                dst = &b.camC[slot].w;
-                            }
-                            *dst = append_pdf_base(sc, L, L.type, nv.x, tx, tN, tt);
+                        f3 tx, tN = mk3(0.0f);
+                        int tt;
+                        float* dst;
+                        if (c1) { tx = mk3(sc.eye.x, sc.eye.y, sc.eye.z); tt = VT_CAMERA; dst = &b.camC[slot].w; }
+                        else {
+                            tx = mk3(pA); tN = mk3(pB); tt = unpack_type(__float_as_int(pB.w));
+                            dst = i >= 2 ? &C[(size_t)(i - 1) * b.S + slot].w : &b.l0C[(size_t)parity * b.S + slot].w;
                         }
+                        *dst = append_pdf_base(sc, L, L.type, nv.x, tx, tN, tt);
                         count++; i++;
                     }
                 }
-                cur_type = nv.type;
+                if (!path_done) {
+                    // slide the window: the new vertex is the one the next ray leaves from
+                    VA = make_float4(nv.x.x, nv.x.y, nv.x.z, nv.pdf);
+                    VB = make_float4(nv.N.x, nv.N.y, nv.N.z, __int_as_float(pack_pt(nv.prim, nv.type)));
+                    prev_x = L.x;
+                    b.prvA[slot] = make_float4(L.x.x, L.x.y, L.x.z, L.pdf);
+                    b.prvB[slot] = make_float4(L.N.x, L.N.y, L.N.z, __int_as_float(pack_pt(L.prim, L.type)));
+                    b.curA[slot] = VA; b.curB[slot] = VB;
+                    b.curC[slot] = make_float4(nv.alpha.x, nv.alpha.y, nv.alpha.z, 0.0f);
+                    cur_type = nv.type;
+                }
             }
 
-            // ---- phase 2: state machine, cheap steps only
+            // ---- phase 2a: does the current subpath end here? (top of the FillPath loop, BDPT.cpp:98-99)
+            fresh = !(info & INFO_PENDING) && !waiting;      // first iteration: nothing traced yet
+            if (!path_done && !fresh && (i >= MAX_BDPT_PATH_LENGTH - 1 || cur_type == VT_BACKGROUND)) path_done = true;
+            completing = path_done && path == 1;             // light subpath complete -> sample complete
             keep = true;
-            for (int guard = 0; guard < 6; ++guard) {
-                if (!path_done) {
-                    // top of the FillPath loop for vertex i (BDPT.cpp:98-99)
-                    if (cur_type < 0) cur_type = unpack_type(__float_as_int((path ? b.lightB : b.camB)[(size_t)i * b.S + slot].w));
-                    if (i >= MAX_BDPT_PATH_LENGTH - 1 || cur_type == VT_BACKGROUND) { path_done = true; continue; }
-                    action = ACT_EXTEND;
-                    break;
-                }
-                if (path == 0) { action = ACT_LIGHT; break; }   // camera subpath complete
-                // light subpath complete -> the sample is complete: reserve its strategies
+        }
+
+        // ---- phase 2b: reserve the strategies of the samples completing in this warp — one atomic per
+        // warp: (samples << 40 | strategies) are allocated together so records and ranges stay ordered
+        {
+            const unsigned cmask = __ballot_sync(0xffffffffu, completing);
+            if (cmask) {
+                const unsigned lane = threadIdx.x & 31u;
                 const unsigned nl = count;
-                const unsigned npairs = nc * (nl + 1) - 1;
-                const unsigned long long old = atomicAdd(&b.ctr->done_pairs, (1ull << 40) | npairs);
-                const unsigned long long off = old & ((1ull << 40) - 1);
-                const unsigned di = (unsigned)(old >> 40);
-                if (off + npairs > b.pair_cap) {
-                    // no room left this iteration: leave a void record (its range is marked
-                    // invalid by k_expand) and complete the sample in a later iteration
-                    b.done_slot[di] = -1;
-                    b.done_info[di] = npairs;
-                    b.done_off[di] = off < b.pair_cap ? (unsigned)off : 0xffffffffu;
-                    flags = INFO_WAIT;
-                    break;
+                const unsigned npairs = completing ? nc * (nl + 1) - 1 : 0u;
+                unsigned incl = npairs;                      // inclusive prefix sum over the warp
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= (unsigned)o) incl += v;
                 }
-                b.done_slot[di] = slot;
-                b.done_info[di] = nc | (nl << 8) | (parity << 16);
-                b.done_off[di] = (unsigned)off;
-                ref_rays += nc + nl;                       // BDPT.cpp:288
-                samples++;
-                const unsigned done = b.spp_done[slot] + 1;
-                b.spp_done[slot] = done;
-                path = 0; i = 1; count = 2; nc = 0; path_done = false; cur_type = -1;
-                if ((int)done >= a.spp) {                  // all samples of this pixel drawn: the slot retires
-                    atomicAdd(&b.ctr->n_retired, 1u);
-                    keep = false;
-                    break;
+                const unsigned wtotal = __shfl_sync(0xffffffffu, incl, 31);
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(&b.ctr->done_pairs, ((unsigned long long)__popc(cmask) << 40) | wtotal);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (completing) {
+                    const unsigned long long off = (base & ((1ull << 40) - 1)) + (incl - npairs);
+                    const unsigned di = (unsigned)(base >> 40) + __popc(cmask & ((1u << lane) - 1u));
+                    if (off + npairs > b.pair_cap) {
+                        // no room left this iteration: leave a void record (its range is marked
+                        // invalid by k_expand) and complete the sample in a later iteration
+                        b.done_slot[di] = -1;
+                        b.done_info[di] = npairs;
+                        b.done_off[di] = off < b.pair_cap ? (unsigned)off : 0xffffffffu;
+                        flags = INFO_WAIT;
+                    } else {
+                        b.done_slot[di] = slot;
+                        b.done_info[di] = nc | (nl << 8) | (parity << 16);
+                        b.done_off[di] = (unsigned)off;
+                        ref_rays += nc + nl;                 // BDPT.cpp:288
+                        samples++;
+                        const unsigned done = b.spp_done[slot] + 1;
+                        b.spp_done[slot] = done;
+                        fresh = true;
+                        if ((int)done >= a.spp) {            // all samples of this pixel drawn: the slot retires
+                            fresh = false; keep = false;
+                            path = 0; i = 1; count = 2; nc = 0;
+                        }
+                    }
                 }
-                // next sample: the camera subpath restarts at the cached primary hit
             }
         }
 
+        // ---- phase 2c: a fresh camera subpath starts at the cached primary hit; pick the action
+        if (fresh) {
+            path = 0; i = 1; count = 2; nc = 0;
+            VA = c1A; VB = c1B; prev_x = mk3(sc.eye.x, sc.eye.y, sc.eye.z);
+            flags = INFO_FROM_C1;
+            path_done = unpack_type(__float_as_int(c1B.w)) == VT_BACKGROUND;
+            if (path_done) flags = 0;
+        }
+        if (live && keep && !(flags & INFO_WAIT)) action = path_done ? ACT_LIGHT : ACT_EXTEND;
+
         // ---- phase 3: the one expensive step of this iteration
         __syncwarp();   // every lane of the warp runs this loop body the same number of times (`total`)
+        float4 ro = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));   // cull < 0: no ray this iteration
         if (action == ACT_EXTEND) {
-            const float4* A = path ? b.lightA : b.camA;
-            const float4* B = path ? b.lightB : b.camB;
-            const float4 va = A[(size_t)i * b.S + slot], vb = B[(size_t)i * b.S + slot];
-            const f3 Vx = mk3(va), VN = mk3(vb);
-            const int Vprim = unpack_prim(__float_as_int(vb.w));
-            f3 prev_x;
-            if (i == 1) prev_x = path ? mk3(b.l0A[(size_t)parity * b.S + slot]) : mk3(sc.eye.x, sc.eye.y, sc.eye.z);
-            else prev_x = mk3(A[(size_t)(i - 1) * b.S + slot]);
+            const f3 Vx = mk3(VA), VN = mk3(VB);
+            const int Vprim = unpack_prim(__float_as_int(VB.w));
             const f3 w_o = s_normalize(prev_x - Vx);
             const NextSample s = sample_next_dir(sc, rng, VN, Vprim, w_o);
             const float rrProb = i > 4 ? .8f : 1.f;
             const bool rr_pass = !(rng_float(rng) > rrProb);      // drawn even when rrProb == 1 (quirk Q16)
-            b.ray_o[slot] = make_float4(Vx.x, Vx.y, Vx.z, __int_as_float(s.cull));
+            ro = make_float4(Vx.x, Vx.y, Vx.z, __int_as_float(s.cull));
             b.ray_d[slot] = make_float4(s.w_i.x, s.w_i.y, s.w_i.z, s.srpdf);
             b.pend[slot] = make_float4(s.alpha.x, s.alpha.y, s.alpha.z, 0.0f);
-            flags = INFO_PENDING | (rr_pass ? INFO_RR_PASS : 0u);
+            flags |= INFO_PENDING | (rr_pass ? INFO_RR_PASS : 0u);
         } else if (action == ACT_LIGHT) {
             // GenerateLightPath head (BDPT.cpp:61-77)
             nc = count;
@@ -346,14 +398,16 @@ __global__ void __launch_bounds__(256) k_shade(SceneView g, RenderArgs a, WfBuff
             PVert v0[1];
             const LightStart ls = light_path_head(sc, rng, sc.emissive[0], v0);
             store_vertex(b.l0A, b.l0B, b.l0C, (size_t)parity * b.S + slot, v0[0]);
+            store_vertex(b.curA, b.curB, b.curC, (size_t)slot, v0[0]);
             const f3 afac = ls.pdf1 != 0.0f ? safe_div(v0[0].alpha, ls.pdf1) : mk3(0.0f);
-            b.ray_o[slot] = make_float4(v0[0].x.x, v0[0].x.y, v0[0].x.z, __int_as_float(0));
+            ro = make_float4(v0[0].x.x, v0[0].x.y, v0[0].x.z, __int_as_float(0));
             b.ray_d[slot] = make_float4(ls.w_i.x, ls.w_i.y, ls.w_i.z, ls.pdf1);
             b.pend[slot] = make_float4(afac.x, afac.y, afac.z, 0.0f);
             path = 1; i = 0; count = 1;
             flags = INFO_PENDING | INFO_LIGHT_FIRST;
         }
         if (live) {
+            b.ray_o[slot] = ro;
             b.rng[slot] = rng;
             b.info[slot] = make_info(path, i, count, flags | (parity ? INFO_PARITY : 0u), nc);
         }
@@ -371,8 +425,8 @@ __global__ void __launch_bounds__(256) k_extend(SceneView g, RenderArgs a, WfBuf
     unsigned long long rays = 0;
     for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
         const int slot = list[q];
-        if (!(b.info[slot] & INFO_PENDING)) continue;
         const float4 o = b.ray_o[slot], d = b.ray_d[slot];
+        if (__float_as_int(o.w) < 0) continue;      // the slot emitted no ray this iteration
         DHit h;
         scene_intersect<false>(sc, make_ray(mk3(o), mk3(d)), __float_as_int(o.w), a.prune != 0, &h, nullptr);
         rays++;
@@ -394,19 +448,20 @@ __global__ void __launch_bounds__(256) k_expand(WfBuffers b) {
                     b.pair_rec[k] = make_uint2(0xffffffffu, 0u);
             continue;
         }
-        const unsigned nc = inf & 255u, nl = (inf >> 8) & 255u;
+        const unsigned nc = inf & 255u, nl = (inf >> 8) & 255u, parity = (inf >> 16) & 1u;
+        const int slot = b.done_slot[di];
         const unsigned np = nc * (nl + 1) - 1;
         // strategy order of the reference loops (BDPT.cpp:290-313): s outer, t inner, (1,0) skipped
         for (unsigned k = lane; k < np; k += 32) {
             const unsigned j = k + 1;
             const unsigned s = j / (nl + 1) + 1, t = j % (nl + 1);
-            b.pair_rec[off + k] = make_uint2(di, s | (t << 8));
+            b.pair_rec[off + k] = make_uint2((unsigned)slot, s | (t << 8) | (parity << 16));
         }
     }
 }
 
 // ---- connect: unweighted contribution, shadow-ray / MIS queueing --------------------------
-__global__ void __launch_bounds__(256) k_connect(SceneView g, WfBuffers b) {
+__global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_connect(SceneView g, WfBuffers b) {
     const SceneView sc = stage_scene(g, tpt_smem);
     const unsigned long long np_all = b.ctr->done_pairs & ((1ull << 40) - 1);
     const unsigned n = (unsigned)(np_all < b.pair_cap ? np_all : b.pair_cap);
@@ -415,9 +470,9 @@ __global__ void __launch_bounds__(256) k_connect(SceneView g, WfBuffers b) {
         bool to_shadow = false, to_mis = false;
         if (p < n && b.pair_rec[p].x != 0xffffffffu) {
             const uint2 rec = b.pair_rec[p];
-            const unsigned inf = b.done_info[rec.x];
-            const int slot = b.done_slot[rec.x];
-            const int s = rec.y & 255u, t = rec.y >> 8;
+            const int slot = (int)rec.x;
+            const int s = rec.y & 255u, t = (rec.y >> 8) & 255u;
+            const unsigned inf = rec.y;               // bit 16: light-vertex-0 parity
             const CamPath cam{b, sc, slot};
             const LightPath light{b, slot, (int)((inf >> 16) & 1u)};
             int needs_shadow;
@@ -449,9 +504,9 @@ __global__ void __launch_bounds__(256) k_shadow_q(SceneView g, RenderArgs a, WfB
         if (live) {
             p = b.shadow_q[q];
             const uint2 rec = b.pair_rec[p];
-            const unsigned inf = b.done_info[rec.x];
-            const int slot = b.done_slot[rec.x];
-            const int s = rec.y & 255u, t = rec.y >> 8;
+            const int slot = (int)rec.x;
+            const int s = rec.y & 255u, t = (rec.y >> 8) & 255u;
+            const unsigned inf = rec.y;               // bit 16: light-vertex-0 parity
             from = s == 1 ? mk3(sc.eye.x, sc.eye.y, sc.eye.z) : mk3(b.camA[(size_t)(s - 1) * b.S + slot]);
             to = t == 1 ? mk3(b.l0A[(size_t)((inf >> 16) & 1u) * b.S + slot]) : mk3(b.lightA[(size_t)(t - 1) * b.S + slot]);
             kind = __float_as_int(b.pair_val[p].w);
@@ -468,19 +523,19 @@ __global__ void __launch_bounds__(256) k_shadow_q(SceneView g, RenderArgs a, WfB
 // pixel (s > 1, BDPT.cpp:301-303 + Renderer.cpp:49) or splatted with the 3x3 tent (s == 1,
 // BDPT.cpp:304-311).  Sums are formed with float atomics: their order is not the
 // reference's loop order (neither is the reference's own splat merge across threads).
-__global__ void __launch_bounds__(256) k_mis(SceneView g, RenderArgs a, WfBuffers b, float* radiance, float* splat) {
+__global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_mis(SceneView g, RenderArgs a, WfBuffers b, float* radiance, float* splat) {
     const SceneView sc = stage_scene(g, tpt_smem);
     const unsigned n = b.ctr->n_mis;
     const float inv_spp = 1.0f / a.spp_total;
     for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
         const unsigned p = b.mis_q[q];
         const uint2 rec = b.pair_rec[p];
-        const unsigned inf = b.done_info[rec.x];
-        const int slot = b.done_slot[rec.x];
-        const int s = rec.y & 255u, t = rec.y >> 8;
+        const int slot = (int)rec.x;
+        const int s = rec.y & 255u, t = (rec.y >> 8) & 255u;
+        const unsigned inf = rec.y;                   // bit 16: light-vertex-0 parity
         const int parity = (int)((inf >> 16) & 1u);
-        const CamPath cam{b, sc, slot};
-        const LightPath light{b, slot, parity};
+        const CamPathT<false> cam{b, sc, slot};
+        const LightPathT<false> light{b, slot, parity};
         f3 w = mk3(b.pair_val[p]);
         // a Background end returns before any weighting (BDPT.cpp:180-185)
         const int endType = s == 1 ? VT_CAMERA : unpack_type(__float_as_int(b.camB[(size_t)(s - 1) * b.S + slot].w));
@@ -542,7 +597,8 @@ static int wf_alloc(TptScene* s, int S) {
               get(2 * F4, (void**)&b.l0A) && get(2 * F4, (void**)&b.l0B) && get(2 * F4, (void**)&b.l0C) &&
               get((size_t)S * 4, (void**)&b.rng) && get((size_t)S * 4, (void**)&b.info) &&
               get((size_t)S * 4, (void**)&b.spp_done) && get(F4, (void**)&b.ray_o) && get(F4, (void**)&b.ray_d) &&
-              get(F4, (void**)&b.pend) && get(F4, (void**)&b.hit) && get((size_t)S * 4, (void**)&b.active[0]) &&
+              get(F4, (void**)&b.pend) && get(F4, (void**)&b.hit) && get(F4, (void**)&b.curA) && get(F4, (void**)&b.curB) &&
+              get(F4, (void**)&b.curC) && get(F4, (void**)&b.prvA) && get(F4, (void**)&b.prvB) && get((size_t)S * 4, (void**)&b.active[0]) &&
               get((size_t)S * 4, (void**)&b.active[1]) && get((size_t)S * 4, (void**)&b.done_slot) &&
               get((size_t)S * 4, (void**)&b.done_info) && get((size_t)S * 4, (void**)&b.done_off) &&
               get(b.pair_cap * sizeof(uint2), (void**)&b.pair_rec) && get(b.pair_cap * sizeof(float4), (void**)&b.pair_val) &&
