@@ -163,6 +163,104 @@ TPT_DEV void closest_hit_range(const SceneView& sc, const DRay& r, int cull, int
     }
 }
 
+// ---- deferred leaf tests ------------------------------------------------------------------------
+// In the loop above a lane that reaches a leaf runs the (long, double precision) primitive test
+// while the other lanes of its warp wait: the test executes with two or three lanes active at
+// almost every step.  The wavefront kernels use this form instead: the walk only RECORDS the
+// leaves it reaches (in visit order, in a per-thread column of shared memory), and the tests run
+// afterwards, when every lane of the warp has its list — round k tests the k-th candidate of all
+// lanes together.  No pruning (a hit is not known during the walk): the walk visits exactly the
+// nodes BVH.cpp:103-143 visits, and the strict first-visited-wins update is applied in the
+// recorded order, so the winner is the reference's by construction.
+#define TPT_CAND_MAX 12           /* candidates recorded per ray before an in-walk flush */
+#define TPT_CAND_BYTES(threads) ((threads) * TPT_CAND_MAX * 4)
+
+TPT_DEV void settle_candidate(const SceneView& sc, const DRay& r, int cull, int prim, int& best, double& best_t) {
+    double t = 0.0;
+    bool ok;
+    if (prim < sc.n_tris) {
+        ok = triangle_test(sc, prim, r, cull, &t);
+    } else {
+        float ts = 0.0f;
+        ok = sphere_test(sc, prim - sc.n_tris, r, cull, &ts);
+        t = (double)ts;
+    }
+    if (ok && (best < 0 || best_t > t)) { best = prim; best_t = t; }
+}
+
+// cand: this thread's column (element k at cand[k * stride]).
+TPT_DEV void closest_hit_deferred(const SceneView& sc, const DRay& r, int cull, int first, int end,
+                                  int* cand, int stride, DHit* hit) {
+    double best_t = 0.0;
+    int best = -1, nc = 0;
+    int i = first;
+    while (i < end) {
+        const float4 n0 = sc.nodes[2 * i], n1 = sc.nodes[2 * i + 1];
+        float nmin;
+        const bool in = slab_test(n0, n1, r, &nmin);
+        const int prim = __float_as_int(n0.w);
+        i = in ? i + 1 : __float_as_int(n1.w);
+        if (in && prim >= 0) {
+            if (nc == TPT_CAND_MAX) {            // column full (rare): settle what is recorded, in order
+                for (int k = 0; k < TPT_CAND_MAX; ++k) settle_candidate(sc, r, cull, cand[k * stride], best, best_t);
+                nc = 0;
+            }
+            cand[nc * stride] = prim;
+            nc++;
+        }
+    }
+    for (int k = 0; k < nc; ++k) settle_candidate(sc, r, cull, cand[k * stride], best, best_t);
+    hit->prim = best;
+    hit->t = best_t;
+    if (best < 0) {
+        hit->coords = mk3(0.0f); hit->normal = mk3(0.0f);
+    } else if (best < sc.n_tris) {
+        hit->coords = x_madd(r.o, r.d, (float)best_t);
+        hit->normal = mk3(sc.tris[4 * best + 3]);
+    } else {
+        hit->coords = x_madd(r.o, r.d, (float)best_t);
+        hit->normal = x_normalize(x_sub(hit->coords, mk3(sc.spheres[2 * (best - sc.n_tris)])));
+    }
+}
+
+// Scene::ShadowCheck in the same form: record the leaves in front of the target, then test them in
+// order until one hit lies inside the limit (the any-hit argument of shadow_check applies).
+TPT_DEV bool shadow_check_deferred(const SceneView& sc, f3 from, f3 to, int cull, int* cand, int stride) {
+    const f3 d0 = x_sub(from, to);
+    const double lightDistanceSqr = dotd(d0, d0);
+    const double limit = lightDistanceSqr - 1.0;
+    const DRay r = make_ray(from, x_normalize(x_sub(to, from)));
+    const float reach = __fsqrt_rn((float)lightDistanceSqr) * 1.0001f + 1e-3f;
+    int i = 0, nc = 0;
+    const int end = sc.n_nodes;
+    bool found = false;
+    while (i < end && !found) {
+        const float4 n0 = sc.nodes[2 * i], n1 = sc.nodes[2 * i + 1];
+        float nmin;
+        const bool in = slab_test(n0, n1, r, &nmin) && !(nmin > reach);
+        const int prim = __float_as_int(n0.w);
+        i = in ? i + 1 : __float_as_int(n1.w);
+        if (in && prim >= 0) {
+            if (nc == TPT_CAND_MAX) {
+                for (int k = 0; k < TPT_CAND_MAX && !found; ++k) {
+                    int b = -1; double t = 0.0;
+                    settle_candidate(sc, r, cull, cand[k * stride], b, t);
+                    if (b >= 0) { const f3 d1 = x_sub(x_madd(r.o, r.d, (float)t), from); found = dotd(d1, d1) < limit; }
+                }
+                nc = 0;
+            }
+            cand[nc * stride] = prim;
+            nc++;
+        }
+    }
+    for (int k = 0; k < nc && !found; ++k) {
+        int b = -1; double t = 0.0;
+        settle_candidate(sc, r, cull, cand[k * stride], b, t);
+        if (b >= 0) { const f3 d1 = x_sub(x_madd(r.o, r.d, (float)t), from); found = dotd(d1, d1) < limit; }
+    }
+    return found;
+}
+
 // Scene::Intersect, Scene.cpp:21-35
 template <bool COUNT>
 TPT_DEV void scene_intersect(const SceneView& sc, const DRay& r, int cull, bool prune, DHit* hit, TravCounters* cnt) {

@@ -190,12 +190,13 @@ __device__ inline void flush_stats(unsigned long long ref_rays, unsigned long lo
 // sample: no jitter, Renderer.cpp:46) -----------------------------------------------------
 __global__ void __launch_bounds__(256) k_generate(SceneView g, RenderArgs a, WfBuffers b, unsigned long long* stats) {
     const SceneView sc = stage_scene(g, tpt_smem);
+    int* cand = reinterpret_cast<int*>(tpt_smem + ((g.stage_bytes + 15u) & ~15u)) + threadIdx.x;
     unsigned long long rays = 0;
     for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < b.S; slot += gridDim.x * blockDim.x) {
         const int pixel = a.partition == TPT_PART_INTERLEAVE ? slot * a.world + a.rank : slot;   // < npix by the choice of S
         const DRay r = make_ray(mk3(sc.eye.x, sc.eye.y, sc.eye.z), pixel_ray(sc, pixel % sc.width, pixel / sc.width));
         DHit h;
-        scene_intersect<false>(sc, r, 0, a.prune != 0, &h, nullptr);
+        closest_hit_deferred(sc, r, 0, 0, sc.n_nodes, cand, blockDim.x, &h);
         rays++;
         PVert cam[2];
         camera_path_head(sc, h, cam);
@@ -420,6 +421,7 @@ __global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_shade(SceneView g, Rende
 // ---- extend: closest hit for the rays of the active slots --------------------------------
 __global__ void __launch_bounds__(256) k_extend(SceneView g, RenderArgs a, WfBuffers b, int cur, unsigned long long* stats) {
     const SceneView sc = stage_scene(g, tpt_smem);
+    int* cand = reinterpret_cast<int*>(tpt_smem + ((g.stage_bytes + 15u) & ~15u)) + threadIdx.x;
     const unsigned n = b.ctr->n_active[cur];
     const int* list = b.active[cur];
     unsigned long long rays = 0;
@@ -428,7 +430,7 @@ __global__ void __launch_bounds__(256) k_extend(SceneView g, RenderArgs a, WfBuf
         const float4 o = b.ray_o[slot], d = b.ray_d[slot];
         if (__float_as_int(o.w) < 0) continue;      // the slot emitted no ray this iteration
         DHit h;
-        scene_intersect<false>(sc, make_ray(mk3(o), mk3(d)), __float_as_int(o.w), a.prune != 0, &h, nullptr);
+        closest_hit_deferred(sc, make_ray(mk3(o), mk3(d)), __float_as_int(o.w), 0, sc.n_nodes, cand, blockDim.x, &h);
         rays++;
         b.hit[slot] = make_float4(h.coords.x, h.coords.y, h.coords.z, __int_as_float(h.prim));
     }
@@ -492,6 +494,7 @@ __global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_connect(SceneView g, WfB
 // ---- shadow: Scene::ShadowCheck for the queued connections -------------------------------
 __global__ void __launch_bounds__(256) k_shadow_q(SceneView g, RenderArgs a, WfBuffers b, unsigned long long* stats) {
     const SceneView sc = stage_scene(g, tpt_smem);
+    int* cand = reinterpret_cast<int*>(tpt_smem + ((g.stage_bytes + 15u) & ~15u)) + threadIdx.x;
     const unsigned n = b.ctr->n_shadow;
     const unsigned total = (n + 31u) & ~31u;
     unsigned long long rays = 0;
@@ -512,7 +515,7 @@ __global__ void __launch_bounds__(256) k_shadow_q(SceneView g, RenderArgs a, WfB
             kind = __float_as_int(b.pair_val[p].w);
             rays++;
         }
-        if (live) visible = !shadow_check<false>(sc, from, to, kind == 2 ? 1 : 0, a.prune != 0, nullptr);
+        if (live) visible = !shadow_check_deferred(sc, from, to, kind == 2 ? 1 : 0, cand, blockDim.x);
         const unsigned am = wf_append(&b.ctr->n_mis, visible);
         if (visible) b.mis_q[am] = p;
     }
@@ -627,23 +630,24 @@ int wavefront_render(TptScene* s, const RenderArgs& a, float* d_radiance, float*
     WavefrontState* w = s->wf;
     WfBuffers& b = w->b;
     const unsigned smem = s->view.stage_bytes;
+    const unsigned tsmem = ((smem + 15u) & ~15u) + TPT_CAND_BYTES(256);   // traversal kernels: + candidate columns
     const int grid = std::max(1, std::min((S + 255) / 256, s->num_sms * 8));
     const int pgrid = s->num_sms * 8;      // strategy kernels: persistent, sized to the machine
     WfCounters init;
     std::memset(&init, 0, sizeof init);
     init.n_active[0] = (unsigned)S;
     TPT_CUDA(cudaMemcpyAsync(b.ctr, &init, sizeof init, cudaMemcpyHostToDevice, st));
-    tm->begin(TPT_K_GENERATE); k_generate<<<grid, 256, smem, st>>>(s->view, a, b, s->d_stats); tm->end();
+    tm->begin(TPT_K_GENERATE); k_generate<<<grid, 256, tsmem, st>>>(s->view, a, b, s->d_stats); tm->end();
     int cur = 0;
     // every sample needs at least 2 iterations; 31 is the longest a sample can take
     const long long max_iters = (long long)a.spp * 32 + 8;
     for (long long it = 0; it < max_iters; ++it) {
         k_reset_iteration<<<1, 1, 0, st>>>(b.ctr, cur ^ 1);
         tm->begin(TPT_K_SHADE); k_shade<<<grid, 256, smem, st>>>(s->view, a, b, cur, s->d_stats); tm->end();
-        tm->begin(TPT_K_EXTEND); k_extend<<<grid, 256, smem, st>>>(s->view, a, b, cur ^ 1, s->d_stats); tm->end();
+        tm->begin(TPT_K_EXTEND); k_extend<<<grid, 256, tsmem, st>>>(s->view, a, b, cur ^ 1, s->d_stats); tm->end();
         tm->begin(TPT_K_EXPAND); k_expand<<<pgrid, 256, 0, st>>>(b); tm->end();
         tm->begin(TPT_K_CONNECT); k_connect<<<pgrid, 256, smem, st>>>(s->view, b); tm->end();
-        tm->begin(TPT_K_SHADOW); k_shadow_q<<<pgrid, 256, smem, st>>>(s->view, a, b, s->d_stats); tm->end();
+        tm->begin(TPT_K_SHADOW); k_shadow_q<<<pgrid, 256, tsmem, st>>>(s->view, a, b, s->d_stats); tm->end();
         tm->begin(TPT_K_MIS); k_mis<<<pgrid, 256, smem, st>>>(s->view, a, b, d_radiance, d_splat); tm->end();
         cur ^= 1;
         if ((it & 7) == 7 || it + 1 == max_iters) {
