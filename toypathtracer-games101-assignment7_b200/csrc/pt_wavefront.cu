@@ -1,0 +1,358 @@
+// pt_wavefront.cu — PathTrace (reference PathTracer.cpp:44-134) as wavefront queues.
+//
+// One slot per pixel keeps the pixel's XorShift32 stream and runs its samples one after
+// another (Renderer.cpp:42-53).  Every iteration of the host loop runs
+//
+//   k_pt_shade   per active slot: fold the direct light of the previous vertex (its two
+//                shadow rays are back), take the extension hit (or start the next sample at
+//                the cached primary hit), add emission, BSDF-sample, sample the light, run the
+//                three light-object probes of DirectLightSampler (a 3-node walk, done in
+//                place), and queue: up to two shadow rays + the extension ray
+//   k_pt_extend  closest hit for the extension rays      } persistent grid-stride kernels,
+//   k_pt_shadow  Scene::ShadowCheck for the shadow rays  } leaf tests deferred (traverse.cuh)
+//
+// Everything a pixel adds up is added by its own slot in the reference's order, so the
+// image is bit-reproducible run to run.  The pipeline handles one emissive object (all
+// BASELINE scenes); scenes with several lights use the per-pixel kernel (tpt.cu).
+#include <algorithm>
+#include <cstring>
+
+#include "wf_common.cuh"
+
+namespace {
+
+struct PtCounters {
+    unsigned n_active[2];
+    unsigned pad[2];
+};
+
+// info bits: [0] extension ray pending  [1] direct-light record pending  [2] explicitLight
+//            [3] flip culling  [4] sample in progress  [8..31] bounces
+#define PT_EXT (1u << 0)
+#define PT_DIRECT (1u << 1)
+#define PT_EXPLICIT (1u << 2)
+#define PT_FLIP (1u << 3)
+#define PT_RUNNING (1u << 4)
+#define PT_BOUNCES(i) ((i) >> 8)
+
+struct PtBuffers {
+    int S;
+    uint32_t* rng;
+    unsigned* info;
+    unsigned* spp_done;
+    float4 *alpha, *rad, *acc;        // throughput, radiance of the running sample, pixel accumulator
+    float4 *prim_hit;                 // cached primary hit {coords, asfloat(prim)}
+    float4 *prim_dir;                 // primary ray direction
+    float4 *ray_o, *ray_d, *hit;      // extension ray {o, cull (<0: none)} {d} -> {coords, prim}
+    float4 *dl_alpha, *dl_e1, *dl_e2; // direct light of the last vertex: alpha, E1, E2 (w = 1: shadow ray queued)
+    float4 *sh_from, *sh_to;          // [2 * S]: shadow ray j of slot s at [j * S + s]; from.w < 0: none
+    unsigned* vis;                    // bit j: shadow ray j found the light visible
+    int* active[2];
+    PtCounters* ctr;
+};
+
+__global__ void __launch_bounds__(256) k_pt_generate(SceneView g, RenderArgs a, PtBuffers b, unsigned long long* stats) {
+    const SceneView sc = stage_scene(g, tpt_smem);
+    int* cand = reinterpret_cast<int*>(tpt_smem + ((g.stage_bytes + 15u) & ~15u)) + threadIdx.x;
+    unsigned long long rays = 0;
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < b.S; slot += gridDim.x * blockDim.x) {
+        const int pixel = a.partition == TPT_PART_INTERLEAVE ? slot * a.world + a.rank : slot;
+        const f3 dir = pixel_ray(sc, pixel % sc.width, pixel / sc.width);
+        DHit h;
+        closest_hit_deferred(sc, make_ray(mk3(sc.eye.x, sc.eye.y, sc.eye.z), dir), 0, 0, sc.n_nodes, cand, blockDim.x, &h);
+        rays++;
+        b.prim_hit[slot] = make_float4(h.coords.x, h.coords.y, h.coords.z, __int_as_float(h.prim));
+        b.prim_dir[slot] = make_float4(dir.x, dir.y, dir.z, 0.0f);
+        b.rng[slot] = tpt_pixel_seed(a.seed_mode, (uint32_t)pixel, (uint32_t)a.rank);
+        b.spp_done[slot] = 0;
+        b.info[slot] = 0;
+        b.acc[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+        b.vis[slot] = 0;
+        b.active[0][slot] = slot;
+    }
+    flush_stats(0, rays, 0, stats);
+}
+
+__global__ void __launch_bounds__(256, 3) k_pt_shade(SceneView g, RenderArgs a, PtBuffers b, int cur, float* radiance,
+                                                     unsigned long long* stats) {
+    const SceneView sc = stage_scene(g, tpt_smem);
+    Ctx c;
+    c.sc = sc; c.prune = true; c.cnt.node_visits = 0; c.cnt.prim_tests = 0; c.scene_rays = 0; c.probe_rays = 0;
+    const unsigned n = b.ctr->n_active[cur];
+    const int* list = b.active[cur];
+    int* next_list = b.active[cur ^ 1];
+    const bool full = a.mode == TPT_MODE_PT_FULL;
+    const float inv_spp = 1.0f / a.spp_total;
+    const int light = sc.emissive[0];
+    const Mat lightMat = load_mat(sc, sc.objs[light].material);
+    unsigned long long ref_rays = 0, samples = 0;
+    const unsigned total = (n + 31u) & ~31u;
+    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+        const bool live = q < n;
+        const int slot = live ? list[q] : 0;
+        bool keep = false, shadeNow = false;
+        unsigned info = 0, bounces = 0;
+        uint32_t rng = 0;
+        f3 alpha = mk3(1.0f), rad = mk3(0.0f), acc = mk3(0.0f);
+        f3 hx = mk3(0.0f), rdir = mk3(0.0f, 0.0f, 1.0f);
+        int hprim = -1;
+        if (live) {
+            info = b.info[slot];
+            rng = b.rng[slot];
+            const unsigned vis = b.vis[slot];
+            const float4 hr = b.hit[slot], rd = b.ray_d[slot], ph = b.prim_hit[slot], pd = b.prim_dir[slot];
+            const float4 al = b.alpha[slot], ra = b.rad[slot], ac = b.acc[slot];
+            const float4 da = b.dl_alpha[slot], e1 = b.dl_e1[slot], e2 = b.dl_e2[slot];
+            alpha = mk3(al); rad = mk3(ra); acc = mk3(ac);
+            bounces = PT_BOUNCES(info);
+            keep = true;
+
+            // ---- the direct light of the previous vertex (PathTracer.cpp:90-105), in the reference's order
+            if (info & PT_DIRECT) {
+                f3 eval_result = mk3(0.0f);
+                if (e1.w != 0.0f && (vis & 1u)) eval_result += mk3(e1);
+                if (e2.w != 0.0f && (vis & 2u)) eval_result += mk3(e2);
+                rad += (mk3(da) * eval_result) * lightMat.emission;
+            }
+
+            bool done = false;
+            if (info & PT_EXT) {
+                hprim = __float_as_int(hr.w); hx = mk3(hr); rdir = mk3(rd);
+                if (hprim < 0) done = true;                              // Background: PathTracer.cpp:58-62
+            } else if (info & PT_RUNNING) {
+                done = true;                                             // the sample ended at its last vertex
+            }
+            if (done) {
+                acc += inv_spp * rad;                                    // Renderer.cpp:51
+                ref_rays += bounces;                                     // PathTracer.cpp:126
+                samples++;
+                const unsigned d = b.spp_done[slot] + 1;
+                b.spp_done[slot] = d;
+                info = 0;
+                if ((int)d >= a.spp) {
+                    keep = false;
+                    const int pixel = a.partition == TPT_PART_INTERLEAVE ? slot * a.world + a.rank : slot;
+                    radiance[3 * (size_t)pixel] = acc.x; radiance[3 * (size_t)pixel + 1] = acc.y; radiance[3 * (size_t)pixel + 2] = acc.z;
+                }
+            }
+            if (keep && !(info & PT_RUNNING)) {
+                // next sample: the primary ray is the same for every sample (no jitter, Renderer.cpp:46)
+                alpha = mk3(1.0f); rad = mk3(0.0f); bounces = 0;
+                info = PT_RUNNING;
+                hprim = __float_as_int(ph.w); hx = mk3(ph); rdir = mk3(pd);
+                if (hprim < 0) {
+                    // the camera ray leaves the scene: the sample is empty; it completes next iteration
+                    info = PT_RUNNING;
+                    hprim = -1;
+                }
+            }
+            shadeNow = keep && hprim >= 0;
+        }
+
+        // ---- shade the vertex (one call site for the whole warp)
+        __syncwarp();
+        unsigned nflags = 0;
+        float4 ro = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        float4 s1f = make_float4(0.f, 0.f, 0.f, -1.0f), s2f = s1f;
+        if (shadeNow) {
+            const Mat mat = load_mat(sc, prim_material(sc, hprim));
+            const bool explicitLight = (info & PT_EXPLICIT) != 0;
+            if (mat.emissive && !explicitLight) rad += alpha * mat.emission;       // PathTracer.cpp:64-68
+            const f3 x = hx, w_o = -rdir, nrm = hit_normal(sc, hprim, hx);
+            float pdf_bsdf;
+            const f3 w_i_bsdf = mat_sample(mat, rng, w_o, nrm, &pdf_bsdf);          // :76
+            // ---- DirectLightSampler + MIS (:82-105); the light probes run in place
+            float pdf_light_light;
+            const f3 w_i_light = light_sample_dir(c, light, rng, x, &pdf_light_light);
+            const float pdf_light_bsdf = mat_pdf(mat, w_o, nrm, w_i_light);
+            const float pdf_bsdf_light = light_pdf<false>(c, light, x, w_i_bsdf);
+            f3 E1 = mk3(0.0f), E2 = mk3(0.0f);
+            float q1 = 0.0f, q2 = 0.0f;
+            if (pdf_bsdf + pdf_bsdf_light > 0.0f) {
+                DHit inte;
+                trace_object<false>(c, light, make_ray(x, w_i_bsdf), 0, &inte);
+                if (inte.prim >= 0) {
+                    E1 = mat_eval(mat, w_o, w_i_bsdf, nrm, true) / (TPT_EPSILON + pdf_bsdf + pdf_bsdf_light);
+                    q1 = 1.0f;
+                    s1f = make_float4(inte.coords.x, inte.coords.y, inte.coords.z, 1.0f);
+                }
+            }
+            if (pdf_light_light + pdf_light_bsdf > 0.0f) {
+                DHit inte;
+                trace_object<false>(c, light, make_ray(x, w_i_light), 0, &inte);
+                // inte.happened is not checked by the reference: a miss shadow-tests from (0,0,0)
+                E2 = mat_eval(mat, w_o, w_i_light, nrm, true) / (TPT_EPSILON + pdf_light_light + pdf_light_bsdf);
+                q2 = 1.0f;
+                s2f = make_float4(inte.coords.x, inte.coords.y, inte.coords.z, 1.0f);
+            }
+            b.dl_alpha[slot] = make_float4(alpha.x, alpha.y, alpha.z, 0.0f);
+            b.dl_e1[slot] = make_float4(E1.x, E1.y, E1.z, q1);
+            b.dl_e2[slot] = make_float4(E2.x, E2.y, E2.z, q2);
+            b.sh_to[slot] = make_float4(x.x, x.y, x.z, 0.0f);
+            nflags = PT_RUNNING | PT_DIRECT | PT_EXPLICIT;
+            if (full) {
+                // PathTracer.cpp:111-131
+                f3 weight = mk3(0.0f);
+                if (pdf_bsdf > 0.0f) weight = mat_eval(mat, w_o, w_i_bsdf, nrm, true) / (TPT_EPSILON + pdf_bsdf);
+                const bool flip = dotd(nrm, w_i_bsdf) < 0.0;
+                const bool rr = bounces > 4;
+                if (!rr || rng_float(rng) < 0.8f) {
+                    alpha = (alpha * weight) / (rr ? 0.8f : 1.0f);
+                    bounces += 1;
+                    // the loop head stops a path whose throughput is exactly zero before tracing (:54-55)
+                    if (!(alpha.x == 0.0f && alpha.y == 0.0f && alpha.z == 0.0f)) {
+                        ro = make_float4(x.x, x.y, x.z, __int_as_float(flip ? 1 : 0));
+                        b.ray_d[slot] = make_float4(w_i_bsdf.x, w_i_bsdf.y, w_i_bsdf.z, 0.0f);
+                        nflags |= PT_EXT;
+                    }
+                }
+            }
+        } else if (keep) {
+            nflags = info & PT_RUNNING;        // an empty sample (camera ray left the scene) completes next time
+        }
+        if (live) {
+            b.ray_o[slot] = ro;
+            b.sh_from[slot] = s1f;
+            b.sh_from[(size_t)b.S + slot] = s2f;
+            b.rng[slot] = rng;
+            b.alpha[slot] = make_float4(alpha.x, alpha.y, alpha.z, 0.0f);
+            b.rad[slot] = make_float4(rad.x, rad.y, rad.z, 0.0f);
+            b.acc[slot] = make_float4(acc.x, acc.y, acc.z, 0.0f);
+            b.info[slot] = nflags | (bounces << 8);
+        }
+        const unsigned at = wf_append(&b.ctr->n_active[cur ^ 1], keep);
+        if (keep) next_list[at] = slot;
+    }
+    // light probes are counted here; scene rays by the traversal kernels
+    unsigned long long v = c.probe_rays;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(stats + STAT_PROBE_RAYS, v);
+    flush_stats(ref_rays, 0, samples, stats);
+}
+
+__global__ void __launch_bounds__(256) k_pt_extend(SceneView g, PtBuffers b, int cur, unsigned long long* stats) {
+    const SceneView sc = stage_scene(g, tpt_smem);
+    int* cand = reinterpret_cast<int*>(tpt_smem + ((g.stage_bytes + 15u) & ~15u)) + threadIdx.x;
+    const unsigned n = b.ctr->n_active[cur];
+    const int* list = b.active[cur];
+    unsigned long long rays = 0;
+    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const int slot = list[q];
+        const float4 o = b.ray_o[slot], d = b.ray_d[slot];
+        if (__float_as_int(o.w) < 0) continue;
+        DHit h;
+        closest_hit_deferred(sc, make_ray(mk3(o), mk3(d)), __float_as_int(o.w), 0, sc.n_nodes, cand, blockDim.x, &h);
+        rays++;
+        b.hit[slot] = make_float4(h.coords.x, h.coords.y, h.coords.z, __int_as_float(h.prim));
+    }
+    flush_stats(0, rays, 0, stats);
+}
+
+// Two shadow-ray slots per active slot: thread 2q+j handles ray j of queue entry q.
+__global__ void __launch_bounds__(256) k_pt_shadow(SceneView g, PtBuffers b, int cur, unsigned long long* stats) {
+    const SceneView sc = stage_scene(g, tpt_smem);
+    int* cand = reinterpret_cast<int*>(tpt_smem + ((g.stage_bytes + 15u) & ~15u)) + threadIdx.x;
+    const unsigned n = b.ctr->n_active[cur];
+    const int* list = b.active[cur];
+    unsigned long long rays = 0;
+    const unsigned total = (2u * n + 31u) & ~31u;
+    for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
+        const bool live = k < 2u * n;
+        const int slot = live ? list[k >> 1] : 0;
+        const unsigned j = k & 1u;
+        bool visible = false;
+        if (live) {
+            const float4 from = b.sh_from[(size_t)j * b.S + slot];
+            if (from.w > 0.0f) {
+                const float4 to = b.sh_to[slot];
+                visible = !shadow_check_deferred(sc, mk3(from), mk3(to), 0, cand, blockDim.x);   // Scene::ShadowCheck(inte.coords, x)
+                rays++;
+            }
+        }
+        // the two lanes of a slot are neighbours: combine their bits with a shuffle, lane j == 0 writes
+        const unsigned other = __shfl_down_sync(0xffffffffu, visible ? 1u : 0u, 1);
+        if (live && j == 0) b.vis[slot] = (visible ? 1u : 0u) | (other << 1);
+    }
+    flush_stats(0, rays, 0, stats, rays);
+}
+
+__global__ void k_pt_reset(PtCounters* c, int next) { c->n_active[next] = 0; }
+
+}  // namespace
+
+struct PtWavefrontState {
+    int S = 0;
+    PtBuffers b;
+    std::vector<void*> allocs;
+    unsigned* h_flag = nullptr;
+};
+
+void pt_wavefront_destroy(TptScene* s) {
+    if (!s || !s->ptwf) return;
+    for (void* p : s->ptwf->allocs) cudaFree(p);
+    if (s->ptwf->h_flag) cudaFreeHost(s->ptwf->h_flag);
+    delete s->ptwf;
+    s->ptwf = nullptr;
+}
+
+static int pt_alloc(TptScene* s, int S) {
+    if (s->ptwf && s->ptwf->S == S) return TPT_OK;
+    pt_wavefront_destroy(s);
+    PtWavefrontState* w = new PtWavefrontState;
+    s->ptwf = w;
+    w->S = S;
+    std::memset(&w->b, 0, sizeof w->b);
+    PtBuffers& b = w->b;
+    b.S = S;
+    auto get = [&](size_t bytes, void** out) -> bool {
+        void* p = nullptr;
+        if (!tpt_cuda_ok(cudaMalloc(&p, std::max<size_t>(bytes, 16)), "cudaMalloc(pt wavefront)")) return false;
+        w->allocs.push_back(p);
+        *out = p;
+        return true;
+    };
+    const size_t F4 = (size_t)S * sizeof(float4), U = (size_t)S * 4;
+    bool ok = get(U, (void**)&b.rng) && get(U, (void**)&b.info) && get(U, (void**)&b.spp_done) &&
+              get(F4, (void**)&b.alpha) && get(F4, (void**)&b.rad) &&
+              get(F4, (void**)&b.acc) && get(F4, (void**)&b.prim_hit) && get(F4, (void**)&b.prim_dir) &&
+              get(F4, (void**)&b.ray_o) && get(F4, (void**)&b.ray_d) && get(F4, (void**)&b.hit) &&
+              get(F4, (void**)&b.dl_alpha) && get(F4, (void**)&b.dl_e1) && get(F4, (void**)&b.dl_e2) &&
+              get(2 * F4, (void**)&b.sh_from) && get(F4, (void**)&b.sh_to) && get(U, (void**)&b.vis) &&
+              get(U, (void**)&b.active[0]) && get(U, (void**)&b.active[1]) && get(sizeof(PtCounters), (void**)&b.ctr);
+    if (ok && !tpt_cuda_ok(cudaMallocHost((void**)&w->h_flag, 64), "cudaMallocHost")) ok = false;
+    if (!ok) { pt_wavefront_destroy(s); return TPT_ERR_OOM; }
+    return TPT_OK;
+}
+
+int pt_wavefront_render(TptScene* s, const RenderArgs& a, float* d_radiance, cudaStream_t st, KernelTimer* tm) {
+    const int npix = s->view.width * s->view.height;
+    const int S = a.partition == TPT_PART_INTERLEAVE ? (npix - a.rank + a.world - 1) / a.world : npix;
+    int rc = pt_alloc(s, S);
+    if (rc != TPT_OK) return rc;
+    PtWavefrontState* w = s->ptwf;
+    PtBuffers& b = w->b;
+    const unsigned smem = s->view.stage_bytes;
+    const unsigned tsmem = ((smem + 15u) & ~15u) + TPT_CAND_BYTES(256);
+    const int grid = std::max(1, std::min((S + 255) / 256, s->num_sms * 8));
+    PtCounters init;
+    std::memset(&init, 0, sizeof init);
+    init.n_active[0] = (unsigned)S;
+    TPT_CUDA(cudaMemcpyAsync(b.ctr, &init, sizeof init, cudaMemcpyHostToDevice, st));
+    tm->begin(TPT_K_GENERATE); k_pt_generate<<<grid, 256, tsmem, st>>>(s->view, a, b, s->d_stats); tm->end();
+    int cur = 0;
+    const long long max_iters = (long long)a.spp * 4096 + 8;
+    for (long long it = 0; it < max_iters; ++it) {
+        k_pt_reset<<<1, 1, 0, st>>>(b.ctr, cur ^ 1);
+        tm->begin(TPT_K_SHADE); k_pt_shade<<<grid, 256, smem, st>>>(s->view, a, b, cur, d_radiance, s->d_stats); tm->end();
+        tm->begin(TPT_K_EXTEND); k_pt_extend<<<grid, 256, tsmem, st>>>(s->view, b, cur ^ 1, s->d_stats); tm->end();
+        tm->begin(TPT_K_SHADOW); k_pt_shadow<<<grid, 256, tsmem, st>>>(s->view, b, cur ^ 1, s->d_stats); tm->end();
+        cur ^= 1;
+        if ((it & 7) == 7) {
+            TPT_CUDA(cudaMemcpyAsync(w->h_flag, &b.ctr->n_active[cur], sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            TPT_CUDA(cudaStreamSynchronize(st));
+            if (w->h_flag[0] == 0) break;
+        }
+    }
+    TPT_CUDA(cudaGetLastError());
+    return TPT_OK;
+}

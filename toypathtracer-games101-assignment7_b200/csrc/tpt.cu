@@ -245,6 +245,7 @@ extern "C" int tpt_scene_destroy(TptScene* s) {
     if (!s) return TPT_OK;
     cudaSetDevice(s->device);
     wavefront_destroy(s);
+    pt_wavefront_destroy(s);
     for (void* p : s->allocs) cudaFree(p);
     if (s->d_stats) cudaFree(s->d_stats);
     delete s;
@@ -653,8 +654,9 @@ extern "C" int tpt_render_device(TptScene* s, const TptRenderParams* p, float* d
     if (stats) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
     TPT_CUDA(cudaMemsetAsync(d_accum, 0, 2 * n3 * sizeof(float), st));
     TPT_CUDA(cudaMemsetAsync(s->d_stats, 0, STAT_COUNT * sizeof(unsigned long long), st));
-    // PathTrace has no queue pipeline yet: both pipeline values run the per-pixel kernel for the PT modes
-    if (p->pipeline == TPT_PIPE_MEGAKERNEL || a.mode != TPT_MODE_BDPT) {
+    // the PathTrace queue pipeline handles one emissive object; other light counts use the per-pixel kernel
+    const bool pt_queue_ok = s->view.n_emissive == 1;
+    if (p->pipeline == TPT_PIPE_MEGAKERNEL || (a.mode != TPT_MODE_BDPT && !pt_queue_ok)) {
         const int npix = s->view.width * s->view.height;
         const int slots = a.partition == TPT_PART_INTERLEAVE ? (npix - a.rank + a.world - 1) / a.world : npix;
         const int grid = (slots + 127) / 128;
@@ -663,7 +665,8 @@ extern "C" int tpt_render_device(TptScene* s, const TptRenderParams* p, float* d
         TPT_CUDA(cudaGetLastError());
         launches += 1;
     } else {
-        rc = wavefront_render(s, a, d_radiance, d_splat, st, &timer);
+        rc = a.mode == TPT_MODE_BDPT ? wavefront_render(s, a, d_radiance, d_splat, st, &timer)
+                                     : pt_wavefront_render(s, a, d_radiance, st, &timer);
         if (rc != TPT_OK) return rc;
         for (int k = 0; k < 8; ++k) launches += timer.launches[k];
     }

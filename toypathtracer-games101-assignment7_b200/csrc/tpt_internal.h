@@ -9,7 +9,8 @@
 #include "scene.cuh"
 #include "tpt.h"
 
-struct WavefrontState;   // wavefront.cu
+struct WavefrontState;     // wavefront.cu
+struct PtWavefrontState;   // pt_wavefront.cu
 
 struct TptScene {
     int device = 0;
@@ -19,7 +20,8 @@ struct TptScene {
     int num_sms = 0;
     int smem_optin = 0;             // max opt-in dynamic shared memory per block
     unsigned long long* d_stats = nullptr;   // 8 counters, see STAT_*
-    WavefrontState* wf = nullptr;   // lazily created work buffers of the wavefront pipeline
+    WavefrontState* wf = nullptr;   // lazily created work buffers of the BDPT wavefront pipeline
+    PtWavefrontState* ptwf = nullptr;   // ... of the PathTrace wavefront pipeline
 };
 
 enum { STAT_REF_RAYS = 0, STAT_SCENE_RAYS, STAT_PROBE_RAYS, STAT_NODE_VISITS, STAT_PRIM_TESTS, STAT_SAMPLES, STAT_SHADOW_RAYS, STAT_COUNT = 8 };
@@ -80,3 +82,7 @@ __host__ __device__ inline uint32_t tpt_pixel_seed(int seed_mode, uint32_t pixel
 int wavefront_render(TptScene* scene, const RenderArgs& a, float* d_radiance, float* d_splat,
                      cudaStream_t stream, KernelTimer* timer);
 void wavefront_destroy(TptScene* scene);
+
+// pt_wavefront.cu
+int pt_wavefront_render(TptScene* scene, const RenderArgs& a, float* d_radiance, cudaStream_t stream, KernelTimer* timer);
+void pt_wavefront_destroy(TptScene* scene);

@@ -23,10 +23,7 @@
 #include <cstdio>
 #include <cstring>
 
-#include "integrators.cuh"
-#include "tpt_internal.h"
-
-extern __shared__ __align__(16) unsigned char tpt_smem[];
+#include "wf_common.cuh"
 
 #ifndef WF_MIN_BLOCKS
 #define WF_MIN_BLOCKS 4   // resident 256-thread CTAs per SM the shading kernels are compiled for
@@ -88,10 +85,6 @@ struct WfBuffers {
     unsigned *shadow_q, *mis_q;
     WfCounters* ctr;
 };
-
-TPT_DEV int pack_pt(int prim, int type) { return ((prim + 1) << 2) | type; }
-TPT_DEV int unpack_prim(int p) { return (p >> 2) - 1; }
-TPT_DEV int unpack_type(int p) { return p & 3; }
 
 TPT_DEV void store_vertex(float4* A, float4* B, float4* C, size_t at, const PVert& v) {
     A[at] = make_float4(v.x.x, v.x.y, v.x.z, v.pdf);
@@ -155,36 +148,6 @@ struct LightAux {
         return make_float2(b.lightA[at].w, b.lightC[at].w);
     }
 };
-
-// Warp-aggregated queue append: one atomicAdd per warp, order inside the warp kept.
-TPT_DEV unsigned wf_append(unsigned* counter, bool want) {
-    const unsigned mask = __ballot_sync(0xffffffffu, want);
-    if (mask == 0) return 0;
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned leader = __ffs(mask) - 1;
-    unsigned base = 0;
-    if (lane == leader) base = atomicAdd(counter, __popc(mask));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    return base + __popc(mask & ((1u << lane) - 1u));
-}
-
-TPT_DEV f3 hit_normal(const SceneView& sc, int prim, f3 coords) {
-    if (prim < sc.n_tris) return mk3(sc.tris[4 * prim + 3]);
-    return x_normalize(x_sub(coords, mk3(sc.spheres[2 * (prim - sc.n_tris)])));
-}
-
-__device__ inline void flush_stats(unsigned long long ref_rays, unsigned long long scene_rays,
-                                   unsigned long long samples, unsigned long long* stats,
-                                   unsigned long long shadow_rays = 0) {
-    unsigned long long v[4] = {ref_rays, scene_rays, samples, shadow_rays};
-    const int idx[4] = {STAT_REF_RAYS, STAT_SCENE_RAYS, STAT_SAMPLES, STAT_SHADOW_RAYS};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        unsigned long long x = v[k];
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if ((threadIdx.x & 31) == 0 && x) atomicAdd(stats + idx[k], x);
-    }
-}
 
 // ---- generate: primary ray + hit, once per pixel (the primary ray is the same for every
 // sample: no jitter, Renderer.cpp:46) -----------------------------------------------------
