@@ -126,7 +126,8 @@ enum { TPT_SEED_REF = 0, TPT_SEED_SPLIT = 1 };
 /* How the frame is shared between `world` cooperating calls (one per GPU). */
 enum {
     TPT_PART_ALL = 0,        /* this call renders every pixel (spp is this call's share) */
-    TPT_PART_INTERLEAVE = 1  /* pixels i with i % world == rank, like Renderer.cpp:38    */
+    TPT_PART_INTERLEAVE = 1, /* pixels i with i % world == rank, like Renderer.cpp:38    */
+    TPT_PART_BLOCK = 2       /* the rank-th of `world` contiguous runs of pixels (tiles of rows) */
 };
 
 /* Scheduling of the work on the device. */

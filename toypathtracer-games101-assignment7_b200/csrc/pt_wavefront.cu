@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) k_pt_generate(SceneView g, RenderArgs a, 
     int* cand = reinterpret_cast<int*>(tpt_smem + ((g.stage_bytes + 15u) & ~15u)) + threadIdx.x;
     unsigned long long rays = 0;
     for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < b.S; slot += gridDim.x * blockDim.x) {
-        const int pixel = a.partition == TPT_PART_INTERLEAVE ? slot * a.world + a.rank : slot;
+        const int pixel = tpt_slot_pixel(a, sc.width * sc.height, slot);
         const f3 dir = pixel_ray(sc, pixel % sc.width, pixel / sc.width);
         DHit h;
         closest_hit_deferred(sc, make_ray(mk3(sc.eye.x, sc.eye.y, sc.eye.z), dir), 0, 0, sc.n_nodes, cand, blockDim.x, &h);
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(256, 3) k_pt_shade(SceneView g, RenderArgs a, 
                 info = 0;
                 if ((int)d >= a.spp) {
                     keep = false;
-                    const int pixel = a.partition == TPT_PART_INTERLEAVE ? slot * a.world + a.rank : slot;
+                    const int pixel = tpt_slot_pixel(a, sc.width * sc.height, slot);
                     radiance[3 * (size_t)pixel] = acc.x; radiance[3 * (size_t)pixel + 1] = acc.y; radiance[3 * (size_t)pixel + 2] = acc.z;
                 }
             }
@@ -326,7 +326,7 @@ static int pt_alloc(TptScene* s, int S) {
 
 int pt_wavefront_render(TptScene* s, const RenderArgs& a, float* d_radiance, cudaStream_t st, KernelTimer* tm) {
     const int npix = s->view.width * s->view.height;
-    const int S = a.partition == TPT_PART_INTERLEAVE ? (npix - a.rank + a.world - 1) / a.world : npix;
+    const int S = tpt_part_slots(a, npix);
     int rc = pt_alloc(s, S);
     if (rc != TPT_OK) return rc;
     PtWavefrontState* w = s->ptwf;

@@ -553,8 +553,7 @@ __global__ void __launch_bounds__(128) k_render_mega(SceneView g, RenderArgs a, 
     const SceneView& sc = c.sc;
     const int npix = sc.width * sc.height;
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    int pixel = slot;
-    if (a.partition == TPT_PART_INTERLEAVE) pixel = slot * a.world + a.rank;
+    const int pixel = slot < tpt_part_slots(a, npix) ? tpt_slot_pixel(a, npix, slot) : npix;
     unsigned long long ref_rays = 0, samples = 0;
     if (pixel < npix) {
         uint32_t rng = tpt_pixel_seed(a.seed_mode, (uint32_t)pixel, (uint32_t)a.rank);
@@ -658,7 +657,7 @@ extern "C" int tpt_render_device(TptScene* s, const TptRenderParams* p, float* d
     const bool pt_queue_ok = s->view.n_emissive == 1;
     if (p->pipeline == TPT_PIPE_MEGAKERNEL || (a.mode != TPT_MODE_BDPT && !pt_queue_ok)) {
         const int npix = s->view.width * s->view.height;
-        const int slots = a.partition == TPT_PART_INTERLEAVE ? (npix - a.rank + a.world - 1) / a.world : npix;
+        const int slots = tpt_part_slots(a, npix);
         const int grid = (slots + 127) / 128;
         if (a.count_visits) k_render_mega<true><<<grid, 128, s->view.stage_bytes, st>>>(s->view, a, d_radiance, d_splat, s->d_stats);
         else k_render_mega<false><<<grid, 128, s->view.stage_bytes, st>>>(s->view, a, d_radiance, d_splat, s->d_stats);

@@ -78,6 +78,24 @@ __host__ __device__ inline uint32_t tpt_pixel_seed(int seed_mode, uint32_t pixel
     return h ? h : 0x6D2B79F5u;
 }
 
+// Pixels of this call: how many slots it needs and which pixel a slot renders.
+//   TPT_PART_ALL         every pixel
+//   TPT_PART_INTERLEAVE  pixels i with i % world == rank (Renderer.cpp:38)
+//   TPT_PART_BLOCK       the rank-th of `world` contiguous runs of pixels (rows of tiles)
+__host__ __device__ inline int tpt_part_begin(const RenderArgs& a, int npix) {
+    return a.partition == TPT_PART_BLOCK ? (int)((long long)npix * a.rank / a.world) : 0;
+}
+__host__ __device__ inline int tpt_part_slots(const RenderArgs& a, int npix) {
+    if (a.partition == TPT_PART_INTERLEAVE) return (npix - a.rank + a.world - 1) / a.world;
+    if (a.partition == TPT_PART_BLOCK) return (int)((long long)npix * (a.rank + 1) / a.world) - tpt_part_begin(a, npix);
+    return npix;
+}
+__host__ __device__ inline int tpt_slot_pixel(const RenderArgs& a, int npix, int slot) {
+    if (a.partition == TPT_PART_INTERLEAVE) return slot * a.world + a.rank;
+    if (a.partition == TPT_PART_BLOCK) return tpt_part_begin(a, npix) + slot;
+    return slot;
+}
+
 // wavefront.cu
 int wavefront_render(TptScene* scene, const RenderArgs& a, float* d_radiance, float* d_splat,
                      cudaStream_t stream, KernelTimer* timer);

@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(256) k_generate(SceneView g, RenderArgs a, WfB
     int* cand = reinterpret_cast<int*>(tpt_smem + ((g.stage_bytes + 15u) & ~15u)) + threadIdx.x;
     unsigned long long rays = 0;
     for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < b.S; slot += gridDim.x * blockDim.x) {
-        const int pixel = a.partition == TPT_PART_INTERLEAVE ? slot * a.world + a.rank : slot;   // < npix by the choice of S
+        const int pixel = tpt_slot_pixel(a, sc.width * sc.height, slot);   // < npix by the choice of S
         const DRay r = make_ray(mk3(sc.eye.x, sc.eye.y, sc.eye.z), pixel_ray(sc, pixel % sc.width, pixel / sc.width));
         DHit h;
         closest_hit_deferred(sc, r, 0, 0, sc.n_nodes, cand, blockDim.x, &h);
@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_mis(SceneView g, RenderA
         w = mk3(std_max(w.x, 0.0f), std_max(w.y, 0.0f), std_max(w.z, 0.0f));   // BDPT.cpp:299
         if (s > 1) {
             if (w.x != 0.0f || w.y != 0.0f || w.z != 0.0f) {
-                const int pixel = a.partition == TPT_PART_INTERLEAVE ? slot * a.world + a.rank : slot;
+                const int pixel = tpt_slot_pixel(a, sc.width * sc.height, slot);
                 float* px = radiance + 3 * (size_t)pixel;
                 atomicAdd(px, inv_spp * w.x); atomicAdd(px + 1, inv_spp * w.y); atomicAdd(px + 2, inv_spp * w.z);
             }
@@ -587,7 +587,7 @@ int wavefront_render(TptScene* s, const RenderArgs& a, float* d_radiance, float*
                      KernelTimer* tm) {
     if (a.mode != TPT_MODE_BDPT) { tpt_set_error("wavefront_render handles BDPT only"); return TPT_ERR_INVALID; }
     const int npix = s->view.width * s->view.height;
-    const int S = a.partition == TPT_PART_INTERLEAVE ? (npix - a.rank + a.world - 1) / a.world : npix;   // pixels i with i % world == rank
+    const int S = tpt_part_slots(a, npix);
     int rc = wf_alloc(s, S);
     if (rc != TPT_OK) return rc;
     WavefrontState* w = s->wf;
