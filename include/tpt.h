@@ -119,8 +119,8 @@ enum { TPT_MODE_PT_SHIPPED = 0, TPT_MODE_PT_FULL = 1, TPT_MODE_BDPT = 2 };
 
 /* Seeding.  REF: ResetRandom(pixel+1) once per pixel, the spp of a pixel drawn
  * one after another from that stream (Renderer.cpp:42-53) — images converge to
- * the reference's sample by sample.  SPLIT: the stream of (pixel, rank) starts
- * from a hashed seed, for spp-split multi-GPU runs (statistical parity only). */
+ * the reference's sample by sample.  SPLIT: the stream of (pixel, params.stream)
+ * starts from a hashed seed, for spp-split multi-GPU runs (statistical parity only). */
 enum { TPT_SEED_REF = 0, TPT_SEED_SPLIT = 1 };
 
 /* How the frame is shared between `world` cooperating calls (one per GPU). */
@@ -145,6 +145,8 @@ typedef struct TptRenderParams {
     int32_t rank, world; /* 0,1 for a single GPU                                     */
     int32_t pipeline;    /* TPT_PIPE_*                                               */
     int32_t flags;       /* TPT_FLAG_*                                               */
+    int32_t stream;      /* TPT_SEED_SPLIT: which independent sample set of its pixels this
+                            call draws (the spp group of a tile x spp split); ignored by REF */
 } TptRenderParams;
 
 enum {
@@ -185,6 +187,18 @@ int         tpt_device_count(void);
  * (Triangle.cpp:69-74) as a device-resident, 128-bit packed scene on `device`. */
 int tpt_scene_create(const TptSceneDesc* desc, int device, TptScene** out);
 int tpt_scene_destroy(TptScene* scene);
+
+/* Device work buffers (path store, queues, frame accumulators) are cached between calls
+ * instead of going back to the driver; this returns every cached block.  The reference
+ * keeps its framebuffer / emission buffers as std::vectors for the length of Render
+ * (Renderer.cpp:72-74,37); here they outlive the call so that a short render is not
+ * dominated by cudaMalloc / cudaFree. */
+int tpt_release_cached_memory(void);
+
+/* Page-locked host memory for the frame tpt_render writes (a plain malloc'ed buffer works
+ * too, through the driver's staging copy).  NULL on failure. */
+void* tpt_host_alloc(size_t bytes);
+void  tpt_host_free(void* p);
 
 /* ---- the exact tier ----------------------------------------------------- */
 

@@ -100,7 +100,7 @@ def test_spp_split_seeding_is_statistically_equivalent(tpt):
     ref, _ = s.render("pt_full", 64)
     acc = np.zeros_like(ref)
     for r in range(4):
-        img, _ = s.render("pt_full", 16, spp_total=64, seed_mode=tpt.SEED_SPLIT, rank=r, world=4)
+        img, _ = s.render("pt_full", 16, spp_total=64, seed_mode=tpt.SEED_SPLIT, stream=r)
         acc += img
     assert np.allclose(acc.mean((0, 1)), ref.mean((0, 1)), rtol=0.01)
     assert not np.allclose(acc, ref)          # different streams

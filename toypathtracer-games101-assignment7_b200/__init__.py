@@ -25,7 +25,7 @@ MODE_PT_SHIPPED, MODE_PT_FULL, MODE_BDPT = 0, 1, 2
 MODES = {"pt_shipped": MODE_PT_SHIPPED, "pt_full": MODE_PT_FULL, "bdpt": MODE_BDPT}
 CULL_BACK, CULL_FRONT, NO_CULL = 0, 1, 2
 SEED_REF, SEED_SPLIT = 0, 1
-PART_ALL, PART_INTERLEAVE = 0, 1
+PART_ALL, PART_INTERLEAVE, PART_BLOCK = 0, 1, 2
 PIPE_WAVEFRONT, PIPE_MEGAKERNEL = 0, 1
 FLAG_REF_TRAVERSAL, FLAG_COUNT_VISITS, FLAG_KERNEL_TIMES = 1, 2, 4
 KERNEL_NAMES = ("generate", "shade", "extend", "expand", "connect", "shadow", "mis", "accumulate")
@@ -55,7 +55,7 @@ class SceneDesc(C.Structure):
 class RenderParams(C.Structure):
     _fields_ = [("mode", C.c_int32), ("spp", C.c_int32), ("spp_total", C.c_int32), ("seed_mode", C.c_int32),
                 ("partition", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32), ("pipeline", C.c_int32),
-                ("flags", C.c_int32)]
+                ("flags", C.c_int32), ("stream", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -92,6 +92,9 @@ def lib():
         _lib = C.CDLL(LIBTPT, mode=C.RTLD_GLOBAL)
         _lib.tpt_last_error.restype = C.c_char_p
         _lib.tpt_accum_floats.restype = C.c_size_t
+        _lib.tpt_host_alloc.restype = C.c_void_p
+        _lib.tpt_host_alloc.argtypes = [C.c_size_t]
+        _lib.tpt_host_free.argtypes = [C.c_void_p]
     return _lib
 
 
@@ -260,15 +263,18 @@ class Scene:
 
     # -- render -----------------------------------------------------------------
     def params(self, mode, spp, spp_total=0, seed_mode=SEED_REF, partition=PART_ALL, rank=0, world=1,
-               pipeline=PIPE_WAVEFRONT, flags=0):
+               pipeline=PIPE_WAVEFRONT, flags=0, stream=0):
         if isinstance(mode, str):
             mode = MODES[mode]
-        return RenderParams(mode, spp, spp_total, seed_mode, partition, rank, world, pipeline, flags)
+        return RenderParams(mode, spp, spp_total, seed_mode, partition, rank, world, pipeline, flags, stream)
 
-    def render(self, mode, spp, **kw):
-        """tpt_render: host buffer out, returns (image[h,w,3] float32, stats dict)."""
+    def render(self, mode, spp, out=None, **kw):
+        """tpt_render: host buffer out, returns (image[h,w,3] float32, stats dict).
+        `out` may be a pinned_image() of this scene's size (no staging copy on the way back)."""
         p = self.params(mode, spp, **kw)
-        out = np.empty((self.height, self.width, 3), np.float32)
+        if out is None:
+            out = np.empty((self.height, self.width, 3), np.float32)
+        assert out.dtype == np.float32 and out.shape == (self.height, self.width, 3) and out.flags["C_CONTIGUOUS"]
         st = Stats()
         _check(lib().tpt_render(self.h, C.byref(p), _p(out), C.byref(st)))
         return out, st.as_dict()
@@ -287,6 +293,27 @@ class Scene:
     def finalize_device(self, d_accum_ptr, d_out_ptr, d_rgb8_ptr=None, stream=None):
         _check(lib().tpt_finalize_device(self.h, C.c_void_p(d_accum_ptr), C.c_void_p(d_out_ptr or 0),
                                          C.c_void_p(d_rgb8_ptr or 0), C.c_void_p(stream or 0)))
+
+
+class PinnedImage:
+    """A height x width x 3 float32 frame in page-locked host memory (tpt_host_alloc)."""
+
+    def __init__(self, height, width):
+        n = height * width * 3 * 4
+        self.ptr = lib().tpt_host_alloc(C.c_size_t(n))
+        if not self.ptr:
+            raise TptError("tpt_host_alloc failed: %s" % lib().tpt_last_error().decode())
+        self.array = np.frombuffer((C.c_char * n).from_address(self.ptr), dtype=np.float32).reshape(height, width, 3)
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            lib().tpt_host_free(C.c_void_p(self.ptr))
+            self.ptr = None
+
+
+def release_cached_memory():
+    _check(lib().tpt_release_cached_memory())
 
 
 def rng(seed, n):

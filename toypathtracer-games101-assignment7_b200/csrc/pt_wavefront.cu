@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) k_pt_generate(SceneView g, RenderArgs a, 
         rays++;
         b.prim_hit[slot] = make_float4(h.coords.x, h.coords.y, h.coords.z, __int_as_float(h.prim));
         b.prim_dir[slot] = make_float4(dir.x, dir.y, dir.z, 0.0f);
-        b.rng[slot] = tpt_pixel_seed(a.seed_mode, (uint32_t)pixel, (uint32_t)a.rank);
+        b.rng[slot] = tpt_pixel_seed(a.seed_mode, (uint32_t)pixel, (uint32_t)a.stream);
         b.spp_done[slot] = 0;
         b.info[slot] = 0;
         b.acc[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -289,8 +289,8 @@ struct PtWavefrontState {
 
 void pt_wavefront_destroy(TptScene* s) {
     if (!s || !s->ptwf) return;
-    for (void* p : s->ptwf->allocs) cudaFree(p);
-    if (s->ptwf->h_flag) cudaFreeHost(s->ptwf->h_flag);
+    for (void* p : s->ptwf->allocs) tpt_dev_free(p);
+    if (s->ptwf->h_flag) tpt_pinned_free(s->ptwf->h_flag);
     delete s->ptwf;
     s->ptwf = nullptr;
 }
@@ -305,8 +305,8 @@ static int pt_alloc(TptScene* s, int S) {
     PtBuffers& b = w->b;
     b.S = S;
     auto get = [&](size_t bytes, void** out) -> bool {
-        void* p = nullptr;
-        if (!tpt_cuda_ok(cudaMalloc(&p, std::max<size_t>(bytes, 16)), "cudaMalloc(pt wavefront)")) return false;
+        void* p = tpt_dev_alloc(bytes);
+        if (!p) return false;
         w->allocs.push_back(p);
         *out = p;
         return true;
@@ -319,7 +319,7 @@ static int pt_alloc(TptScene* s, int S) {
               get(F4, (void**)&b.dl_alpha) && get(F4, (void**)&b.dl_e1) && get(F4, (void**)&b.dl_e2) &&
               get(2 * F4, (void**)&b.sh_from) && get(F4, (void**)&b.sh_to) && get(U, (void**)&b.vis) &&
               get(U, (void**)&b.active[0]) && get(U, (void**)&b.active[1]) && get(sizeof(PtCounters), (void**)&b.ctr);
-    if (ok && !tpt_cuda_ok(cudaMallocHost((void**)&w->h_flag, 64), "cudaMallocHost")) ok = false;
+    if (ok && !(w->h_flag = static_cast<unsigned*>(tpt_pinned_alloc(64)))) ok = false;
     if (!ok) { pt_wavefront_destroy(s); return TPT_ERR_OOM; }
     return TPT_OK;
 }

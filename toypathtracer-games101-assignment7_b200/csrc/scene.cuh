@@ -17,9 +17,10 @@
 //   mats[4*m+0..3]   = { emission | asfloat(type) } { Kd | rough } { ior_m | ior_d } { ior_m_k | asfloat(emissive?) }
 //   objs[k]          = per Scene::objects entry: root / end node of its subtree, areas, material
 //   lnodes[n]        = BVHAccel::getSample tree of the meshes (left, right, triangle, area)
-// A whole Cornell scene is 4-5 KB: every kernel copies it into shared memory
-// (SceneView::stage) and traverses it there; larger scenes stay in global memory
-// and are served by L1/L2.
+// All arrays are sections of ONE device allocation (the "scene blob"), so a whole Cornell
+// scene (4-6 KB) is brought into shared memory by a single bulk asynchronous copy per
+// block (stage_scene) and traversed there; larger scenes stay in global memory and are
+// served by L1/L2.
 #pragma once
 
 #include "vec.cuh"
@@ -58,48 +59,48 @@ struct SceneView {
     float aspect;             // (float)(width / height): integer division, SceneRenderingHelper.cpp:17
     float3 eye;
     float3 background;
-    unsigned stage_bytes;     // bytes stage() needs; 0 = do not stage (scene too large)
+    const unsigned char* blob;   // the arrays above are sections of this one allocation, in this order
+    unsigned blob_bytes;         // multiple of 16
+    unsigned stage_bytes;        // = blob_bytes when the blob is staged in shared memory; 0 = too large
 };
 
-// Total bytes of the read-only arrays, 16-byte granular.
-__host__ __device__ inline unsigned scene_stage_bytes(const SceneView& s) {
-    unsigned b = 0;
-    b += (unsigned)s.n_nodes * 32u;
-    b += (unsigned)s.n_tris * 96u;
-    b += (unsigned)s.n_spheres * 32u;
-    b += (unsigned)s.n_mats * 64u;
-    b += (unsigned)s.n_objs * 48u;
-    b += (((unsigned)s.n_lnodes * 16u) + 15u) & ~15u;
-    b += (((unsigned)s.n_emissive * 4u) + 15u) & ~15u;
-    return b;
-}
-
-// Copy the scene arrays into dynamic shared memory (128-bit loads, whole block) and
-// return a view whose pointers address that copy.  Call from every thread; ends with
-// __syncthreads().  With stage_bytes == 0 the global view is returned untouched.
+// Copy the scene blob into dynamic shared memory and return a view whose pointers address that
+// copy.  Call from every thread of the block; ends with a block-wide wait.  With stage_bytes == 0
+// the global view is returned untouched.
+//
+// The copy is ONE bulk asynchronous copy (TMA, cp.async.bulk -> UBLKCP in SASS): thread 0 arms an
+// mbarrier with the byte count and issues the copy, every thread waits on the barrier's phase.
 __device__ inline SceneView stage_scene(const SceneView& g, unsigned char* smem) {
     if (g.stage_bytes == 0) return g;
-    SceneView s = g;
-    float4* dst = reinterpret_cast<float4*>(smem);
-    unsigned off = 0;   // in float4 units
-    auto put = [&](const void* src, unsigned bytes) -> const float4* {
-        const unsigned n = (bytes + 15u) / 16u;
-        const float4* from = reinterpret_cast<const float4*>(src);
-#pragma unroll 1
-        for (unsigned i = threadIdx.x; i < n; i += blockDim.x) dst[off + i] = __ldg(from + i);
-        const float4* at = dst + off;
-        off += n;
-        return at;
-    };
-    s.nodes = put(g.nodes, (unsigned)g.n_nodes * 32u);
-    s.tris = put(g.tris, (unsigned)g.n_tris * 64u);
-    s.tverts = put(g.tverts, (unsigned)g.n_tris * 32u);
-    s.spheres = put(g.spheres, (unsigned)g.n_spheres * 32u);
-    s.mats = put(g.mats, (unsigned)g.n_mats * 64u);
-    s.objs = reinterpret_cast<const DevObject*>(put(g.objs, (unsigned)g.n_objs * 48u));
-    s.lnodes = reinterpret_cast<const DevLightNode*>(put(g.lnodes, (unsigned)g.n_lnodes * 16u));
-    s.emissive = reinterpret_cast<const int*>(put(g.emissive, (unsigned)g.n_emissive * 4u));
+    __shared__ __align__(8) unsigned long long stage_bar;
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&stage_bar);
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(g.stage_bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(g.blob), "r"(g.stage_bytes), "r"(bar) : "memory");
+    }
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar) : "memory");
+    }
+    SceneView s = g;
+    // every array keeps its offset inside the blob
+    auto move = [&](const void* p) { return smem + (unsigned)(reinterpret_cast<const unsigned char*>(p) - g.blob); };
+    s.nodes = reinterpret_cast<const float4*>(move(g.nodes));
+    s.tris = reinterpret_cast<const float4*>(move(g.tris));
+    s.tverts = reinterpret_cast<const float4*>(move(g.tverts));
+    s.spheres = reinterpret_cast<const float4*>(move(g.spheres));
+    s.mats = reinterpret_cast<const float4*>(move(g.mats));
+    s.objs = reinterpret_cast<const DevObject*>(move(g.objs));
+    s.lnodes = reinterpret_cast<const DevLightNode*>(move(g.lnodes));
+    s.emissive = reinterpret_cast<const int*>(move(g.emissive));
     return s;
 }
 

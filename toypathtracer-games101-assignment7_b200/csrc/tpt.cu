@@ -7,6 +7,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 
 #include "integrators.cuh"
 #include "tpt_internal.h"
@@ -19,6 +21,81 @@ bool tpt_cuda_ok(cudaError_t e, const char* what) {
     tpt_set_error(std::string(what) + ": " + cudaGetErrorString(e));
     return false;
 }
+
+// ------------------------------------------------------------------ caching allocator
+namespace {
+struct BlockCache {
+    std::mutex mu;
+    std::map<std::pair<int, size_t>, std::vector<void*>> free_dev;   // (device, bytes) -> blocks
+    std::map<void*, std::pair<int, size_t>> live_dev;
+    std::map<size_t, std::vector<void*>> free_pinned;
+    std::map<void*, size_t> live_pinned;
+};
+BlockCache& cache() { static BlockCache* c = new BlockCache; return *c; }   // never destroyed: outlives every scene
+size_t round_block(size_t bytes) { return (std::max<size_t>(bytes, 16) + 255) & ~size_t(255); }
+}  // namespace
+
+void* tpt_dev_alloc(size_t bytes) {
+    bytes = round_block(bytes);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    BlockCache& c = cache();
+    std::lock_guard<std::mutex> lock(c.mu);
+    std::vector<void*>& fl = c.free_dev[std::make_pair(dev, bytes)];
+    void* p = nullptr;
+    if (!fl.empty()) { p = fl.back(); fl.pop_back(); }
+    else if (!tpt_cuda_ok(cudaMalloc(&p, bytes), "cudaMalloc")) return nullptr;
+    c.live_dev[p] = std::make_pair(dev, bytes);
+    return p;
+}
+void tpt_dev_free(void* p) {
+    if (!p) return;
+    BlockCache& c = cache();
+    std::lock_guard<std::mutex> lock(c.mu);
+    auto it = c.live_dev.find(p);
+    if (it == c.live_dev.end()) return;
+    c.free_dev[it->second].push_back(p);
+    c.live_dev.erase(it);
+}
+void* tpt_pinned_alloc(size_t bytes) {
+    bytes = round_block(bytes);
+    BlockCache& c = cache();
+    std::lock_guard<std::mutex> lock(c.mu);
+    std::vector<void*>& fl = c.free_pinned[bytes];
+    void* p = nullptr;
+    if (!fl.empty()) { p = fl.back(); fl.pop_back(); }
+    else if (!tpt_cuda_ok(cudaMallocHost(&p, bytes), "cudaMallocHost")) return nullptr;
+    c.live_pinned[p] = bytes;
+    return p;
+}
+void tpt_pinned_free(void* p) {
+    if (!p) return;
+    BlockCache& c = cache();
+    std::lock_guard<std::mutex> lock(c.mu);
+    auto it = c.live_pinned.find(p);
+    if (it == c.live_pinned.end()) return;
+    c.free_pinned[it->second].push_back(p);
+    c.live_pinned.erase(it);
+}
+extern "C" int tpt_release_cached_memory(void) {
+    BlockCache& c = cache();
+    std::lock_guard<std::mutex> lock(c.mu);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    for (auto& kv : c.free_dev) {
+        cudaSetDevice(kv.first.first);
+        for (void* p : kv.second) cudaFree(p);
+        kv.second.clear();
+    }
+    cudaSetDevice(dev);
+    for (auto& kv : c.free_pinned) {
+        for (void* p : kv.second) cudaFreeHost(p);
+        kv.second.clear();
+    }
+    return TPT_OK;
+}
+extern "C" void* tpt_host_alloc(size_t bytes) { return tpt_pinned_alloc(bytes); }
+extern "C" void tpt_host_free(void* p) { tpt_pinned_free(p); }
 
 extern "C" int tpt_abi_version(void) { return TPT_ABI_VERSION; }
 extern "C" const char* tpt_last_error(void) { return g_last_error.c_str(); }
@@ -102,14 +179,28 @@ struct HostBuild {
     }
 };
 
-template <class T> int upload(TptScene* s, const std::vector<T>& host, const T** dev) {
-    void* p = nullptr;
-    const size_t bytes = std::max<size_t>(host.size() * sizeof(T), 16);
-    TPT_CUDA(cudaMalloc(&p, bytes));
-    s->allocs.push_back(p);
-    TPT_CUDA(cudaMemset(p, 0, bytes));
-    if (!host.empty()) TPT_CUDA(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
-    *dev = reinterpret_cast<const T*>(p);
+// Appends one array to the scene blob (16-byte granular) and returns its byte offset.
+template <class T> size_t blob_put(std::vector<unsigned char>& blob, const std::vector<T>& host) {
+    const size_t off = blob.size();
+    const size_t bytes = (host.size() * sizeof(T) + 15) & ~size_t(15);
+    blob.resize(off + bytes, 0);
+    if (!host.empty()) std::memcpy(blob.data() + off, host.data(), host.size() * sizeof(T));
+    return off;
+}
+
+struct DeviceInfo { int num_sms, smem_optin; };
+int device_info(int device, DeviceInfo* out) {      // cudaGetDeviceProperties costs milliseconds: ask once
+    static std::mutex mu;
+    static std::map<int, DeviceInfo> known;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = known.find(device);
+    if (it == known.end()) {
+        DeviceInfo d;
+        TPT_CUDA(cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, device));
+        TPT_CUDA(cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        it = known.emplace(device, d).first;
+    }
+    *out = it->second;
     return TPT_OK;
 }
 
@@ -203,21 +294,34 @@ extern "C" int tpt_scene_create(const TptSceneDesc* d, int device, TptScene** ou
     int rc = require_device(device);
     if (rc != TPT_OK) return rc;
 
+    // one blob, one allocation, one host->device copy: the arrays in the order stage_scene expects
+    std::vector<unsigned char> blob;
+    const size_t o_nodes = blob_put(blob, hb.nodes), o_tris = blob_put(blob, tris), o_tverts = blob_put(blob, tverts),
+                 o_spheres = blob_put(blob, spheres), o_mats = blob_put(blob, mats), o_objs = blob_put(blob, hb.objs),
+                 o_lnodes = blob_put(blob, lnodes), o_emissive = blob_put(blob, emissive);
     TptScene* s = new TptScene;
     s->device = device;
     s->n_prims = d->n_tris + d->n_spheres;
     SceneView& v = s->view;
     std::memset(&v, 0, sizeof v);
-    rc = upload(s, hb.nodes, &v.nodes);
-    if (rc == TPT_OK) rc = upload(s, tris, &v.tris);
-    if (rc == TPT_OK) rc = upload(s, tverts, &v.tverts);
-    if (rc == TPT_OK) rc = upload(s, spheres, &v.spheres);
-    if (rc == TPT_OK) rc = upload(s, mats, &v.mats);
-    if (rc == TPT_OK) rc = upload(s, hb.objs, &v.objs);
-    if (rc == TPT_OK) rc = upload(s, lnodes, &v.lnodes);
-    if (rc == TPT_OK) rc = upload(s, emissive, &v.emissive);
-    if (rc == TPT_OK && !tpt_cuda_ok(cudaMalloc(&s->d_stats, STAT_COUNT * sizeof(unsigned long long)), "cudaMalloc stats")) rc = TPT_ERR_CUDA;
-    if (rc != TPT_OK) { tpt_scene_destroy(s); return rc; }
+    unsigned char* dblob = static_cast<unsigned char*>(tpt_dev_alloc(blob.size()));
+    s->d_stats = static_cast<unsigned long long*>(tpt_dev_alloc(STAT_COUNT * sizeof(unsigned long long)));
+    if (!dblob || !s->d_stats) { if (dblob) tpt_dev_free(dblob); tpt_scene_destroy(s); return TPT_ERR_OOM; }
+    s->allocs.push_back(dblob);
+    if (!tpt_cuda_ok(cudaMemcpy(dblob, blob.data(), blob.size(), cudaMemcpyHostToDevice), "cudaMemcpy(scene)")) {
+        tpt_scene_destroy(s);
+        return TPT_ERR_CUDA;
+    }
+    v.blob = dblob;
+    v.blob_bytes = (unsigned)blob.size();
+    v.nodes = reinterpret_cast<const float4*>(dblob + o_nodes);
+    v.tris = reinterpret_cast<const float4*>(dblob + o_tris);
+    v.tverts = reinterpret_cast<const float4*>(dblob + o_tverts);
+    v.spheres = reinterpret_cast<const float4*>(dblob + o_spheres);
+    v.mats = reinterpret_cast<const float4*>(dblob + o_mats);
+    v.objs = reinterpret_cast<const DevObject*>(dblob + o_objs);
+    v.lnodes = reinterpret_cast<const DevLightNode*>(dblob + o_lnodes);
+    v.emissive = reinterpret_cast<const int*>(dblob + o_emissive);
     v.n_nodes = (int)hb.nodes.size() / 2; v.n_tris = d->n_tris; v.n_spheres = d->n_spheres;
     v.n_mats = d->n_materials; v.n_objs = d->n_objects; v.n_lnodes = d->n_mesh_nodes; v.n_emissive = d->n_emissive;
     v.width = d->width; v.height = d->height;
@@ -231,12 +335,11 @@ extern "C" int tpt_scene_create(const TptSceneDesc* d, int device, TptScene** ou
     v.aspect = (float)(d->width / d->height);
     v.eye = make_float3(d->eye.x, d->eye.y, d->eye.z);
     v.background = make_float3(d->background.x, d->background.y, d->background.z);
-    cudaDeviceProp prop;
-    cudaGetDeviceProperties(&prop, device);
-    s->num_sms = prop.multiProcessorCount;
-    s->smem_optin = (int)prop.sharedMemPerBlockOptin;
-    const unsigned need = scene_stage_bytes(v);
-    v.stage_bytes = need <= 40u * 1024u ? need : 0u;   // larger scenes are read through L1/L2
+    DeviceInfo di;
+    if ((rc = device_info(device, &di)) != TPT_OK) { tpt_scene_destroy(s); return rc; }
+    s->num_sms = di.num_sms;
+    s->smem_optin = di.smem_optin;
+    v.stage_bytes = v.blob_bytes <= 40u * 1024u ? v.blob_bytes : 0u;   // larger scenes are read through L1/L2
     *out = s;
     return TPT_OK;
 }
@@ -244,10 +347,11 @@ extern "C" int tpt_scene_create(const TptSceneDesc* d, int device, TptScene** ou
 extern "C" int tpt_scene_destroy(TptScene* s) {
     if (!s) return TPT_OK;
     cudaSetDevice(s->device);
+    cudaDeviceSynchronize();       // blocks go back to the cache: nothing may still be reading them
     wavefront_destroy(s);
     pt_wavefront_destroy(s);
-    for (void* p : s->allocs) cudaFree(p);
-    if (s->d_stats) cudaFree(s->d_stats);
+    for (void* p : s->allocs) tpt_dev_free(p);
+    if (s->d_stats) tpt_dev_free(s->d_stats);
     delete s;
     return TPT_OK;
 }
@@ -259,8 +363,8 @@ namespace {
 
 struct DevBuf {
     void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    int alloc(size_t bytes) { return tpt_cuda_ok(cudaMalloc(&p, std::max<size_t>(bytes, 16)), "cudaMalloc") ? TPT_OK : TPT_ERR_CUDA; }
+    ~DevBuf() { if (p) tpt_dev_free(p); }    // every user synchronises before it goes out of scope
+    int alloc(size_t bytes) { p = tpt_dev_alloc(bytes); return p ? TPT_OK : TPT_ERR_OOM; }
     int from_host(const void* h, size_t bytes) {
         int rc = alloc(bytes);
         if (rc != TPT_OK) return rc;
@@ -556,7 +660,7 @@ __global__ void __launch_bounds__(128) k_render_mega(SceneView g, RenderArgs a, 
     const int pixel = slot < tpt_part_slots(a, npix) ? tpt_slot_pixel(a, npix, slot) : npix;
     unsigned long long ref_rays = 0, samples = 0;
     if (pixel < npix) {
-        uint32_t rng = tpt_pixel_seed(a.seed_mode, (uint32_t)pixel, (uint32_t)a.rank);
+        uint32_t rng = tpt_pixel_seed(a.seed_mode, (uint32_t)pixel, (uint32_t)a.stream);
         const float inv_spp = 1.0f / a.spp_total;
         const DRay primary = make_ray(mk3(sc.eye.x, sc.eye.y, sc.eye.z), pixel_ray(sc, pixel % sc.width, pixel / sc.width));
         f3 acc = mk3(0.0f);
@@ -629,6 +733,8 @@ static int check_params(const TptScene* s, const TptRenderParams* p, RenderArgs*
     if (p->mode == TPT_MODE_BDPT && s->view.n_emissive == 0) { tpt_set_error("BDPT needs an emissive object (BDPT.cpp:287)"); return TPT_ERR_INVALID; }
     a->mode = p->mode; a->spp = p->spp; a->spp_total = p->spp_total > 0 ? p->spp_total : p->spp;
     a->seed_mode = p->seed_mode; a->partition = p->partition; a->rank = p->rank; a->world = world;
+    a->stream = p->stream;
+    if (p->partition < TPT_PART_ALL || p->partition > TPT_PART_BLOCK) { tpt_set_error("unknown partition"); return TPT_ERR_INVALID; }
     a->prune = (p->flags & TPT_FLAG_REF_TRAVERSAL) ? 0 : 1;
     a->count_visits = (p->flags & TPT_FLAG_COUNT_VISITS) ? 1 : 0;
     a->kernel_times = (p->flags & TPT_FLAG_KERNEL_TIMES) ? 1 : 0;

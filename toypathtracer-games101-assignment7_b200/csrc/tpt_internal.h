@@ -28,7 +28,7 @@ enum { STAT_REF_RAYS = 0, STAT_SCENE_RAYS, STAT_PROBE_RAYS, STAT_NODE_VISITS, ST
 
 struct RenderArgs {
     int mode, spp, spp_total;
-    int seed_mode, partition, rank, world;
+    int seed_mode, partition, rank, world, stream;
     int prune, count_visits, kernel_times;
 };
 
@@ -67,13 +67,22 @@ struct KernelTimer {
 
 void tpt_set_error(const std::string& msg);
 bool tpt_cuda_ok(cudaError_t e, const char* what);
+
+// Caching allocator (tpt.cu).  The render path allocates a few large work buffers per call; a
+// cudaMalloc/cudaFree pair per call costs more than the kernels of a short render, so freed blocks
+// are kept per (device, size) and handed out again.  tpt_release_cached_memory() returns them to
+// the driver.  Blocks are only recycled after the work that used them has been synchronised.
+void* tpt_dev_alloc(size_t bytes);      // on the current device; nullptr + tpt_last_error on failure
+void tpt_dev_free(void* p);
+void* tpt_pinned_alloc(size_t bytes);   // page-locked host memory, cached the same way
+void tpt_pinned_free(void* p);
 #define TPT_CUDA(call) do { if (!tpt_cuda_ok((call), #call)) return TPT_ERR_CUDA; } while (0)
 
 // Per-pixel stream seed.  REF: pixel + 1 (Renderer.cpp:42).  SPLIT: a hash of
-// (pixel, rank) that is never zero (XorShift32 is stuck at zero).
-__host__ __device__ inline uint32_t tpt_pixel_seed(int seed_mode, uint32_t pixel, uint32_t rank) {
+// (pixel, stream) that is never zero (XorShift32 is stuck at zero).
+__host__ __device__ inline uint32_t tpt_pixel_seed(int seed_mode, uint32_t pixel, uint32_t stream) {
     if (seed_mode == TPT_SEED_REF) return pixel + 1u;
-    uint32_t h = pixel * 0x9E3779B1u + (rank + 1u) * 0x85EBCA77u;
+    uint32_t h = pixel * 0x9E3779B1u + (stream + 1u) * 0x85EBCA77u;
     h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
     return h ? h : 0x6D2B79F5u;
 }

@@ -59,6 +59,29 @@ TPT_DEV bool slab_test(const float4 lo, const float4 hi, const DRay& r, float* n
     return nmax > 0.0f && nmin <= nmax;
 }
 
+// The same test when no product can be NaN: the compare-and-swap / std::max / std::min chain
+// then returns exactly min / max of its operands, which FMNMX computes in one instruction each
+// (signed zeros aside, which no comparison here can tell apart).  NaN needs 0 * inf: an infinite
+// reciprocal (a zero or denormal direction component) against a zero difference, or a non-finite
+// origin; ray_is_plain() rules both out.
+TPT_DEV bool ray_is_plain(const DRay& r) {
+    const float big = fmaxf(fmaxf(fabsf(r.inv.x), fabsf(r.inv.y)), fabsf(r.inv.z));
+    const float far = fmaxf(fmaxf(fabsf(r.o.x), fabsf(r.o.y)), fabsf(r.o.z));
+    return big < INFINITY && far < INFINITY;      // false for NaN as well
+}
+TPT_DEV bool slab_test_plain(const float4 lo, const float4 hi, const DRay& r, float* nmin_out) {
+    const float ax = __fmul_rn(__fsub_rn(lo.x, r.o.x), r.inv.x), bx = __fmul_rn(__fsub_rn(hi.x, r.o.x), r.inv.x);
+    const float ay = __fmul_rn(__fsub_rn(lo.y, r.o.y), r.inv.y), by = __fmul_rn(__fsub_rn(hi.y, r.o.y), r.inv.y);
+    const float az = __fmul_rn(__fsub_rn(lo.z, r.o.z), r.inv.z), bz = __fmul_rn(__fsub_rn(hi.z, r.o.z), r.inv.z);
+    const float nmin = fmaxf(fmaxf(fmaxf(FLT_MIN, fminf(ax, bx)), fminf(ay, by)), fminf(az, bz));
+    const float nmax = fminf(fminf(fminf(FLT_MAX, fmaxf(ax, bx)), fmaxf(ay, by)), fmaxf(az, bz));
+    *nmin_out = nmin;
+    return nmax > 0.0f && nmin <= nmax;
+}
+template <bool PLAIN> TPT_DEV bool slab_test_t(const float4 lo, const float4 hi, const DRay& r, float* nmin_out) {
+    return PLAIN ? slab_test_plain(lo, hi, r, nmin_out) : slab_test(lo, hi, r, nmin_out);
+}
+
 // Triangle::GetIntersection, reference Triangle.cpp:77-118.  Returns true and fills
 // *t on a hit; the hit point / normal are produced by the caller for the winner only.
 TPT_DEV bool triangle_test(const SceneView& sc, int prim, const DRay& r, int cull, double* t_out) {
@@ -126,11 +149,13 @@ TPT_DEV void closest_hit_range(const SceneView& sc, const DRay& r, int cull, int
     int best = -1;
     float prune_t = FLT_MAX;
     int i = first;
+    const bool plain = ray_is_plain(r);
     while (i < end) {     // one back edge, no `continue`: the warp reconverges every iteration
         const float4 n0 = sc.nodes[2 * i], n1 = sc.nodes[2 * i + 1];
         if (COUNT) cnt->node_visits++;
         float nmin;
-        const bool in = slab_test(n0, n1, r, &nmin) && !(nmin > prune_t);   // prune_t stays FLT_MAX unless pruning
+        const bool in = (plain ? slab_test_plain(n0, n1, r, &nmin) : slab_test(n0, n1, r, &nmin)) &&
+                        !(nmin > prune_t);   // prune_t stays FLT_MAX unless pruning
         const int prim = __float_as_int(n0.w);
         i = in ? i + 1 : __float_as_int(n1.w);       // descend (a leaf's miss link is i+1 too) or skip the subtree
         if (in && prim >= 0) {
@@ -188,16 +213,16 @@ TPT_DEV void settle_candidate(const SceneView& sc, const DRay& r, int cull, int 
     if (ok && (best < 0 || best_t > t)) { best = prim; best_t = t; }
 }
 
-// cand: this thread's column (element k at cand[k * stride]).
-TPT_DEV void closest_hit_deferred(const SceneView& sc, const DRay& r, int cull, int first, int end,
-                                  int* cand, int stride, DHit* hit) {
-    double best_t = 0.0;
-    int best = -1, nc = 0;
+// The walk of closest_hit_deferred: records the leaves the ray reaches; a full column is settled in place.
+template <bool PLAIN>
+TPT_DEV int walk_record(const SceneView& sc, const DRay& r, int cull, int first, int end, int* cand, int stride,
+                        int& best, double& best_t) {
+    int nc = 0;
     int i = first;
     while (i < end) {
         const float4 n0 = sc.nodes[2 * i], n1 = sc.nodes[2 * i + 1];
         float nmin;
-        const bool in = slab_test(n0, n1, r, &nmin);
+        const bool in = slab_test_t<PLAIN>(n0, n1, r, &nmin);
         const int prim = __float_as_int(n0.w);
         i = in ? i + 1 : __float_as_int(n1.w);
         if (in && prim >= 0) {
@@ -209,6 +234,16 @@ TPT_DEV void closest_hit_deferred(const SceneView& sc, const DRay& r, int cull, 
             nc++;
         }
     }
+    return nc;
+}
+
+// cand: this thread's column (element k at cand[k * stride]).
+TPT_DEV void closest_hit_deferred(const SceneView& sc, const DRay& r, int cull, int first, int end,
+                                  int* cand, int stride, DHit* hit) {
+    double best_t = 0.0;
+    int best = -1;
+    const int nc = ray_is_plain(r) ? walk_record<true>(sc, r, cull, first, end, cand, stride, best, best_t)
+                                   : walk_record<false>(sc, r, cull, first, end, cand, stride, best, best_t);
     for (int k = 0; k < nc; ++k) settle_candidate(sc, r, cull, cand[k * stride], best, best_t);
     hit->prim = best;
     hit->t = best_t;
@@ -225,39 +260,45 @@ TPT_DEV void closest_hit_deferred(const SceneView& sc, const DRay& r, int cull, 
 
 // Scene::ShadowCheck in the same form: record the leaves in front of the target, then test them in
 // order until one hit lies inside the limit (the any-hit argument of shadow_check applies).
-TPT_DEV bool shadow_check_deferred(const SceneView& sc, f3 from, f3 to, int cull, int* cand, int stride) {
-    const f3 d0 = x_sub(from, to);
-    const double lightDistanceSqr = dotd(d0, d0);
-    const double limit = lightDistanceSqr - 1.0;
-    const DRay r = make_ray(from, x_normalize(x_sub(to, from)));
-    const float reach = __fsqrt_rn((float)lightDistanceSqr) * 1.0001f + 1e-3f;
+TPT_DEV bool shadow_candidate(const SceneView& sc, const DRay& r, int cull, int prim, f3 from, double limit) {
+    int b = -1; double t = 0.0;
+    settle_candidate(sc, r, cull, prim, b, t);
+    if (b < 0) return false;
+    const f3 d1 = x_sub(x_madd(r.o, r.d, (float)t), from);
+    return dotd(d1, d1) < limit;
+}
+template <bool PLAIN>
+TPT_DEV int shadow_walk_record(const SceneView& sc, const DRay& r, int cull, f3 from, double limit, float reach,
+                               int* cand, int stride, bool& found) {
     int i = 0, nc = 0;
     const int end = sc.n_nodes;
-    bool found = false;
     while (i < end && !found) {
         const float4 n0 = sc.nodes[2 * i], n1 = sc.nodes[2 * i + 1];
         float nmin;
-        const bool in = slab_test(n0, n1, r, &nmin) && !(nmin > reach);
+        const bool in = slab_test_t<PLAIN>(n0, n1, r, &nmin) && !(nmin > reach);
         const int prim = __float_as_int(n0.w);
         i = in ? i + 1 : __float_as_int(n1.w);
         if (in && prim >= 0) {
             if (nc == TPT_CAND_MAX) {
-                for (int k = 0; k < TPT_CAND_MAX && !found; ++k) {
-                    int b = -1; double t = 0.0;
-                    settle_candidate(sc, r, cull, cand[k * stride], b, t);
-                    if (b >= 0) { const f3 d1 = x_sub(x_madd(r.o, r.d, (float)t), from); found = dotd(d1, d1) < limit; }
-                }
+                for (int k = 0; k < TPT_CAND_MAX && !found; ++k) found = shadow_candidate(sc, r, cull, cand[k * stride], from, limit);
                 nc = 0;
             }
             cand[nc * stride] = prim;
             nc++;
         }
     }
-    for (int k = 0; k < nc && !found; ++k) {
-        int b = -1; double t = 0.0;
-        settle_candidate(sc, r, cull, cand[k * stride], b, t);
-        if (b >= 0) { const f3 d1 = x_sub(x_madd(r.o, r.d, (float)t), from); found = dotd(d1, d1) < limit; }
-    }
+    return nc;
+}
+TPT_DEV bool shadow_check_deferred(const SceneView& sc, f3 from, f3 to, int cull, int* cand, int stride) {
+    const f3 d0 = x_sub(from, to);
+    const double lightDistanceSqr = dotd(d0, d0);
+    const double limit = lightDistanceSqr - 1.0;
+    const DRay r = make_ray(from, x_normalize(x_sub(to, from)));
+    const float reach = __fsqrt_rn((float)lightDistanceSqr) * 1.0001f + 1e-3f;
+    bool found = false;
+    const int nc = ray_is_plain(r) ? shadow_walk_record<true>(sc, r, cull, from, limit, reach, cand, stride, found)
+                                   : shadow_walk_record<false>(sc, r, cull, from, limit, reach, cand, stride, found);
+    for (int k = 0; k < nc && !found; ++k) found = shadow_candidate(sc, r, cull, cand[k * stride], from, limit);
     return found;
 }
 
@@ -319,11 +360,12 @@ TPT_DEV bool shadow_check(const SceneView& sc, f3 from, f3 to, int cull, bool pr
     int i = 0;
     const int end = sc.n_nodes;
     bool found = false;
+    const bool plain = ray_is_plain(r);
     while (i < end && !found) {
         const float4 n0 = sc.nodes[2 * i], n1 = sc.nodes[2 * i + 1];
         if (COUNT) cnt->node_visits++;
         float nmin;
-        const bool in = slab_test(n0, n1, r, &nmin) && !(nmin > reach);
+        const bool in = (plain ? slab_test_plain(n0, n1, r, &nmin) : slab_test(n0, n1, r, &nmin)) && !(nmin > reach);
         const int prim = __float_as_int(n0.w);
         i = in ? i + 1 : __float_as_int(n1.w);
         if (in && prim >= 0) {

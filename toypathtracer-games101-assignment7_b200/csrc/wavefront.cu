@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(256) k_generate(SceneView g, RenderArgs a, WfB
         PVert cam[2];
         camera_path_head(sc, h, cam);
         store_vertex(b.camA, b.camB, b.camC, (size_t)1 * b.S + slot, cam[1]);
-        b.rng[slot] = tpt_pixel_seed(a.seed_mode, (uint32_t)pixel, (uint32_t)a.rank);
+        b.rng[slot] = tpt_pixel_seed(a.seed_mode, (uint32_t)pixel, (uint32_t)a.stream);
         b.spp_done[slot] = 0;
         b.info[slot] = make_info(0, 1, 2, 0, 0);
         b.active[0][slot] = slot;
@@ -548,8 +548,8 @@ static int wf_alloc(TptScene* s, int S) {
     WfBuffers& b = w->b;
     b.S = S;
     auto get = [&](size_t bytes, void** out) -> bool {
-        void* p = nullptr;
-        if (!tpt_cuda_ok(cudaMalloc(&p, std::max<size_t>(bytes, 16)), "cudaMalloc(wavefront)")) return false;
+        void* p = tpt_dev_alloc(bytes);
+        if (!p) return false;
         w->allocs.push_back(p);
         *out = p;
         return true;
@@ -570,15 +570,15 @@ static int wf_alloc(TptScene* s, int S) {
               get(b.pair_cap * sizeof(uint2), (void**)&b.pair_rec) && get(b.pair_cap * sizeof(float4), (void**)&b.pair_val) &&
               get(b.pair_cap * 4, (void**)&b.shadow_q) && get(b.pair_cap * 4, (void**)&b.mis_q) &&
               get(sizeof(WfCounters), (void**)&b.ctr);
-    if (ok && !tpt_cuda_ok(cudaMallocHost((void**)&w->h_flag, 64), "cudaMallocHost")) ok = false;
+    if (ok && !(w->h_flag = static_cast<unsigned*>(tpt_pinned_alloc(64)))) ok = false;
     if (!ok) { wavefront_destroy(s); return TPT_ERR_OOM; }
     return TPT_OK;
 }
 
 void wavefront_destroy(TptScene* s) {
     if (!s || !s->wf) return;
-    for (void* p : s->wf->allocs) cudaFree(p);
-    if (s->wf->h_flag) cudaFreeHost(s->wf->h_flag);
+    for (void* p : s->wf->allocs) tpt_dev_free(p);
+    if (s->wf->h_flag) tpt_pinned_free(s->wf->h_flag);
     delete s->wf;
     s->wf = nullptr;
 }
