@@ -51,6 +51,16 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0}, "fallback"
 
 
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the traversal kernels, from the committed
+    ncu capture of this workload (profiles/traffic.json, written by tools/ncu_traffic.py); None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)["traversal_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
 
@@ -190,15 +200,16 @@ def main():
     accum = torch.zeros(scene.accum_floats(), dtype=torch.float32, device="cuda")
     out = torch.zeros(n3, dtype=torch.float32, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
-    kw = dict(spp_total=SPP * world, seed_mode=T.SEED_SPLIT if world > 1 else T.SEED_REF, rank=rank, world=world)
+    import importlib
+    D = importlib.import_module("tpt_b200.distributed")
+    # weak scaling: every rank draws SPP samples of every pixel from its own streams ("spp" shares of SPP * world)
+    share = D.plan("spp", rank, world, SPP * world, W * H)
+    kw = share.params()
 
     def step(flags=0, want_stats=False):
-        st = scene.render_device(MODE, SPP, accum.data_ptr(), stream=stream, want_stats=want_stats, flags=flags, **kw)
-        if world > 1:
-            dist.reduce(accum, dst=0)               # one NCCL sum over NVLink: [radiance | splat]
-        if rank == 0:
-            scene.finalize_device(accum.data_ptr(), out.data_ptr(), stream=stream)
-        return st
+        # this rank's share -> ONE NCCL sum-reduce of [radiance | splat] over NVLink -> merge on rank 0
+        return D.render_frame(scene, MODE, SPP * world, accum, out, strategy="spp", rank=rank, world=world,
+                              stream=stream, flags=flags, want_stats=want_stats)
 
     def barrier():
         if world > 1:
@@ -274,7 +285,7 @@ def main():
                     "h2d_bytes_per_step": scene_bytes, "d2h_bytes_per_step": n3 * 4, "ms_per_step": e2e_ms},
             "gpu_launches": int(st["launches"]) * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": measured_traffic(), "peak_source": peak_src,
                          "kernel": "k_extend + k_shadow_q + k_generate (BVH traversal)",
                          "algorithmic_bytes_per_ray": BYTES_PER_RAY, "rays_per_step": rays,
                          "kernel_ms_per_step": trav_ms, "share_of_kernel_time": trav_ms / total_k if total_k else None,

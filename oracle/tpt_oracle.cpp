@@ -5,7 +5,7 @@
 // the flat TptSceneDesc arrays of include/tpt.h.  Every function cites the
 // reference file:line it follows.  It is pinned against the compiled reference
 // itself (oracle/_ref/libtptref.so, built by oracle/build_ref.sh) and against the
-// committed golden vectors in tests/golden/ — see tests/test_oracle_vs_ref.py.
+// committed golden vectors in tests/golden/ — see tests/test_oracle.py.
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load
 // liboracle.so.  The product (libtpt.so) never links, loads or calls it.

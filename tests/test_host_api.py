@@ -1,10 +1,12 @@
 """The product's host API (Scene / MeshTriangle / Sphere / BVHAccel, host/tpt_api.hpp) builds,
 node for node and bit for bit, the trees the reference builds — the tree shape is the tie
 order of the closest-hit query."""
+import os
+
 import numpy as np
 import pytest
 
-from conftest import desc_from_golden, golden
+from conftest import ROOT, desc_from_golden, golden
 from oracle import bindings as B
 
 SCENES = ["standard", "smooth", "silver", "refractive", "occlusion", "bunny"]
@@ -65,3 +67,19 @@ def test_obj_reader_variants(tpt, tmp_path):
     ta = B.desc_arrays(B.SceneDesc.from_buffer_copy(bytes(a)))["tris"]
     tb = B.desc_arrays(B.SceneDesc.from_buffer_copy(bytes(b)))["tris"]
     assert (ta == tb).all()
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/main.cpp"), reason="reference sources not present")
+def test_reference_main_compiles_unchanged(tpt, tmp_path):
+    """The drop-in claim of INTEGRATION.md level 1: the reference's own main.cpp (scene script + CLI,
+    main.cpp:36-151) compiles and links, unmodified, against host/*.hpp + the two product libraries.
+    (Fed through stdin so that its quoted includes resolve to the drop-in headers.)"""
+    import subprocess
+    pkg = os.path.dirname(tpt.LIBTPT)
+    exe = str(tmp_path / "RayTracing_b200")
+    with open("/root/reference/main.cpp", "rb") as src:
+        r = subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(pkg, "host"), "-I", os.path.join(ROOT, "include"),
+                            "-x", "c++", "-", "-o", exe, "-L", pkg, "-ltpt_host", "-ltpt", "-Wl,-rpath," + pkg],
+                           stdin=src, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert os.path.exists(exe)
