@@ -191,8 +191,8 @@ TPT_DEV f3 path_trace(Ctx& c, uint32_t& rng, DRay ray, bool full, int* outBounce
 TPT_DEV float srpdf_to_area(float srpdf, f3 x1, f3 N1, int type1, f3 x2, f3 N2, int type2) {
     float distSqr;
     const f3 w = s_normalize_len2(x2 - x1, &distSqr);
-    const float cos1 = type1 == VT_CAMERA ? 1.0f : (float)fabs(dotd(w, N1));
-    const float cos2 = type2 == VT_CAMERA ? 1.0f : (float)fabs(dotd(-w, N2));
+    const float cos1 = type1 == VT_CAMERA ? 1.0f : fabsf(dotf(w, N1));
+    const float cos2 = type2 == VT_CAMERA ? 1.0f : fabsf(dotf(w, N2));
     return srpdf * fabsf(cos1 * cos2 / distSqr);
 }
 
@@ -294,7 +294,7 @@ TPT_DEV float append_pdf_base(const SceneView& sc, const PVert& L, int Ltype, f3
     float distSqr;
     const f3 w = s_normalize_len2(vx - L.x, &distSqr);
     const f3 NL = Ltype == VT_CAMERA ? mk3(0.0f, 0.0f, 1.0f) : L.N;
-    const float cosine = (float)fabs(dotd(w, NL));
+    const float cosine = fabsf(dotf(w, NL));
     float srpdf;
     if (Ltype == VT_LIGHT) srpdf = safe_div(cosine_pdf(NL, w), cosine);
     else if (Ltype == VT_CAMERA) srpdf = CAMERA_RAY_PDF;
@@ -304,8 +304,8 @@ TPT_DEV float append_pdf_base(const SceneView& sc, const PVert& L, int Ltype, f3
         const Mat mat = load_mat(sc, prim_material(sc, L.prim));
         srpdf = safe_div(mat_pdf(mat, wo, NL, w), cosine);
     }
-    const float cos1 = Ltype == VT_CAMERA ? 1.0f : (float)fabs(dotd(w, L.N));
-    const float cos2 = vtype == VT_CAMERA ? 1.0f : (float)fabs(dotd(-w, vN));
+    const float cos1 = Ltype == VT_CAMERA ? 1.0f : cosine;
+    const float cos2 = vtype == VT_CAMERA ? 1.0f : fabsf(dotf(w, vN));
     return srpdf * fabsf(cos1 * cos2 / distSqr);
 }
 // ... and with it: vertex number `count` of the temporary path (BDPT.cpp:162-165).
@@ -347,9 +347,9 @@ TPT_DEV f3 connect_unweighted(const SceneView& sc, const CamPath& cam, int s, co
         // Le(z1) * (N . w_i), BDPT.cpp:189-195
         if (z1.prim < 0) return mk3(0.0f);
         const Mat mat = load_mat(sc, prim_material(sc, z1.prim));
-        if (dotd(mat.emission, mat.emission) == 0.0) return mk3(0.0f);
+        if (mat.emission.x == 0.0f && mat.emission.y == 0.0f && mat.emission.z == 0.0f) return mk3(0.0f);   // |Le|^2 == 0
         const f3 w_i = s_normalize(cam.pos(s - 2) - z1.x);
-        const f3 c_st = mat.emission * (float)dotd(vert_normal(z1), w_i);
+        const f3 c_st = mat.emission * dotf(vert_normal(z1), w_i);
         return (mk3(1.0f) * z1.alpha) * c_st;
     }
     const PVert y = light(t - 1);
@@ -359,7 +359,7 @@ TPT_DEV f3 connect_unweighted(const SceneView& sc, const CamPath& cam, int s, co
     *needs_shadow = shadow_query_kind(sc, z1, y);
     const f3 fl = vertex_bsdf(sc, y, t >= 2 ? light.pos(t - 2) : mk3(0.0f), dir_ltoc);
     const f3 fc = vertex_bsdf(sc, z1, s >= 2 ? cam.pos(s - 2) : mk3(0.0f), -dir_ltoc);
-    const float g = (float)fabs(dotd(vert_normal(y), dir_ltoc) * dotd(vert_normal(z1), -dir_ltoc) / (double)distSqr);
+    const float g = fabsf(dotf(vert_normal(y), dir_ltoc) * dotf(vert_normal(z1), dir_ltoc) / distSqr);
     const f3 c_st = (fl * fc) * g;
     return (y.alpha * z1.alpha) * c_st;
 }

@@ -63,7 +63,7 @@ TPT_DEV f3 cosine_sample(uint32_t& rng, f3 N, float* pdf) {                     
     sincosf(theta, &sn, &cs);
     const float x = r * cs, y = r * sn;
     const f3 wi = s_normalize(to_world(mk3(x, y, sqrtf(1.0f - u1)), N));
-    *pdf = (float)(dotd(wi, N) / (double)TPT_PI);   // double / float -> double, then narrowed
+    *pdf = dotf(wi, N) / TPT_PI;
     return wi;
 }
 
@@ -113,7 +113,7 @@ TPT_DEV f3 mat_fresnel(const Mat& m, f3 I, f3 N) {                     // fresne
         return 0.5f * (Rp + Rs);
     }
     I = -I;
-    float cosi = (float)std_clampd(dotd(I, N), -1., 1.);
+    float cosi = std_clamp(dotf(I, N), -1.f, 1.f);
     float etai = 1, etat = m.ior_d;
     if (cosi > 0) { float s = etai; etai = etat; etat = s; }
     const float sint = etai / etat * sqrtf(std_max(0.f, __fsub_rn(1.0f, __fmul_rn(cosi, cosi))));
@@ -132,7 +132,7 @@ TPT_DEV f3 mat_eval(const Mat& m, f3 wo, f3 wi, f3 N, bool combineCosineTerm) {
     const float nv = dotf(N, wo);
     if (nl == 0.0f || nv == 0.0f) return mk3(0.0f);
     const f3 h = half_dir(N, wi, wo, m.ior_d, nl, nv);
-    const float nh = dotf(N, h);
+    const float nh = dotf_exact(N, h);      // GGX D is hypersensitive to cos(theta_h) for the near-specular materials
     const float lh = dotf(wi, h);
     const float vh = dotf(wo, h);
     const float D = ggx_term(nh, m.rough);

@@ -91,47 +91,6 @@ TPT_DEV void store_vertex(float4* A, float4* B, float4* C, size_t at, const PVer
     B[at] = make_float4(v.N.x, v.N.y, v.N.z, __int_as_float(pack_pt(v.prim, v.type)));
     C[at] = make_float4(v.alpha.x, v.alpha.y, v.alpha.z, 0.0f);
 }
-TPT_DEV PVert load_vertex(const float4* A, const float4* B, const float4* C, size_t at, bool alpha) {
-    const float4 a = A[at], b = B[at];
-    PVert v;
-    v.x = mk3(a); v.pdf = a.w; v.N = mk3(b);
-    const int p = __float_as_int(b.w);
-    v.prim = unpack_prim(p); v.type = unpack_type(p);
-    v.alpha = alpha ? mk3(C[at]) : mk3(0.0f);
-    return v;
-}
-TPT_DEV PVert camera_vertex(const SceneView& sc) {
-    PVert v;
-    v.type = VT_CAMERA; v.x = mk3(sc.eye.x, sc.eye.y, sc.eye.z); v.N = mk3(0.0f); v.prim = -1;
-    v.pdf = CAMERA_ZERO_PDF; v.alpha = mk3(1.0f);
-    return v;
-}
-
-// Path-store views.  ALPHA = false skips the third 128-bit word (throughput), which the
-// MIS weights never read.
-template <bool ALPHA> struct CamPathT {
-    const WfBuffers& b; const SceneView& sc; int slot;
-    TPT_DEV PVert operator()(int k) const {
-        if (k == 0) return camera_vertex(sc);
-        return load_vertex(b.camA, b.camB, b.camC, (size_t)k * b.S + slot, ALPHA);
-    }
-    TPT_DEV f3 pos(int k) const {
-        return k == 0 ? mk3(sc.eye.x, sc.eye.y, sc.eye.z) : mk3(b.camA[(size_t)k * b.S + slot]);
-    }
-};
-template <bool ALPHA> struct LightPathT {
-    const WfBuffers& b; int slot; int parity;
-    TPT_DEV PVert operator()(int k) const {
-        if (k == 0) return load_vertex(b.l0A, b.l0B, b.l0C, (size_t)parity * b.S + slot, ALPHA);
-        return load_vertex(b.lightA, b.lightB, b.lightC, (size_t)k * b.S + slot, ALPHA);
-    }
-    TPT_DEV f3 pos(int k) const {
-        return k == 0 ? mk3(b.l0A[(size_t)parity * b.S + slot]) : mk3(b.lightA[(size_t)k * b.S + slot]);
-    }
-};
-typedef CamPathT<true> CamPath;
-typedef LightPathT<true> LightPath;
-
 // {original area pdf of vertex i, reverse pdf towards vertex i (C.w, written by k_shade)}
 struct CamAux {
     const WfBuffers& b; int slot;
@@ -147,6 +106,71 @@ struct LightAux {
         const size_t at = (size_t)i * b.S + slot;
         return make_float2(b.lightA[at].w, b.lightC[at].w);
     }
+};
+
+// ---- everything one strategy (s,t) reads, fetched before anything is computed ------------------
+// A strategy touches the two subpath ends (z = cam[s-1], y = light[t-1]), their predecessors and,
+// for long subpaths, stored pdf ratios.  Fetched on demand these loads sit behind branches and
+// each one exposes a full HBM round trip; here every address is formed from (slot, s, t) alone
+// (indices clamped into valid memory, the value ignored where the vertex does not exist) so all
+// loads are in flight together.
+struct StrategyVerts {
+    float4 zA, zB, zC, zpA, zpB, yA, yB, yC, ypA, ypB;
+    float2 auxC[2], auxL[2];      // {pdf, reverse pdf} of cam[s-3], cam[s-4], light[t-3], light[t-4]
+};
+template <bool ALPHA>
+TPT_DEV StrategyVerts fetch_strategy(const WfBuffers& b, const SceneView& sc, int slot, int s, int t, int parity) {
+    StrategyVerts v;
+    const size_t S = (size_t)b.S;
+    const size_t zi = (size_t)max(s - 1, 1) * S + slot, zpi = (size_t)max(s - 2, 1) * S + slot;
+    const size_t l0 = (size_t)parity * S + slot;
+    const bool y0 = t <= 1, yp0 = t <= 2;      // light vertex 0 lives in the two-parity l0* arrays
+    const size_t yi = (size_t)max(t - 1, 1) * S + slot, ypi = (size_t)max(t - 2, 1) * S + slot;
+    v.zA = b.camA[zi]; v.zB = b.camB[zi];
+    v.zpA = b.camA[zpi]; v.zpB = b.camB[zpi];
+    v.yA = y0 ? b.l0A[l0] : b.lightA[yi]; v.yB = y0 ? b.l0B[l0] : b.lightB[yi];
+    v.ypA = yp0 ? b.l0A[l0] : b.lightA[ypi]; v.ypB = yp0 ? b.l0B[l0] : b.lightB[ypi];
+    if (ALPHA) { v.zC = b.camC[zi]; v.yC = y0 ? b.l0C[l0] : b.lightC[yi]; }
+    else {
+        v.zC = v.yC = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int ci = s - 3 - k, li = t - 3 - k;
+            v.auxC[k] = v.auxL[k] = make_float2(0.f, 0.f);
+            if (ci >= 0) { const size_t at = (size_t)ci * S + slot; v.auxC[k] = make_float2(ci == 0 ? CAMERA_ZERO_PDF : b.camA[at].w, b.camC[at].w); }
+            if (li > 0) { const size_t at = (size_t)li * S + slot; v.auxL[k] = make_float2(b.lightA[at].w, b.lightC[at].w); }
+            else if (li == 0) v.auxL[k] = make_float2(b.l0A[l0].w, b.l0C[l0].w);
+        }
+    }
+    if (s == 1) {      // z is the camera vertex (BDPT.cpp:44-47)
+        v.zA = make_float4(sc.eye.x, sc.eye.y, sc.eye.z, CAMERA_ZERO_PDF);
+        v.zB = make_float4(0.f, 0.f, 0.f, __int_as_float(pack_pt(-1, VT_CAMERA)));
+        v.zC = make_float4(1.f, 1.f, 1.f, 0.f);
+    }
+    if (s == 2) {      // ... or its predecessor is
+        v.zpA = make_float4(sc.eye.x, sc.eye.y, sc.eye.z, CAMERA_ZERO_PDF);
+        v.zpB = make_float4(0.f, 0.f, 0.f, __int_as_float(pack_pt(-1, VT_CAMERA)));
+    }
+    return v;
+}
+TPT_DEV PVert unpack_vertex3(const float4 a, const float4 b, const float4 c) {
+    PVert v;
+    v.x = mk3(a); v.pdf = a.w; v.N = mk3(b);
+    const int p = __float_as_int(b.w);
+    v.prim = unpack_prim(p); v.type = unpack_type(p);
+    v.alpha = mk3(c);
+    return v;
+}
+// The two vertices of a subpath a strategy reads: its end (index n - 1) and the one before it.
+struct EndPair {
+    PVert last, prev; int n;
+    TPT_DEV PVert operator()(int k) const { return k == n - 1 ? last : prev; }
+    TPT_DEV f3 pos(int k) const { return k == n - 1 ? last.x : prev.x; }
+};
+// Stored {pdf, reverse pdf}: the two deepest ones a strategy needs are prefetched, longer walks read on.
+template <class Fallback> struct AuxPair {
+    float2 a0, a1; int i0; Fallback rest;
+    TPT_DEV float2 operator()(int i) const { return i == i0 ? a0 : (i == i0 - 1 ? a1 : rest(i)); }
 };
 
 // ---- generate: primary ray + hit, once per pixel (the primary ray is the same for every
@@ -438,8 +462,9 @@ __global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_connect(SceneView g, WfB
             const int slot = (int)rec.x;
             const int s = rec.y & 255u, t = (rec.y >> 8) & 255u;
             const unsigned inf = rec.y;               // bit 16: light-vertex-0 parity
-            const CamPath cam{b, sc, slot};
-            const LightPath light{b, slot, (int)((inf >> 16) & 1u)};
+            const StrategyVerts v = fetch_strategy<true>(b, sc, slot, s, t, (int)((inf >> 16) & 1u));
+            const EndPair cam{unpack_vertex3(v.zA, v.zB, v.zC), unpack_vertex3(v.zpA, v.zpB, v.zC), s};
+            const EndPair light{unpack_vertex3(v.yA, v.yB, v.yC), unpack_vertex3(v.ypA, v.ypB, v.yC), t};
             int needs_shadow;
             const f3 u = connect_unweighted(sc, cam, s, light, t, &needs_shadow);
             const bool zero = u.x == 0.0f && u.y == 0.0f && u.z == 0.0f;
@@ -500,13 +525,17 @@ __global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_mis(SceneView g, RenderA
         const int s = rec.y & 255u, t = (rec.y >> 8) & 255u;
         const unsigned inf = rec.y;                   // bit 16: light-vertex-0 parity
         const int parity = (int)((inf >> 16) & 1u);
-        const CamPathT<false> cam{b, sc, slot};
-        const LightPathT<false> light{b, slot, parity};
-        f3 w = mk3(b.pair_val[p]);
+        const float4 pv = b.pair_val[p];
+        const StrategyVerts v = fetch_strategy<false>(b, sc, slot, s, t, parity);
+        const EndPair cam{unpack_vertex3(v.zA, v.zB, v.zC), unpack_vertex3(v.zpA, v.zpB, v.zC), s};
+        const EndPair light{unpack_vertex3(v.yA, v.yB, v.yC), unpack_vertex3(v.ypA, v.ypB, v.yC), t};
+        const AuxPair<CamAux> camAux{v.auxC[0], v.auxC[1], s - 3, CamAux{b, slot}};
+        const AuxPair<LightAux> lightAux{v.auxL[0], v.auxL[1], t - 3, LightAux{b, slot, parity}};
+        f3 w = mk3(pv);
         // a Background end returns before any weighting (BDPT.cpp:180-185)
-        const int endType = s == 1 ? VT_CAMERA : unpack_type(__float_as_int(b.camB[(size_t)(s - 1) * b.S + slot].w));
+        const int endType = cam.last.type;
         if (endType != VT_BACKGROUND)
-            w = w / mis_denominator_shared(sc, cam, s, light, t, CamAux{b, slot}, LightAux{b, slot, parity});
+            w = w / mis_denominator_shared(sc, cam, s, light, t, camAux, lightAux);
         w = mk3(std_max(w.x, 0.0f), std_max(w.y, 0.0f), std_max(w.z, 0.0f));   // BDPT.cpp:299
         if (s > 1) {
             if (w.x != 0.0f || w.y != 0.0f || w.z != 0.0f) {
@@ -515,8 +544,7 @@ __global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_mis(SceneView g, RenderA
                 atomicAdd(px, inv_spp * w.x); atomicAdd(px + 1, inv_spp * w.y); atomicAdd(px + 2, inv_spp * w.z);
             }
         } else {
-            const f3 lx = t == 1 ? mk3(b.l0A[(size_t)parity * b.S + slot]) : mk3(b.lightA[(size_t)(t - 1) * b.S + slot]);
-            splat_to_image(sc, lx, w, splat);
+            splat_to_image(sc, light.last.x, w, splat);      // t >= 1 here: (s,t) = (1,0) is not a strategy
         }
     }
 }
