@@ -17,6 +17,8 @@
 //   mats[4*m+0..3]   = { emission | asfloat(type) } { Kd | rough } { ior_m | ior_d } { ior_m_k | asfloat(emissive?) }
 //   objs[k]          = per Scene::objects entry: root / end node of its subtree, areas, material
 //   lnodes[n]        = BVHAccel::getSample tree of the meshes (left, right, triangle, area)
+//   leaves[2*l+0..1] = the leaf nodes of nodes[] alone, in visit order, for scenes of <= 64 leaves
+//                      whose every box contains its children's (see closest_hit_flat in traverse.cuh)
 // All arrays are sections of ONE device allocation (the "scene blob"), so a whole Cornell
 // scene (4-6 KB) is brought into shared memory by a single bulk asynchronous copy per
 // block (stage_scene) and traversed there; larger scenes stay in global memory and are
@@ -53,6 +55,8 @@ struct SceneView {
     const DevObject* objs;
     const DevLightNode* lnodes;
     const int* emissive;      // object indices, Scene::m_emissionObjects order
+    const float4* leaves;     // n_leaves > 0: the flat leaf list is usable for this scene
+    int n_leaves;
     int n_nodes, n_tris, n_spheres, n_mats, n_objs, n_lnodes, n_emissive;
     int width, height;
     float scale;              // CalculateScale(fov), computed on the host with the host libm
@@ -101,6 +105,7 @@ __device__ inline SceneView stage_scene(const SceneView& g, unsigned char* smem)
     s.objs = reinterpret_cast<const DevObject*>(move(g.objs));
     s.lnodes = reinterpret_cast<const DevLightNode*>(move(g.lnodes));
     s.emissive = reinterpret_cast<const int*>(move(g.emissive));
+    s.leaves = reinterpret_cast<const float4*>(move(g.leaves));
     return s;
 }
 

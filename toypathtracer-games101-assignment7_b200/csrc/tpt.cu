@@ -294,11 +294,34 @@ extern "C" int tpt_scene_create(const TptSceneDesc* d, int device, TptScene** ou
     int rc = require_device(device);
     if (rc != TPT_OK) return rc;
 
+    // Flat leaf list (traverse.cuh, closest_hit_flat): valid when every node's box contains the boxes of
+    // its whole subtree, which is what Union() builds (BVH.cpp:44-52, 93-95); checked, not assumed.
+    std::vector<float4> leaves;
+    {
+        const int nn = (int)hb.nodes.size() / 2;
+        int nleaf = 0;
+        for (int i = 0; i < nn; ++i) { int prim; std::memcpy(&prim, &hb.nodes[2 * i].w, 4); nleaf += prim >= 0; }
+        bool ok = nleaf > 0 && nleaf <= 64;
+        for (int i = 0; ok && i < nn; ++i) {
+            int miss; std::memcpy(&miss, &hb.nodes[2 * i + 1].w, 4);
+            const float4 lo = hb.nodes[2 * i], hi = hb.nodes[2 * i + 1];
+            for (int k = i + 1; ok && k < miss; ++k) {
+                const float4 a = hb.nodes[2 * k], b = hb.nodes[2 * k + 1];
+                ok = a.x >= lo.x && a.y >= lo.y && a.z >= lo.z && b.x <= hi.x && b.y <= hi.y && b.z <= hi.z &&
+                     a.x <= b.x && a.y <= b.y && a.z <= b.z;
+            }
+        }
+        if (ok)
+            for (int i = 0; i < nn; ++i) {
+                int prim; std::memcpy(&prim, &hb.nodes[2 * i].w, 4);
+                if (prim >= 0) { leaves.push_back(hb.nodes[2 * i]); leaves.push_back(hb.nodes[2 * i + 1]); }
+            }
+    }
     // one blob, one allocation, one host->device copy: the arrays in the order stage_scene expects
     std::vector<unsigned char> blob;
     const size_t o_nodes = blob_put(blob, hb.nodes), o_tris = blob_put(blob, tris), o_tverts = blob_put(blob, tverts),
                  o_spheres = blob_put(blob, spheres), o_mats = blob_put(blob, mats), o_objs = blob_put(blob, hb.objs),
-                 o_lnodes = blob_put(blob, lnodes), o_emissive = blob_put(blob, emissive);
+                 o_lnodes = blob_put(blob, lnodes), o_emissive = blob_put(blob, emissive), o_leaves = blob_put(blob, leaves);
     TptScene* s = new TptScene;
     s->device = device;
     s->n_prims = d->n_tris + d->n_spheres;
@@ -322,6 +345,8 @@ extern "C" int tpt_scene_create(const TptSceneDesc* d, int device, TptScene** ou
     v.objs = reinterpret_cast<const DevObject*>(dblob + o_objs);
     v.lnodes = reinterpret_cast<const DevLightNode*>(dblob + o_lnodes);
     v.emissive = reinterpret_cast<const int*>(dblob + o_emissive);
+    v.leaves = reinterpret_cast<const float4*>(dblob + o_leaves);
+    v.n_leaves = (int)leaves.size() / 2;
     v.n_nodes = (int)hb.nodes.size() / 2; v.n_tris = d->n_tris; v.n_spheres = d->n_spheres;
     v.n_mats = d->n_materials; v.n_objs = d->n_objects; v.n_lnodes = d->n_mesh_nodes; v.n_emissive = d->n_emissive;
     v.width = d->width; v.height = d->height;
@@ -408,10 +433,14 @@ __global__ void __launch_bounds__(256) k_intersect(SceneView g, const float* __r
                                                    size_t n, int prune, int32_t* prim, double* t, float* coords,
                                                    float* normal, unsigned long long* stats) {
     Ctx c = make_ctx(stage_scene(g, tpt_smem), prune != 0);
+    int* cand = reinterpret_cast<int*>(tpt_smem + ((g.stage_bytes + 15u) & ~15u)) + threadIdx.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const DRay r = make_ray(ld3(org, i), ld3(dir, i));
         DHit h;
-        trace_scene<COUNT>(c, r, cull[i], &h);
+        // default: the traversal of the render kernels (flat leaf list / deferred leaf tests);
+        // TPT_FLAG_REF_TRAVERSAL or COUNT: the reference's literal walk
+        if (!COUNT && prune) closest_hit_deferred(c.sc, r, cull[i], 0, c.sc.n_nodes, cand, blockDim.x, &h);
+        else trace_scene<COUNT>(c, r, cull[i], &h);
         if (prim) prim[i] = h.prim;
         if (t) t[i] = h.prim >= 0 ? h.t : 0.0;
         if (coords) st3(coords, i, h.coords);
@@ -423,9 +452,10 @@ __global__ void __launch_bounds__(256) k_intersect(SceneView g, const float* __r
 __global__ void __launch_bounds__(256) k_shadow(SceneView g, const float* __restrict__ from,
                                                 const float* __restrict__ to, const uint8_t* __restrict__ cull,
                                                 size_t n, uint8_t* out) {
-    Ctx c = make_ctx(stage_scene(g, tpt_smem), true);
+    const SceneView sc = stage_scene(g, tpt_smem);
+    int* cand = reinterpret_cast<int*>(tpt_smem + ((g.stage_bytes + 15u) & ~15u)) + threadIdx.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        out[i] = trace_shadow<false>(c, ld3(from, i), ld3(to, i), cull[i]) ? 1 : 0;
+        out[i] = shadow_check_deferred(sc, ld3(from, i), ld3(to, i), cull[i], cand, blockDim.x) ? 1 : 0;   // as the render kernels do
 }
 
 static int launch_grid(const TptScene* s, size_t n) {
@@ -443,11 +473,12 @@ extern "C" int tpt_intersect_batch_device(TptScene* s, const float* d_org, const
     cudaStream_t st = (cudaStream_t)stream;
     const int prune = (flags & TPT_FLAG_REF_TRAVERSAL) ? 0 : 1;
     const int grid = launch_grid(s, n);
+    const unsigned tsmem = ((s->view.stage_bytes + 15u) & ~15u) + TPT_CAND_BYTES(256);
     if (flags & TPT_FLAG_COUNT_VISITS)
-        k_intersect<true><<<grid, 256, s->view.stage_bytes, st>>>(s->view, d_org, d_dir, d_cull, n, prune, d_prim, d_t,
+        k_intersect<true><<<grid, 256, tsmem, st>>>(s->view, d_org, d_dir, d_cull, n, prune, d_prim, d_t,
                                                                   d_coords, d_normal, s->d_stats);
     else
-        k_intersect<false><<<grid, 256, s->view.stage_bytes, st>>>(s->view, d_org, d_dir, d_cull, n, prune, d_prim, d_t,
+        k_intersect<false><<<grid, 256, tsmem, st>>>(s->view, d_org, d_dir, d_cull, n, prune, d_prim, d_t,
                                                                    d_coords, d_normal, s->d_stats);
     TPT_CUDA(cudaGetLastError());
     return TPT_OK;
@@ -507,7 +538,7 @@ extern "C" int tpt_shadow_batch(TptScene* s, const float* from, const float* to,
     DevBuf a, b, c, o;
     int rc;
     if ((rc = a.from_host(from, n * 12)) || (rc = b.from_host(to, n * 12)) || (rc = c.from_host(cull, n)) || (rc = o.alloc(n))) return rc;
-    k_shadow<<<launch_grid(s, n), 256, s->view.stage_bytes>>>(s->view, a.as<float>(), b.as<float>(), c.as<uint8_t>(), n, o.as<uint8_t>());
+    k_shadow<<<launch_grid(s, n), 256, ((s->view.stage_bytes + 15u) & ~15u) + TPT_CAND_BYTES(256)>>>(s->view, a.as<float>(), b.as<float>(), c.as<uint8_t>(), n, o.as<uint8_t>());
     TPT_CUDA(cudaGetLastError());
     TPT_CUDA(cudaDeviceSynchronize());
     TPT_CUDA(cudaMemcpy(shadowed, o.p, n, cudaMemcpyDeviceToHost));
