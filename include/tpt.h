@@ -281,6 +281,14 @@ int tpt_bdpt_pathweight_batch(TptScene* scene, const TptPathVertex* cam, const i
                               const TptPathVertex* light, const int32_t* light_count,
                               size_t n, float* weights);
 
+/* BDPTPath::GenerateCameraPath + GenerateLightPath (BDPT.cpp:41-118, 261-279) for n samples:
+ * sample i starts from ResetRandom(seeds[i]) at pixel pixels[i]; its camera subpath is written to
+ * cam + 16*i (cam_count[i] vertices), the light subpath to light + 16*i, the RNG state after both to
+ * out_state[i].  The subpaths the render kernels build, exposed for parity tests. */
+int tpt_bdpt_subpaths_batch(TptScene* scene, const int32_t* pixels, const uint32_t* seeds, size_t n,
+                            TptPathVertex* cam, int32_t* cam_count, TptPathVertex* light,
+                            int32_t* light_count, uint32_t* out_state);
+
 #ifdef __cplusplus
 }
 #endif

@@ -261,6 +261,15 @@ class Scene:
         _check(lib().tpt_bdpt_pathweight_batch(self.h, _p(cam), _p(cc), _p(light), _p(lc), C.c_size_t(n), _p(w)))
         return w
 
+    def subpaths(self, pixels, seeds):
+        """tpt_bdpt_subpaths_batch: (cam[n,16], cam_count[n], light[n,16], light_count[n], state[n])."""
+        pixels = np.ascontiguousarray(pixels, dtype=np.int32); seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        n = len(pixels)
+        cam = np.zeros((n, 16), PATHVERTEX_DTYPE); light = np.zeros((n, 16), PATHVERTEX_DTYPE)
+        cc = np.zeros(n, np.int32); lc = np.zeros(n, np.int32); st = np.zeros(n, np.uint32)
+        _check(lib().tpt_bdpt_subpaths_batch(self.h, _p(pixels), _p(seeds), C.c_size_t(n), _p(cam), _p(cc), _p(light), _p(lc), _p(st)))
+        return cam, cc, light, lc, st
+
     # -- render -----------------------------------------------------------------
     def params(self, mode, spp, spp_total=0, seed_mode=SEED_REF, partition=PART_ALL, rank=0, world=1,
                pipeline=PIPE_WAVEFRONT, flags=0, stream=0):

@@ -219,6 +219,19 @@ TPT_DEV NextSample sample_next_dir(const SceneView& sc, uint32_t& rng, f3 N, int
     s.alpha = safe_div(bsdf, s.srpdf);
     return s;
 }
+// Deliberate deviations from the reference, both only where the reference itself produces NaN:
+//  * a subpath ends at a vertex whose area pdf is not a positive finite number.  BDPT.cpp:110 stops
+//    on pdf == 0 only; a ray leaving a point that lies exactly on an edge can hit the adjacent face
+//    at t = 0, the two vertices coincide, SrpdfToAreaPdf divides by a zero distance and the NaN
+//    then runs through the rest of the subpath and into the pixel (seen once in 39 M samples).
+//  * a strategy weight that is not finite is dropped instead of added (BDPT.cpp:299 keeps NaN:
+//    std::max(NaN, 0) is NaN).
+// The north star asks for images without NaN / Inf pixels; everything finite is untouched.
+TPT_DEV bool usable_pdf(float pdf) { return pdf > 0.0f && pdf < INFINITY; }
+TPT_DEV f3 finite_or_zero(f3 w) {
+    return (fabsf(w.x) < INFINITY && fabsf(w.y) < INFINITY && fabsf(w.z) < INFINITY) ? w : mk3(0.0f);
+}
+
 // ... and the vertex it becomes once the hit is known.
 TPT_DEV PVert vertex_from_hit(const DHit& h) {
     PVert v;
@@ -244,7 +257,7 @@ TPT_DEV int fill_path(Ctx& c, uint32_t& rng, PVert* verts) {
         verts[i + 1] = nv;
         const float rrProb = i > 4 ? .8f : 1.f;
         if (rng_float(rng) > rrProb) break;     // the draw is consumed even when rrProb == 1 (quirk Q16)
-        if (nv.pdf == 0.0f) break;
+        if (!usable_pdf(nv.pdf)) break;          // BDPT.cpp:110 (pdf == 0) + the NaN guard above
         verts[i + 1].pdf = nv.pdf * rrProb;
         verts[i + 1].alpha = (verts[i].alpha * nv.alpha) / rrProb;
         count++;
@@ -483,7 +496,7 @@ TPT_DEV f3 path_weight(Ctx& c, const CamPath& cam, int s, const LightPath& light
         return mk3(0.0f);
     f3 w = unweighted;                                   // a Background end returns before any weighting
     if (cam(s - 1).type != VT_BACKGROUND) w = unweighted / mis_denominator(c.sc, cam, s, light, t);
-    return mk3(std_max(w.x, 0.0f), std_max(w.y, 0.0f), std_max(w.z, 0.0f));
+    return finite_or_zero(mk3(std_max(w.x, 0.0f), std_max(w.y, 0.0f), std_max(w.z, 0.0f)));
 }
 
 // DrawToImage + RayToUV, SceneRenderingHelper.cpp:24-55: 3x3 tent splat of `value`

@@ -677,6 +677,62 @@ extern "C" int tpt_bdpt_pathweight_batch(TptScene* s, const TptPathVertex* cam, 
     return TPT_OK;
 }
 
+// Subpath generation for explicit (pixel, seed) pairs: one thread per sample.
+TPT_DEV TptPathVertex from_pvert(const PVert& v) {
+    TptPathVertex o;
+    o.x = TptVec3{v.x.x, v.x.y, v.x.z}; o.N = TptVec3{v.N.x, v.N.y, v.N.z};
+    o.prim = v.prim; o.type = v.type; o.pdf = v.pdf; o.alpha = TptVec3{v.alpha.x, v.alpha.y, v.alpha.z};
+    return o;
+}
+__global__ void __launch_bounds__(128) k_subpaths(SceneView g, const int32_t* pixels, const uint32_t* seeds, size_t n,
+                                                  TptPathVertex* cam, int32_t* camCount, TptPathVertex* light,
+                                                  int32_t* lightCount, uint32_t* outState) {
+    Ctx c = make_ctx(stage_scene(g, tpt_smem), true);
+    const SceneView& sc = c.sc;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t rng = seeds[i];
+        const int pixel = pixels[i];
+        PVert cv[MAX_BDPT_PATH_LENGTH], lv[MAX_BDPT_PATH_LENGTH];
+        DHit h;
+        trace_scene<false>(c, make_ray(mk3(sc.eye.x, sc.eye.y, sc.eye.z), pixel_ray(sc, pixel % sc.width, pixel / sc.width)), 0, &h);
+        camera_path_head(sc, h, cv);
+        const int nc = fill_path<false>(c, rng, cv);
+        const LightStart ls = light_path_head(sc, rng, sc.emissive[0], lv);
+        trace_scene<false>(c, make_ray(lv[0].x, ls.w_i), 0, &h);
+        int nl = 2;
+        if (light_path_first_hit(ls, h, lv)) nl = fill_path<false>(c, rng, lv);
+        for (int k = 0; k < nc; ++k) cam[16 * i + k] = from_pvert(cv[k]);
+        for (int k = 0; k < nl; ++k) light[16 * i + k] = from_pvert(lv[k]);
+        camCount[i] = nc; lightCount[i] = nl;
+        if (outState) outState[i] = rng;
+    }
+}
+extern "C" int tpt_bdpt_subpaths_batch(TptScene* s, const int32_t* pixels, const uint32_t* seeds, size_t n,
+                                       TptPathVertex* cam, int32_t* cam_count, TptPathVertex* light,
+                                       int32_t* light_count, uint32_t* out_state) {
+    if (!s || (n && (!pixels || !seeds || !cam || !cam_count || !light || !light_count))) { tpt_set_error("null argument"); return TPT_ERR_INVALID; }
+    if (s->view.n_emissive == 0) { tpt_set_error("BDPT needs an emissive object (BDPT.cpp:287)"); return TPT_ERR_INVALID; }
+    TPT_CUDA(cudaSetDevice(s->device));
+    if (n == 0) return TPT_OK;
+    DevBuf dp, ds, dc, dcc, dl, dlc, dst;
+    int rc;
+    if ((rc = dp.from_host(pixels, n * 4)) || (rc = ds.from_host(seeds, n * 4)) || (rc = dc.alloc(n * 16 * sizeof(TptPathVertex))) ||
+        (rc = dcc.alloc(n * 4)) || (rc = dl.alloc(n * 16 * sizeof(TptPathVertex))) || (rc = dlc.alloc(n * 4)) || (rc = dst.alloc(n * 4))) return rc;
+    TPT_CUDA(cudaMemset(dc.p, 0, n * 16 * sizeof(TptPathVertex)));
+    TPT_CUDA(cudaMemset(dl.p, 0, n * 16 * sizeof(TptPathVertex)));
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((n + 127) / 128, (size_t)s->num_sms * 8));
+    k_subpaths<<<grid, 128, s->view.stage_bytes>>>(s->view, dp.as<int32_t>(), ds.as<uint32_t>(), n, dc.as<TptPathVertex>(), dcc.as<int32_t>(),
+                                                   dl.as<TptPathVertex>(), dlc.as<int32_t>(), dst.as<uint32_t>());
+    TPT_CUDA(cudaGetLastError());
+    TPT_CUDA(cudaDeviceSynchronize());
+    TPT_CUDA(cudaMemcpy(cam, dc.p, n * 16 * sizeof(TptPathVertex), cudaMemcpyDeviceToHost));
+    TPT_CUDA(cudaMemcpy(cam_count, dcc.p, n * 4, cudaMemcpyDeviceToHost));
+    TPT_CUDA(cudaMemcpy(light, dl.p, n * 16 * sizeof(TptPathVertex), cudaMemcpyDeviceToHost));
+    TPT_CUDA(cudaMemcpy(light_count, dlc.p, n * 4, cudaMemcpyDeviceToHost));
+    if (out_state) TPT_CUDA(cudaMemcpy(out_state, dst.p, n * 4, cudaMemcpyDeviceToHost));
+    return TPT_OK;
+}
+
 // ------------------------------------------------------------------ validation renderer
 // One thread per pixel runs FillBufferThread's loop body (Renderer.cpp:40-53) start
 // to finish.  Divergent by construction; it exists to validate the integrators and

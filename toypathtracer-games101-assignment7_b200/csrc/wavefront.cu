@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_shade(SceneView g, Rende
                     if (srpdf == 0.0f && nv.type == VT_BACKGROUND) path_done = true;   // BDPT.cpp:85-88
                 } else {
                     const float rrProb = i > 4 ? .8f : 1.f;
-                    if (!(info & INFO_RR_PASS) || nv.pdf == 0.0f) {
+                    if (!(info & INFO_RR_PASS) || !usable_pdf(nv.pdf)) {
                         path_done = true;                  // BDPT.cpp:106-111: vertex i+1 is not part of the path
                     } else {
                         nv.pdf = nv.pdf * rrProb;
@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_mis(SceneView g, RenderA
         const int endType = cam.last.type;
         if (endType != VT_BACKGROUND)
             w = w / mis_denominator_shared(sc, cam, s, light, t, camAux, lightAux);
-        w = mk3(std_max(w.x, 0.0f), std_max(w.y, 0.0f), std_max(w.z, 0.0f));   // BDPT.cpp:299
+        w = finite_or_zero(mk3(std_max(w.x, 0.0f), std_max(w.y, 0.0f), std_max(w.z, 0.0f)));   // BDPT.cpp:299
         if (s > 1) {
             if (w.x != 0.0f || w.y != 0.0f || w.z != 0.0f) {
                 const int pixel = tpt_slot_pixel(a, sc.width * sc.height, slot);
@@ -584,7 +584,10 @@ static int wf_alloc(TptScene* s, int S) {
     };
     const size_t V = (size_t)MAX_BDPT_PATH_LENGTH * S * sizeof(float4);
     const size_t F4 = (size_t)S * sizeof(float4);
-    b.pair_cap = (unsigned long long)S * 48ull;
+    // strategies of one iteration: 48 per slot on average is generous (17 per completing sample, one sample in
+    // 7.5 iterations); never less than a block's worth of the longest samples (16*17 - 1 strategies each), so
+    // that a sample waiting for room always gets it once the queue has drained
+    b.pair_cap = std::max<unsigned long long>((unsigned long long)S * 48ull, 1ull << 16);
     if (b.pair_cap > 0x7fffffffull) b.pair_cap = 0x7fffffffull;
     bool ok = get(V, (void**)&b.camA) && get(V, (void**)&b.camB) && get(V, (void**)&b.camC) &&
               get(V, (void**)&b.lightA) && get(V, (void**)&b.lightB) && get(V, (void**)&b.lightC) &&
