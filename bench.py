@@ -209,7 +209,7 @@ def main():
     def step(flags=0, want_stats=False):
         # this rank's share -> ONE NCCL sum-reduce of [radiance | splat] over NVLink -> merge on rank 0
         return D.render_frame(scene, MODE, SPP * world, accum, out, strategy="spp", rank=rank, world=world,
-                              stream=stream, flags=flags, want_stats=want_stats)
+                              cuda_stream=stream, flags=flags, want_stats=want_stats)
 
     def barrier():
         if world > 1:

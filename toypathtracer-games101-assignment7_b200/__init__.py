@@ -291,17 +291,17 @@ class Scene:
     def accum_floats(self):
         return lib().tpt_accum_floats(self.h)
 
-    def render_device(self, mode, spp, d_accum_ptr, stream=None, want_stats=True, **kw):
+    def render_device(self, mode, spp, d_accum_ptr, cuda_stream=None, want_stats=True, **kw):
         """tpt_render_device into a device buffer of accum_floats() floats (e.g. a torch tensor's data_ptr())."""
         p = self.params(mode, spp, **kw)
         st = Stats()
-        _check(lib().tpt_render_device(self.h, C.byref(p), C.c_void_p(d_accum_ptr), C.c_void_p(stream or 0),
+        _check(lib().tpt_render_device(self.h, C.byref(p), C.c_void_p(d_accum_ptr), C.c_void_p(cuda_stream or 0),
                                        C.byref(st) if want_stats else None))
         return st.as_dict() if want_stats else None
 
-    def finalize_device(self, d_accum_ptr, d_out_ptr, d_rgb8_ptr=None, stream=None):
+    def finalize_device(self, d_accum_ptr, d_out_ptr, d_rgb8_ptr=None, cuda_stream=None):
         _check(lib().tpt_finalize_device(self.h, C.c_void_p(d_accum_ptr), C.c_void_p(d_out_ptr or 0),
-                                         C.c_void_p(d_rgb8_ptr or 0), C.c_void_p(stream or 0)))
+                                         C.c_void_p(d_rgb8_ptr or 0), C.c_void_p(cuda_stream or 0)))
 
 
 class PinnedImage:

@@ -212,7 +212,7 @@ TPT_DEV PVert unpack_vertex(const float4 a, const float4 b, const float4 c) {
     return v;
 }
 
-__global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_shade(SceneView g, RenderArgs a, WfBuffers b, int cur, unsigned long long* stats) {
+__global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfBuffers b, int cur, unsigned long long* stats) {
     const SceneView sc = stage_scene(g, tpt_smem);
     const unsigned n = b.ctr->n_active[cur];
     const int* list = b.active[cur];

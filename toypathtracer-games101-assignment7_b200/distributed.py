@@ -99,7 +99,7 @@ def reduce_frame(accum, dst=0, group=None):
     return accum
 
 
-def render_frame(scene, mode, spp_total, accum, out=None, strategy="spp", rank=0, world=1, stream=None, flags=0,
+def render_frame(scene, mode, spp_total, accum, out=None, strategy="spp", rank=0, world=1, cuda_stream=None, flags=0,
                  want_stats=False, render=None):
     """One frame on `world` ranks: this rank's share -> reduce -> merge on rank 0.
 
@@ -111,9 +111,9 @@ def render_frame(scene, mode, spp_total, accum, out=None, strategy="spp", rank=0
     if render is not None:
         st = render(share, accum)
     else:
-        st = scene.render_device(mode, share.spp, accum.data_ptr(), stream=stream, want_stats=want_stats, flags=flags,
+        st = scene.render_device(mode, share.spp, accum.data_ptr(), cuda_stream=cuda_stream, want_stats=want_stats, flags=flags,
                                  **share.params())
     reduce_frame(accum, dst=0)
     if rank == 0 and out is not None and render is None:
-        scene.finalize_device(accum.data_ptr(), out.data_ptr(), stream=stream)
+        scene.finalize_device(accum.data_ptr(), out.data_ptr(), cuda_stream=cuda_stream)
     return st
