@@ -14,8 +14,9 @@ render of that frame: 784*784*16 = 9 834 496 samples.  The metric is Msamples/s 
              scene arrays and the device->host copy of the frame are inside the timed region.
   roofline   traversal kernels (extend + shadow): algorithmic bytes per ray (1.16 KB
              for this scene/mode) x rays traced / summed CUDA-event launch time, against the measured
-             HBM copy bandwidth of MEASURED_PEAKS.json.  The scene is ~5 KB and lives in shared
-             memory, so this is an instruction-bound kernel and the fraction is not a DRAM fraction.
+             HBM copy bandwidth of MEASURED_PEAKS.json.  The scene is a few KB and lives in shared
+             memory, so these are instruction-bound kernels and the fraction is not a DRAM fraction (it
+             exceeds 1); `traffic` is the measured DRAM bytes per launch (profiles/traffic.json, ncu).
   cpu_baseline  the compiled reference (oracle/_ref, kind "reference") or the restatement
              (oracle/liboracle.so, kind "port") on all host cores for a bounded sample (2 spp of the
              same frame), rank 0, N = 1 only.

@@ -406,7 +406,10 @@ __global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfB
 }
 
 // ---- extend: closest hit for the rays of the active slots --------------------------------
-__global__ void __launch_bounds__(256) k_extend(SceneView g, RenderArgs a, WfBuffers b, int cur, unsigned long long* stats) {
+#ifndef TRAV_MIN_BLOCKS
+#define TRAV_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(256, TRAV_MIN_BLOCKS) k_extend(SceneView g, RenderArgs a, WfBuffers b, int cur, unsigned long long* stats) {
     const SceneView sc = stage_scene(g, tpt_smem);
     int* cand = reinterpret_cast<int*>(tpt_smem + ((g.stage_bytes + 15u) & ~15u)) + threadIdx.x;
     const unsigned n = b.ctr->n_active[cur];
@@ -480,7 +483,7 @@ __global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_connect(SceneView g, WfB
 }
 
 // ---- shadow: Scene::ShadowCheck for the queued connections -------------------------------
-__global__ void __launch_bounds__(256) k_shadow_q(SceneView g, RenderArgs a, WfBuffers b, unsigned long long* stats) {
+__global__ void __launch_bounds__(256, TRAV_MIN_BLOCKS) k_shadow_q(SceneView g, RenderArgs a, WfBuffers b, unsigned long long* stats) {
     const SceneView sc = stage_scene(g, tpt_smem);
     int* cand = reinterpret_cast<int*>(tpt_smem + ((g.stage_bytes + 15u) & ~15u)) + threadIdx.x;
     const unsigned n = b.ctr->n_shadow;
