@@ -35,7 +35,7 @@ namespace {
 struct WfCounters {
     unsigned n_active[2];      // active queue lengths (double buffered)
     unsigned long long done_pairs;   // (done count << 40) | pair count, allocated together
-    unsigned n_shadow, n_mis;
+    unsigned long long shadow_mis;   // low word: shadow queue length, high word: MIS queue length (appended together)
     unsigned n_retired;        // slots that rendered all their spp
     unsigned pad;
 };
@@ -227,6 +227,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfB
         int action = ACT_NONE;
         unsigned path = 0, i = 0, count = 0, nc = 0, parity = 0, flags = 0;
         uint32_t rng = 0;
+        unsigned spp_seen = 0;
         // the vertex the next ray leaves from (V) and its predecessor's position, kept in registers
         float4 VA = zero4, VB = zero4, c1A = zero4, c1B = zero4;
         f3 prev_x = mk3(0.0f);
@@ -234,6 +235,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfB
         if (live) {
             // ---- every load of this iteration, issued together (all addressed by the slot alone)
             const unsigned info = b.info[slot];
+            spp_seen = b.spp_done[slot];
             rng = b.rng[slot];
             const float4 hr = b.hit[slot], rd = b.ray_d[slot], pa = b.pend[slot];
             const float4 cA = b.curA[slot], cB = b.curB[slot], cC = b.curC[slot];
@@ -343,7 +345,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfB
                         b.done_off[di] = (unsigned)off;
                         ref_rays += nc + nl;                 // BDPT.cpp:288
                         samples++;
-                        const unsigned done = b.spp_done[slot] + 1;
+                        const unsigned done = spp_seen + 1;
                         b.spp_done[slot] = done;
                         fresh = true;
                         if ((int)done >= a.spp) {            // all samples of this pixel drawn: the slot retires
@@ -475,10 +477,19 @@ __global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_connect(SceneView g, WfB
             to_shadow = !zero && needs_shadow != 0;
             to_mis = !zero && needs_shadow == 0;
         }
-        const unsigned as = wf_append(&b.ctr->n_shadow, to_shadow);
-        if (to_shadow) b.shadow_q[as] = p;
-        const unsigned am = wf_append(&b.ctr->n_mis, to_mis);
-        if (to_mis) b.mis_q[am] = p;
+        // both queues with ONE atomic per warp: its round trip is what a warp waits for here
+        {
+            const unsigned ms = __ballot_sync(0xffffffffu, to_shadow), mm = __ballot_sync(0xffffffffu, to_mis);
+            if (ms | mm) {
+                const unsigned lane = threadIdx.x & 31u;
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(&b.ctr->shadow_mis, (unsigned long long)__popc(ms) | ((unsigned long long)__popc(mm) << 32));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const unsigned below = (1u << lane) - 1u;
+                if (to_shadow) b.shadow_q[(unsigned)base + __popc(ms & below)] = p;
+                if (to_mis) b.mis_q[(unsigned)(base >> 32) + __popc(mm & below)] = p;
+            }
+        }
     }
 }
 
@@ -486,7 +497,7 @@ __global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_connect(SceneView g, WfB
 __global__ void __launch_bounds__(256, TRAV_MIN_BLOCKS) k_shadow_q(SceneView g, RenderArgs a, WfBuffers b, unsigned long long* stats) {
     const SceneView sc = stage_scene(g, tpt_smem);
     int* cand = reinterpret_cast<int*>(tpt_smem + ((g.stage_bytes + 15u) & ~15u)) + threadIdx.x;
-    const unsigned n = b.ctr->n_shadow;
+    const unsigned n = (unsigned)b.ctr->shadow_mis;
     const unsigned total = (n + 31u) & ~31u;
     unsigned long long rays = 0;
     for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
@@ -507,7 +518,7 @@ __global__ void __launch_bounds__(256, TRAV_MIN_BLOCKS) k_shadow_q(SceneView g, 
             rays++;
         }
         if (live) visible = !shadow_check_deferred(sc, from, to, kind == 2 ? 1 : 0, cand, blockDim.x);
-        const unsigned am = wf_append(&b.ctr->n_mis, visible);
+        const unsigned am = wf_append(reinterpret_cast<unsigned*>(&b.ctr->shadow_mis) + 1, visible);   // the MIS word
         if (visible) b.mis_q[am] = p;
     }
     flush_stats(0, rays, 0, stats, rays);
@@ -519,7 +530,7 @@ __global__ void __launch_bounds__(256, TRAV_MIN_BLOCKS) k_shadow_q(SceneView g, 
 // reference's loop order (neither is the reference's own splat merge across threads).
 __global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_mis(SceneView g, RenderArgs a, WfBuffers b, float* radiance, float* splat) {
     const SceneView sc = stage_scene(g, tpt_smem);
-    const unsigned n = b.ctr->n_mis;
+    const unsigned n = (unsigned)(b.ctr->shadow_mis >> 32);
     const float inv_spp = 1.0f / a.spp_total;
     for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
         const unsigned p = b.mis_q[q];
@@ -555,8 +566,7 @@ __global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_mis(SceneView g, RenderA
 __global__ void k_reset_iteration(WfCounters* c, int next) {
     c->n_active[next] = 0;
     c->done_pairs = 0;
-    c->n_shadow = 0;
-    c->n_mis = 0;
+    c->shadow_mis = 0;
 }
 
 }  // namespace
