@@ -82,7 +82,10 @@ struct WfBuffers {
     unsigned long long pair_cap;
     uint2* pair_rec;                   // {slot, s | t << 8 | parity << 16}; slot 0xffffffff = void
     float4* pair_val;
-    unsigned *shadow_q, *mis_q;
+    // Queue entries carry what their consumer needs, so it starts from ONE coalesced load instead of
+    // chasing queue -> strategy record -> vertices:
+    float4* shadow_q;                  // 2 per entry: {from, asfloat(strategy id)} {to, asfloat(cull)}
+    uint4* mis_q;                      // {slot, s | t << 8 | parity << 16, strategy id, 0}
     WfCounters* ctr;
 };
 
@@ -462,8 +465,12 @@ __global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_connect(SceneView g, WfB
     const unsigned total = (n + 31u) & ~31u;
     for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
         bool to_shadow = false, to_mis = false;
+        f3 sh_from = mk3(0.0f), sh_to = mk3(0.0f);
+        int sh_cull = 0;
+        uint2 q_rec = make_uint2(0u, 0u);
         if (p < n && b.pair_rec[p].x != 0xffffffffu) {
             const uint2 rec = b.pair_rec[p];
+            q_rec = rec;
             const int slot = (int)rec.x;
             const int s = rec.y & 255u, t = (rec.y >> 8) & 255u;
             const unsigned inf = rec.y;               // bit 16: light-vertex-0 parity
@@ -476,6 +483,8 @@ __global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_connect(SceneView g, WfB
             if (!zero) b.pair_val[p] = make_float4(u.x, u.y, u.z, __int_as_float(needs_shadow));
             to_shadow = !zero && needs_shadow != 0;
             to_mis = !zero && needs_shadow == 0;
+            sh_from = cam.last.x; sh_to = light.last.x;         // Scene::ShadowCheck(cam[s-1], light[t-1])
+            sh_cull = needs_shadow == 2 ? 1 : 0;
         }
         // both queues with ONE atomic per warp: its round trip is what a warp waits for here
         {
@@ -486,8 +495,12 @@ __global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_connect(SceneView g, WfB
                 if (lane == 0) base = atomicAdd(&b.ctr->shadow_mis, (unsigned long long)__popc(ms) | ((unsigned long long)__popc(mm) << 32));
                 base = __shfl_sync(0xffffffffu, base, 0);
                 const unsigned below = (1u << lane) - 1u;
-                if (to_shadow) b.shadow_q[(unsigned)base + __popc(ms & below)] = p;
-                if (to_mis) b.mis_q[(unsigned)(base >> 32) + __popc(mm & below)] = p;
+                if (to_shadow) {
+                    const size_t at = 2 * (size_t)((unsigned)base + __popc(ms & below));
+                    b.shadow_q[at] = make_float4(sh_from.x, sh_from.y, sh_from.z, __uint_as_float(p));
+                    b.shadow_q[at + 1] = make_float4(sh_to.x, sh_to.y, sh_to.z, __int_as_float(sh_cull));
+                }
+                if (to_mis) b.mis_q[(unsigned)(base >> 32) + __popc(mm & below)] = make_uint4(q_rec.x, q_rec.y, p, 0u);
             }
         }
     }
@@ -502,24 +515,18 @@ __global__ void __launch_bounds__(256, TRAV_MIN_BLOCKS) k_shadow_q(SceneView g, 
     unsigned long long rays = 0;
     for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
         bool visible = false;
-        unsigned p = 0;
         const bool live = q < n;
-        f3 from = mk3(0.0f), to = mk3(0.0f, 0.0f, 1.0f);
-        int kind = 1;
+        uint4 out = make_uint4(0u, 0u, 0u, 0u);
         if (live) {
-            p = b.shadow_q[q];
-            const uint2 rec = b.pair_rec[p];
-            const int slot = (int)rec.x;
-            const int s = rec.y & 255u, t = (rec.y >> 8) & 255u;
-            const unsigned inf = rec.y;               // bit 16: light-vertex-0 parity
-            from = s == 1 ? mk3(sc.eye.x, sc.eye.y, sc.eye.z) : mk3(b.camA[(size_t)(s - 1) * b.S + slot]);
-            to = t == 1 ? mk3(b.l0A[(size_t)((inf >> 16) & 1u) * b.S + slot]) : mk3(b.lightA[(size_t)(t - 1) * b.S + slot]);
-            kind = __float_as_int(b.pair_val[p].w);
+            const float4 e0 = b.shadow_q[2 * (size_t)q], e1 = b.shadow_q[2 * (size_t)q + 1];
+            const unsigned p = __float_as_uint(e0.w);
+            const uint2 rec = b.pair_rec[p];          // only forwarded to the MIS queue: not needed before the walk
+            visible = !shadow_check_deferred(sc, mk3(e0), mk3(e1), __float_as_int(e1.w), cand, blockDim.x);
+            out = make_uint4(rec.x, rec.y, p, 0u);
             rays++;
         }
-        if (live) visible = !shadow_check_deferred(sc, from, to, kind == 2 ? 1 : 0, cand, blockDim.x);
         const unsigned am = wf_append(reinterpret_cast<unsigned*>(&b.ctr->shadow_mis) + 1, visible);   // the MIS word
-        if (visible) b.mis_q[am] = p;
+        if (visible) b.mis_q[am] = out;
     }
     flush_stats(0, rays, 0, stats, rays);
 }
@@ -533,8 +540,9 @@ __global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_mis(SceneView g, RenderA
     const unsigned n = (unsigned)(b.ctr->shadow_mis >> 32);
     const float inv_spp = 1.0f / a.spp_total;
     for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
-        const unsigned p = b.mis_q[q];
-        const uint2 rec = b.pair_rec[p];
+        const uint4 e = b.mis_q[q];
+        const unsigned p = e.z;
+        const uint2 rec = make_uint2(e.x, e.y);
         const int slot = (int)rec.x;
         const int s = rec.y & 255u, t = (rec.y >> 8) & 255u;
         const unsigned inf = rec.y;                   // bit 16: light-vertex-0 parity
@@ -597,10 +605,10 @@ static int wf_alloc(TptScene* s, int S) {
     };
     const size_t V = (size_t)MAX_BDPT_PATH_LENGTH * S * sizeof(float4);
     const size_t F4 = (size_t)S * sizeof(float4);
-    // strategies of one iteration: 48 per slot on average is generous (17 per completing sample, one sample in
-    // 7.5 iterations); never less than a block's worth of the longest samples (16*17 - 1 strategies each), so
+    // strategies of one iteration: 16 per slot is generous (17 per completing sample, one sample in 7.5
+    // iterations: ~2.5 per slot; a sample that finds no room waits an iteration); never less than a block's worth of the longest samples (16*17 - 1 strategies each), so
     // that a sample waiting for room always gets it once the queue has drained
-    b.pair_cap = std::max<unsigned long long>((unsigned long long)S * 48ull, 1ull << 16);
+    b.pair_cap = std::max<unsigned long long>((unsigned long long)S * 16ull, 1ull << 16);
     if (b.pair_cap > 0x7fffffffull) b.pair_cap = 0x7fffffffull;
     bool ok = get(V, (void**)&b.camA) && get(V, (void**)&b.camB) && get(V, (void**)&b.camC) &&
               get(V, (void**)&b.lightA) && get(V, (void**)&b.lightB) && get(V, (void**)&b.lightC) &&
@@ -612,7 +620,7 @@ static int wf_alloc(TptScene* s, int S) {
               get((size_t)S * 4, (void**)&b.active[1]) && get((size_t)S * 4, (void**)&b.done_slot) &&
               get((size_t)S * 4, (void**)&b.done_info) && get((size_t)S * 4, (void**)&b.done_off) &&
               get(b.pair_cap * sizeof(uint2), (void**)&b.pair_rec) && get(b.pair_cap * sizeof(float4), (void**)&b.pair_val) &&
-              get(b.pair_cap * 4, (void**)&b.shadow_q) && get(b.pair_cap * 4, (void**)&b.mis_q) &&
+              get(b.pair_cap * 2 * sizeof(float4), (void**)&b.shadow_q) && get(b.pair_cap * sizeof(uint4), (void**)&b.mis_q) &&
               get(sizeof(WfCounters), (void**)&b.ctr);
     if (ok && !(w->h_flag = static_cast<unsigned*>(tpt_pinned_alloc(64)))) ok = false;
     if (!ok) { wavefront_destroy(s); return TPT_ERR_OOM; }
