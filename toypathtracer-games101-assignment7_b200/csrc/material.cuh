@@ -26,7 +26,7 @@ TPT_DEV f3 refract_dir(f3 I, f3 N, float ior) {           // Refract, .cpp:37-48
     const float eta = etai / etat;
     const float k = __fsub_rn(1.0f, __fmul_rn(__fmul_rn(eta, eta), __fsub_rn(1.0f, __fmul_rn(cosi, cosi))));
     if (k < 0) return mk3(0.0f);
-    return s_normalize(eta * I + (eta * cosi - sqrtf(k)) * n);
+    return s_normalize_exact(eta * I + (eta * cosi - sqrtf(k)) * n);
 }
 TPT_DEV f3 any_perpendicular(f3 i) {                       // AnyPerpendicular, .cpp:51-67
     if (i.z == 0.0f) {
@@ -46,11 +46,11 @@ TPT_DEV f3 half_dir(f3 N, f3 wi, f3 wo, float matIor, float nl, float nv) {   //
     if (nl == 0.0f || nv == 0.0f) return mk3(0.0f);
     f3 h;
     if (nl * nv > 0.0f) {
-        h = s_normalize(wi + wo);
+        h = s_normalize_exact(wi + wo);
         if (nv < 0.0f) h = -h;
     } else {
-        if (nv < 0.0f) h = -s_normalize(matIor * wo + wi);
-        else h = -s_normalize(wo + wi * matIor);
+        if (nv < 0.0f) h = -s_normalize_exact(matIor * wo + wi);
+        else h = -s_normalize_exact(wo + wi * matIor);
     }
     return h;
 }
@@ -62,7 +62,7 @@ TPT_DEV f3 cosine_sample(uint32_t& rng, f3 N, float* pdf) {                     
     float sn, cs;
     sincosf(theta, &sn, &cs);
     const float x = r * cs, y = r * sn;
-    const f3 wi = s_normalize(to_world(mk3(x, y, sqrtf(1.0f - u1)), N));
+    const f3 wi = s_normalize_exact(to_world(mk3(x, y, sqrtf(1.0f - u1)), N));
     *pdf = dotf(wi, N) / TPT_PI;
     return wi;
 }
@@ -97,7 +97,7 @@ TPT_DEV f3 ggx_sample_h(uint32_t& rng, f3 N, float roughness) {        // Sample
     const float phi = 2.0f * TPT_PI * d2;
     float sp, cp;
     sincosf(phi, &sp, &cp);
-    return s_normalize(to_world(mk3(st * cp, st * sp, ct), N));
+    return s_normalize_exact(to_world(mk3(st * cp, st * sp, ct), N));
 }
 
 // ---- Material.cpp -----------------------------------------------------------------
@@ -214,7 +214,7 @@ TPT_DEV f3 mat_sample(const Mat& m, uint32_t& rng, f3 w_o, f3 n, float* pdf) {
         }
         float pdf_d;
         const f3 w_i_d = cosine_sample(rng, n, &pdf_d);
-        H = s_normalize(w_i_d + w_o);
+        H = s_normalize_exact(w_i_d + w_o);
         vh = dotf(w_o, H);
         abs_vh = fabsf(vh);
         pdf_h = ggx_half_pdf(n, H, m.rough);
