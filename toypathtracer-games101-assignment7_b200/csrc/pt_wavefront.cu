@@ -233,17 +233,22 @@ __global__ void __launch_bounds__(256, 3) k_pt_shade(SceneView g, RenderArgs a, 
 __global__ void __launch_bounds__(256) k_pt_extend(SceneView g, PtBuffers b, int cur, unsigned long long* stats) {
     const SceneView sc = stage_scene(g, tpt_smem);
     int* cand = reinterpret_cast<int*>(tpt_smem + ((g.stage_bytes + 15u) & ~15u)) + threadIdx.x;
+    unsigned char* coop = trav_coop(tpt_smem, g.stage_bytes);
     const unsigned n = b.ctr->n_active[cur];
     const int* list = b.active[cur];
     unsigned long long rays = 0;
-    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
-        const int slot = list[q];
-        const float4 o = b.ray_o[slot], d = b.ray_d[slot];
-        if (__float_as_int(o.w) < 0) continue;
+    const unsigned total = (n + 31u) & ~31u;        // whole warps: the primitive tests are shared inside a warp
+    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+        int slot = 0;
+        float4 o = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)), d = make_float4(0.f, 0.f, 1.f, 0.f);
+        if (q < n) { slot = list[q]; o = b.ray_o[slot]; d = b.ray_d[slot]; }
+        const bool has_ray = __float_as_int(o.w) >= 0;
         DHit h;
-        closest_hit_deferred(sc, make_ray(mk3(o), mk3(d)), __float_as_int(o.w), 0, sc.n_nodes, cand, blockDim.x, &h);
-        rays++;
-        b.hit[slot] = make_float4(h.coords.x, h.coords.y, h.coords.z, __int_as_float(h.prim));
+        closest_hit_warp(sc, make_ray(mk3(o), mk3(d)), __float_as_int(o.w), has_ray, coop, cand, blockDim.x, &h);
+        if (has_ray) {
+            rays++;
+            b.hit[slot] = make_float4(h.coords.x, h.coords.y, h.coords.z, __int_as_float(h.prim));
+        }
     }
     flush_stats(0, rays, 0, stats);
 }
@@ -260,15 +265,13 @@ __global__ void __launch_bounds__(256) k_pt_shadow(SceneView g, PtBuffers b, int
         const bool live = k < 2u * n;
         const int slot = live ? list[k >> 1] : 0;
         const unsigned j = k & 1u;
-        bool visible = false;
+        bool visible = false, has_ray = false;
+        float4 from = make_float4(0.f, 0.f, 0.f, -1.f), to = make_float4(0.f, 0.f, 1.f, 0.f);
         if (live) {
-            const float4 from = b.sh_from[(size_t)j * b.S + slot];
-            if (from.w > 0.0f) {
-                const float4 to = b.sh_to[slot];
-                visible = !shadow_check_deferred(sc, mk3(from), mk3(to), 0, cand, blockDim.x);   // Scene::ShadowCheck(inte.coords, x)
-                rays++;
-            }
+            from = b.sh_from[(size_t)j * b.S + slot];
+            if (from.w > 0.0f) { to = b.sh_to[slot]; has_ray = true; rays++; }
         }
+        if (has_ray) visible = !shadow_check_deferred(sc, mk3(from), mk3(to), 0, cand, blockDim.x);   // Scene::ShadowCheck(inte.coords, x)
         // the two lanes of a slot are neighbours: combine their bits with a shuffle, lane j == 0 writes
         const unsigned other = __shfl_down_sync(0xffffffffu, visible ? 1u : 0u, 1);
         if (live && j == 0) b.vis[slot] = (visible ? 1u : 0u) | (other << 1);
@@ -332,7 +335,12 @@ int pt_wavefront_render(TptScene* s, const RenderArgs& a, float* d_radiance, cud
     PtWavefrontState* w = s->ptwf;
     PtBuffers& b = w->b;
     const unsigned smem = s->view.stage_bytes;
-    const unsigned tsmem = ((smem + 15u) & ~15u) + TPT_CAND_BYTES(256);
+    const unsigned tsmem = TPT_TRAV_SMEM(smem, 256);
+    if (tsmem > 48u * 1024u) {                         // mid-size staged scenes: opt in to more dynamic shared memory
+        TPT_CUDA(cudaFuncSetAttribute(k_pt_generate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+        TPT_CUDA(cudaFuncSetAttribute(k_pt_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+        TPT_CUDA(cudaFuncSetAttribute(k_pt_shadow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+    }
     const int grid = std::max(1, std::min((S + 255) / 256, s->num_sms * 8));
     PtCounters init;
     std::memset(&init, 0, sizeof init);
@@ -345,7 +353,7 @@ int pt_wavefront_render(TptScene* s, const RenderArgs& a, float* d_radiance, cud
         k_pt_reset<<<1, 1, 0, st>>>(b.ctr, cur ^ 1);
         tm->begin(TPT_K_SHADE); k_pt_shade<<<grid, 256, smem, st>>>(s->view, a, b, cur, d_radiance, s->d_stats); tm->end();
         tm->begin(TPT_K_EXTEND); k_pt_extend<<<grid, 256, tsmem, st>>>(s->view, b, cur ^ 1, s->d_stats); tm->end();
-        tm->begin(TPT_K_SHADOW); k_pt_shadow<<<grid, 256, tsmem, st>>>(s->view, b, cur ^ 1, s->d_stats); tm->end();
+        tm->begin(TPT_K_SHADOW); k_pt_shadow<<<grid, 256, TPT_SHADOW_SMEM(smem, 256), st>>>(s->view, b, cur ^ 1, s->d_stats); tm->end();
         cur ^= 1;
         if ((it & 7) == 7) {
             TPT_CUDA(cudaMemcpyAsync(w->h_flag, &b.ctr->n_active[cur], sizeof(unsigned), cudaMemcpyDeviceToHost, st));

@@ -434,13 +434,18 @@ __global__ void __launch_bounds__(256) k_intersect(SceneView g, const float* __r
                                                    float* normal, unsigned long long* stats) {
     Ctx c = make_ctx(stage_scene(g, tpt_smem), prune != 0);
     int* cand = reinterpret_cast<int*>(tpt_smem + ((g.stage_bytes + 15u) & ~15u)) + threadIdx.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const DRay r = make_ray(ld3(org, i), ld3(dir, i));
+    unsigned char* coop = trav_coop(tpt_smem, g.stage_bytes);
+    const size_t total = (n + 31) & ~(size_t)31;      // whole warps (closest_hit_warp shares the primitive tests inside a warp)
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const bool live = i < n;
+        const DRay r = live ? make_ray(ld3(org, i), ld3(dir, i)) : make_ray(mk3(0.0f), mk3(0.0f, 0.0f, 1.0f));
+        const int cl = live ? cull[i] : 0;
         DHit h;
-        // default: the traversal of the render kernels (flat leaf list / deferred leaf tests);
+        // default: the traversal of the render kernels (flat leaf list, warp-shared primitive tests);
         // TPT_FLAG_REF_TRAVERSAL or COUNT: the reference's literal walk
-        if (!COUNT && prune) closest_hit_deferred(c.sc, r, cull[i], 0, c.sc.n_nodes, cand, blockDim.x, &h);
-        else trace_scene<COUNT>(c, r, cull[i], &h);
+        if (!COUNT && prune) closest_hit_warp(c.sc, r, cl, live, coop, cand, blockDim.x, &h);
+        else if (live) trace_scene<COUNT>(c, r, cl, &h);
+        if (!live) continue;
         if (prim) prim[i] = h.prim;
         if (t) t[i] = h.prim >= 0 ? h.t : 0.0;
         if (coords) st3(coords, i, h.coords);
@@ -473,7 +478,11 @@ extern "C" int tpt_intersect_batch_device(TptScene* s, const float* d_org, const
     cudaStream_t st = (cudaStream_t)stream;
     const int prune = (flags & TPT_FLAG_REF_TRAVERSAL) ? 0 : 1;
     const int grid = launch_grid(s, n);
-    const unsigned tsmem = ((s->view.stage_bytes + 15u) & ~15u) + TPT_CAND_BYTES(256);
+    const unsigned tsmem = TPT_TRAV_SMEM(s->view.stage_bytes, 256);
+    if (tsmem > 48u * 1024u) {
+        TPT_CUDA(cudaFuncSetAttribute(k_intersect<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+        TPT_CUDA(cudaFuncSetAttribute(k_intersect<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+    }
     if (flags & TPT_FLAG_COUNT_VISITS)
         k_intersect<true><<<grid, 256, tsmem, st>>>(s->view, d_org, d_dir, d_cull, n, prune, d_prim, d_t,
                                                                   d_coords, d_normal, s->d_stats);
@@ -538,7 +547,9 @@ extern "C" int tpt_shadow_batch(TptScene* s, const float* from, const float* to,
     DevBuf a, b, c, o;
     int rc;
     if ((rc = a.from_host(from, n * 12)) || (rc = b.from_host(to, n * 12)) || (rc = c.from_host(cull, n)) || (rc = o.alloc(n))) return rc;
-    k_shadow<<<launch_grid(s, n), 256, ((s->view.stage_bytes + 15u) & ~15u) + TPT_CAND_BYTES(256)>>>(s->view, a.as<float>(), b.as<float>(), c.as<uint8_t>(), n, o.as<uint8_t>());
+    if (TPT_TRAV_SMEM(s->view.stage_bytes, 256) > 48u * 1024u)
+        TPT_CUDA(cudaFuncSetAttribute(k_shadow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TPT_TRAV_SMEM(s->view.stage_bytes, 256)));
+    k_shadow<<<launch_grid(s, n), 256, TPT_TRAV_SMEM(s->view.stage_bytes, 256)>>>(s->view, a.as<float>(), b.as<float>(), c.as<uint8_t>(), n, o.as<uint8_t>());
     TPT_CUDA(cudaGetLastError());
     TPT_CUDA(cudaDeviceSynchronize());
     TPT_CUDA(cudaMemcpy(shadowed, o.p, n, cudaMemcpyDeviceToHost));

@@ -347,6 +347,128 @@ TPT_DEV bool shadow_check_deferred(const SceneView& sc, f3 from, f3 to, int cull
     return found;
 }
 
+// ---- warp-cooperative primitive tests -------------------------------------------------------------
+// After the flat leaf pass every lane holds a mask of candidates: 3.6 on average for Cornell, up to
+// ~10, so testing "the k-th candidate of every lane" keeps a third of the lanes busy.  Here the
+// candidates of the WHOLE warp are listed in shared memory (lane-major, each lane's in visit order)
+// and dealt out 32 at a time: a lane tests a candidate of whichever lane owns it, fetching that
+// ray with shuffles, and leaves t (or "miss") in shared memory; afterwards every lane reads back
+// its own results in visit order and applies the strict first-wins update — the same comparisons on
+// the same numbers as the per-lane loop, so the winner is the same.
+// Every lane of the warp must call these (has_ray = false for a lane with nothing to trace).
+#define TPT_COOP_CAP 256                                   /* candidates of one warp per pass */
+#define TPT_COOP_WARP_BYTES (TPT_COOP_CAP * 8 + TPT_COOP_CAP * 2)
+#define TPT_COOP_BYTES(threads) (((threads) / 32) * TPT_COOP_WARP_BYTES)
+
+struct CoopWarp {
+    double* res;            // t of candidate e, < 0: no hit
+    unsigned short* ent;    // owner lane << 8 | leaf
+};
+TPT_DEV CoopWarp coop_warp(unsigned char* block_base) {
+    unsigned char* w = block_base + (threadIdx.x >> 5) * TPT_COOP_WARP_BYTES;
+    CoopWarp c;
+    c.res = reinterpret_cast<double*>(w);
+    c.ent = reinterpret_cast<unsigned short*>(w + TPT_COOP_CAP * 8);
+    return c;
+}
+
+// Lists the candidates (m0, m1) of all lanes and tests them cooperatively.  Returns false (nothing done)
+// when the warp has more than TPT_COOP_CAP candidates: the caller then falls back to its own loop.
+// On success lane's results are res[base .. base + cnt) in visit order, with leaves in ent[].
+TPT_DEV bool coop_test(const SceneView& sc, const DRay& r, int cull, unsigned m0, unsigned m1, const CoopWarp& cw,
+                       unsigned* base_out, unsigned* cnt_out) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned cnt = __popc(m0) + __popc(m1);
+    unsigned incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += v;
+    }
+    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+    const unsigned base = incl - cnt;
+    *base_out = base; *cnt_out = cnt;
+    if (total > TPT_COOP_CAP) return false;
+    {
+        unsigned a0 = m0, a1 = m1, at = base;
+        while (a0 | a1) cw.ent[at++] = (unsigned short)((lane << 8) | (unsigned)flat_next(a0, a1));
+    }
+    __syncwarp();
+    for (unsigned e0 = 0; e0 < total; e0 += 32) {
+        const unsigned e = e0 + lane;
+        const bool have = e < total;
+        const unsigned entry = have ? cw.ent[e] : (lane << 8);
+        const int owner = (int)(entry >> 8);
+        DRay q;
+        q.o.x = __shfl_sync(0xffffffffu, r.o.x, owner); q.o.y = __shfl_sync(0xffffffffu, r.o.y, owner); q.o.z = __shfl_sync(0xffffffffu, r.o.z, owner);
+        q.d.x = __shfl_sync(0xffffffffu, r.d.x, owner); q.d.y = __shfl_sync(0xffffffffu, r.d.y, owner); q.d.z = __shfl_sync(0xffffffffu, r.d.z, owner);
+        q.inv = q.d;       // not read by the primitive tests
+        const int qcull = __shfl_sync(0xffffffffu, cull, owner);
+        if (have) {
+            int b = -1; double t = 0.0;
+            settle_candidate(sc, q, qcull, __float_as_int(sc.leaves[2 * (entry & 255u)].w), b, t);
+            cw.res[e] = b >= 0 ? t : -1.0;
+        }
+    }
+    __syncwarp();
+    return true;
+}
+
+TPT_DEV void finish_hit(const SceneView& sc, const DRay& r, int best, double best_t, DHit* hit) {
+    hit->prim = best;
+    hit->t = best_t;
+    if (best < 0) {
+        hit->coords = mk3(0.0f); hit->normal = mk3(0.0f);
+    } else if (best < sc.n_tris) {
+        hit->coords = x_madd(r.o, r.d, (float)best_t);
+        hit->normal = mk3(sc.tris[4 * best + 3]);
+    } else {
+        hit->coords = x_madd(r.o, r.d, (float)best_t);
+        hit->normal = x_normalize(x_sub(hit->coords, mk3(sc.spheres[2 * (best - sc.n_tris)])));
+    }
+}
+
+// Dynamic shared memory of a traversal kernel: [scene blob | candidate columns | cooperative area].
+#define TPT_TRAV_SMEM(stage_bytes, threads) ((((stage_bytes) + 15u) & ~15u) + TPT_CAND_BYTES(threads) + TPT_COOP_BYTES(threads))
+#define TPT_SHADOW_SMEM(stage_bytes, threads) ((((stage_bytes) + 15u) & ~15u) + TPT_CAND_BYTES(threads))   /* no cooperative area */
+TPT_DEV int* trav_cand(unsigned char* smem, unsigned stage_bytes) {
+    return reinterpret_cast<int*>(smem + ((stage_bytes + 15u) & ~15u)) + threadIdx.x;
+}
+TPT_DEV unsigned char* trav_coop(unsigned char* smem, unsigned stage_bytes) {
+    return smem + ((stage_bytes + 15u) & ~15u) + TPT_CAND_BYTES(blockDim.x);
+}
+
+// Scene::Intersect for a whole warp.  coop: this block's cooperative area (TPT_COOP_BYTES), cand: the
+// thread's candidate column for the fallback walk.
+TPT_DEV void closest_hit_warp(const SceneView& sc, const DRay& r, int cull, bool has_ray, unsigned char* coop, int* cand,
+                              int stride, DHit* hit) {
+    if (sc.n_leaves == 0) {                                   // large scene (uniform): the hierarchy walk
+        if (has_ray) closest_hit_deferred(sc, r, cull, 0, sc.n_nodes, cand, stride, hit);
+        return;
+    }
+    const bool flat = has_ray && ray_is_plain(r);
+    unsigned m0 = 0u, m1 = 0u;
+    if (flat) flat_masks(sc, r, FLT_MAX, m0, m1);
+    const CoopWarp cw = coop_warp(coop);
+    unsigned base, cnt;
+    const bool done = coop_test(sc, r, cull, m0, m1, cw, &base, &cnt);
+    if (has_ray && !flat) { closest_hit_deferred(sc, r, cull, 0, sc.n_nodes, cand, stride, hit); return; }
+    if (!has_ray) return;
+    double best_t = 0.0;
+    int best = -1;
+    if (done) {
+        for (unsigned k = 0; k < cnt; ++k) {
+            const double t = cw.res[base + k];
+            if (t >= 0.0 && (best < 0 || best_t > t)) {       // strict: first visited wins ties, BVH.cpp:131
+                best = __float_as_int(sc.leaves[2 * (cw.ent[base + k] & 255u)].w); best_t = t;
+            }
+        }
+    } else {
+        while (m0 | m1) settle_candidate(sc, r, cull, __float_as_int(sc.leaves[2 * flat_next(m0, m1)].w), best, best_t);
+    }
+    finish_hit(sc, r, best, best_t, hit);
+}
+
 // Scene::Intersect, Scene.cpp:21-35
 template <bool COUNT>
 TPT_DEV void scene_intersect(const SceneView& sc, const DRay& r, int cull, bool prune, DHit* hit, TravCounters* cnt) {

@@ -417,17 +417,22 @@ __global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfB
 __global__ void __launch_bounds__(256, TRAV_MIN_BLOCKS) k_extend(SceneView g, RenderArgs a, WfBuffers b, int cur, unsigned long long* stats) {
     const SceneView sc = stage_scene(g, tpt_smem);
     int* cand = reinterpret_cast<int*>(tpt_smem + ((g.stage_bytes + 15u) & ~15u)) + threadIdx.x;
+    unsigned char* coop = trav_coop(tpt_smem, g.stage_bytes);
     const unsigned n = b.ctr->n_active[cur];
     const int* list = b.active[cur];
     unsigned long long rays = 0;
-    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
-        const int slot = list[q];
-        const float4 o = b.ray_o[slot], d = b.ray_d[slot];
-        if (__float_as_int(o.w) < 0) continue;      // the slot emitted no ray this iteration
+    const unsigned total = (n + 31u) & ~31u;        // whole warps: the primitive tests are shared inside a warp
+    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+        int slot = 0;
+        float4 o = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)), d = make_float4(0.f, 0.f, 1.f, 0.f);
+        if (q < n) { slot = list[q]; o = b.ray_o[slot]; d = b.ray_d[slot]; }
+        const bool has_ray = __float_as_int(o.w) >= 0;      // < 0: the slot emitted no ray this iteration
         DHit h;
-        closest_hit_deferred(sc, make_ray(mk3(o), mk3(d)), __float_as_int(o.w), 0, sc.n_nodes, cand, blockDim.x, &h);
-        rays++;
-        b.hit[slot] = make_float4(h.coords.x, h.coords.y, h.coords.z, __int_as_float(h.prim));
+        closest_hit_warp(sc, make_ray(mk3(o), mk3(d)), __float_as_int(o.w), has_ray, coop, cand, blockDim.x, &h);
+        if (has_ray) {
+            rays++;
+            b.hit[slot] = make_float4(h.coords.x, h.coords.y, h.coords.z, __int_as_float(h.prim));
+        }
     }
     flush_stats(0, rays, 0, stats);
 }
@@ -517,14 +522,16 @@ __global__ void __launch_bounds__(256, TRAV_MIN_BLOCKS) k_shadow_q(SceneView g, 
         bool visible = false;
         const bool live = q < n;
         uint4 out = make_uint4(0u, 0u, 0u, 0u);
+        float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f), e1 = make_float4(0.f, 0.f, 1.f, 0.f);
         if (live) {
-            const float4 e0 = b.shadow_q[2 * (size_t)q], e1 = b.shadow_q[2 * (size_t)q + 1];
+            e0 = b.shadow_q[2 * (size_t)q]; e1 = b.shadow_q[2 * (size_t)q + 1];
             const unsigned p = __float_as_uint(e0.w);
             const uint2 rec = b.pair_rec[p];          // only forwarded to the MIS queue: not needed before the walk
-            visible = !shadow_check_deferred(sc, mk3(e0), mk3(e1), __float_as_int(e1.w), cand, blockDim.x);
             out = make_uint4(rec.x, rec.y, p, 0u);
             rays++;
         }
+        // per-lane tests here: a shadow query stops at its first blocking hit, which sharing the tests would give up
+        if (live) visible = !shadow_check_deferred(sc, mk3(e0), mk3(e1), __float_as_int(e1.w), cand, blockDim.x);
         const unsigned am = wf_append(reinterpret_cast<unsigned*>(&b.ctr->shadow_mis) + 1, visible);   // the MIS word
         if (visible) b.mis_q[am] = out;
     }
@@ -645,7 +652,12 @@ int wavefront_render(TptScene* s, const RenderArgs& a, float* d_radiance, float*
     WavefrontState* w = s->wf;
     WfBuffers& b = w->b;
     const unsigned smem = s->view.stage_bytes;
-    const unsigned tsmem = ((smem + 15u) & ~15u) + TPT_CAND_BYTES(256);   // traversal kernels: + candidate columns
+    const unsigned tsmem = TPT_TRAV_SMEM(smem, 256);   // traversal kernels: + candidate columns + cooperative area
+    if (tsmem > 48u * 1024u) {                         // mid-size staged scenes: opt in to more dynamic shared memory
+        TPT_CUDA(cudaFuncSetAttribute(k_generate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+        TPT_CUDA(cudaFuncSetAttribute(k_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+        TPT_CUDA(cudaFuncSetAttribute(k_shadow_q, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+    }
     const int grid = std::max(1, std::min((S + 255) / 256, s->num_sms * 8));
     const int pgrid = s->num_sms * 8;      // strategy kernels: persistent, sized to the machine
     WfCounters init;
@@ -662,7 +674,7 @@ int wavefront_render(TptScene* s, const RenderArgs& a, float* d_radiance, float*
         tm->begin(TPT_K_EXTEND); k_extend<<<grid, 256, tsmem, st>>>(s->view, a, b, cur ^ 1, s->d_stats); tm->end();
         tm->begin(TPT_K_EXPAND); k_expand<<<pgrid, 256, 0, st>>>(b); tm->end();
         tm->begin(TPT_K_CONNECT); k_connect<<<pgrid, 256, smem, st>>>(s->view, b); tm->end();
-        tm->begin(TPT_K_SHADOW); k_shadow_q<<<pgrid, 256, tsmem, st>>>(s->view, a, b, s->d_stats); tm->end();
+        tm->begin(TPT_K_SHADOW); k_shadow_q<<<pgrid, 256, TPT_SHADOW_SMEM(smem, 256), st>>>(s->view, a, b, s->d_stats); tm->end();
         tm->begin(TPT_K_MIS); k_mis<<<pgrid, 256, smem, st>>>(s->view, a, b, d_radiance, d_splat); tm->end();
         cur ^= 1;
         if ((it & 7) == 7 || it + 1 == max_iters) {
