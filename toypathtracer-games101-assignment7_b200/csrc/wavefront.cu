@@ -62,9 +62,13 @@ TPT_DEV unsigned make_info(unsigned path, unsigned i, unsigned count, unsigned f
 struct WfBuffers {
     int S;                     // slots
     // path store: vertex k of slot s at [k * S + s]
-    float4 *camA, *camB, *camC;        // A = {x, pdf}  B = {N, asfloat(pack(prim,type))}  C = {alpha, 0}
-    float4 *lightA, *lightB, *lightC;  // index 0 unused here: light vertex 0 lives in l0* (two parities)
-    float4 *l0A, *l0B, *l0C;           // [parity * S + s]
+    // path store, array of structures: a vertex is three consecutive 128-bit words
+    //   A = {x, pdf}  B = {N, asfloat(pack(prim,type))}  C = {alpha, reverse pdf}
+    // and the 16 vertices of a subpath are consecutive (vtx_at), so the vertices a strategy reads share
+    // sectors and DRAM pages instead of lying in nine arrays S * 16 bytes apart.  Light vertex 0 lives in
+    // l0 (two parities per slot, l0_at): the finished sample's stays readable while the next one starts.
+    float4* verts;
+    float4* l0;
     uint32_t* rng;
     unsigned* info;
     unsigned* spp_done;
@@ -89,25 +93,27 @@ struct WfBuffers {
     WfCounters* ctr;
 };
 
-TPT_DEV void store_vertex(float4* A, float4* B, float4* C, size_t at, const PVert& v) {
-    A[at] = make_float4(v.x.x, v.x.y, v.x.z, v.pdf);
-    B[at] = make_float4(v.N.x, v.N.y, v.N.z, __int_as_float(pack_pt(v.prim, v.type)));
-    C[at] = make_float4(v.alpha.x, v.alpha.y, v.alpha.z, 0.0f);
+TPT_DEV size_t vtx_at(int path, int k, int slot) { return (((size_t)slot * 2 + path) * MAX_BDPT_PATH_LENGTH + k) * 3; }
+TPT_DEV size_t l0_at(int parity, int slot) { return ((size_t)slot * 2 + parity) * 3; }
+TPT_DEV void store_vertex(float4* w, size_t at, const PVert& v) {
+    w[at] = make_float4(v.x.x, v.x.y, v.x.z, v.pdf);
+    w[at + 1] = make_float4(v.N.x, v.N.y, v.N.z, __int_as_float(pack_pt(v.prim, v.type)));
+    w[at + 2] = make_float4(v.alpha.x, v.alpha.y, v.alpha.z, 0.0f);
 }
 // {original area pdf of vertex i, reverse pdf towards vertex i (C.w, written by k_shade)}
 struct CamAux {
     const WfBuffers& b; int slot;
     TPT_DEV float2 operator()(int i) const {
-        const size_t at = (size_t)i * b.S + slot;
-        return make_float2(i == 0 ? CAMERA_ZERO_PDF : b.camA[at].w, b.camC[at].w);
+        const size_t at = vtx_at(0, i, slot);
+        return make_float2(i == 0 ? CAMERA_ZERO_PDF : b.verts[at].w, b.verts[at + 2].w);
     }
 };
 struct LightAux {
     const WfBuffers& b; int slot; int parity;
     TPT_DEV float2 operator()(int i) const {
-        if (i == 0) { const size_t at = (size_t)parity * b.S + slot; return make_float2(b.l0A[at].w, b.l0C[at].w); }
-        const size_t at = (size_t)i * b.S + slot;
-        return make_float2(b.lightA[at].w, b.lightC[at].w);
+        if (i == 0) { const size_t at = l0_at(parity, slot); return make_float2(b.l0[at].w, b.l0[at + 2].w); }
+        const size_t at = vtx_at(1, i, slot);
+        return make_float2(b.verts[at].w, b.verts[at + 2].w);
     }
 };
 
@@ -124,25 +130,25 @@ struct StrategyVerts {
 template <bool ALPHA>
 TPT_DEV StrategyVerts fetch_strategy(const WfBuffers& b, const SceneView& sc, int slot, int s, int t, int parity) {
     StrategyVerts v;
-    const size_t S = (size_t)b.S;
-    const size_t zi = (size_t)max(s - 1, 1) * S + slot, zpi = (size_t)max(s - 2, 1) * S + slot;
-    const size_t l0 = (size_t)parity * S + slot;
-    const bool y0 = t <= 1, yp0 = t <= 2;      // light vertex 0 lives in the two-parity l0* arrays
-    const size_t yi = (size_t)max(t - 1, 1) * S + slot, ypi = (size_t)max(t - 2, 1) * S + slot;
-    v.zA = b.camA[zi]; v.zB = b.camB[zi];
-    v.zpA = b.camA[zpi]; v.zpB = b.camB[zpi];
-    v.yA = y0 ? b.l0A[l0] : b.lightA[yi]; v.yB = y0 ? b.l0B[l0] : b.lightB[yi];
-    v.ypA = yp0 ? b.l0A[l0] : b.lightA[ypi]; v.ypB = yp0 ? b.l0B[l0] : b.lightB[ypi];
-    if (ALPHA) { v.zC = b.camC[zi]; v.yC = y0 ? b.l0C[l0] : b.lightC[yi]; }
+    const float4* z = b.verts + vtx_at(0, max(s - 1, 1), slot);
+    const float4* zp = b.verts + vtx_at(0, max(s - 2, 1), slot);
+    const float4* l0 = b.l0 + l0_at(parity, slot);
+    const float4* y = t <= 1 ? l0 : b.verts + vtx_at(1, t - 1, slot);      // light vertex 0 lives in the two-parity l0 array
+    const float4* yp = t <= 2 ? l0 : b.verts + vtx_at(1, t - 2, slot);
+    v.zA = z[0]; v.zB = z[1];
+    v.zpA = zp[0]; v.zpB = zp[1];
+    v.yA = y[0]; v.yB = y[1];
+    v.ypA = yp[0]; v.ypB = yp[1];
+    if (ALPHA) { v.zC = z[2]; v.yC = y[2]; }
     else {
         v.zC = v.yC = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             const int ci = s - 3 - k, li = t - 3 - k;
             v.auxC[k] = v.auxL[k] = make_float2(0.f, 0.f);
-            if (ci >= 0) { const size_t at = (size_t)ci * S + slot; v.auxC[k] = make_float2(ci == 0 ? CAMERA_ZERO_PDF : b.camA[at].w, b.camC[at].w); }
-            if (li > 0) { const size_t at = (size_t)li * S + slot; v.auxL[k] = make_float2(b.lightA[at].w, b.lightC[at].w); }
-            else if (li == 0) v.auxL[k] = make_float2(b.l0A[l0].w, b.l0C[l0].w);
+            if (ci >= 0) { const float4* c = b.verts + vtx_at(0, ci, slot); v.auxC[k] = make_float2(ci == 0 ? CAMERA_ZERO_PDF : c[0].w, c[2].w); }
+            if (li > 0) { const float4* l = b.verts + vtx_at(1, li, slot); v.auxL[k] = make_float2(l[0].w, l[2].w); }
+            else if (li == 0) v.auxL[k] = make_float2(l0[0].w, l0[2].w);
         }
     }
     if (s == 1) {      // z is the camera vertex (BDPT.cpp:44-47)
@@ -190,7 +196,7 @@ __global__ void __launch_bounds__(256) k_generate(SceneView g, RenderArgs a, WfB
         rays++;
         PVert cam[2];
         camera_path_head(sc, h, cam);
-        store_vertex(b.camA, b.camB, b.camC, (size_t)1 * b.S + slot, cam[1]);
+        store_vertex(b.verts, vtx_at(0, 1, slot), cam[1]);
         b.rng[slot] = tpt_pixel_seed(a.seed_mode, (uint32_t)pixel, (uint32_t)a.stream);
         b.spp_done[slot] = 0;
         b.info[slot] = make_info(0, 1, 2, 0, 0);
@@ -243,7 +249,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfB
             const float4 hr = b.hit[slot], rd = b.ray_d[slot], pa = b.pend[slot];
             const float4 cA = b.curA[slot], cB = b.curB[slot], cC = b.curC[slot];
             const float4 pA = b.prvA[slot], pB = b.prvB[slot];
-            c1A = b.camA[(size_t)b.S + slot]; c1B = b.camB[(size_t)b.S + slot];
+            c1A = b.verts[vtx_at(0, 1, slot)]; c1B = b.verts[vtx_at(0, 1, slot) + 1];
 
             path = INFO_PATH(info); i = INFO_I(info); count = INFO_COUNT(info); nc = INFO_NC(info);
             parity = (info & INFO_PARITY) ? 1u : 0u;
@@ -253,9 +259,6 @@ __global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfB
 
             // ---- phase 1: the vertex the traced ray produced (SampleNextVertex tail + FillPath body)
             if (info & INFO_PENDING) {
-                float4* A = path ? b.lightA : b.camA;
-                float4* B = path ? b.lightB : b.camB;
-                float4* C = path ? b.lightC : b.camC;
                 const bool lf = (info & INFO_LIGHT_FIRST) != 0;
                 const bool c1 = (info & INFO_FROM_C1) != 0;
                 DHit h;
@@ -269,7 +272,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfB
                 nv.pdf = srpdf_to_area(srpdf, L.x, L.N, L.type, nv.x, nv.N, nv.type);
                 if (lf) {
                     nv.alpha = afac;                       // SafeDivide(verts[0].alpha, pdf1), or 0 when pdf1 == 0
-                    store_vertex(A, B, C, (size_t)1 * b.S + slot, nv);
+                    store_vertex(b.verts, vtx_at((int)path, 1, slot), nv);
                     i = 1; count = 2;
                     if (srpdf == 0.0f && nv.type == VT_BACKGROUND) path_done = true;   // BDPT.cpp:85-88
                 } else {
@@ -279,16 +282,16 @@ __global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfB
                     } else {
                         nv.pdf = nv.pdf * rrProb;
                         nv.alpha = (L.alpha * afac) / rrProb;
-                        store_vertex(A, B, C, (size_t)(i + 1) * b.S + slot, nv);
+                        store_vertex(b.verts, vtx_at((int)path, (int)i + 1, slot), nv);
                         // reverse pdf towards vertex i-1: it is appended behind vertex i whose
                         // predecessor is the new vertex i+1 (mis_denominator_shared reads it)
                         f3 tx, tN = mk3(0.0f);
                         int tt;
                         float* dst;
-                        if (c1) { tx = mk3(sc.eye.x, sc.eye.y, sc.eye.z); tt = VT_CAMERA; dst = &b.camC[slot].w; }
+                        if (c1) { tx = mk3(sc.eye.x, sc.eye.y, sc.eye.z); tt = VT_CAMERA; dst = &b.verts[vtx_at(0, 0, slot) + 2].w; }
                         else {
                             tx = mk3(pA); tN = mk3(pB); tt = unpack_type(__float_as_int(pB.w));
-                            dst = i >= 2 ? &C[(size_t)(i - 1) * b.S + slot].w : &b.l0C[(size_t)parity * b.S + slot].w;
+                            dst = i >= 2 ? &b.verts[vtx_at((int)path, (int)i - 1, slot) + 2].w : &b.l0[l0_at((int)parity, slot) + 2].w;
                         }
                         *dst = append_pdf_base(sc, L, L.type, nv.x, tx, tN, tt);
                         count++; i++;
@@ -390,8 +393,10 @@ __global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfB
             parity ^= 1u;                                  // the finished sample's light vertex 0 stays readable
             PVert v0[1];
             const LightStart ls = light_path_head(sc, rng, sc.emissive[0], v0);
-            store_vertex(b.l0A, b.l0B, b.l0C, (size_t)parity * b.S + slot, v0[0]);
-            store_vertex(b.curA, b.curB, b.curC, (size_t)slot, v0[0]);
+            store_vertex(b.l0, l0_at((int)parity, slot), v0[0]);
+            b.curA[slot] = make_float4(v0[0].x.x, v0[0].x.y, v0[0].x.z, v0[0].pdf);
+            b.curB[slot] = make_float4(v0[0].N.x, v0[0].N.y, v0[0].N.z, __int_as_float(pack_pt(v0[0].prim, v0[0].type)));
+            b.curC[slot] = make_float4(v0[0].alpha.x, v0[0].alpha.y, v0[0].alpha.z, 0.0f);
             const f3 afac = ls.pdf1 != 0.0f ? safe_div(v0[0].alpha, ls.pdf1) : mk3(0.0f);
             ro = make_float4(v0[0].x.x, v0[0].x.y, v0[0].x.z, __int_as_float(0));
             b.ray_d[slot] = make_float4(ls.w_i.x, ls.w_i.y, ls.w_i.z, ls.pdf1);
@@ -617,9 +622,7 @@ static int wf_alloc(TptScene* s, int S) {
     // that a sample waiting for room always gets it once the queue has drained
     b.pair_cap = std::max<unsigned long long>((unsigned long long)S * 16ull, 1ull << 16);
     if (b.pair_cap > 0x7fffffffull) b.pair_cap = 0x7fffffffull;
-    bool ok = get(V, (void**)&b.camA) && get(V, (void**)&b.camB) && get(V, (void**)&b.camC) &&
-              get(V, (void**)&b.lightA) && get(V, (void**)&b.lightB) && get(V, (void**)&b.lightC) &&
-              get(2 * F4, (void**)&b.l0A) && get(2 * F4, (void**)&b.l0B) && get(2 * F4, (void**)&b.l0C) &&
+    bool ok = get(6 * V, (void**)&b.verts) && get(6 * F4, (void**)&b.l0) &&
               get((size_t)S * 4, (void**)&b.rng) && get((size_t)S * 4, (void**)&b.info) &&
               get((size_t)S * 4, (void**)&b.spp_done) && get(F4, (void**)&b.ray_o) && get(F4, (void**)&b.ray_d) &&
               get(F4, (void**)&b.pend) && get(F4, (void**)&b.hit) && get(F4, (void**)&b.curA) && get(F4, (void**)&b.curB) &&
