@@ -69,6 +69,8 @@ struct WfBuffers {
     // l0 (two parities per slot, l0_at): the finished sample's stays readable while the next one starts.
     float4* verts;
     float4* l0;
+    float4 *c1A, *c1B;                 // camera vertex 1 (the cached primary hit) once more, indexed by slot alone:
+                                       // k_shade reads it every iteration, coalesced
     uint32_t* rng;
     unsigned* info;
     unsigned* spp_done;
@@ -197,6 +199,7 @@ __global__ void __launch_bounds__(256) k_generate(SceneView g, RenderArgs a, WfB
         PVert cam[2];
         camera_path_head(sc, h, cam);
         store_vertex(b.verts, vtx_at(0, 1, slot), cam[1]);
+        b.c1A[slot] = b.verts[vtx_at(0, 1, slot)]; b.c1B[slot] = b.verts[vtx_at(0, 1, slot) + 1];
         b.rng[slot] = tpt_pixel_seed(a.seed_mode, (uint32_t)pixel, (uint32_t)a.stream);
         b.spp_done[slot] = 0;
         b.info[slot] = make_info(0, 1, 2, 0, 0);
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfB
             const float4 hr = b.hit[slot], rd = b.ray_d[slot], pa = b.pend[slot];
             const float4 cA = b.curA[slot], cB = b.curB[slot], cC = b.curC[slot];
             const float4 pA = b.prvA[slot], pB = b.prvB[slot];
-            c1A = b.verts[vtx_at(0, 1, slot)]; c1B = b.verts[vtx_at(0, 1, slot) + 1];
+            c1A = b.c1A[slot]; c1B = b.c1B[slot];
 
             path = INFO_PATH(info); i = INFO_I(info); count = INFO_COUNT(info); nc = INFO_NC(info);
             parity = (info & INFO_PARITY) ? 1u : 0u;
@@ -622,7 +625,7 @@ static int wf_alloc(TptScene* s, int S) {
     // that a sample waiting for room always gets it once the queue has drained
     b.pair_cap = std::max<unsigned long long>((unsigned long long)S * 16ull, 1ull << 16);
     if (b.pair_cap > 0x7fffffffull) b.pair_cap = 0x7fffffffull;
-    bool ok = get(6 * V, (void**)&b.verts) && get(6 * F4, (void**)&b.l0) &&
+    bool ok = get(6 * V, (void**)&b.verts) && get(6 * F4, (void**)&b.l0) && get(F4, (void**)&b.c1A) && get(F4, (void**)&b.c1B) &&
               get((size_t)S * 4, (void**)&b.rng) && get((size_t)S * 4, (void**)&b.info) &&
               get((size_t)S * 4, (void**)&b.spp_done) && get(F4, (void**)&b.ray_o) && get(F4, (void**)&b.ray_d) &&
               get(F4, (void**)&b.pend) && get(F4, (void**)&b.hit) && get(F4, (void**)&b.curA) && get(F4, (void**)&b.curB) &&
