@@ -34,6 +34,11 @@ void        tpth_scene_destroy(TpthScene* scene);
 int tpth_render(TpthScene* scene, const char* output_file, int spp, int bdpt, int pt_full,
                 int device, float* out_rgb, double* seconds);
 
+/* SaveFloatImageToJpg (reference SceneRenderingHelper.cpp:57-70) for a linear-float frame of
+ * width*height*3 floats: clamp, pow 0.6, *255 truncated, then by extension .jpg/.jpeg (baseline JPEG,
+ * quality 100, 4:4:4 like the reference's stb call), .ppm, .pfm/.f32 (raw floats).  0 on success. */
+int tpth_save_image(const float* rgb, int width, int height, const char* path);
+
 #ifdef __cplusplus
 }
 #endif

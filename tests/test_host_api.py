@@ -83,3 +83,21 @@ def test_reference_main_compiles_unchanged(tpt, tmp_path):
                            stdin=src, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
     assert os.path.exists(exe)
+
+
+def test_output_image_is_a_real_jpeg(tpt, tmp_path):
+    """SaveFloatImageToJpg (SceneRenderingHelper.cpp:57-70): the reference's tonemap (clamp, pow 0.6, * 255
+    truncated) followed by a baseline JPEG at quality 100 without chroma subsampling.  The file must decode
+    (PIL) to the tonemapped frame within the rounding of the colour transform."""
+    import ctypes as C
+    from PIL import Image
+    w, h = 100, 77                                        # not multiples of 8: edge blocks are replicated
+    y, x = np.mgrid[0:h, 0:w]
+    img = np.stack([x / w, y / h, 0.5 + 0.5 * np.sin(x / 7.0) * np.cos(y / 5.0)], -1).astype(np.float32)
+    img[10:20, 10:20] = [1.5, -0.2, 0.3]                  # out-of-range values are clamped
+    path = str(tmp_path / "frame.jpg")
+    assert tpt.host().tpth_save_image(img.ctypes.data_as(C.c_void_p), w, h, path.encode()) == 0
+    got = np.asarray(Image.open(path).convert("RGB")).astype(np.int32)
+    ref = np.floor(255 * np.power(np.clip(img, 0, 1), np.float32(0.6))).astype(np.int32)
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 4 and np.abs(got - ref).mean() < 1.0

@@ -29,11 +29,12 @@ TPT_DEV f3 refract_dir(f3 I, f3 N, float ior) {           // Refract, .cpp:37-48
     return s_normalize_exact(eta * I + (eta * cosi - sqrtf(k)) * n);
 }
 TPT_DEV f3 any_perpendicular(f3 i) {                       // AnyPerpendicular, .cpp:51-67
-    if (i.z == 0.0f) {
-        if (i.y == 0.0f) return mk3(0.0f, 1.0f, 0.0f);
-        return s_normalize(mk3(1.0f, -i.x / i.y, 0.0f));
-    }
-    return s_normalize(mk3(0.0f, 1.0f, -1.0f * i.y / i.z));
+    // the three cases as selects and ONE normalisation: lanes shading walls with different normals stay
+    // together ((0,1,0) normalises to itself, so the first case is unchanged)
+    const bool z0 = i.z == 0.0f, y0 = i.y == 0.0f;
+    const float q = z0 ? -i.x / i.y : -1.0f * i.y / i.z;
+    const f3 v = z0 ? (y0 ? mk3(0.0f, 1.0f, 0.0f) : mk3(1.0f, q, 0.0f)) : mk3(0.0f, 1.0f, q);
+    return s_normalize(v);
 }
 TPT_DEV f3 to_world(f3 a, f3 N) {                          // TransformVectorToWorld, .hpp:46-54
     const f3 tangent = any_perpendicular(N);

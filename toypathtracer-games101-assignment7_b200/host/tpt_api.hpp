@@ -290,7 +290,8 @@ public:
 
 // ---- SceneRenderingHelper.hpp -----------------------------------------------
 // Tonemap of reference SceneRenderingHelper.cpp:57-66 (clamp, pow 0.6, *255
-// truncated).  The file format follows the extension: .ppm (binary P6), .pfm /
-// .f32 (raw linear floats); any other extension (e.g. the reference's .jpg
-// default) gets a .ppm written next to the requested name.
+// truncated).  The file format follows the extension: .jpg / .jpeg (baseline JPEG,
+// quality 100, no chroma subsampling — what the reference's stbi_write_jpg call
+// produces; host/jpeg_writer.hpp), .ppm (binary P6), .pfm / .f32 (raw linear
+// floats); any other extension gets a .ppm written next to the requested name.
 void SaveFloatImageToJpg(std::vector<Vector3f> framebuffer, int width, int height, std::string path);

@@ -2,6 +2,7 @@
 // build (tree shape = tie order, so it follows reference BVH.cpp:30-99 exactly),
 // Renderer::Render as flatten -> tpt_render (GPU) -> report -> image file, the
 // README scene scripts, and a small C surface for the Python tests and bench.
+#include "jpeg_writer.hpp"
 #include "tpt_api.hpp"
 
 #include <chrono>
@@ -178,7 +179,15 @@ void SaveFloatImageToJpg(std::vector<Vector3f> framebuffer, int width, int heigh
         for (int i = 0; i < width * height; ++i) out.write((const char*)&framebuffer[i].x, 3 * sizeof(float));
         return;
     }
-    if (!EndsWith(path, ".ppm")) path += ".ppm";   // no JPEG encoder in this backend
+    if (EndsWith(path, ".jpg") || EndsWith(path, ".jpeg")) {      // what the reference writes (stbi_write_jpg, quality 100)
+        std::vector<unsigned char> rgb((size_t)width * height * 3);
+        for (int i = 0; i < width * height; ++i) {
+            rgb[3 * i] = Tonemap(framebuffer[i].x); rgb[3 * i + 1] = Tonemap(framebuffer[i].y); rgb[3 * i + 2] = Tonemap(framebuffer[i].z);
+        }
+        tptjpeg::write_jpeg(path, rgb.data(), width, height);
+        return;
+    }
+    if (!EndsWith(path, ".ppm")) path += ".ppm";
     std::ofstream out(path, std::ios::binary);
     out << "P6\n" << width << " " << height << "\n255\n";
     for (int i = 0; i < width * height; ++i) {
@@ -331,6 +340,14 @@ TpthScene* tpth_scene_build(const char* sceneName, const char* modelsDir, int wi
 const char* tpth_scene_error(const TpthScene* h) { return h->error.empty() ? nullptr : h->error.c_str(); }
 void tpth_scene_desc(const TpthScene* h, TptSceneDesc* out) { *out = h->flat.desc(); }
 void tpth_scene_destroy(TpthScene* h) { delete h; }
+
+int tpth_save_image(const float* rgb, int width, int height, const char* path) {
+    if (!rgb || !path || width <= 0 || height <= 0) return 1;
+    std::vector<Vector3f> fb((size_t)width * height);
+    for (size_t i = 0; i < fb.size(); ++i) fb[i] = Vector3f(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
+    SaveFloatImageToJpg(fb, width, height, path);
+    return 0;
+}
 
 // Renderer::Render on a built scene; returns 0 on success.  out_rgb may be NULL.
 int tpth_render(TpthScene* h, const char* outputFile, int spp, int bdpt, int ptFull, int device,
