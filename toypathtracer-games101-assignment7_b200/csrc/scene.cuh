@@ -17,6 +17,8 @@
 //   mats[4*m+0..3]   = { emission | asfloat(type) } { Kd | rough } { ior_m | ior_d } { ior_m_k | asfloat(emissive?) }
 //   objs[k]          = per Scene::objects entry: root / end node of its subtree, areas, material
 //   lnodes[n]        = BVHAccel::getSample tree of the meshes (left, right, triangle, area)
+//   uboxes[2*u+0..1] = the distinct boxes among those leaves, each with the bit mask of the leaves that have it
+//                      (the two triangles of an axis-aligned quad share one box: Cornell has 32 leaves, 17 boxes)
 //   leaves[2*l+0..1] = the leaf nodes of nodes[] alone, in visit order, for scenes of <= 64 leaves
 //                      whose every box contains its children's (see closest_hit_flat in traverse.cuh)
 // All arrays are sections of ONE device allocation (the "scene blob"), so a whole Cornell
@@ -57,6 +59,8 @@ struct SceneView {
     const int* emissive;      // object indices, Scene::m_emissionObjects order
     const float4* leaves;     // n_leaves > 0: the flat leaf list is usable for this scene
     int n_leaves;
+    const float4* uboxes;     // the DISTINCT leaf boxes: {bmin, asfloat(leaf mask bits 0-31)} {bmax, asfloat(bits 32-63)}
+    int n_uboxes;
     int n_nodes, n_tris, n_spheres, n_mats, n_objs, n_lnodes, n_emissive;
     int width, height;
     float scale;              // CalculateScale(fov), computed on the host with the host libm
@@ -106,6 +110,7 @@ __device__ inline SceneView stage_scene(const SceneView& g, unsigned char* smem)
     s.lnodes = reinterpret_cast<const DevLightNode*>(move(g.lnodes));
     s.emissive = reinterpret_cast<const int*>(move(g.emissive));
     s.leaves = reinterpret_cast<const float4*>(move(g.leaves));
+    s.uboxes = reinterpret_cast<const float4*>(move(g.uboxes));
     return s;
 }
 

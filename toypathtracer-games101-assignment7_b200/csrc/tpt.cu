@@ -317,11 +317,29 @@ extern "C" int tpt_scene_create(const TptSceneDesc* d, int device, TptScene** ou
                 if (prim >= 0) { leaves.push_back(hb.nodes[2 * i]); leaves.push_back(hb.nodes[2 * i + 1]); }
             }
     }
+    // leaves with bit-identical boxes are tested once: the same numbers give the same answer
+    std::vector<float4> uboxes;
+    for (size_t l = 0; l < leaves.size() / 2; ++l) {
+        float4 lo = leaves[2 * l], hi = leaves[2 * l + 1];
+        size_t u = 0;
+        for (; u < uboxes.size() / 2; ++u)
+            if (std::memcmp(&uboxes[2 * u], &lo, 12) == 0 && std::memcmp(&uboxes[2 * u + 1], &hi, 12) == 0) break;
+        if (u == uboxes.size() / 2) {
+            lo.w = hi.w = HostBuild::as_f(0);
+            uboxes.push_back(lo); uboxes.push_back(hi);
+        }
+        unsigned bits;
+        float4& word = l < 32 ? uboxes[2 * u] : uboxes[2 * u + 1];
+        std::memcpy(&bits, &word.w, 4);
+        bits |= 1u << (l & 31);
+        std::memcpy(&word.w, &bits, 4);
+    }
     // one blob, one allocation, one host->device copy: the arrays in the order stage_scene expects
     std::vector<unsigned char> blob;
     const size_t o_nodes = blob_put(blob, hb.nodes), o_tris = blob_put(blob, tris), o_tverts = blob_put(blob, tverts),
                  o_spheres = blob_put(blob, spheres), o_mats = blob_put(blob, mats), o_objs = blob_put(blob, hb.objs),
-                 o_lnodes = blob_put(blob, lnodes), o_emissive = blob_put(blob, emissive), o_leaves = blob_put(blob, leaves);
+                 o_lnodes = blob_put(blob, lnodes), o_emissive = blob_put(blob, emissive), o_leaves = blob_put(blob, leaves),
+                 o_uboxes = blob_put(blob, uboxes);
     TptScene* s = new TptScene;
     s->device = device;
     s->n_prims = d->n_tris + d->n_spheres;
@@ -347,6 +365,8 @@ extern "C" int tpt_scene_create(const TptSceneDesc* d, int device, TptScene** ou
     v.emissive = reinterpret_cast<const int*>(dblob + o_emissive);
     v.leaves = reinterpret_cast<const float4*>(dblob + o_leaves);
     v.n_leaves = (int)leaves.size() / 2;
+    v.uboxes = reinterpret_cast<const float4*>(dblob + o_uboxes);
+    v.n_uboxes = (int)uboxes.size() / 2;
     v.n_nodes = (int)hb.nodes.size() / 2; v.n_tris = d->n_tris; v.n_spheres = d->n_spheres;
     v.n_mats = d->n_materials; v.n_objs = d->n_objects; v.n_lnodes = d->n_mesh_nodes; v.n_emissive = d->n_emissive;
     v.width = d->width; v.height = d->height;

@@ -226,17 +226,14 @@ TPT_DEV void settle_candidate(const SceneView& sc, const DRay& r, int cull, int 
 // over ~27 of 69 nodes.
 TPT_DEV void flat_masks(const SceneView& sc, const DRay& r, float reach, unsigned& m0, unsigned& m1) {
     m0 = m1 = 0u;
-    const int n = sc.n_leaves;
+    const int n = sc.n_uboxes;          // distinct boxes: leaves sharing a box get the same answer from one test
 #pragma unroll 4
-    for (int l = 0; l < min(n, 32); ++l) {
+    for (int u = 0; u < n; ++u) {
+        const float4 lo = sc.uboxes[2 * u], hi = sc.uboxes[2 * u + 1];
         float nmin;
-        const bool in = slab_test_plain(sc.leaves[2 * l], sc.leaves[2 * l + 1], r, &nmin) && !(nmin > reach);
-        m0 |= (in ? 1u : 0u) << l;
-    }
-    for (int l = 32; l < n; ++l) {
-        float nmin;
-        const bool in = slab_test_plain(sc.leaves[2 * l], sc.leaves[2 * l + 1], r, &nmin) && !(nmin > reach);
-        m1 |= (in ? 1u : 0u) << (l - 32);
+        const bool in = slab_test_plain(lo, hi, r, &nmin) && !(nmin > reach);
+        m0 |= in ? __float_as_uint(lo.w) : 0u;
+        m1 |= in ? __float_as_uint(hi.w) : 0u;
     }
 }
 TPT_DEV int flat_next(unsigned& m0, unsigned& m1) {      // lowest set bit = next leaf in visit order
