@@ -34,10 +34,12 @@ namespace {
 // ---- per-iteration device counters ------------------------------------------------
 struct WfCounters {
     unsigned n_active[2];      // active queue lengths (double buffered)
-    unsigned long long done_pairs;   // (done count << 40) | pair count, allocated together
-    unsigned long long shadow_mis;   // low word: shadow queue length, high word: MIS queue length (appended together)
     unsigned n_retired;        // slots that rendered all their spp
     unsigned pad;
+    // per-iteration counters, one set per iteration parity: the set of iteration i + 1 is cleared by
+    // k_extend of iteration i (no separate reset launch)
+    unsigned long long done_pairs[2];   // (done count << 40) | pair count, allocated together
+    unsigned long long shadow_mis[2];   // low word: shadow queue length, high word: MIS queue length (appended together)
 };
 
 // ---- slot state ----------------------------------------------------------------------
@@ -187,7 +189,9 @@ template <class Fallback> struct AuxPair {
 // ---- generate: primary ray + hit, once per pixel (the primary ray is the same for every
 // sample: no jitter, Renderer.cpp:46) -----------------------------------------------------
 __global__ void __launch_bounds__(256) k_generate(SceneView g, RenderArgs a, WfBuffers b, unsigned long long* stats) {
+    pdl_launch_dependents();
     const SceneView sc = stage_scene(g, tpt_smem);
+    pdl_wait();
     int* cand = reinterpret_cast<int*>(tpt_smem + ((g.stage_bytes + 15u) & ~15u)) + threadIdx.x;
     unsigned long long rays = 0;
     for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < b.S; slot += gridDim.x * blockDim.x) {
@@ -224,8 +228,10 @@ TPT_DEV PVert unpack_vertex(const float4 a, const float4 b, const float4 c) {
     return v;
 }
 
-__global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfBuffers b, int cur, unsigned long long* stats) {
+__global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfBuffers b, int cur, int par, unsigned long long* stats) {
+    pdl_launch_dependents();
     const SceneView sc = stage_scene(g, tpt_smem);
+    pdl_wait();
     const unsigned n = b.ctr->n_active[cur];
     const int* list = b.active[cur];
     int* next_list = b.active[cur ^ 1];
@@ -336,7 +342,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfB
                 }
                 const unsigned wtotal = __shfl_sync(0xffffffffu, incl, 31);
                 unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(&b.ctr->done_pairs, ((unsigned long long)__popc(cmask) << 40) | wtotal);
+                if (lane == 0) base = atomicAdd(&b.ctr->done_pairs[par], ((unsigned long long)__popc(cmask) << 40) | wtotal);
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (completing) {
                     const unsigned long long off = (base & ((1ull << 40) - 1)) + (incl - npairs);
@@ -422,8 +428,15 @@ __global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfB
 #ifndef TRAV_MIN_BLOCKS
 #define TRAV_MIN_BLOCKS 4
 #endif
-__global__ void __launch_bounds__(256, TRAV_MIN_BLOCKS) k_extend(SceneView g, RenderArgs a, WfBuffers b, int cur, unsigned long long* stats) {
+__global__ void __launch_bounds__(256, TRAV_MIN_BLOCKS) k_extend(SceneView g, RenderArgs a, WfBuffers b, int cur, int par, unsigned long long* stats) {
+    pdl_launch_dependents();
     const SceneView sc = stage_scene(g, tpt_smem);
+    pdl_wait();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {      // the next iteration's counters (nothing in flight reads them)
+        b.ctr->n_active[cur ^ 1] = 0;                // the list k_shade just consumed: the next one is built there
+        b.ctr->done_pairs[par ^ 1] = 0;
+        b.ctr->shadow_mis[par ^ 1] = 0;
+    }
     int* cand = reinterpret_cast<int*>(tpt_smem + ((g.stage_bytes + 15u) & ~15u)) + threadIdx.x;
     unsigned char* coop = trav_coop(tpt_smem, g.stage_bytes);
     const unsigned n = b.ctr->n_active[cur];
@@ -446,8 +459,10 @@ __global__ void __launch_bounds__(256, TRAV_MIN_BLOCKS) k_extend(SceneView g, Re
 }
 
 // ---- expand: one work item per strategy of every completed sample ------------------------
-__global__ void __launch_bounds__(256) k_expand(WfBuffers b) {
-    const unsigned n_done = (unsigned)(b.ctr->done_pairs >> 40);
+__global__ void __launch_bounds__(256) k_expand(WfBuffers b, int par) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const unsigned n_done = (unsigned)(b.ctr->done_pairs[par] >> 40);
     const unsigned lane = threadIdx.x & 31u;
     const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     for (unsigned di = warp; di < n_done; di += nwarps) {
@@ -471,9 +486,11 @@ __global__ void __launch_bounds__(256) k_expand(WfBuffers b) {
 }
 
 // ---- connect: unweighted contribution, shadow-ray / MIS queueing --------------------------
-__global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_connect(SceneView g, WfBuffers b) {
+__global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_connect(SceneView g, WfBuffers b, int par) {
+    pdl_launch_dependents();
     const SceneView sc = stage_scene(g, tpt_smem);
-    const unsigned long long np_all = b.ctr->done_pairs & ((1ull << 40) - 1);
+    pdl_wait();
+    const unsigned long long np_all = b.ctr->done_pairs[par] & ((1ull << 40) - 1);
     const unsigned n = (unsigned)(np_all < b.pair_cap ? np_all : b.pair_cap);
     const unsigned total = (n + 31u) & ~31u;
     for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
@@ -505,7 +522,7 @@ __global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_connect(SceneView g, WfB
             if (ms | mm) {
                 const unsigned lane = threadIdx.x & 31u;
                 unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(&b.ctr->shadow_mis, (unsigned long long)__popc(ms) | ((unsigned long long)__popc(mm) << 32));
+                if (lane == 0) base = atomicAdd(&b.ctr->shadow_mis[par], (unsigned long long)__popc(ms) | ((unsigned long long)__popc(mm) << 32));
                 base = __shfl_sync(0xffffffffu, base, 0);
                 const unsigned below = (1u << lane) - 1u;
                 if (to_shadow) {
@@ -520,10 +537,12 @@ __global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_connect(SceneView g, WfB
 }
 
 // ---- shadow: Scene::ShadowCheck for the queued connections -------------------------------
-__global__ void __launch_bounds__(256, TRAV_MIN_BLOCKS) k_shadow_q(SceneView g, RenderArgs a, WfBuffers b, unsigned long long* stats) {
+__global__ void __launch_bounds__(256, TRAV_MIN_BLOCKS) k_shadow_q(SceneView g, RenderArgs a, WfBuffers b, int par, unsigned long long* stats) {
+    pdl_launch_dependents();
     const SceneView sc = stage_scene(g, tpt_smem);
+    pdl_wait();
     int* cand = reinterpret_cast<int*>(tpt_smem + ((g.stage_bytes + 15u) & ~15u)) + threadIdx.x;
-    const unsigned n = (unsigned)b.ctr->shadow_mis;
+    const unsigned n = (unsigned)b.ctr->shadow_mis[par];
     const unsigned total = (n + 31u) & ~31u;
     unsigned long long rays = 0;
     for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
@@ -540,7 +559,7 @@ __global__ void __launch_bounds__(256, TRAV_MIN_BLOCKS) k_shadow_q(SceneView g, 
         }
         // per-lane tests here: a shadow query stops at its first blocking hit, which sharing the tests would give up
         if (live) visible = !shadow_check_deferred(sc, mk3(e0), mk3(e1), __float_as_int(e1.w), cand, blockDim.x);
-        const unsigned am = wf_append(reinterpret_cast<unsigned*>(&b.ctr->shadow_mis) + 1, visible);   // the MIS word
+        const unsigned am = wf_append(reinterpret_cast<unsigned*>(&b.ctr->shadow_mis[par]) + 1, visible);   // the MIS word
         if (visible) b.mis_q[am] = out;
     }
     flush_stats(0, rays, 0, stats, rays);
@@ -550,9 +569,11 @@ __global__ void __launch_bounds__(256, TRAV_MIN_BLOCKS) k_shadow_q(SceneView g, 
 // pixel (s > 1, BDPT.cpp:301-303 + Renderer.cpp:49) or splatted with the 3x3 tent (s == 1,
 // BDPT.cpp:304-311).  Sums are formed with float atomics: their order is not the
 // reference's loop order (neither is the reference's own splat merge across threads).
-__global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_mis(SceneView g, RenderArgs a, WfBuffers b, float* radiance, float* splat) {
+__global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_mis(SceneView g, RenderArgs a, WfBuffers b, int par, float* radiance, float* splat) {
+    pdl_launch_dependents();
     const SceneView sc = stage_scene(g, tpt_smem);
-    const unsigned n = (unsigned)(b.ctr->shadow_mis >> 32);
+    pdl_wait();
+    const unsigned n = (unsigned)(b.ctr->shadow_mis[par] >> 32);
     const float inv_spp = 1.0f / a.spp_total;
     for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
         const uint4 e = b.mis_q[q];
@@ -586,15 +607,22 @@ __global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_mis(SceneView g, RenderA
     }
 }
 
-__global__ void k_reset_iteration(WfCounters* c, int next) {
-    c->n_active[next] = 0;
-    c->done_pairs = 0;
-    c->shadow_mis = 0;
-}
-
 }  // namespace
 
 // ---- host side -------------------------------------------------------------------------------
+// Launch with programmatic stream serialization: the grid may start while its predecessor in the
+// stream drains; it orders itself with pdl_wait() (wf_common.cuh).
+template <class... KArgs, class... Args>
+static void launch_pdl(void (*kernel)(KArgs...), int grid, unsigned smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 struct WavefrontState {
     int S = 0;
     WfBuffers b;
@@ -670,18 +698,18 @@ int wavefront_render(TptScene* s, const RenderArgs& a, float* d_radiance, float*
     std::memset(&init, 0, sizeof init);
     init.n_active[0] = (unsigned)S;
     TPT_CUDA(cudaMemcpyAsync(b.ctr, &init, sizeof init, cudaMemcpyHostToDevice, st));
-    tm->begin(TPT_K_GENERATE); k_generate<<<grid, 256, tsmem, st>>>(s->view, a, b, s->d_stats); tm->end();
+    tm->begin(TPT_K_GENERATE); launch_pdl(k_generate, grid, tsmem, st, s->view, a, b, s->d_stats); tm->end();
     int cur = 0;
     // every sample needs at least 2 iterations; 31 is the longest a sample can take
     const long long max_iters = (long long)a.spp * 32 + 8;
     for (long long it = 0; it < max_iters; ++it) {
-        k_reset_iteration<<<1, 1, 0, st>>>(b.ctr, cur ^ 1);
-        tm->begin(TPT_K_SHADE); k_shade<<<grid, 256, smem, st>>>(s->view, a, b, cur, s->d_stats); tm->end();
-        tm->begin(TPT_K_EXTEND); k_extend<<<grid, 256, tsmem, st>>>(s->view, a, b, cur ^ 1, s->d_stats); tm->end();
-        tm->begin(TPT_K_EXPAND); k_expand<<<pgrid, 256, 0, st>>>(b); tm->end();
-        tm->begin(TPT_K_CONNECT); k_connect<<<pgrid, 256, smem, st>>>(s->view, b); tm->end();
-        tm->begin(TPT_K_SHADOW); k_shadow_q<<<pgrid, 256, TPT_SHADOW_SMEM(smem, 256), st>>>(s->view, a, b, s->d_stats); tm->end();
-        tm->begin(TPT_K_MIS); k_mis<<<pgrid, 256, smem, st>>>(s->view, a, b, d_radiance, d_splat); tm->end();
+        const int par = (int)(it & 1);
+        tm->begin(TPT_K_SHADE); launch_pdl(k_shade, grid, smem, st, s->view, a, b, cur, par, s->d_stats); tm->end();
+        tm->begin(TPT_K_EXTEND); launch_pdl(k_extend, grid, tsmem, st, s->view, a, b, cur ^ 1, par, s->d_stats); tm->end();
+        tm->begin(TPT_K_EXPAND); launch_pdl(k_expand, pgrid, 0u, st, b, par); tm->end();
+        tm->begin(TPT_K_CONNECT); launch_pdl(k_connect, pgrid, smem, st, s->view, b, par); tm->end();
+        tm->begin(TPT_K_SHADOW); launch_pdl(k_shadow_q, pgrid, (unsigned)TPT_SHADOW_SMEM(smem, 256), st, s->view, a, b, par, s->d_stats); tm->end();
+        tm->begin(TPT_K_MIS); launch_pdl(k_mis, pgrid, smem, st, s->view, a, b, par, d_radiance, d_splat); tm->end();
         cur ^= 1;
         if ((it & 7) == 7 || it + 1 == max_iters) {
             TPT_CUDA(cudaMemcpyAsync(w->h_flag, &b.ctr->n_active[cur], sizeof(unsigned), cudaMemcpyDeviceToHost, st));

@@ -25,6 +25,15 @@ TPT_DEV unsigned wf_append(unsigned* counter, bool want) {
     return base + __popc(mask & ((1u << lane) - 1u));
 }
 
+// Programmatic dependent launch (griddepcontrol): a kernel of the wavefront loop lets its successor's
+// blocks become resident as soon as its own last wave is running (pdl_launch_dependents, first
+// statement) and the successor does everything that does not depend on earlier kernels — staging the
+// scene blob, setting up shared memory — before pdl_wait(), which returns once the predecessor grid has
+// completed and its writes are visible.  Every kernel in the loop calls pdl_wait() before it touches
+// queue state, so completion is transitive along the stream.
+TPT_DEV void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+TPT_DEV void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 TPT_DEV f3 hit_normal(const SceneView& sc, int prim, f3 coords) {
     if (prim < sc.n_tris) return mk3(sc.tris[4 * prim + 3]);
     return x_normalize(x_sub(coords, mk3(sc.spheres[2 * (prim - sc.n_tris)])));
