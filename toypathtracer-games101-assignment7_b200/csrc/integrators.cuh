@@ -485,6 +485,108 @@ TPT_DEV float mis_denominator_shared(const SceneView& sc, const CamPath& cam, in
     return den;
 }
 
+// mis_denominator_shared once more, with the four pdfs a strategy evaluates itself formed in PAIRS.
+// They are the two directions through z = cam[s-1] (from zp towards y and from y towards zp) and the
+// two through y = light[t-1] (from yp towards z, from z towards yp): per vertex the same two unit
+// vectors, the same cosines and — on the reflection side of a GGX material — the same half vector
+// (mat_pdf_pair).  Operation order of the products is the reference's (BDPT.cpp:219-253).
+struct SolidPair { float pre_to_conn, conn_to_pre; };     // solid-angle pdfs at one vertex
+TPT_DEV SolidPair vertex_pdf_pair(const SceneView& sc, const PVert& V, int type, f3 w_pre, f3 w_conn, float cos_pre, float cos_conn) {
+    SolidPair r;
+    if (type == VT_CAMERA) { r.pre_to_conn = r.conn_to_pre = CAMERA_RAY_PDF; return r; }
+    if (type == VT_LIGHT) {
+        r.pre_to_conn = safe_div(cosine_pdf(V.N, w_conn), cos_conn);
+        r.conn_to_pre = safe_div(cosine_pdf(V.N, w_pre), cos_pre);
+        return r;
+    }
+    float pab, pba;
+    mat_pdf_pair(load_mat(sc, prim_material(sc, V.prim)), w_pre, V.N, w_conn, &pab, &pba);
+    r.pre_to_conn = cos_conn == 0.0f ? 0.0f : safe_div(pab, cos_conn);
+    r.conn_to_pre = cos_pre == 0.0f ? 0.0f : safe_div(pba, cos_pre);
+    return r;
+}
+template <class CamPath, class LightPath, class CamAux, class LightAux>
+TPT_DEV float mis_denominator_paired(const SceneView& sc, const CamPath& cam, int s, const LightPath& light, int t,
+                                     const CamAux& camAux, const LightAux& lightAux) {
+    float den = 1.0f;
+    const PVert z = cam(s - 1);
+    PVert zp = z;
+    if (s >= 2) zp = cam(s - 2);
+    const f3 Nz = vert_normal(z);
+    float dzp2 = 1.0f;
+    const f3 w_zp = s_normalize_len2(zp.x - z.x, &dzp2);          // unused for s == 1
+    const float cos_zp = fabsf(dotf(w_zp, Nz));
+    // area-measure factor of appending zp behind z: |cos at z| * |cos at zp| / dist^2 (SrpdfToAreaPdf)
+    const float g_zp = fabsf((z.type == VT_CAMERA ? 1.0f : cos_zp) * (zp.type == VT_CAMERA ? 1.0f : fabsf(dotf(w_zp, zp.N))) / dzp2);
+    if (t == 0) {
+        // light subpath empty: cam[s-1] starts the path re-typed Light with its primitive's own 1/area (quirk Q15)
+        float cur = safe_div(prim_pdf(sc, z.prim), z.pdf);
+        den += cur * cur;
+        int count = 1;
+        if (cur != 0.0f && s >= 2) {
+            const float sr = safe_div(cosine_pdf(Nz, w_zp), cos_zp);
+            cur *= safe_div(sr * fabsf(cos_zp * (zp.type == VT_CAMERA ? 1.0f : fabsf(dotf(w_zp, zp.N))) / dzp2) * (count > 4 ? .8f : 1.f), zp.pdf);
+            den += cur * cur;
+            count++;
+            for (int i = s - 3; i >= 0 && cur != 0.0f; --i) {
+                const float2 aux = camAux(i);
+                cur *= safe_div(aux.y * (count > 4 ? .8f : 1.f), aux.x);
+                den += cur * cur;
+                count++;
+            }
+        }
+        return den;
+    }
+    const PVert y = light(t - 1);
+    PVert yp = y;
+    if (t >= 2) yp = light(t - 2);
+    const f3 Ny = vert_normal(y);
+    float d2 = 1.0f, dyp2 = 1.0f;
+    const f3 w_zy = s_normalize_len2(y.x - z.x, &d2);               // z towards y; y towards z is its negation
+    const f3 w_yp = s_normalize_len2(yp.x - y.x, &dyp2);            // unused for t == 1
+    const float cos_z = fabsf(dotf(w_zy, Nz)), cos_y = fabsf(dotf(w_zy, Ny));
+    const float cos_yp = fabsf(dotf(w_yp, Ny));
+    const float g_zy = fabsf((z.type == VT_CAMERA ? 1.0f : cos_z) * (y.type == VT_CAMERA ? 1.0f : cos_y) / d2);
+    const float g_yp = fabsf((y.type == VT_CAMERA ? 1.0f : cos_yp) * (yp.type == VT_CAMERA ? 1.0f : fabsf(dotf(w_yp, yp.N))) / dyp2);
+    const SolidPair pz = vertex_pdf_pair(sc, z, z.type, w_zp, w_zy, cos_zp, cos_z);
+    const SolidPair py = vertex_pdf_pair(sc, y, y.type, w_yp, -w_zy, cos_yp, cos_y);
+    {   // camera subpath extended by light[t-1], ..., light[0]
+        int count = s;
+        float cur = safe_div(pz.pre_to_conn * g_zy * (count > 4 ? .8f : 1.f), y.pdf);
+        den += cur * cur;
+        count++;
+        if (cur != 0.0f && t >= 2) {
+            cur *= safe_div(py.conn_to_pre * g_yp * (count > 4 ? .8f : 1.f), yp.pdf);
+            den += cur * cur;
+            count++;
+            for (int i = t - 3; i >= 0 && cur != 0.0f; --i) {
+                const float2 aux = lightAux(i);
+                cur *= safe_div(aux.y * (count > 4 ? .8f : 1.f), aux.x);
+                den += cur * cur;
+                count++;
+            }
+        }
+    }
+    {   // light subpath extended by cam[s-1], ..., cam[0]
+        int count = t;
+        float cur = safe_div(py.pre_to_conn * g_zy * (count > 4 ? .8f : 1.f), z.pdf);
+        den += cur * cur;
+        count++;
+        if (cur != 0.0f && s >= 2) {
+            cur *= safe_div(pz.conn_to_pre * g_zp * (count > 4 ? .8f : 1.f), zp.pdf);
+            den += cur * cur;
+            count++;
+            for (int i = s - 3; i >= 0 && cur != 0.0f; --i) {
+                const float2 aux = camAux(i);
+                cur *= safe_div(aux.y * (count > 4 ? .8f : 1.f), aux.x);
+                den += cur * cur;
+                count++;
+            }
+        }
+    }
+    return den;
+}
+
 // Full BDPTPath::PathWeight for one strategy, clamped like BDPT.cpp:299.  The shadow
 // ray is skipped when the unweighted term is already zero (the result is zero either way).
 template <bool COUNT, class CamPath, class LightPath>

@@ -191,6 +191,25 @@ TPT_DEV float mat_pdf(const Mat& m, f3 w_o, f3 n, f3 w_i) {
     return 0.0f;
 }
 
+// pdf(m, a, n, b) and pdf(m, b, n, a) together — the MIS weight of a connection needs both at each of
+// its two end vertices.  On the reflection side the half vector (a + b, normalised) and with it the GGX
+// half-vector density are the same for both directions, so the pair costs little more than one.
+TPT_DEV void mat_pdf_pair(const Mat& m, f3 a, f3 n, f3 b, float* pab, float* pba) {
+    const float na = dotf(n, a), nb = dotf(n, b);
+    *pab = 0.0f; *pba = 0.0f;
+    if (na == 0.0f || nb == 0.0f) return;
+    if (na * nb > 0.0f) {
+        const f3 h = half_dir(n, b, a, m.ior_d, nb, na);
+        const float pdf_h = ggx_half_pdf(n, h, m.rough);
+        const float ja = safe_div(1.0f, (4.0f * fabsf(dotf(a, h)))), jb = safe_div(1.0f, (4.0f * fabsf(dotf(b, h))));
+        if (m.type == 1) { *pab = pdf_h * ja; *pba = pdf_h * jb; }
+        else if (m.type == 0) { *pab = (cosine_pdf(n, b) + pdf_h * ja) * 0.5f; *pba = (cosine_pdf(n, a) + pdf_h * jb) * 0.5f; }
+        else { *pab = pdf_h * mat_fresnel(m, a, h).x * ja; *pba = pdf_h * mat_fresnel(m, b, h).x * jb; }
+    } else if (na * nb < 0.0f && m.type == 2) {       // refraction: the two half vectors differ
+        *pab = mat_pdf(m, a, n, b); *pba = mat_pdf(m, b, n, a);
+    }
+}
+
 // sample, :150-214.  RNG draws: 2 for H, then Dieletric 1 (+2 on the diffuse branch),
 // Transparent 1, Metal 0 — same order as the reference.
 TPT_DEV f3 mat_sample(const Mat& m, uint32_t& rng, f3 w_o, f3 n, float* pdf) {

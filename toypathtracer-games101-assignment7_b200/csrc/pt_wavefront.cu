@@ -52,7 +52,9 @@ struct PtBuffers {
 };
 
 __global__ void __launch_bounds__(256) k_pt_generate(SceneView g, RenderArgs a, PtBuffers b, unsigned long long* stats) {
+    pdl_launch_dependents();
     const SceneView sc = stage_scene(g, tpt_smem);
+    pdl_wait();
     int* cand = reinterpret_cast<int*>(tpt_smem + ((g.stage_bytes + 15u) & ~15u)) + threadIdx.x;
     unsigned long long rays = 0;
     for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < b.S; slot += gridDim.x * blockDim.x) {
@@ -75,7 +77,9 @@ __global__ void __launch_bounds__(256) k_pt_generate(SceneView g, RenderArgs a, 
 
 __global__ void __launch_bounds__(256, 3) k_pt_shade(SceneView g, RenderArgs a, PtBuffers b, int cur, float* radiance,
                                                      unsigned long long* stats) {
+    pdl_launch_dependents();
     const SceneView sc = stage_scene(g, tpt_smem);
+    pdl_wait();
     Ctx c;
     c.sc = sc; c.prune = true; c.cnt.node_visits = 0; c.cnt.prim_tests = 0; c.scene_rays = 0; c.probe_rays = 0;
     const unsigned n = b.ctr->n_active[cur];
@@ -231,9 +235,12 @@ __global__ void __launch_bounds__(256, 3) k_pt_shade(SceneView g, RenderArgs a, 
 }
 
 __global__ void __launch_bounds__(256) k_pt_extend(SceneView g, PtBuffers b, int cur, unsigned long long* stats) {
+    pdl_launch_dependents();
     const SceneView sc = stage_scene(g, tpt_smem);
+    pdl_wait();
     int* cand = reinterpret_cast<int*>(tpt_smem + ((g.stage_bytes + 15u) & ~15u)) + threadIdx.x;
     unsigned char* coop = trav_coop(tpt_smem, g.stage_bytes);
+    if (blockIdx.x == 0 && threadIdx.x == 0) b.ctr->n_active[cur ^ 1] = 0;   // the list k_pt_shade consumed: the next one is built there
     const unsigned n = b.ctr->n_active[cur];
     const int* list = b.active[cur];
     unsigned long long rays = 0;
@@ -255,7 +262,9 @@ __global__ void __launch_bounds__(256) k_pt_extend(SceneView g, PtBuffers b, int
 
 // Two shadow-ray slots per active slot: thread 2q+j handles ray j of queue entry q.
 __global__ void __launch_bounds__(256) k_pt_shadow(SceneView g, PtBuffers b, int cur, unsigned long long* stats) {
+    pdl_launch_dependents();
     const SceneView sc = stage_scene(g, tpt_smem);
+    pdl_wait();
     int* cand = reinterpret_cast<int*>(tpt_smem + ((g.stage_bytes + 15u) & ~15u)) + threadIdx.x;
     const unsigned n = b.ctr->n_active[cur];
     const int* list = b.active[cur];
@@ -278,8 +287,6 @@ __global__ void __launch_bounds__(256) k_pt_shadow(SceneView g, PtBuffers b, int
     }
     flush_stats(0, rays, 0, stats, rays);
 }
-
-__global__ void k_pt_reset(PtCounters* c, int next) { c->n_active[next] = 0; }
 
 }  // namespace
 
@@ -346,14 +353,13 @@ int pt_wavefront_render(TptScene* s, const RenderArgs& a, float* d_radiance, cud
     std::memset(&init, 0, sizeof init);
     init.n_active[0] = (unsigned)S;
     TPT_CUDA(cudaMemcpyAsync(b.ctr, &init, sizeof init, cudaMemcpyHostToDevice, st));
-    tm->begin(TPT_K_GENERATE); k_pt_generate<<<grid, 256, tsmem, st>>>(s->view, a, b, s->d_stats); tm->end();
+    tm->begin(TPT_K_GENERATE); launch_pdl(k_pt_generate, grid, tsmem, st, s->view, a, b, s->d_stats); tm->end();
     int cur = 0;
     const long long max_iters = (long long)a.spp * 4096 + 8;
     for (long long it = 0; it < max_iters; ++it) {
-        k_pt_reset<<<1, 1, 0, st>>>(b.ctr, cur ^ 1);
-        tm->begin(TPT_K_SHADE); k_pt_shade<<<grid, 256, smem, st>>>(s->view, a, b, cur, d_radiance, s->d_stats); tm->end();
-        tm->begin(TPT_K_EXTEND); k_pt_extend<<<grid, 256, tsmem, st>>>(s->view, b, cur ^ 1, s->d_stats); tm->end();
-        tm->begin(TPT_K_SHADOW); k_pt_shadow<<<grid, 256, TPT_SHADOW_SMEM(smem, 256), st>>>(s->view, b, cur ^ 1, s->d_stats); tm->end();
+        tm->begin(TPT_K_SHADE); launch_pdl(k_pt_shade, grid, smem, st, s->view, a, b, cur, d_radiance, s->d_stats); tm->end();
+        tm->begin(TPT_K_EXTEND); launch_pdl(k_pt_extend, grid, tsmem, st, s->view, b, cur ^ 1, s->d_stats); tm->end();
+        tm->begin(TPT_K_SHADOW); launch_pdl(k_pt_shadow, grid, (unsigned)TPT_SHADOW_SMEM(smem, 256), st, s->view, b, cur ^ 1, s->d_stats); tm->end();
         cur ^= 1;
         if ((it & 7) == 7) {
             TPT_CUDA(cudaMemcpyAsync(w->h_flag, &b.ctr->n_active[cur], sizeof(unsigned), cudaMemcpyDeviceToHost, st));

@@ -593,7 +593,7 @@ __global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_mis(SceneView g, RenderA
         // a Background end returns before any weighting (BDPT.cpp:180-185)
         const int endType = cam.last.type;
         if (endType != VT_BACKGROUND)
-            w = w / mis_denominator_shared(sc, cam, s, light, t, camAux, lightAux);
+            w = w / mis_denominator_paired(sc, cam, s, light, t, camAux, lightAux);
         w = finite_or_zero(mk3(std_max(w.x, 0.0f), std_max(w.y, 0.0f), std_max(w.z, 0.0f)));   // BDPT.cpp:299
         if (s > 1) {
             if (w.x != 0.0f || w.y != 0.0f || w.z != 0.0f) {
@@ -610,19 +610,6 @@ __global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_mis(SceneView g, RenderA
 }  // namespace
 
 // ---- host side -------------------------------------------------------------------------------
-// Launch with programmatic stream serialization: the grid may start while its predecessor in the
-// stream drains; it orders itself with pdl_wait() (wf_common.cuh).
-template <class... KArgs, class... Args>
-static void launch_pdl(void (*kernel)(KArgs...), int grid, unsigned smem, cudaStream_t st, Args... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
-}
-
 struct WavefrontState {
     int S = 0;
     WfBuffers b;

@@ -53,4 +53,17 @@ __device__ inline void flush_stats(unsigned long long ref_rays, unsigned long lo
 }
 
 
+// Launch with programmatic stream serialization: the grid may start while its predecessor in the
+// stream drains; it orders itself with pdl_wait() (wf_common.cuh).
+template <class... KArgs, class... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), int grid, unsigned smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace
