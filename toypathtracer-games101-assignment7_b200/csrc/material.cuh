@@ -132,6 +132,7 @@ TPT_DEV f3 mat_eval(const Mat& m, f3 wo, f3 wi, f3 N, bool combineCosineTerm) {
     const float nl = dotf(N, wi);
     const float nv = dotf(N, wo);
     if (nl == 0.0f || nv == 0.0f) return mk3(0.0f);
+    if (!(nl * nv > 0.0f) && m.type != 2) return mk3(0.0f);    // the `return 0` below, reached without the GGX terms
     const f3 h = half_dir(N, wi, wo, m.ior_d, nl, nv);
     const float nh = dotf_exact(N, h);      // GGX D is hypersensitive to cos(theta_h) for the near-specular materials
     const float lh = dotf(wi, h);
@@ -168,6 +169,7 @@ TPT_DEV f3 mat_eval(const Mat& m, f3 wo, f3 wi, f3 N, bool combineCosineTerm) {
 TPT_DEV float mat_pdf(const Mat& m, f3 w_o, f3 n, f3 w_i) {
     const float nv = dotf(n, w_o), nl = dotf(n, w_i);
     if (nv == 0.0f || nl == 0.0f) return 0.0f;
+    if (!(nv * nl > 0.0f) && m.type != 2) return 0.0f;          // both `return 0` paths below, reached early
     const f3 h = half_dir(n, w_i, w_o, m.ior_d, nl, nv);
     const float pdf_h = ggx_half_pdf(n, h, m.rough);
     const float vh = dotf(w_o, h);

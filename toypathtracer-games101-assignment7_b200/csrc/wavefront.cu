@@ -46,7 +46,7 @@ struct WfCounters {
 // info bits: [0] path (0 camera, 1 light)  [1..4] i = index of the last stored vertex
 //            [5..9] count  [10] pending ray  [11] light-first ray  [12] rr pass
 //            [13] waiting for pair space  [14] light-0 buffer parity  [15] ray left from cam[1]
-//            [16..20] nc of this sample
+//            [16..20] nc of this sample  [21] camera subpath ended on a Background vertex  [22] light subpath did
 #define INFO_PATH(i) ((i) & 1u)
 #define INFO_I(i) (((i) >> 1) & 15u)
 #define INFO_COUNT(i) (((i) >> 5) & 31u)
@@ -57,6 +57,8 @@ struct WfCounters {
 #define INFO_PARITY (1u << 14)
 #define INFO_FROM_C1 (1u << 15)
 #define INFO_NC(i) (((i) >> 16) & 31u)
+#define INFO_CAM_BG (1u << 21)
+#define INFO_LIGHT_BG (1u << 22)
 TPT_DEV unsigned make_info(unsigned path, unsigned i, unsigned count, unsigned flags, unsigned nc) {
     return path | (i << 1) | (count << 5) | flags | (nc << 16);
 }
@@ -76,6 +78,7 @@ struct WfBuffers {
     uint32_t* rng;
     unsigned* info;
     unsigned* spp_done;
+    unsigned* emask;                   // bit k: camera vertex k of the sample in flight lies on an emitter
     float4 *ray_o, *ray_d, *pend;      // {o, asfloat(cull), cull < 0: no ray} {d, srpdf} {alpha factor, 0}
     float4* hit;                       // {coords, asfloat(prim)}
     // rolling window: the vertex the pending ray left from (cur) and the one before it (prv), indexed
@@ -84,7 +87,7 @@ struct WfBuffers {
     int* active[2];
     // completed samples of this iteration
     int* done_slot;
-    unsigned* done_info;               // nc | nl << 8 | parity << 16
+    unsigned* done_info;               // nc | nl << 5 | parity << 10 | camBG << 11 | lightBG << 12 | bgStrategy << 13 | emask << 16
     unsigned* done_off;
     // strategies
     unsigned long long pair_cap;
@@ -186,6 +189,34 @@ template <class Fallback> struct AuxPair {
     TPT_DEV float2 operator()(int i) const { return i == i0 ? a0 : (i == i0 - 1 ? a1 : rest(i)); }
 };
 
+// ---- which strategies of a completed sample exist --------------------------------------------------
+// Of the nc * (nl + 1) - 1 strategies the reference loops over (BDPT.cpp:290-313), those with a
+// Background end contribute exactly zero (BDPT.cpp:180-187; (nc, 0) adds alpha * backgroundColor, zero
+// for a black background) and so do the t = 0 strategies whose camera vertex is not on an emitter
+// (BDPT.cpp:196-197).  k_shade knows both when the vertices are made, so those strategies are never
+// enumerated: connections s = 1..nc', t = 1..nl' (primes: without a Background end), then (s, 0) for the
+// emitter vertices, then (nc, 0) if the background is lit.
+TPT_DEV bool prim_emissive(const SceneView& sc, int prim) {
+    if (prim < 0) return false;
+    const float4 e = sc.mats[4 * prim_material(sc, prim)];
+    return !(e.x == 0.0f && e.y == 0.0f && e.z == 0.0f);
+}
+struct StrategySet { unsigned ncp, nlp, grid, emitters, ne, bg; };
+TPT_DEV StrategySet strategy_set(unsigned dinfo) {
+    StrategySet r;
+    const unsigned nc = dinfo & 31u, nl = (dinfo >> 5) & 31u;
+    r.ncp = nc - ((dinfo >> 11) & 1u); r.nlp = nl - ((dinfo >> 12) & 1u);
+    r.grid = r.ncp * r.nlp;
+    r.emitters = (dinfo >> 16) & ((1u << r.ncp) - 2u);        // camera vertices 1 .. ncp-1
+    r.ne = __popc(r.emitters);
+    r.bg = (dinfo >> 13) & 1u;
+    return r;
+}
+TPT_DEV unsigned strategy_count(unsigned dinfo) {
+    const StrategySet r = strategy_set(dinfo);
+    return r.grid + r.ne + r.bg;
+}
+
 // ---- generate: primary ray + hit, once per pixel (the primary ray is the same for every
 // sample: no jitter, Renderer.cpp:46) -----------------------------------------------------
 __global__ void __launch_bounds__(256) k_generate(SceneView g, RenderArgs a, WfBuffers b, unsigned long long* stats) {
@@ -206,6 +237,7 @@ __global__ void __launch_bounds__(256) k_generate(SceneView g, RenderArgs a, WfB
         b.c1A[slot] = b.verts[vtx_at(0, 1, slot)]; b.c1B[slot] = b.verts[vtx_at(0, 1, slot) + 1];
         b.rng[slot] = tpt_pixel_seed(a.seed_mode, (uint32_t)pixel, (uint32_t)a.stream);
         b.spp_done[slot] = 0;
+        b.emask[slot] = 0;
         b.info[slot] = make_info(0, 1, 2, 0, 0);
         b.active[0][slot] = slot;
     }
@@ -245,7 +277,8 @@ __global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfB
         int action = ACT_NONE;
         unsigned path = 0, i = 0, count = 0, nc = 0, parity = 0, flags = 0;
         uint32_t rng = 0;
-        unsigned spp_seen = 0;
+        unsigned spp_seen = 0, emask = 0, bgbits = 0;      // bgbits: INFO_CAM_BG / INFO_LIGHT_BG of the sample in flight
+        bool last_bg = false;                              // the subpath ending in this iteration ends on a Background vertex
         // the vertex the next ray leaves from (V) and its predecessor's position, kept in registers
         float4 VA = zero4, VB = zero4, c1A = zero4, c1B = zero4;
         f3 prev_x = mk3(0.0f);
@@ -254,6 +287,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfB
             // ---- every load of this iteration, issued together (all addressed by the slot alone)
             const unsigned info = b.info[slot];
             spp_seen = b.spp_done[slot];
+            emask = b.emask[slot];
             rng = b.rng[slot];
             const float4 hr = b.hit[slot], rd = b.ray_d[slot], pa = b.pend[slot];
             const float4 cA = b.curA[slot], cB = b.curB[slot], cC = b.curC[slot];
@@ -262,6 +296,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfB
 
             path = INFO_PATH(info); i = INFO_I(info); count = INFO_COUNT(info); nc = INFO_NC(info);
             parity = (info & INFO_PARITY) ? 1u : 0u;
+            bgbits = info & (INFO_CAM_BG | INFO_LIGHT_BG);
             const bool waiting = (info & INFO_WAIT) != 0;
             path_done = waiting;          // a waiting slot sits on a finished light subpath
             int cur_type = -1;            // type of vertex i, when known
@@ -283,7 +318,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfB
                     nv.alpha = afac;                       // SafeDivide(verts[0].alpha, pdf1), or 0 when pdf1 == 0
                     store_vertex(b.verts, vtx_at((int)path, 1, slot), nv);
                     i = 1; count = 2;
-                    if (srpdf == 0.0f && nv.type == VT_BACKGROUND) path_done = true;   // BDPT.cpp:85-88
+                    if (srpdf == 0.0f && nv.type == VT_BACKGROUND) { path_done = true; last_bg = true; }   // BDPT.cpp:85-88
                 } else {
                     const float rrProb = i > 4 ? .8f : 1.f;
                     if (!(info & INFO_RR_PASS) || !usable_pdf(nv.pdf)) {
@@ -292,6 +327,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfB
                         nv.pdf = nv.pdf * rrProb;
                         nv.alpha = (L.alpha * afac) / rrProb;
                         store_vertex(b.verts, vtx_at((int)path, (int)i + 1, slot), nv);
+                        if (path == 0 && prim_emissive(sc, nv.prim)) emask |= 1u << (i + 1);
                         // reverse pdf towards vertex i-1: it is appended behind vertex i whose
                         // predecessor is the new vertex i+1 (mis_denominator_shared reads it)
                         f3 tx, tN = mk3(0.0f);
@@ -321,7 +357,11 @@ __global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfB
 
             // ---- phase 2a: does the current subpath end here? (top of the FillPath loop, BDPT.cpp:98-99)
             fresh = !(info & INFO_PENDING) && !waiting;      // first iteration: nothing traced yet
-            if (!path_done && !fresh && (i >= MAX_BDPT_PATH_LENGTH - 1 || cur_type == VT_BACKGROUND)) path_done = true;
+            if (!path_done && !fresh && (i >= MAX_BDPT_PATH_LENGTH - 1 || cur_type == VT_BACKGROUND)) {
+                path_done = true;
+                last_bg = cur_type == VT_BACKGROUND;
+            }
+            if (path_done && !waiting && last_bg) bgbits |= path == 0 ? INFO_CAM_BG : INFO_LIGHT_BG;
             completing = path_done && path == 1;             // light subpath complete -> sample complete
             keep = true;
         }
@@ -332,8 +372,14 @@ __global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfB
             const unsigned cmask = __ballot_sync(0xffffffffu, completing);
             if (cmask) {
                 const unsigned lane = threadIdx.x & 31u;
+                // strategies that can contribute at all (strategy_count): a Background end only through (nc, 0) and a
+                // background colour, (s, 0) only from a camera vertex on an emitter — the others are exact zeros
                 const unsigned nl = count;
-                const unsigned npairs = completing ? nc * (nl + 1) - 1 : 0u;
+                const bool bg_lit = sc.background.x != 0.0f || sc.background.y != 0.0f || sc.background.z != 0.0f;
+                const unsigned dinfo = nc | (nl << 5) | (parity << 10) | ((bgbits & INFO_CAM_BG) ? 1u << 11 : 0u) |
+                                       ((bgbits & INFO_LIGHT_BG) ? 1u << 12 : 0u) |
+                                       (((bgbits & INFO_CAM_BG) && bg_lit) ? 1u << 13 : 0u) | (emask << 16);
+                const unsigned npairs = completing ? strategy_count(dinfo) : 0u;
                 unsigned incl = npairs;                      // inclusive prefix sum over the warp
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -356,7 +402,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfB
                         flags = INFO_WAIT;
                     } else {
                         b.done_slot[di] = slot;
-                        b.done_info[di] = nc | (nl << 8) | (parity << 16);
+                        b.done_info[di] = dinfo;
                         b.done_off[di] = (unsigned)off;
                         ref_rays += nc + nl;                 // BDPT.cpp:288
                         samples++;
@@ -378,6 +424,8 @@ __global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfB
             VA = c1A; VB = c1B; prev_x = mk3(sc.eye.x, sc.eye.y, sc.eye.z);
             flags = INFO_FROM_C1;
             path_done = unpack_type(__float_as_int(c1B.w)) == VT_BACKGROUND;
+            emask = prim_emissive(sc, unpack_prim(__float_as_int(c1B.w))) ? 2u : 0u;     // camera vertex 1
+            bgbits = path_done ? INFO_CAM_BG : 0u;
             if (path_done) flags = 0;
         }
         if (live && keep && !(flags & INFO_WAIT)) action = path_done ? ACT_LIGHT : ACT_EXTEND;
@@ -416,7 +464,8 @@ __global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfB
         if (live) {
             b.ray_o[slot] = ro;
             b.rng[slot] = rng;
-            b.info[slot] = make_info(path, i, count, flags | (parity ? INFO_PARITY : 0u), nc);
+            b.emask[slot] = emask;
+            b.info[slot] = make_info(path, i, count, flags | (parity ? INFO_PARITY : 0u) | bgbits, nc);
         }
         const unsigned at = wf_append(&b.ctr->n_active[cur ^ 1], keep);
         if (keep) next_list[at] = slot;
@@ -473,13 +522,15 @@ __global__ void __launch_bounds__(256) k_expand(WfBuffers b, int par) {
                     b.pair_rec[k] = make_uint2(0xffffffffu, 0u);
             continue;
         }
-        const unsigned nc = inf & 255u, nl = (inf >> 8) & 255u, parity = (inf >> 16) & 1u;
+        const unsigned nc = inf & 31u, parity = (inf >> 10) & 1u;
         const int slot = b.done_slot[di];
-        const unsigned np = nc * (nl + 1) - 1;
-        // strategy order of the reference loops (BDPT.cpp:290-313): s outer, t inner, (1,0) skipped
+        const StrategySet ss = strategy_set(inf);
+        const unsigned np = ss.grid + ss.ne + ss.bg;
         for (unsigned k = lane; k < np; k += 32) {
-            const unsigned j = k + 1;
-            const unsigned s = j / (nl + 1) + 1, t = j % (nl + 1);
+            unsigned s, t = 0u;
+            if (k < ss.grid) { s = k / ss.nlp + 1; t = k % ss.nlp + 1; }
+            else if (k < ss.grid + ss.ne) s = __fns(ss.emitters, 0u, (int)(k - ss.grid) + 1) + 1;      // z = cam[s-1] on an emitter
+            else s = nc;                                                                              // Background end, lit background
             b.pair_rec[off + k] = make_uint2((unsigned)slot, s | (t << 8) | (parity << 16));
         }
     }
@@ -642,7 +693,7 @@ static int wf_alloc(TptScene* s, int S) {
     if (b.pair_cap > 0x7fffffffull) b.pair_cap = 0x7fffffffull;
     bool ok = get(6 * V, (void**)&b.verts) && get(6 * F4, (void**)&b.l0) && get(F4, (void**)&b.c1A) && get(F4, (void**)&b.c1B) &&
               get((size_t)S * 4, (void**)&b.rng) && get((size_t)S * 4, (void**)&b.info) &&
-              get((size_t)S * 4, (void**)&b.spp_done) && get(F4, (void**)&b.ray_o) && get(F4, (void**)&b.ray_d) &&
+              get((size_t)S * 4, (void**)&b.spp_done) && get((size_t)S * 4, (void**)&b.emask) && get(F4, (void**)&b.ray_o) && get(F4, (void**)&b.ray_d) &&
               get(F4, (void**)&b.pend) && get(F4, (void**)&b.hit) && get(F4, (void**)&b.curA) && get(F4, (void**)&b.curB) &&
               get(F4, (void**)&b.curC) && get(F4, (void**)&b.prvA) && get(F4, (void**)&b.prvB) && get((size_t)S * 4, (void**)&b.active[0]) &&
               get((size_t)S * 4, (void**)&b.active[1]) && get((size_t)S * 4, (void**)&b.done_slot) &&
