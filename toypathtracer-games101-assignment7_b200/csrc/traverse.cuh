@@ -242,24 +242,33 @@ TPT_DEV int flat_next(unsigned& m0, unsigned& m1) {      // lowest set bit = nex
 }
 
 // The walk of closest_hit_deferred: records the leaves the ray reaches; a full column is settled in place.
+// Large scenes (no flat leaf list) settle every TPT_WALK_FLUSH candidates and then skip the subtrees that
+// start beyond the best hit so far — the pruning of closest_hit_range (same margin, same argument: nothing
+// that could hold a hit at t <= best is skipped and the visit order is unchanged, so the winner and its
+// tie-break are the reference's).
+#ifndef TPT_WALK_FLUSH
+#define TPT_WALK_FLUSH 1
+#endif
 template <bool PLAIN>
 TPT_DEV int walk_record(const SceneView& sc, const DRay& r, int cull, int first, int end, int* cand, int stride,
                         int& best, double& best_t) {
     int nc = 0;
     int i = first;
+    float prune_t = FLT_MAX;
     while (i < end) {
         const float4 n0 = sc.nodes[2 * i], n1 = sc.nodes[2 * i + 1];
         float nmin;
-        const bool in = slab_test_t<PLAIN>(n0, n1, r, &nmin);
+        const bool in = slab_test_t<PLAIN>(n0, n1, r, &nmin) && !(nmin > prune_t);
         const int prim = __float_as_int(n0.w);
         i = in ? i + 1 : __float_as_int(n1.w);
         if (in && prim >= 0) {
-            if (nc == TPT_CAND_MAX) {            // column full (rare): settle what is recorded, in order
-                for (int k = 0; k < TPT_CAND_MAX; ++k) settle_candidate(sc, r, cull, cand[k * stride], best, best_t);
-                nc = 0;
-            }
             cand[nc * stride] = prim;
             nc++;
+            if (nc == TPT_WALK_FLUSH) {          // settle what is recorded, in order
+                for (int k = 0; k < TPT_WALK_FLUSH; ++k) settle_candidate(sc, r, cull, cand[k * stride], best, best_t);
+                nc = 0;
+                if (best >= 0) prune_t = (float)best_t * 1.0001f + 1e-3f;
+            }
         }
     }
     return nc;
@@ -302,6 +311,9 @@ TPT_DEV bool shadow_candidate(const SceneView& sc, const DRay& r, int cull, int 
     const f3 d1 = x_sub(x_madd(r.o, r.d, (float)t), from);
     return dotd(d1, d1) < limit;
 }
+#ifndef TPT_SHADOW_FLUSH
+#define TPT_SHADOW_FLUSH 1
+#endif
 template <bool PLAIN>
 TPT_DEV int shadow_walk_record(const SceneView& sc, const DRay& r, int cull, f3 from, double limit, float reach,
                                int* cand, int stride, bool& found) {
@@ -314,12 +326,12 @@ TPT_DEV int shadow_walk_record(const SceneView& sc, const DRay& r, int cull, f3 
         const int prim = __float_as_int(n0.w);
         i = in ? i + 1 : __float_as_int(n1.w);
         if (in && prim >= 0) {
-            if (nc == TPT_CAND_MAX) {
-                for (int k = 0; k < TPT_CAND_MAX && !found; ++k) found = shadow_candidate(sc, r, cull, cand[k * stride], from, limit);
-                nc = 0;
-            }
             cand[nc * stride] = prim;
             nc++;
+            if (nc == TPT_SHADOW_FLUSH) {        // test what is recorded: a blocking hit ends the walk
+                for (int k = 0; k < TPT_SHADOW_FLUSH && !found; ++k) found = shadow_candidate(sc, r, cull, cand[k * stride], from, limit);
+                nc = 0;
+            }
         }
     }
     return nc;
