@@ -79,11 +79,12 @@ struct WfBuffers {
     unsigned* info;
     unsigned* spp_done;
     unsigned* emask;                   // bit k: camera vertex k of the sample in flight lies on an emitter
-    float4 *ray_o, *ray_d, *pend;      // {o, asfloat(cull), cull < 0: no ray} {d, srpdf} {alpha factor, 0}
+    float4 *ray_o, *ray_d, *pend;      // {o, asfloat(cull), cull < 0: no ray} {d, srpdf} {alpha factor, srpdf}
     float4* hit;                       // {coords, asfloat(prim)}
-    // rolling window: the vertex the pending ray left from (cur) and the one before it (prv), indexed
-    // by slot alone so that k_shade can issue every load of an iteration at once
-    float4 *curA, *curB, *curC, *prvA, *prvB;
+    // the vertex the pending ray left from, once more, indexed by slot alone so that k_shade can issue
+    // every load of an iteration at once
+    float4 *curA, *curB, *curC;
+    float4* back;                      // {unit vector from that vertex to its predecessor, |cos cos'| / dist^2 between the two}
     int* active[2];
     // completed samples of this iteration
     int* done_slot;
@@ -281,7 +282,8 @@ __global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfB
         bool last_bg = false;                              // the subpath ending in this iteration ends on a Background vertex
         // the vertex the next ray leaves from (V) and its predecessor's position, kept in registers
         float4 VA = zero4, VB = zero4, c1A = zero4, c1B = zero4;
-        f3 prev_x = mk3(0.0f);
+        f3 prev_x = mk3(0.0f), prev_N = mk3(0.0f);
+        int prev_type = VT_CAMERA;
         bool path_done = false, completing = false, fresh = false;
         if (live) {
             // ---- every load of this iteration, issued together (all addressed by the slot alone)
@@ -289,9 +291,8 @@ __global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfB
             spp_seen = b.spp_done[slot];
             emask = b.emask[slot];
             rng = b.rng[slot];
-            const float4 hr = b.hit[slot], rd = b.ray_d[slot], pa = b.pend[slot];
-            const float4 cA = b.curA[slot], cB = b.curB[slot], cC = b.curC[slot];
-            const float4 pA = b.prvA[slot], pB = b.prvB[slot];
+            const float4 hr = b.hit[slot], pa = b.pend[slot];
+            const float4 cA = b.curA[slot], cB = b.curB[slot], cC = b.curC[slot], bk = b.back[slot];
             c1A = b.c1A[slot]; c1B = b.c1B[slot];
 
             path = INFO_PATH(info); i = INFO_I(info); count = INFO_COUNT(info); nc = INFO_NC(info);
@@ -309,9 +310,9 @@ __global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfB
                 h.prim = __float_as_int(hr.w); h.coords = mk3(hr); h.t = 0.0;
                 h.normal = h.prim >= 0 ? hit_normal(sc, h.prim, h.coords) : mk3(0.0f);
                 PVert nv = vertex_from_hit(h);
-                const float srpdf = rd.w;
+                const float srpdf = pa.w;
                 const f3 afac = mk3(pa);
-                // L: the vertex the ray left from; T: the vertex before it (target of the reverse pdf)
+                // L: the vertex the ray left from
                 const PVert L = c1 ? unpack_vertex(c1A, c1B, make_float4(1.f, 1.f, 1.f, 0.f)) : unpack_vertex(cA, cB, cC);
                 nv.pdf = srpdf_to_area(srpdf, L.x, L.N, L.type, nv.x, nv.N, nv.type);
                 if (lf) {
@@ -328,17 +329,20 @@ __global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfB
                         nv.alpha = (L.alpha * afac) / rrProb;
                         store_vertex(b.verts, vtx_at((int)path, (int)i + 1, slot), nv);
                         if (path == 0 && prim_emissive(sc, nv.prim)) emask |= 1u << (i + 1);
-                        // reverse pdf towards vertex i-1: it is appended behind vertex i whose
-                        // predecessor is the new vertex i+1 (mis_denominator_shared reads it)
-                        f3 tx, tN = mk3(0.0f);
-                        int tt;
-                        float* dst;
-                        if (c1) { tx = mk3(sc.eye.x, sc.eye.y, sc.eye.z); tt = VT_CAMERA; dst = &b.verts[vtx_at(0, 0, slot) + 2].w; }
-                        else {
-                            tx = mk3(pA); tN = mk3(pB); tt = unpack_type(__float_as_int(pB.w));
-                            dst = i >= 2 ? &b.verts[vtx_at((int)path, (int)i - 1, slot) + 2].w : &b.l0[l0_at((int)parity, slot) + 2].w;
+                        // reverse pdf towards vertex i-1: it is appended behind vertex i whose predecessor is the
+                        // new vertex i+1 (mis_denominator reads it).  append_pdf_base (BDPT.cpp:141-161) with the
+                        // half that only involves vertices i and i-1 — the unit vector between them and the
+                        // area-measure factor — formed when the ray left vertex i (phase 3, `back`)
+                        {
+                            const f3 w = mk3(bk);
+                            const float cosine = fabsf(dotf(w, L.N));
+                            float rsr = 0.0f;
+                            if (cosine != 0.0f)
+                                rsr = safe_div(mat_pdf(load_mat(sc, prim_material(sc, L.prim)), s_normalize(nv.x - L.x), L.N, w), cosine);
+                            float* dst = i >= 2 ? &b.verts[vtx_at((int)path, (int)i - 1, slot) + 2].w
+                                                : (path == 1 ? &b.l0[l0_at((int)parity, slot) + 2].w : &b.verts[vtx_at(0, 0, slot) + 2].w);
+                            *dst = rsr * bk.w;
                         }
-                        *dst = append_pdf_base(sc, L, L.type, nv.x, tx, tN, tt);
                         count++; i++;
                     }
                 }
@@ -346,9 +350,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfB
                     // slide the window: the new vertex is the one the next ray leaves from
                     VA = make_float4(nv.x.x, nv.x.y, nv.x.z, nv.pdf);
                     VB = make_float4(nv.N.x, nv.N.y, nv.N.z, __int_as_float(pack_pt(nv.prim, nv.type)));
-                    prev_x = L.x;
-                    b.prvA[slot] = make_float4(L.x.x, L.x.y, L.x.z, L.pdf);
-                    b.prvB[slot] = make_float4(L.N.x, L.N.y, L.N.z, __int_as_float(pack_pt(L.prim, L.type)));
+                    prev_x = L.x; prev_N = L.N; prev_type = L.type;
                     b.curA[slot] = VA; b.curB[slot] = VB;
                     b.curC[slot] = make_float4(nv.alpha.x, nv.alpha.y, nv.alpha.z, 0.0f);
                     cur_type = nv.type;
@@ -421,7 +423,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfB
         // ---- phase 2c: a fresh camera subpath starts at the cached primary hit; pick the action
         if (fresh) {
             path = 0; i = 1; count = 2; nc = 0;
-            VA = c1A; VB = c1B; prev_x = mk3(sc.eye.x, sc.eye.y, sc.eye.z);
+            VA = c1A; VB = c1B; prev_x = mk3(sc.eye.x, sc.eye.y, sc.eye.z); prev_type = VT_CAMERA;
             flags = INFO_FROM_C1;
             path_done = unpack_type(__float_as_int(c1B.w)) == VT_BACKGROUND;
             emask = prim_emissive(sc, unpack_prim(__float_as_int(c1B.w))) ? 2u : 0u;     // camera vertex 1
@@ -438,11 +440,20 @@ __global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfB
             const int Vprim = unpack_prim(__float_as_int(VB.w));
             const f3 w_o = s_normalize(prev_x - Vx);
             const NextSample s = sample_next_dir(sc, rng, VN, Vprim, w_o);
+            {
+                // what the reverse pdf towards vertex i-1 needs from this side (phase 1 of the next iteration
+                // finishes it): unit vector to the predecessor and |cos cos'| / dist^2 as SrpdfToAreaPdf forms them
+                float d2;
+                const f3 w = s_normalize_len2(prev_x - Vx, &d2);
+                const float cosine = fabsf(dotf(w, VN));
+                const float cosT = prev_type == VT_CAMERA ? 1.0f : fabsf(dotf(w, prev_N));
+                b.back[slot] = make_float4(w.x, w.y, w.z, fabsf(cosine * cosT / d2));
+            }
             const float rrProb = i > 4 ? .8f : 1.f;
             const bool rr_pass = !(rng_float(rng) > rrProb);      // drawn even when rrProb == 1 (quirk Q16)
             ro = make_float4(Vx.x, Vx.y, Vx.z, __int_as_float(s.cull));
             b.ray_d[slot] = make_float4(s.w_i.x, s.w_i.y, s.w_i.z, s.srpdf);
-            b.pend[slot] = make_float4(s.alpha.x, s.alpha.y, s.alpha.z, 0.0f);
+            b.pend[slot] = make_float4(s.alpha.x, s.alpha.y, s.alpha.z, s.srpdf);
             flags |= INFO_PENDING | (rr_pass ? INFO_RR_PASS : 0u);
         } else if (action == ACT_LIGHT) {
             // GenerateLightPath head (BDPT.cpp:61-77)
@@ -457,7 +468,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfB
             const f3 afac = ls.pdf1 != 0.0f ? safe_div(v0[0].alpha, ls.pdf1) : mk3(0.0f);
             ro = make_float4(v0[0].x.x, v0[0].x.y, v0[0].x.z, __int_as_float(0));
             b.ray_d[slot] = make_float4(ls.w_i.x, ls.w_i.y, ls.w_i.z, ls.pdf1);
-            b.pend[slot] = make_float4(afac.x, afac.y, afac.z, 0.0f);
+            b.pend[slot] = make_float4(afac.x, afac.y, afac.z, ls.pdf1);
             path = 1; i = 0; count = 1;
             flags = INFO_PENDING | INFO_LIGHT_FIRST;
         }
@@ -695,7 +706,7 @@ static int wf_alloc(TptScene* s, int S) {
               get((size_t)S * 4, (void**)&b.rng) && get((size_t)S * 4, (void**)&b.info) &&
               get((size_t)S * 4, (void**)&b.spp_done) && get((size_t)S * 4, (void**)&b.emask) && get(F4, (void**)&b.ray_o) && get(F4, (void**)&b.ray_d) &&
               get(F4, (void**)&b.pend) && get(F4, (void**)&b.hit) && get(F4, (void**)&b.curA) && get(F4, (void**)&b.curB) &&
-              get(F4, (void**)&b.curC) && get(F4, (void**)&b.prvA) && get(F4, (void**)&b.prvB) && get((size_t)S * 4, (void**)&b.active[0]) &&
+              get(F4, (void**)&b.curC) && get(F4, (void**)&b.back) && get((size_t)S * 4, (void**)&b.active[0]) &&
               get((size_t)S * 4, (void**)&b.active[1]) && get((size_t)S * 4, (void**)&b.done_slot) &&
               get((size_t)S * 4, (void**)&b.done_info) && get((size_t)S * 4, (void**)&b.done_off) &&
               get(b.pair_cap * sizeof(uint2), (void**)&b.pair_rec) && get(b.pair_cap * sizeof(float4), (void**)&b.pair_val) &&
