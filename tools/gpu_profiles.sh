@@ -1,11 +1,11 @@
 #!/bin/bash
 # the artefacts profiles/ holds for a round: bench line, launch list of the bench command, DRAM traffic per launch
 mkdir -p gpurun_out
-R=${ROUND:-r01c}
+R=${ROUND:-r01e}
 timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/${R}_bench.json 2> gpurun_out/bench.err; tail -c 600 gpurun_out/${R}_bench.json
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${R}_bench_reference.json 2>> gpurun_out/bench.err; tail -c 700 gpurun_out/${R}_bench_reference.json
 timeout 300 python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -s 1200 -c 1200 --csv --log-file gpurun_out/${R}_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu1.log 2>&1
 timeout 300 python tools/prof_render.py standard bdpt 16 > gpurun_out/plain2.log 2>&1 && \
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:'k_' -c 1200 --csv --log-file gpurun_out/${R}_traffic.csv python tools/prof_render.py standard bdpt 16 > gpurun_out/ncu2.log 2>&1
-tail -2 gpurun_out/ncu1.log gpurun_out/ncu2.log
+tail -n 2 gpurun_out/ncu1.log; tail -n 2 gpurun_out/ncu2.log

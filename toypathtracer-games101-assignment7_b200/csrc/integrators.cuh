@@ -91,16 +91,19 @@ TPT_DEV float object_pdf(const SceneView& sc, int obj) { return 1.0f / sc.objs[o
 
 // ======================================================================= PathTrace
 // DirectLightSampler::pdf, PathTracer.cpp:14-24
-template <bool COUNT> TPT_DEV float light_pdf(Ctx& c, int light, f3 x, f3 w_i) {
-    DHit h;
-    trace_object<COUNT>(c, light, make_ray(x, w_i), 2 /*NoCull*/, &h);
+TPT_DEV float light_pdf_from_hit(const SceneView& sc, int light, const DHit& h, f3 x, f3 w_i) {
     if (h.prim < 0) return 0.0f;
     const f3 d = h.coords - x;
     const float lightDistanceSqr = dotf(d, d);
-    const float rawpdf = object_pdf(c.sc, light);
+    const float rawpdf = object_pdf(sc, light);
     const float costhetap = dotf(h.normal, -w_i);
     if (costhetap == 0.0f) return 0.0f;
     return (float)((double)rawpdf * lightDistanceSqr / fabsf(costhetap));
+}
+template <bool COUNT> TPT_DEV float light_pdf(Ctx& c, int light, f3 x, f3 w_i) {
+    DHit h;
+    trace_object<COUNT>(c, light, make_ray(x, w_i), 2 /*NoCull*/, &h);
+    return light_pdf_from_hit(c.sc, light, h, x, w_i);
 }
 // DirectLightSampler::sample, PathTracer.cpp:26-40 (no `else` after the zero test: inf pdf, quirk Q11)
 TPT_DEV f3 light_sample_dir(Ctx& c, int light, uint32_t& rng, f3 x, float* pdf) {

@@ -75,7 +75,10 @@ __global__ void __launch_bounds__(256) k_pt_generate(SceneView g, RenderArgs a, 
     flush_stats(0, rays, 0, stats);
 }
 
-__global__ void __launch_bounds__(256, 3) k_pt_shade(SceneView g, RenderArgs a, PtBuffers b, int cur, float* radiance,
+#ifndef PT_SHADE_MIN_BLOCKS
+#define PT_SHADE_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(256, PT_SHADE_MIN_BLOCKS) k_pt_shade(SceneView g, RenderArgs a, PtBuffers b, int cur, float* radiance,
                                                      unsigned long long* stats) {
     pdl_launch_dependents();
     const SceneView sc = stage_scene(g, tpt_smem);
@@ -169,12 +172,16 @@ __global__ void __launch_bounds__(256, 3) k_pt_shade(SceneView g, RenderArgs a, 
             float pdf_light_light;
             const f3 w_i_light = light_sample_dir(c, light, rng, x, &pdf_light_light);
             const float pdf_light_bsdf = mat_pdf(mat, w_o, nrm, w_i_light);
-            const float pdf_bsdf_light = light_pdf<false>(c, light, x, w_i_bsdf);
+            // the light object along the BSDF direction, NoCull (DirectLightSampler::pdf) and CullBack (:93), in one walk
+            DHit hl, inte_bsdf;
+            object_intersect_dual(sc, light, make_ray(x, w_i_bsdf), &hl, &inte_bsdf);
+            c.probe_rays++;
+            const float pdf_bsdf_light = light_pdf_from_hit(sc, light, hl, x, w_i_bsdf);
             f3 E1 = mk3(0.0f), E2 = mk3(0.0f);
             float q1 = 0.0f, q2 = 0.0f;
             if (pdf_bsdf + pdf_bsdf_light > 0.0f) {
-                DHit inte;
-                trace_object<false>(c, light, make_ray(x, w_i_bsdf), 0, &inte);
+                const DHit inte = inte_bsdf;
+                c.probe_rays++;
                 if (inte.prim >= 0) {
                     E1 = mat_eval(mat, w_o, w_i_bsdf, nrm, true) / (TPT_EPSILON + pdf_bsdf + pdf_bsdf_light);
                     q1 = 1.0f;

@@ -507,6 +507,43 @@ TPT_DEV void object_intersect(const SceneView& sc, int obj, const DRay& r, int c
     closest_hit_range<COUNT>(sc, r, cull, o.root, o.end, prune, hit, cnt);
 }
 
+// The same object probed along ONE ray with NoCull and with CullBack at once — PathTrace asks the light object
+// both questions about the BSDF-sampled direction (DirectLightSampler::pdf, PathTracer.cpp:15, and the
+// visibility probe, PathTracer.cpp:93).  A triangle's intersection does not depend on the culling mode, only
+// whether it is tested at all (Triangle.cpp:80-88), so one walk tests every reached triangle once and keeps
+// two winners, each updated with the strict first-visited-wins rule over the triangles ITS mode accepts:
+// the two separate walks' results, bit for bit.  A sphere's root selection depends on the mode: two tests.
+TPT_DEV void object_intersect_dual(const SceneView& sc, int obj, const DRay& r, DHit* h_nocull, DHit* h_cullback) {
+    const DevObject o = sc.objs[obj];
+    if (o.kind == 1) {
+        TravCounters none;
+        object_intersect<false>(sc, obj, r, 2, false, h_nocull, &none);
+        object_intersect<false>(sc, obj, r, 0, false, h_cullback, &none);
+        return;
+    }
+    double tn = 0.0, tc = 0.0;
+    int bn = -1, bc = -1;
+    int i = o.root;
+    const bool plain = ray_is_plain(r);
+    while (i < o.end) {
+        const float4 n0 = sc.nodes[2 * i], n1 = sc.nodes[2 * i + 1];
+        float nmin;
+        const bool in = plain ? slab_test_plain(n0, n1, r, &nmin) : slab_test(n0, n1, r, &nmin);
+        const int prim = __float_as_int(n0.w);
+        i = in ? i + 1 : __float_as_int(n1.w);
+        if (in && prim >= 0) {
+            double t = 0.0;
+            if (triangle_test(sc, prim, r, 2, &t)) {
+                if (bn < 0 || tn > t) { bn = prim; tn = t; }
+                const bool accepted = !(dotd(r.d, mk3(sc.tris[4 * prim + 3])) > 0);      // CullBack, Triangle.cpp:80-83
+                if (accepted && (bc < 0 || tc > t)) { bc = prim; tc = t; }
+            }
+        }
+    }
+    finish_hit(sc, r, bn, tn, h_nocull);
+    finish_hit(sc, r, bc, tc, h_cullback);
+}
+
 // Scene::ShadowCheck(Vector3f lightCoords, Vector3f x, cull), Scene.cpp:37-48:
 // the ray leaves `from` toward `to`; shadowed iff the closest hit is more than
 // (squared distance - 1) short of `to`.
