@@ -17,6 +17,9 @@ render of that frame: 784*784*16 = 9 834 496 samples.  The metric is Msamples/s 
              HBM copy bandwidth of MEASURED_PEAKS.json.  The scene is a few KB and lives in shared
              memory, so these are instruction-bound kernels and the fraction is not a DRAM fraction (it
              exceeds 1); `traffic` is the measured DRAM bytes per launch (profiles/traffic.json, ncu).
+  ceilings   SURVEY.md 8(d)'s other two: the traversal figure against the L2 read bandwidth measured live
+             (tpt_probe_read_bandwidth over a 48 MB buffer) and the DRAM bytes of the WHOLE step (ncu, all
+             kernels, profiles/traffic.json) per second against the HBM peak.
   cpu_baseline  the compiled reference (oracle/_ref, kind "reference") or the restatement
              (oracle/liboracle.so, kind "port") on all host cores for a bounded sample (2 spp of the
              same frame), rank 0, N = 1 only.
@@ -58,6 +61,16 @@ def measured_traffic():
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             return json.load(f)["traversal_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+def step_dram_bytes():
+    """DRAM bytes of one whole step (all launches of every kernel), from the same ncu capture; None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            ks = json.load(f)["kernels"]
+        return sum(v["dram_bytes_per_launch"] * v["launches"] for v in ks.values())
     except Exception:
         return None
 
@@ -272,6 +285,21 @@ def main():
         rays = st["traced_rays"]
         achieved = rays * BYTES_PER_RAY / (trav_ms * 1e-3) / 1e9 if trav_ms > 0 else 0.0
         total_k = sum(k_ms.values())
+        # the traversal kernels against the L2 and HBM ceilings (both measured live with the
+        # library's streaming-read probe), and the DRAM traffic of the whole step against the HBM ceiling
+        l2_gbs = T.probe_read_bandwidth(48 << 20, 40, local_rank)
+        hbm_gbs = T.probe_read_bandwidth(4 << 30, 3, local_rank)
+        dram = step_dram_bytes()
+        step_ms = ms / args.steps
+        ceilings = {
+            "l2_read_gbs_measured": l2_gbs, "hbm_read_gbs_measured": hbm_gbs,
+            "traversal_algorithmic_gbs": achieved, "traversal_frac_of_l2": achieved / l2_gbs if l2_gbs else None,
+            "traversal_frac_of_hbm": achieved / peaks["hbm_gbs"],
+            "step_dram_bytes_ncu": dram,
+            "step_dram_gbs": dram / (step_ms * 1e-3) / 1e9 if dram else None,
+            "step_dram_frac_of_hbm": dram / (step_ms * 1e-3) / 1e9 / peaks["hbm_gbs"] if dram else None,
+            "note": "scene in shared memory: the traversal kernels read neither L2 nor HBM for it; the step as a "
+                    "whole is bound by instruction issue and HBM latency (profiles/*_ncu_summary.csv)"}
         line = {
             "metric": "Msamples/s", "value": world * SAMPLES_PER_STEP * args.steps / ms / 1e3, "unit": "Msamples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -291,6 +319,7 @@ def main():
                          "algorithmic_bytes_per_ray": BYTES_PER_RAY, "rays_per_step": rays,
                          "kernel_ms_per_step": trav_ms, "share_of_kernel_time": trav_ms / total_k if total_k else None,
                          "note": "scene (~5 KB) is staged in shared memory: instruction-bound, DRAM traffic ~0"},
+            "ceilings": ceilings,
             "kernel_ms_per_step": k_ms, "kernel_launches_per_step": st["kernel_launches"],
             "clocks": clocks, "image_mean_rgb": image_mean, "finite": finite,
         }

@@ -195,6 +195,12 @@ int tpt_scene_destroy(TptScene* scene);
  * dominated by cudaMalloc / cudaFree. */
 int tpt_release_cached_memory(void);
 
+/* Measurement aid for the roofline of the traversal kernels ("measure L2 peak on the box
+ * with a microbenchmark"): streams `bytes` of device memory `repeats` times with 128-bit loads from a
+ * persistent grid and reports the read bandwidth in GB/s.  A buffer well below the L2 size (126 MB on
+ * B200) measures L2, one well above it measures HBM.  No counterpart in the reference. */
+int tpt_probe_read_bandwidth(int device, size_t bytes, int repeats, double* gb_per_s);
+
 /* Page-locked host memory for the frame tpt_render writes (a plain malloc'ed buffer works
  * too, through the driver's staging copy).  NULL on failure. */
 void* tpt_host_alloc(size_t bytes);

@@ -68,3 +68,13 @@ def test_no_cpu_fallback_without_a_device(tpt):
         tpt.Scene(hs.desc)
     with pytest.raises(tpt.TptError, match="no CUDA device"):
         tpt.rng(1, 4)
+
+
+@pytest.mark.gpu
+def test_read_bandwidth_probe(tpt):
+    """tpt_probe_read_bandwidth (the L2 / HBM ceilings bench.py reports): an L2-resident buffer streams faster
+    than one far larger than the L2, and both are in the range a B200 can have."""
+    l2 = tpt.probe_read_bandwidth(48 << 20, 20)
+    hbm = tpt.probe_read_bandwidth(2 << 30, 2)
+    assert 1000.0 < hbm < 9000.0, hbm
+    assert l2 > hbm, (l2, hbm)

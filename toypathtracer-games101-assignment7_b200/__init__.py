@@ -325,6 +325,14 @@ def release_cached_memory():
     _check(lib().tpt_release_cached_memory())
 
 
+def probe_read_bandwidth(nbytes, repeats=20, device=0):
+    """tpt_probe_read_bandwidth: GB/s of streaming `nbytes` of device memory `repeats` times (L2 when the
+    buffer is far below the L2 size, HBM when far above)."""
+    out = C.c_double(0.0)
+    _check(lib().tpt_probe_read_bandwidth(C.c_int(device), C.c_size_t(nbytes), C.c_int(repeats), C.byref(out)))
+    return out.value
+
+
 def rng(seed, n):
     st = np.empty(n, np.uint32); fl = np.empty(n, np.float32)
     _check(lib().tpt_rng_batch(C.c_uint32(seed), C.c_size_t(n), _p(st), _p(fl)))

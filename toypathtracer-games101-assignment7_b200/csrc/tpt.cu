@@ -113,6 +113,44 @@ static int require_device(int device) {
     return TPT_OK;
 }
 
+// ---- read-bandwidth probe (tpt_probe_read_bandwidth) -----------------------------------------------
+__global__ void __launch_bounds__(256) k_probe_read(const float4* __restrict__ p, size_t n4, int repeats, float* sink) {
+    float acc = 0.0f;
+    for (int r = 0; r < repeats; ++r)
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+            const float4 v = p[i];
+            acc += v.x + v.y + v.z + v.w;
+        }
+    if (acc == 1.2345e-30f) *sink = acc;      // never true for a zeroed buffer: keeps the loads alive
+}
+extern "C" int tpt_probe_read_bandwidth(int device, size_t bytes, int repeats, double* gb_per_s) {
+    if (!gb_per_s || bytes < 16 || repeats < 1) { tpt_set_error("tpt_probe_read_bandwidth: bad arguments"); return TPT_ERR_INVALID; }
+    int rc = require_device(device);
+    if (rc != TPT_OK) return rc;
+    cudaDeviceProp prop;
+    TPT_CUDA(cudaGetDeviceProperties(&prop, device));
+    const size_t n4 = bytes / 16;
+    float4* buf = static_cast<float4*>(tpt_dev_alloc(n4 * 16 + 16));
+    if (!buf) return TPT_ERR_OOM;
+    TPT_CUDA(cudaMemset(buf, 0, n4 * 16 + 16));
+    float* sink = reinterpret_cast<float*>(buf + n4);
+    const int grid = prop.multiProcessorCount * 8;
+    cudaEvent_t e0, e1;
+    TPT_CUDA(cudaEventCreate(&e0)); TPT_CUDA(cudaEventCreate(&e1));
+    k_probe_read<<<grid, 256>>>(buf, n4, 1, sink);      // warm-up: page tables, L2 fill
+    TPT_CUDA(cudaEventRecord(e0));
+    k_probe_read<<<grid, 256>>>(buf, n4, repeats, sink);
+    TPT_CUDA(cudaEventRecord(e1));
+    TPT_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.0f;
+    TPT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    tpt_dev_free(buf);
+    TPT_CUDA(cudaGetLastError());
+    *gb_per_s = (double)n4 * 16.0 * repeats / (ms * 1e-3) / 1e9;
+    return TPT_OK;
+}
+
 // ------------------------------------------------------------------ scene builder
 namespace {
 

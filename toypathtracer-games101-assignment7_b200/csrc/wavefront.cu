@@ -261,7 +261,10 @@ TPT_DEV PVert unpack_vertex(const float4 a, const float4 b, const float4 c) {
     return v;
 }
 
-__global__ void __launch_bounds__(256, 3) k_shade(SceneView g, RenderArgs a, WfBuffers b, int cur, int par, unsigned long long* stats) {
+#ifndef SHADE_MIN_BLOCKS
+#define SHADE_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(256, SHADE_MIN_BLOCKS) k_shade(SceneView g, RenderArgs a, WfBuffers b, int cur, int par, unsigned long long* stats) {
     pdl_launch_dependents();
     const SceneView sc = stage_scene(g, tpt_smem);
     pdl_wait();
