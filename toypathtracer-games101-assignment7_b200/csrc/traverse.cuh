@@ -197,7 +197,9 @@ TPT_DEV void closest_hit_range(const SceneView& sc, const DRay& r, int cull, int
 // lanes together.  No pruning (a hit is not known during the walk): the walk visits exactly the
 // nodes BVH.cpp:103-143 visits, and the strict first-visited-wins update is applied in the
 // recorded order, so the winner is the reference's by construction.
-#define TPT_CAND_MAX 12           /* candidates recorded per ray before an in-walk flush */
+#ifndef TPT_CAND_MAX
+#define TPT_CAND_MAX 12           /* per-thread column of recorded candidates (>= TPT_WALK_FLUSH, TPT_SHADOW_FLUSH) */
+#endif
 #define TPT_CAND_BYTES(threads) ((threads) * TPT_CAND_MAX * 4)
 
 TPT_DEV void settle_candidate(const SceneView& sc, const DRay& r, int cull, int prim, int& best, double& best_t) {
