@@ -191,6 +191,11 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    # stdout carries the ONE JSON line and nothing else: whatever libraries print while the bench runs
+    # (NCCL's version banner at communicator creation, for one) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
 
     import numpy as np
     import torch
@@ -327,7 +332,8 @@ def main():
             cb = cpu_baseline()
             cb.pop("seconds", None)
             line["cpu_baseline"] = cb
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     return 0
