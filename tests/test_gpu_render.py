@@ -81,6 +81,29 @@ def test_bdpt_pipelines_agree_per_pixel(tpt, scene):
     s.close()
 
 
+def test_lit_background_strategies_agree_with_the_reference_loops(tpt):
+    """The wavefront pipeline never enumerates strategies that are exact zeros (a Background end, a t = 0 camera
+    vertex off the emitters).  With a LIT background the (nc, 0) strategy of a camera subpath that leaves the
+    scene is not zero (BDPT.cpp:182-183): it must survive the screening.  Same streams, same image as the
+    per-pixel kernel that runs the reference's full strategy loop, and against the oracle within the tier."""
+    from conftest import desc_from_golden, product_desc
+    from oracle import bindings as B
+    d, keep = desc_from_golden("standard", 96, 96)
+    d.background = B.Vec3(0.25, 0.5, 1.0)
+    s = tpt.Scene(product_desc(d), device=0)
+    a, sa = s.render("bdpt", 6, pipeline=tpt.PIPE_WAVEFRONT)
+    b, sb = s.render("bdpt", 6, pipeline=tpt.PIPE_MEGAKERNEL)
+    assert sa["ref_rays"] == sb["ref_rays"]
+    assert np.isfinite(a).all()
+    err = np.abs(a - b) / (np.abs(b) + 1e-3)
+    assert np.percentile(err, 99.9) < 1e-3, np.percentile(err, 99.9)
+    assert a[0, 0].sum() > 0.1                      # the corner pixel looks past the box: it sees the background
+    orc = B.oracle_scene(d, keep)
+    ref, _, _ = orc.render(tpt.MODE_BDPT, 6, 2, 96, 96)
+    assert np.allclose(a.mean((0, 1)), ref.mean((0, 1)), rtol=0.02)
+    s.close()
+
+
 def test_pixel_interleave_partition_is_exact(tpt):
     """Renderer.cpp:38 striding across `world` calls: the union of the stripes is the 1-GPU image
     (PT bit for bit; BDPT up to the float-add order of the splats)."""

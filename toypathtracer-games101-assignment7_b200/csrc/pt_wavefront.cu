@@ -15,6 +15,7 @@
 // image is bit-reproducible run to run.  The pipeline handles one emissive object (all
 // BASELINE scenes); scenes with several lights use the per-pixel kernel (tpt.cu).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "wf_common.cuh"
@@ -302,12 +303,18 @@ struct PtWavefrontState {
     PtBuffers b;
     std::vector<void*> allocs;
     unsigned* h_flag = nullptr;
+    // k_pt_extend and k_pt_shadow both depend on k_pt_shade only: they run side by side on two streams
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_shade = nullptr, ev_side = nullptr;
 };
 
 void pt_wavefront_destroy(TptScene* s) {
     if (!s || !s->ptwf) return;
     for (void* p : s->ptwf->allocs) tpt_dev_free(p);
     if (s->ptwf->h_flag) tpt_pinned_free(s->ptwf->h_flag);
+    if (s->ptwf->side) cudaStreamDestroy(s->ptwf->side);
+    if (s->ptwf->ev_shade) cudaEventDestroy(s->ptwf->ev_shade);
+    if (s->ptwf->ev_side) cudaEventDestroy(s->ptwf->ev_side);
     delete s->ptwf;
     s->ptwf = nullptr;
 }
@@ -363,10 +370,21 @@ int pt_wavefront_render(TptScene* s, const RenderArgs& a, float* d_radiance, cud
     tm->begin(TPT_K_GENERATE); launch_pdl(k_pt_generate, grid, tsmem, st, s->view, a, b, s->d_stats); tm->end();
     int cur = 0;
     const long long max_iters = (long long)a.spp * 4096 + 8;
+    const char* env_two = getenv("TPT_WF_TWO_STREAMS");
+    const bool two = !tm->on && !(env_two && atoi(env_two) == 0);      // per-kernel timing needs one stream
+    if (two && !w->side) {
+        TPT_CUDA(cudaStreamCreateWithFlags(&w->side, cudaStreamNonBlocking));
+        TPT_CUDA(cudaEventCreateWithFlags(&w->ev_shade, cudaEventDisableTiming));
+        TPT_CUDA(cudaEventCreateWithFlags(&w->ev_side, cudaEventDisableTiming));
+    }
+    cudaStream_t ss = two ? w->side : st;
     for (long long it = 0; it < max_iters; ++it) {
+        if (two && it > 0) TPT_CUDA(cudaStreamWaitEvent(st, w->ev_side, 0));
         tm->begin(TPT_K_SHADE); launch_pdl(k_pt_shade, grid, smem, st, s->view, a, b, cur, d_radiance, s->d_stats); tm->end();
+        if (two) { TPT_CUDA(cudaEventRecord(w->ev_shade, st)); TPT_CUDA(cudaStreamWaitEvent(ss, w->ev_shade, 0)); }
         tm->begin(TPT_K_EXTEND); launch_pdl(k_pt_extend, grid, tsmem, st, s->view, b, cur ^ 1, s->d_stats); tm->end();
-        tm->begin(TPT_K_SHADOW); launch_pdl(k_pt_shadow, grid, (unsigned)TPT_SHADOW_SMEM(smem, 256), st, s->view, b, cur ^ 1, s->d_stats); tm->end();
+        tm->begin(TPT_K_SHADOW); launch_pdl(k_pt_shadow, grid, (unsigned)TPT_SHADOW_SMEM(smem, 256), ss, s->view, b, cur ^ 1, s->d_stats); tm->end();
+        if (two) TPT_CUDA(cudaEventRecord(w->ev_side, ss));
         cur ^= 1;
         if ((it & 7) == 7) {
             TPT_CUDA(cudaMemcpyAsync(w->h_flag, &b.ctr->n_active[cur], sizeof(unsigned), cudaMemcpyDeviceToHost, st));
@@ -374,6 +392,7 @@ int pt_wavefront_render(TptScene* s, const RenderArgs& a, float* d_radiance, cud
             if (w->h_flag[0] == 0) break;
         }
     }
+    if (two) TPT_CUDA(cudaStreamWaitEvent(st, w->ev_side, 0));
     TPT_CUDA(cudaGetLastError());
     return TPT_OK;
 }

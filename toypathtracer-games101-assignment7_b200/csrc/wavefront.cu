@@ -21,6 +21,7 @@
 // iterations cost only what is still alive.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "wf_common.cuh"
@@ -680,6 +681,10 @@ struct WavefrontState {
     WfBuffers b;
     std::vector<void*> allocs;
     unsigned* h_flag = nullptr;     // pinned: [0] n_active, [1] n_retired
+    // the strategy kernels of an iteration (expand / connect / shadow / MIS) depend on k_shade only, like k_extend:
+    // they run on a second stream beside k_extend and the next k_shade waits for both
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_shade = nullptr, ev_side = nullptr;
 };
 
 static int wf_alloc(TptScene* s, int S) {
@@ -724,6 +729,9 @@ void wavefront_destroy(TptScene* s) {
     if (!s || !s->wf) return;
     for (void* p : s->wf->allocs) tpt_dev_free(p);
     if (s->wf->h_flag) tpt_pinned_free(s->wf->h_flag);
+    if (s->wf->side) cudaStreamDestroy(s->wf->side);
+    if (s->wf->ev_shade) cudaEventDestroy(s->wf->ev_shade);
+    if (s->wf->ev_side) cudaEventDestroy(s->wf->ev_side);
     delete s->wf;
     s->wf = nullptr;
 }
@@ -754,14 +762,27 @@ int wavefront_render(TptScene* s, const RenderArgs& a, float* d_radiance, float*
     int cur = 0;
     // every sample needs at least 2 iterations; 31 is the longest a sample can take
     const long long max_iters = (long long)a.spp * 32 + 8;
+    // (per-kernel timing brackets launches with events on ONE stream: it runs the chain serially;
+    // TPT_WF_TWO_STREAMS=0 does the same, for A/B measurements)
+    const char* env_two = getenv("TPT_WF_TWO_STREAMS");
+    const bool two = !tm->on && !(env_two && atoi(env_two) == 0);
+    if (two && !w->side) {
+        TPT_CUDA(cudaStreamCreateWithFlags(&w->side, cudaStreamNonBlocking));
+        TPT_CUDA(cudaEventCreateWithFlags(&w->ev_shade, cudaEventDisableTiming));
+        TPT_CUDA(cudaEventCreateWithFlags(&w->ev_side, cudaEventDisableTiming));
+    }
+    cudaStream_t ss = two ? w->side : st;
     for (long long it = 0; it < max_iters; ++it) {
         const int par = (int)(it & 1);
+        if (two && it > 0) TPT_CUDA(cudaStreamWaitEvent(st, w->ev_side, 0));      // the previous side chain read the path store
         tm->begin(TPT_K_SHADE); launch_pdl(k_shade, grid, smem, st, s->view, a, b, cur, par, s->d_stats); tm->end();
+        if (two) { TPT_CUDA(cudaEventRecord(w->ev_shade, st)); TPT_CUDA(cudaStreamWaitEvent(ss, w->ev_shade, 0)); }
         tm->begin(TPT_K_EXTEND); launch_pdl(k_extend, grid, tsmem, st, s->view, a, b, cur ^ 1, par, s->d_stats); tm->end();
-        tm->begin(TPT_K_EXPAND); launch_pdl(k_expand, pgrid, 0u, st, b, par); tm->end();
-        tm->begin(TPT_K_CONNECT); launch_pdl(k_connect, pgrid, smem, st, s->view, b, par); tm->end();
-        tm->begin(TPT_K_SHADOW); launch_pdl(k_shadow_q, pgrid, (unsigned)TPT_SHADOW_SMEM(smem, 256), st, s->view, a, b, par, s->d_stats); tm->end();
-        tm->begin(TPT_K_MIS); launch_pdl(k_mis, pgrid, smem, st, s->view, a, b, par, d_radiance, d_splat); tm->end();
+        tm->begin(TPT_K_EXPAND); launch_pdl(k_expand, pgrid, 0u, ss, b, par); tm->end();
+        tm->begin(TPT_K_CONNECT); launch_pdl(k_connect, pgrid, smem, ss, s->view, b, par); tm->end();
+        tm->begin(TPT_K_SHADOW); launch_pdl(k_shadow_q, pgrid, (unsigned)TPT_SHADOW_SMEM(smem, 256), ss, s->view, a, b, par, s->d_stats); tm->end();
+        tm->begin(TPT_K_MIS); launch_pdl(k_mis, pgrid, smem, ss, s->view, a, b, par, d_radiance, d_splat); tm->end();
+        if (two) TPT_CUDA(cudaEventRecord(w->ev_side, ss));
         cur ^= 1;
         if ((it & 7) == 7 || it + 1 == max_iters) {
             TPT_CUDA(cudaMemcpyAsync(w->h_flag, &b.ctr->n_active[cur], sizeof(unsigned), cudaMemcpyDeviceToHost, st));
@@ -769,6 +790,7 @@ int wavefront_render(TptScene* s, const RenderArgs& a, float* d_radiance, float*
             if (w->h_flag[0] == 0) break;
         }
     }
+    if (two) TPT_CUDA(cudaStreamWaitEvent(st, w->ev_side, 0));
     TPT_CUDA(cudaGetLastError());
     return TPT_OK;
 }
