@@ -312,7 +312,7 @@ def main():
             "config": {"workload": "Cornell-Standard %dx%d BDPT %d spp" % (W, H, SPP), "scene": SCENE, "mode": MODE,
                        "spp_per_gpu": SPP, "pipeline": "wavefront", "seeds": "reference" if world == 1 else "split",
                        "cache": "working set per step (path store %.0f MB) exceeds the 126 MB L2" %
-                                (W * H * 32 * 48 / 1e6)},
+                                (W * H * 3 * 32 * 48 / 1e6)},
             "mrays_per_s": world * rays / (ms / args.steps) / 1e3,
             "traced_rays_per_step": rays, "ref_rays_per_step": st["ref_rays"],
             "e2e": {"value": world * SAMPLES_PER_STEP / e2e_ms / 1e3, "unit": "Msamples/s",

@@ -37,17 +37,19 @@ struct WfCounters {
     unsigned n_active[2];      // active queue lengths (double buffered)
     unsigned n_retired;        // slots that rendered all their spp
     unsigned pad;
-    // per-iteration counters, one set per iteration parity: the set of iteration i + 1 is cleared by
-    // k_extend of iteration i (no separate reset launch)
-    unsigned long long done_pairs[2];   // (done count << 40) | pair count, allocated together
-    unsigned long long shadow_mis[2];   // low word: shadow queue length, high word: MIS queue length (appended together)
+    // per-iteration counters, three sets used in rotation (iteration i uses set i % 3): the strategy kernels of
+    // iteration i may still be running while k_shade / k_extend of iteration i + 1 run, and k_extend of iteration
+    // i clears the set of iteration i + 1 (no separate reset launch)
+    unsigned long long done_pairs[3];   // (done count << 40) | pair count, allocated together
+    unsigned long long shadow_mis[3];   // low word: shadow queue length, high word: MIS queue length (appended together)
 };
 
 // ---- slot state ----------------------------------------------------------------------
 // info bits: [0] path (0 camera, 1 light)  [1..4] i = index of the last stored vertex
 //            [5..9] count  [10] pending ray  [11] light-first ray  [12] rr pass
-//            [13] waiting for pair space  [14] light-0 buffer parity  [15] ray left from cam[1]
+//            [13] waiting for pair space  [15] ray left from cam[1]
 //            [16..20] nc of this sample  [21] camera subpath ended on a Background vertex  [22] light subpath did
+//            [23..24] which copy of the path store this sample writes (vtx_at)
 #define INFO_PATH(i) ((i) & 1u)
 #define INFO_I(i) (((i) >> 1) & 15u)
 #define INFO_COUNT(i) (((i) >> 5) & 31u)
@@ -55,7 +57,7 @@ struct WfCounters {
 #define INFO_LIGHT_FIRST (1u << 11)
 #define INFO_RR_PASS (1u << 12)
 #define INFO_WAIT (1u << 13)
-#define INFO_PARITY (1u << 14)
+#define INFO_PARITY(i) (((i) >> 23) & 3u)
 #define INFO_FROM_C1 (1u << 15)
 #define INFO_NC(i) (((i) >> 16) & 31u)
 #define INFO_CAM_BG (1u << 21)
@@ -87,9 +89,9 @@ struct WfBuffers {
     float4 *curA, *curB, *curC;
     float4* back;                      // {unit vector from that vertex to its predecessor, |cos cos'| / dist^2 between the two}
     int* active[2];
-    // completed samples of this iteration
+    // completed samples of an iteration, three buffers used in rotation like the counters
     int* done_slot;
-    unsigned* done_info;               // nc | nl << 5 | parity << 10 | camBG << 11 | lightBG << 12 | bgStrategy << 13 | emask << 16
+    unsigned* done_info;               // nc | nl << 5 | camBG << 11 | lightBG << 12 | bgStrategy << 13 | parity << 14 | emask << 16
     unsigned* done_off;
     // strategies
     unsigned long long pair_cap;
@@ -102,8 +104,13 @@ struct WfBuffers {
     WfCounters* ctr;
 };
 
-TPT_DEV size_t vtx_at(int path, int k, int slot) { return (((size_t)slot * 2 + path) * MAX_BDPT_PATH_LENGTH + k) * 3; }
-TPT_DEV size_t l0_at(int parity, int slot) { return ((size_t)slot * 2 + parity) * 3; }
+// Three copies ("parities") of a slot's path store, used in rotation by its consecutive samples: the strategy
+// kernels of iteration i run beside k_shade / k_extend of iteration i + 1, a sample can complete one iteration
+// after the previous one (primary ray leaves the scene, light ray leaves the scene), so the sample after THAT
+// must not write where the first one is still being read.
+#define PATH_PARITIES 3
+TPT_DEV size_t vtx_at(int parity, int path, int k, int slot) { return ((((size_t)slot * PATH_PARITIES + parity) * 2 + path) * MAX_BDPT_PATH_LENGTH + k) * 3; }
+TPT_DEV size_t l0_at(int parity, int slot) { return ((size_t)slot * PATH_PARITIES + parity) * 3; }
 TPT_DEV void store_vertex(float4* w, size_t at, const PVert& v) {
     w[at] = make_float4(v.x.x, v.x.y, v.x.z, v.pdf);
     w[at + 1] = make_float4(v.N.x, v.N.y, v.N.z, __int_as_float(pack_pt(v.prim, v.type)));
@@ -111,9 +118,9 @@ TPT_DEV void store_vertex(float4* w, size_t at, const PVert& v) {
 }
 // {original area pdf of vertex i, reverse pdf towards vertex i (C.w, written by k_shade)}
 struct CamAux {
-    const WfBuffers& b; int slot;
+    const WfBuffers& b; int slot; int parity;
     TPT_DEV float2 operator()(int i) const {
-        const size_t at = vtx_at(0, i, slot);
+        const size_t at = vtx_at(parity, 0, i, slot);
         return make_float2(i == 0 ? CAMERA_ZERO_PDF : b.verts[at].w, b.verts[at + 2].w);
     }
 };
@@ -121,7 +128,7 @@ struct LightAux {
     const WfBuffers& b; int slot; int parity;
     TPT_DEV float2 operator()(int i) const {
         if (i == 0) { const size_t at = l0_at(parity, slot); return make_float2(b.l0[at].w, b.l0[at + 2].w); }
-        const size_t at = vtx_at(1, i, slot);
+        const size_t at = vtx_at(parity, 1, i, slot);
         return make_float2(b.verts[at].w, b.verts[at + 2].w);
     }
 };
@@ -139,11 +146,11 @@ struct StrategyVerts {
 template <bool ALPHA>
 TPT_DEV StrategyVerts fetch_strategy(const WfBuffers& b, const SceneView& sc, int slot, int s, int t, int parity) {
     StrategyVerts v;
-    const float4* z = b.verts + vtx_at(0, max(s - 1, 1), slot);
-    const float4* zp = b.verts + vtx_at(0, max(s - 2, 1), slot);
+    const float4* z = b.verts + vtx_at(parity, 0, max(s - 1, 1), slot);
+    const float4* zp = b.verts + vtx_at(parity, 0, max(s - 2, 1), slot);
     const float4* l0 = b.l0 + l0_at(parity, slot);
-    const float4* y = t <= 1 ? l0 : b.verts + vtx_at(1, t - 1, slot);      // light vertex 0 lives in the two-parity l0 array
-    const float4* yp = t <= 2 ? l0 : b.verts + vtx_at(1, t - 2, slot);
+    const float4* y = t <= 1 ? l0 : b.verts + vtx_at(parity, 1, t - 1, slot);      // light vertex 0 lives in the two-parity l0 array
+    const float4* yp = t <= 2 ? l0 : b.verts + vtx_at(parity, 1, t - 2, slot);
     v.zA = z[0]; v.zB = z[1];
     v.zpA = zp[0]; v.zpB = zp[1];
     v.yA = y[0]; v.yB = y[1];
@@ -155,8 +162,8 @@ TPT_DEV StrategyVerts fetch_strategy(const WfBuffers& b, const SceneView& sc, in
         for (int k = 0; k < 2; ++k) {
             const int ci = s - 3 - k, li = t - 3 - k;
             v.auxC[k] = v.auxL[k] = make_float2(0.f, 0.f);
-            if (ci >= 0) { const float4* c = b.verts + vtx_at(0, ci, slot); v.auxC[k] = make_float2(ci == 0 ? CAMERA_ZERO_PDF : c[0].w, c[2].w); }
-            if (li > 0) { const float4* l = b.verts + vtx_at(1, li, slot); v.auxL[k] = make_float2(l[0].w, l[2].w); }
+            if (ci >= 0) { const float4* c = b.verts + vtx_at(parity, 0, ci, slot); v.auxC[k] = make_float2(ci == 0 ? CAMERA_ZERO_PDF : c[0].w, c[2].w); }
+            if (li > 0) { const float4* l = b.verts + vtx_at(parity, 1, li, slot); v.auxL[k] = make_float2(l[0].w, l[2].w); }
             else if (li == 0) v.auxL[k] = make_float2(l0[0].w, l0[2].w);
         }
     }
@@ -235,8 +242,9 @@ __global__ void __launch_bounds__(256) k_generate(SceneView g, RenderArgs a, WfB
         rays++;
         PVert cam[2];
         camera_path_head(sc, h, cam);
-        store_vertex(b.verts, vtx_at(0, 1, slot), cam[1]);
-        b.c1A[slot] = b.verts[vtx_at(0, 1, slot)]; b.c1B[slot] = b.verts[vtx_at(0, 1, slot) + 1];
+        for (int par = 0; par < PATH_PARITIES; ++par)               // the same primary hit for every sample
+            store_vertex(b.verts, vtx_at(par, 0, 1, slot), cam[1]);
+        b.c1A[slot] = b.verts[vtx_at(0, 0, 1, slot)]; b.c1B[slot] = b.verts[vtx_at(0, 0, 1, slot) + 1];
         b.rng[slot] = tpt_pixel_seed(a.seed_mode, (uint32_t)pixel, (uint32_t)a.stream);
         b.spp_done[slot] = 0;
         b.emask[slot] = 0;
@@ -300,7 +308,7 @@ __global__ void __launch_bounds__(256, SHADE_MIN_BLOCKS) k_shade(SceneView g, Re
             c1A = b.c1A[slot]; c1B = b.c1B[slot];
 
             path = INFO_PATH(info); i = INFO_I(info); count = INFO_COUNT(info); nc = INFO_NC(info);
-            parity = (info & INFO_PARITY) ? 1u : 0u;
+            parity = INFO_PARITY(info);
             bgbits = info & (INFO_CAM_BG | INFO_LIGHT_BG);
             const bool waiting = (info & INFO_WAIT) != 0;
             path_done = waiting;          // a waiting slot sits on a finished light subpath
@@ -321,7 +329,7 @@ __global__ void __launch_bounds__(256, SHADE_MIN_BLOCKS) k_shade(SceneView g, Re
                 nv.pdf = srpdf_to_area(srpdf, L.x, L.N, L.type, nv.x, nv.N, nv.type);
                 if (lf) {
                     nv.alpha = afac;                       // SafeDivide(verts[0].alpha, pdf1), or 0 when pdf1 == 0
-                    store_vertex(b.verts, vtx_at((int)path, 1, slot), nv);
+                    store_vertex(b.verts, vtx_at((int)parity, (int)path, 1, slot), nv);
                     i = 1; count = 2;
                     if (srpdf == 0.0f && nv.type == VT_BACKGROUND) { path_done = true; last_bg = true; }   // BDPT.cpp:85-88
                 } else {
@@ -331,7 +339,7 @@ __global__ void __launch_bounds__(256, SHADE_MIN_BLOCKS) k_shade(SceneView g, Re
                     } else {
                         nv.pdf = nv.pdf * rrProb;
                         nv.alpha = (L.alpha * afac) / rrProb;
-                        store_vertex(b.verts, vtx_at((int)path, (int)i + 1, slot), nv);
+                        store_vertex(b.verts, vtx_at((int)parity, (int)path, (int)i + 1, slot), nv);
                         if (path == 0 && prim_emissive(sc, nv.prim)) emask |= 1u << (i + 1);
                         // reverse pdf towards vertex i-1: it is appended behind vertex i whose predecessor is the
                         // new vertex i+1 (mis_denominator reads it).  append_pdf_base (BDPT.cpp:141-161) with the
@@ -343,8 +351,8 @@ __global__ void __launch_bounds__(256, SHADE_MIN_BLOCKS) k_shade(SceneView g, Re
                             float rsr = 0.0f;
                             if (cosine != 0.0f)
                                 rsr = safe_div(mat_pdf(load_mat(sc, prim_material(sc, L.prim)), s_normalize(nv.x - L.x), L.N, w), cosine);
-                            float* dst = i >= 2 ? &b.verts[vtx_at((int)path, (int)i - 1, slot) + 2].w
-                                                : (path == 1 ? &b.l0[l0_at((int)parity, slot) + 2].w : &b.verts[vtx_at(0, 0, slot) + 2].w);
+                            float* dst = i >= 2 ? &b.verts[vtx_at((int)parity, (int)path, (int)i - 1, slot) + 2].w
+                                                : (path == 1 ? &b.l0[l0_at((int)parity, slot) + 2].w : &b.verts[vtx_at((int)parity, 0, 0, slot) + 2].w);
                             *dst = rsr * bk.w;
                         }
                         count++; i++;
@@ -382,7 +390,7 @@ __global__ void __launch_bounds__(256, SHADE_MIN_BLOCKS) k_shade(SceneView g, Re
                 // background colour, (s, 0) only from a camera vertex on an emitter — the others are exact zeros
                 const unsigned nl = count;
                 const bool bg_lit = sc.background.x != 0.0f || sc.background.y != 0.0f || sc.background.z != 0.0f;
-                const unsigned dinfo = nc | (nl << 5) | (parity << 10) | ((bgbits & INFO_CAM_BG) ? 1u << 11 : 0u) |
+                const unsigned dinfo = nc | (nl << 5) | (parity << 14) | ((bgbits & INFO_CAM_BG) ? 1u << 11 : 0u) |
                                        ((bgbits & INFO_LIGHT_BG) ? 1u << 12 : 0u) |
                                        (((bgbits & INFO_CAM_BG) && bg_lit) ? 1u << 13 : 0u) | (emask << 16);
                 const unsigned npairs = completing ? strategy_count(dinfo) : 0u;
@@ -402,14 +410,14 @@ __global__ void __launch_bounds__(256, SHADE_MIN_BLOCKS) k_shade(SceneView g, Re
                     if (off + npairs > b.pair_cap) {
                         // no room left this iteration: leave a void record (its range is marked
                         // invalid by k_expand) and complete the sample in a later iteration
-                        b.done_slot[di] = -1;
-                        b.done_info[di] = npairs;
-                        b.done_off[di] = off < b.pair_cap ? (unsigned)off : 0xffffffffu;
+                        b.done_slot[(size_t)par * b.S + di] = -1;
+                        b.done_info[(size_t)par * b.S + di] = npairs;
+                        b.done_off[(size_t)par * b.S + di] = off < b.pair_cap ? (unsigned)off : 0xffffffffu;
                         flags = INFO_WAIT;
                     } else {
-                        b.done_slot[di] = slot;
-                        b.done_info[di] = dinfo;
-                        b.done_off[di] = (unsigned)off;
+                        b.done_slot[(size_t)par * b.S + di] = slot;
+                        b.done_info[(size_t)par * b.S + di] = dinfo;
+                        b.done_off[(size_t)par * b.S + di] = (unsigned)off;
                         ref_rays += nc + nl;                 // BDPT.cpp:288
                         samples++;
                         const unsigned done = spp_seen + 1;
@@ -427,6 +435,8 @@ __global__ void __launch_bounds__(256, SHADE_MIN_BLOCKS) k_shade(SceneView g, Re
         // ---- phase 2c: a fresh camera subpath starts at the cached primary hit; pick the action
         if (fresh) {
             path = 0; i = 1; count = 2; nc = 0;
+            parity = (parity + 1u) % PATH_PARITIES;      // the new sample's vertices go to the next copy of the path store: the finished
+                                   // sample's stay readable for the strategy kernels running beside the next iterations
             VA = c1A; VB = c1B; prev_x = mk3(sc.eye.x, sc.eye.y, sc.eye.z); prev_type = VT_CAMERA;
             flags = INFO_FROM_C1;
             path_done = unpack_type(__float_as_int(c1B.w)) == VT_BACKGROUND;
@@ -462,7 +472,6 @@ __global__ void __launch_bounds__(256, SHADE_MIN_BLOCKS) k_shade(SceneView g, Re
         } else if (action == ACT_LIGHT) {
             // GenerateLightPath head (BDPT.cpp:61-77)
             nc = count;
-            parity ^= 1u;                                  // the finished sample's light vertex 0 stays readable
             PVert v0[1];
             const LightStart ls = light_path_head(sc, rng, sc.emissive[0], v0);
             store_vertex(b.l0, l0_at((int)parity, slot), v0[0]);
@@ -480,7 +489,7 @@ __global__ void __launch_bounds__(256, SHADE_MIN_BLOCKS) k_shade(SceneView g, Re
             b.ray_o[slot] = ro;
             b.rng[slot] = rng;
             b.emask[slot] = emask;
-            b.info[slot] = make_info(path, i, count, flags | (parity ? INFO_PARITY : 0u) | bgbits, nc);
+            b.info[slot] = make_info(path, i, count, flags | (parity << 23) | bgbits, nc);
         }
         const unsigned at = wf_append(&b.ctr->n_active[cur ^ 1], keep);
         if (keep) next_list[at] = slot;
@@ -498,8 +507,8 @@ __global__ void __launch_bounds__(256, TRAV_MIN_BLOCKS) k_extend(SceneView g, Re
     pdl_wait();
     if (blockIdx.x == 0 && threadIdx.x == 0) {      // the next iteration's counters (nothing in flight reads them)
         b.ctr->n_active[cur ^ 1] = 0;                // the list k_shade just consumed: the next one is built there
-        b.ctr->done_pairs[par ^ 1] = 0;
-        b.ctr->shadow_mis[par ^ 1] = 0;
+        b.ctr->done_pairs[(par + 1) % 3] = 0;
+        b.ctr->shadow_mis[(par + 1) % 3] = 0;
     }
     int* cand = reinterpret_cast<int*>(tpt_smem + ((g.stage_bytes + 15u) & ~15u)) + threadIdx.x;
     unsigned char* coop = trav_coop(tpt_smem, g.stage_bytes);
@@ -527,18 +536,20 @@ __global__ void __launch_bounds__(256) k_expand(WfBuffers b, int par) {
     pdl_launch_dependents();
     pdl_wait();
     const unsigned n_done = (unsigned)(b.ctr->done_pairs[par] >> 40);
+    const int* done_slot = b.done_slot + (size_t)par * b.S;
+    const unsigned *done_info = b.done_info + (size_t)par * b.S, *done_off = b.done_off + (size_t)par * b.S;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     for (unsigned di = warp; di < n_done; di += nwarps) {
-        const unsigned inf = b.done_info[di], off = b.done_off[di];
-        if (b.done_slot[di] < 0) {          // void record: invalidate the part of its range below the cap
+        const unsigned inf = done_info[di], off = done_off[di];
+        if (done_slot[di] < 0) {          // void record: invalidate the part of its range below the cap
             if (off != 0xffffffffu)
                 for (unsigned long long k = off + lane; k < b.pair_cap && k < (unsigned long long)off + inf; k += 32)
                     b.pair_rec[k] = make_uint2(0xffffffffu, 0u);
             continue;
         }
-        const unsigned nc = inf & 31u, parity = (inf >> 10) & 1u;
-        const int slot = b.done_slot[di];
+        const unsigned nc = inf & 31u, parity = (inf >> 14) & 3u;
+        const int slot = done_slot[di];
         const StrategySet ss = strategy_set(inf);
         const unsigned np = ss.grid + ss.ne + ss.bg;
         for (unsigned k = lane; k < np; k += 32) {
@@ -570,7 +581,7 @@ __global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_connect(SceneView g, WfB
             const int slot = (int)rec.x;
             const int s = rec.y & 255u, t = (rec.y >> 8) & 255u;
             const unsigned inf = rec.y;               // bit 16: light-vertex-0 parity
-            const StrategyVerts v = fetch_strategy<true>(b, sc, slot, s, t, (int)((inf >> 16) & 1u));
+            const StrategyVerts v = fetch_strategy<true>(b, sc, slot, s, t, (int)((inf >> 16) & 3u));
             const EndPair cam{unpack_vertex3(v.zA, v.zB, v.zC), unpack_vertex3(v.zpA, v.zpB, v.zC), s};
             const EndPair light{unpack_vertex3(v.yA, v.yB, v.yC), unpack_vertex3(v.ypA, v.ypB, v.yC), t};
             int needs_shadow;
@@ -648,12 +659,12 @@ __global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_mis(SceneView g, RenderA
         const int slot = (int)rec.x;
         const int s = rec.y & 255u, t = (rec.y >> 8) & 255u;
         const unsigned inf = rec.y;                   // bit 16: light-vertex-0 parity
-        const int parity = (int)((inf >> 16) & 1u);
+        const int parity = (int)((inf >> 16) & 3u);
         const float4 pv = b.pair_val[p];
         const StrategyVerts v = fetch_strategy<false>(b, sc, slot, s, t, parity);
         const EndPair cam{unpack_vertex3(v.zA, v.zB, v.zC), unpack_vertex3(v.zpA, v.zpB, v.zC), s};
         const EndPair light{unpack_vertex3(v.yA, v.yB, v.yC), unpack_vertex3(v.ypA, v.ypB, v.yC), t};
-        const AuxPair<CamAux> camAux{v.auxC[0], v.auxC[1], s - 3, CamAux{b, slot}};
+        const AuxPair<CamAux> camAux{v.auxC[0], v.auxC[1], s - 3, CamAux{b, slot, parity}};
         const AuxPair<LightAux> lightAux{v.auxL[0], v.auxL[1], t - 3, LightAux{b, slot, parity}};
         f3 w = mk3(pv);
         // a Background end returns before any weighting (BDPT.cpp:180-185)
@@ -681,10 +692,11 @@ struct WavefrontState {
     WfBuffers b;
     std::vector<void*> allocs;
     unsigned* h_flag = nullptr;     // pinned: [0] n_active, [1] n_retired
-    // the strategy kernels of an iteration (expand / connect / shadow / MIS) depend on k_shade only, like k_extend:
-    // they run on a second stream beside k_extend and the next k_shade waits for both
+    // the strategy kernels of an iteration (expand / connect / shadow / MIS) depend on k_shade only: they run on a
+    // second stream beside k_extend of the same iteration and k_shade / k_extend of the next one (k_shade of
+    // iteration i waits for the strategy kernels of iteration i - 2; see PATH_PARITIES)
     cudaStream_t side = nullptr;
-    cudaEvent_t ev_shade = nullptr, ev_side = nullptr;
+    cudaEvent_t ev_shade[2] = {nullptr, nullptr}, ev_side[2] = {nullptr, nullptr};
 };
 
 static int wf_alloc(TptScene* s, int S) {
@@ -710,13 +722,13 @@ static int wf_alloc(TptScene* s, int S) {
     // that a sample waiting for room always gets it once the queue has drained
     b.pair_cap = std::max<unsigned long long>((unsigned long long)S * 16ull, 1ull << 16);
     if (b.pair_cap > 0x7fffffffull) b.pair_cap = 0x7fffffffull;
-    bool ok = get(6 * V, (void**)&b.verts) && get(6 * F4, (void**)&b.l0) && get(F4, (void**)&b.c1A) && get(F4, (void**)&b.c1B) &&
+    bool ok = get(6 * PATH_PARITIES * V, (void**)&b.verts) && get(3 * PATH_PARITIES * F4, (void**)&b.l0) && get(F4, (void**)&b.c1A) && get(F4, (void**)&b.c1B) &&
               get((size_t)S * 4, (void**)&b.rng) && get((size_t)S * 4, (void**)&b.info) &&
               get((size_t)S * 4, (void**)&b.spp_done) && get((size_t)S * 4, (void**)&b.emask) && get(F4, (void**)&b.ray_o) && get(F4, (void**)&b.ray_d) &&
               get(F4, (void**)&b.pend) && get(F4, (void**)&b.hit) && get(F4, (void**)&b.curA) && get(F4, (void**)&b.curB) &&
               get(F4, (void**)&b.curC) && get(F4, (void**)&b.back) && get((size_t)S * 4, (void**)&b.active[0]) &&
-              get((size_t)S * 4, (void**)&b.active[1]) && get((size_t)S * 4, (void**)&b.done_slot) &&
-              get((size_t)S * 4, (void**)&b.done_info) && get((size_t)S * 4, (void**)&b.done_off) &&
+              get((size_t)S * 4, (void**)&b.active[1]) && get((size_t)S * 12, (void**)&b.done_slot) &&
+              get((size_t)S * 12, (void**)&b.done_info) && get((size_t)S * 12, (void**)&b.done_off) &&
               get(b.pair_cap * sizeof(uint2), (void**)&b.pair_rec) && get(b.pair_cap * sizeof(float4), (void**)&b.pair_val) &&
               get(b.pair_cap * 2 * sizeof(float4), (void**)&b.shadow_q) && get(b.pair_cap * sizeof(uint4), (void**)&b.mis_q) &&
               get(sizeof(WfCounters), (void**)&b.ctr);
@@ -730,8 +742,10 @@ void wavefront_destroy(TptScene* s) {
     for (void* p : s->wf->allocs) tpt_dev_free(p);
     if (s->wf->h_flag) tpt_pinned_free(s->wf->h_flag);
     if (s->wf->side) cudaStreamDestroy(s->wf->side);
-    if (s->wf->ev_shade) cudaEventDestroy(s->wf->ev_shade);
-    if (s->wf->ev_side) cudaEventDestroy(s->wf->ev_side);
+    for (int k = 0; k < 2; ++k) {
+        if (s->wf->ev_shade[k]) cudaEventDestroy(s->wf->ev_shade[k]);
+        if (s->wf->ev_side[k]) cudaEventDestroy(s->wf->ev_side[k]);
+    }
     delete s->wf;
     s->wf = nullptr;
 }
@@ -768,21 +782,24 @@ int wavefront_render(TptScene* s, const RenderArgs& a, float* d_radiance, float*
     const bool two = !tm->on && !(env_two && atoi(env_two) == 0);
     if (two && !w->side) {
         TPT_CUDA(cudaStreamCreateWithFlags(&w->side, cudaStreamNonBlocking));
-        TPT_CUDA(cudaEventCreateWithFlags(&w->ev_shade, cudaEventDisableTiming));
-        TPT_CUDA(cudaEventCreateWithFlags(&w->ev_side, cudaEventDisableTiming));
+        for (int k = 0; k < 2; ++k) {
+            TPT_CUDA(cudaEventCreateWithFlags(&w->ev_shade[k], cudaEventDisableTiming));
+            TPT_CUDA(cudaEventCreateWithFlags(&w->ev_side[k], cudaEventDisableTiming));
+        }
     }
     cudaStream_t ss = two ? w->side : st;
     for (long long it = 0; it < max_iters; ++it) {
-        const int par = (int)(it & 1);
-        if (two && it > 0) TPT_CUDA(cudaStreamWaitEvent(st, w->ev_side, 0));      // the previous side chain read the path store
+        const int par = (int)(it % 3), e = (int)(it & 1);
+        // the strategy kernels of iteration it - 2 read path-store halves and light starts that this k_shade may write
+        if (two && it >= 2) TPT_CUDA(cudaStreamWaitEvent(st, w->ev_side[e], 0));
         tm->begin(TPT_K_SHADE); launch_pdl(k_shade, grid, smem, st, s->view, a, b, cur, par, s->d_stats); tm->end();
-        if (two) { TPT_CUDA(cudaEventRecord(w->ev_shade, st)); TPT_CUDA(cudaStreamWaitEvent(ss, w->ev_shade, 0)); }
+        if (two) { TPT_CUDA(cudaEventRecord(w->ev_shade[e], st)); TPT_CUDA(cudaStreamWaitEvent(ss, w->ev_shade[e], 0)); }
         tm->begin(TPT_K_EXTEND); launch_pdl(k_extend, grid, tsmem, st, s->view, a, b, cur ^ 1, par, s->d_stats); tm->end();
         tm->begin(TPT_K_EXPAND); launch_pdl(k_expand, pgrid, 0u, ss, b, par); tm->end();
         tm->begin(TPT_K_CONNECT); launch_pdl(k_connect, pgrid, smem, ss, s->view, b, par); tm->end();
         tm->begin(TPT_K_SHADOW); launch_pdl(k_shadow_q, pgrid, (unsigned)TPT_SHADOW_SMEM(smem, 256), ss, s->view, a, b, par, s->d_stats); tm->end();
         tm->begin(TPT_K_MIS); launch_pdl(k_mis, pgrid, smem, ss, s->view, a, b, par, d_radiance, d_splat); tm->end();
-        if (two) TPT_CUDA(cudaEventRecord(w->ev_side, ss));
+        if (two) TPT_CUDA(cudaEventRecord(w->ev_side[e], ss));
         cur ^= 1;
         if ((it & 7) == 7 || it + 1 == max_iters) {
             TPT_CUDA(cudaMemcpyAsync(w->h_flag, &b.ctr->n_active[cur], sizeof(unsigned), cudaMemcpyDeviceToHost, st));
@@ -790,7 +807,7 @@ int wavefront_render(TptScene* s, const RenderArgs& a, float* d_radiance, float*
             if (w->h_flag[0] == 0) break;
         }
     }
-    if (two) TPT_CUDA(cudaStreamWaitEvent(st, w->ev_side, 0));
+    if (two) { TPT_CUDA(cudaStreamWaitEvent(st, w->ev_side[0], 0)); TPT_CUDA(cudaStreamWaitEvent(st, w->ev_side[1], 0)); }
     TPT_CUDA(cudaGetLastError());
     return TPT_OK;
 }
