@@ -1,7 +1,7 @@
 #!/bin/bash
 # the artefacts profiles/ holds for a round: bench line, launch list of the bench command, DRAM traffic per launch
 mkdir -p gpurun_out
-R=${ROUND:-r01e}
+R=${ROUND:-r01f}
 timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/${R}_bench.json 2> gpurun_out/bench.err; tail -c 600 gpurun_out/${R}_bench.json
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${R}_bench_reference.json 2>> gpurun_out/bench.err; tail -c 700 gpurun_out/${R}_bench_reference.json
 timeout 300 python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/plain.log 2>&1 && \
