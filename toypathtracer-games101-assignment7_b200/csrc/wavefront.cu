@@ -695,7 +695,8 @@ struct WavefrontState {
     // the strategy kernels of an iteration (expand / connect / shadow / MIS) depend on k_shade only: they run on a
     // second stream beside k_extend of the same iteration and k_shade / k_extend of the next one (k_shade of
     // iteration i waits for the strategy kernels of iteration i - 2; see PATH_PARITIES)
-    cudaStream_t side = nullptr;
+    cudaStream_t side[2] = {nullptr, nullptr};   // even / odd iterations: two strategy chains can be in flight
+    WfBuffers b_odd;                             // = b with the second set of strategy buffers (pair_*, shadow_q, mis_q)
     cudaEvent_t ev_shade[2] = {nullptr, nullptr}, ev_side[2] = {nullptr, nullptr};
 };
 
@@ -732,6 +733,9 @@ static int wf_alloc(TptScene* s, int S) {
               get(b.pair_cap * sizeof(uint2), (void**)&b.pair_rec) && get(b.pair_cap * sizeof(float4), (void**)&b.pair_val) &&
               get(b.pair_cap * 2 * sizeof(float4), (void**)&b.shadow_q) && get(b.pair_cap * sizeof(uint4), (void**)&b.mis_q) &&
               get(sizeof(WfCounters), (void**)&b.ctr);
+    w->b_odd = b;
+    ok = ok && get(b.pair_cap * sizeof(uint2), (void**)&w->b_odd.pair_rec) && get(b.pair_cap * sizeof(float4), (void**)&w->b_odd.pair_val) &&
+         get(b.pair_cap * 2 * sizeof(float4), (void**)&w->b_odd.shadow_q) && get(b.pair_cap * sizeof(uint4), (void**)&w->b_odd.mis_q);
     if (ok && !(w->h_flag = static_cast<unsigned*>(tpt_pinned_alloc(64)))) ok = false;
     if (!ok) { wavefront_destroy(s); return TPT_ERR_OOM; }
     return TPT_OK;
@@ -741,7 +745,7 @@ void wavefront_destroy(TptScene* s) {
     if (!s || !s->wf) return;
     for (void* p : s->wf->allocs) tpt_dev_free(p);
     if (s->wf->h_flag) tpt_pinned_free(s->wf->h_flag);
-    if (s->wf->side) cudaStreamDestroy(s->wf->side);
+    for (int k = 0; k < 2; ++k) if (s->wf->side[k]) cudaStreamDestroy(s->wf->side[k]);
     for (int k = 0; k < 2; ++k) {
         if (s->wf->ev_shade[k]) cudaEventDestroy(s->wf->ev_shade[k]);
         if (s->wf->ev_side[k]) cudaEventDestroy(s->wf->ev_side[k]);
@@ -780,25 +784,26 @@ int wavefront_render(TptScene* s, const RenderArgs& a, float* d_radiance, float*
     // TPT_WF_TWO_STREAMS=0 does the same, for A/B measurements)
     const char* env_two = getenv("TPT_WF_TWO_STREAMS");
     const bool two = !tm->on && !(env_two && atoi(env_two) == 0);
-    if (two && !w->side) {
-        TPT_CUDA(cudaStreamCreateWithFlags(&w->side, cudaStreamNonBlocking));
+    if (two && !w->side[0]) {
         for (int k = 0; k < 2; ++k) {
+            TPT_CUDA(cudaStreamCreateWithFlags(&w->side[k], cudaStreamNonBlocking));
             TPT_CUDA(cudaEventCreateWithFlags(&w->ev_shade[k], cudaEventDisableTiming));
             TPT_CUDA(cudaEventCreateWithFlags(&w->ev_side[k], cudaEventDisableTiming));
         }
     }
-    cudaStream_t ss = two ? w->side : st;
     for (long long it = 0; it < max_iters; ++it) {
         const int par = (int)(it % 3), e = (int)(it & 1);
+        cudaStream_t ss = two ? w->side[e] : st;
+        const WfBuffers& bs = (two && e) ? w->b_odd : b;      // strategy buffers of this chain
         // the strategy kernels of iteration it - 2 read path-store halves and light starts that this k_shade may write
         if (two && it >= 2) TPT_CUDA(cudaStreamWaitEvent(st, w->ev_side[e], 0));
         tm->begin(TPT_K_SHADE); launch_pdl(k_shade, grid, smem, st, s->view, a, b, cur, par, s->d_stats); tm->end();
         if (two) { TPT_CUDA(cudaEventRecord(w->ev_shade[e], st)); TPT_CUDA(cudaStreamWaitEvent(ss, w->ev_shade[e], 0)); }
         tm->begin(TPT_K_EXTEND); launch_pdl(k_extend, grid, tsmem, st, s->view, a, b, cur ^ 1, par, s->d_stats); tm->end();
-        tm->begin(TPT_K_EXPAND); launch_pdl(k_expand, pgrid, 0u, ss, b, par); tm->end();
-        tm->begin(TPT_K_CONNECT); launch_pdl(k_connect, pgrid, smem, ss, s->view, b, par); tm->end();
-        tm->begin(TPT_K_SHADOW); launch_pdl(k_shadow_q, pgrid, (unsigned)TPT_SHADOW_SMEM(smem, 256), ss, s->view, a, b, par, s->d_stats); tm->end();
-        tm->begin(TPT_K_MIS); launch_pdl(k_mis, pgrid, smem, ss, s->view, a, b, par, d_radiance, d_splat); tm->end();
+        tm->begin(TPT_K_EXPAND); launch_pdl(k_expand, pgrid, 0u, ss, bs, par); tm->end();
+        tm->begin(TPT_K_CONNECT); launch_pdl(k_connect, pgrid, smem, ss, s->view, bs, par); tm->end();
+        tm->begin(TPT_K_SHADOW); launch_pdl(k_shadow_q, pgrid, (unsigned)TPT_SHADOW_SMEM(smem, 256), ss, s->view, a, bs, par, s->d_stats); tm->end();
+        tm->begin(TPT_K_MIS); launch_pdl(k_mis, pgrid, smem, ss, s->view, a, bs, par, d_radiance, d_splat); tm->end();
         if (two) TPT_CUDA(cudaEventRecord(w->ev_side[e], ss));
         cur ^= 1;
         if ((it & 7) == 7 || it + 1 == max_iters) {
