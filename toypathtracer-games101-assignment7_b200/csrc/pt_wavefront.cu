@@ -298,40 +298,58 @@ __global__ void __launch_bounds__(256) k_pt_shadow(SceneView g, PtBuffers b, int
 
 }  // namespace
 
-struct PtWavefrontState {
+// One launch chain over a set of slots.  A frame is rendered by PT_PIPES chains over interleaved halves of the
+// partition's slots, launched alternately from the one host thread: k_pt_shade of one half runs beside
+// k_pt_extend / k_pt_shadow of the other (a chain by itself is shade -> (extend || shadow) -> shade, strictly
+// serial).  Slots never interact and every pixel is written by its own slot, so the image is the same bit for bit.
+#ifndef PT_PIPES
+#define PT_PIPES 2
+#endif
+struct PtPipe {
     int S = 0;
     PtBuffers b;
     std::vector<void*> allocs;
     unsigned* h_flag = nullptr;
+    cudaStream_t main = nullptr;    // chains after the first have their own main stream
     // k_pt_extend and k_pt_shadow both depend on k_pt_shade only: they run side by side on two streams
     cudaStream_t side = nullptr;
-    cudaEvent_t ev_shade = nullptr, ev_side = nullptr;
+    cudaEvent_t ev_shade = nullptr, ev_side = nullptr, ev_join = nullptr;
+};
+struct PtWavefrontState {
+    PtPipe pipe[PT_PIPES];
 };
 
+static void pt_pipe_free(PtPipe& w) {
+    for (void* p : w.allocs) tpt_dev_free(p);
+    w.allocs.clear();
+    if (w.h_flag) { tpt_pinned_free(w.h_flag); w.h_flag = nullptr; }
+    w.S = 0;
+}
 void pt_wavefront_destroy(TptScene* s) {
     if (!s || !s->ptwf) return;
-    for (void* p : s->ptwf->allocs) tpt_dev_free(p);
-    if (s->ptwf->h_flag) tpt_pinned_free(s->ptwf->h_flag);
-    if (s->ptwf->side) cudaStreamDestroy(s->ptwf->side);
-    if (s->ptwf->ev_shade) cudaEventDestroy(s->ptwf->ev_shade);
-    if (s->ptwf->ev_side) cudaEventDestroy(s->ptwf->ev_side);
+    for (PtPipe& w : s->ptwf->pipe) {
+        pt_pipe_free(w);
+        if (w.main) cudaStreamDestroy(w.main);
+        if (w.side) cudaStreamDestroy(w.side);
+        if (w.ev_shade) cudaEventDestroy(w.ev_shade);
+        if (w.ev_side) cudaEventDestroy(w.ev_side);
+        if (w.ev_join) cudaEventDestroy(w.ev_join);
+    }
     delete s->ptwf;
     s->ptwf = nullptr;
 }
 
-static int pt_alloc(TptScene* s, int S) {
-    if (s->ptwf && s->ptwf->S == S) return TPT_OK;
-    pt_wavefront_destroy(s);
-    PtWavefrontState* w = new PtWavefrontState;
-    s->ptwf = w;
-    w->S = S;
-    std::memset(&w->b, 0, sizeof w->b);
-    PtBuffers& b = w->b;
+static int pt_alloc(PtPipe& w, int S) {
+    if (w.S == S && !w.allocs.empty()) return TPT_OK;
+    pt_pipe_free(w);
+    w.S = S;
+    std::memset(&w.b, 0, sizeof w.b);
+    PtBuffers& b = w.b;
     b.S = S;
     auto get = [&](size_t bytes, void** out) -> bool {
         void* p = tpt_dev_alloc(bytes);
         if (!p) return false;
-        w->allocs.push_back(p);
+        w.allocs.push_back(p);
         *out = p;
         return true;
     };
@@ -343,18 +361,19 @@ static int pt_alloc(TptScene* s, int S) {
               get(F4, (void**)&b.dl_alpha) && get(F4, (void**)&b.dl_e1) && get(F4, (void**)&b.dl_e2) &&
               get(2 * F4, (void**)&b.sh_from) && get(F4, (void**)&b.sh_to) && get(U, (void**)&b.vis) &&
               get(U, (void**)&b.active[0]) && get(U, (void**)&b.active[1]) && get(sizeof(PtCounters), (void**)&b.ctr);
-    if (ok && !(w->h_flag = static_cast<unsigned*>(tpt_pinned_alloc(64)))) ok = false;
-    if (!ok) { pt_wavefront_destroy(s); return TPT_ERR_OOM; }
+    if (ok && !(w.h_flag = static_cast<unsigned*>(tpt_pinned_alloc(64)))) ok = false;
+    if (!ok) { pt_pipe_free(w); return TPT_ERR_OOM; }
     return TPT_OK;
 }
 
-int pt_wavefront_render(TptScene* s, const RenderArgs& a, float* d_radiance, cudaStream_t st, KernelTimer* tm) {
+int pt_wavefront_render(TptScene* s, const RenderArgs& a0, float* d_radiance, cudaStream_t st, KernelTimer* tm) {
     const int npix = s->view.width * s->view.height;
-    const int S = tpt_part_slots(a, npix);
-    int rc = pt_alloc(s, S);
-    if (rc != TPT_OK) return rc;
-    PtWavefrontState* w = s->ptwf;
-    PtBuffers& b = w->b;
+    if (!s->ptwf) s->ptwf = new PtWavefrontState;
+    PtWavefrontState* W = s->ptwf;
+    const char* env_two = getenv("TPT_WF_TWO_STREAMS");
+    const bool two = !tm->on && !(env_two && atoi(env_two) == 0);      // per-kernel timing needs one stream
+    // small partitions stay one chain: half of them would not fill the machine
+    const int npipes = (two && tpt_part_slots(a0, npix) >= s->num_sms * 2048) ? PT_PIPES : 1;
     const unsigned smem = s->view.stage_bytes;
     const unsigned tsmem = TPT_TRAV_SMEM(smem, 256);
     if (tsmem > 48u * 1024u) {                         // mid-size staged scenes: opt in to more dynamic shared memory
@@ -362,37 +381,68 @@ int pt_wavefront_render(TptScene* s, const RenderArgs& a, float* d_radiance, cud
         TPT_CUDA(cudaFuncSetAttribute(k_pt_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
         TPT_CUDA(cudaFuncSetAttribute(k_pt_shadow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
     }
-    const int grid = std::max(1, std::min((S + 255) / 256, s->num_sms * 8));
-    PtCounters init;
-    std::memset(&init, 0, sizeof init);
-    init.n_active[0] = (unsigned)S;
-    TPT_CUDA(cudaMemcpyAsync(b.ctr, &init, sizeof init, cudaMemcpyHostToDevice, st));
-    tm->begin(TPT_K_GENERATE); launch_pdl(k_pt_generate, grid, tsmem, st, s->view, a, b, s->d_stats); tm->end();
-    int cur = 0;
-    const long long max_iters = (long long)a.spp * 4096 + 8;
-    const char* env_two = getenv("TPT_WF_TWO_STREAMS");
-    const bool two = !tm->on && !(env_two && atoi(env_two) == 0);      // per-kernel timing needs one stream
-    if (two && !w->side) {
-        TPT_CUDA(cudaStreamCreateWithFlags(&w->side, cudaStreamNonBlocking));
-        TPT_CUDA(cudaEventCreateWithFlags(&w->ev_shade, cudaEventDisableTiming));
-        TPT_CUDA(cudaEventCreateWithFlags(&w->ev_side, cudaEventDisableTiming));
+    RenderArgs args[PT_PIPES];
+    int grid[PT_PIPES], cur[PT_PIPES];
+    bool live[PT_PIPES];
+    cudaStream_t ms[PT_PIPES], ss[PT_PIPES];
+    for (int p = 0; p < npipes; ++p) {
+        PtPipe& w = W->pipe[p];
+        args[p] = a0; args[p].sub = p; args[p].nsub = npipes;
+        const int S = tpt_part_slots(args[p], npix);
+        int rc = pt_alloc(w, S);
+        if (rc != TPT_OK) return rc;
+        if (two && !w.side) {
+            TPT_CUDA(cudaStreamCreateWithFlags(&w.side, cudaStreamNonBlocking));
+            TPT_CUDA(cudaEventCreateWithFlags(&w.ev_shade, cudaEventDisableTiming));
+            TPT_CUDA(cudaEventCreateWithFlags(&w.ev_side, cudaEventDisableTiming));
+            TPT_CUDA(cudaEventCreateWithFlags(&w.ev_join, cudaEventDisableTiming));
+        }
+        if (p > 0 && !w.main) TPT_CUDA(cudaStreamCreateWithFlags(&w.main, cudaStreamNonBlocking));
+        ms[p] = p == 0 ? st : w.main;
+        ss[p] = two ? w.side : st;
+        grid[p] = std::max(1, std::min((S + 255) / 256, s->num_sms * 8));
+        cur[p] = 0; live[p] = true;
+        if (p > 0) {       // what the caller queued on its stream (the cleared frame) comes first
+            TPT_CUDA(cudaEventRecord(w.ev_join, st));
+            TPT_CUDA(cudaStreamWaitEvent(ms[p], w.ev_join, 0));
+        }
+        PtCounters init;
+        std::memset(&init, 0, sizeof init);
+        init.n_active[0] = (unsigned)S;
+        TPT_CUDA(cudaMemcpyAsync(w.b.ctr, &init, sizeof init, cudaMemcpyHostToDevice, ms[p]));
+        tm->begin(TPT_K_GENERATE); launch_pdl(k_pt_generate, grid[p], tsmem, ms[p], s->view, args[p], w.b, s->d_stats); tm->end();
     }
-    cudaStream_t ss = two ? w->side : st;
+    const long long max_iters = (long long)a0.spp * 4096 + 8;
     for (long long it = 0; it < max_iters; ++it) {
-        if (two && it > 0) TPT_CUDA(cudaStreamWaitEvent(st, w->ev_side, 0));
-        tm->begin(TPT_K_SHADE); launch_pdl(k_pt_shade, grid, smem, st, s->view, a, b, cur, d_radiance, s->d_stats); tm->end();
-        if (two) { TPT_CUDA(cudaEventRecord(w->ev_shade, st)); TPT_CUDA(cudaStreamWaitEvent(ss, w->ev_shade, 0)); }
-        tm->begin(TPT_K_EXTEND); launch_pdl(k_pt_extend, grid, tsmem, st, s->view, b, cur ^ 1, s->d_stats); tm->end();
-        tm->begin(TPT_K_SHADOW); launch_pdl(k_pt_shadow, grid, (unsigned)TPT_SHADOW_SMEM(smem, 256), ss, s->view, b, cur ^ 1, s->d_stats); tm->end();
-        if (two) TPT_CUDA(cudaEventRecord(w->ev_side, ss));
-        cur ^= 1;
+        for (int p = 0; p < npipes; ++p) {
+            if (!live[p]) continue;
+            PtPipe& w = W->pipe[p];
+            if (two && it > 0) TPT_CUDA(cudaStreamWaitEvent(ms[p], w.ev_side, 0));
+            tm->begin(TPT_K_SHADE); launch_pdl(k_pt_shade, grid[p], smem, ms[p], s->view, args[p], w.b, cur[p], d_radiance, s->d_stats); tm->end();
+            if (two) { TPT_CUDA(cudaEventRecord(w.ev_shade, ms[p])); TPT_CUDA(cudaStreamWaitEvent(ss[p], w.ev_shade, 0)); }
+            tm->begin(TPT_K_EXTEND); launch_pdl(k_pt_extend, grid[p], tsmem, ms[p], s->view, w.b, cur[p] ^ 1, s->d_stats); tm->end();
+            tm->begin(TPT_K_SHADOW); launch_pdl(k_pt_shadow, grid[p], (unsigned)TPT_SHADOW_SMEM(smem, 256), ss[p], s->view, w.b, cur[p] ^ 1, s->d_stats); tm->end();
+            if (two) TPT_CUDA(cudaEventRecord(w.ev_side, ss[p]));
+            cur[p] ^= 1;
+        }
         if ((it & 7) == 7) {
-            TPT_CUDA(cudaMemcpyAsync(w->h_flag, &b.ctr->n_active[cur], sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-            TPT_CUDA(cudaStreamSynchronize(st));
-            if (w->h_flag[0] == 0) break;
+            bool any = false;
+            for (int p = 0; p < npipes; ++p)
+                if (live[p]) TPT_CUDA(cudaMemcpyAsync(W->pipe[p].h_flag, &W->pipe[p].b.ctr->n_active[cur[p]], sizeof(unsigned), cudaMemcpyDeviceToHost, ms[p]));
+            for (int p = 0; p < npipes; ++p) {
+                if (!live[p]) continue;
+                TPT_CUDA(cudaStreamSynchronize(ms[p]));
+                if (W->pipe[p].h_flag[0] == 0) live[p] = false;
+                any = any || live[p];
+            }
+            if (!any) break;
         }
     }
-    if (two) TPT_CUDA(cudaStreamWaitEvent(st, w->ev_side, 0));
+    for (int p = 0; p < npipes; ++p) {       // everything joins the caller's stream
+        PtPipe& w = W->pipe[p];
+        if (two) TPT_CUDA(cudaStreamWaitEvent(ms[p], w.ev_side, 0));
+        if (p > 0) { TPT_CUDA(cudaEventRecord(w.ev_join, ms[p])); TPT_CUDA(cudaStreamWaitEvent(st, w.ev_join, 0)); }
+    }
     TPT_CUDA(cudaGetLastError());
     return TPT_OK;
 }

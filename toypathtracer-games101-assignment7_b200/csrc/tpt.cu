@@ -890,6 +890,7 @@ static int check_params(const TptScene* s, const TptRenderParams* p, RenderArgs*
     a->mode = p->mode; a->spp = p->spp; a->spp_total = p->spp_total > 0 ? p->spp_total : p->spp;
     a->seed_mode = p->seed_mode; a->partition = p->partition; a->rank = p->rank; a->world = world;
     a->stream = p->stream;
+    a->sub = 0; a->nsub = 1;
     if (p->partition < TPT_PART_ALL || p->partition > TPT_PART_BLOCK) { tpt_set_error("unknown partition"); return TPT_ERR_INVALID; }
     a->prune = (p->flags & TPT_FLAG_REF_TRAVERSAL) ? 0 : 1;
     a->count_visits = (p->flags & TPT_FLAG_COUNT_VISITS) ? 1 : 0;

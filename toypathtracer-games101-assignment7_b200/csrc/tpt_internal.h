@@ -30,6 +30,7 @@ struct RenderArgs {
     int mode, spp, spp_total;
     int seed_mode, partition, rank, world, stream;
     int prune, count_visits, kernel_times;
+    int sub, nsub;      // this launch chain handles every nsub-th slot of the partition, starting at sub (1 chain: 0, 1)
 };
 
 // CUDA-event stopwatch around individual launches (TPT_FLAG_KERNEL_TIMES).
@@ -94,12 +95,17 @@ __host__ __device__ inline uint32_t tpt_pixel_seed(int seed_mode, uint32_t pixel
 __host__ __device__ inline int tpt_part_begin(const RenderArgs& a, int npix) {
     return a.partition == TPT_PART_BLOCK ? (int)((long long)npix * a.rank / a.world) : 0;
 }
-__host__ __device__ inline int tpt_part_slots(const RenderArgs& a, int npix) {
+__host__ __device__ inline int tpt_part_slots_all(const RenderArgs& a, int npix) {
     if (a.partition == TPT_PART_INTERLEAVE) return (npix - a.rank + a.world - 1) / a.world;
     if (a.partition == TPT_PART_BLOCK) return (int)((long long)npix * (a.rank + 1) / a.world) - tpt_part_begin(a, npix);
     return npix;
 }
+__host__ __device__ inline int tpt_part_slots(const RenderArgs& a, int npix) {
+    const int all = tpt_part_slots_all(a, npix);
+    return a.nsub > 1 ? (all - a.sub + a.nsub - 1) / a.nsub : all;
+}
 __host__ __device__ inline int tpt_slot_pixel(const RenderArgs& a, int npix, int slot) {
+    if (a.nsub > 1) slot = slot * a.nsub + a.sub;
     if (a.partition == TPT_PART_INTERLEAVE) return slot * a.world + a.rank;
     if (a.partition == TPT_PART_BLOCK) return tpt_part_begin(a, npix) + slot;
     return slot;
