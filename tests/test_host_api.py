@@ -101,3 +101,21 @@ def test_output_image_is_a_real_jpeg(tpt, tmp_path):
     ref = np.floor(255 * np.power(np.clip(img, 0, 1), np.float32(0.6))).astype(np.int32)
     assert got.shape == ref.shape
     assert np.abs(got - ref).max() <= 4 and np.abs(got - ref).mean() < 1.0
+
+
+def test_slot_to_pixel_maps_cover_every_pixel_once(tmp_path):
+    """csrc/tpt_internal.h: the slots of all (rank, launch chain) pairs of a partition cover every pixel exactly
+    once, for every partition kind, world size and chain count (tests/native/part_check.cu; host code only)."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "part_check")
+    src = os.path.join(ROOT, "tests", "native", "part_check.cu")
+    pkg = os.path.join(ROOT, "toypathtracer-games101-assignment7_b200", "csrc")
+    r = subprocess.run([nvcc, "-std=c++17", "-I", os.path.join(ROOT, "include"), "-I", pkg, "-o", exe, src],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "0 errors" in r.stdout, r.stdout + r.stderr
