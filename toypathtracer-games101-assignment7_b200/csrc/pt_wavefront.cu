@@ -341,6 +341,7 @@ void pt_wavefront_destroy(TptScene* s) {
 
 static int pt_alloc(PtPipe& w, int S) {
     if (w.S == S && !w.allocs.empty()) return TPT_OK;
+    if (!w.allocs.empty()) cudaDeviceSynchronize();      // a different share: the previous one's launches may still be running
     pt_pipe_free(w);
     w.S = S;
     std::memset(&w.b, 0, sizeof w.b);
