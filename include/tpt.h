@@ -240,7 +240,12 @@ int tpt_render(TptScene* scene, const TptRenderParams* params, float* out_rgb,
 /* The same work leaving this call's partial sums on the device:
  * d_accum is 2*width*height*3 floats, [radiance | splat], already weighted by
  * 1/spp_total, to be summed over ranks (one NCCL reduce) and then merged by
- * tpt_finalize_device.  Asynchronous on `stream`. */
+ * tpt_finalize_device.  Asynchronous on `stream`: the launch chains of the wavefront
+ * pipeline run on streams of their own, forked from `stream` after everything queued on
+ * it before the call and joined back into it before the call returns, so work queued on
+ * `stream` afterwards (the reduce, tpt_finalize_device, a copy) sees the complete sums.
+ * With a non-null `stats` the call waits for the result (it reads the counters);
+ * TPT_FLAG_KERNEL_TIMES additionally runs the kernels one after another on `stream`. */
 int tpt_render_device(TptScene* scene, const TptRenderParams* params, float* d_accum,
                       void* stream, TptStats* stats);
 size_t tpt_accum_floats(const TptScene* scene);
