@@ -434,61 +434,8 @@ TPT_DEV float mis_denominator(const SceneView& sc, const CamPath& cam, int s, co
 // (rev = append_pdf_base); a strategy then evaluates at most four pdfs of its own and
 // walks the stored ratios, multiplying in the reference's order so the floats agree.
 // camAux(i) / lightAux(i) return {original pdf of vertex i, reverse pdf towards vertex i}.
-template <class CamPath, class LightPath, class CamAux, class LightAux>
-TPT_DEV float mis_denominator_shared(const SceneView& sc, const CamPath& cam, int s, const LightPath& light, int t,
-                                     const CamAux& camAux, const LightAux& lightAux) {
-    float den = 1.0f;
-    const PVert z = cam(s - 1);                       // camera subpath end
-    PVert zp = z;                                     // its predecessor (unused for s == 1)
-    if (s >= 2) zp = cam(s - 2);
-    PVert y = z, yp = z;                              // light subpath end and its predecessor
-    if (t >= 1) { y = light(t - 1); yp = y; }
-    if (t >= 2) yp = light(t - 2);
-    if (t >= 1) {   // camera subpath extended by light[t-1], ..., light[0]
-        int count = s;
-        float cur = safe_div(append_pdf(sc, z, z.type, zp.x, y, count), y.pdf);
-        den += cur * cur;
-        count++;
-        if (cur != 0.0f && t >= 2) {
-            cur *= safe_div(append_pdf(sc, y, y.type, z.x, yp, count), yp.pdf);
-            den += cur * cur;
-            count++;
-            for (int i = t - 3; i >= 0 && cur != 0.0f; --i) {
-                const float2 aux = lightAux(i);
-                cur *= safe_div(aux.y * (count > 4 ? .8f : 1.f), aux.x);
-                den += cur * cur;
-                count++;
-            }
-        }
-    }
-    {   // light subpath extended by cam[s-1], ..., cam[0]
-        int count = t;
-        float cur;
-        if (t == 0) {
-            // Append to an empty path (BDPT.cpp:127-139): pdf = the primitive's own 1/area (quirk Q15)
-            cur = safe_div(prim_pdf(sc, z.prim), z.pdf);
-        } else {
-            cur = safe_div(append_pdf(sc, y, y.type, yp.x, z, count), z.pdf);
-        }
-        den += cur * cur;
-        count++;
-        if (cur != 0.0f && s >= 2) {
-            // behind cam[s-1] (re-typed Light when it started the path), predecessor light[t-1]
-            cur *= safe_div(append_pdf(sc, z, t == 0 ? VT_LIGHT : z.type, y.x, zp, count), zp.pdf);
-            den += cur * cur;
-            count++;
-            for (int i = s - 3; i >= 0 && cur != 0.0f; --i) {
-                const float2 aux = camAux(i);
-                cur *= safe_div(aux.y * (count > 4 ? .8f : 1.f), aux.x);
-                den += cur * cur;
-                count++;
-            }
-        }
-    }
-    return den;
-}
-
-// mis_denominator_shared once more, with the four pdfs a strategy evaluates itself formed in PAIRS.
+//
+// The four pdfs a strategy evaluates itself are formed in PAIRS.
 // They are the two directions through z = cam[s-1] (from zp towards y and from y towards zp) and the
 // two through y = light[t-1] (from yp towards z, from z towards yp): per vertex the same two unit
 // vectors, the same cosines and — on the reflection side of a GGX material — the same half vector
