@@ -207,6 +207,10 @@ class Checker:
         state = f(self.h, C.c_int(pixel), C.c_uint32(seed), _p(cam), C.byref(nc), _p(light), C.byref(nl), _p(w))
         return cam, nc.value, light, nl.value, w, state
 
+    def set_background(self, r, g, b):
+        """Reference checker only: Scene::backgroundColor (and the flattened description's copy)."""
+        self._fn("scene_set_background")(self.h, C.c_float(r), C.c_float(g), C.c_float(b))
+
     def render(self, mode, spp, threads, w, h):
         out = np.empty((h * w, 3), np.float32); rays = C.c_longlong(0); sec = C.c_double(0)
         self._fn("render")(self.h, C.c_int(mode), C.c_int(spp), C.c_int(threads), _p(out), C.byref(rays), C.byref(sec))

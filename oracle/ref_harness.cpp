@@ -157,6 +157,13 @@ RefScene* ref_scene_create(const char* scene_name, const char* models_dir, int w
 
 void ref_scene_destroy(RefScene* rs) { delete rs; }
 
+// Scene::backgroundColor is a public field main.cpp sets to 0 (main.cpp:51); the (nc, 0) strategy of BDPT and the
+// Background branch of PathTrace only show with another value.  Also updates the flattened description.
+void ref_scene_set_background(RefScene* rs, float r, float g, float b) {
+    rs->scene->backgroundColor = Vector3f(r, g, b);
+    rs->flat.background.x = r; rs->flat.background.y = g; rs->flat.background.z = b;
+}
+
 // The reference's own trees, flattened.  The pointers stay valid until destroy.
 void ref_scene_desc(const RefScene* rs, TptSceneDesc* out) { *out = rs->flat.desc(); }
 

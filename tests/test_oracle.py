@@ -173,3 +173,21 @@ def test_restatement_equals_compiled_reference(scene):
         a, ra, _ = ref.render(mode, spp, 1, 48, 40)
         b, rb, _ = orc.render(mode, spp, 1, 48, 40)
         assert (a.view(np.uint32) == b.view(np.uint32)).all() and ra == rb
+
+
+@pytest.mark.skipif(not B.have_ref(), reason="compiled reference not present")
+def test_lit_background_restatement_equals_compiled_reference():
+    """main.cpp renders against a black background; with another colour the Background branches show
+    (PathTracer.cpp:58-62, BDPT.cpp:180-185).  Same bits from the restatement and from the reference's object code."""
+    ref, _ = B.ref_scene("standard", 40, 40)
+    ref.set_background(0.25, 0.5, 1.0)
+    desc = B.SceneDesc()
+    import ctypes as C
+    ref.lib.ref_scene_desc(ref.h, C.byref(desc))
+    assert abs(desc.background.z - 1.0) < 1e-7
+    orc = B.oracle_scene(desc)
+    for mode, spp in ((0, 3), (1, 4), (2, 3)):
+        a, ra, _ = ref.render(mode, spp, 1, 40, 40)
+        b, rb, _ = orc.render(mode, spp, 1, 40, 40)
+        assert (a.view(np.uint32) == b.view(np.uint32)).all() and ra == rb
+    assert a[0, 0].sum() > 0.1            # the corner pixel looks past the box
