@@ -40,6 +40,8 @@ def main():
     ap.add_argument("--cpu", action="store_true")
     ap.add_argument("--c5-spp", type=int, default=1024)
     ap.add_argument("--only", default="")
+    ap.add_argument("--small-frames", default="interleave", choices=["interleave", "spp"],
+                    help="how C1-C3 (784^2) are shared with N > 1: by pixels (bit-compatible with one GPU) or by samples")
     args = ap.parse_args()
 
     import torch
@@ -70,6 +72,8 @@ def main():
             continue
         if cid == "C5":
             spp = args.c5_spp
+        if strategy == "interleave" and args.small_frames == "spp" and spp >= world:
+            strategy = "spp"
         scene = T.Scene(scene_name, w, h, device=local_rank)
         accum = torch.zeros(scene.accum_floats(), dtype=torch.float32, device="cuda")
         out = torch.zeros(w * h * 3, dtype=torch.float32, device="cuda")
