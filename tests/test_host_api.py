@@ -85,6 +85,20 @@ def test_reference_main_compiles_unchanged(tpt, tmp_path):
     assert os.path.exists(exe)
 
 
+def test_mesh_placement_constructors(tpt, tmp_path):
+    """MeshTriangle(path | xyz, material, scale, translate) (the reference has no transform): bit-identical
+    to a mesh whose vertices the caller placed with the same float arithmetic (tests/native/mesh_place.cpp)."""
+    import subprocess
+    pkg = os.path.dirname(tpt.LIBTPT)
+    exe = str(tmp_path / "mesh_place")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(pkg, "host"), "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "native", "mesh_place.cpp"), "-o", exe,
+                        "-L", pkg, "-ltpt_host", "-ltpt", "-Wl,-rpath," + pkg], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([exe, str(tmp_path / "fan.obj")], capture_output=True, text=True)
+    assert r.returncode == 0 and " 0 errors" in r.stdout, r.stdout + r.stderr
+
+
 def test_output_image_is_a_real_jpeg(tpt, tmp_path):
     """SaveFloatImageToJpg (SceneRenderingHelper.cpp:57-70): the reference's tonemap (clamp, pow 0.6, * 255
     truncated) followed by a baseline JPEG at quality 100 without chroma subsampling.  The file must decode

@@ -220,6 +220,11 @@ public:
     MeshTriangle(const std::string& filename, Material* m_ = new Material());
     // Same mesh from memory: 3 floats per vertex, 3 vertices per triangle.
     MeshTriangle(const float* xyz, size_t numTriangles, Material* m_);
+    // Placement (the reference has none, Triangle.cpp:32-75 takes the file's coordinates
+    // as they are): every vertex becomes v * scale + translate, componentwise in float, before the
+    // triangles and the BVH are built — the Cornell + bunny fixture from the unscaled bunny.obj.
+    MeshTriangle(const std::string& filename, Material* m_, const Vector3f& scale, const Vector3f& translate);
+    MeshTriangle(const float* xyz, size_t numTriangles, Material* m_, const Vector3f& scale, const Vector3f& translate);
     float pdf() override { return 1.0f / bvh->GN(bvh->Root()).area; }
     Bounds3 GetBounds() override { return bounding_box; }
     float getArea() override { return area; }
@@ -231,6 +236,7 @@ public:
 
 private:
     void Build(const std::vector<Vector3f>& faceVertices);
+    void Load(const std::string& filename, const Vector3f* scale, const Vector3f* translate);
 };
 
 // ---- Sphere.hpp -------------------------------------------------------------

@@ -116,18 +116,36 @@ bool ReadObjFaces(const std::string& path, std::vector<Vector3f>* faceVertices) 
 
 }  // namespace
 
-MeshTriangle::MeshTriangle(const std::string& filename, Material* m_) : Object(m_) {
+namespace {
+void Place(std::vector<Vector3f>* fv, const Vector3f& scale, const Vector3f& translate) {
+    for (Vector3f& v : *fv) v = v * scale + translate;
+}
+}  // namespace
+
+void MeshTriangle::Load(const std::string& filename, const Vector3f* scale, const Vector3f* translate) {
     std::vector<Vector3f> fv;
     if (!ReadObjFaces(filename, &fv) || fv.empty()) {
         std::fprintf(stderr, "MeshTriangle: cannot read triangles from '%s'\n", filename.c_str());
         return;   // an empty mesh; Scene::BuildBVH / the flattener report it
     }
+    if (scale) Place(&fv, *scale, *translate);
     Build(fv);
 }
+
+MeshTriangle::MeshTriangle(const std::string& filename, Material* m_) : Object(m_) { Load(filename, nullptr, nullptr); }
+MeshTriangle::MeshTriangle(const std::string& filename, Material* m_, const Vector3f& scale, const Vector3f& translate)
+    : Object(m_) { Load(filename, &scale, &translate); }
 
 MeshTriangle::MeshTriangle(const float* xyz, size_t numTriangles, Material* m_) : Object(m_) {
     std::vector<Vector3f> fv;
     for (size_t i = 0; i < numTriangles * 3; ++i) fv.emplace_back(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    if (!fv.empty()) Build(fv);
+}
+MeshTriangle::MeshTriangle(const float* xyz, size_t numTriangles, Material* m_, const Vector3f& scale, const Vector3f& translate)
+    : Object(m_) {
+    std::vector<Vector3f> fv;
+    for (size_t i = 0; i < numTriangles * 3; ++i) fv.emplace_back(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    Place(&fv, scale, translate);
     if (!fv.empty()) Build(fv);
 }
 
