@@ -85,17 +85,29 @@ def test_reference_main_compiles_unchanged(tpt, tmp_path):
     assert os.path.exists(exe)
 
 
+def _native(tpt, tmp_path, name, *args):
+    import subprocess
+    pkg = os.path.dirname(tpt.LIBTPT)
+    exe = str(tmp_path / name)
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(pkg, "host"), "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "native", name + ".cpp"), "-o", exe,
+                        "-L", pkg, "-ltpt_host", "-ltpt", "-Wl,-rpath," + pkg], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return subprocess.run([exe, *args], capture_output=True, text=True, timeout=600)
+
+
+def test_in_place_bvh_build_equals_the_reference_recursion(tpt, tmp_path):
+    """BVHAccel's constructor (in-place sort of {centroid, index} records, subtrees as concurrent tasks) against
+    BVHAccel::recursiveBuild (reference BVH.cpp:30-99 as written) on tie-heavy inputs, 1 / 3 / 8 build threads:
+    identical node arrays (tests/native/bvh_build.cpp)."""
+    r = _native(tpt, tmp_path, "bvh_build")
+    assert r.returncode == 0 and " 0 errors" in r.stdout, r.stdout + r.stderr
+
+
 def test_mesh_placement_constructors(tpt, tmp_path):
     """MeshTriangle(path | xyz, material, scale, translate) (the reference has no transform): bit-identical
     to a mesh whose vertices the caller placed with the same float arithmetic (tests/native/mesh_place.cpp)."""
-    import subprocess
-    pkg = os.path.dirname(tpt.LIBTPT)
-    exe = str(tmp_path / "mesh_place")
-    r = subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(pkg, "host"), "-I", os.path.join(ROOT, "include"),
-                        os.path.join(ROOT, "tests", "native", "mesh_place.cpp"), "-o", exe,
-                        "-L", pkg, "-ltpt_host", "-ltpt", "-Wl,-rpath," + pkg], capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr[-2000:]
-    r = subprocess.run([exe, str(tmp_path / "fan.obj")], capture_output=True, text=True)
+    r = _native(tpt, tmp_path, "mesh_place", str(tmp_path / "fan.obj"))
     assert r.returncode == 0 and " 0 errors" in r.stdout, r.stdout + r.stderr
 
 

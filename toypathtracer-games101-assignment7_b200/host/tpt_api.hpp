@@ -182,6 +182,8 @@ class BVHAccel {
 public:
     enum class SplitMethod { NAIVE, SAH };
     BVHAccel(std::vector<Object*> p, int maxPrimsInNode = 1, SplitMethod splitMethod = SplitMethod::NAIVE);
+    // The reference's recursion as written (appends to `nodes`); the constructor builds the identical
+    // array in place and in parallel (tpt_host.cpp, buildInPlace).
     BVHNodeIndex recursiveBuild(std::vector<Object*> objects);
     BVHNodeIndex Root() { return 0; }
     BVHBuildNode& GN(BVHNodeIndex i) { return nodes[i]; }
@@ -191,6 +193,9 @@ public:
     const SplitMethod splitMethod;
     std::vector<Object*> primitives;
     std::vector<BVHBuildNode> nodes;
+
+private:
+    void buildInPlace();
 };
 
 // ---- Triangle.hpp -----------------------------------------------------------

@@ -10,8 +10,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <future>
 #include <iostream>
 #include <sstream>
+#include <thread>
 
 #include "flatten.hpp"
 #include "tpt.h"
@@ -22,7 +24,90 @@ const float EPSILON = 1e-4;
 // ---------------------------------------------------------------- BVH build
 BVHAccel::BVHAccel(std::vector<Object*> p, int maxPrims, SplitMethod method)
     : maxPrimsInNode(std::min(255, maxPrims)), splitMethod(method), primitives(std::move(p)) {
-    if (!primitives.empty()) recursiveBuild(primitives);
+    if (!primitives.empty()) buildInPlace();
+}
+
+// ---- the same tree without the per-level copies (large meshes) -------------------------
+// recursiveBuild below is the reference's recursion as written (BVH.cpp:30-99): every level copies its
+// object list twice and every comparison of its std::sort recomputes two bounding boxes through virtual
+// calls — 23 s for a million triangles.  buildInPlace produces the IDENTICAL node array:
+//  * bounds and centroids are taken once per object, with the same expressions;
+//  * a level sorts its range of {centroid, object index} records in place.  std::sort is driven by the
+//    comparison results and the element count alone, the records compare exactly as the objects do and a
+//    child's range starts in the order the parent's sort left it — which is what the copies hold — so
+//    every sort performs the same permutation, ties included;
+//  * a subtree over n objects has 2n - 1 nodes, appended in pre-order with the left subtree first, so the
+//    index of every node is known before it is built: subtrees fill disjoint index ranges and the large
+//    ones are built by concurrent tasks.
+// tests/native/bvh_build.cpp compares the two builds field by field.
+namespace {
+struct BuildItem {
+    float c[3];     // GetBounds().Centroid()
+    int obj;        // index into BVHAccel::primitives
+};
+template <int AXIS> bool ItemLess(const BuildItem& a, const BuildItem& b) { return a.c[AXIS] < b.c[AXIS]; }
+
+struct InPlaceBuild {
+    BVHAccel* bvh;
+    std::vector<Bounds3> bounds;
+    std::vector<BuildItem> items;
+    int spawnDepth;                     // levels below the root whose left subtree gets its own task
+    static constexpr size_t kTaskMin = 1u << 13;
+
+    void Range(BuildItem* it, size_t n, BVHNodeIndex self, int depth) {
+        BVHBuildNode& node = bvh->nodes[self];
+        if (n == 1) {
+            Object* o = bvh->primitives[it[0].obj];
+            node.bounds = bounds[it[0].obj];
+            node.object = o;
+            node.area = o->getArea();
+            return;
+        }
+        size_t nl = 1;
+        if (n > 2) {
+            Bounds3 centroids;
+            for (size_t i = 0; i < n; ++i) centroids = Union(centroids, Vector3f(it[i].c[0], it[i].c[1], it[i].c[2]));
+            switch (centroids.maxExtent()) {
+                case 0: std::sort(it, it + n, ItemLess<0>); break;
+                case 1: std::sort(it, it + n, ItemLess<1>); break;
+                default: std::sort(it, it + n, ItemLess<2>); break;
+            }
+            nl = n / 2;
+        }
+        const BVHNodeIndex l = self + 1, r = self + 1 + (BVHNodeIndex)(2 * nl - 1);
+        if (depth < spawnDepth && n >= kTaskMin) {
+            auto left = std::async(std::launch::async, [=] { Range(it, nl, l, depth + 1); });
+            Range(it + nl, n - nl, r, depth + 1);
+            left.get();
+        } else {
+            Range(it, nl, l, depth + 1);
+            Range(it + nl, n - nl, r, depth + 1);
+        }
+        node.left = l;
+        node.right = r;
+        node.bounds = Union(bvh->nodes[l].bounds, bvh->nodes[r].bounds);
+        node.area = bvh->nodes[l].area + bvh->nodes[r].area;
+    }
+};
+}  // namespace
+
+void BVHAccel::buildInPlace() {
+    const size_t n = primitives.size();
+    InPlaceBuild b;
+    b.bvh = this;
+    b.bounds.reserve(n);
+    b.items.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+        b.bounds.push_back(primitives[i]->GetBounds());
+        const Vector3f c = b.bounds[i].Centroid();
+        b.items[i] = BuildItem{{c.x, c.y, c.z}, (int)i};
+    }
+    unsigned threads = std::thread::hardware_concurrency();
+    if (const char* e = std::getenv("TPT_BUILD_THREADS")) threads = (unsigned)std::max(1, std::atoi(e));
+    b.spawnDepth = 0;
+    while ((1u << b.spawnDepth) < threads) ++b.spawnDepth;      // 2^depth concurrent subtrees
+    nodes.assign(2 * n - 1, BVHBuildNode());
+    b.Range(b.items.data(), n, 0, 0);
 }
 
 namespace {
