@@ -69,6 +69,27 @@ def test_obj_reader_variants(tpt, tmp_path):
     assert (ta == tb).all()
 
 
+def test_obj_reader_number_and_line_syntax(tpt, tmp_path):
+    """Number spellings strtof accepts (sign, exponent, bare point), tabs, CRLF line ends, a last line without a
+    newline: the vertices must come out as numpy's correctly rounded float32 of the same text."""
+    import shutil
+    box = tmp_path / "cornellbox"
+    os.makedirs(box)
+    tpt.ensure_models()
+    for f in os.listdir(os.path.join(tpt.MODELS_DIR, "cornellbox")):
+        shutil.copy(os.path.join(tpt.MODELS_DIR, "cornellbox", f), box / f)
+    toks = [["+1.5", "1e2", ".5"], ["-0", "1.0E+1", "552.8000000000001"], ["0.1", "16777217", "3.4028234e38"],
+            ["1e-46", "-.25e-3", "0x1p3"]]
+    text = "".join("v\t%s  %s\t%s \r\n" % tuple(t) for t in toks) + "f 1 2 3\r\nf 2 3 4"
+    (box / "floor.obj").write_bytes(text.encode())
+    sc = tpt.HostScene("standard", 64, 64, models_dir=str(tmp_path))
+    arr = B.desc_arrays(B.SceneDesc.from_buffer_copy(bytes(sc.desc)))["tris"]
+    want = np.array([[float.fromhex(x) if x.startswith("0x") else float(x) for x in t] for t in toks], dtype=np.float32)
+    got = arr.view(np.float32).reshape(-1, 19)[:2, :9].reshape(2, 3, 3)       # TptTriangle: v0 v1 v2 e1 e2 normal area
+    with np.errstate(all="ignore"):
+        assert got.tobytes() == np.stack([want[[0, 1, 2]], want[[1, 2, 3]]]).tobytes()
+
+
 @pytest.mark.skipif(not os.path.exists("/root/reference/main.cpp"), reason="reference sources not present")
 def test_reference_main_compiles_unchanged(tpt, tmp_path):
     """The drop-in claim of INTEGRATION.md level 1: the reference's own main.cpp (scene script + CLI,

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <fstream>
 #include <future>
+#include <charconv>
 #include <iostream>
 #include <sstream>
 #include <thread>
@@ -157,36 +158,65 @@ BVHNodeIndex BVHAccel::recursiveBuild(std::vector<Object*> objs) {
 namespace {
 
 // "12", "12/3", "12//4", "-1" -> 0-based position index
-bool ParseFaceIndex(const std::string& tok, size_t nPositions, size_t* out) {
+bool ParseFaceIndex(const char* tok, size_t nPositions, size_t* out) {
     char* end = nullptr;
-    long v = std::strtol(tok.c_str(), &end, 10);
-    if (end == tok.c_str() || v == 0) return false;
+    long v = std::strtol(tok, &end, 10);
+    if (end == tok || v == 0) return false;
     long idx = v > 0 ? v - 1 : (long)nPositions + v;
     if (idx < 0 || (size_t)idx >= nPositions) return false;
     *out = (size_t)idx;
     return true;
 }
 
+// strtof's value (both round correctly) at a third of its cost; whatever from_chars does not take whole
+// (a leading '+', hexadecimal, "inf") goes to strtof itself.
+float ParseFloat(const char* tok) {
+    float v = 0.0f;
+    const char* end = tok + std::strlen(tok);
+    const std::from_chars_result r = std::from_chars(tok, end, v);
+    if (r.ec == std::errc() && r.ptr == end) return v;
+    return std::strtof(tok, nullptr);
+}
+
+// The file is read in one piece and cut into lines and blank-separated tokens in place (a million-triangle
+// mesh is four million lines: a stream object per line costs more than the BVH build).
 bool ReadObjFaces(const std::string& path, std::vector<Vector3f>* faceVertices) {
-    std::ifstream in(path);
-    if (!in.is_open()) return false;
+    std::FILE* file = std::fopen(path.c_str(), "rb");
+    if (!file) return false;
+    std::string text;
+    {
+        char chunk[1 << 16];
+        size_t got;
+        while ((got = std::fread(chunk, 1, sizeof chunk, file)) > 0) text.append(chunk, got);
+        std::fclose(file);
+    }
+    text.push_back('\n');
     std::vector<Vector3f> positions;
-    std::string line;
-    while (std::getline(in, line)) {
-        std::istringstream ls(line);
-        std::string tag;
-        if (!(ls >> tag)) continue;
-        if (tag == "v") {
-            std::string a, b, c;
-            if (!(ls >> a >> b >> c)) return false;
-            positions.emplace_back(std::strtof(a.c_str(), nullptr), std::strtof(b.c_str(), nullptr),
-                                   std::strtof(c.c_str(), nullptr));
-        } else if (tag == "f") {
-            std::vector<size_t> idx;
-            std::string tok;
-            while (ls >> tok) {
+    std::vector<char*> tok;
+    std::vector<size_t> idx;
+    auto blank = [](char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\v' || c == '\f'; };
+    char* p = &text[0];
+    char* const stop = p + text.size();
+    while (p < stop) {
+        char* eol = static_cast<char*>(std::memchr(p, '\n', (size_t)(stop - p)));
+        *eol = 0;
+        tok.clear();
+        for (char* q = p; q < eol;) {
+            while (q < eol && blank(*q)) *q++ = 0;
+            if (q == eol) break;
+            tok.push_back(q);
+            while (q < eol && !blank(*q)) ++q;
+        }
+        p = eol + 1;
+        if (tok.empty()) continue;
+        if (std::strcmp(tok[0], "v") == 0) {
+            if (tok.size() < 4) return false;
+            positions.emplace_back(ParseFloat(tok[1]), ParseFloat(tok[2]), ParseFloat(tok[3]));
+        } else if (std::strcmp(tok[0], "f") == 0) {
+            idx.clear();
+            for (size_t k = 1; k < tok.size(); ++k) {
                 size_t i;
-                if (!ParseFaceIndex(tok, positions.size(), &i)) return false;
+                if (!ParseFaceIndex(tok[k], positions.size(), &i)) return false;
                 idx.push_back(i);
             }
             for (size_t k = 1; k + 1 < idx.size(); ++k) {   // triangles as-is; polygons as a fan
