@@ -78,3 +78,34 @@ def test_read_bandwidth_probe(tpt):
     hbm = tpt.probe_read_bandwidth(2 << 30, 2)
     assert 1000.0 < hbm < 9000.0, hbm
     assert l2 > hbm, (l2, hbm)
+
+
+def test_device_code_is_sm100a_with_the_documented_resources(tpt):
+    """Static view of libtpt.so's device code (cuobjdump, no GPU needed): built for sm_100a only; the registers /
+    local memory of the wavefront kernels are the launch-bound choices DESIGN.md section 5 quotes (64 registers =
+    4 CTAs of 256 threads per SM, k_shade 80 = 3, k_pt_shade 128 = 2; spills of a few words at most); the scene
+    blob is staged by a bulk asynchronous copy (UBLKCP) and every loop kernel is a programmatic dependent launch
+    (griddepcontrol.wait / launch_dependents = ACQBULK / PREEXIT)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    elf = subprocess.run([cuobjdump, "-lelf", tpt.LIBTPT], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", elf))
+    assert archs == {"sm_100a"}, archs
+    res = subprocess.run([cuobjdump, "-res-usage", tpt.LIBTPT], capture_output=True, text=True).stdout
+    usage = {}
+    for name, reg, stack in re.findall(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+)", res):
+        short = re.search(r"(k_[a-z_]+)(?:E|I)", name)
+        if short:
+            usage.setdefault(short.group(1), []).append((int(reg), int(stack)))
+    limits = {"k_shade": 80, "k_extend": 64, "k_expand": 64, "k_connect": 64, "k_shadow_q": 64, "k_mis": 64,
+              "k_pt_shade": 128, "k_pt_extend": 64, "k_pt_shadow": 64}
+    for k, lim in limits.items():
+        assert k in usage, "kernel %s not found in libtpt.so" % k
+        for reg, stack in usage[k]:
+            assert reg <= lim, "%s uses %d registers (> %d: fewer resident CTAs than designed)" % (k, reg, lim)
+            assert stack <= 64, "%s has a %d-byte stack frame (spilling)" % (k, stack)
+    sass = subprocess.run([cuobjdump, "-sass", tpt.LIBTPT], capture_output=True, text=True).stdout
+    assert sass.count("UBLKCP") >= 10 and sass.count("ACQBULK") >= 9 and sass.count("PREEXIT") >= 9
