@@ -1,0 +1,168 @@
+"""The exact tier without a GPU: csrc/traverse.cuh — the traversal source the kernels are compiled from — built
+for the host (tests/native/traverse_host.cu: device intrinsics mapped to plain IEEE float operations, no
+contraction) over a host copy of the scene blob made by the product's own builder (csrc/scene_build.h), run on
+the golden ray batches P / S / R / A of SURVEY 8(d) and compared bit for bit with the reference's answers
+(tests/golden/rays_<scene>.npz, generated from the compiled reference by tests/golden/make_golden.py).
+
+What this pins on the CPU: the grafted visit-ordered node array, the flat leaf list and its bit masks, the pruning
+margins, the any-hit form of ShadowCheck, the deferred (recorded) walk — every walk the kernels use returns the
+reference's primitive id, t, hit point, normal and shadow decision.  What it cannot pin is the device's own
+arithmetic (that a B200 rounds these operations the same way): tests/test_gpu_exact.py does, through the C ABI."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, desc_from_golden, golden
+
+SCENES = ["standard", "smooth", "silver", "refractive", "occlusion", "bunny"]
+PKG = os.path.join(ROOT, "toypathtracer-games101-assignment7_b200")
+
+
+@pytest.fixture(scope="module")
+def mirror(tmp_path_factory):
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    so = str(tmp_path_factory.mktemp("mirror") / "libtraverse_host.so")
+    r = subprocess.run([nvcc, "-std=c++17", "-O2", "-gencode", "arch=compute_100a,code=sm_100a", "--expt-relaxed-constexpr",
+                        "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-I", os.path.join(ROOT, "include"),
+                        "-I", os.path.join(PKG, "csrc"), os.path.join(ROOT, "tests", "native", "traverse_host.cu"), "-o", so],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lib = C.CDLL(so)
+    lib.th_scene_create.restype = C.c_void_p
+    lib.th_scene_create.argtypes = [C.c_void_p]
+    lib.th_scene_destroy.argtypes = [C.c_void_p]
+    lib.th_scene_leaves.argtypes = [C.c_void_p]
+    lib.th_scene_nodes.argtypes = [C.c_void_p]
+    lib.th_last_error.restype = C.c_char_p
+    lib.th_intersect.argtypes = [C.c_void_p] * 4 + [C.c_size_t, C.c_int] + [C.c_void_p] * 5
+    lib.th_shadow.argtypes = [C.c_void_p] * 4 + [C.c_size_t, C.c_int, C.c_void_p]
+    lib.th_rng.argtypes = [C.c_uint32, C.c_size_t, C.c_void_p, C.c_void_p]
+    return lib
+
+
+class Mirror:
+    def __init__(self, lib, scene):
+        self.lib = lib
+        self.desc, self.keep = desc_from_golden(scene)          # the REFERENCE's trees
+        self.h = lib.th_scene_create(C.addressof(self.desc))
+        assert self.h, lib.th_last_error()
+
+    def close(self):
+        self.lib.th_scene_destroy(self.h)
+
+    def intersect(self, org, dirs, cull, variant):
+        org, dirs = np.ascontiguousarray(org, np.float32), np.ascontiguousarray(dirs, np.float32)
+        cull = np.ascontiguousarray(cull, np.uint8)
+        n = len(cull)
+        prim, t = np.empty(n, np.int32), np.empty(n, np.float64)
+        coords, normal = np.empty((n, 3), np.float32), np.empty((n, 3), np.float32)
+        counts = np.zeros(2, np.uint64)
+        self.lib.th_intersect(self.h, org.ctypes.data, dirs.ctypes.data, cull.ctypes.data, n, variant, prim.ctypes.data,
+                              t.ctypes.data, coords.ctypes.data, normal.ctypes.data, counts.ctypes.data)
+        return prim, t, coords, normal, counts
+
+    def shadow(self, src, dst, cull, variant):
+        src, dst = np.ascontiguousarray(src, np.float32), np.ascontiguousarray(dst, np.float32)
+        cull = np.ascontiguousarray(cull, np.uint8)
+        out = np.empty(len(cull), np.uint8)
+        self.lib.th_shadow(self.h, src.ctypes.data, dst.ctypes.data, cull.ctypes.data, len(cull), variant, out.ctypes.data)
+        return out
+
+
+def bits32(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+@pytest.mark.parametrize("scene", SCENES)
+def test_every_walk_returns_the_reference_hit(mirror, scene):
+    m = Mirror(mirror, scene)
+    g = golden("rays_%s.npz" % scene)
+    small = scene != "bunny"
+    assert (mirror.th_scene_leaves(m.h) > 0) == small          # Cornell scenes take the flat leaf list, the bunny walks
+    for tag in ("P", "S", "R", "A"):
+        for variant, name in ((0, "reference walk"), (1, "pruned walk"), (2, "deferred / flat")):
+            prim, t, coords, normal, _ = m.intersect(g[tag + "_org"], g[tag + "_dir"], g[tag + "_cull"], variant)
+            where = "%s/%s/%s" % (scene, tag, name)
+            bad = np.nonzero(prim != g[tag + "_prim"])[0]
+            assert len(bad) == 0, "%s: %d primitive ids differ, first at %s" % (where, len(bad), bad[:5])
+            assert (t.view(np.uint64) == g[tag + "_t"].view(np.uint64)).all(), where     # Intersection::distance, every bit
+            assert (bits32(coords) == bits32(g[tag + "_coords"])).all(), where
+            assert (bits32(normal) == bits32(g[tag + "_normal"])).all(), where
+    for variant in (0, 1, 2):
+        sh = m.shadow(g["shadow_from"], g["shadow_to"], g["shadow_cull"], variant)
+        assert (sh == g["shadow"]).all(), "%s shadow variant %d: %d differ" % (scene, variant, (sh != g["shadow"]).sum())
+    m.close()
+
+
+@pytest.mark.parametrize("scene", ["standard", "refractive", "bunny"])
+def test_pruning_only_removes_work_and_counts_follow_the_reference(mirror, scene):
+    """Visit counters of the literal walk against the oracle's (the algorithmic bytes per ray are
+    these counts); the pruned walk visits a subset."""
+    from conftest import oracle_for
+    from oracle import bindings as B
+    m = Mirror(mirror, scene)
+    g = golden("rays_%s.npz" % scene)
+    o, d, c = g["R_org"], g["R_dir"], g["R_cull"]
+    orc, _ = oracle_for(scene)
+    B.oracle_stats(orc)
+    orc.intersect(o, d, c)
+    st = B.oracle_stats(orc)
+    full = m.intersect(o, d, c, 0)[4]
+    pruned = m.intersect(o, d, c, 1)[4]
+    mesh_entries = st["traversals"] - st["scene_rays"]       # the reference tests a mesh's box twice (leaf, then mesh root)
+    assert int(full[1]) == st["prim_tests"]
+    assert int(full[0]) == st["node_visits"] - mesh_entries
+    assert pruned[0] <= full[0] and pruned[1] <= full[1] and pruned[0] < full[0]
+    m.close()
+
+
+def test_non_plain_rays_take_the_nan_safe_path(mirror):
+    """Rays with a zero direction component (infinite reciprocal: 0 * inf = NaN in the slab test) and origins on box
+    planes: the flat leaf list is not used for them and the NaN-preserving std::max / std::min chain of
+    Bounds3.hpp:92-115 decides — all three walks must still agree with each other and with the oracle."""
+    from conftest import oracle_for
+    rs = np.random.RandomState(7)
+    n = 6000
+    org = (rs.rand(n, 3) * np.array([556.0, 548.8, 559.2])).astype(np.float32)
+    d = (rs.rand(n, 3) * 2 - 1).astype(np.float32)
+    axis = rs.randint(0, 3, n)
+    d[np.arange(n), axis] = np.where(rs.rand(n) < 0.5, 0.0, -0.0).astype(np.float32)
+    snap = rs.rand(n) < 0.5                                    # origin exactly on a wall plane of that axis
+    planes = np.array([[0.0, 556.0], [0.0, 548.8], [0.0, 559.2]], np.float32)
+    org[np.arange(n)[snap], axis[snap]] = planes[axis[snap], rs.randint(0, 2, snap.sum())]
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    d[np.arange(n), axis] = 0.0
+    cull = (np.arange(n) % 3).astype(np.uint8)
+    for scene in ("standard", "refractive"):
+        m = Mirror(mirror, scene)
+        orc, _ = oracle_for(scene)
+        op, ot, oc, on = orc.intersect(org, d, cull)
+        for variant in (0, 1, 2):
+            prim, t, coords, normal, _ = m.intersect(org, d, cull, variant)
+            assert (prim == op).all(), (scene, variant, int((prim != op).sum()))
+            assert (t.view(np.uint64) == ot.view(np.uint64)).all()
+            assert (bits32(coords) == bits32(oc)).all() and (bits32(normal) == bits32(on)).all()
+        assert 0.2 < (op >= 0).mean()
+        m.close()
+
+
+def test_rng_product_form_is_the_division(mirror):
+    """rng_float multiplies by 1/4294967295 instead of dividing (traverse.cuh): the same float for the golden stream."""
+    n = 200000
+    st, fl = np.empty(n, np.uint32), np.empty(n, np.float32)
+    mirror.th_rng(0xC0FFEE, n, st.ctypes.data, fl.ctypes.data)
+    # XorShift32 restated in numpy for the first 1000 draws (global.cpp:5-22)
+    s = 0xC0FFEE
+    for i in range(1000):
+        s ^= (s << 13) & 0xFFFFFFFF
+        s ^= s >> 17
+        s ^= (s << 15) & 0xFFFFFFFF
+        assert st[i] == s
+        assert fl[i] == np.float32(np.float64(s) / np.float64(0xFFFFFFFF))
+    assert (fl > 0).all() and (fl <= 1).all()

@@ -11,6 +11,7 @@
 #include <mutex>
 
 #include "integrators.cuh"
+#include "scene_build.h"
 #include "tpt_internal.h"
 
 // ------------------------------------------------------------------ error plumbing
@@ -154,78 +155,6 @@ extern "C" int tpt_probe_read_bandwidth(int device, size_t bytes, int repeats, d
 // ------------------------------------------------------------------ scene builder
 namespace {
 
-struct HostBuild {
-    const TptSceneDesc* d;
-    std::vector<float4> nodes;       // 2 per node
-    std::vector<DevObject> objs;
-    std::string err;
-
-    static float as_f(int v) { float f; std::memcpy(&f, &v, 4); return f; }
-
-    int push(const TptVec3& lo, const TptVec3& hi, int prim) {
-        const int self = (int)nodes.size() / 2;
-        nodes.push_back(make_float4(lo.x, lo.y, lo.z, as_f(prim)));
-        nodes.push_back(make_float4(hi.x, hi.y, hi.z, as_f(self + 1)));
-        return self;
-    }
-    void set_miss(int node) { nodes[2 * node + 1].w = as_f((int)nodes.size() / 2); }
-
-    // the reference pops `right` first (BVH.cpp:137-138,121): right subtree precedes left
-    bool emit_mesh(const TptObject& o, int local, int depth) {
-        if (local < 0 || local >= o.n_nodes || depth > 128) { err = "malformed mesh BVH"; return false; }
-        const TptNode& n = d->mesh_nodes[o.first_node + local];
-        if (n.object >= 0) {
-            if (n.object >= o.n_prims) { err = "mesh BVH leaf outside its mesh"; return false; }
-            push(n.bmin, n.bmax, o.first_prim + n.object);
-            return true;
-        }
-        const int self = push(n.bmin, n.bmax, -1);
-        if (!emit_mesh(o, n.right, depth + 1) || !emit_mesh(o, n.left, depth + 1)) return false;
-        set_miss(self);
-        return true;
-    }
-    bool emit_top(int idx, int depth) {
-        if (idx < 0 || idx >= d->n_top_nodes || depth > 128) { err = "malformed top-level BVH"; return false; }
-        const TptNode& n = d->top_nodes[idx];
-        if (n.object >= 0) {
-            if (n.object >= d->n_objects) { err = "top-level leaf outside objects[]"; return false; }
-            const TptObject& o = d->objects[n.object];
-            DevObject& dev = objs[n.object];
-            if (o.kind == TPT_OBJ_SPHERE) {
-                dev.root = push(n.bmin, n.bmax, d->n_tris + o.first_prim);
-                dev.end = dev.root + 1;
-                return true;
-            }
-            if (o.n_nodes <= 0) { err = "mesh without a BVH"; return false; }
-            // The leaf box (MeshTriangle::bounding_box) and the mesh root box are the same
-            // numbers for a mesh built by the host API; then one slab test stands for both.
-            const TptNode& mr = d->mesh_nodes[o.first_node];
-            const bool same = std::memcmp(&mr.bmin, &n.bmin, sizeof(TptVec3)) == 0 &&
-                              std::memcmp(&mr.bmax, &n.bmax, sizeof(TptVec3)) == 0;
-            int gate = -1;
-            if (!same) gate = push(n.bmin, n.bmax, -1);
-            dev.root = (int)nodes.size() / 2;
-            if (!emit_mesh(o, 0, depth + 1)) return false;
-            dev.end = (int)nodes.size() / 2;
-            if (gate >= 0) set_miss(gate);
-            return true;
-        }
-        const int self = push(n.bmin, n.bmax, -1);
-        if (!emit_top(n.right, depth + 1) || !emit_top(n.left, depth + 1)) return false;
-        set_miss(self);
-        return true;
-    }
-};
-
-// Appends one array to the scene blob (16-byte granular) and returns its byte offset.
-template <class T> size_t blob_put(std::vector<unsigned char>& blob, const std::vector<T>& host) {
-    const size_t off = blob.size();
-    const size_t bytes = (host.size() * sizeof(T) + 15) & ~size_t(15);
-    blob.resize(off + bytes, 0);
-    if (!host.empty()) std::memcpy(blob.data() + off, host.data(), host.size() * sizeof(T));
-    return off;
-}
-
 struct DeviceInfo { int num_sms, smem_optin; };
 int device_info(int device, DeviceInfo* out) {      // cudaGetDeviceProperties costs milliseconds: ask once
     static std::mutex mu;
@@ -247,177 +176,25 @@ int device_info(int device, DeviceInfo* out) {      // cudaGetDeviceProperties c
 extern "C" int tpt_scene_create(const TptSceneDesc* d, int device, TptScene** out) {
     if (!d || !out) { tpt_set_error("null argument"); return TPT_ERR_INVALID; }
     *out = nullptr;
-    if (d->width <= 0 || d->height <= 0 || d->n_objects <= 0 || d->n_top_nodes <= 0 || d->n_materials <= 0 ||
-        !d->objects || !d->top_nodes || !d->materials) {
-        tpt_set_error("scene description is empty or incomplete");
-        return TPT_ERR_INVALID;
-    }
-    HostBuild hb;
-    hb.d = d;
-    hb.objs.assign(d->n_objects, DevObject());
-    for (int k = 0; k < d->n_objects; ++k) {
-        const TptObject& o = d->objects[k];
-        DevObject& dev = hb.objs[k];
-        std::memset(&dev, 0, sizeof dev);
-        if (o.material < 0 || o.material >= d->n_materials) { tpt_set_error("object material out of range"); return TPT_ERR_INVALID; }
-        dev.kind = o.kind; dev.material = o.material; dev.first_prim = o.first_prim; dev.n_prims = o.n_prims;
-        dev.root = dev.end = -1; dev.lroot = o.first_node; dev.area = o.area;
-        if (o.kind == TPT_OBJ_MESH) {
-            if (o.first_prim < 0 || o.first_prim + o.n_prims > d->n_tris || o.first_node < 0 ||
-                o.first_node + o.n_nodes > d->n_mesh_nodes || o.n_nodes <= 0) {
-                tpt_set_error("mesh ranges out of bounds");
-                return TPT_ERR_INVALID;
-            }
-            dev.root_area = d->mesh_nodes[o.first_node].area;
-        } else if (o.kind == TPT_OBJ_SPHERE) {
-            if (o.first_prim < 0 || o.first_prim >= d->n_spheres) { tpt_set_error("sphere index out of bounds"); return TPT_ERR_INVALID; }
-            dev.root_area = d->spheres[o.first_prim].area;
-        } else { tpt_set_error("unknown object kind"); return TPT_ERR_INVALID; }
-    }
-    if (!hb.emit_top(0, 0)) { tpt_set_error(hb.err); return TPT_ERR_INVALID; }
-    for (int k = 0; k < d->n_objects; ++k)
-        if (hb.objs[k].root < 0) { tpt_set_error("an object is not reachable from the top-level BVH"); return TPT_ERR_INVALID; }
-
-    std::vector<float4> tris, tverts, spheres, mats;
-    std::vector<DevLightNode> lnodes(d->n_mesh_nodes);
-    for (int k = 0; k < d->n_objects; ++k) {
-        const TptObject& o = d->objects[k];
-        if (o.kind != TPT_OBJ_MESH) continue;
-        for (int j = 0; j < o.n_nodes; ++j) {
-            const TptNode& n = d->mesh_nodes[o.first_node + j];
-            DevLightNode& l = lnodes[o.first_node + j];
-            l.left = n.left; l.right = n.right; l.area = n.area;
-            l.tri = n.object >= 0 ? o.first_prim + n.object : -1;
-        }
-    }
-    std::vector<int> triMat(d->n_tris, 0), triObj(d->n_tris, 0);
-    for (int k = 0; k < d->n_objects; ++k)
-        if (d->objects[k].kind == TPT_OBJ_MESH)
-            for (int j = 0; j < d->objects[k].n_prims; ++j) {
-                triMat[d->objects[k].first_prim + j] = d->objects[k].material;
-                triObj[d->objects[k].first_prim + j] = k;
-            }
-    for (int p = 0; p < d->n_tris; ++p) {
-        const TptTriangle& t = d->tris[p];
-        tris.push_back(make_float4(t.v0.x, t.v0.y, t.v0.z, HostBuild::as_f(triMat[p])));
-        tris.push_back(make_float4(t.e1.x, t.e1.y, t.e1.z, t.area));
-        tris.push_back(make_float4(t.e2.x, t.e2.y, t.e2.z, HostBuild::as_f(triObj[p])));
-        tris.push_back(make_float4(t.normal.x, t.normal.y, t.normal.z, 0.0f));
-        tverts.push_back(make_float4(t.v1.x, t.v1.y, t.v1.z, 0.0f));
-        tverts.push_back(make_float4(t.v2.x, t.v2.y, t.v2.z, 0.0f));
-    }
-    std::vector<int> sphMat(d->n_spheres, 0), sphObj(d->n_spheres, 0);
-    for (int k = 0; k < d->n_objects; ++k)
-        if (d->objects[k].kind == TPT_OBJ_SPHERE) {
-            sphMat[d->objects[k].first_prim] = d->objects[k].material;
-            sphObj[d->objects[k].first_prim] = k;
-        }
-    for (int j = 0; j < d->n_spheres; ++j) {
-        const TptSphere& s = d->spheres[j];
-        spheres.push_back(make_float4(s.center.x, s.center.y, s.center.z, s.radius));
-        spheres.push_back(make_float4(s.radius2, s.area, HostBuild::as_f(sphMat[j]), HostBuild::as_f(sphObj[j])));
-    }
-    for (int m = 0; m < d->n_materials; ++m) {
-        const TptMaterial& t = d->materials[m];
-        const int emissive = (t.emission.x > 0.0f || t.emission.y > 0.0f || t.emission.z > 0.0f) ? 1 : 0;   // Material.hpp:29-32
-        mats.push_back(make_float4(t.emission.x, t.emission.y, t.emission.z, HostBuild::as_f(t.type)));
-        mats.push_back(make_float4(t.Kd.x, t.Kd.y, t.Kd.z, t.rough));
-        mats.push_back(make_float4(t.ior_m.x, t.ior_m.y, t.ior_m.z, t.ior_d));
-        mats.push_back(make_float4(t.ior_m_k.x, t.ior_m_k.y, t.ior_m_k.z, HostBuild::as_f(emissive)));
-    }
-    std::vector<int> emissive(d->emissive_objects, d->emissive_objects + d->n_emissive);
-    for (int e : emissive)
-        if (e < 0 || e >= d->n_objects) { tpt_set_error("emissive object index out of range"); return TPT_ERR_INVALID; }
-
-    int rc = require_device(device);
+    SceneBlob blob;       // validation, grafted node array, leaf lists, one blob: scene_build.h
+    int rc = tpt_build_scene_blob(d, &blob);
+    if (rc != TPT_OK) return rc;
+    rc = require_device(device);
     if (rc != TPT_OK) return rc;
 
-    // Flat leaf list (traverse.cuh, closest_hit_flat): valid when every node's box contains the boxes of
-    // its whole subtree, which is what Union() builds (BVH.cpp:44-52, 93-95); checked, not assumed.
-    std::vector<float4> leaves;
-    {
-        const int nn = (int)hb.nodes.size() / 2;
-        int nleaf = 0;
-        for (int i = 0; i < nn; ++i) { int prim; std::memcpy(&prim, &hb.nodes[2 * i].w, 4); nleaf += prim >= 0; }
-        bool ok = nleaf > 0 && nleaf <= 64;
-        for (int i = 0; ok && i < nn; ++i) {
-            int miss; std::memcpy(&miss, &hb.nodes[2 * i + 1].w, 4);
-            const float4 lo = hb.nodes[2 * i], hi = hb.nodes[2 * i + 1];
-            for (int k = i + 1; ok && k < miss; ++k) {
-                const float4 a = hb.nodes[2 * k], b = hb.nodes[2 * k + 1];
-                ok = a.x >= lo.x && a.y >= lo.y && a.z >= lo.z && b.x <= hi.x && b.y <= hi.y && b.z <= hi.z &&
-                     a.x <= b.x && a.y <= b.y && a.z <= b.z;
-            }
-        }
-        if (ok)
-            for (int i = 0; i < nn; ++i) {
-                int prim; std::memcpy(&prim, &hb.nodes[2 * i].w, 4);
-                if (prim >= 0) { leaves.push_back(hb.nodes[2 * i]); leaves.push_back(hb.nodes[2 * i + 1]); }
-            }
-    }
-    // leaves with bit-identical boxes are tested once: the same numbers give the same answer
-    std::vector<float4> uboxes;
-    for (size_t l = 0; l < leaves.size() / 2; ++l) {
-        float4 lo = leaves[2 * l], hi = leaves[2 * l + 1];
-        size_t u = 0;
-        for (; u < uboxes.size() / 2; ++u)
-            if (std::memcmp(&uboxes[2 * u], &lo, 12) == 0 && std::memcmp(&uboxes[2 * u + 1], &hi, 12) == 0) break;
-        if (u == uboxes.size() / 2) {
-            lo.w = hi.w = HostBuild::as_f(0);
-            uboxes.push_back(lo); uboxes.push_back(hi);
-        }
-        unsigned bits;
-        float4& word = l < 32 ? uboxes[2 * u] : uboxes[2 * u + 1];
-        std::memcpy(&bits, &word.w, 4);
-        bits |= 1u << (l & 31);
-        std::memcpy(&word.w, &bits, 4);
-    }
-    // one blob, one allocation, one host->device copy: the arrays in the order stage_scene expects
-    std::vector<unsigned char> blob;
-    const size_t o_nodes = blob_put(blob, hb.nodes), o_tris = blob_put(blob, tris), o_tverts = blob_put(blob, tverts),
-                 o_spheres = blob_put(blob, spheres), o_mats = blob_put(blob, mats), o_objs = blob_put(blob, hb.objs),
-                 o_lnodes = blob_put(blob, lnodes), o_emissive = blob_put(blob, emissive), o_leaves = blob_put(blob, leaves),
-                 o_uboxes = blob_put(blob, uboxes);
     TptScene* s = new TptScene;
     s->device = device;
     s->n_prims = d->n_tris + d->n_spheres;
-    SceneView& v = s->view;
-    std::memset(&v, 0, sizeof v);
-    unsigned char* dblob = static_cast<unsigned char*>(tpt_dev_alloc(blob.size()));
+    unsigned char* dblob = static_cast<unsigned char*>(tpt_dev_alloc(blob.bytes.size()));
     s->d_stats = static_cast<unsigned long long*>(tpt_dev_alloc(STAT_COUNT * sizeof(unsigned long long)));
     if (!dblob || !s->d_stats) { if (dblob) tpt_dev_free(dblob); tpt_scene_destroy(s); return TPT_ERR_OOM; }
     s->allocs.push_back(dblob);
-    if (!tpt_cuda_ok(cudaMemcpy(dblob, blob.data(), blob.size(), cudaMemcpyHostToDevice), "cudaMemcpy(scene)")) {
+    if (!tpt_cuda_ok(cudaMemcpy(dblob, blob.bytes.data(), blob.bytes.size(), cudaMemcpyHostToDevice), "cudaMemcpy(scene)")) {
         tpt_scene_destroy(s);
         return TPT_ERR_CUDA;
     }
-    v.blob = dblob;
-    v.blob_bytes = (unsigned)blob.size();
-    v.nodes = reinterpret_cast<const float4*>(dblob + o_nodes);
-    v.tris = reinterpret_cast<const float4*>(dblob + o_tris);
-    v.tverts = reinterpret_cast<const float4*>(dblob + o_tverts);
-    v.spheres = reinterpret_cast<const float4*>(dblob + o_spheres);
-    v.mats = reinterpret_cast<const float4*>(dblob + o_mats);
-    v.objs = reinterpret_cast<const DevObject*>(dblob + o_objs);
-    v.lnodes = reinterpret_cast<const DevLightNode*>(dblob + o_lnodes);
-    v.emissive = reinterpret_cast<const int*>(dblob + o_emissive);
-    v.leaves = reinterpret_cast<const float4*>(dblob + o_leaves);
-    v.n_leaves = (int)leaves.size() / 2;
-    v.uboxes = reinterpret_cast<const float4*>(dblob + o_uboxes);
-    v.n_uboxes = (int)uboxes.size() / 2;
-    v.n_nodes = (int)hb.nodes.size() / 2; v.n_tris = d->n_tris; v.n_spheres = d->n_spheres;
-    v.n_mats = d->n_materials; v.n_objs = d->n_objects; v.n_lnodes = d->n_mesh_nodes; v.n_emissive = d->n_emissive;
-    v.width = d->width; v.height = d->height;
-    // CalculateScale(fov) with the reference's promotions (SceneRenderingHelper.cpp:12-14, global.hpp:9)
-    {
-        const float fov = (float)d->fov;
-        const float half = (float)(fov * 0.5);
-        const float rad = (float)((double)(half * 3.141592653589793f) / 180.0);
-        v.scale = (float)std::tan((double)rad);
-    }
-    v.aspect = (float)(d->width / d->height);
-    v.eye = make_float3(d->eye.x, d->eye.y, d->eye.z);
-    v.background = make_float3(d->background.x, d->background.y, d->background.z);
+    SceneView& v = s->view;
+    tpt_scene_view(blob, dblob, d, &v);
     DeviceInfo di;
     if ((rc = device_info(device, &di)) != TPT_OK) { tpt_scene_destroy(s); return rc; }
     s->num_sms = di.num_sms;
