@@ -3,8 +3,12 @@
 // to plain IEEE single-precision operations (this file is built with -ffp-contract=off, so nothing is fused: the
 // same roundings as __fadd_rn / __fmul_rn / ... on the device).  The scene goes through the product's own host-side
 // builder (csrc/scene_build.h: grafted node array, flat leaf list, blob) and the SceneView points into a host copy
-// of the blob.  tests/test_traverse_host.py feeds the golden ray batches through every walk and compares with the
+// of the blob.  tests/test_host_mirror.py feeds the golden ray batches through every walk and compares with the
 // reference's answers bit for bit — the device-independent half of the exact tier, checked without a GPU.
+//
+// The second half does the same for the shading tier and the integrators (csrc/material.cuh, csrc/integrators.cuh:
+// Material::*, subpath generation, PathWeight, PathTrace, the BDPT strategy loop with its splats) with the loop
+// body of the one-thread-per-pixel validation kernel (k_render_mega, tpt.cu) restated around them.
 //
 // Not mirrored: the warp-cooperative pooling of the primitive tests (coop_test: shuffles); it runs the same
 // settle_candidate on the same candidates in the same order as closest_hit_deferred, which is mirrored.
@@ -46,8 +50,10 @@ static const HmDim hm_thread = {0, 0, 0}, hm_block = {1, 1, 1};
 #define __syncwarp hm_syncwarp
 #define threadIdx hm_thread
 #define blockDim hm_block
+__host__ __device__ inline float hm_atomic_add(float* p, float v) { const float old = *p; *p = old + v; return old; }   // one host thread
+#define atomicAdd hm_atomic_add
 
-#include "traverse.cuh"
+#include "integrators.cuh"
 #include "scene_build.h"
 
 static thread_local std::string g_error;
@@ -125,6 +131,144 @@ void th_rng(uint32_t seed, size_t n, uint32_t* states, float* floats) {
         states[i] = s;
         floats[i] = f;
     }
+}
+
+// ---- shading tier ---------------------------------------------------------------------------------
+// op 0: evalGivenSample(a = wo, b = wi, c = N), 1: pdf(a = wo, b = N, c = wi), 2: fresnel(a = I, b = N),
+// 3: sample(a = wo, b = N, seeds) -> out3 = wi, out1 = pdf, out_state — the argument order of k_material (tpt.cu)
+void th_material(const HostScene* s, int op, int mat, const float* a, const float* b, const float* c, const uint32_t* seeds,
+                 int combine, size_t n, float* out3, float* out1, uint32_t* out_state) {
+    const Mat m = load_mat(s->view, mat);
+    for (size_t i = 0; i < n; ++i) {
+        if (op == 0) St3(out3, i, mat_eval(m, Ld3(a, i), Ld3(b, i), Ld3(c, i), combine != 0));
+        else if (op == 1) out1[i] = mat_pdf(m, Ld3(a, i), Ld3(b, i), Ld3(c, i));
+        else if (op == 2) St3(out3, i, mat_fresnel(m, Ld3(a, i), Ld3(b, i)));
+        else {
+            uint32_t st = seeds[i];
+            float pdf;
+            St3(out3, i, mat_sample(m, st, Ld3(a, i), Ld3(b, i), &pdf));
+            out1[i] = pdf;
+            out_state[i] = st;
+        }
+    }
+}
+
+}  // extern "C"
+
+static Ctx MakeCtx(const SceneView& sc, bool prune) {
+    Ctx c;
+    c.sc = sc; c.prune = prune;
+    c.cnt.node_visits = 0; c.cnt.prim_tests = 0; c.scene_rays = 0; c.probe_rays = 0;
+    return c;
+}
+__host__ __device__ inline PVert ToPVert(const PVert& v) { return v; }
+__host__ __device__ inline PVert ToPVert(const TptPathVertex& v) {
+    PVert p;
+    p.x = mk3(v.x.x, v.x.y, v.x.z); p.N = mk3(v.N.x, v.N.y, v.N.z);
+    p.prim = v.prim; p.type = v.type; p.pdf = v.pdf; p.alpha = mk3(v.alpha.x, v.alpha.y, v.alpha.z);
+    return p;
+}
+static TptPathVertex FromPVert(const PVert& v) {
+    TptPathVertex o;
+    o.x = TptVec3{v.x.x, v.x.y, v.x.z}; o.N = TptVec3{v.N.x, v.N.y, v.N.z};
+    o.prim = v.prim; o.type = v.type; o.pdf = v.pdf; o.alpha = TptVec3{v.alpha.x, v.alpha.y, v.alpha.z};
+    return o;
+}
+template <class V> struct HostPath {
+    const V* v;
+    __host__ __device__ PVert operator()(int k) const { return ToPVert(v[k]); }
+    __host__ __device__ f3 pos(int k) const { return ToPVert(v[k]).x; }
+};
+
+extern "C" {
+
+// BDPTPath::PathWeight for every (s, t) of n subpath pairs: weights[n][16][17][3], as tpt_bdpt_pathweight_batch
+void th_pathweight(const HostScene* s, const TptPathVertex* cam, const int32_t* camCount, const TptPathVertex* light,
+                   const int32_t* lightCount, size_t n, float* weights) {
+    Ctx c = MakeCtx(s->view, true);
+    for (size_t i = 0; i < n * 16 * 17; ++i) {
+        const size_t pair = i / (16 * 17);
+        const int st = (int)(i % (16 * 17)), sc = st / 17 + 1, t = st % 17;
+        f3 w = mk3(0.0f);
+        if (sc <= camCount[pair] && t <= lightCount[pair] && sc + t >= 2) {
+            const HostPath<TptPathVertex> camA{cam + 16 * pair}, lightA{light + 16 * pair};
+            w = path_weight<false>(c, camA, sc, lightA, t);
+        }
+        St3(weights, i, w);
+    }
+}
+
+// GenerateCameraPath / GenerateLightPath for explicit (pixel, seed) pairs, as tpt_bdpt_subpaths_batch
+void th_subpaths(const HostScene* s, const int32_t* pixels, const uint32_t* seeds, size_t n, TptPathVertex* cam,
+                 int32_t* camCount, TptPathVertex* light, int32_t* lightCount, uint32_t* outState) {
+    Ctx c = MakeCtx(s->view, true);
+    const SceneView& sc = c.sc;
+    for (size_t i = 0; i < n; ++i) {
+        uint32_t rng = seeds[i];
+        const int pixel = pixels[i];
+        PVert cv[MAX_BDPT_PATH_LENGTH], lv[MAX_BDPT_PATH_LENGTH];
+        DHit h;
+        trace_scene<false>(c, make_ray(mk3(sc.eye.x, sc.eye.y, sc.eye.z), pixel_ray(sc, pixel % sc.width, pixel / sc.width)), 0, &h);
+        camera_path_head(sc, h, cv);
+        const int nc = fill_path<false>(c, rng, cv);
+        const LightStart ls = light_path_head(sc, rng, sc.emissive[0], lv);
+        trace_scene<false>(c, make_ray(lv[0].x, ls.w_i), 0, &h);
+        int nl = 2;
+        if (light_path_first_hit(ls, h, lv)) nl = fill_path<false>(c, rng, lv);
+        for (int k = 0; k < nc; ++k) cam[16 * i + k] = FromPVert(cv[k]);
+        for (int k = 0; k < nl; ++k) light[16 * i + k] = FromPVert(lv[k]);
+        camCount[i] = nc; lightCount[i] = nl;
+        outState[i] = rng;
+    }
+}
+
+// FillBufferThread's loop body (Renderer.cpp:40-53) for every pixel, as k_render_mega runs it: radiance[w*h*3] is the
+// per-pixel sum, splat[w*h*3] the t = 1 strategies' image (both already divided by spp, Renderer.cpp:49-60).
+// mode: TPT_MODE_*; seeds are pixel + 1.  Returns the reference-style ray count.
+unsigned long long th_render(const HostScene* s, int mode, int spp, float* radiance, float* splat) {
+    Ctx c = MakeCtx(s->view, true);
+    const SceneView& sc = c.sc;
+    const int npix = sc.width * sc.height;
+    unsigned long long ref_rays = 0;
+    for (int i = 0; i < npix * 3; ++i) radiance[i] = splat[i] = 0.0f;
+    for (int pixel = 0; pixel < npix; ++pixel) {
+        uint32_t rng = (uint32_t)pixel + 1u;
+        const float inv_spp = 1.0f / spp;
+        const DRay primary = make_ray(mk3(sc.eye.x, sc.eye.y, sc.eye.z), pixel_ray(sc, pixel % sc.width, pixel / sc.width));
+        f3 acc = mk3(0.0f);
+        for (int k = 0; k < spp; ++k) {
+            f3 L;
+            if (mode == TPT_MODE_BDPT) {
+                PVert cam[MAX_BDPT_PATH_LENGTH], light[MAX_BDPT_PATH_LENGTH];
+                DHit h;
+                trace_scene<false>(c, primary, 0, &h);
+                camera_path_head(sc, h, cam);
+                const int nc = fill_path<false>(c, rng, cam);
+                const LightStart ls = light_path_head(sc, rng, sc.emissive[0], light);
+                trace_scene<false>(c, make_ray(light[0].x, ls.w_i), 0, &h);
+                int nl = 2;
+                if (light_path_first_hit(ls, h, light)) nl = fill_path<false>(c, rng, light);
+                ref_rays += nc + nl;
+                const HostPath<PVert> camA{cam}, lightA{light};
+                L = mk3(0.0f);
+                for (int sv = 1; sv <= nc; ++sv)
+                    for (int t = 0; t <= nl; ++t) {
+                        if (sv + t < 2) continue;
+                        const f3 w = path_weight<false>(c, camA, sv, lightA, t);
+                        if (sv > 1) L += w;
+                        else splat_to_image(sc, light[t - 1].x, w, splat);
+                    }
+            } else {
+                int bounces;
+                L = path_trace<false>(c, rng, primary, mode == TPT_MODE_PT_FULL, &bounces);
+                ref_rays += bounces;
+            }
+            acc += inv_spp * L;
+        }
+        St3(radiance, pixel, acc);
+    }
+    for (int i = 0; i < npix * 3; ++i) splat[i] = splat[i] * 1.0f / spp;      // Renderer.cpp:58-60
+    return ref_rays;
 }
 
 }  // extern "C"

@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 from conftest import golden, gpu_scene
+from shading_checks import check_small_renders
 
 pytestmark = pytest.mark.gpu
 SCENES = ["standard", "smooth", "silver", "refractive", "occlusion", "bunny"]
@@ -17,25 +18,8 @@ def tonemap8(img):
 @pytest.mark.parametrize("pipeline", [0, 1], ids=["wavefront", "megakernel"])
 @pytest.mark.parametrize("scene", SCENES)
 def test_small_renders_against_reference(tpt, scene, pipeline):
-    """64x64, same spp and the same per-pixel streams as the golden reference renders.  Paths diverge
-    from the reference only where an ulp flips a decision, so the images agree far better than two
-    independent renders would: global mean within 1 % per channel (2 % for the firefly-prone
-    silver / occlusion scenes at this tiny sample count)."""
-    g = golden("render.npz")
     s = gpu_scene(scene, 64, 64)
-    for name, mode, spp in MODES:
-        img, st = s.render(name, spp, pipeline=pipeline)
-        ref = g["%s_m%d" % (scene, mode)]
-        assert np.isfinite(img).all(), (scene, name)
-        tol = 0.02 if scene in ("silver", "occlusion") else 0.01
-        rel = np.abs(img.mean((0, 1)) - ref.mean((0, 1))) / ref.mean((0, 1))
-        assert (rel < tol).all(), (scene, name, rel)
-        assert st["samples"] == 64 * 64 * spp
-        if mode == 0:
-            assert st["ref_rays"] == 0                                  # the reference prints "Rays: 0"
-        else:
-            rr = int(g["%s_m%d_rays" % (scene, mode)])
-            assert abs(st["ref_rays"] - rr) < 0.01 * rr, (scene, name, st["ref_rays"], rr)
+    check_small_renders(s, scene, pipeline=pipeline)          # tolerances: tests/shading_checks.py
     s.close()
 
 

@@ -1,118 +1,41 @@
 """GPU parity of the shading functions (Material::sample / pdf / evalGivenSample / fresnel and
-BDPTPath::PathWeight) against golden vectors produced by the compiled reference.  The arithmetic
-is fp32 with double dot products ("f32/f64"); the device may contract a*b+c into FMAs outside the
-cancellation-prone terms, so the tolerance is a few ulps for the rough materials and statistical
-for the near-specular ones (rough 0.002 / 0.01), whose GGX D term amplifies one ulp of cos(theta_h)
-into percents."""
+BDPTPath::PathWeight, subpath generation) against golden vectors produced by the compiled reference.  The
+assertions and their tolerances live in tests/shading_checks.py (shared with the host-compiled mirror of the
+same source, tests/test_host_mirror.py)."""
 import numpy as np
 import pytest
 
-from conftest import golden, gpu_scene
+from conftest import gpu_scene
+from shading_checks import GLOSSY, ROUGH, check_glossy_material, check_pathweight, check_rough_material, check_subpaths
 
 pytestmark = pytest.mark.gpu
-
-ROUGH = [("white", "refractive", 0), ("red", "refractive", 1), ("light", "refractive", 3)]
-GLOSSY = [("glass", "refractive", 4), ("silver", "silver", 0)]
-
-
-def rel_err(a, b):
-    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
-    return np.abs(a - b) / np.maximum(np.abs(b), 1e-30)
-
-
-def close_stats(got, ref):
-    """Error of `got` against `ref` relative to max(|ref|, 1e-4 * largest |ref|): (median, 99.9th percentile, max)."""
-    got = np.asarray(got, np.float64); ref = np.asarray(ref, np.float64)
-    floor = 1e-4 * np.abs(ref).max()
-    e = (np.abs(got - ref) / np.maximum(np.abs(ref), floor)).ravel()
-    return float(np.median(e)), float(np.percentile(e, 99.9)), float(e.max())
 
 
 @pytest.mark.parametrize("tag,scene,mat", ROUGH)
 def test_rough_materials_match_to_ulps(tpt, tag, scene, mat):
-    """Stated tolerance of the shading tier (single-precision dot products, <= 2 ulp division / sqrt):
-    median relative error < 2e-6 (a few ulps), 99.9 % of the values within 2e-4, none beyond 5e-3 —
-    the tail is grazing directions, where a cosine of 1e-3 carries the 1e-7 absolute error of its dot
-    product as 1e-4 relative.  Zero / non-zero decisions must agree exactly."""
     s = gpu_scene(scene)
-    k = golden("kat.npz")
-    wo, wi, n = k["mat_wo"], k["mat_wi"], k["mat_n"]
-    for name, got, ref in (("eval1", s.mat_eval(mat, wo, wi, n, True), k["eval1_" + tag]),
-                           ("eval0", s.mat_eval(mat, wo, wi, n, False), k["eval0_" + tag]),
-                           ("pdf", s.mat_pdf(mat, wo, n, wi), k["pdf_" + tag]),
-                           ("fresnel", s.mat_fresnel(mat, wi, n), k["fresnel_" + tag])):
-        assert ((got == 0) == (ref == 0)).all(), name
-        med, p999, worst = close_stats(got, ref)
-        assert med < 2e-6 and p999 < 2e-4 and worst < 5e-3, (name, med, p999, worst)
-    swi, spdf, sst = s.mat_sample(mat, wo, n, k["mat_seeds"])
-    assert (sst == k["sample_state_" + tag]).all()                      # same number of draws, same stream
-    assert np.allclose(swi, k["sample_wi_" + tag], atol=2e-5)           # libm vs CUDA sin/cos/atan2
-    assert np.allclose(spdf, k["sample_pdf_" + tag], rtol=2e-3, atol=1e-7)
+    check_rough_material(s, tag, mat)
     s.close()
 
 
 @pytest.mark.parametrize("tag,scene,mat", GLOSSY)
 def test_glossy_materials_match_statistically(tpt, tag, scene, mat):
     s = gpu_scene(scene)
-    k = golden("kat.npz")
-    wo, wi, n = k["mat_wo"], k["mat_wi"], k["mat_n"]
-    for got, ref in ((s.mat_eval(mat, wo, wi, n, True), k["eval1_" + tag]),
-                     (s.mat_eval(mat, wo, wi, n, False), k["eval0_" + tag]),
-                     (s.mat_pdf(mat, wo, n, wi), k["pdf_" + tag]),
-                     (s.mat_fresnel(mat, wi, n), k["fresnel_" + tag])):
-        assert ((got == 0) == (ref == 0)).mean() > 0.999            # same support (reflect/refract/zero decisions)
-        nz = ref != 0
-        e = rel_err(got[nz], ref[nz])
-        assert np.median(e) < 1e-5 and np.percentile(e, 99) < 1e-2, (tag, np.median(e), np.percentile(e, 99))
-    swi, spdf, sst = s.mat_sample(mat, wo, n, k["mat_seeds"])
-    assert (sst == k["sample_state_" + tag]).mean() > 0.999            # a Fresnel coin may flip on an ulp
-    ok = sst == k["sample_state_" + tag]
-    assert np.allclose(swi[ok], k["sample_wi_" + tag][ok], atol=5e-5)
+    check_glossy_material(s, tag, mat)
     s.close()
 
 
 @pytest.mark.parametrize("scene,rtol", [("standard", 2e-3), ("refractive", 2e-2), ("silver", 5e-2)])
 def test_pathweight_on_reference_subpaths(tpt, scene, rtol):
-    """Subpaths generated by the reference are handed to the GPU; every strategy weight (s,t) must
-    come back as BDPTPath::PathWeight computed it."""
-    g = golden("bdpt_%s.npz" % scene)
     s = gpu_scene(scene)
-    w = s.pathweights(g["cam"], g["cam_count"], g["light"], g["light_count"])
-    ref = g["weights"]
-    assert w.shape == ref.shape
-    assert np.isfinite(w).all()
-    scale = np.abs(ref).max()
-    big = np.abs(ref) > 1e-7 * scale
-    assert ((w != 0) == (ref != 0)).mean() > 0.9995                   # same shadowed / unshadowed / zero decisions
-    e = rel_err(w[big], ref[big])
-    assert np.median(e) < 1e-5, np.median(e)
-    assert np.percentile(e, 99) < rtol, np.percentile(e, 99)
-    # the sums the integrator forms from them
-    tot, rtot = w.sum((1, 2)), ref.sum((1, 2))
-    assert np.allclose(tot.sum(0), rtot.sum(0), rtol=5e-3)
+    check_pathweight(s, scene, rtol)
     s.close()
 
 
 @pytest.mark.parametrize("scene", ["standard", "refractive", "silver"])
 def test_subpaths_follow_the_reference(tpt, scene):
-    """BDPTPath::GenerateCameraPath / GenerateLightPath on the device against the reference's own
-    subpaths (240 pixels, first sample, seed pixel + 1): same vertex counts and the same RNG state
-    afterwards — i.e. the same number of draws in the same order — for all but the few samples where
-    an ulp of sin/cos (libm vs CUDA) flips a coin; where the counts agree the vertices agree."""
-    g = golden("bdpt_%s.npz" % scene)
     s = gpu_scene(scene)
-    cam, cc, light, lc, st = s.subpaths(g["pixels"], g["pixels"].astype(np.uint32) + 1)
-    same = (cc == g["cam_count"]) & (lc == g["light_count"]) & (st == g["state"])
-    assert same.mean() > 0.95, same.mean()
-    pdf_ok = []
-    for i in np.nonzero(same)[0]:
-        for got, ref, n in ((cam[i], g["cam"][i], cc[i]), (light[i], g["light"][i], lc[i])):
-            assert (got["prim"][:n] == ref["prim"][:n]).all() and (got["type"][:n] == ref["type"][:n]).all()
-            # 556-unit box, float hit points; chains of near-specular bounces amplify the last ulp of a direction
-            assert np.allclose(got["x"][:n], ref["x"][:n], rtol=0, atol=0.05 if scene == "standard" else 5.0)
-            pdf_ok.extend(np.isclose(got["pdf"][:n], ref["pdf"][:n], rtol=2e-2, atol=1e-12).tolist())
-    # area pdfs: within 2 % for the rough scene; the near-specular materials amplify an ulp of cos(theta_h)
-    assert np.mean(pdf_ok) > (0.99 if scene == "standard" else 0.8), np.mean(pdf_ok)
+    check_subpaths(s, scene)
     s.close()
 
 

@@ -1,13 +1,19 @@
-"""The exact tier without a GPU: csrc/traverse.cuh — the traversal source the kernels are compiled from — built
-for the host (tests/native/traverse_host.cu: device intrinsics mapped to plain IEEE float operations, no
-contraction) over a host copy of the scene blob made by the product's own builder (csrc/scene_build.h), run on
-the golden ray batches P / S / R / A of SURVEY 8(d) and compared bit for bit with the reference's answers
-(tests/golden/rays_<scene>.npz, generated from the compiled reference by tests/golden/make_golden.py).
+"""The kernels' source without a GPU.  csrc/traverse.cuh, material.cuh and integrators.cuh — what the CUDA kernels
+are compiled from — built for the host (tests/native/traverse_host.cu: device intrinsics mapped to plain IEEE
+float operations, no contraction) over a host copy of the scene blob made by the product's own builder
+(csrc/scene_build.h).
+
+Exact tier: the golden ray batches P / S / R / A of SURVEY 8(d) through every walk, compared bit for bit with the
+reference's answers (tests/golden/rays_<scene>.npz, generated from the compiled reference by
+tests/golden/make_golden.py).  Function and image tiers: the assertions of the GPU tests themselves
+(tests/shading_checks.py) applied to this build — materials, subpaths, PathWeight, 64x64 renders of six scenes
+in the three modes with the loop body of the validation kernel.
 
 What this pins on the CPU: the grafted visit-ordered node array, the flat leaf list and its bit masks, the pruning
 margins, the any-hit form of ShadowCheck, the deferred (recorded) walk — every walk the kernels use returns the
 reference's primitive id, t, hit point, normal and shadow decision.  What it cannot pin is the device's own
-arithmetic (that a B200 rounds these operations the same way): tests/test_gpu_exact.py does, through the C ABI."""
+arithmetic (that a B200 rounds these operations the same way), nor the wavefront pipeline's queues and launch
+chains: tests/test_gpu_*.py do, through the C ABI.  This module is test infrastructure: the product has no CPU path."""
 import ctypes as C
 import os
 import shutil
@@ -43,13 +49,21 @@ def mirror(tmp_path_factory):
     lib.th_intersect.argtypes = [C.c_void_p] * 4 + [C.c_size_t, C.c_int] + [C.c_void_p] * 5
     lib.th_shadow.argtypes = [C.c_void_p] * 4 + [C.c_size_t, C.c_int, C.c_void_p]
     lib.th_rng.argtypes = [C.c_uint32, C.c_size_t, C.c_void_p, C.c_void_p]
+    lib.th_material.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_size_t] + [C.c_void_p] * 3
+    lib.th_pathweight.argtypes = [C.c_void_p] * 5 + [C.c_size_t, C.c_void_p]
+    lib.th_subpaths.argtypes = [C.c_void_p] * 3 + [C.c_size_t] + [C.c_void_p] * 5
+    lib.th_render.restype = C.c_uint64
+    lib.th_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     return lib
 
 
 class Mirror:
-    def __init__(self, lib, scene):
+    """The methods of tpt_b200.Scene the parity checks use, served by the host build of the kernels' source."""
+
+    def __init__(self, lib, scene, width=None, height=None):
         self.lib = lib
-        self.desc, self.keep = desc_from_golden(scene)          # the REFERENCE's trees
+        self.desc, self.keep = desc_from_golden(scene, width, height)          # the REFERENCE's trees
+        self.width, self.height = self.desc.width, self.desc.height
         self.h = lib.th_scene_create(C.addressof(self.desc))
         assert self.h, lib.th_last_error()
 
@@ -73,6 +87,58 @@ class Mirror:
         out = np.empty(len(cull), np.uint8)
         self.lib.th_shadow(self.h, src.ctypes.data, dst.ctypes.data, cull.ctypes.data, len(cull), variant, out.ctypes.data)
         return out
+
+
+    # -- shading tier: same signatures as tpt_b200.Scene
+    def _mat(self, op, mat, a, b, c=None, seeds=None, combine=0):
+        a, b = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32)
+        c = None if c is None else np.ascontiguousarray(c, np.float32)
+        seeds = None if seeds is None else np.ascontiguousarray(seeds, np.uint32)
+        n = len(a)
+        out3, out1, st = np.zeros((n, 3), np.float32), np.zeros(n, np.float32), np.zeros(n, np.uint32)
+        self.lib.th_material(self.h, op, mat, a.ctypes.data, b.ctypes.data, None if c is None else c.ctypes.data,
+                             None if seeds is None else seeds.ctypes.data, int(combine), n, out3.ctypes.data,
+                             out1.ctypes.data, st.ctypes.data)
+        return out3, out1, st
+
+    def mat_eval(self, mat, wo, wi, nrm, combine=True):
+        return self._mat(0, mat, wo, wi, nrm, combine=combine)[0]
+
+    def mat_pdf(self, mat, wo, nrm, wi):
+        return self._mat(1, mat, wo, nrm, wi)[1]
+
+    def mat_fresnel(self, mat, I, nrm):
+        return self._mat(2, mat, I, nrm)[0]
+
+    def mat_sample(self, mat, wo, nrm, seeds):
+        return self._mat(3, mat, wo, nrm, seeds=seeds)
+
+    def pathweights(self, cam, cam_count, light, light_count):
+        import tpt_b200 as T
+        cam = np.ascontiguousarray(cam, dtype=T.PATHVERTEX_DTYPE).reshape(-1, 16)
+        light = np.ascontiguousarray(light, dtype=T.PATHVERTEX_DTYPE).reshape(-1, 16)
+        cc, lc = np.ascontiguousarray(cam_count, np.int32), np.ascontiguousarray(light_count, np.int32)
+        w = np.empty((len(cc), 16, 17, 3), np.float32)
+        self.lib.th_pathweight(self.h, cam.ctypes.data, cc.ctypes.data, light.ctypes.data, lc.ctypes.data, len(cc), w.ctypes.data)
+        return w
+
+    def subpaths(self, pixels, seeds):
+        import tpt_b200 as T
+        pixels, seeds = np.ascontiguousarray(pixels, np.int32), np.ascontiguousarray(seeds, np.uint32)
+        n = len(pixels)
+        cam, light = np.zeros((n, 16), T.PATHVERTEX_DTYPE), np.zeros((n, 16), T.PATHVERTEX_DTYPE)
+        cc, lc, st = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.uint32)
+        self.lib.th_subpaths(self.h, pixels.ctypes.data, seeds.ctypes.data, n, cam.ctypes.data, cc.ctypes.data,
+                             light.ctypes.data, lc.ctypes.data, st.ctypes.data)
+        return cam, cc, light, lc, st
+
+    def render(self, mode, spp):
+        """(image[h, w, 3] = radiance + splat as tpt_render returns it, {"samples", "ref_rays"})."""
+        import tpt_b200 as T
+        rad = np.zeros((self.height, self.width, 3), np.float32)
+        splat = np.zeros_like(rad)
+        rays = self.lib.th_render(self.h, T.MODES[mode], spp, rad.ctypes.data, splat.ctypes.data)
+        return rad + splat, {"samples": self.width * self.height * spp, "ref_rays": int(rays)}
 
 
 def bits32(a):
@@ -166,3 +232,45 @@ def test_rng_product_form_is_the_division(mirror):
         assert st[i] == s
         assert fl[i] == np.float32(np.float64(s) / np.float64(0xFFFFFFFF))
     assert (fl > 0).all() and (fl <= 1).all()
+
+
+# ---- function level and image level: the GPU tests' own assertions on the host build --------------------------
+from shading_checks import (GLOSSY, RENDER_SCENES, ROUGH, check_glossy_material, check_pathweight,      # noqa: E402
+                            check_rough_material, check_small_renders, check_subpaths)
+
+
+@pytest.mark.parametrize("tag,scene,mat", ROUGH)
+def test_rough_materials_match_to_ulps(mirror, tag, scene, mat):
+    m = Mirror(mirror, scene)
+    check_rough_material(m, tag, mat)
+    m.close()
+
+
+@pytest.mark.parametrize("tag,scene,mat", GLOSSY)
+def test_glossy_materials_match_statistically(mirror, tag, scene, mat):
+    m = Mirror(mirror, scene)
+    check_glossy_material(m, tag, mat)
+    m.close()
+
+
+@pytest.mark.parametrize("scene,rtol", [("standard", 2e-3), ("refractive", 2e-2), ("silver", 5e-2)])
+def test_pathweight_on_reference_subpaths(mirror, scene, rtol):
+    m = Mirror(mirror, scene)
+    check_pathweight(m, scene, rtol)
+    m.close()
+
+
+@pytest.mark.parametrize("scene", ["standard", "refractive", "silver"])
+def test_subpaths_follow_the_reference(mirror, scene):
+    m = Mirror(mirror, scene)
+    check_subpaths(m, scene)
+    m.close()
+
+
+@pytest.mark.parametrize("scene", RENDER_SCENES)
+def test_small_renders_against_reference(mirror, scene):
+    """PathTrace (shipped / full) and BDPT, 64x64, the reference's per-pixel streams: FillBufferThread's loop body as
+    k_render_mega runs it (tpt.cu), around the integrators of csrc/integrators.cuh."""
+    m = Mirror(mirror, scene, 64, 64)
+    check_small_renders(m, scene)
+    m.close()
