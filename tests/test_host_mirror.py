@@ -28,13 +28,17 @@ SCENES = ["standard", "smooth", "silver", "refractive", "occlusion", "bunny"]
 PKG = os.path.join(ROOT, "toypathtracer-games101-assignment7_b200")
 
 
-@pytest.fixture(scope="module")
-def mirror(tmp_path_factory):
+# Compile-time experiments of csrc/ (off in the shipped build, `make NVEXTRA=<define>` to try one on the GPU): each must
+# leave the exact tier bit-exact, which is checked here before any GPU time goes into timing it.
+EXPERIMENTS = ["-DTPT_WIDE_TRIS"]
+
+
+def build_mirror(tmp_path_factory, defines=()):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         pytest.skip("nvcc not available")
     so = str(tmp_path_factory.mktemp("mirror") / "libtraverse_host.so")
-    r = subprocess.run([nvcc, "-std=c++17", "-O2", "-gencode", "arch=compute_100a,code=sm_100a", "--expt-relaxed-constexpr",
+    r = subprocess.run([nvcc, *defines, "-std=c++17", "-O2", "-gencode", "arch=compute_100a,code=sm_100a", "--expt-relaxed-constexpr",
                         "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-I", os.path.join(ROOT, "include"),
                         "-I", os.path.join(PKG, "csrc"), os.path.join(ROOT, "tests", "native", "traverse_host.cu"), "-o", so],
                        capture_output=True, text=True)
@@ -55,6 +59,16 @@ def mirror(tmp_path_factory):
     lib.th_render.restype = C.c_uint64
     lib.th_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     return lib
+
+
+@pytest.fixture(scope="module")
+def mirror(tmp_path_factory):
+    return build_mirror(tmp_path_factory)
+
+
+@pytest.fixture(scope="module", params=EXPERIMENTS)
+def experiment(request, tmp_path_factory):
+    return build_mirror(tmp_path_factory, request.param.split())
 
 
 class Mirror:
@@ -145,8 +159,8 @@ def bits32(a):
     return np.ascontiguousarray(a, np.float32).view(np.uint32)
 
 
-@pytest.mark.parametrize("scene", SCENES)
-def test_every_walk_returns_the_reference_hit(mirror, scene):
+def check_every_walk(lib, scene):
+    mirror = lib
     m = Mirror(mirror, scene)
     g = golden("rays_%s.npz" % scene)
     small = scene != "bunny"
@@ -164,6 +178,16 @@ def test_every_walk_returns_the_reference_hit(mirror, scene):
         sh = m.shadow(g["shadow_from"], g["shadow_to"], g["shadow_cull"], variant)
         assert (sh == g["shadow"]).all(), "%s shadow variant %d: %d differ" % (scene, variant, (sh != g["shadow"]).sum())
     m.close()
+
+
+@pytest.mark.parametrize("scene", SCENES)
+def test_every_walk_returns_the_reference_hit(mirror, scene):
+    check_every_walk(mirror, scene)
+
+
+@pytest.mark.parametrize("scene", SCENES)
+def test_experiments_keep_the_exact_tier(experiment, scene):
+    check_every_walk(experiment, scene)
 
 
 @pytest.mark.parametrize("scene", ["standard", "refractive", "bunny"])
