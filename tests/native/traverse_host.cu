@@ -225,11 +225,13 @@ void th_subpaths(const HostScene* s, const int32_t* pixels, const uint32_t* seed
 // FillBufferThread's loop body (Renderer.cpp:40-53) for every pixel, as k_render_mega runs it: radiance[w*h*3] is the
 // per-pixel sum, splat[w*h*3] the t = 1 strategies' image (both already divided by spp, Renderer.cpp:49-60).
 // mode: TPT_MODE_*; seeds are pixel + 1.  Returns the reference-style ray count.
-unsigned long long th_render(const HostScene* s, int mode, int spp, float* radiance, float* splat) {
-    Ctx c = MakeCtx(s->view, true);
+}  // extern "C"
+template <bool COUNT>
+static unsigned long long RenderAll(const HostScene* s, int mode, int spp, float* radiance, float* splat, unsigned long long* counts) {
+    Ctx c = MakeCtx(s->view, !COUNT);       // counting: the reference's literal walk (unpruned), SURVEY 8(d)
     const SceneView& sc = c.sc;
     const int npix = sc.width * sc.height;
-    unsigned long long ref_rays = 0;
+    unsigned long long ref_rays = 0, tot[4] = {0, 0, 0, 0};
     for (int i = 0; i < npix * 3; ++i) radiance[i] = splat[i] = 0.0f;
     for (int pixel = 0; pixel < npix; ++pixel) {
         uint32_t rng = (uint32_t)pixel + 1u;
@@ -241,34 +243,49 @@ unsigned long long th_render(const HostScene* s, int mode, int spp, float* radia
             if (mode == TPT_MODE_BDPT) {
                 PVert cam[MAX_BDPT_PATH_LENGTH], light[MAX_BDPT_PATH_LENGTH];
                 DHit h;
-                trace_scene<false>(c, primary, 0, &h);
+                trace_scene<COUNT>(c, primary, 0, &h);
                 camera_path_head(sc, h, cam);
-                const int nc = fill_path<false>(c, rng, cam);
+                const int nc = fill_path<COUNT>(c, rng, cam);
                 const LightStart ls = light_path_head(sc, rng, sc.emissive[0], light);
-                trace_scene<false>(c, make_ray(light[0].x, ls.w_i), 0, &h);
+                trace_scene<COUNT>(c, make_ray(light[0].x, ls.w_i), 0, &h);
                 int nl = 2;
-                if (light_path_first_hit(ls, h, light)) nl = fill_path<false>(c, rng, light);
+                if (light_path_first_hit(ls, h, light)) nl = fill_path<COUNT>(c, rng, light);
                 ref_rays += nc + nl;
                 const HostPath<PVert> camA{cam}, lightA{light};
                 L = mk3(0.0f);
                 for (int sv = 1; sv <= nc; ++sv)
                     for (int t = 0; t <= nl; ++t) {
                         if (sv + t < 2) continue;
-                        const f3 w = path_weight<false>(c, camA, sv, lightA, t);
+                        const f3 w = path_weight<COUNT>(c, camA, sv, lightA, t);
                         if (sv > 1) L += w;
                         else splat_to_image(sc, light[t - 1].x, w, splat);
                     }
             } else {
                 int bounces;
-                L = path_trace<false>(c, rng, primary, mode == TPT_MODE_PT_FULL, &bounces);
+                L = path_trace<COUNT>(c, rng, primary, mode == TPT_MODE_PT_FULL, &bounces);
                 ref_rays += bounces;
             }
             acc += inv_spp * L;
         }
         St3(radiance, pixel, acc);
+        tot[0] += c.scene_rays; tot[1] += c.probe_rays; tot[2] += c.cnt.node_visits; tot[3] += c.cnt.prim_tests;      // 32-bit per-thread counters
+        c.scene_rays = c.probe_rays = c.cnt.node_visits = c.cnt.prim_tests = 0u;
     }
     for (int i = 0; i < npix * 3; ++i) splat[i] = splat[i] * 1.0f / spp;      // Renderer.cpp:58-60
+    if (counts) for (int k = 0; k < 4; ++k) counts[k] = tot[k];
     return ref_rays;
+}
+
+extern "C" {
+
+unsigned long long th_render(const HostScene* s, int mode, int spp, float* radiance, float* splat) {
+    return RenderAll<false>(s, mode, spp, radiance, splat, nullptr);
+}
+// The same render with the reference's unpruned walk and its visit counters: counts = {Scene::Intersect calls
+// (extension + shadow), light-object probes, nodes visited, primitives tested} — the per-ray figures SURVEY 8(d)
+// builds the algorithmic bytes per ray from (tools/algorithmic_bytes.py).
+unsigned long long th_render_counted(const HostScene* s, int mode, int spp, float* radiance, float* splat, unsigned long long* counts) {
+    return RenderAll<true>(s, mode, spp, radiance, splat, counts);
 }
 
 }  // extern "C"

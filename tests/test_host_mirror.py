@@ -58,6 +58,8 @@ def build_mirror(tmp_path_factory, defines=()):
     lib.th_subpaths.argtypes = [C.c_void_p] * 3 + [C.c_size_t] + [C.c_void_p] * 5
     lib.th_render.restype = C.c_uint64
     lib.th_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.th_render_counted.restype = C.c_uint64
+    lib.th_render_counted.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     return lib
 
 
@@ -297,4 +299,26 @@ def test_small_renders_against_reference(mirror, scene):
     k_render_mega runs it (tpt.cu), around the integrators of csrc/integrators.cuh."""
     m = Mirror(mirror, scene, 64, 64)
     check_small_renders(m, scene)
+    m.close()
+
+
+def test_algorithmic_bytes_per_ray_of_the_bench_workload(mirror):
+    """bench.py credits a traced ray of Cornell-Standard BDPT with SURVEY 8(d)'s 27.5 nodes * 32 B + 3.56 primitives *
+    64 B + 48 B = 1155.84 B.  The reference-semantics counters of the kernels' integrators give the same picture:
+    3.5 primitive tests and 25.8 grafted nodes per ray (the reference's 27.5 count a mesh's box twice: as the
+    top-level leaf and as the mesh root, one node here), about 17 traced rays per sample (tools/algorithmic_bytes.py)."""
+    import tpt_b200 as T
+    m = Mirror(mirror, "standard", 96, 96)
+    rad = np.zeros((96, 96, 3), np.float32)
+    splat = np.zeros_like(rad)
+    counts = np.zeros(4, np.uint64)
+    mirror.th_render_counted(m.h, T.MODES["bdpt"], 4, rad.ctypes.data, splat.ctypes.data, counts.ctypes.data)
+    scene_rays, probes, nodes, prims = [int(c) for c in counts]
+    assert probes == 0 and 16.0 < scene_rays / (96 * 96 * 4) < 18.5
+    assert 3.4 < prims / scene_rays < 3.7
+    assert 25.0 < nodes / scene_rays < 27.5
+    assert abs((nodes / scene_rays * 32 + prims / scene_rays * 64 + 48) / 1155.84 - 1) < 0.08
+    # the counted (unpruned, literal) walk renders the same image as the pruned one
+    img, _ = m.render("bdpt", 4)
+    assert np.allclose(rad + splat, img, rtol=1e-5, atol=1e-6)
     m.close()
