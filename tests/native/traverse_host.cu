@@ -109,6 +109,36 @@ void th_intersect(const HostScene* s, const float* org, const float* dir, const 
     if (counts) { counts[0] = nodes; counts[1] = prims; }
 }
 
+// The resumable walk (walk_resume): the same rays, each walked `budget` node visits at a time.
+void th_intersect_budgeted(const HostScene* s, const float* org, const float* dir, const uint8_t* cull, size_t n, int prune,
+                           int budget, int32_t* prim, double* t, float* coords, float* normal, unsigned* rounds) {
+    const SceneView& sc = s->view;
+    for (size_t i = 0; i < n; ++i) {
+        const DRay r = make_ray(Ld3(org, i), Ld3(dir, i));
+        WalkCursor c = walk_begin(0);
+        unsigned k = 1;
+        while (!walk_resume(sc, r, cull[i], sc.n_nodes, prune != 0, budget, c)) ++k;
+        DHit h;
+        finish_hit(sc, r, c.best, c.best_t, &h);
+        prim[i] = h.prim;
+        t[i] = h.prim >= 0 ? h.t : 0.0;
+        St3(coords, i, h.coords);
+        St3(normal, i, h.normal);
+        if (rounds) rounds[i] = k;
+    }
+}
+void th_shadow_budgeted(const HostScene* s, const float* from, const float* to, const uint8_t* cull, size_t n, int budget,
+                        uint8_t* out) {
+    const SceneView& sc = s->view;
+    for (size_t i = 0; i < n; ++i) {
+        const ShadowQuery q = shadow_begin(Ld3(from, i), Ld3(to, i));
+        int cursor = 0;
+        bool found = false;
+        while (!shadow_resume(sc, q, cull[i], budget, cursor, &found)) {}
+        out[i] = found ? 1 : 0;
+    }
+}
+
 // variant 0: shadow_check in the reference's closest-hit form; 1: as an any-hit query; 2: shadow_check_deferred
 void th_shadow(const HostScene* s, const float* from, const float* to, const uint8_t* cull, size_t n, int variant,
                uint8_t* out) {

@@ -58,6 +58,8 @@ def build_mirror(tmp_path_factory, defines=()):
     lib.th_subpaths.argtypes = [C.c_void_p] * 3 + [C.c_size_t] + [C.c_void_p] * 5
     lib.th_render.restype = C.c_uint64
     lib.th_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.th_intersect_budgeted.argtypes = [C.c_void_p] * 4 + [C.c_size_t, C.c_int, C.c_int] + [C.c_void_p] * 5
+    lib.th_shadow_budgeted.argtypes = [C.c_void_p] * 4 + [C.c_size_t, C.c_int, C.c_void_p]
     lib.th_render_counted.restype = C.c_uint64
     lib.th_render_counted.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     return lib
@@ -211,6 +213,38 @@ def test_pruning_only_removes_work_and_counts_follow_the_reference(mirror, scene
     assert int(full[1]) == st["prim_tests"]
     assert int(full[0]) == st["node_visits"] - mesh_entries
     assert pruned[0] <= full[0] and pruned[1] <= full[1] and pruned[0] < full[0]
+    m.close()
+
+
+@pytest.mark.parametrize("scene", ["bunny", "refractive"])
+@pytest.mark.parametrize("budget", [1, 7, 32])
+def test_resumable_walk_is_the_walk(mirror, scene, budget):
+    """walk_resume / shadow_resume (traverse.cuh): a walk cut into pieces of `budget` node visits performs the same tests
+    in the same order, so every batch must come back as the reference has it, with and without pruning; a long
+    walk really is cut (the bunny's rays need up to ~280 visits)."""
+    m = Mirror(mirror, scene)
+    g = golden("rays_%s.npz" % scene)
+    most = 0
+    for tag in ("P", "S", "R", "A"):
+        org, dirs = np.ascontiguousarray(g[tag + "_org"]), np.ascontiguousarray(g[tag + "_dir"])
+        cull = np.ascontiguousarray(g[tag + "_cull"])
+        n = len(cull)
+        for prune in (0, 1):
+            prim, t = np.empty(n, np.int32), np.empty(n, np.float64)
+            coords, normal = np.empty((n, 3), np.float32), np.empty((n, 3), np.float32)
+            rounds = np.zeros(n, np.uint32)
+            mirror.th_intersect_budgeted(m.h, org.ctypes.data, dirs.ctypes.data, cull.ctypes.data, n, prune, budget,
+                                         prim.ctypes.data, t.ctypes.data, coords.ctypes.data, normal.ctypes.data, rounds.ctypes.data)
+            assert (prim == g[tag + "_prim"]).all(), (scene, tag, prune)
+            assert (t.view(np.uint64) == g[tag + "_t"].view(np.uint64)).all()
+            assert (bits32(coords) == bits32(g[tag + "_coords"])).all() and (bits32(normal) == bits32(g[tag + "_normal"])).all()
+            most = max(most, int(rounds.max()))
+    assert most > (3 if scene == "bunny" else 1)          # walks really were cut
+    src, dst = np.ascontiguousarray(g["shadow_from"]), np.ascontiguousarray(g["shadow_to"])
+    cull = np.ascontiguousarray(g["shadow_cull"])
+    out = np.empty(len(cull), np.uint8)
+    mirror.th_shadow_budgeted(m.h, src.ctypes.data, dst.ctypes.data, cull.ctypes.data, len(cull), budget, out.ctypes.data)
+    assert (out == g["shadow"]).all()
     m.close()
 
 

@@ -393,6 +393,79 @@ TPT_DEV bool shadow_check_deferred(const SceneView& sc, f3 from, f3 to, int cull
     return found;
 }
 
+// ---- resumable walk (large scenes) ----------------------------------------------------------------
+// The walk above keeps no stack: its whole state is the cursor i and the best hit so far.  So it can stop after any
+// number of steps and go on later — in another loop iteration, lane or launch — performing the very same sequence
+// of tests: the result cannot differ.  That is what lets a kernel bound the steps a lane spends on one ray: in a
+// scene with one large mesh a tenth of the rays enter the mesh and walk 100-280 nodes while the others are done
+// after 20, and a warp takes as long as its slowest lane (3.4-4.3x the mean on the Cornell + bunny batches; with a
+// budget of 32 steps and the unfinished rays re-dealt densely, 1.6-1.8x — DESIGN.md section 10).
+struct WalkCursor {
+    int i;            // next node to visit
+    int best;         // primitive of the best hit so far, -1: none
+    double best_t;
+};
+TPT_DEV WalkCursor walk_begin(int first) { WalkCursor c; c.i = first; c.best = -1; c.best_t = 0.0; return c; }
+// Advances by at most `budget` node visits; true when the walk over [.., end) is complete.  Pruning as in
+// closest_hit_range (same margin); finish with finish_hit(sc, r, c.best, c.best_t, &hit).
+TPT_DEV bool walk_resume(const SceneView& sc, const DRay& r, int cull, int end, bool prune, int budget, WalkCursor& c) {
+    int i = c.i, best = c.best;
+    double best_t = c.best_t;
+    float prune_t = (prune && best >= 0) ? (float)best_t * 1.0001f + 1e-3f : FLT_MAX;
+    const bool plain = ray_is_plain(r);
+    int steps = 0;
+    while (i < end && steps < budget) {
+        const float4 n0 = sc.nodes[2 * i], n1 = sc.nodes[2 * i + 1];
+        ++steps;
+        float nmin;
+        const bool in = (plain ? slab_test_plain(n0, n1, r, &nmin) : slab_test(n0, n1, r, &nmin)) && !(nmin > prune_t);
+        const int prim = __float_as_int(n0.w);
+        i = in ? i + 1 : __float_as_int(n1.w);
+        if (in && prim >= 0) {
+            settle_candidate(sc, r, cull, prim, best, best_t);
+            if (prune && best >= 0) prune_t = (float)best_t * 1.0001f + 1e-3f;
+        }
+    }
+    c.i = i; c.best = best; c.best_t = best_t;
+    return i >= end;
+}
+// Scene::ShadowCheck as a resumable any-hit walk: the cursor is the node index alone.  Returns true when the query is
+// decided (*found says how); false: out of budget, call again with the same cursor.
+struct ShadowQuery {
+    DRay r;
+    f3 from;
+    double limit;
+    float reach;
+};
+TPT_DEV ShadowQuery shadow_begin(f3 from, f3 to) {
+    ShadowQuery q;
+    const f3 d0 = x_sub(from, to);
+    const double lightDistanceSqr = dotd(d0, d0);
+    q.limit = lightDistanceSqr - 1.0;
+    q.r = make_ray(from, x_normalize(x_sub(to, from)));
+    q.reach = __fsqrt_rn((float)lightDistanceSqr) * 1.0001f + 1e-3f;
+    q.from = from;
+    return q;
+}
+TPT_DEV bool shadow_resume(const SceneView& sc, const ShadowQuery& q, int cull, int budget, int& cursor, bool* found) {
+    int i = cursor, steps = 0;
+    const int end = sc.n_nodes;
+    const bool plain = ray_is_plain(q.r);
+    bool hit = false;
+    while (i < end && !hit && steps < budget) {
+        const float4 n0 = sc.nodes[2 * i], n1 = sc.nodes[2 * i + 1];
+        ++steps;
+        float nmin;
+        const bool in = (plain ? slab_test_plain(n0, n1, q.r, &nmin) : slab_test(n0, n1, q.r, &nmin)) && !(nmin > q.reach);
+        const int prim = __float_as_int(n0.w);
+        i = in ? i + 1 : __float_as_int(n1.w);
+        if (in && prim >= 0) hit = shadow_candidate(sc, q.r, cull, prim, q.from, q.limit);
+    }
+    cursor = i;
+    *found = hit;
+    return hit || i >= end;
+}
+
 // ---- warp-cooperative primitive tests -------------------------------------------------------------
 // After the flat leaf pass every lane holds a mask of candidates: 3.6 on average for Cornell, up to
 // ~10, so testing "the k-th candidate of every lane" keeps a third of the lanes busy.  Here the
