@@ -1,11 +1,19 @@
 #!/bin/bash
-# First GPU call of a new round, in one trip (about 4 minutes of box time):
+# First GPU call of a new round, in one trip (about 6 minutes of box time):
 #   1. the round's profile artefacts of the tree as it is (bench line, reference arm, ncu launch list, DRAM traffic)
-#   2. GPU tests + timing of the shipped build, then of every compile-time experiment that the host mirror has already
-#      shown to be exact (tests/test_host_mirror.py EXPERIMENTS), each with the GPU tests on top
-#   gpurun --timeout 900 -- 'ROUND=r02a bash tools/gpu_next_round.sh'
+#   2. GPU tests + BDPT timing of the shipped build, then of -DTPT_WIDE_TRIS (exactness already shown on the host
+#      mirror, tests/test_host_mirror.py EXPERIMENTS) with the GPU tests on top
+#   3. Cornell + bunny timing of the shipped build against -DTPT_BUDGET_WALK (16 / 32 / 48 node visits per turn), then
+#      the GPU tests on the last of them (bunny renders, BASELINE config 4)
+#   gpurun --timeout 1200 -- 'ROUND=r02a bash tools/gpu_next_round.sh'
 R=${ROUND:-r02a}
 mkdir -p gpurun_out
 ROUND=$R bash tools/gpu_profiles.sh
-VARIANTS=${VARIANTS:--DTPT_WIDE_TRIS} TESTV=1 bash tools/gpu_ab.sh > gpurun_out/${R}_ab.log 2>&1
-tail -40 gpurun_out/${R}_ab.log | cut -c1-250
+VARIANTS=-DTPT_WIDE_TRIS TESTV=1 bash tools/gpu_ab.sh > gpurun_out/${R}_ab_wide_tris.log 2>&1
+tail -30 gpurun_out/${R}_ab_wide_tris.log | cut -c1-250
+touch toypathtracer-games101-assignment7_b200/csrc/*.cu; make -C toypathtracer-games101-assignment7_b200 -j8 libtpt.so 2>&1 | grep -E "error"
+VARIANTS="-DTPT_BUDGET_WALK=16;-DTPT_BUDGET_WALK=32;-DTPT_BUDGET_WALK=48" bash tools/gpu_ab_bunny.sh > gpurun_out/${R}_ab_budget_walk.log 2>&1
+timeout 600 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider >> gpurun_out/${R}_ab_budget_walk.log 2>&1
+tail -40 gpurun_out/${R}_ab_budget_walk.log | cut -c1-250
+# leave the tree's library as shipped
+touch toypathtracer-games101-assignment7_b200/csrc/*.cu; make -C toypathtracer-games101-assignment7_b200 -j8 libtpt.so 2>&1 | grep -E "error"
