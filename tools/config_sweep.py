@@ -34,6 +34,19 @@ CONFIGS = [
 CPU_SPP = {"pt_shipped": 8, "pt_full": 4, "bdpt": 2}
 
 
+def load_algorithmic_bytes():
+    """profiles/algorithmic_bytes.json (tools/algorithmic_bytes.py): reference-semantics visit counts per configuration."""
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "algorithmic_bytes.json")
+    try:
+        with open(path) as f:
+            return {row["config"]: row["algorithmic_bytes_per_ray"] for row in json.load(f)["rows"]}
+    except (OSError, ValueError, KeyError):
+        return {}
+
+
+ALGO_BYTES = load_algorithmic_bytes()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
@@ -104,6 +117,9 @@ def main():
                  "ms": ms, "msamples_per_s": samples / ms / 1e3, "mrays_per_s": traced / ms / 1e3,
                  "samples": samples, "traced_rays": traced, "reference_style_rays": ref_rays,
                  "finite": bool(torch.isfinite(out).all().item()), "image_mean_rgb": mean}
+            if cid in ALGO_BYTES:       # algorithmic bytes per traced ray x traced rays / frame time
+                r["algorithmic_bytes_per_ray"] = ALGO_BYTES[cid]
+                r["algorithmic_gb_per_s"] = traced * ALGO_BYTES[cid] / (ms * 1e-3) / 1e9
             if ref_mean is not None:
                 r["reference_mean_rgb"] = ref_mean
                 r["mean_rel_err"] = [abs(a - b) / b for a, b in zip(mean, ref_mean)]
