@@ -10,8 +10,8 @@
 // Material::*, subpath generation, PathWeight, PathTrace, the BDPT strategy loop with its splats) with the loop
 // body of the one-thread-per-pixel validation kernel (k_render_mega, tpt.cu) restated around them.
 //
-// Not mirrored: the warp-cooperative pooling of the primitive tests (coop_test: shuffles); it runs the same
-// settle_candidate on the same candidates in the same order as closest_hit_deferred, which is mirrored.
+// The warp-cooperative pooling of the primitive tests (coop_test / closest_hit_warp: shuffles, results handed over
+// through shared memory) runs as 32 coroutines in lockstep at the collectives (run_warp below).
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -31,10 +31,121 @@ __host__ __device__ inline int hm_f2i(float f) { int i; memcpy(&i, &f, 4); retur
 __host__ __device__ inline unsigned hm_f2u(float f) { unsigned i; memcpy(&i, &f, 4); return i; }
 __host__ __device__ inline int hm_ffs(unsigned v) { int n = 0; if (!v) return 0; while (!(v & 1u)) { v >>= 1; ++n; } return n + 1; }
 __host__ __device__ inline int hm_popc(unsigned v) { int n = 0; while (v) { v &= v - 1u; ++n; } return n; }
-template <class T> __host__ __device__ inline T hm_shfl(unsigned, T v, int) { return v; }      // never executed here
-__host__ __device__ inline void hm_syncwarp() {}
+// ---- one warp on the CPU ---------------------------------------------------------------------------
+// The warp-cooperative code (coop_test / closest_hit_warp: shuffles, __syncwarp, results handed over through shared
+// memory) runs here as 32 coroutines (ucontext): a lane that reaches a warp collective parks; when all 32 are parked at
+// it the exchange is performed and they go on.  Outside run_warp() there is one "lane 0" and the collectives are
+// identities.  Lockstep is only enforced at the collectives, which is all the code relies on (full masks).
+#include <ucontext.h>
+#include <cstdio>
+#include <cstdlib>
+#include <functional>
+struct WarpEmu {
+    enum { LANES = 32, STACK = 256 * 1024 };
+    ucontext_t sched, ctx[LANES];
+    char* stacks = nullptr;
+    int lane = 0;                   // the coroutine that is running
+    bool active = false;
+    bool finished[LANES];
+    int op[LANES];                  // 0: none, 1: shfl (idx), 2: shfl_up, 3: syncwarp
+    unsigned long long val[LANES];
+    int arg[LANES];
+    std::function<void(int)> body;
+};
+static WarpEmu g_warp;
+static void warp_entry() {
+    const int l = g_warp.lane;
+    g_warp.body(l);
+    g_warp.finished[l] = true;
+    swapcontext(&g_warp.ctx[l], &g_warp.sched);
+}
+// Runs body(lane) for lanes 0..31 as one warp.
+static void run_warp(const std::function<void(int)>& body) {
+    WarpEmu& w = g_warp;
+    if (!w.stacks) w.stacks = static_cast<char*>(malloc((size_t)WarpEmu::LANES * WarpEmu::STACK));
+    w.body = body;
+    w.active = true;
+    for (int l = 0; l < WarpEmu::LANES; ++l) {
+        w.finished[l] = false; w.op[l] = 0;
+        getcontext(&w.ctx[l]);
+        w.ctx[l].uc_stack.ss_sp = w.stacks + (size_t)l * WarpEmu::STACK;
+        w.ctx[l].uc_stack.ss_size = WarpEmu::STACK;
+        w.ctx[l].uc_link = &w.sched;
+        makecontext(&w.ctx[l], warp_entry, 0);
+    }
+    for (;;) {
+        int parked = 0, done = 0, kind = 0;
+        for (int l = 0; l < WarpEmu::LANES; ++l) {
+            if (w.finished[l]) { ++done; continue; }
+            w.lane = l;
+            w.op[l] = 0;
+            swapcontext(&w.sched, &w.ctx[l]);          // until its next collective or its end
+            if (w.finished[l]) { ++done; continue; }
+            ++parked;
+            if (kind && kind != w.op[l]) { fprintf(stderr, "warp emulation: lanes at different collectives\n"); abort(); }
+            kind = w.op[l];
+        }
+        if (done == WarpEmu::LANES) break;
+        if (done) { fprintf(stderr, "warp emulation: %d lanes finished while %d wait at a collective\n", done, parked); abort(); }
+        unsigned long long out[WarpEmu::LANES];
+        for (int l = 0; l < WarpEmu::LANES; ++l) {
+            if (kind == 1) out[l] = w.val[w.arg[l] & 31];
+            else if (kind == 2) out[l] = l >= w.arg[l] ? w.val[l - w.arg[l]] : w.val[l];
+            else out[l] = 0;
+        }
+        for (int l = 0; l < WarpEmu::LANES; ++l) w.val[l] = out[l];
+    }
+    w.active = false;
+    w.lane = 0;
+}
+static unsigned long long warp_collective(int kind, unsigned long long v, int arg) {
+    WarpEmu& w = g_warp;
+    if (!w.active) return v;
+    const int l = w.lane;
+    w.op[l] = kind; w.val[l] = v; w.arg[l] = arg;
+    swapcontext(&w.ctx[l], &w.sched);
+    return w.val[l];
+}
+template <class T> __host__ __device__ inline T hm_shfl(unsigned, T v, int src) {
+    static_assert(sizeof(T) <= 8, "shuffle payload");
+#ifndef __CUDA_ARCH__       /* nvcc's device pass only has to compile this file */
+    unsigned long long raw = 0;
+    memcpy(&raw, &v, sizeof(T));
+    raw = warp_collective(1, raw, src);
+    memcpy(&v, &raw, sizeof(T));
+#endif
+    return v;
+}
+template <class T> __host__ __device__ inline T hm_shfl_up(unsigned, T v, unsigned delta) {
+#ifndef __CUDA_ARCH__
+    unsigned long long raw = 0;
+    memcpy(&raw, &v, sizeof(T));
+    raw = warp_collective(2, raw, (int)delta);
+    memcpy(&v, &raw, sizeof(T));
+#endif
+    return v;
+}
+__host__ __device__ inline void hm_syncwarp() {
+#ifndef __CUDA_ARCH__
+    warp_collective(3, 0, 0);
+#endif
+}
 struct HmDim { unsigned x, y, z; };
-static const HmDim hm_thread = {0, 0, 0}, hm_block = {1, 1, 1};
+__host__ __device__ inline HmDim hm_thread_now() {
+#ifndef __CUDA_ARCH__
+    return HmDim{(unsigned)g_warp.lane, 0u, 0u};
+#else
+    return HmDim{0u, 0u, 0u};
+#endif
+}
+__host__ __device__ inline HmDim hm_block_now() {
+#ifndef __CUDA_ARCH__
+    return HmDim{g_warp.active ? 32u : 1u, 1u, 1u};
+#else
+    return HmDim{1u, 1u, 1u};
+#endif
+}
+__host__ __device__ inline float hm_atomic_add(float* p, float v) { const float old = *p; *p = old + v; return old; }   // one host thread
 #define __fadd_rn hm_add
 #define __fsub_rn hm_sub
 #define __fmul_rn hm_mul
@@ -46,11 +157,10 @@ static const HmDim hm_thread = {0, 0, 0}, hm_block = {1, 1, 1};
 #define __ffs hm_ffs
 #define __popc hm_popc
 #define __shfl_sync hm_shfl
-#define __shfl_up_sync hm_shfl
+#define __shfl_up_sync hm_shfl_up
 #define __syncwarp hm_syncwarp
-#define threadIdx hm_thread
-#define blockDim hm_block
-__host__ __device__ inline float hm_atomic_add(float* p, float v) { const float old = *p; *p = old + v; return old; }   // one host thread
+#define threadIdx hm_thread_now()
+#define blockDim hm_block_now()
 #define atomicAdd hm_atomic_add
 
 #include "integrators.cuh"
@@ -107,6 +217,30 @@ void th_intersect(const HostScene* s, const float* org, const float* dir, const 
         St3(normal, i, h.normal);
     }
     if (counts) { counts[0] = nodes; counts[1] = prims; }
+}
+
+// closest_hit_warp as k_extend / k_pt_extend / k_intersect call it: 32 rays at a time as one emulated warp, the
+// cooperative area and the candidate columns in "shared memory" of one warp.  n need not be a multiple of 32 (the
+// last warp has lanes without a ray).
+void th_intersect_warp(const HostScene* s, const float* org, const float* dir, const uint8_t* cull, size_t n,
+                       int32_t* prim, double* t, float* coords, float* normal) {
+    const SceneView& sc = s->view;
+    static unsigned char coop[TPT_COOP_WARP_BYTES + 16];
+    static int cand[32 * TPT_CAND_MAX];
+    for (size_t base = 0; base < n; base += 32) {
+        run_warp([&](int lane) {
+            const size_t i = base + lane;
+            const bool live = i < n;
+            const DRay r = live ? make_ray(Ld3(org, i), Ld3(dir, i)) : make_ray(mk3(0.0f), mk3(0.0f, 0.0f, 1.0f));
+            DHit h;
+            closest_hit_warp(sc, r, live ? cull[i] : 0, live, coop, cand + lane, 32, &h);
+            if (!live) return;
+            prim[i] = h.prim;
+            t[i] = h.prim >= 0 ? h.t : 0.0;
+            St3(coords, i, h.coords);
+            St3(normal, i, h.normal);
+        });
+    }
 }
 
 // The resumable walk (walk_resume): the same rays, each walked `budget` node visits at a time.

@@ -39,7 +39,7 @@ def build_mirror(tmp_path_factory, defines=()):
         pytest.skip("nvcc not available")
     so = str(tmp_path_factory.mktemp("mirror") / "libtraverse_host.so")
     r = subprocess.run([nvcc, *defines, "-std=c++17", "-O2", "-gencode", "arch=compute_100a,code=sm_100a", "--expt-relaxed-constexpr",
-                        "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-I", os.path.join(ROOT, "include"),
+                        "-Xcompiler", "-fPIC,-ffp-contract=off", "-diag-suppress", "177", "-shared", "-I", os.path.join(ROOT, "include"),
                         "-I", os.path.join(PKG, "csrc"), os.path.join(ROOT, "tests", "native", "traverse_host.cu"), "-o", so],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
@@ -58,6 +58,7 @@ def build_mirror(tmp_path_factory, defines=()):
     lib.th_subpaths.argtypes = [C.c_void_p] * 3 + [C.c_size_t] + [C.c_void_p] * 5
     lib.th_render.restype = C.c_uint64
     lib.th_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.th_intersect_warp.argtypes = [C.c_void_p] * 4 + [C.c_size_t] + [C.c_void_p] * 4
     lib.th_intersect_budgeted.argtypes = [C.c_void_p] * 4 + [C.c_size_t, C.c_int, C.c_int] + [C.c_void_p] * 5
     lib.th_shadow_budgeted.argtypes = [C.c_void_p] * 4 + [C.c_size_t, C.c_int, C.c_void_p]
     lib.th_render_counted.restype = C.c_uint64
@@ -98,6 +99,16 @@ class Mirror:
         self.lib.th_intersect(self.h, org.ctypes.data, dirs.ctypes.data, cull.ctypes.data, n, variant, prim.ctypes.data,
                               t.ctypes.data, coords.ctypes.data, normal.ctypes.data, counts.ctypes.data)
         return prim, t, coords, normal, counts
+
+    def intersect_warp(self, org, dirs, cull):
+        org, dirs = np.ascontiguousarray(org, np.float32), np.ascontiguousarray(dirs, np.float32)
+        cull = np.ascontiguousarray(cull, np.uint8)
+        n = len(cull)
+        prim, t = np.empty(n, np.int32), np.empty(n, np.float64)
+        coords, normal = np.empty((n, 3), np.float32), np.empty((n, 3), np.float32)
+        self.lib.th_intersect_warp(self.h, org.ctypes.data, dirs.ctypes.data, cull.ctypes.data, n, prim.ctypes.data,
+                                   t.ctypes.data, coords.ctypes.data, normal.ctypes.data)
+        return prim, t, coords, normal
 
     def shadow(self, src, dst, cull, variant):
         src, dst = np.ascontiguousarray(src, np.float32), np.ascontiguousarray(dst, np.float32)
@@ -245,6 +256,45 @@ def test_resumable_walk_is_the_walk(mirror, scene, budget):
     out = np.empty(len(cull), np.uint8)
     mirror.th_shadow_budgeted(m.h, src.ctypes.data, dst.ctypes.data, cull.ctypes.data, len(cull), budget, out.ctypes.data)
     assert (out == g["shadow"]).all()
+    m.close()
+
+
+@pytest.mark.parametrize("scene", SCENES)
+def test_warp_cooperative_closest_hit(mirror, scene):
+    """closest_hit_warp (what k_extend / k_pt_extend / k_intersect call): the candidates of a warp's 32 rays pooled in
+    shared memory, dealt out 32 at a time, tested by whichever lane gets them with the owner's ray fetched by shuffles,
+    and read back by the owner in visit order.  Run as 32 coroutines that meet at every warp collective."""
+    m = Mirror(mirror, scene)
+    g = golden("rays_%s.npz" % scene)
+    for tag in ("P", "S", "R", "A"):
+        prim, t, coords, normal = m.intersect_warp(g[tag + "_org"], g[tag + "_dir"], g[tag + "_cull"])
+        assert (prim == g[tag + "_prim"]).all(), (scene, tag, int((prim != g[tag + "_prim"]).sum()))
+        assert (t.view(np.uint64) == g[tag + "_t"].view(np.uint64)).all()
+        assert (bits32(coords) == bits32(g[tag + "_coords"])).all() and (bits32(normal) == bits32(g[tag + "_normal"])).all()
+    m.close()
+
+
+def test_warp_pool_overflow_falls_back_to_the_lane_loop(mirror):
+    """More than TPT_COOP_CAP (256) candidates in one warp: coop_test declines and every lane tests its own candidates.
+    Rays that cross the whole box from outside reach 9+ leaves each; 32 of them overflow the pool."""
+    from conftest import oracle_for
+    m = Mirror(mirror, "standard")
+    orc, _ = oracle_for("standard")
+    rs = np.random.RandomState(11)
+    n = 4000
+    org = (rs.rand(n, 3) * 40 - 60).astype(np.float32)                       # outside, near the (0, 0, 0) corner
+    tgt = (np.array([556.0, 548.8, 559.2]) * (0.55 + 0.45 * rs.rand(n, 3))).astype(np.float32)
+    d = tgt - org
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    cull = np.full(n, 2, np.uint8)
+    per_ray = np.array([int(m.intersect(org[i:i + 1], d[i:i + 1], cull[i:i + 1], 0)[4][1]) for i in range(n)])
+    pick = np.argsort(-per_ray)[:64]
+    assert per_ray[pick].min() >= 9 and per_ray[pick[:32]].sum() > 256, per_ray[pick][:40]
+    o, dd, c = org[pick], d[pick], cull[pick]
+    prim, t, coords, normal = m.intersect_warp(o, dd, c)
+    op, ot, oc, on = orc.intersect(o, dd, c)
+    assert (prim == op).all() and (t.view(np.uint64) == ot.view(np.uint64)).all()
+    assert (bits32(coords) == bits32(oc)).all() and (bits32(normal) == bits32(on)).all()
     m.close()
 
 
