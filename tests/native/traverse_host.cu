@@ -31,121 +31,152 @@ __host__ __device__ inline int hm_f2i(float f) { int i; memcpy(&i, &f, 4); retur
 __host__ __device__ inline unsigned hm_f2u(float f) { unsigned i; memcpy(&i, &f, 4); return i; }
 __host__ __device__ inline int hm_ffs(unsigned v) { int n = 0; if (!v) return 0; while (!(v & 1u)) { v >>= 1; ++n; } return n + 1; }
 __host__ __device__ inline int hm_popc(unsigned v) { int n = 0; while (v) { v &= v - 1u; ++n; } return n; }
-// ---- one warp on the CPU ---------------------------------------------------------------------------
-// The warp-cooperative code (coop_test / closest_hit_warp: shuffles, __syncwarp, results handed over through shared
-// memory) runs here as 32 coroutines (ucontext): a lane that reaches a warp collective parks; when all 32 are parked at
-// it the exchange is performed and they go on.  Outside run_warp() there is one "lane 0" and the collectives are
-// identities.  Lockstep is only enforced at the collectives, which is all the code relies on (full masks).
+// ---- a thread block on the CPU ---------------------------------------------------------------------
+// Warp- and block-cooperative code (coop_test / closest_hit_warp here; the wavefront kernels in wavefront_host.cu:
+// ballots, shuffles, __syncwarp, __syncthreads) runs as coroutines (ucontext), one per thread of the block: a thread
+// that reaches a collective parks; when the 32 lanes of its warp are parked at the same warp collective — or every
+// live thread of the block at __syncthreads — the exchange is performed and they go on.  Lockstep is only enforced at
+// the collectives, which is all the code relies on (full masks, whole warps in every loop).  Outside run_block()
+// there is one "thread 0" and the collectives are identities.  One block at a time, one host thread: atomics are
+// plain read-modify-writes.
 #include <ucontext.h>
 #include <cstdio>
 #include <cstdlib>
 #include <functional>
-struct WarpEmu {
-    enum { LANES = 32, STACK = 256 * 1024 };
-    ucontext_t sched, ctx[LANES];
+struct BlockEmu {
+    enum { MAX_LANES = 256, STACK = 256 * 1024 };
+    enum { OP_NONE = 0, OP_SHFL, OP_SHFL_UP, OP_SYNCWARP, OP_SHFL_DOWN, OP_SHFL_XOR, OP_BALLOT, OP_SYNCTHREADS };
+    ucontext_t sched, ctx[MAX_LANES];
     char* stacks = nullptr;
     int lane = 0;                   // the coroutine that is running
+    int nlanes = 1;
+    unsigned block_idx = 0, grid_dim = 1;
     bool active = false;
-    bool finished[LANES];
-    int op[LANES];                  // 0: none, 1: shfl (idx), 2: shfl_up, 3: syncwarp
-    unsigned long long val[LANES];
-    int arg[LANES];
-    std::function<void(int)> body;
+    bool finished[MAX_LANES], parked[MAX_LANES];
+    int op[MAX_LANES];
+    unsigned long long val[MAX_LANES];
+    int arg[MAX_LANES];
+    std::function<void()> body;
 };
-static WarpEmu g_warp;
-static void warp_entry() {
-    const int l = g_warp.lane;
-    g_warp.body(l);
-    g_warp.finished[l] = true;
-    swapcontext(&g_warp.ctx[l], &g_warp.sched);
+static BlockEmu g_blk;
+static void block_entry() {
+    const int l = g_blk.lane;
+    g_blk.body();
+    g_blk.finished[l] = true;
+    swapcontext(&g_blk.ctx[l], &g_blk.sched);
 }
-// Runs body(lane) for lanes 0..31 as one warp.
-static void run_warp(const std::function<void(int)>& body) {
-    WarpEmu& w = g_warp;
-    if (!w.stacks) w.stacks = static_cast<char*>(malloc((size_t)WarpEmu::LANES * WarpEmu::STACK));
-    w.body = body;
+static void emu_die(const char* what) { fprintf(stderr, "block emulation: %s\n", what); abort(); }
+// Runs body() on `nlanes` threads (a multiple of 32) as block `block_idx` of `grid_dim`.
+static void run_block(int nlanes, unsigned block_idx, unsigned grid_dim, const std::function<void()>& body) {
+    BlockEmu& w = g_blk;
+    if (w.active) emu_die("nested launch");
+    if (nlanes % 32 || nlanes > BlockEmu::MAX_LANES) emu_die("block size");
+    if (!w.stacks) w.stacks = static_cast<char*>(malloc((size_t)BlockEmu::MAX_LANES * BlockEmu::STACK));
+    w.body = body; w.nlanes = nlanes; w.block_idx = block_idx; w.grid_dim = grid_dim;
     w.active = true;
-    for (int l = 0; l < WarpEmu::LANES; ++l) {
-        w.finished[l] = false; w.op[l] = 0;
+    for (int l = 0; l < nlanes; ++l) {
+        w.finished[l] = false; w.parked[l] = false; w.op[l] = BlockEmu::OP_NONE;
         getcontext(&w.ctx[l]);
-        w.ctx[l].uc_stack.ss_sp = w.stacks + (size_t)l * WarpEmu::STACK;
-        w.ctx[l].uc_stack.ss_size = WarpEmu::STACK;
+        w.ctx[l].uc_stack.ss_sp = w.stacks + (size_t)l * BlockEmu::STACK;
+        w.ctx[l].uc_stack.ss_size = BlockEmu::STACK;
         w.ctx[l].uc_link = &w.sched;
-        makecontext(&w.ctx[l], warp_entry, 0);
+        makecontext(&w.ctx[l], block_entry, 0);
     }
     for (;;) {
-        int parked = 0, done = 0, kind = 0;
-        for (int l = 0; l < WarpEmu::LANES; ++l) {
-            if (w.finished[l]) { ++done; continue; }
-            w.lane = l;
-            w.op[l] = 0;
-            swapcontext(&w.sched, &w.ctx[l]);          // until its next collective or its end
-            if (w.finished[l]) { ++done; continue; }
-            ++parked;
-            if (kind && kind != w.op[l]) { fprintf(stderr, "warp emulation: lanes at different collectives\n"); abort(); }
-            kind = w.op[l];
+        int live = 0, at_barrier = 0;
+        for (int l = 0; l < nlanes; ++l) {
+            if (!w.finished[l] && !w.parked[l]) {
+                w.lane = l;
+                swapcontext(&w.sched, &w.ctx[l]);          // until its next collective or its end
+                if (!w.finished[l]) w.parked[l] = true;
+            }
+            if (!w.finished[l]) { ++live; at_barrier += w.op[l] == BlockEmu::OP_SYNCTHREADS; }
         }
-        if (done == WarpEmu::LANES) break;
-        if (done) { fprintf(stderr, "warp emulation: %d lanes finished while %d wait at a collective\n", done, parked); abort(); }
-        unsigned long long out[WarpEmu::LANES];
-        for (int l = 0; l < WarpEmu::LANES; ++l) {
-            if (kind == 1) out[l] = w.val[w.arg[l] & 31];
-            else if (kind == 2) out[l] = l >= w.arg[l] ? w.val[l - w.arg[l]] : w.val[l];
-            else out[l] = 0;
+        if (!live) break;
+        bool progress = false;
+        if (at_barrier == live) {                          // __syncthreads: threads that have exited count as arrived
+            for (int l = 0; l < nlanes; ++l) w.parked[l] = false;
+            progress = true;
+        } else {
+            for (int base = 0; base < nlanes; base += 32) {
+                int kind = -1, n = 0;
+                for (int l = base; l < base + 32; ++l) {
+                    if (w.finished[l] || w.op[l] == BlockEmu::OP_SYNCTHREADS) { kind = -2; break; }
+                    if (kind == -1) kind = w.op[l];
+                    if (w.op[l] != kind) emu_die("lanes of a warp at different collectives");
+                    ++n;
+                }
+                if (kind == -2) {
+                    for (int l = base; l < base + 32; ++l)
+                        if (!w.finished[l] && w.op[l] != BlockEmu::OP_SYNCTHREADS) emu_die("a warp collective that part of the warp never reaches");
+                    continue;
+                }
+                unsigned long long out[32];
+                unsigned ballot = 0;
+                if (kind == BlockEmu::OP_BALLOT) for (int k = 0; k < 32; ++k) ballot |= w.val[base + k] ? 1u << k : 0u;
+                for (int k = 0; k < 32; ++k) {
+                    const int l = base + k, a = w.arg[l];
+                    switch (kind) {
+                        case BlockEmu::OP_SHFL: out[k] = w.val[base + (a & 31)]; break;
+                        case BlockEmu::OP_SHFL_UP: out[k] = k >= a ? w.val[l - a] : w.val[l]; break;
+                        case BlockEmu::OP_SHFL_DOWN: out[k] = k + a < 32 ? w.val[l + a] : w.val[l]; break;
+                        case BlockEmu::OP_SHFL_XOR: out[k] = w.val[base + ((k ^ a) & 31)]; break;
+                        case BlockEmu::OP_BALLOT: out[k] = ballot; break;
+                        default: out[k] = 0; break;
+                    }
+                }
+                for (int k = 0; k < 32; ++k) { w.val[base + k] = out[k]; w.parked[base + k] = false; }
+                progress = true;
+            }
         }
-        for (int l = 0; l < WarpEmu::LANES; ++l) w.val[l] = out[l];
+        if (!progress) emu_die("deadlock: neither a full warp at a collective nor the whole block at __syncthreads");
     }
     w.active = false;
-    w.lane = 0;
+    w.lane = 0; w.nlanes = 1; w.block_idx = 0; w.grid_dim = 1;
+}
+static void run_warp(const std::function<void(int)>& body) {      // one warp: body(lane)
+    run_block(32, 0, 1, [&] { body(g_blk.lane); });
 }
 static unsigned long long warp_collective(int kind, unsigned long long v, int arg) {
-    WarpEmu& w = g_warp;
-    if (!w.active) return v;
+    BlockEmu& w = g_blk;
+    if (!w.active) return kind == BlockEmu::OP_BALLOT ? (v ? 1ull : 0ull) : v;
     const int l = w.lane;
     w.op[l] = kind; w.val[l] = v; w.arg[l] = arg;
     swapcontext(&w.ctx[l], &w.sched);
+    w.op[l] = BlockEmu::OP_NONE;
     return w.val[l];
 }
-template <class T> __host__ __device__ inline T hm_shfl(unsigned, T v, int src) {
+template <class T> inline T hm_exchange(int kind, T v, int arg) {
     static_assert(sizeof(T) <= 8, "shuffle payload");
+    unsigned long long raw = 0;
+    memcpy(&raw, &v, sizeof(T));
+    raw = warp_collective(kind, raw, arg);
+    memcpy(&v, &raw, sizeof(T));
+    return v;
+}
 #ifndef __CUDA_ARCH__       /* nvcc's device pass only has to compile this file */
-    unsigned long long raw = 0;
-    memcpy(&raw, &v, sizeof(T));
-    raw = warp_collective(1, raw, src);
-    memcpy(&v, &raw, sizeof(T));
+#define HM_HOST(...) __VA_ARGS__
+#else
+#define HM_HOST(...)
 #endif
-    return v;
+template <class T> __host__ __device__ inline T hm_shfl(unsigned, T v, int src) { HM_HOST(v = hm_exchange(BlockEmu::OP_SHFL, v, src);) return v; }
+template <class T> __host__ __device__ inline T hm_shfl_up(unsigned, T v, unsigned d) { HM_HOST(v = hm_exchange(BlockEmu::OP_SHFL_UP, v, (int)d);) return v; }
+template <class T> __host__ __device__ inline T hm_shfl_down(unsigned, T v, unsigned d) { HM_HOST(v = hm_exchange(BlockEmu::OP_SHFL_DOWN, v, (int)d);) return v; }
+template <class T> __host__ __device__ inline T hm_shfl_xor(unsigned, T v, int m) { HM_HOST(v = hm_exchange(BlockEmu::OP_SHFL_XOR, v, m);) return v; }
+__host__ __device__ inline unsigned hm_ballot(unsigned, bool pred) {
+    unsigned r = pred ? 1u : 0u;
+    HM_HOST(r = (unsigned)warp_collective(BlockEmu::OP_BALLOT, pred ? 1ull : 0ull, 0);)
+    return r;
 }
-template <class T> __host__ __device__ inline T hm_shfl_up(unsigned, T v, unsigned delta) {
-#ifndef __CUDA_ARCH__
-    unsigned long long raw = 0;
-    memcpy(&raw, &v, sizeof(T));
-    raw = warp_collective(2, raw, (int)delta);
-    memcpy(&v, &raw, sizeof(T));
-#endif
-    return v;
-}
-__host__ __device__ inline void hm_syncwarp() {
-#ifndef __CUDA_ARCH__
-    warp_collective(3, 0, 0);
-#endif
-}
+__host__ __device__ inline void hm_syncwarp() { HM_HOST(warp_collective(BlockEmu::OP_SYNCWARP, 0, 0);) }
+__host__ __device__ inline void hm_syncthreads() { HM_HOST(warp_collective(BlockEmu::OP_SYNCTHREADS, 0, 0);) }
 struct HmDim { unsigned x, y, z; };
-__host__ __device__ inline HmDim hm_thread_now() {
-#ifndef __CUDA_ARCH__
-    return HmDim{(unsigned)g_warp.lane, 0u, 0u};
-#else
-    return HmDim{0u, 0u, 0u};
-#endif
-}
-__host__ __device__ inline HmDim hm_block_now() {
-#ifndef __CUDA_ARCH__
-    return HmDim{g_warp.active ? 32u : 1u, 1u, 1u};
-#else
-    return HmDim{1u, 1u, 1u};
-#endif
-}
-__host__ __device__ inline float hm_atomic_add(float* p, float v) { const float old = *p; *p = old + v; return old; }   // one host thread
+__host__ __device__ inline HmDim hm_thread_now() { HmDim d = {0u, 0u, 0u}; HM_HOST(d.x = (unsigned)g_blk.lane;) return d; }
+__host__ __device__ inline HmDim hm_block_dim() { HmDim d = {1u, 1u, 1u}; HM_HOST(d.x = g_blk.active ? (unsigned)g_blk.nlanes : 1u;) return d; }
+__host__ __device__ inline HmDim hm_block_idx() { HmDim d = {0u, 0u, 0u}; HM_HOST(d.x = g_blk.block_idx;) return d; }
+__host__ __device__ inline HmDim hm_grid_dim() { HmDim d = {1u, 1u, 1u}; HM_HOST(d.x = g_blk.grid_dim;) return d; }
+template <class T, class U> __host__ __device__ inline T hm_atomic_add(T* p, U v) { const T old = *p; *p = old + (T)v; return old; }   // one host thread
+template <class T, class U> __host__ __device__ inline T hm_atomic_or(T* p, U v) { const T old = *p; *p = old | (T)v; return old; }
 #define __fadd_rn hm_add
 #define __fsub_rn hm_sub
 #define __fmul_rn hm_mul
@@ -158,10 +189,17 @@ __host__ __device__ inline float hm_atomic_add(float* p, float v) { const float 
 #define __popc hm_popc
 #define __shfl_sync hm_shfl
 #define __shfl_up_sync hm_shfl_up
+#define __shfl_down_sync hm_shfl_down
+#define __shfl_xor_sync hm_shfl_xor
+#define __ballot_sync hm_ballot
 #define __syncwarp hm_syncwarp
+#define __syncthreads hm_syncthreads
 #define threadIdx hm_thread_now()
-#define blockDim hm_block_now()
+#define blockDim hm_block_dim()
+#define blockIdx hm_block_idx()
+#define gridDim hm_grid_dim()
 #define atomicAdd hm_atomic_add
+#define atomicOr hm_atomic_or
 
 #include "integrators.cuh"
 #include "scene_build.h"
