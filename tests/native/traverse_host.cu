@@ -20,6 +20,12 @@
 #include <string>
 
 #define TPT_DEV __host__ __device__ inline
+#ifndef __CUDACC__          /* built as plain C++ (wavefront_host.cu): what nvcc's headers would have declared */
+#include <algorithm>
+using std::max;
+using std::min;
+inline size_t __cvta_generic_to_shared(const void* p) { return reinterpret_cast<size_t>(p); }
+#endif
 
 __host__ __device__ inline float hm_add(float a, float b) { return a + b; }
 __host__ __device__ inline float hm_sub(float a, float b) { return a - b; }
@@ -29,7 +35,17 @@ __host__ __device__ inline float hm_sqrt(float a) { return sqrtf(a); }
 __host__ __device__ inline float hm_fma(float a, float b, float c) { return fmaf(a, b, c); }
 __host__ __device__ inline int hm_f2i(float f) { int i; memcpy(&i, &f, 4); return i; }
 __host__ __device__ inline unsigned hm_f2u(float f) { unsigned i; memcpy(&i, &f, 4); return i; }
+__host__ __device__ inline float hm_i2f(int i) { float f; memcpy(&f, &i, 4); return f; }
+__host__ __device__ inline float hm_u2f(unsigned i) { float f; memcpy(&f, &i, 4); return f; }
 __host__ __device__ inline int hm_ffs(unsigned v) { int n = 0; if (!v) return 0; while (!(v & 1u)) { v >>= 1; ++n; } return n + 1; }
+// fns.b32: position of the offset-th set bit of mask at or above (offset > 0) / at or below (offset < 0) bit `base`
+__host__ __device__ inline unsigned hm_fns(unsigned mask, unsigned base, int offset) {
+    if (offset == 0) return (mask >> base) & 1u ? base : 0xffffffffu;
+    int seen = 0;
+    if (offset > 0) { for (unsigned b = base; b < 32u; ++b) if ((mask >> b) & 1u) if (++seen == offset) return b; }
+    else { for (int b = (int)base; b >= 0; --b) if ((mask >> b) & 1u) if (++seen == -offset) return (unsigned)b; }
+    return 0xffffffffu;
+}
 __host__ __device__ inline int hm_popc(unsigned v) { int n = 0; while (v) { v &= v - 1u; ++n; } return n; }
 // ---- a thread block on the CPU ---------------------------------------------------------------------
 // Warp- and block-cooperative code (coop_test / closest_hit_warp here; the wavefront kernels in wavefront_host.cu:
@@ -185,8 +201,11 @@ template <class T, class U> __host__ __device__ inline T hm_atomic_or(T* p, U v)
 #define __fmaf_rn hm_fma
 #define __float_as_int hm_f2i
 #define __float_as_uint hm_f2u
+#define __int_as_float hm_i2f
+#define __uint_as_float hm_u2f
 #define __ffs hm_ffs
 #define __popc hm_popc
+#define __fns hm_fns
 #define __shfl_sync hm_shfl
 #define __shfl_up_sync hm_shfl_up
 #define __shfl_down_sync hm_shfl_down

@@ -406,3 +406,92 @@ def test_algorithmic_bytes_per_ray_of_the_bench_workload(mirror):
     img, _ = m.render("bdpt", 4)
     assert np.allclose(rad + splat, img, rtol=1e-5, atol=1e-6)
     m.close()
+
+
+# ---- the wavefront pipelines on a block emulator ----------------------------------------------------------
+# tests/native/wavefront_host.cu: csrc/wavefront.cu and csrc/pt_wavefront.cu — kernels and the host loops that launch
+# them — compiled as plain C++; a launch runs block after block as 256 coroutines that meet at ballots, shuffles and
+# __syncthreads.  The frame must be the one the per-pixel loop (th_render: FillBufferThread's body around the same
+# integrator functions) computes from the same per-pixel streams: identical for PathTrace, which adds every pixel's
+# samples in the reference's order, and equal up to the order of float additions for BDPT (splats and strategy sums
+# arrive through atomics).
+def build_wavefront_mirror(tmp_path_factory, defines=()):
+    gxx = shutil.which("g++")
+    cuda_inc = "/usr/local/cuda/include"
+    if not gxx or not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("g++ / CUDA headers not available")
+    so = str(tmp_path_factory.mktemp("wfmirror") / "libwavefront_host.so")
+    r = subprocess.run([gxx, *defines, "-std=c++17", "-O2", "-x", "c++", "-fPIC", "-ffp-contract=off", "-shared", "-w",
+                        "-I", cuda_inc, "-I", os.path.join(ROOT, "include"), "-I", os.path.join(PKG, "csrc"),
+                        "-I", os.path.join(ROOT, "tests", "native"), os.path.join(ROOT, "tests", "native", "wavefront_host.cu"),
+                        "-o", so, "-L/usr/local/cuda/lib64", "-lcudart_static", "-ldl", "-lrt", "-lpthread"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lib = C.CDLL(so)
+    lib.th_scene_create.restype = C.c_void_p
+    lib.th_scene_create.argtypes = [C.c_void_p]
+    lib.th_scene_destroy.argtypes = [C.c_void_p]
+    lib.th_last_error.restype = C.c_char_p
+    lib.th_render.restype = C.c_uint64
+    lib.th_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.th_wavefront_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    return lib
+
+
+@pytest.fixture(scope="module")
+def wfmirror(tmp_path_factory):
+    return build_wavefront_mirror(tmp_path_factory)
+
+
+# experiments of the wavefront kernels (off in the shipped build): a budget of 5 cuts every walk many times over
+WF_EXPERIMENTS = ["-DTPT_BUDGET_WALK=32", "-DTPT_BUDGET_WALK=5", "-DTPT_WIDE_TRIS"]
+
+
+@pytest.fixture(scope="module", params=WF_EXPERIMENTS)
+def wf_experiment(request, tmp_path_factory):
+    return build_wavefront_mirror(tmp_path_factory, request.param.split())
+
+
+def wavefront_vs_pixel_loop(lib, scene, mode, spp, size, sms=1):
+    import tpt_b200 as T
+    m = Mirror(lib, scene, size, size)
+    img = np.zeros((size, size, 3), np.float32)
+    stats = np.zeros(8, np.uint64)
+    rc = lib.th_wavefront_render(m.h, T.MODES[mode], spp, sms, img.ctypes.data, stats.ctypes.data)
+    assert rc == 0, lib.th_last_error()
+    ref, st = m.render(mode, spp)
+    m.close()
+    assert int(stats[5]) == size * size * spp                      # STAT_SAMPLES
+    assert int(stats[0]) == st["ref_rays"]                         # the reference's "Rays" (STAT_REF_RAYS)
+    return img, ref
+
+
+@pytest.mark.parametrize("scene,mode,spp", [("standard", "pt_full", 4), ("standard", "pt_shipped", 8), ("refractive", "pt_full", 3),
+                                            ("bunny", "pt_full", 3)])
+def test_pathtrace_wavefront_is_the_pixel_loop(wfmirror, scene, mode, spp):
+    """k_pt_generate / k_pt_shade / k_pt_extend / k_pt_shadow with pt_wavefront_render's launch chains (two interleaved
+    chains over alternate slots at this size): the same image bit for bit."""
+    img, ref = wavefront_vs_pixel_loop(wfmirror, scene, mode, spp, 32)
+    assert (img.view(np.uint32) == ref.view(np.uint32)).all(), float(np.abs(img - ref).max())
+    assert ref.mean() > 0.05
+
+
+@pytest.mark.parametrize("scene,spp,sms", [("standard", 4, 1), ("refractive", 3, 2), ("occlusion", 3, 1), ("bunny", 2, 1)])
+def test_bdpt_wavefront_is_the_pixel_loop(wfmirror, scene, spp, sms):
+    """k_generate / k_shade / k_extend / k_expand / k_connect / k_shadow_q / k_mis with wavefront_render's loop (strategy
+    records, shadow and MIS queues, rotating path-store copies): every pixel within float addition order of the pixel
+    loop, the same number of subpath vertices."""
+    img, ref = wavefront_vs_pixel_loop(wfmirror, scene, "bdpt", spp, 32, sms)
+    assert np.isfinite(img).all()
+    assert np.allclose(img, ref, rtol=2e-4, atol=2e-5), float(np.abs(img - ref).max())
+    assert ref.mean() > 0.05
+
+
+def test_wavefront_experiments_render_the_same_frames(wf_experiment):
+    """-DTPT_BUDGET_WALK (walks cut into turns, unfinished ones parked in a block-local queue and re-dealt) and
+    -DTPT_WIDE_TRIS must not change a bit of the PathTrace frames, large scene and small."""
+    for scene, mode, spp in (("bunny", "pt_full", 3), ("standard", "pt_full", 2)):
+        img, ref = wavefront_vs_pixel_loop(wf_experiment, scene, mode, spp, 32)
+        assert (img.view(np.uint32) == ref.view(np.uint32)).all(), (scene, float(np.abs(img - ref).max()))
+    img, ref = wavefront_vs_pixel_loop(wf_experiment, "bunny", "bdpt", 2, 32)
+    assert np.allclose(img, ref, rtol=2e-4, atol=2e-5)

@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(256, PT_SHADE_MIN_BLOCKS) k_pt_shade(SceneView
 struct ExtCont { int slot, i, best, pad; double best_t; };
 struct ShCont { unsigned k; int i; };
 
-__device__ void pt_extend_budgeted(const SceneView& sc, const PtBuffers& b, const int* list, unsigned n, unsigned long long& rays) {
+TPT_DEV void pt_extend_budgeted(const SceneView& sc, const PtBuffers& b, const int* list, unsigned n, unsigned long long& rays) {
     __shared__ ExtCont cq[512];
     __shared__ unsigned cq_n;
     if (threadIdx.x == 0) cq_n = 0;
@@ -292,7 +292,7 @@ __device__ void pt_extend_budgeted(const SceneView& sc, const PtBuffers& b, cons
     while (cq_n > 0) drain();
 }
 
-__device__ void pt_shadow_budgeted(const SceneView& sc, const PtBuffers& b, const int* list, unsigned n, unsigned long long& rays) {
+TPT_DEV void pt_shadow_budgeted(const SceneView& sc, const PtBuffers& b, const int* list, unsigned n, unsigned long long& rays) {
     __shared__ ShCont sq[512];
     __shared__ unsigned sq_n;
     if (threadIdx.x == 0) sq_n = 0;

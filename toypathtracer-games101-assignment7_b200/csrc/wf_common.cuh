@@ -31,15 +31,25 @@ TPT_DEV unsigned wf_append(unsigned* counter, bool want) {
 // scene blob, setting up shared memory — before pdl_wait(), which returns once the predecessor grid has
 // completed and its writes are visible.  Every kernel in the loop calls pdl_wait() before it touches
 // queue state, so completion is transitive along the stream.
-TPT_DEV void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-TPT_DEV void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// (PTX only in the device pass: tests/native/wavefront_host.cu compiles the kernels for the host, where launches
+// run one after another and there is nothing to wait for)
+TPT_DEV void pdl_launch_dependents() {
+#ifdef __CUDA_ARCH__
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+TPT_DEV void pdl_wait() {
+#ifdef __CUDA_ARCH__
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
 
 TPT_DEV f3 hit_normal(const SceneView& sc, int prim, f3 coords) {
     if (prim < sc.n_tris) return mk3(sc.tris[4 * prim + 3]);
     return x_normalize(x_sub(coords, mk3(sc.spheres[2 * (prim - sc.n_tris)])));
 }
 
-__device__ inline void flush_stats(unsigned long long ref_rays, unsigned long long scene_rays,
+TPT_DEV void flush_stats(unsigned long long ref_rays, unsigned long long scene_rays,
                                    unsigned long long samples, unsigned long long* stats,
                                    unsigned long long shadow_rays = 0) {
     unsigned long long v[4] = {ref_rays, scene_rays, samples, shadow_rays};
