@@ -12,8 +12,9 @@ in the three modes with the loop body of the validation kernel.
 What this pins on the CPU: the grafted visit-ordered node array, the flat leaf list and its bit masks, the pruning
 margins, the any-hit form of ShadowCheck, the deferred (recorded) walk — every walk the kernels use returns the
 reference's primitive id, t, hit point, normal and shadow decision.  What it cannot pin is the device's own
-arithmetic (that a B200 rounds these operations the same way), nor the wavefront pipeline's queues and launch
-chains: tests/test_gpu_*.py do, through the C ABI.  This module is test infrastructure: the product has no CPU path."""
+arithmetic (that a B200 rounds these operations the same way), real concurrency between streams, and timing:
+tests/test_gpu_*.py do, through the C ABI.  The last part of this module runs the wavefront pipelines (kernels and
+launch loops) on a block emulator.  All of it is test infrastructure: the product has no CPU path."""
 import ctypes as C
 import os
 import shutil
