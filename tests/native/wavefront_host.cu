@@ -59,6 +59,19 @@ void tpt_dev_free(void* p) { free(p); }
 void* tpt_pinned_alloc(size_t bytes) { return calloc(1, bytes ? bytes : 1); }
 void tpt_pinned_free(void* p) { free(p); }
 
+// How the lanes of k_shade's warps split between its two expensive branches (all lanes of a warp get here together):
+// [0] warps, [1] live lanes, [2] lanes that extend, [3] lanes that start a light subpath, [4] warps with an extending
+// lane, [5] warps with a light-start lane.  A warp runs a branch for all 32 lanes if one lane takes it.
+static unsigned long long g_shade_trace[6];
+static inline void hm_trace_shade(int action, bool live) {
+    const unsigned e = hm_ballot(0xffffffffu, action == 1), l = hm_ballot(0xffffffffu, action == 2), v = hm_ballot(0xffffffffu, live);
+    if ((hm_thread_now().x & 31u) == 0u) {
+        g_shade_trace[0] += 1; g_shade_trace[1] += hm_popc(v); g_shade_trace[2] += hm_popc(e); g_shade_trace[3] += hm_popc(l);
+        g_shade_trace[4] += e != 0u; g_shade_trace[5] += l != 0u;
+    }
+}
+#define WF_TRACE_SHADE(action, live) hm_trace_shade(action, live)
+
 #include "wavefront.cu"
 #include "pt_wavefront.cu"
 
@@ -66,6 +79,10 @@ extern "C" {
 
 // tpt_render for the wavefront pipelines: image = radiance + splat / spp (k_scale + k_finalize of tpt.cu on the host).
 // sms plays the role of the multiprocessor count (grids are sms * 8 blocks at most).  Returns 0, or a TPT_ERR_* code.
+void th_shade_trace(unsigned long long* out6, int reset) {
+    for (int k = 0; k < 6; ++k) { out6[k] = g_shade_trace[k]; if (reset) g_shade_trace[k] = 0; }
+}
+
 int th_wavefront_render(HostScene* hs, int mode, int spp, int sms, float* image, unsigned long long* stats8) {
     TptScene scene;
     scene.device = 0;
