@@ -71,6 +71,10 @@ static inline void hm_trace_shade(int action, bool live) {
     }
 }
 #define WF_TRACE_SHADE(action, live) hm_trace_shade(action, live)
+// k_mis: per lane (s, t) of the strategy it weighs (its loop is not whole-warp: lanes report one by one)
+static unsigned long long g_mis_n, g_mis_hist[17][17];
+static unsigned char g_mis_seq[1 << 22][2]; static unsigned g_mis_seq_n;
+#define WF_TRACE_MIS(s, t) do { g_mis_n++; g_mis_hist[(s) & 15][(t) & 15]++; if (g_mis_seq_n < (1u << 22)) { g_mis_seq[g_mis_seq_n][0] = (unsigned char)(s); g_mis_seq[g_mis_seq_n][1] = (unsigned char)(t); g_mis_seq_n++; } } while (0)
 
 #include "wavefront.cu"
 #include "pt_wavefront.cu"
@@ -79,6 +83,12 @@ extern "C" {
 
 // tpt_render for the wavefront pipelines: image = radiance + splat / spp (k_scale + k_finalize of tpt.cu on the host).
 // sms plays the role of the multiprocessor count (grids are sms * 8 blocks at most).  Returns 0, or a TPT_ERR_* code.
+unsigned th_mis_trace(unsigned char* st, unsigned cap) {
+    const unsigned n = g_mis_seq_n < cap ? g_mis_seq_n : cap;
+    memcpy(st, g_mis_seq, (size_t)n * 2);
+    g_mis_seq_n = 0;
+    return n;
+}
 void th_shade_trace(unsigned long long* out6, int reset) {
     for (int k = 0; k < 6; ++k) { out6[k] = g_shade_trace[k]; if (reset) g_shade_trace[k] = 0; }
 }

@@ -40,7 +40,7 @@ def build_mirror(tmp_path_factory, defines=()):
         pytest.skip("nvcc not available")
     so = str(tmp_path_factory.mktemp("mirror") / "libtraverse_host.so")
     r = subprocess.run([nvcc, *defines, "-std=c++17", "-O2", "-gencode", "arch=compute_100a,code=sm_100a", "--expt-relaxed-constexpr",
-                        "-Xcompiler", "-fPIC,-ffp-contract=off", "-diag-suppress", "177", "-shared", "-I", os.path.join(ROOT, "include"),
+                        "-Xcompiler", "-fPIC,-ffp-contract=off", "-diag-suppress", "177", "-shared", "-Xlinker", "-Bsymbolic", "-I", os.path.join(ROOT, "include"),
                         "-I", os.path.join(PKG, "csrc"), os.path.join(ROOT, "tests", "native", "traverse_host.cu"), "-o", so],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
@@ -425,7 +425,8 @@ def build_wavefront_mirror(tmp_path_factory, defines=()):
     r = subprocess.run([gxx, *defines, "-std=c++17", "-O2", "-x", "c++", "-fPIC", "-ffp-contract=off", "-shared", "-w",
                         "-I", cuda_inc, "-I", os.path.join(ROOT, "include"), "-I", os.path.join(PKG, "csrc"),
                         "-I", os.path.join(ROOT, "tests", "native"), os.path.join(ROOT, "tests", "native", "wavefront_host.cu"),
-                        "-o", so, "-L/usr/local/cuda/lib64", "-lcudart_static", "-ldl", "-lrt", "-lpthread"],
+                        "-o", so, "-Wl,-Bsymbolic",        # libtpt.so (RTLD_GLOBAL in this process) has a tpt_dev_alloc of its own
+                        "-L/usr/local/cuda/lib64", "-lcudart_static", "-ldl", "-lrt", "-lpthread"],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     lib = C.CDLL(so)
