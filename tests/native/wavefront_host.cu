@@ -93,7 +93,21 @@ void th_shade_trace(unsigned long long* out6, int reset) {
     for (int k = 0; k < 6; ++k) { out6[k] = g_shade_trace[k]; if (reset) g_shade_trace[k] = 0; }
 }
 
+static int RenderShare(HostScene* hs, int mode, int spp, int sms, int partition, int rank, int world, float* image, unsigned long long* stats8);
+
 int th_wavefront_render(HostScene* hs, int mode, int spp, int sms, float* image, unsigned long long* stats8) {
+    return RenderShare(hs, mode, spp, sms, TPT_PART_ALL, 0, 1, image, stats8);
+}
+// One rank's share of a frame (TPT_PART_INTERLEAVE / TPT_PART_BLOCK, tpt.h): pixels of other ranks stay zero in the
+// radiance part; BDPT splats land anywhere.  The shares of all ranks add up to the frame (the multi-GPU reduce).
+int th_wavefront_render_share(HostScene* hs, int mode, int spp, int sms, int partition, int rank, int world, float* image,
+                              unsigned long long* stats8) {
+    return RenderShare(hs, mode, spp, sms, partition, rank, world, image, stats8);
+}
+
+}  // extern "C"
+
+static int RenderShare(HostScene* hs, int mode, int spp, int sms, int partition, int rank, int world, float* image, unsigned long long* stats8) {
     TptScene scene;
     scene.device = 0;
     scene.view = hs->view;
@@ -105,7 +119,7 @@ int th_wavefront_render(HostScene* hs, int mode, int spp, int sms, float* image,
     RenderArgs a;
     memset(&a, 0, sizeof a);
     a.mode = mode; a.spp = spp; a.spp_total = spp;
-    a.seed_mode = TPT_SEED_REF; a.partition = TPT_PART_ALL; a.rank = 0; a.world = 1; a.stream = 0;
+    a.seed_mode = TPT_SEED_REF; a.partition = partition; a.rank = rank; a.world = world; a.stream = 0;
     a.prune = 1; a.sub = 0; a.nsub = 1;
     const size_t n3 = (size_t)hs->view.width * hs->view.height * 3;
     float* radiance = static_cast<float*>(calloc(n3, sizeof(float)));
@@ -125,5 +139,3 @@ int th_wavefront_render(HostScene* hs, int mode, int spp, int sms, float* image,
     free(scene.d_stats); free(radiance); free(splat);
     return rc;
 }
-
-}  // extern "C"

@@ -438,6 +438,7 @@ def build_wavefront_mirror(tmp_path_factory, defines=()):
     lib.th_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.th_wavefront_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.th_shade_trace.argtypes = [C.c_void_p, C.c_int]
+    lib.th_wavefront_render_share.argtypes = [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p]
     return lib
 
 
@@ -521,3 +522,31 @@ def test_binned_active_lists_make_the_warps_of_k_shade_uniform(wfmirror, tmp_pat
     ext1, light1 = shade_lane_split(binned)
     assert 24 < ext0 < 28 and 3 < light0 < 8, (ext0, light0)
     assert ext1 > 29.5 and light1 > 20, (ext1, light1)
+
+
+@pytest.mark.parametrize("partition,world", [(1, 2), (1, 3), (2, 4)], ids=["interleave-2", "interleave-3", "block-4"])
+def test_rank_shares_add_up_to_the_frame(wfmirror, partition, world):
+    """The multi-GPU split: rank r renders pixels i = r (mod world) or the r-th contiguous run with the
+    reference's per-pixel streams; radiance cells are disjoint, BDPT splats land anywhere, and the sum over ranks
+    (the NCCL reduce) is the one-GPU frame — bit for bit for PathTrace, up to the order of the splat additions for BDPT."""
+    import tpt_b200 as T
+    size = 24
+    for mode, spp in (("pt_full", 3), ("bdpt", 3)):
+        m = Mirror(wfmirror, "standard", size, size)
+        full = np.zeros((size, size, 3), np.float32)
+        assert wfmirror.th_wavefront_render(m.h, T.MODES[mode], spp, 1, full.ctypes.data, None) == 0
+        total = np.zeros_like(full)
+        samples = 0
+        for rank in range(world):
+            part = np.zeros_like(full)
+            stats = np.zeros(8, np.uint64)
+            assert wfmirror.th_wavefront_render_share(m.h, T.MODES[mode], spp, 1, partition, rank, world, part.ctypes.data,
+                                                      stats.ctypes.data) == 0
+            total += part
+            samples += int(stats[5])
+        m.close()
+        assert samples == size * size * spp
+        if mode == "pt_full":
+            assert (total.view(np.uint32) == full.view(np.uint32)).all()
+        else:
+            assert np.allclose(total, full, rtol=2e-4, atol=2e-5)
