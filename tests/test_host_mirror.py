@@ -31,7 +31,7 @@ PKG = os.path.join(ROOT, "toypathtracer-games101-assignment7_b200")
 
 # Compile-time experiments of csrc/ (off in the shipped build, `make NVEXTRA=<define>` to try one on the GPU): each must
 # leave the exact tier bit-exact, which is checked here before any GPU time goes into timing it.
-EXPERIMENTS = ["-DTPT_WIDE_TRIS"]
+EXPERIMENTS = []      # none open (round 2 timed -DTPT_WIDE_TRIS: neutral, removed)
 
 
 def build_mirror(tmp_path_factory, defines=()):
@@ -447,8 +447,9 @@ def wfmirror(tmp_path_factory):
     return build_wavefront_mirror(tmp_path_factory)
 
 
-# experiments of the wavefront kernels (off in the shipped build): a budget of 5 cuts every walk many times over
-WF_EXPERIMENTS = ["-DTPT_BUDGET_WALK=32", "-DTPT_BUDGET_WALK=5", "-DTPT_WIDE_TRIS", "-DWF_BIN_ACTIVE"]
+# experiments of the wavefront kernels (off in the shipped build).  None open: round 2 timed -DTPT_BUDGET_WALK (slower),
+# -DTPT_WIDE_TRIS (neutral) and -DWF_BIN_ACTIVE (slower) on the B200 and removed them (profiles/r02a_ab_*.log)
+WF_EXPERIMENTS = []
 
 
 @pytest.fixture(scope="module", params=WF_EXPERIMENTS)
@@ -492,36 +493,13 @@ def test_bdpt_wavefront_is_the_pixel_loop(wfmirror, scene, spp, sms):
 
 
 def test_wavefront_experiments_render_the_same_frames(wf_experiment):
-    """-DTPT_BUDGET_WALK (walks cut into turns, unfinished ones parked in a block-local queue and re-dealt) and
-    -DTPT_WIDE_TRIS must not change a bit of the PathTrace frames, large scene and small."""
+    """A compile-time experiment must not change a bit of the PathTrace frames, large scene and small."""
     for scene, mode, spp in (("bunny", "pt_full", 3), ("standard", "pt_full", 2)):
         img, ref = wavefront_vs_pixel_loop(wf_experiment, scene, mode, spp, 32)
         assert (img.view(np.uint32) == ref.view(np.uint32)).all(), (scene, float(np.abs(img - ref).max()))
     for scene, spp in (("bunny", 2), ("refractive", 3)):
         img, ref = wavefront_vs_pixel_loop(wf_experiment, scene, "bdpt", spp, 32)
         assert np.allclose(img, ref, rtol=2e-4, atol=2e-5), scene
-
-
-def shade_lane_split(lib, size=48, spp=5):
-    """(lanes per warp that sample a direction, lanes per warp that start a light subpath) over the warps of k_shade
-    that have at least one such lane: a warp runs a branch for all 32 lanes if one lane takes it."""
-    trace = np.zeros(6, np.uint64)
-    lib.th_shade_trace(trace.ctypes.data, 1)
-    wavefront_vs_pixel_loop(lib, "standard", "bdpt", spp, size)
-    lib.th_shade_trace(trace.ctypes.data, 1)
-    warps, live, ext, light, wext, wlight = [int(x) for x in trace]
-    return ext / wext, light / wlight
-
-
-def test_binned_active_lists_make_the_warps_of_k_shade_uniform(wfmirror, tmp_path_factory):
-    """-DWF_BIN_ACTIVE: k_extend groups the active slots by what k_shade will do with them.  As shipped nearly every
-    warp of k_shade holds a few lanes that start a light subpath among lanes that sample a direction (5 and 26 of 32
-    lanes: the 19-of-32 lane utilisation ncu reports for k_shade); binned, each branch runs in warps of its own."""
-    ext0, light0 = shade_lane_split(wfmirror)
-    binned = build_wavefront_mirror(tmp_path_factory, ["-DWF_BIN_ACTIVE"])
-    ext1, light1 = shade_lane_split(binned)
-    assert 24 < ext0 < 28 and 3 < light0 < 8, (ext0, light0)
-    assert ext1 > 29.5 and light1 > 20, (ext1, light1)
 
 
 @pytest.mark.parametrize("partition,world", [(1, 2), (1, 3), (2, 4)], ids=["interleave-2", "interleave-3", "block-4"])

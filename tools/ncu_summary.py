@@ -13,6 +13,11 @@ KEYS = ["Kernel Name", "gpu__time_duration.sum", "launch__registers_per_thread",
         "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "sm__inst_issued.sum", "sm__inst_issued.avg.pct_of_peak_sustained_active", "smsp__thread_inst_executed.sum",
+        "sm__cycles_active.avg", "lts__t_bytes.sum", "lts__t_sectors_srcunit_tex_lookup_hit.sum",
+        "lts__t_sectors_srcunit_tex_lookup_miss.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+        "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum",
+        "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__pcsamp_warps_issue_stalled_long_scoreboard", "smsp__pcsamp_warps_issue_stalled_no_instructions",
         "smsp__pcsamp_warps_issue_stalled_wait", "smsp__pcsamp_warps_issue_stalled_short_scoreboard",

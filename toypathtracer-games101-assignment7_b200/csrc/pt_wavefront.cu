@@ -242,102 +242,6 @@ __global__ void __launch_bounds__(256, PT_SHADE_MIN_BLOCKS) k_pt_shade(SceneView
     flush_stats(ref_rays, 0, samples, stats);
 }
 
-#ifdef TPT_BUDGET_WALK
-// Experiment (off by default; `make NVEXTRA=-DTPT_BUDGET_WALK=32`), large scenes only (no flat leaf list): a lane
-// spends at most TPT_BUDGET_WALK node visits on a ray (walk_resume, traverse.cuh — the same walk, cut in pieces) and
-// parks an unfinished walk in a block-local queue; whenever a block's worth of walks is parked the block takes them
-// up again, one per thread, so the long walks (the tenth of the rays that enter the big mesh) run in full warps of
-// their own instead of holding 31 finished lanes each.  Untimed so far: DESIGN.md section 10 has the host-side estimate.
-struct ExtCont { int slot, i, best, pad; double best_t; };
-struct ShCont { unsigned k; int i; };
-
-TPT_DEV void pt_extend_budgeted(const SceneView& sc, const PtBuffers& b, const int* list, unsigned n, unsigned long long& rays) {
-    __shared__ ExtCont cq[512];
-    __shared__ unsigned cq_n;
-    if (threadIdx.x == 0) cq_n = 0;
-    __syncthreads();
-    auto step = [&](int slot, WalkCursor c) {           // walk on; done: write the hit, else park
-        const float4 o = b.ray_o[slot], d = b.ray_d[slot];
-        const DRay r = make_ray(mk3(o), mk3(d));
-        if (walk_resume(sc, r, __float_as_int(o.w), sc.n_nodes, true, TPT_BUDGET_WALK, c)) {
-            DHit h;
-            finish_hit(sc, r, c.best, c.best_t, &h);
-            b.hit[slot] = make_float4(h.coords.x, h.coords.y, h.coords.z, __int_as_float(h.prim));
-        } else {
-            ExtCont e; e.slot = slot; e.i = c.i; e.best = c.best; e.pad = 0; e.best_t = c.best_t;
-            cq[atomicAdd(&cq_n, 1u)] = e;
-        }
-    };
-    auto drain = [&]() {                                 // every thread of the block calls; takes up to blockDim.x parked walks
-        const unsigned have = cq_n;
-        const unsigned m = have < blockDim.x ? have : blockDim.x;
-        const bool mine = threadIdx.x < m;
-        ExtCont e;
-        if (mine) e = cq[have - m + threadIdx.x];
-        __syncthreads();
-        if (threadIdx.x == 0) cq_n = have - m;
-        __syncthreads();
-        if (mine) { WalkCursor c; c.i = e.i; c.best = e.best; c.best_t = e.best_t; step(e.slot, c); }
-        __syncthreads();
-    };
-    for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {      // uniform per block
-        const unsigned q = base + threadIdx.x;
-        if (q < n) {
-            const int slot = list[q];
-            if (__float_as_int(b.ray_o[slot].w) >= 0) { rays++; step(slot, walk_begin(0)); }
-        }
-        __syncthreads();
-        while (cq_n >= blockDim.x) drain();
-    }
-    while (cq_n > 0) drain();
-}
-
-TPT_DEV void pt_shadow_budgeted(const SceneView& sc, const PtBuffers& b, const int* list, unsigned n, unsigned long long& rays) {
-    __shared__ ShCont sq[512];
-    __shared__ unsigned sq_n;
-    if (threadIdx.x == 0) sq_n = 0;
-    __syncthreads();
-    auto step = [&](unsigned k, int cursor) {
-        const int slot = list[k >> 1];
-        const unsigned j = k & 1u;
-        const ShadowQuery qy = shadow_begin(mk3(b.sh_from[(size_t)j * b.S + slot]), mk3(b.sh_to[slot]));
-        bool found = false;
-        if (shadow_resume(sc, qy, 0, TPT_BUDGET_WALK, cursor, &found)) {
-            if (!found) atomicOr(&b.vis[slot], 1u << j);          // visible
-        } else {
-            ShCont e; e.k = k; e.i = cursor;
-            sq[atomicAdd(&sq_n, 1u)] = e;
-        }
-    };
-    auto drain = [&]() {
-        const unsigned have = sq_n;
-        const unsigned m = have < blockDim.x ? have : blockDim.x;
-        const bool mine = threadIdx.x < m;
-        ShCont e;
-        if (mine) e = sq[have - m + threadIdx.x];
-        __syncthreads();
-        if (threadIdx.x == 0) sq_n = have - m;
-        __syncthreads();
-        if (mine) step(e.k, e.i);
-        __syncthreads();
-    };
-    for (unsigned base = blockIdx.x * blockDim.x; base < 2u * n; base += gridDim.x * blockDim.x) {
-        const unsigned k = base + threadIdx.x;
-        const bool live = k < 2u * n;
-        bool has_ray = false;
-        if (live) {
-            const int slot = list[k >> 1];
-            if ((k & 1u) == 0) b.vis[slot] = 0u;                   // both rays of a slot sit in one warp: cleared before either reports
-            has_ray = b.sh_from[(size_t)(k & 1u) * b.S + slot].w > 0.0f;
-        }
-        __syncwarp();
-        if (has_ray) { rays++; step(k, 0); }
-        __syncthreads();
-        while (sq_n >= blockDim.x) drain();
-    }
-    while (sq_n > 0) drain();
-}
-#endif
 
 __global__ void __launch_bounds__(256) k_pt_extend(SceneView g, PtBuffers b, int cur, unsigned long long* stats) {
     pdl_launch_dependents();
@@ -349,9 +253,6 @@ __global__ void __launch_bounds__(256) k_pt_extend(SceneView g, PtBuffers b, int
     const unsigned n = b.ctr->n_active[cur];
     const int* list = b.active[cur];
     unsigned long long rays = 0;
-#ifdef TPT_BUDGET_WALK
-    if (sc.n_leaves == 0) { pt_extend_budgeted(sc, b, list, n, rays); flush_stats(0, rays, 0, stats); return; }
-#endif
     const unsigned total = (n + 31u) & ~31u;        // whole warps: the primitive tests are shared inside a warp
     for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
         int slot = 0;
@@ -377,9 +278,6 @@ __global__ void __launch_bounds__(256) k_pt_shadow(SceneView g, PtBuffers b, int
     const unsigned n = b.ctr->n_active[cur];
     const int* list = b.active[cur];
     unsigned long long rays = 0;
-#ifdef TPT_BUDGET_WALK
-    if (sc.n_leaves == 0) { pt_shadow_budgeted(sc, b, list, n, rays); flush_stats(0, rays, 0, stats, rays); return; }
-#endif
     const unsigned total = (2u * n + 31u) & ~31u;
     for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
         const bool live = k < 2u * n;

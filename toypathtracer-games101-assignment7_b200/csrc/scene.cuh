@@ -61,9 +61,6 @@ struct SceneView {
     int n_leaves;
     const float4* uboxes;     // the DISTINCT leaf boxes: {bmin, asfloat(leaf mask bits 0-31)} {bmax, asfloat(bits 32-63)}
     int n_uboxes;
-#ifdef TPT_WIDE_TRIS
-    const double* dtris;      // 9 per triangle: normal, e1, e2 widened to double on the host (see triangle_test)
-#endif
     int n_nodes, n_tris, n_spheres, n_mats, n_objs, n_lnodes, n_emissive;
     int width, height;
     float scale;              // CalculateScale(fov), computed on the host with the host libm
@@ -114,9 +111,6 @@ __device__ inline SceneView stage_scene(const SceneView& g, unsigned char* smem)
     s.emissive = reinterpret_cast<const int*>(move(g.emissive));
     s.leaves = reinterpret_cast<const float4*>(move(g.leaves));
     s.uboxes = reinterpret_cast<const float4*>(move(g.uboxes));
-#ifdef TPT_WIDE_TRIS
-    s.dtris = reinterpret_cast<const double*>(move(g.dtris));
-#endif
     return s;
 }
 

@@ -16,9 +16,6 @@ struct SceneBlob {
     std::vector<unsigned char> bytes;      // the arrays in the order stage_scene expects, 16-byte granular
     size_t o_nodes = 0, o_tris = 0, o_tverts = 0, o_spheres = 0, o_mats = 0, o_objs = 0, o_lnodes = 0, o_emissive = 0,
            o_leaves = 0, o_uboxes = 0;
-#ifdef TPT_WIDE_TRIS
-    size_t o_dtris = 0;
-#endif
     int n_nodes = 0, n_leaves = 0, n_uboxes = 0;
 };
 
@@ -230,18 +227,6 @@ static int tpt_build_scene_blob(const TptSceneDesc* d, SceneBlob* out) {
     out->o_spheres = blob_put(blob, spheres); out->o_mats = blob_put(blob, mats); out->o_objs = blob_put(blob, hb.objs);
     out->o_lnodes = blob_put(blob, lnodes); out->o_emissive = blob_put(blob, emissive); out->o_leaves = blob_put(blob, leaves);
     out->o_uboxes = blob_put(blob, uboxes);
-#ifdef TPT_WIDE_TRIS
-    {   // (double)float is exact: the widened copies carry the same numbers the device would convert per test
-        std::vector<double> dtris;
-        dtris.reserve((size_t)d->n_tris * 9);
-        for (int p = 0; p < d->n_tris; ++p) {
-            const TptTriangle& t = d->tris[p];
-            const float v[9] = {t.normal.x, t.normal.y, t.normal.z, t.e1.x, t.e1.y, t.e1.z, t.e2.x, t.e2.y, t.e2.z};
-            for (float f : v) dtris.push_back((double)f);
-        }
-        out->o_dtris = blob_put(blob, dtris);
-    }
-#endif
     out->n_nodes = (int)hb.nodes.size() / 2;
     out->n_leaves = (int)leaves.size() / 2;
     out->n_uboxes = (int)uboxes.size() / 2;
@@ -265,9 +250,6 @@ static void tpt_scene_view(const SceneBlob& b, const unsigned char* base, const 
     v->n_leaves = b.n_leaves;
     v->uboxes = reinterpret_cast<const float4*>(base + b.o_uboxes);
     v->n_uboxes = b.n_uboxes;
-#ifdef TPT_WIDE_TRIS
-    v->dtris = reinterpret_cast<const double*>(base + b.o_dtris);
-#endif
     v->n_nodes = b.n_nodes; v->n_tris = d->n_tris; v->n_spheres = d->n_spheres;
     v->n_mats = d->n_materials; v->n_objs = d->n_objects; v->n_lnodes = d->n_mesh_nodes; v->n_emissive = d->n_emissive;
     v->width = d->width; v->height = d->height;

@@ -108,41 +108,6 @@ TPT_DEV bool triangle_test(const SceneView& sc, int prim, const DRay& r, int cul
     *t_out = t;
     return true;
 }
-#ifdef TPT_WIDE_TRIS
-// Experiment (off by default; `make NVEXTRA=-DTPT_WIDE_TRIS`): the same test with the triangle's normal, e1 and e2
-// read as doubles that the host widened once (scene_build.h).  Every dot product of the test is formed in double
-// from float operands (Vector.hpp:103-104); widening is exact, so a widened copy holds the very number the
-// conversion would produce and the result is the same bit for bit — what changes is 9 of the 19 f32->f64
-// conversions per test (quarter-rate XU pipe, the busiest pipe of k_shadow_q) becoming three 64-bit loads.
-TPT_DEV double dotd_w(f3 a, const double* b) { return (double)a.x * b[0] + (double)a.y * b[1] + (double)a.z * b[2]; }
-TPT_DEV bool triangle_test_wide(const SceneView& sc, int prim, const DRay& r, int cull, double* t_out) {
-    const double* w = sc.dtris + 9 * prim;          // normal, e1, e2
-    if (cull == 0) {            // CullBack
-        if (dotd_w(r.d, w) > 0) return false;
-    } else if (cull == 1) {     // CullFront
-        if (dotd_w(r.d, w) < 0) return false;
-    }
-    const f3 e2 = mk3(sc.tris[4 * prim + 2]);
-    const f3 e1 = mk3(sc.tris[4 * prim + 1]);
-    const f3 pvec = x_cross(r.d, e2);
-    const double det = dotd_w(pvec, w + 3);
-    if (fabs(det) < (double)TPT_EPSILON) return false;
-    const double det_inv = 1. / det;
-    const f3 tvec = x_sub(r.o, mk3(sc.tris[4 * prim]));
-    const double u = dotd(tvec, pvec) * det_inv;
-    if (u < 0 || u > 1) return false;
-    const f3 qvec = x_cross(tvec, e1);
-    const double v = dotd(r.d, qvec) * det_inv;
-    if (v < 0 || u + v > 1) return false;
-    const double t = dotd_w(qvec, w + 6) * det_inv;
-    if (t < 0.0) return false;
-    *t_out = t;
-    return true;
-}
-#define TPT_TRIANGLE_TEST triangle_test_wide
-#else
-#define TPT_TRIANGLE_TEST triangle_test
-#endif
 
 // SolveQuadratic (SampleHelperFunctions.cpp:4-18) + Sphere::GetIntersection (Sphere.cpp:4-41).
 TPT_DEV bool sphere_test(const SceneView& sc, int sphere, const DRay& r, int cull, float* t_out) {
@@ -198,7 +163,7 @@ TPT_DEV void closest_hit_range(const SceneView& sc, const DRay& r, int cull, int
             double t = 0.0;
             bool ok;
             if (prim < sc.n_tris) {
-                ok = TPT_TRIANGLE_TEST(sc, prim, r, cull, &t);
+                ok = triangle_test(sc, prim, r, cull, &t);
             } else {
                 float ts = 0.0f;
                 ok = sphere_test(sc, prim - sc.n_tris, r, cull, &ts);
@@ -241,7 +206,7 @@ TPT_DEV void settle_candidate(const SceneView& sc, const DRay& r, int cull, int 
     double t = 0.0;
     bool ok;
     if (prim < sc.n_tris) {
-        ok = TPT_TRIANGLE_TEST(sc, prim, r, cull, &t);
+        ok = triangle_test(sc, prim, r, cull, &t);
     } else {
         float ts = 0.0f;
         ok = sphere_test(sc, prim - sc.n_tris, r, cull, &ts);
@@ -643,7 +608,7 @@ TPT_DEV void object_intersect_dual(const SceneView& sc, int obj, const DRay& r, 
         i = in ? i + 1 : __float_as_int(n1.w);
         if (in && prim >= 0) {
             double t = 0.0;
-            if (TPT_TRIANGLE_TEST(sc, prim, r, 2, &t)) {
+            if (triangle_test(sc, prim, r, 2, &t)) {
                 if (bn < 0 || tn > t) { bn = prim; tn = t; }
                 const bool accepted = !(dotd(r.d, mk3(sc.tris[4 * prim + 3])) > 0);      // CullBack, Triangle.cpp:80-83
                 if (accepted && (bc < 0 || tc > t)) { bc = prim; tc = t; }
@@ -697,7 +662,7 @@ TPT_DEV bool shadow_check(const SceneView& sc, f3 from, f3 to, int cull, bool pr
             bool ok;
             if (prim < sc.n_tris) {
                 double t = 0.0;
-                ok = TPT_TRIANGLE_TEST(sc, prim, r, cull, &t);
+                ok = triangle_test(sc, prim, r, cull, &t);
                 tf = (float)t;
             } else {
                 ok = sphere_test(sc, prim - sc.n_tris, r, cull, &tf);
