@@ -12,21 +12,30 @@ render of that frame: 784*784*16 = 9 834 496 samples.  The metric is Msamples/s 
   e2e        the same metric through the C ABI call a host program makes (tpt_scene_create from a
              HOST scene description + tpt_render into a HOST buffer): host->device copies of the
              scene arrays and the device->host copy of the frame are inside the timed region.
-  roofline   traversal kernels (extend + shadow): algorithmic bytes per ray (1.16 KB
-             for this scene/mode) x rays traced / summed CUDA-event launch time, against the measured
-             HBM copy bandwidth of MEASURED_PEAKS.json.  The scene is a few KB and lives in shared
-             memory, so these are instruction-bound kernels and the fraction is not a DRAM fraction (it
-             exceeds 1); `traffic` is the measured DRAM bytes per launch (profiles/traffic.json, ncu).
-  ceilings   SURVEY.md 8(d)'s other two: the traversal figure against the L2 read bandwidth measured live
-             (tpt_probe_read_bandwidth over a 48 MB buffer) and the DRAM bytes of the WHOLE step (ncu, all
-             kernels, profiles/traffic.json) per second against the HBM peak.
-  cpu_baseline  the compiled reference (oracle/_ref, kind "reference") or the restatement
-             (oracle/liboracle.so, kind "port") on all host cores for a bounded sample (2 spp of the
-             same frame), rank 0, N = 1 only.
+  roofline   the resource that binds the step: instruction ISSUE.  The scene (5.7 KB) lives in shared memory, so
+             no kernel of the step is bound by HBM or L2 bandwidth (the algorithmic-bytes figure of SURVEY.md 8(d)
+             exceeds the HBM peak: see `ceilings`).  achieved = warp instructions of one step (ncu
+             smsp__inst_executed.sum over every launch of the frame, profiles/step_counters.json) / the live step
+             time; peak = warp instructions/s of independent FFMA chains measured live on this GPU
+             (tpt_probe_fma_throughput: one instruction per scheduler per cycle, 148 SMs x 4 x clock).  Beside it
+             `lane_efficiency` (thread instructions / 32 x warp instructions), the fp32 FLOP/s of the step against
+             the probe's fp32 rate, and per kernel: live CUDA-event time, issue fraction, lanes, DRAM and L2 GB/s.
+             `hbm` is the same accounting for the kernel that moves the most DRAM bytes (k_shade: 324 B of slot
+             state per active slot and iteration, algorithmic) against the measured HBM peak.
+  ceilings   SURVEY.md 8(d)'s three: traversal algorithmic bytes/s against measured L2 and HBM read bandwidth
+             (tpt_probe_read_bandwidth), and the DRAM bytes of the WHOLE step (ncu) per second against the HBM peak.
+  cpu_baseline  the compiled reference (oracle/_ref, kind "reference") or the restatement (oracle/liboracle.so,
+             kind "port") on all host cores rendering THE SAME frame at the same 16 spp once (after a 1-spp
+             warm-up), rank 0, N = 1 only.
+  strong     (N > 1) the FIXED job of the workload — one 784x784 frame at 16 spp — shared by samples (16/N spp per
+             GPU, hashed streams, one NCCL reduce): ms, speed-up against one GPU rendering it alone in the same
+             run, and what limits it.  Also the 4K-shaped job (Cornell-Occlusion 1920x1080, tile x spp).
 
 Multi-GPU (N > 1, one process per GPU): weak scaling — every rank renders the full frame at 16 spp
 with its own streams (TPT_SEED_SPLIT), the partial [radiance|splat] buffers are summed with one
-NCCL reduce over NVLink and merged on rank 0; value = N * samples / max-over-ranks time.
+NCCL reduce over NVLink and merged on rank 0; value = N * samples / max-over-ranks time.  e2e at N > 1 is
+the whole multi-GPU call by the wall clock between barriers: scene upload on every rank, render, reduce,
+merge, device->host copy of the frame on rank 0.
 """
 import argparse
 import json
@@ -44,7 +53,9 @@ SAMPLES_PER_STEP = W * H * SPP
 # reference-semantics visits per scene ray for Cornell-Standard BDPT:
 # 27.5 nodes x 32 B + 3.56 primitives x 64 B + 48 B ray/hit record
 BYTES_PER_RAY = 27.5 * 32 + 3.56 * 64 + 48
-CPU_SAMPLE_SPP = 2
+CPU_SAMPLE_SPP = SPP          # the reference arm renders the same 16 spp as the GPU arm (same_config)
+# slot state k_shade loads + stores per active slot and iteration: the algorithmic DRAM bytes
+SHADE_STATE_BYTES = 144 + 180
 
 
 def measured_peaks():
@@ -61,6 +72,17 @@ def measured_traffic():
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             return json.load(f)["traversal_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+def step_counters():
+    """Per-kernel sums over ONE step of the workload, from an ncu pass over every launch of a frame
+    (profiles/step_counters.json, written by tools/ncu_step_counters.py): warp / thread instructions, fp32 flops,
+    DRAM and L2 bytes.  None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "step_counters.json")) as f:
+            return json.load(f)
     except Exception:
         return None
 
@@ -134,8 +156,8 @@ class quiet_stdout:
         os.close(self.null)
 
 
-def cpu_baseline(spp=CPU_SAMPLE_SPP, threads=None):
-    """The reference's CPU renderer on this box's host cores for a bounded sample of the workload."""
+def cpu_baseline(spp=CPU_SAMPLE_SPP, threads=None, warm=False):
+    """The reference's CPU renderer on this box's host cores: the workload's frame at `spp` samples per pixel."""
     from oracle import bindings as B
     import tpt_b200 as T
     threads = threads or os.cpu_count() or 1
@@ -148,31 +170,49 @@ def cpu_baseline(spp=CPU_SAMPLE_SPP, threads=None):
             hs = T.HostScene(SCENE, W, H)
             chk = B.oracle_scene(B.SceneDesc.from_buffer_copy(bytes(hs.desc)))
             kind = "port"
+        if warm:
+            chk.render(T.MODES[MODE], 1, threads, W, H)        # page in the library, start the thread pool's pages
         _, rays, sec = chk.render(T.MODES[MODE], spp, threads, W, H)
     return {"value": W * H * spp / sec / 1e6, "unit": "Msamples/s", "cores": threads, "kind": kind,
             "sample": "%s %dx%d %s %d spp (%.2f s, reference 'Rays' %d)" % (SCENE, W, H, MODE, spp, sec, rays),
             "seconds": sec}
 
 
+def workload_config():
+    """`config` of BOTH arms (the driver compares them): the workload and nothing arm-specific."""
+    return {"workload": "Cornell-Standard %dx%d BDPT %d spp" % (W, H, SPP), "scene": SCENE, "mode": MODE,
+            "width": W, "height": H, "spp": SPP,
+            "cache": "GPU arm: the working set of a step (path store %.0f MB) exceeds the 126 MB L2, no flush needed"
+                     % (W * H * 3 * 32 * 48 / 1e6)}
+
+
+REFERENCE_BUDGET_S = 330.0     # the reference arm stops taking steps once it would run past this
+
+
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation, all host threads, same config."""
+    """--impl reference: the reference's own CPU implementation (Renderer.cpp:32-114 compiled from /root/reference into
+    oracle/_ref), all host threads, the SAME frame at the same 16 spp per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
     for _ in range(args.warmup):
-        cpu_baseline(1, threads)
+        cpu_baseline(1, threads)             # warm-up steps page the library and the scene in: 1 spp is enough
     t = 0.0
     last = None
+    done = 0
     for _ in range(args.steps):
         last = cpu_baseline(CPU_SAMPLE_SPP, threads)
         t += last["seconds"]
-    value = W * H * CPU_SAMPLE_SPP * args.steps / t / 1e6
+        done += 1
+        if done >= 3 and t + t / done > REFERENCE_BUDGET_S:
+            break                            # keep the arm within a few minutes on a small host
+    value = W * H * CPU_SAMPLE_SPP * done / t / 1e6
     line = {"impl": "reference", "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
-            "config": {"workload": "Cornell-Standard %dx%d BDPT %d spp" % (W, H, SPP), "scene": SCENE,
-                       "step": "bounded sample: %d spp of the frame on the host CPU" % CPU_SAMPLE_SPP},
+            "steps": done, "steps_requested": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / done,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
+            "config": workload_config(),
+            "step": "the whole frame at %d spp on the host CPU, %d threads (Renderer.cpp:76-114)" % (CPU_SAMPLE_SPP, threads),
             "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": threads, "kind": last["kind"],
                              "sample": last["sample"]},
             "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -259,77 +299,183 @@ def main():
     image_mean = out.view(H, W, 3).mean((0, 1)).tolist() if rank == 0 else None
     finite = bool(torch.isfinite(out).all().item()) if rank == 0 else True
 
-    # end to end through the host-buffer C ABI (rank-local; every rank does the same work)
-    host_img = None
+    # ---- end to end: what a host program pays for one frame, by the wall clock -----------------------------------
+    # N = 1: tpt_scene_create from the HOST description (H2D of the flat scene arrays) + tpt_render into a pinned HOST
+    # frame (kernels + D2H).  N > 1: the whole multi-GPU call between barriers — scene upload on every rank, this
+    # rank's share, ONE NCCL reduce, merge and D2H of the frame on rank 0.
     e2e_steps = max(2, min(args.steps, 5))
     scene_bytes = 0
     d = hs.desc
     for cnt, size in ((d.n_objects, 48), (d.n_top_nodes, 40), (d.n_mesh_nodes, 40), (d.n_tris, 76), (d.n_spheres, 24),
                       (d.n_materials, 72), (d.n_emissive, 4)):
         scene_bytes += cnt * size
-    t_e2e = 0.0
     pinned = T.PinnedImage(H, W)                             # page-locked frame the D2H copy lands in
+    pinned_t = torch.from_numpy(pinned.array).view(-1)
+    t_e2e = 0.0
     for i in range(e2e_steps + 1):
         barrier()
         t0 = time.perf_counter()
         s2 = T.Scene(hs.desc, device=local_rank)            # H2D: flat scene arrays (one blob)
-        host_img, _ = s2.render(MODE, SPP, out=pinned.array, **kw)   # kernels + D2H of the frame into the host buffer
+        if world == 1:
+            s2.render(MODE, SPP, out=pinned.array, **kw)     # kernels + D2H of the frame into the host buffer
+        else:
+            D.render_frame(s2, MODE, SPP * world, accum, out, strategy="spp", rank=rank, world=world, cuda_stream=stream)
+            if rank == 0:
+                pinned_t.copy_(out, non_blocking=True)       # D2H of the merged frame
+            barrier()
         dt = time.perf_counter() - t0
         s2.close()
-        if i > 0:                                            # first one warms the allocator
-            t_e2e = max(t_e2e, 0.0) + dt
+        if i > 0:                                            # the first one warms the allocator
+            t_e2e += dt
     e2e_ms = torch.tensor([1e3 * t_e2e / e2e_steps], device="cuda")
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_ms.item())
+
+    # ---- strong scaling of the FIXED job (N > 1): the same frame shared by samples, against one GPU alone ----------
+    strong = None
+    if world > 1:
+        strong = {}
+        for tag, sc_name, sw, sh, sspp, strat in (("c2_by_samples", SCENE, W, H, SPP, "spp"),
+                                                  ("c5_shaped_tile_spp", "occlusion", 1920, 1080, SPP, "tile_spp")):
+            if sspp < world:
+                continue
+            if (sc_name, sw, sh) == (SCENE, W, H):
+                sscene, sacc, sout = scene, accum, out
+            else:
+                sscene = T.Scene(sc_name, sw, sh, device=local_rank)
+                sacc = torch.zeros(sscene.accum_floats(), dtype=torch.float32, device="cuda")
+                sout = torch.zeros(sw * sh * 3, dtype=torch.float32, device="cuda")
+
+            def timed(fn, reps):
+                fn()                                         # warm-up: work buffers of this share
+                barrier()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for _ in range(reps):
+                    fn()
+                a1.record()
+                barrier()
+                t = torch.tensor([a0.elapsed_time(a1) / reps], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                return float(t.item())
+
+            def alone():                                     # one GPU renders the whole job; the others wait
+                if rank == 0:
+                    sscene.render_device(MODE, sspp, sacc.data_ptr(), cuda_stream=stream, want_stats=False)
+                    sscene.finalize_device(sacc.data_ptr(), sout.data_ptr(), cuda_stream=stream)
+
+            def shared():
+                D.render_frame(sscene, MODE, sspp, sacc, sout, strategy=strat, rank=rank, world=world, cuda_stream=stream)
+
+            ms1 = timed(alone, 2)
+            msn = timed(shared, 3)
+            stn = D.render_frame(sscene, MODE, sspp, sacc, sout, strategy=strat, rank=rank, world=world, cuda_stream=stream,
+                                 want_stats=True)
+            barrier()
+            share_n = D.plan(strat, rank, world, sspp, sw * sh)
+            strong[tag] = {"job": "%s %dx%d %s %d spp" % (sc_name, sw, sh, MODE, sspp), "share": strat,
+                           "rank0_share": {"spp": share_n.spp, "pixel_sets": share_n.world},
+                           "ms_1gpu": ms1, "ms": msn, "speedup": ms1 / msn, "n_gpus": world,
+                           "launches_per_frame_rank0": int(stn["launches"]),
+                           "limiter": "the dependent launch chain: a frame is %d launches on rank 0 whatever the share (a "
+                                      "sample is a chain of ~11 shade/extend iterations; the strategy kernels of an "
+                                      "iteration follow it); %.1f us per launch" % (int(stn["launches"]), 1e3 * msn / max(1, int(stn["launches"])))}
+            if sscene is not scene:
+                del sacc, sout
+                sscene.close()
+                T.release_cached_memory()
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
         k_ms = st["kernel_ms"]
         trav_ms = k_ms["extend"] + k_ms["shadow"] + k_ms["generate"]
         rays = st["traced_rays"]
-        achieved = rays * BYTES_PER_RAY / (trav_ms * 1e-3) / 1e9 if trav_ms > 0 else 0.0
+        trav_gbs = rays * BYTES_PER_RAY / (trav_ms * 1e-3) / 1e9 if trav_ms > 0 else 0.0
         total_k = sum(k_ms.values())
-        # the traversal kernels against the L2 and HBM ceilings (both measured live with the
-        # library's streaming-read probe), and the DRAM traffic of the whole step against the HBM ceiling
+        step_ms = ms / args.steps
+        # measured ceilings of this GPU, live: L2 / HBM streaming reads, fp32 + issue rate of independent FFMA chains
         l2_gbs = T.probe_read_bandwidth(48 << 20, 40, local_rank)
         hbm_gbs = T.probe_read_bandwidth(4 << 30, 3, local_rank)
+        fma_tflops, issue_peak = T.probe_fma_throughput(1 << 15, local_rank)
         dram = step_dram_bytes()
-        step_ms = ms / args.steps
         ceilings = {
             "l2_read_gbs_measured": l2_gbs, "hbm_read_gbs_measured": hbm_gbs,
-            "traversal_algorithmic_gbs": achieved, "traversal_frac_of_l2": achieved / l2_gbs if l2_gbs else None,
-            "traversal_frac_of_hbm": achieved / peaks["hbm_gbs"],
+            "fp32_tflops_measured": fma_tflops, "issue_gwarp_inst_per_s_measured": issue_peak,
+            "traversal_algorithmic_bytes_per_ray": BYTES_PER_RAY, "traversal_algorithmic_gbs": trav_gbs,
+            "traversal_frac_of_l2": trav_gbs / l2_gbs if l2_gbs else None,
+            "traversal_frac_of_hbm": trav_gbs / peaks["hbm_gbs"],
+            "traversal_dram_bytes_per_launch_ncu": measured_traffic(),
             "step_dram_bytes_ncu": dram,
             "step_dram_gbs": dram / (step_ms * 1e-3) / 1e9 if dram else None,
             "step_dram_frac_of_hbm": dram / (step_ms * 1e-3) / 1e9 / peaks["hbm_gbs"] if dram else None,
-            "note": "scene in shared memory: the traversal kernels read neither L2 nor HBM for it; the step as a "
-                    "whole is bound by instruction issue and HBM latency (profiles/*_ncu_summary.csv)"}
+            "note": "the scene (5.7 KB) is staged in shared memory: the traversal kernels read neither L2 nor HBM for it, so "
+                    "the algorithmic-bytes figure is above the HBM peak and below the L2 one; neither binds"}
+        # the roofline that binds: instruction issue (counts: ncu over every launch of one step, committed profile)
+        sc_ = step_counters()
+        roofline = {"bound": "issue", "achieved": None, "peak": issue_peak, "unit": "Gwarp-inst/s", "frac": None,
+                    "traffic": None, "peak_source": "tpt_probe_fma_throughput, live (148 SMs x 4 schedulers x clock)"}
+        if sc_:
+            tot = sc_["step"]
+            winst, tinst, flops = tot["warp_inst"], tot["thread_inst"], tot["fp32_flops"]
+            achieved = winst / (step_ms * 1e-3) / 1e9
+            kernels = {}
+            live = {"k_generate": "generate", "k_shade": "shade", "k_extend": "extend", "k_expand": "expand",
+                    "k_connect": "connect", "k_shadow_q": "shadow", "k_mis": "mis"}
+            for kname, c in sc_["kernels"].items():
+                if kname not in live or k_ms.get(live[kname], 0) <= 0:
+                    continue
+                t = k_ms[live[kname]] * 1e-3
+                kernels[kname] = {"ms": k_ms[live[kname]], "issue_frac": c["warp_inst"] / t / 1e9 / issue_peak,
+                                  "lanes": c["thread_inst"] / c["warp_inst"], "dram_gbs": c["dram_bytes"] / t / 1e9,
+                                  "l2_gbs": c["l2_bytes"] / t / 1e9, "fp32_tflops": c["fp32_flops"] / t / 1e12}
+            shade = sc_["kernels"].get("k_shade")
+            roofline.update({
+                "achieved": achieved, "frac": achieved / issue_peak,
+                "kernel": "whole step (k_shade 29 % of the kernel time is the largest; three kernels are resident at a time)",
+                "warp_inst_per_step": winst, "lane_efficiency": tinst / (32.0 * winst),
+                "useful_lane_frac": achieved / issue_peak * tinst / (32.0 * winst),
+                "fp32": {"flops_per_step": flops, "achieved_tflops": flops / (step_ms * 1e-3) / 1e12,
+                         "peak_tflops": fma_tflops, "frac": flops / (step_ms * 1e-3) / 1e12 / fma_tflops},
+                "per_kernel_serialised": kernels,
+                "counts_source": "profiles/step_counters.json (%s)" % sc_.get("source", "ncu"),
+                "note": "per-kernel times are CUDA-event times of a serialised run (TPT_FLAG_KERNEL_TIMES); in the timed "
+                        "run the strategy kernels overlap k_shade / k_extend, which is what `frac` of the step shows"})
+            if shade and k_ms.get("shade", 0) > 0:
+                # every slot-iteration of k_shade emits one ray (extension or light start) or retires the slot
+                slot_iters = int(st["extend_rays"]) + W * H
+                algo = SHADE_STATE_BYTES * slot_iters
+                t = k_ms["shade"] * 1e-3
+                roofline["hbm"] = {"bound": "hbm", "kernel": "k_shade (largest DRAM mover: slot state in, slot state + path "
+                                   "vertices out)", "algorithmic_bytes_per_slot_iteration": SHADE_STATE_BYTES,
+                                   "slot_iterations_per_step": slot_iters,
+                                   "achieved": algo / t / 1e9 if algo else None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                   "frac": algo / t / 1e9 / peaks["hbm_gbs"] if algo else None,
+                                   "traffic": shade["dram_bytes"] / max(1, shade["launches"]), "peak_source": peak_src}
+                roofline["traffic"] = shade["dram_bytes"] / max(1, shade["launches"])
+        cfg = workload_config()
         line = {
             "metric": "Msamples/s", "value": world * SAMPLES_PER_STEP * args.steps / ms / 1e3, "unit": "Msamples/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
-            "config": {"workload": "Cornell-Standard %dx%d BDPT %d spp" % (W, H, SPP), "scene": SCENE, "mode": MODE,
-                       "spp_per_gpu": SPP, "pipeline": "wavefront", "seeds": "reference" if world == 1 else "split",
-                       "cache": "working set per step (path store %.0f MB) exceeds the 126 MB L2" %
-                                (W * H * 3 * 32 * 48 / 1e6)},
-            "mrays_per_s": world * rays / (ms / args.steps) / 1e3,
+            "config": cfg,
+            "arm": {"spp_per_gpu": SPP, "pipeline": "wavefront", "seeds": "reference" if world == 1 else "split"},
+            "mrays_per_s": world * rays / step_ms / 1e3,
             "traced_rays_per_step": rays, "ref_rays_per_step": st["ref_rays"],
             "e2e": {"value": world * SAMPLES_PER_STEP / e2e_ms / 1e3, "unit": "Msamples/s",
-                    "h2d_bytes_per_step": scene_bytes, "d2h_bytes_per_step": n3 * 4, "ms_per_step": e2e_ms},
+                    "h2d_bytes_per_step": scene_bytes, "d2h_bytes_per_step": n3 * 4, "ms_per_step": e2e_ms,
+                    "path": "tpt_scene_create + tpt_render (host buffers)" if world == 1 else
+                            "per rank tpt_scene_create + tpt_render_device, one NCCL reduce, tpt_finalize_device + D2H on rank 0, wall clock between barriers"},
             "gpu_launches": int(st["launches"]) * args.steps,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": measured_traffic(), "peak_source": peak_src,
-                         "kernel": "k_extend + k_shadow_q + k_generate (BVH traversal)",
-                         "algorithmic_bytes_per_ray": BYTES_PER_RAY, "rays_per_step": rays,
-                         "kernel_ms_per_step": trav_ms, "share_of_kernel_time": trav_ms / total_k if total_k else None,
-                         "note": "scene (~5 KB) is staged in shared memory: instruction-bound, DRAM traffic ~0"},
+            "roofline": roofline,
             "ceilings": ceilings,
             "kernel_ms_per_step": k_ms, "kernel_launches_per_step": st["kernel_launches"],
             "clocks": clocks, "image_mean_rgb": image_mean, "finite": finite,
         }
+        if strong:
+            line["strong"] = strong
         if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_baseline()
+            cb = cpu_baseline(warm=True)
             cb.pop("seconds", None)
             line["cpu_baseline"] = cb
         sys.stdout.flush()

@@ -201,6 +201,12 @@ int tpt_release_cached_memory(void);
  * B200) measures L2, one well above it measures HBM.  No counterpart in the reference. */
 int tpt_probe_read_bandwidth(int device, size_t bytes, int repeats, double* gb_per_s);
 
+/* Measurement aid for the issue roofline of the render step: independent FFMA chains from a full machine.
+ * Reports the fp32 rate in TFLOP/s and (optionally) the warp-instruction issue rate in G warp-instructions/s —
+ * the ceiling "one instruction per scheduler per cycle" as this GPU sustains it at its clocks.  No counterpart in
+ * the reference. */
+int tpt_probe_fma_throughput(int device, int iters, double* tflops, double* gwarp_inst_per_s);
+
 /* Page-locked host memory for the frame tpt_render writes (a plain malloc'ed buffer works
  * too, through the driver's staging copy).  NULL on failure. */
 void* tpt_host_alloc(size_t bytes);
@@ -255,6 +261,49 @@ size_t tpt_accum_floats(const TptScene* scene);
  * SaveFloatImageToJpg's tonemap (SceneRenderingHelper.cpp:57-66). */
 int tpt_finalize_device(TptScene* scene, const float* d_accum, float* d_out_rgb,
                         uint8_t* d_rgb8, void* stream);
+
+/* ---- one frame on several GPUs of this process ------------------------------------------------
+ *
+ * Replaces the thread fan-out and host-side merge of Renderer::Render (Renderer.cpp:76-114: thread t
+ * renders pixels i = t (mod T) into disjoint framebuffer cells and its own emission buffer, the
+ * emission buffers are summed afterwards) with "a thread is a GPU": one host thread per device
+ * renders its share into its own [radiance | splat] accumulator, ONE sum-reduce over NVLink combines
+ * them on the first device (NCCL, loaded at run time; or a fused peer-memory reduce + merge kernel,
+ * TPT_MULTI_REDUCE=p2p), which merges, tonemaps and copies the frame to the host. */
+
+/* How the frame is shared between the GPUs. */
+enum {
+    TPT_SPLIT_INTERLEAVE = 0, /* pixels i % n == r, all spp, reference seeds: the 1-GPU image (PathTrace bit for bit) */
+    TPT_SPLIT_TILE = 1,       /* the r-th contiguous run of pixels, all spp, reference seeds                            */
+    TPT_SPLIT_SPP = 2,        /* every pixel, spp/n samples per GPU from hashed streams (statistical tier)            */
+    TPT_SPLIT_TILE_SPP = 3    /* tiles until a tile is ~1 Mpixel, then spp groups (BASELINE config 5)                 */
+};
+
+/* The share of GPU `rank` of `world`: fills partition / rank / world / spp / spp_total / seed_mode /
+ * stream of *params and leaves mode, pipeline and flags alone.  Pure host logic (no device needed). */
+int tpt_multi_plan(int split, int rank, int world, int spp_total, long long npix, TptRenderParams* params);
+
+typedef struct TptMulti TptMulti;
+
+/* The scene on n_gpus devices (devices[] = NULL: 0 .. n_gpus-1), an accumulator and a stream on each,
+ * the communicator.  Keep it for as many frames as needed: communicator set-up is not per frame. */
+int tpt_multi_create(const TptSceneDesc* desc, int n_gpus, const int* devices, TptMulti** out);
+int tpt_multi_destroy(TptMulti* multi);
+int tpt_multi_gpus(const TptMulti* multi);
+/* "nccl", "p2p" or "none" (one GPU): the exchange step this handle uses. */
+const char* tpt_multi_exchange(const TptMulti* multi);
+
+/* One frame.  params: mode, spp (= total samples per pixel of the frame; spp_total if set), pipeline,
+ * flags; the sharing fields are filled per GPU from `split`.  out_rgb (width*height*3 floats) and
+ * out_rgb8 (width*height*3 bytes, tonemapped like SaveFloatImageToJpg) are host buffers, either may
+ * be NULL.  stats: counters summed over the GPUs, device_ms = the slowest share, d2h_ms = merge +
+ * device->host copies. */
+int tpt_multi_render(TptMulti* multi, const TptRenderParams* params, int split, float* out_rgb,
+                     uint8_t* out_rgb8, TptStats* stats);
+
+/* tpt_multi_create + tpt_multi_render + tpt_multi_destroy. */
+int tpt_render_multi(const TptSceneDesc* desc, const TptRenderParams* params, int n_gpus, int split,
+                     float* out_rgb, uint8_t* out_rgb8, TptStats* stats);
 
 /* ---- per-function entry points (parity tests against the oracle) --------- */
 

@@ -34,6 +34,13 @@ void        tpth_scene_destroy(TpthScene* scene);
 int tpth_render(TpthScene* scene, const char* output_file, int spp, int bdpt, int pt_full,
                 int device, float* out_rgb, double* seconds);
 
+/* The same on `gpus` CUDA devices of this process that share the frame (tpt_render_multi, include/tpt.h): what
+ * thread_count is to the reference (Renderer.cpp:76-114: fan-out over pixels, host-side merge), one level up.
+ * split: TPT_SPLIT_* (0 = pixel interleave with the reference's seeds).  ref_rays (may be NULL): the reference's
+ * "Rays" figure (PathTracer.cpp:126 / BDPT.cpp:288) summed over the GPUs. */
+int tpth_render_gpus(TpthScene* scene, const char* output_file, int spp, int bdpt, int pt_full, int gpus, int split,
+                     float* out_rgb, double* seconds, unsigned long long* ref_rays);
+
 /* SaveFloatImageToJpg (reference SceneRenderingHelper.cpp:57-70) for a linear-float frame of
  * width*height*3 floats: clamp, pow 0.6, *255 truncated, then by extension .jpg/.jpeg (baseline JPEG,
  * quality 100, 4:4:4 like the reference's stb call), .ppm, .pfm/.f32 (raw floats).  0 on success. */

@@ -28,7 +28,7 @@ def test_libtpt_exports_every_declared_symbol(tpt):
 def test_libtpt_host_exports_every_declared_symbol(tpt):
     h = tpt.host()
     names = [n for n in declared("tpt_host.h") if n.startswith("tpth_")]
-    assert len(names) == 6
+    assert len(names) == 7
     for n in names:
         assert hasattr(h, n), "libtpt_host.so does not export " + n
 

@@ -16,7 +16,7 @@ import sys
 import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB = os.path.join(ROOT, "toypathtracer-games101-assignment7_b200", "libtpt.so")
+LIB = os.environ.get("TPT_LIB") or os.path.join(ROOT, "toypathtracer-games101-assignment7_b200", "libtpt.so")
 
 
 def sass_lines(kernel):

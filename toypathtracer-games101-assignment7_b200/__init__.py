@@ -304,6 +304,67 @@ class Scene:
                                          C.c_void_p(d_rgb8_ptr or 0), C.c_void_p(cuda_stream or 0)))
 
 
+SPLIT_INTERLEAVE, SPLIT_TILE, SPLIT_SPP, SPLIT_TILE_SPP = 0, 1, 2, 3
+SPLITS = {"interleave": SPLIT_INTERLEAVE, "tile": SPLIT_TILE, "spp": SPLIT_SPP, "tile_spp": SPLIT_TILE_SPP}
+
+
+def multi_plan(split, rank, world, spp_total, npix):
+    """tpt_multi_plan: the share of GPU `rank` of `world` as the C ABI plans it (host logic, no device needed).
+    Returns the RenderParams fields that depend on the rank."""
+    if isinstance(split, str):
+        split = SPLITS[split]
+    p = RenderParams()
+    _check(lib().tpt_multi_plan(C.c_int(split), C.c_int(rank), C.c_int(world), C.c_int(spp_total), C.c_longlong(npix), C.byref(p)))
+    return dict(partition=p.partition, rank=p.rank, world=p.world, spp=p.spp, spp_total=p.spp_total,
+                seed_mode=p.seed_mode, stream=p.stream)
+
+
+class MultiScene:
+    """tpt_multi_*: one frame on several GPUs of THIS process — a host thread per device, one reduce over NVLink
+    (NCCL loaded at run time, or the fused peer-memory merge with TPT_MULTI_REDUCE=p2p), merge on the first device."""
+
+    def __init__(self, name_or_desc, width=784, height=784, gpus=1, devices=None, models_dir=None):
+        self._host_scene = None
+        if isinstance(name_or_desc, str):
+            self._host_scene = HostScene(name_or_desc, width, height, models_dir)
+            desc = self._host_scene.desc
+        else:
+            desc = name_or_desc
+        self.width, self.height, self.gpus = desc.width, desc.height, gpus
+        dev = (C.c_int * gpus)(*devices) if devices is not None else None
+        handle = C.c_void_p()
+        _check(lib().tpt_multi_create(C.byref(desc), C.c_int(gpus), dev, C.byref(handle)))
+        self.h = handle
+        lib().tpt_multi_exchange.restype = C.c_char_p
+        self.exchange = lib().tpt_multi_exchange(self.h).decode()
+
+    def render(self, mode, spp, split="interleave", want_rgb8=False, pipeline=PIPE_WAVEFRONT, flags=0):
+        """(image[h,w,3] float32, rgb8[h,w,3] uint8 or None, stats dict)"""
+        if isinstance(mode, str):
+            mode = MODES[mode]
+        if isinstance(split, str):
+            split = SPLITS[split]
+        p = RenderParams(mode, spp, spp, SEED_REF, PART_ALL, 0, 1, pipeline, flags, 0)
+        out = np.empty((self.height, self.width, 3), np.float32)
+        rgb8 = np.empty((self.height, self.width, 3), np.uint8) if want_rgb8 else None
+        st = Stats()
+        _check(lib().tpt_multi_render(self.h, C.byref(p), C.c_int(split), _p(out), _p(rgb8), C.byref(st)))
+        return out, rgb8, st.as_dict()
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().tpt_multi_destroy(self.h)
+            self.h = None
+        if self._host_scene is not None:
+            self._host_scene.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class PinnedImage:
     """A height x width x 3 float32 frame in page-locked host memory (tpt_host_alloc)."""
 
@@ -331,6 +392,13 @@ def probe_read_bandwidth(nbytes, repeats=20, device=0):
     out = C.c_double(0.0)
     _check(lib().tpt_probe_read_bandwidth(C.c_int(device), C.c_size_t(nbytes), C.c_int(repeats), C.byref(out)))
     return out.value
+
+
+def probe_fma_throughput(iters=4096, device=0):
+    """tpt_probe_fma_throughput: (fp32 TFLOP/s, G warp-instructions/s) of independent FFMA chains on the whole GPU."""
+    tf, gi = C.c_double(0.0), C.c_double(0.0)
+    _check(lib().tpt_probe_fma_throughput(C.c_int(device), C.c_int(iters), C.byref(tf), C.byref(gi)))
+    return tf.value, gi.value
 
 
 def rng(seed, n):

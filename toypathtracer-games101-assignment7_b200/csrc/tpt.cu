@@ -152,6 +152,51 @@ extern "C" int tpt_probe_read_bandwidth(int device, size_t bytes, int repeats, d
     return TPT_OK;
 }
 
+// ---- instruction-issue / fp32 probe (tpt_probe_fma_throughput) --------------------------------------
+// 16 independent FFMA chains per thread, 8 resident 256-thread blocks per SM: every scheduler has an FFMA to issue
+// every cycle, so the measured rate is both the fp32 peak (2 flops per lane) and the warp-instruction issue peak
+// (one instruction per scheduler per cycle) the step's issue roofline is quoted against.
+__global__ void __launch_bounds__(256) k_probe_fma(int iters, float seed, float* sink) {
+    float a[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = seed + (float)k + (float)threadIdx.x * 1e-3f;
+    const float m = 1.0000001f, c = 1e-7f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) a[k] = __fmaf_rn(a[k], m, c);
+    }
+    float acc = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc += a[k];
+    if (acc == 1.2345e-30f) *sink = acc;
+}
+extern "C" int tpt_probe_fma_throughput(int device, int iters, double* tflops, double* gwarp_inst_per_s) {
+    if (!tflops || iters < 1) { tpt_set_error("tpt_probe_fma_throughput: bad arguments"); return TPT_ERR_INVALID; }
+    int rc = require_device(device);
+    if (rc != TPT_OK) return rc;
+    cudaDeviceProp prop;
+    TPT_CUDA(cudaGetDeviceProperties(&prop, device));
+    float* sink = static_cast<float*>(tpt_dev_alloc(16));
+    if (!sink) return TPT_ERR_OOM;
+    const int grid = prop.multiProcessorCount * 8;
+    cudaEvent_t e0, e1;
+    TPT_CUDA(cudaEventCreate(&e0)); TPT_CUDA(cudaEventCreate(&e1));
+    k_probe_fma<<<grid, 256>>>(iters / 8 + 1, 1.0f, sink);      // warm-up: clocks
+    TPT_CUDA(cudaEventRecord(e0));
+    k_probe_fma<<<grid, 256>>>(iters, 1.0f, sink);
+    TPT_CUDA(cudaEventRecord(e1));
+    TPT_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.0f;
+    TPT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    tpt_dev_free(sink);
+    TPT_CUDA(cudaGetLastError());
+    const double ffma = (double)grid * 256.0 * 16.0 * iters;    // thread-level FFMAs
+    *tflops = 2.0 * ffma / (ms * 1e-3) / 1e12;
+    if (gwarp_inst_per_s) *gwarp_inst_per_s = ffma / 32.0 / (ms * 1e-3) / 1e9;
+    return TPT_OK;
+}
+
 // ------------------------------------------------------------------ scene builder
 namespace {
 

@@ -198,7 +198,7 @@ TPT_DEV void closest_hit_range(const SceneView& sc, const DRay& r, int cull, int
 // nodes BVH.cpp:103-143 visits, and the strict first-visited-wins update is applied in the
 // recorded order, so the winner is the reference's by construction.
 #ifndef TPT_CAND_MAX
-#define TPT_CAND_MAX 12           /* per-thread column of recorded candidates (>= TPT_WALK_FLUSH, TPT_SHADOW_FLUSH) */
+#define TPT_CAND_MAX 2            /* per-thread column of recorded candidates (>= TPT_WALK_FLUSH, TPT_SHADOW_FLUSH) */
 #endif
 #define TPT_CAND_BYTES(threads) ((threads) * TPT_CAND_MAX * 4)
 

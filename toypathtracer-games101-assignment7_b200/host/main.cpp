@@ -34,7 +34,10 @@ int main(int argc, char** argv) {
         return 1;
     }
     double sec = 0;
-    const int rc = tpth_render(s, out.c_str(), spp, bdpt, full, device, nullptr, &sec);
+    const int gpus = Arg(argc, argv, "-gpus", 1);       // GPUs sharing the frame; -split 0 interleave 1 tile 2 spp 3 tile x spp
+    const int split = Arg(argc, argv, "-split", 0);
+    const int rc = gpus > 1 ? tpth_render_gpus(s, out.c_str(), spp, bdpt, full, gpus, split, nullptr, &sec, nullptr)
+                            : tpth_render(s, out.c_str(), spp, bdpt, full, device, nullptr, &sec);
     if (rc == 0) std::printf("rendered %s %dx%d spp %d in %.3f s -> %s\n", scene.c_str(), w, h, spp, sec, out.c_str());
     tpth_scene_destroy(s);
     return rc;

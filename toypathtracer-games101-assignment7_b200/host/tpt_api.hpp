@@ -292,6 +292,11 @@ public:
 
     bool pt_full = false;   // PathTrace without the stray `break` (README PT images)
     int device = 0;
+    // GPUs of this process that share the frame (the reference's thread_count, one level up: Renderer.cpp:76-114);
+    // TPT_GPUS in the environment overrides it.  split: TPT_SPLIT_* of include/tpt.h (0 = pixel interleave with the
+    // reference's seeds: the one-GPU image)
+    int gpus = 1;
+    int split = 0;
     bool quiet = false;
     // filled by Render(): radiance + merged splats, width*height Vector3f
     std::vector<Vector3f> framebuffer;

@@ -339,11 +339,10 @@ void Renderer::Render(std::string outputFileName, const Scene& scene, int spp, i
         return;
     }
     TptSceneDesc desc = flat.desc();
-    TptScene* dev = nullptr;
-    if (tpt_scene_create(&desc, device, &dev) != TPT_OK) {
-        std::cerr << "Renderer::Render: " << tpt_last_error() << std::endl;
-        return;
-    }
+    // thread_count threads -> gpus devices: Renderer::gpus, or TPT_GPUS in the environment (an unchanged main.cpp has
+    // no member to set), each rendering its share of the frame; one reduce over NVLink merges them (tpt_render_multi)
+    int ngpu = gpus;
+    if (const char* env = std::getenv("TPT_GPUS")) ngpu = std::max(1, std::atoi(env));
     if (!quiet) std::cout << "SPP: " << spp << "\n";
     TptRenderParams p;
     std::memset(&p, 0, sizeof p);
@@ -353,10 +352,17 @@ void Renderer::Render(std::string outputFileName, const Scene& scene, int spp, i
     TptStats st;
     std::memset(&st, 0, sizeof st);
     std::vector<float> rgb((size_t)scene.width * scene.height * 3);
+    int rc;
     auto start = std::chrono::system_clock::now();
-    int rc = tpt_render(dev, &p, rgb.data(), &st);
+    if (ngpu > 1) {
+        rc = tpt_render_multi(&desc, &p, ngpu, split, rgb.data(), nullptr, &st);
+    } else {
+        TptScene* dev = nullptr;
+        rc = tpt_scene_create(&desc, device, &dev);
+        if (rc == TPT_OK) rc = tpt_render(dev, &p, rgb.data(), &st);
+        tpt_scene_destroy(dev);
+    }
     auto stop = std::chrono::system_clock::now();
-    tpt_scene_destroy(dev);
     if (rc != TPT_OK) {
         std::cerr << "Renderer::Render: " << tpt_last_error() << std::endl;
         return;
@@ -483,6 +489,8 @@ int tpth_save_image(const float* rgb, int width, int height, const char* path) {
 }
 
 // Renderer::Render on a built scene; returns 0 on success.  out_rgb may be NULL.
+int tpth_render_gpus(TpthScene* h, const char* outputFile, int spp, int bdpt, int ptFull, int gpus, int split,
+                     float* out_rgb, double* seconds, unsigned long long* refRays);
 int tpth_render(TpthScene* h, const char* outputFile, int spp, int bdpt, int ptFull, int device,
                 float* out_rgb, double* seconds) {
     Renderer r;
@@ -496,6 +504,25 @@ int tpth_render(TpthScene* h, const char* outputFile, int spp, int bdpt, int ptF
             out_rgb[3 * i] = r.framebuffer[i].x; out_rgb[3 * i + 1] = r.framebuffer[i].y; out_rgb[3 * i + 2] = r.framebuffer[i].z;
         }
     if (seconds) *seconds = r.seconds;
+    return 0;
+}
+
+// The same on `gpus` devices of this process (Renderer::gpus / Renderer::split); refRays: the reference's "Rays" figure.
+int tpth_render_gpus(TpthScene* h, const char* outputFile, int spp, int bdpt, int ptFull, int gpus, int split,
+                     float* out_rgb, double* seconds, unsigned long long* refRays) {
+    Renderer r;
+    r.pt_full = ptFull != 0;
+    r.gpus = gpus;
+    r.split = split;
+    r.quiet = true;
+    r.Render(outputFile ? outputFile : "", *h->scene, spp, 1, bdpt != 0);
+    if (r.framebuffer.empty()) return 1;
+    if (out_rgb)
+        for (size_t i = 0; i < r.framebuffer.size(); ++i) {
+            out_rgb[3 * i] = r.framebuffer[i].x; out_rgb[3 * i + 1] = r.framebuffer[i].y; out_rgb[3 * i + 2] = r.framebuffer[i].z;
+        }
+    if (seconds) *seconds = r.seconds;
+    if (refRays) *refRays = r.refRays;
     return 0;
 }
 
