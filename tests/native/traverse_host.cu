@@ -218,6 +218,7 @@ template <class T, class U> __host__ __device__ inline T hm_atomic_or(T* p, U v)
 #define blockIdx hm_block_idx()
 #define gridDim hm_grid_dim()
 #define atomicAdd hm_atomic_add
+#define __threadfence() ((void)0)
 #define atomicOr hm_atomic_or
 
 #include "integrators.cuh"

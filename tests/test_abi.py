@@ -83,7 +83,7 @@ def test_read_bandwidth_probe(tpt):
 def test_device_code_is_sm100a_with_the_documented_resources(tpt):
     """Static view of libtpt.so's device code (cuobjdump, no GPU needed): built for sm_100a only; the registers /
     local memory of the wavefront kernels are the launch-bound choices DESIGN.md section 5 quotes (64 registers =
-    4 CTAs of 256 threads per SM, k_shade 80 = 3, k_pt_shade 128 = 2; spills of a few words at most); the scene
+    4 CTAs of 256 threads per SM, k_path 85 = 3, k_pt_shade 128 = 2; spills of a few words at most); the scene
     blob is staged by a bulk asynchronous copy (UBLKCP) and every loop kernel is a programmatic dependent launch
     (griddepcontrol.wait / launch_dependents = ACQBULK / PREEXIT)."""
     import shutil
@@ -100,7 +100,7 @@ def test_device_code_is_sm100a_with_the_documented_resources(tpt):
         short = re.search(r"(k_[a-z_]+)(?:E|I)", name)
         if short:
             usage.setdefault(short.group(1), []).append((int(reg), int(stack)))
-    limits = {"k_shade": 80, "k_extend": 64, "k_expand": 64, "k_connect": 64, "k_shadow_q": 64, "k_mis": 64,
+    limits = {"k_path": 88, "k_expand": 64, "k_connect": 64, "k_shadow_q": 64, "k_mis": 64,
               "k_pt_shade": 128, "k_pt_extend": 64, "k_pt_shadow": 64}
     for k, lim in limits.items():
         assert k in usage, "kernel %s not found in libtpt.so" % k

@@ -149,4 +149,4 @@ def test_batch_R_at_full_size_against_the_compiled_reference(tpt, scene):
         assert len(bad) == 0, "%s: %d primitive ids differ in [%d, %d), first %s" % (scene, len(bad), a, a + step, bad[:5] + a)
         assert (t[sl].view(np.uint64) == ot.view(np.uint64)).all()
         assert (coords[sl].view(np.uint32) == oc.view(np.uint32)).all()
-    assert 0.9 < (prim >= 0).mean() <= 1.0                    # origins inside a closed box: nearly every ray hits
+    assert 0.5 < (prim >= 0).mean() < 0.8                      # the box is open towards the camera; CullFront rays see the walls' fronts

@@ -40,6 +40,21 @@ def test_readme_images(tpt, scene, mode, spp):
     s.close()
 
 
+def test_bdpt_samples_without_strategy_room_wait_and_nothing_is_lost(tpt, monkeypatch):
+    """TPT_WF_PAIR_CAP shrinks the strategy buffer: completing samples find their block's share full, leave a void
+    record, wait and complete in a later round (INFO_WAIT; wavefront.cu k_path phase 2b, k_expand).  The frame and
+    the counters are those of the roomy run — and of the per-pixel validation kernel."""
+    s = gpu_scene("standard", 96, 96)
+    ref, st0 = s.render("bdpt", 4)
+    monkeypatch.setenv("TPT_WF_PAIR_CAP", "2048")
+    img, st = s.render("bdpt", 4)
+    monkeypatch.delenv("TPT_WF_PAIR_CAP")
+    s.close()
+    assert st["samples"] == st0["samples"] == 96 * 96 * 4 and st["ref_rays"] == st0["ref_rays"]
+    assert st["launches"] > 1.5 * st0["launches"]                  # it did have to wait
+    assert np.isfinite(img).all() and np.allclose(img, ref, rtol=2e-4, atol=2e-5), float(np.abs(img - ref).max())
+
+
 def test_pt_is_deterministic_and_pipelines_agree(tpt):
     s = gpu_scene("standard", 256, 256)
     a, _ = s.render("pt_full", 8)

@@ -492,6 +492,16 @@ def test_bdpt_wavefront_is_the_pixel_loop(wfmirror, scene, spp, sms):
     assert ref.mean() > 0.05
 
 
+def test_bdpt_samples_that_find_no_strategy_room_wait_a_round(wfmirror, monkeypatch):
+    """TPT_WF_PAIR_CAP shrinks the strategy buffer so that most completing samples find their block's share full: they
+    leave a void record (k_expand invalidates its range), wait (INFO_WAIT) and complete in a later round.  Same frame,
+    same sample and vertex counts as the pixel loop — nothing is dropped, nothing is counted twice."""
+    monkeypatch.setenv("TPT_WF_PAIR_CAP", "512")           # 272 records per 256-slot block: one or two samples per round
+    img, ref = wavefront_vs_pixel_loop(wfmirror, "standard", "bdpt", 2, 32)
+    assert np.isfinite(img).all()
+    assert np.allclose(img, ref, rtol=2e-4, atol=2e-5), float(np.abs(img - ref).max())
+
+
 def test_wavefront_experiments_render_the_same_frames(wf_experiment):
     """A compile-time experiment must not change a bit of the PathTrace frames, large scene and small."""
     for scene, mode, spp in (("bunny", "pt_full", 3), ("standard", "pt_full", 2)):

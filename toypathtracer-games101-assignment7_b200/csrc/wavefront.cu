@@ -2,13 +2,13 @@
 //
 // One SLOT per pixel keeps that pixel's XorShift32 stream, so the spp of a pixel
 // run one after another exactly as FillBufferThread draws them (Renderer.cpp:42-53)
-// while all pixels advance in parallel.  Every iteration of the host loop runs
+// while all pixels advance in parallel.  Every round of the host loop runs
 //
-//   k_shade    per active slot: finish the vertex its last ray produced (area pdf,
-//              Russian roulette, throughput), move through the sample's state
-//              machine (camera subpath -> light subpath -> sample complete -> next
-//              sample) and BSDF-sample the next direction; emits one ray per slot
-//   k_extend   closest hit for those rays (persistent threads, scene in shared memory)
+//   k_path     per active slot, PATH_ITERS steps with the slot's state in registers: finish the
+//              vertex the last ray produced (area pdf, Russian roulette, throughput), move through
+//              the sample's state machine (camera subpath -> light subpath -> sample complete ->
+//              next sample), BSDF-sample the next direction and find that ray's closest hit
+//              (scene in shared memory, the warp's 32 rays tested together)
 //   k_expand   completed samples -> one work item per strategy (s,t)
 //   k_connect  unweighted contribution of each strategy; queues a shadow ray or
 //              passes the item straight to the MIS queue
@@ -18,7 +18,7 @@
 //
 // Queues are compacted with warp ballots + one atomic per warp (wf_append); a slot
 // that finished its spp simply stops re-entering the active queue, so late
-// iterations cost only what is still alive.
+// rounds cost only what is still alive.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -30,14 +30,24 @@
 #define WF_MIN_BLOCKS 4   // resident 256-thread CTAs per SM the shading kernels are compiled for
 #endif
 
-// How many samples of one slot can be in the pipeline at once: the one being generated by k_shade / k_extend plus
-// WF_CHAINS finished ones whose strategy kernels are still running.  Everything a finished sample's strategy
-// kernels read or count with exists in PATH_PARITIES rotating copies / sets.
+// The strategy kernels of a round run beside k_path of the next WF_CHAINS - 1 rounds (k_path of round i waits for the
+// strategy kernels of round i - WF_CHAINS), so everything they count with exists in ROUND_SETS rotating sets, and a
+// completed sample's subpaths must stay readable that long: a slot has PATH_COPIES copies of its path store, used in
+// rotation by its consecutive samples.  With u(i) = samples the slot completed in round i, the copies in use during
+// round i are those completed in rounds i - 1 and i plus the one being written, so a sample may complete in round i
+// iff u(i - 1) + u(i) + 2 <= PATH_COPIES (the completed copy stays busy, the next sample needs a free one):
+// PATH_COPIES = 5 sustains two samples per slot and round, three in a round after a round without any.
 #ifndef WF_CHAINS
 #define WF_CHAINS 2
 #endif
-#define PATH_PARITIES (WF_CHAINS + 1)
-static_assert(PATH_PARITIES >= 2 && PATH_PARITIES <= 8, "the parity fields are 3 bits wide");
+static_assert(WF_CHAINS >= 1 && WF_CHAINS <= 2, "the completion rule of k_path looks one round back");
+#define ROUND_SETS (WF_CHAINS + 1)
+#ifndef PATH_COPIES
+#define PATH_COPIES 5
+#endif
+static_assert(PATH_COPIES >= 3 && PATH_COPIES <= 8, "the copy index fields are 3 bits wide");
+#define DONE_PER_SLOT (PATH_COPIES - 2)      /* most samples a slot can complete in one round */
+#define WF_REGION_DONE (256 * DONE_PER_SLOT)  /* done records of a block of 256 slots */
 
 namespace {
 
@@ -45,12 +55,12 @@ namespace {
 struct WfCounters {
     unsigned n_active[2];      // active queue lengths (double buffered)
     unsigned n_retired;        // slots that rendered all their spp
-    unsigned pad;
-    // per-iteration counters, three sets used in rotation (iteration i uses set i % 3): the strategy kernels of
-    // iteration i may still be running while k_shade / k_extend of iteration i + 1 run, and k_extend of iteration
-    // i clears the set of iteration i + 1 (no separate reset launch)
-    unsigned long long done_pairs[PATH_PARITIES];   // (done count << 40) | pair count, allocated together
-    unsigned long long shadow_mis[PATH_PARITIES];   // low word: shadow queue length, high word: MIS queue length (appended together)
+    unsigned ticket;           // blocks of the running k_path that have finished (the last one resets the next round's counters)
+    // per-round counters, three sets used in rotation (round i uses set i % 3): the strategy kernels of
+    // round i may still be running while k_path of round i + 1 runs, and k_path of round
+    // i clears the set of round i + 1 (no separate reset launch)
+    unsigned long long done_pairs[ROUND_SETS];   // strategy records of the round (written by k_expand)
+    unsigned long long shadow_mis[ROUND_SETS];   // low word: shadow queue length, high word: MIS queue length (appended together)
 };
 
 // ---- slot state ----------------------------------------------------------------------
@@ -59,6 +69,7 @@ struct WfCounters {
 //            [13] waiting for pair space  [15] ray left from cam[1]
 //            [16..20] nc of this sample  [21] camera subpath ended on a Background vertex  [22] light subpath did
 //            [23..25] which copy of the path store this sample writes (vtx_at)
+//            [26..28] samples the slot completed in the previous round (k_path: which copies are still being read)
 #define INFO_PATH(i) ((i) & 1u)
 #define INFO_I(i) (((i) >> 1) & 15u)
 #define INFO_COUNT(i) (((i) >> 5) & 31u)
@@ -67,6 +78,7 @@ struct WfCounters {
 #define INFO_RR_PASS (1u << 12)
 #define INFO_WAIT (1u << 13)
 #define INFO_PARITY(i) (((i) >> 23) & 7u)
+#define INFO_UPREV(i) (((i) >> 26) & 7u)
 #define INFO_FROM_C1 (1u << 15)
 #define INFO_NC(i) (((i) >> 16) & 31u)
 #define INFO_CAM_BG (1u << 21)
@@ -91,17 +103,22 @@ struct WfBuffers {
     unsigned* info;
     unsigned* spp_done;
     unsigned* emask;                   // bit k: camera vertex k of the sample in flight lies on an emitter
-    float4 *ray_o, *ray_d, *pend;      // {o, asfloat(cull), cull < 0: no ray} {d, srpdf} {alpha factor, srpdf}
-    float4* hit;                       // {coords, asfloat(prim)}
-    // the vertex the pending ray left from, once more, indexed by slot alone so that k_shade can issue
-    // every load of an iteration at once
+    float4* pend;                      // {alpha factor, srpdf} of the ray in flight
+    float4* hit;                       // {coords, asfloat(prim)}: what that ray hit
+    // the vertex the pending ray left from, indexed by slot alone (k_path keeps it in registers between its
+    // steps and parks it here between launches)
     float4 *curA, *curB, *curC;
     float4* back;                      // {unit vector from that vertex to its predecessor, |cos cos'| / dist^2 between the two}
     int* active[2];
-    // completed samples of an iteration, three buffers used in rotation like the counters
+    // completed samples of a round, three buffers used in rotation like the counters.  Block r of k_path owns
+    // region r: 256 records here (a slot completes at most one sample per launch) and region_pairs strategy records
+    int n_regions;
+    unsigned region_pairs;
+    unsigned* reg_pairs;               // [parity][region]: strategy records reserved by the region (clamped to region_pairs)
+    unsigned* reg_done;                // [parity][region]: done records of the region
     int* done_slot;
     unsigned* done_info;               // nc | nl << 5 | camBG << 10 | lightBG << 11 | bgStrategy << 12 | parity << 13 | emask << 16
-    unsigned* done_off;
+    unsigned* done_off;                // first strategy record of the sample, relative to its region
     // strategies
     unsigned long long pair_cap;
     uint2* pair_rec;                   // {slot, s | t << 8 | parity << 16}; slot 0xffffffff = void
@@ -117,8 +134,8 @@ struct WfBuffers {
 // kernels of iteration i run beside k_shade / k_extend of iteration i + 1, a sample can complete one iteration
 // after the previous one (primary ray leaves the scene, light ray leaves the scene), so the sample after THAT
 // must not write where the first one is still being read.
-TPT_DEV size_t vtx_at(int parity, int path, int k, int slot) { return ((((size_t)slot * PATH_PARITIES + parity) * 2 + path) * MAX_BDPT_PATH_LENGTH + k) * 3; }
-TPT_DEV size_t l0_at(int parity, int slot) { return ((size_t)slot * PATH_PARITIES + parity) * 3; }
+TPT_DEV size_t vtx_at(int parity, int path, int k, int slot) { return ((((size_t)slot * PATH_COPIES + parity) * 2 + path) * MAX_BDPT_PATH_LENGTH + k) * 3; }
+TPT_DEV size_t l0_at(int parity, int slot) { return ((size_t)slot * PATH_COPIES + parity) * 3; }
 TPT_DEV void store_vertex(float4* w, size_t at, const PVert& v) {
     w[at] = make_float4(v.x.x, v.x.y, v.x.z, v.pdf);
     w[at + 1] = make_float4(v.N.x, v.N.y, v.N.z, __int_as_float(pack_pt(v.prim, v.type)));
@@ -250,7 +267,7 @@ __global__ void __launch_bounds__(256) k_generate(SceneView g, RenderArgs a, WfB
         rays++;
         PVert cam[2];
         camera_path_head(sc, h, cam);
-        for (int par = 0; par < PATH_PARITIES; ++par)               // the same primary hit for every sample
+        for (int par = 0; par < PATH_COPIES; ++par)                 // the same primary hit for every sample
             store_vertex(b.verts, vtx_at(par, 0, 1, slot), cam[1]);
         b.c1A[slot] = b.verts[vtx_at(0, 0, 1, slot)]; b.c1B[slot] = b.verts[vtx_at(0, 0, 1, slot) + 1];
         b.rng[slot] = tpt_pixel_seed(a.seed_mode, (uint32_t)pixel, (uint32_t)a.stream);
@@ -262,11 +279,25 @@ __global__ void __launch_bounds__(256) k_generate(SceneView g, RenderArgs a, WfB
     flush_stats(0, rays, 0, stats);
 }
 
-// ---- shade: the per-slot state machine ----------------------------------------------------
-// Written in three phases so that the expensive code has ONE call site that all lanes of
-// a warp reach together: (1) finish the vertex the last ray produced, (2) walk the cheap
-// state machine until the slot knows what it does next, (3) BSDF-sample (or start the
-// light subpath) and emit the ray.
+// ---- path: the per-slot state machine AND its rays, PATH_ITERS iterations per launch ---------------
+// One launch advances every active slot by up to PATH_ITERS steps of
+//     finish the vertex the last ray produced  ->  camera subpath / light subpath / sample complete / next sample
+//     ->  BSDF-sample (or start the light subpath)  ->  closest hit of the new ray
+// with the slot's state in registers for the whole launch: it is loaded once and stored once per launch instead of
+// once per step (324 B per slot and step through HBM before), the closest hit is found by the same warp right after
+// the ray is made (no ray / hit round trip through memory, no second launch), and nothing inside the loop waits for a
+// global atomic: completed samples are recorded in the BLOCK's region of the done list and reserve their strategy
+// records from the block's share of the strategy buffer with shared-memory atomics.  k_expand turns the regions into
+// one dense strategy list afterwards.
+//
+// A slot completes at most ONE sample per launch (its strategy kernels run beside the next launches and read the
+// sample's copy of the path store, which is rotated per sample): a slot whose next sample would also complete in
+// the same launch — a pixel whose primary ray leaves the scene, a light path of one vertex — waits for the next one
+// (INFO_WAIT), and so does a sample that finds the block's strategy share full.
+//
+// Written in phases so that the expensive code has ONE call site that all lanes of a warp reach together:
+// (1) finish the vertex the last ray produced, (2) walk the cheap state machine until the slot knows what it does
+// next, (3) BSDF-sample (or start the light subpath), (4) trace.
 enum { ACT_NONE = 0, ACT_EXTEND = 1, ACT_LIGHT = 2 };
 #ifndef WF_TRACE_SHADE       /* tests/native/wavefront_host.cu counts how the lanes of a warp split between the actions */
 #define WF_TRACE_SHADE(action, live)
@@ -284,46 +315,58 @@ TPT_DEV PVert unpack_vertex(const float4 a, const float4 b, const float4 c) {
     return v;
 }
 
-#ifndef SHADE_MIN_BLOCKS
-#define SHADE_MIN_BLOCKS 3
+#ifndef PATH_ITERS
+#define PATH_ITERS 8          /* steps per launch; the host reads the active count every few launches */
 #endif
-__global__ void __launch_bounds__(256, SHADE_MIN_BLOCKS) k_shade(SceneView g, RenderArgs a, WfBuffers b, int cur, int par, unsigned long long* stats) {
+#ifndef PATH_MIN_BLOCKS
+#define PATH_MIN_BLOCKS 3         /* 85 registers, no spills: 33.1 vs 33.4 ms (Cornell), 44.5 vs 48.3 ms (bunny) against 2 */
+#endif
+__global__ void __launch_bounds__(256, PATH_MIN_BLOCKS) k_path(SceneView g, RenderArgs a, WfBuffers b, int cur, int par, unsigned long long* stats) {
     pdl_launch_dependents();
     const SceneView sc = stage_scene(g, tpt_smem);
+    __shared__ unsigned s_pairs, s_done;
+    if (threadIdx.x == 0) { s_pairs = 0u; s_done = 0u; }
     pdl_wait();
+    __syncthreads();
+    int* cand = reinterpret_cast<int*>(tpt_smem + ((g.stage_bytes + 15u) & ~15u)) + threadIdx.x;
+    unsigned char* coop = trav_coop(tpt_smem, g.stage_bytes);
     const unsigned n = b.ctr->n_active[cur];
     const int* list = b.active[cur];
     int* next_list = b.active[cur ^ 1];
-    unsigned long long ref_rays = 0, samples = 0;
-    unsigned total = (n + 31u) & ~31u;     // whole warps enter the loop (ballots below)
+    const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = q < n;
+    const int slot = live ? list[q] : 0;
+    const size_t reg_done0 = ((size_t)par * b.n_regions + blockIdx.x) * WF_REGION_DONE;      // this block's part of the done list
+    unsigned long long ref_rays = 0, samples = 0, rays = 0;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
-        const bool live = q < n;
-        const int slot = live ? list[q] : 0;
-        bool keep = false;        // slot stays in the active queue
+
+    // ---- the slot's state, in registers for the whole launch
+    unsigned info = 0, spp_seen = 0, emask = 0;
+    uint32_t rng = 0;
+    float4 hr = zero4, pa = zero4, cA = zero4, cB = zero4, cC = zero4, bk = zero4, c1A = zero4, c1B = zero4;
+    if (live) {
+        info = b.info[slot]; spp_seen = b.spp_done[slot]; emask = b.emask[slot]; rng = b.rng[slot];
+        hr = b.hit[slot]; pa = b.pend[slot];
+        cA = b.curA[slot]; cB = b.curB[slot]; cC = b.curC[slot]; bk = b.back[slot];
+        c1A = b.c1A[slot]; c1B = b.c1B[slot];
+    }
+    bool alive = live;          // still stepping in this launch
+    bool keep = live;           // stays in the active queue
+    const unsigned u_prev = INFO_UPREV(info);      // samples this slot completed in the previous round: their copies are being read
+    unsigned u_now = 0;                            // ... and in this one
+
+    for (int step = 0; step < PATH_ITERS; ++step) {
+        if (__ballot_sync(0xffffffffu, alive) == 0u) break;        // the whole warp is done with this launch
+        const bool stepping = alive;                               // (a lane that stopped keeps its state as it is)
         int action = ACT_NONE;
-        unsigned path = 0, i = 0, count = 0, nc = 0, parity = 0, flags = 0;
-        uint32_t rng = 0;
-        unsigned spp_seen = 0, emask = 0, bgbits = 0;      // bgbits: INFO_CAM_BG / INFO_LIGHT_BG of the sample in flight
-        bool last_bg = false;                              // the subpath ending in this iteration ends on a Background vertex
-        // the vertex the next ray leaves from (V) and its predecessor's position, kept in registers
-        float4 VA = zero4, VB = zero4, c1A = zero4, c1B = zero4;
+        unsigned path = INFO_PATH(info), i = INFO_I(info), count = INFO_COUNT(info), nc = INFO_NC(info);
+        unsigned parity = INFO_PARITY(info), flags = 0;
+        unsigned bgbits = info & (INFO_CAM_BG | INFO_LIGHT_BG);
+        bool last_bg = false;                              // the subpath ending in this step ends on a Background vertex
         f3 prev_x = mk3(0.0f), prev_N = mk3(0.0f);
         int prev_type = VT_CAMERA;
         bool path_done = false, completing = false, fresh = false;
-        if (live) {
-            // ---- every load of this iteration, issued together (all addressed by the slot alone)
-            const unsigned info = b.info[slot];
-            spp_seen = b.spp_done[slot];
-            emask = b.emask[slot];
-            rng = b.rng[slot];
-            const float4 hr = b.hit[slot], pa = b.pend[slot];
-            const float4 cA = b.curA[slot], cB = b.curB[slot], cC = b.curC[slot], bk = b.back[slot];
-            c1A = b.c1A[slot]; c1B = b.c1B[slot];
-
-            path = INFO_PATH(info); i = INFO_I(info); count = INFO_COUNT(info); nc = INFO_NC(info);
-            parity = INFO_PARITY(info);
-            bgbits = info & (INFO_CAM_BG | INFO_LIGHT_BG);
+        if (alive) {
             const bool waiting = (info & INFO_WAIT) != 0;
             path_done = waiting;          // a waiting slot sits on a finished light subpath
             int cur_type = -1;            // type of vertex i, when known
@@ -331,15 +374,13 @@ __global__ void __launch_bounds__(256, SHADE_MIN_BLOCKS) k_shade(SceneView g, Re
             // ---- phase 1: the vertex the traced ray produced (SampleNextVertex tail + FillPath body)
             if (info & INFO_PENDING) {
                 const bool lf = (info & INFO_LIGHT_FIRST) != 0;
-                const bool c1 = (info & INFO_FROM_C1) != 0;
                 DHit h;
                 h.prim = __float_as_int(hr.w); h.coords = mk3(hr); h.t = 0.0;
                 h.normal = h.prim >= 0 ? hit_normal(sc, h.prim, h.coords) : mk3(0.0f);
                 PVert nv = vertex_from_hit(h);
                 const float srpdf = pa.w;
                 const f3 afac = mk3(pa);
-                // L: the vertex the ray left from
-                const PVert L = c1 ? unpack_vertex(c1A, c1B, make_float4(1.f, 1.f, 1.f, 0.f)) : unpack_vertex(cA, cB, cC);
+                const PVert L = unpack_vertex(cA, cB, cC);          // the vertex the ray left from
                 nv.pdf = srpdf_to_area(srpdf, L.x, L.N, L.type, nv.x, nv.N, nv.type);
                 if (lf) {
                     nv.alpha = afac;                       // SafeDivide(verts[0].alpha, pdf1), or 0 when pdf1 == 0
@@ -374,115 +415,104 @@ __global__ void __launch_bounds__(256, SHADE_MIN_BLOCKS) k_shade(SceneView g, Re
                 }
                 if (!path_done) {
                     // slide the window: the new vertex is the one the next ray leaves from
-                    VA = make_float4(nv.x.x, nv.x.y, nv.x.z, nv.pdf);
-                    VB = make_float4(nv.N.x, nv.N.y, nv.N.z, __int_as_float(pack_pt(nv.prim, nv.type)));
                     prev_x = L.x; prev_N = L.N; prev_type = L.type;
-                    b.curA[slot] = VA; b.curB[slot] = VB;
-                    b.curC[slot] = make_float4(nv.alpha.x, nv.alpha.y, nv.alpha.z, 0.0f);
+                    cA = make_float4(nv.x.x, nv.x.y, nv.x.z, nv.pdf);
+                    cB = make_float4(nv.N.x, nv.N.y, nv.N.z, __int_as_float(pack_pt(nv.prim, nv.type)));
+                    cC = make_float4(nv.alpha.x, nv.alpha.y, nv.alpha.z, 0.0f);
                     cur_type = nv.type;
                 }
             }
 
             // ---- phase 2a: does the current subpath end here? (top of the FillPath loop, BDPT.cpp:98-99)
-            fresh = !(info & INFO_PENDING) && !waiting;      // first iteration: nothing traced yet
+            fresh = !(info & INFO_PENDING) && !waiting;      // first step of the frame: nothing traced yet
             if (!path_done && !fresh && (i >= MAX_BDPT_PATH_LENGTH - 1 || cur_type == VT_BACKGROUND)) {
                 path_done = true;
                 last_bg = cur_type == VT_BACKGROUND;
             }
             if (path_done && !waiting && last_bg) bgbits |= path == 0 ? INFO_CAM_BG : INFO_LIGHT_BG;
             completing = path_done && path == 1;             // light subpath complete -> sample complete
-            keep = true;
-        }
 
-        // ---- phase 2b: reserve the strategies of the samples completing in this warp — one atomic per
-        // warp: (samples << 40 | strategies) are allocated together so records and ranges stay ordered
-        {
-            const unsigned cmask = __ballot_sync(0xffffffffu, completing);
-            if (cmask) {
-                const unsigned lane = threadIdx.x & 31u;
-                // strategies that can contribute at all (strategy_count): a Background end only through (nc, 0) and a
-                // background colour, (s, 0) only from a camera vertex on an emitter — the others are exact zeros
+            // ---- phase 2b: record the completed sample in this block's region and reserve its strategies
+            // from the block's share (shared-memory atomics: nothing here waits for a global round trip).
+            // Strategies that can contribute at all (strategy_count): a Background end only through (nc, 0) and
+            // a background colour, (s, 0) only from a camera vertex on an emitter — the others are exact zeros
+            if (completing) {
                 const unsigned nl = count;
                 const bool bg_lit = sc.background.x != 0.0f || sc.background.y != 0.0f || sc.background.z != 0.0f;
                 const unsigned dinfo = nc | (nl << 5) | (parity << 13) | ((bgbits & INFO_CAM_BG) ? 1u << 10 : 0u) |
                                        ((bgbits & INFO_LIGHT_BG) ? 1u << 11 : 0u) |
                                        (((bgbits & INFO_CAM_BG) && bg_lit) ? 1u << 12 : 0u) | (emask << 16);
-                const unsigned npairs = completing ? strategy_count(dinfo) : 0u;
-                unsigned incl = npairs;                      // inclusive prefix sum over the warp
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= (unsigned)o) incl += v;
-                }
-                const unsigned wtotal = __shfl_sync(0xffffffffu, incl, 31);
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(&b.ctr->done_pairs[par], ((unsigned long long)__popc(cmask) << 40) | wtotal);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (completing) {
-                    const unsigned long long off = (base & ((1ull << 40) - 1)) + (incl - npairs);
-                    const unsigned di = (unsigned)(base >> 40) + __popc(cmask & ((1u << lane) - 1u));
-                    if (off + npairs > b.pair_cap) {
-                        // no room left this iteration: leave a void record (its range is marked
-                        // invalid by k_expand) and complete the sample in a later iteration
-                        b.done_slot[(size_t)par * b.S + di] = -1;
-                        b.done_info[(size_t)par * b.S + di] = npairs;
-                        b.done_off[(size_t)par * b.S + di] = off < b.pair_cap ? (unsigned)off : 0xffffffffu;
-                        flags = INFO_WAIT;
+                const unsigned npairs = strategy_count(dinfo);
+                bool ok = u_prev + u_now + 2u <= (unsigned)PATH_COPIES;      // a copy is free for the next sample
+                if (ok) {
+                    const unsigned off = atomicAdd(&s_pairs, npairs);
+                    const unsigned di = atomicAdd(&s_done, 1u);          // < WF_REGION_DONE: DONE_PER_SLOT records per slot at most, void ones included
+                    if (off + npairs > b.region_pairs) {
+                        // the block's share is full: leave a void record (k_expand marks its range invalid) and
+                        // complete the sample in a later launch
+                        b.done_slot[reg_done0 + di] = -1;
+                        b.done_info[reg_done0 + di] = npairs;
+                        b.done_off[reg_done0 + di] = off < b.region_pairs ? off : 0xffffffffu;
+                        ok = false;
                     } else {
-                        b.done_slot[(size_t)par * b.S + di] = slot;
-                        b.done_info[(size_t)par * b.S + di] = dinfo;
-                        b.done_off[(size_t)par * b.S + di] = (unsigned)off;
-                        ref_rays += nc + nl;                 // BDPT.cpp:288
-                        samples++;
-                        const unsigned done = spp_seen + 1;
-                        b.spp_done[slot] = done;
-                        fresh = true;
-                        if ((int)done >= a.spp) {            // all samples of this pixel drawn: the slot retires
-                            fresh = false; keep = false;
-                            path = 0; i = 1; count = 2; nc = 0;
-                        }
+                        b.done_slot[reg_done0 + di] = slot;
+                        b.done_info[reg_done0 + di] = dinfo;
+                        b.done_off[reg_done0 + di] = off;
+                    }
+                }
+                if (!ok) {
+                    flags = INFO_WAIT;
+                    alive = false;                           // nothing more to do in this launch
+                } else {
+                    u_now++;
+                    ref_rays += nc + nl;                     // BDPT.cpp:288
+                    samples++;
+                    spp_seen++;
+                    fresh = true;
+                    if ((int)spp_seen >= a.spp) {            // all samples of this pixel drawn: the slot retires
+                        fresh = false; keep = false; alive = false;
+                        path = 0; i = 1; count = 2; nc = 0;
                     }
                 }
             }
-        }
 
-        // ---- phase 2c: a fresh camera subpath starts at the cached primary hit; pick the action
-        if (fresh) {
-            path = 0; i = 1; count = 2; nc = 0;
-            parity = (parity + 1u) % PATH_PARITIES;      // the new sample's vertices go to the next copy of the path store: the finished
-                                   // sample's stay readable for the strategy kernels running beside the next iterations
-            VA = c1A; VB = c1B; prev_x = mk3(sc.eye.x, sc.eye.y, sc.eye.z); prev_type = VT_CAMERA;
-            flags = INFO_FROM_C1;
-            path_done = unpack_type(__float_as_int(c1B.w)) == VT_BACKGROUND;
-            emask = prim_emissive(sc, unpack_prim(__float_as_int(c1B.w))) ? 2u : 0u;     // camera vertex 1
-            bgbits = path_done ? INFO_CAM_BG : 0u;
-            if (path_done) flags = 0;
+            // ---- phase 2c: a fresh camera subpath starts at the cached primary hit; pick the action
+            if (fresh) {
+                path = 0; i = 1; count = 2; nc = 0;
+                parity = (parity + 1u) % PATH_COPIES;        // the new sample's vertices go to the next copy of the path store: the finished
+                                       // sample's stay readable for the strategy kernels running beside the next launches
+                cA = c1A; cB = c1B; cC = make_float4(1.f, 1.f, 1.f, 0.f);
+                prev_x = mk3(sc.eye.x, sc.eye.y, sc.eye.z); prev_type = VT_CAMERA;
+                path_done = unpack_type(__float_as_int(c1B.w)) == VT_BACKGROUND;
+                emask = prim_emissive(sc, unpack_prim(__float_as_int(c1B.w))) ? 2u : 0u;     // camera vertex 1
+                bgbits = path_done ? INFO_CAM_BG : 0u;
+            }
+            if (alive) action = path_done ? ACT_LIGHT : ACT_EXTEND;
         }
-        if (live && keep && !(flags & INFO_WAIT)) action = path_done ? ACT_LIGHT : ACT_EXTEND;
-        WF_TRACE_SHADE(action, live);
+        WF_TRACE_SHADE(action, alive);
 
-        // ---- phase 3: the one expensive step of this iteration
-        __syncwarp();   // every lane of the warp runs this loop body the same number of times (`total`)
-        float4 ro = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));   // cull < 0: no ray this iteration
+        // ---- phase 3: the one expensive shading step
+        __syncwarp();
+        float4 ro = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)), rd = make_float4(0.f, 0.f, 1.f, 0.f);   // cull < 0: no ray
         if (action == ACT_EXTEND) {
-            const f3 Vx = mk3(VA), VN = mk3(VB);
-            const int Vprim = unpack_prim(__float_as_int(VB.w));
+            const f3 Vx = mk3(cA), VN = mk3(cB);
+            const int Vprim = unpack_prim(__float_as_int(cB.w));
             const f3 w_o = s_normalize(prev_x - Vx);
             const NextSample s = sample_next_dir(sc, rng, VN, Vprim, w_o);
             {
-                // what the reverse pdf towards vertex i-1 needs from this side (phase 1 of the next iteration
+                // what the reverse pdf towards vertex i-1 needs from this side (phase 1 of the next step
                 // finishes it): unit vector to the predecessor and |cos cos'| / dist^2 as SrpdfToAreaPdf forms them
                 float d2;
                 const f3 w = s_normalize_len2(prev_x - Vx, &d2);
                 const float cosine = fabsf(dotf(w, VN));
                 const float cosT = prev_type == VT_CAMERA ? 1.0f : fabsf(dotf(w, prev_N));
-                b.back[slot] = make_float4(w.x, w.y, w.z, fabsf(cosine * cosT / d2));
+                bk = make_float4(w.x, w.y, w.z, fabsf(cosine * cosT / d2));
             }
             const float rrProb = i > 4 ? .8f : 1.f;
             const bool rr_pass = !(rng_float(rng) > rrProb);      // drawn even when rrProb == 1 (quirk Q16)
             ro = make_float4(Vx.x, Vx.y, Vx.z, __int_as_float(s.cull));
-            b.ray_d[slot] = make_float4(s.w_i.x, s.w_i.y, s.w_i.z, s.srpdf);
-            b.pend[slot] = make_float4(s.alpha.x, s.alpha.y, s.alpha.z, s.srpdf);
+            rd = make_float4(s.w_i.x, s.w_i.y, s.w_i.z, s.srpdf);
+            pa = make_float4(s.alpha.x, s.alpha.y, s.alpha.z, s.srpdf);
             flags |= INFO_PENDING | (rr_pass ? INFO_RR_PASS : 0u);
         } else if (action == ACT_LIGHT) {
             // GenerateLightPath head (BDPT.cpp:61-77)
@@ -490,77 +520,89 @@ __global__ void __launch_bounds__(256, SHADE_MIN_BLOCKS) k_shade(SceneView g, Re
             PVert v0[1];
             const LightStart ls = light_path_head(sc, rng, sc.emissive[0], v0);
             store_vertex(b.l0, l0_at((int)parity, slot), v0[0]);
-            b.curA[slot] = make_float4(v0[0].x.x, v0[0].x.y, v0[0].x.z, v0[0].pdf);
-            b.curB[slot] = make_float4(v0[0].N.x, v0[0].N.y, v0[0].N.z, __int_as_float(pack_pt(v0[0].prim, v0[0].type)));
-            b.curC[slot] = make_float4(v0[0].alpha.x, v0[0].alpha.y, v0[0].alpha.z, 0.0f);
+            cA = make_float4(v0[0].x.x, v0[0].x.y, v0[0].x.z, v0[0].pdf);
+            cB = make_float4(v0[0].N.x, v0[0].N.y, v0[0].N.z, __int_as_float(pack_pt(v0[0].prim, v0[0].type)));
+            cC = make_float4(v0[0].alpha.x, v0[0].alpha.y, v0[0].alpha.z, 0.0f);
             const f3 afac = ls.pdf1 != 0.0f ? safe_div(v0[0].alpha, ls.pdf1) : mk3(0.0f);
             ro = make_float4(v0[0].x.x, v0[0].x.y, v0[0].x.z, __int_as_float(0));
-            b.ray_d[slot] = make_float4(ls.w_i.x, ls.w_i.y, ls.w_i.z, ls.pdf1);
-            b.pend[slot] = make_float4(afac.x, afac.y, afac.z, ls.pdf1);
+            rd = make_float4(ls.w_i.x, ls.w_i.y, ls.w_i.z, ls.pdf1);
+            pa = make_float4(afac.x, afac.y, afac.z, ls.pdf1);
             path = 1; i = 0; count = 1;
             flags = INFO_PENDING | INFO_LIGHT_FIRST;
         }
-        if (live) {
-            b.ray_o[slot] = ro;
-            b.rng[slot] = rng;
-            b.emask[slot] = emask;
-            b.info[slot] = make_info(path, i, count, flags | (parity << 23) | bgbits, nc);
-        }
-        const unsigned at = wf_append(&b.ctr->n_active[cur ^ 1], keep);
-        if (keep) next_list[at] = slot;
-    }
-    flush_stats(ref_rays, 0, samples, stats);
-}
+        if (stepping) info = make_info(path, i, count, flags | (parity << 23) | bgbits, nc);
 
-// ---- extend: closest hit for the rays of the active slots --------------------------------
-#ifndef TRAV_MIN_BLOCKS
-#define TRAV_MIN_BLOCKS 4
-#endif
-__global__ void __launch_bounds__(256, TRAV_MIN_BLOCKS) k_extend(SceneView g, RenderArgs a, WfBuffers b, int cur, int par, unsigned long long* stats) {
-    pdl_launch_dependents();
-    const SceneView sc = stage_scene(g, tpt_smem);
-    pdl_wait();
-    if (blockIdx.x == 0 && threadIdx.x == 0) {      // the next iteration's counters (nothing in flight reads them)
-        b.ctr->n_active[cur ^ 1] = 0;                // the list k_shade just consumed: the next one is built there
-        b.ctr->done_pairs[(par + 1) % PATH_PARITIES] = 0;
-        b.ctr->shadow_mis[(par + 1) % PATH_PARITIES] = 0;
-    }
-    int* cand = reinterpret_cast<int*>(tpt_smem + ((g.stage_bytes + 15u) & ~15u)) + threadIdx.x;
-    unsigned char* coop = trav_coop(tpt_smem, g.stage_bytes);
-    const unsigned n = b.ctr->n_active[cur];
-    const int* list = b.active[cur];
-    unsigned long long rays = 0;
-    const unsigned total = (n + 31u) & ~31u;        // whole warps: the primitive tests are shared inside a warp
-    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
-        int slot = 0;
-        float4 o = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)), d = make_float4(0.f, 0.f, 1.f, 0.f);
-        if (q < n) { slot = list[q]; o = b.ray_o[slot]; d = b.ray_d[slot]; }
-        const bool has_ray = __float_as_int(o.w) >= 0;      // < 0: the slot emitted no ray this iteration
+        // ---- phase 4: closest hit of the new ray (Scene::Intersect), the warp's 32 rays together
+        const bool has_ray = __float_as_int(ro.w) >= 0;
         DHit h;
-        closest_hit_warp(sc, make_ray(mk3(o), mk3(d)), __float_as_int(o.w), has_ray, coop, cand, blockDim.x, &h);
+        closest_hit_warp(sc, make_ray(mk3(ro), mk3(rd)), __float_as_int(ro.w), has_ray, coop, cand, blockDim.x, &h);
         if (has_ray) {
             rays++;
-            b.hit[slot] = make_float4(h.coords.x, h.coords.y, h.coords.z, __int_as_float(h.prim));
+            hr = make_float4(h.coords.x, h.coords.y, h.coords.z, __int_as_float(h.prim));
         }
     }
-    flush_stats(0, rays, 0, stats);
+
+    if (live) {
+        b.info[slot] = (info & ~(7u << 26)) | (u_now << 26); b.spp_done[slot] = spp_seen; b.emask[slot] = emask; b.rng[slot] = rng;
+        b.hit[slot] = hr; b.pend[slot] = pa;
+        b.curA[slot] = cA; b.curB[slot] = cB; b.curC[slot] = cC; b.back[slot] = bk;
+    }
+    const unsigned at = wf_append(&b.ctr->n_active[cur ^ 1], keep);
+    if (keep) next_list[at] = slot;
+    flush_stats(ref_rays, rays, samples, stats);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        b.reg_pairs[(size_t)par * b.n_regions + blockIdx.x] = s_pairs < b.region_pairs ? s_pairs : b.region_pairs;
+        b.reg_done[(size_t)par * b.n_regions + blockIdx.x] = s_done;
+        // the last block to finish resets what the next launches count with (every block has read its inputs)
+        __threadfence();
+        if (atomicAdd(&b.ctr->ticket, 1u) == gridDim.x - 1u) {
+            b.ctr->ticket = 0u;
+            b.ctr->n_active[cur] = 0u;                                   // the list just consumed: the next launch builds its successor there
+            b.ctr->shadow_mis[(par + 1) % ROUND_SETS] = 0ull;         // (its last readers finished before this launch started)
+        }
+    }
 }
 
 // ---- expand: one work item per strategy of every completed sample ------------------------
+// Block r turns region r of the done list into strategy records.  Regions are laid end to end: the records of
+// region r start at the sum of the (clamped) reservations of the regions before it, so the strategy list the
+// connect kernel walks is dense.
 __global__ void __launch_bounds__(256) k_expand(WfBuffers b, int par) {
     pdl_launch_dependents();
     pdl_wait();
-    const unsigned n_done = (unsigned)(b.ctr->done_pairs[par] >> 40);
-    const int* done_slot = b.done_slot + (size_t)par * b.S;
-    const unsigned *done_info = b.done_info + (size_t)par * b.S, *done_off = b.done_off + (size_t)par * b.S;
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (unsigned di = warp; di < n_done; di += nwarps) {
+    __shared__ unsigned s_part[8];
+    __shared__ unsigned long long s_base;
+    const unsigned* reg_pairs = b.reg_pairs + (size_t)par * b.n_regions;
+    const unsigned lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+    // pairs reserved by the regions before this one (and, block 0: by all of them)
+    {
+        const unsigned upto = blockIdx.x == 0 ? (unsigned)b.n_regions : blockIdx.x;
+        unsigned long long acc = 0;
+        for (unsigned r = threadIdx.x; r < upto; r += blockDim.x) acc += reg_pairs[r];
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        // (sums of at most n_regions * region_pairs <= pair_cap < 2^31: 32 bits per warp are enough)
+        if (lane == 0) s_part[wib] = (unsigned)acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long t = 0;
+            for (int k = 0; k < 8; ++k) t += s_part[k];
+            if (blockIdx.x == 0) { b.ctr->done_pairs[par] = t; s_base = 0; }      // the total k_connect walks
+            else s_base = t;
+        }
+        __syncthreads();
+    }
+    const unsigned long long base = s_base;
+    const unsigned n_done = b.reg_done[(size_t)par * b.n_regions + blockIdx.x];
+    const size_t reg0 = ((size_t)par * b.n_regions + blockIdx.x) * WF_REGION_DONE;
+    const int* done_slot = b.done_slot + reg0;
+    const unsigned *done_info = b.done_info + reg0, *done_off = b.done_off + reg0;
+    for (unsigned di = wib; di < n_done; di += blockDim.x >> 5) {
         const unsigned inf = done_info[di], off = done_off[di];
-        if (done_slot[di] < 0) {          // void record: invalidate the part of its range below the cap
+        if (done_slot[di] < 0) {          // void record: invalidate the part of its range inside the region
             if (off != 0xffffffffu)
-                for (unsigned long long k = off + lane; k < b.pair_cap && k < (unsigned long long)off + inf; k += 32)
-                    b.pair_rec[k] = make_uint2(0xffffffffu, 0u);
+                for (unsigned k = off + lane; k < b.region_pairs && k < off + inf; k += 32)
+                    b.pair_rec[base + k] = make_uint2(0xffffffffu, 0u);
             continue;
         }
         const unsigned nc = inf & 31u, parity = (inf >> 13) & 7u;
@@ -572,7 +614,7 @@ __global__ void __launch_bounds__(256) k_expand(WfBuffers b, int par) {
             if (k < ss.grid) { s = k / ss.nlp + 1; t = k % ss.nlp + 1; }
             else if (k < ss.grid + ss.ne) s = __fns(ss.emitters, 0u, (int)(k - ss.grid) + 1) + 1;      // z = cam[s-1] on an emitter
             else s = nc;                                                                              // Background end, lit background
-            b.pair_rec[off + k] = make_uint2((unsigned)slot, s | (t << 8) | (parity << 16));
+            b.pair_rec[base + off + k] = make_uint2((unsigned)slot, s | (t << 8) | (parity << 16));
         }
     }
 }
@@ -633,7 +675,10 @@ __global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_connect(SceneView g, WfB
 }
 
 // ---- shadow: Scene::ShadowCheck for the queued connections -------------------------------
-__global__ void __launch_bounds__(256, TRAV_MIN_BLOCKS) k_shadow_q(SceneView g, RenderArgs a, WfBuffers b, int par, unsigned long long* stats) {
+#ifndef SHADOW_MIN_BLOCKS
+#define SHADOW_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(256, SHADOW_MIN_BLOCKS) k_shadow_q(SceneView g, RenderArgs a, WfBuffers b, int par, unsigned long long* stats) {
     pdl_launch_dependents();
     const SceneView sc = stage_scene(g, tpt_smem);
     pdl_wait();
@@ -711,18 +756,31 @@ struct WavefrontState {
     int S = 0;
     WfBuffers b;
     std::vector<void*> allocs;
-    unsigned* h_flag = nullptr;     // pinned: [0] n_active, [1] n_retired
-    // the strategy kernels of an iteration (expand / connect / shadow / MIS) depend on k_shade only: they run on a
-    // second stream beside k_extend of the same iteration and k_shade / k_extend of the next one (k_shade of
-    // iteration i waits for the strategy kernels of iteration i - 2; see PATH_PARITIES)
-    // iteration i's strategy kernels run on stream i % WF_CHAINS with that chain's strategy buffers
+    unsigned* h_flag = nullptr;     // pinned: [0] n_active
+    // The strategy kernels of a round (expand / connect / shadow / MIS) depend on that round's k_path only: they run
+    // on a side stream beside k_path of the next rounds (k_path of round i waits for the strategy kernels of round
+    // i - WF_CHAINS; see ROUND_SETS).  Round i's strategy kernels run on stream i % WF_CHAINS with that chain's
+    // strategy buffers.
     cudaStream_t side[WF_CHAINS] = {};
     WfBuffers bs[WF_CHAINS];                     // = b with the chain's own pair_*, shadow_q, mis_q
-    cudaEvent_t ev_shade[WF_CHAINS] = {}, ev_side[WF_CHAINS] = {};
+    cudaEvent_t ev_path[WF_CHAINS] = {}, ev_side[WF_CHAINS] = {};
 };
 
+// Strategy records per slot and round the buffers are sized for.  A round completes at most one sample per slot
+// (17 strategies on average, 271 at most); a sample that does not fit its block's share waits a round.
+#ifndef WF_PAIRS_PER_SLOT
+#define WF_PAIRS_PER_SLOT 24
+#endif
+static unsigned long long wf_pair_cap(int S) {
+    unsigned long long cap = std::max<unsigned long long>((unsigned long long)S * WF_PAIRS_PER_SLOT, 1ull << 16);
+    if (const char* env = getenv("TPT_WF_PAIR_CAP")) cap = std::max<unsigned long long>(512ull, strtoull(env, nullptr, 10));   // tests: force the waiting path
+    return std::min<unsigned long long>(cap, 0x7fffffffull);
+}
+
 static int wf_alloc(TptScene* s, int S) {
-    if (s->wf && s->wf->S == S) return TPT_OK;
+    const int n_regions = (S + 255) / 256;
+    const unsigned long long cap = wf_pair_cap(S);
+    if (s->wf && s->wf->S == S && s->wf->b.pair_cap == cap) return TPT_OK;
     if (s->wf) cudaDeviceSynchronize();      // a different share: the previous one's launches may still be running on its streams
     wavefront_destroy(s);
     WavefrontState* w = new WavefrontState;
@@ -740,19 +798,20 @@ static int wf_alloc(TptScene* s, int S) {
     };
     const size_t V = (size_t)MAX_BDPT_PATH_LENGTH * S * sizeof(float4);
     const size_t F4 = (size_t)S * sizeof(float4);
-    // strategies of one iteration: 16 per slot is generous (17 per completing sample, one sample in 7.5
-    // iterations: ~2.5 per slot; a sample that finds no room waits an iteration); never less than a block's worth of the longest samples (16*17 - 1 strategies each), so
-    // that a sample waiting for room always gets it once the queue has drained
-    b.pair_cap = std::max<unsigned long long>((unsigned long long)S * 16ull, 1ull << 16);
-    if (b.pair_cap > 0x7fffffffull) b.pair_cap = 0x7fffffffull;
-    bool ok = get(6 * PATH_PARITIES * V, (void**)&b.verts) && get(3 * PATH_PARITIES * F4, (void**)&b.l0) && get(F4, (void**)&b.c1A) && get(F4, (void**)&b.c1B) &&
+    b.n_regions = n_regions;
+    // every region the same share, never less than the longest sample (16 * 17 - 1 strategies), so that a sample
+    // waiting for room always gets it at the start of a round
+    b.region_pairs = (unsigned)std::max<unsigned long long>(cap / n_regions, 272ull);
+    b.pair_cap = (unsigned long long)b.region_pairs * n_regions;
+    const size_t DONE = (size_t)ROUND_SETS * n_regions * WF_REGION_DONE * 4, REG = (size_t)ROUND_SETS * n_regions * 4;
+    bool ok = get(6 * PATH_COPIES * V, (void**)&b.verts) && get(3 * PATH_COPIES * F4, (void**)&b.l0) && get(F4, (void**)&b.c1A) && get(F4, (void**)&b.c1B) &&
               get((size_t)S * 4, (void**)&b.rng) && get((size_t)S * 4, (void**)&b.info) &&
-              get((size_t)S * 4, (void**)&b.spp_done) && get((size_t)S * 4, (void**)&b.emask) && get(F4, (void**)&b.ray_o) && get(F4, (void**)&b.ray_d) &&
+              get((size_t)S * 4, (void**)&b.spp_done) && get((size_t)S * 4, (void**)&b.emask) &&
               get(F4, (void**)&b.pend) && get(F4, (void**)&b.hit) && get(F4, (void**)&b.curA) && get(F4, (void**)&b.curB) &&
               get(F4, (void**)&b.curC) && get(F4, (void**)&b.back) && get((size_t)S * 4, (void**)&b.active[0]) &&
               get((size_t)S * 4, (void**)&b.active[1]) &&
- get((size_t)S * 4 * PATH_PARITIES, (void**)&b.done_slot) &&
-              get((size_t)S * 4 * PATH_PARITIES, (void**)&b.done_info) && get((size_t)S * 4 * PATH_PARITIES, (void**)&b.done_off) &&
+              get(DONE, (void**)&b.done_slot) && get(DONE, (void**)&b.done_info) && get(DONE, (void**)&b.done_off) &&
+              get(REG, (void**)&b.reg_pairs) && get(REG, (void**)&b.reg_done) &&
               get(b.pair_cap * sizeof(uint2), (void**)&b.pair_rec) && get(b.pair_cap * sizeof(float4), (void**)&b.pair_val) &&
               get(b.pair_cap * 2 * sizeof(float4), (void**)&b.shadow_q) && get(b.pair_cap * sizeof(uint4), (void**)&b.mis_q) &&
               get(sizeof(WfCounters), (void**)&b.ctr);
@@ -773,7 +832,7 @@ void wavefront_destroy(TptScene* s) {
     if (s->wf->h_flag) tpt_pinned_free(s->wf->h_flag);
     for (int k = 0; k < WF_CHAINS; ++k) if (s->wf->side[k]) cudaStreamDestroy(s->wf->side[k]);
     for (int k = 0; k < WF_CHAINS; ++k) {
-        if (s->wf->ev_shade[k]) cudaEventDestroy(s->wf->ev_shade[k]);
+        if (s->wf->ev_path[k]) cudaEventDestroy(s->wf->ev_path[k]);
         if (s->wf->ev_side[k]) cudaEventDestroy(s->wf->ev_side[k]);
     }
     delete s->wf;
@@ -793,7 +852,7 @@ int wavefront_render(TptScene* s, const RenderArgs& a, float* d_radiance, float*
     const unsigned tsmem = TPT_TRAV_SMEM(smem, 256);   // traversal kernels: + candidate columns + cooperative area
     if (tsmem > 48u * 1024u) {                         // mid-size staged scenes: opt in to more dynamic shared memory
         TPT_CUDA(cudaFuncSetAttribute(k_generate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
-        TPT_CUDA(cudaFuncSetAttribute(k_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+        TPT_CUDA(cudaFuncSetAttribute(k_path, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
         TPT_CUDA(cudaFuncSetAttribute(k_shadow_q, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
     }
     const int grid = std::max(1, std::min((S + 255) / 256, s->num_sms * 8));
@@ -804,8 +863,9 @@ int wavefront_render(TptScene* s, const RenderArgs& a, float* d_radiance, float*
     TPT_CUDA(cudaMemcpyAsync(b.ctr, &init, sizeof init, cudaMemcpyHostToDevice, st));
     tm->begin(TPT_K_GENERATE); launch_pdl(k_generate, grid, tsmem, st, s->view, a, b, s->d_stats); tm->end();
     int cur = 0;
-    // every sample needs at least 2 iterations; 31 is the longest a sample can take
-    const long long max_iters = (long long)a.spp * 32 + 8;
+    // Safety bound only (an incomplete frame must not pass for a frame): every round completes at least one waiting
+    // sample per block, a sample takes at most 31 steps
+    const long long max_rounds = (long long)a.spp * (256 + 32 / PATH_ITERS + 2) + 8;
     // (per-kernel timing brackets launches with events on ONE stream: it runs the chain serially;
     // TPT_WF_TWO_STREAMS=0 does the same, for A/B measurements)
     const char* env_two = getenv("TPT_WF_TWO_STREAMS");
@@ -813,32 +873,39 @@ int wavefront_render(TptScene* s, const RenderArgs& a, float* d_radiance, float*
     if (two && !w->side[0]) {
         for (int k = 0; k < WF_CHAINS; ++k) {
             TPT_CUDA(cudaStreamCreateWithFlags(&w->side[k], cudaStreamNonBlocking));
-            TPT_CUDA(cudaEventCreateWithFlags(&w->ev_shade[k], cudaEventDisableTiming));
+            TPT_CUDA(cudaEventCreateWithFlags(&w->ev_path[k], cudaEventDisableTiming));
             TPT_CUDA(cudaEventCreateWithFlags(&w->ev_side[k], cudaEventDisableTiming));
         }
     }
-    for (long long it = 0; it < max_iters; ++it) {
-        const int par = (int)(it % PATH_PARITIES), e = (int)(it % WF_CHAINS);
+    unsigned left = (unsigned)S;
+    for (long long it = 0; it < max_rounds && left != 0u; ++it) {
+        const int par = (int)(it % ROUND_SETS), e = (int)(it % WF_CHAINS);
         cudaStream_t ss = two ? w->side[e] : st;
         const WfBuffers& bs = two ? w->bs[e] : b;              // strategy buffers of this chain
-        // the strategy kernels of iteration it - WF_CHAINS read the path-store copy and light start this k_shade may write
+        // the strategy kernels of round it - WF_CHAINS read the path-store copy and light start this k_path may write
         if (two && it >= WF_CHAINS) TPT_CUDA(cudaStreamWaitEvent(st, w->ev_side[e], 0));
-        tm->begin(TPT_K_SHADE); launch_pdl(k_shade, grid, smem, st, s->view, a, b, cur, par, s->d_stats); tm->end();
-        if (two) { TPT_CUDA(cudaEventRecord(w->ev_shade[e], st)); TPT_CUDA(cudaStreamWaitEvent(ss, w->ev_shade[e], 0)); }
-        tm->begin(TPT_K_EXTEND); launch_pdl(k_extend, grid, tsmem, st, s->view, a, b, cur ^ 1, par, s->d_stats); tm->end();
-        tm->begin(TPT_K_EXPAND); launch_pdl(k_expand, pgrid, 0u, ss, bs, par); tm->end();
+        // one block per 256 slots of the frame (a block past the end of the active list exits at once): the blocks
+        // are the regions of the done list
+        tm->begin(TPT_K_SHADE); launch_pdl(k_path, b.n_regions, tsmem, st, s->view, a, b, cur, par, s->d_stats); tm->end();
+        if (two) { TPT_CUDA(cudaEventRecord(w->ev_path[e], st)); TPT_CUDA(cudaStreamWaitEvent(ss, w->ev_path[e], 0)); }
+        tm->begin(TPT_K_EXPAND); launch_pdl(k_expand, b.n_regions, 0u, ss, bs, par); tm->end();
         tm->begin(TPT_K_CONNECT); launch_pdl(k_connect, pgrid, smem, ss, s->view, bs, par); tm->end();
         tm->begin(TPT_K_SHADOW); launch_pdl(k_shadow_q, pgrid, (unsigned)TPT_SHADOW_SMEM(smem, 256), ss, s->view, a, bs, par, s->d_stats); tm->end();
         tm->begin(TPT_K_MIS); launch_pdl(k_mis, pgrid, smem, ss, s->view, a, bs, par, d_radiance, d_splat); tm->end();
         if (two) TPT_CUDA(cudaEventRecord(w->ev_side[e], ss));
         cur ^= 1;
-        if ((it & 7) == 7 || it + 1 == max_iters) {
+        if ((it & 3) == 3 || it + 1 == max_rounds) {
             TPT_CUDA(cudaMemcpyAsync(w->h_flag, &b.ctr->n_active[cur], sizeof(unsigned), cudaMemcpyDeviceToHost, st));
             TPT_CUDA(cudaStreamSynchronize(st));
-            if (w->h_flag[0] == 0) break;
+            left = w->h_flag[0];
         }
     }
     if (two) for (int k = 0; k < WF_CHAINS; ++k) TPT_CUDA(cudaStreamWaitEvent(st, w->ev_side[k], 0));
     TPT_CUDA(cudaGetLastError());
+    if (left != 0u) {          // never seen; an incomplete frame must not pass for a frame
+        TPT_CUDA(cudaStreamSynchronize(st));
+        tpt_set_error("wavefront_render: " + std::to_string(left) + " slots still had samples to draw after " + std::to_string(max_rounds) + " rounds");
+        return TPT_ERR_CUDA;
+    }
     return TPT_OK;
 }
