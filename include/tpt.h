@@ -251,7 +251,12 @@ int tpt_render(TptScene* scene, const TptRenderParams* params, float* out_rgb,
  * it before the call and joined back into it before the call returns, so work queued on
  * `stream` afterwards (the reduce, tpt_finalize_device, a copy) sees the complete sums.
  * With a non-null `stats` the call waits for the result (it reads the counters);
- * TPT_FLAG_KERNEL_TIMES additionally runs the kernels one after another on `stream`. */
+ * TPT_FLAG_KERNEL_TIMES additionally runs the kernels one after another on `stream`.
+ * One render at a time per scene handle (the handle owns one set of work buffers: a second call while one is
+ * inside the function fails with TPT_ERR_INVALID; a second call on another stream before the first one's work has
+ * finished is the caller's to order).  The host thread is used to feed the launch chain: it waits for the device
+ * every few rounds to learn whether samples are left.  A frame that could not be completed is an error, never a
+ * partial image. */
 int tpt_render_device(TptScene* scene, const TptRenderParams* params, float* d_accum,
                       void* stream, TptStats* stats);
 size_t tpt_accum_floats(const TptScene* scene);

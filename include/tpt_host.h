@@ -19,7 +19,7 @@ extern "C" {
 
 typedef struct TpthScene TpthScene;
 
-/* scene_name: standard | smooth | silver | refractive | occlusion | bunny.
+/* scene_name: standard | smooth | silver | refractive | occlusion | bunny | twolights (standard + an emissive Sphere).
  * models_dir holds cornellbox/<mesh>.obj and bunny/bunny_x1500.obj.
  * Never returns NULL; check tpth_scene_error(). */
 TpthScene*  tpth_scene_build(const char* scene_name, const char* models_dir, int width, int height);

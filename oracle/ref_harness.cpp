@@ -85,7 +85,7 @@ void Put(float* p, const Vector3f& v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
 
 extern "C" {
 
-// scene_name: standard | smooth | silver | refractive | occlusion | bunny.
+// scene_name: standard | smooth | silver | refractive | occlusion | bunny | twolights.
 // models_dir holds cornellbox/*.obj (and bunny/bunny_x1500.obj for "bunny").
 RefScene* ref_scene_create(const char* scene_name, const char* models_dir, int w, int h) {
     std::string name(scene_name), dir(models_dir);
@@ -137,6 +137,12 @@ RefScene* ref_scene_create(const char* scene_name, const char* models_dir, int w
         }
         if (name == "occlusion")     // main.cpp:89,102
             scene.Add(NewMesh(rs, box + "lightocculuder.obj", white));
+        if (name == "twolights") {   // a second emitter, and a Sphere at that: PathTrace loops over m_emissionObjects (PathTracer.cpp:82)
+            Material* lamp = NewMaterial(rs, Dieletric, Vector3f(6.0f, 9.0f, 14.0f));
+            lamp->Kd = Vector3f(0.65f);
+            rs->spheres.emplace_back(new Sphere(Vector3f(400.0f, 90.0f, 120.0f), 40.0f, lamp));
+            scene.Add(rs->spheres.back().get());
+        }
     }
     scene.BuildBVH();
 

@@ -45,6 +45,8 @@ static cudaError_t hm_launch(const cudaLaunchConfig_t* cfg, void (*kernel)(KArgs
 #define cudaGetLastError() (cudaSuccess)
 #define cudaFuncSetAttribute(f, a, v) (cudaSuccess)
 #define cudaStreamCreateWithFlags(p, f) (*(p) = reinterpret_cast<cudaStream_t>(1), cudaSuccess)
+#define cudaStreamCreateWithPriority(p, f, pr) (*(p) = reinterpret_cast<cudaStream_t>(1), cudaSuccess)
+#define cudaDeviceGetStreamPriorityRange(lo, hi) (*(lo) = 0, *(hi) = 0, cudaSuccess)
 #define cudaEventCreateWithFlags(p, f) (*(p) = reinterpret_cast<cudaEvent_t>(1), cudaSuccess)
 #define cudaStreamDestroy(s) (cudaSuccess)
 #define cudaEventDestroy(e) (cudaSuccess)

@@ -23,6 +23,20 @@ def test_small_renders_against_reference(tpt, scene, pipeline):
     s.close()
 
 
+@pytest.mark.parametrize("pipeline", [0, 1], ids=["wavefront", "megakernel"])
+def test_every_emissive_object_lights_pathtrace(tpt, pipeline):
+    """Cornell-Standard plus an emissive Sphere (tests/golden/make_twolights.py): PathTrace samples EVERY entry of
+    Scene::m_emissionObjects per vertex (PathTracer.cpp:82), sphere lights through Sphere::Sample (Sphere.cpp:48-55);
+    BDPT starts its light subpaths on the first one only (BDPT.cpp:287).  Against the compiled reference's renders."""
+    s = gpu_scene("twolights", 64, 64)
+    check_small_renders(s, "twolights", pipeline=pipeline)
+    if pipeline == 0:                       # the queue pipeline adds up in the reference's order: the per-pixel kernel's frame
+        a, _ = s.render("pt_full", 8)
+        b, _ = s.render("pt_full", 8, pipeline=tpt.PIPE_MEGAKERNEL)
+        assert np.allclose(a, b, rtol=1e-4, atol=1e-5)
+    s.close()
+
+
 @pytest.mark.parametrize("scene,mode,spp", [("standard", "bdpt", 16), ("standard", "pt_full", 64),
                                             ("refractive", "bdpt", 16), ("smooth", "pt_full", 64)])
 def test_readme_images(tpt, scene, mode, spp):

@@ -472,7 +472,7 @@ def wavefront_vs_pixel_loop(lib, scene, mode, spp, size, sms=1):
 
 
 @pytest.mark.parametrize("scene,mode,spp", [("standard", "pt_full", 4), ("standard", "pt_shipped", 8), ("refractive", "pt_full", 3),
-                                            ("bunny", "pt_full", 3)])
+                                            ("bunny", "pt_full", 3), ("twolights", "pt_full", 3)])
 def test_pathtrace_wavefront_is_the_pixel_loop(wfmirror, scene, mode, spp):
     """k_pt_generate / k_pt_shade / k_pt_extend / k_pt_shadow with pt_wavefront_render's launch chains (two interleaved
     chains over alternate slots at this size): the same image bit for bit."""

@@ -119,13 +119,13 @@ TPT_DEV f3 light_sample_dir(Ctx& c, int light, uint32_t& rng, f3 x, float* pdf) 
 }
 
 // One shaded vertex of PathTrace: BSDF sample + per-light two-sample MIS direct
-// lighting (PathTracer.cpp:70-107).  Returns sum over lights of alpha * eval * Le.
+// lighting (PathTracer.cpp:70-107).  Every light's alpha * eval * Le is added to `radiance` as the reference adds it
+// (resultRadiance += ... inside the loop, PathTracer.cpp:105: the association of the float sum is part of the result).
 template <bool COUNT>
-TPT_DEV f3 pt_direct_light(Ctx& c, uint32_t& rng, const Mat& mat, f3 alpha, f3 x, f3 w_o, f3 n,
-                           f3* w_i_bsdf_out, float* pdf_bsdf_out) {
+TPT_DEV void pt_direct_light(Ctx& c, uint32_t& rng, const Mat& mat, f3 alpha, f3 x, f3 w_o, f3 n,
+                             f3* w_i_bsdf_out, float* pdf_bsdf_out, f3& radiance) {
     float pdf_bsdf;
     const f3 w_i_bsdf = mat_sample(mat, rng, w_o, n, &pdf_bsdf);
-    f3 result = mk3(0.0f);
     for (int iLight = 0; iLight < c.sc.n_emissive; iLight++) {
         const int light = c.sc.emissive[iLight];
         float pdf_light_light;
@@ -147,11 +147,10 @@ TPT_DEV f3 pt_direct_light(Ctx& c, uint32_t& rng, const Mat& mat, f3 alpha, f3 x
                 eval_result += mat_eval(mat, w_o, w_i_light, n, true) / (TPT_EPSILON + pdf_light_light + pdf_light_bsdf);
         }
         const Mat lm = load_mat(c.sc, c.sc.objs[light].material);
-        result += (alpha * eval_result) * lm.emission;
+        radiance += (alpha * eval_result) * lm.emission;
     }
     *w_i_bsdf_out = w_i_bsdf;
     *pdf_bsdf_out = pdf_bsdf;
-    return result;
 }
 
 // PathTrace, PathTracer.cpp:44-134.  full == false stops at the `break;` of line 109.
@@ -171,7 +170,7 @@ TPT_DEV f3 path_trace(Ctx& c, uint32_t& rng, DRay ray, bool full, int* outBounce
         f3 w_i_bsdf;
         float pdf_bsdf;
         explicitLight = true;
-        radiance += pt_direct_light<COUNT>(c, rng, mat, alpha, x, w_o, n, &w_i_bsdf, &pdf_bsdf);
+        pt_direct_light<COUNT>(c, rng, mat, alpha, x, w_o, n, &w_i_bsdf, &pdf_bsdf, radiance);
         if (!full) break;
         f3 weight = mk3(0.0f);
         if (pdf_bsdf > 0.0f) weight = mat_eval(mat, w_o, w_i_bsdf, n, true) / (TPT_EPSILON + pdf_bsdf);

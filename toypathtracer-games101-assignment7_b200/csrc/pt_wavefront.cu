@@ -3,17 +3,18 @@
 // One slot per pixel keeps the pixel's XorShift32 stream and runs its samples one after
 // another (Renderer.cpp:42-53).  Every iteration of the host loop runs
 //
-//   k_pt_shade   per active slot: fold the direct light of the previous vertex (its two
-//                shadow rays are back), take the extension hit (or start the next sample at
-//                the cached primary hit), add emission, BSDF-sample, sample the light, run the
-//                three light-object probes of DirectLightSampler (a 3-node walk, done in
-//                place), and queue: up to two shadow rays + the extension ray
+//   k_pt_shade   per active slot: fold the direct light of the previous vertex (its shadow
+//                rays are back), take the extension hit (or start the next sample at
+//                the cached primary hit), add emission, BSDF-sample, and for EVERY emissive object
+//                (PathTracer.cpp:82) sample the light and run the light-object probes of
+//                DirectLightSampler (a 3-node walk, done in place); queues up to two shadow rays
+//                per light + the extension ray
 //   k_pt_extend  closest hit for the extension rays      } persistent grid-stride kernels,
 //   k_pt_shadow  Scene::ShadowCheck for the shadow rays  } leaf tests deferred (traverse.cuh)
 //
 // Everything a pixel adds up is added by its own slot in the reference's order, so the
-// image is bit-reproducible run to run.  The pipeline handles one emissive object (all
-// BASELINE scenes); scenes with several lights use the per-pixel kernel (tpt.cu).
+// image is bit-reproducible run to run.  Up to PT_MAX_LIGHTS emissive objects (one bit of
+// `vis` per shadow ray of a slot).
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -36,8 +37,10 @@ struct PtCounters {
 #define PT_RUNNING (1u << 4)
 #define PT_BOUNCES(i) ((i) >> 8)
 
+#define PT_MAX_LIGHTS 16
 struct PtBuffers {
     int S;
+    int nl;                           // emissive objects of the scene
     uint32_t* rng;
     unsigned* info;
     unsigned* spp_done;
@@ -45,8 +48,8 @@ struct PtBuffers {
     float4 *prim_hit;                 // cached primary hit {coords, asfloat(prim)}
     float4 *prim_dir;                 // primary ray direction
     float4 *ray_o, *ray_d, *hit;      // extension ray {o, cull (<0: none)} {d} -> {coords, prim}
-    float4 *dl_alpha, *dl_e1, *dl_e2; // direct light of the last vertex: alpha, E1, E2 (w = 1: shadow ray queued)
-    float4 *sh_from, *sh_to;          // [2 * S]: shadow ray j of slot s at [j * S + s]; from.w < 0: none
+    float4 *dl_alpha, *dl_e1, *dl_e2; // direct light of the last vertex: alpha; E1, E2 of light l at [l * S + s] (w = 1: shadow ray queued)
+    float4 *sh_from, *sh_to;          // [2 * nl * S]: shadow ray j = 2 l + {0, 1} of slot s at [j * S + s]; from.w < 0: none
     unsigned* vis;                    // bit j: shadow ray j found the light visible
     int* active[2];
     PtCounters* ctr;
@@ -91,8 +94,6 @@ __global__ void __launch_bounds__(256, PT_SHADE_MIN_BLOCKS) k_pt_shade(SceneView
     int* next_list = b.active[cur ^ 1];
     const bool full = a.mode == TPT_MODE_PT_FULL;
     const float inv_spp = 1.0f / a.spp_total;
-    const int light = sc.emissive[0];
-    const Mat lightMat = load_mat(sc, sc.objs[light].material);
     unsigned long long ref_rays = 0, samples = 0;
     const unsigned total = (n + 31u) & ~31u;
     for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
@@ -110,18 +111,20 @@ __global__ void __launch_bounds__(256, PT_SHADE_MIN_BLOCKS) k_pt_shade(SceneView
             const unsigned vis = b.vis[slot];
             const float4 hr = b.hit[slot], rd = b.ray_d[slot], ph = b.prim_hit[slot], pd = b.prim_dir[slot];
             const float4 al = b.alpha[slot], ra = b.rad[slot], ac = b.acc[slot];
-            const float4 da = b.dl_alpha[slot], e1 = b.dl_e1[slot], e2 = b.dl_e2[slot];
+            const float4 da = b.dl_alpha[slot];
             alpha = mk3(al); rad = mk3(ra); acc = mk3(ac);
             bounces = PT_BOUNCES(info);
             keep = true;
 
             // ---- the direct light of the previous vertex (PathTracer.cpp:90-105), in the reference's order
-            if (info & PT_DIRECT) {
-                f3 eval_result = mk3(0.0f);
-                if (e1.w != 0.0f && (vis & 1u)) eval_result += mk3(e1);
-                if (e2.w != 0.0f && (vis & 2u)) eval_result += mk3(e2);
-                rad += (mk3(da) * eval_result) * lightMat.emission;
-            }
+            if (info & PT_DIRECT)
+                for (int l = 0; l < b.nl; ++l) {                          // one `resultRadiance +=` per light (PathTracer.cpp:105)
+                    const float4 e1 = b.dl_e1[(size_t)l * b.S + slot], e2 = b.dl_e2[(size_t)l * b.S + slot];
+                    f3 eval_result = mk3(0.0f);
+                    if (e1.w != 0.0f && ((vis >> (2 * l)) & 1u)) eval_result += mk3(e1);
+                    if (e2.w != 0.0f && ((vis >> (2 * l + 1)) & 1u)) eval_result += mk3(e2);
+                    rad += (mk3(da) * eval_result) * load_mat(sc, sc.objs[sc.emissive[l]].material).emission;
+                }
 
             bool done = false;
             if (info & PT_EXT) {
@@ -161,7 +164,7 @@ __global__ void __launch_bounds__(256, PT_SHADE_MIN_BLOCKS) k_pt_shade(SceneView
         __syncwarp();
         unsigned nflags = 0;
         float4 ro = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-        float4 s1f = make_float4(0.f, 0.f, 0.f, -1.0f), s2f = s1f;
+        const float4 no_ray = make_float4(0.f, 0.f, 0.f, -1.0f);
         if (shadeNow) {
             const Mat mat = load_mat(sc, prim_material(sc, hprim));
             const bool explicitLight = (info & PT_EXPLICIT) != 0;
@@ -169,37 +172,43 @@ __global__ void __launch_bounds__(256, PT_SHADE_MIN_BLOCKS) k_pt_shade(SceneView
             const f3 x = hx, w_o = -rdir, nrm = hit_normal(sc, hprim, hx);
             float pdf_bsdf;
             const f3 w_i_bsdf = mat_sample(mat, rng, w_o, nrm, &pdf_bsdf);          // :76
-            // ---- DirectLightSampler + MIS (:82-105); the light probes run in place
-            float pdf_light_light;
-            const f3 w_i_light = light_sample_dir(c, light, rng, x, &pdf_light_light);
-            const float pdf_light_bsdf = mat_pdf(mat, w_o, nrm, w_i_light);
-            // the light object along the BSDF direction, NoCull (DirectLightSampler::pdf) and CullBack (:93), in one walk
-            DHit hl, inte_bsdf;
-            object_intersect_dual(sc, light, make_ray(x, w_i_bsdf), &hl, &inte_bsdf);
-            c.probe_rays++;
-            const float pdf_bsdf_light = light_pdf_from_hit(sc, light, hl, x, w_i_bsdf);
-            f3 E1 = mk3(0.0f), E2 = mk3(0.0f);
-            float q1 = 0.0f, q2 = 0.0f;
-            if (pdf_bsdf + pdf_bsdf_light > 0.0f) {
-                const DHit inte = inte_bsdf;
+            // ---- DirectLightSampler + MIS for every emissive object (:82-105); the light probes run in place
+            for (int l = 0; l < b.nl; ++l) {
+                const int light = sc.emissive[l];
+                float pdf_light_light;
+                const f3 w_i_light = light_sample_dir(c, light, rng, x, &pdf_light_light);
+                const float pdf_light_bsdf = mat_pdf(mat, w_o, nrm, w_i_light);
+                // the light object along the BSDF direction, NoCull (DirectLightSampler::pdf) and CullBack (:93), in one walk
+                DHit hl, inte_bsdf;
+                object_intersect_dual(sc, light, make_ray(x, w_i_bsdf), &hl, &inte_bsdf);
                 c.probe_rays++;
-                if (inte.prim >= 0) {
-                    E1 = mat_eval(mat, w_o, w_i_bsdf, nrm, true) / (TPT_EPSILON + pdf_bsdf + pdf_bsdf_light);
-                    q1 = 1.0f;
-                    s1f = make_float4(inte.coords.x, inte.coords.y, inte.coords.z, 1.0f);
+                const float pdf_bsdf_light = light_pdf_from_hit(sc, light, hl, x, w_i_bsdf);
+                f3 E1 = mk3(0.0f), E2 = mk3(0.0f);
+                float q1 = 0.0f, q2 = 0.0f;
+                float4 s1f = no_ray, s2f = no_ray;
+                if (pdf_bsdf + pdf_bsdf_light > 0.0f) {
+                    const DHit inte = inte_bsdf;
+                    c.probe_rays++;
+                    if (inte.prim >= 0) {
+                        E1 = mat_eval(mat, w_o, w_i_bsdf, nrm, true) / (TPT_EPSILON + pdf_bsdf + pdf_bsdf_light);
+                        q1 = 1.0f;
+                        s1f = make_float4(inte.coords.x, inte.coords.y, inte.coords.z, 1.0f);
+                    }
                 }
-            }
-            if (pdf_light_light + pdf_light_bsdf > 0.0f) {
-                DHit inte;
-                trace_object<false>(c, light, make_ray(x, w_i_light), 0, &inte);
-                // inte.happened is not checked by the reference: a miss shadow-tests from (0,0,0)
-                E2 = mat_eval(mat, w_o, w_i_light, nrm, true) / (TPT_EPSILON + pdf_light_light + pdf_light_bsdf);
-                q2 = 1.0f;
-                s2f = make_float4(inte.coords.x, inte.coords.y, inte.coords.z, 1.0f);
+                if (pdf_light_light + pdf_light_bsdf > 0.0f) {
+                    DHit inte;
+                    trace_object<false>(c, light, make_ray(x, w_i_light), 0, &inte);
+                    // inte.happened is not checked by the reference: a miss shadow-tests from (0,0,0)
+                    E2 = mat_eval(mat, w_o, w_i_light, nrm, true) / (TPT_EPSILON + pdf_light_light + pdf_light_bsdf);
+                    q2 = 1.0f;
+                    s2f = make_float4(inte.coords.x, inte.coords.y, inte.coords.z, 1.0f);
+                }
+                b.dl_e1[(size_t)l * b.S + slot] = make_float4(E1.x, E1.y, E1.z, q1);
+                b.dl_e2[(size_t)l * b.S + slot] = make_float4(E2.x, E2.y, E2.z, q2);
+                b.sh_from[(size_t)(2 * l) * b.S + slot] = s1f;
+                b.sh_from[(size_t)(2 * l + 1) * b.S + slot] = s2f;
             }
             b.dl_alpha[slot] = make_float4(alpha.x, alpha.y, alpha.z, 0.0f);
-            b.dl_e1[slot] = make_float4(E1.x, E1.y, E1.z, q1);
-            b.dl_e2[slot] = make_float4(E2.x, E2.y, E2.z, q2);
             b.sh_to[slot] = make_float4(x.x, x.y, x.z, 0.0f);
             nflags = PT_RUNNING | PT_DIRECT | PT_EXPLICIT;
             if (full) {
@@ -224,8 +233,8 @@ __global__ void __launch_bounds__(256, PT_SHADE_MIN_BLOCKS) k_pt_shade(SceneView
         }
         if (live) {
             b.ray_o[slot] = ro;
-            b.sh_from[slot] = s1f;
-            b.sh_from[(size_t)b.S + slot] = s2f;
+            if (!shadeNow) for (int j = 0; j < 2 * b.nl; ++j) b.sh_from[(size_t)j * b.S + slot] = no_ray;
+            if (b.nl > 1) b.vis[slot] = 0u;               // k_pt_shadow ORs the visible rays' bits in
             b.rng[slot] = rng;
             b.alpha[slot] = make_float4(alpha.x, alpha.y, alpha.z, 0.0f);
             b.rad[slot] = make_float4(rad.x, rad.y, rad.z, 0.0f);
@@ -278,11 +287,12 @@ __global__ void __launch_bounds__(256) k_pt_shadow(SceneView g, PtBuffers b, int
     const unsigned n = b.ctr->n_active[cur];
     const int* list = b.active[cur];
     unsigned long long rays = 0;
-    const unsigned total = (2u * n + 31u) & ~31u;
+    const unsigned R = 2u * (unsigned)b.nl;          // shadow rays per slot: thread R q + j handles ray j of queue entry q
+    const unsigned total = (R * n + 31u) & ~31u;
     for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
-        const bool live = k < 2u * n;
-        const int slot = live ? list[k >> 1] : 0;
-        const unsigned j = k & 1u;
+        const bool live = k < R * n;
+        const int slot = live ? list[k / R] : 0;
+        const unsigned j = k % R;
         bool visible = false, has_ray = false;
         float4 from = make_float4(0.f, 0.f, 0.f, -1.f), to = make_float4(0.f, 0.f, 1.f, 0.f);
         if (live) {
@@ -290,9 +300,13 @@ __global__ void __launch_bounds__(256) k_pt_shadow(SceneView g, PtBuffers b, int
             if (from.w > 0.0f) { to = b.sh_to[slot]; has_ray = true; rays++; }
         }
         if (has_ray) visible = !shadow_check_deferred(sc, mk3(from), mk3(to), 0, cand, blockDim.x);   // Scene::ShadowCheck(inte.coords, x)
-        // the two lanes of a slot are neighbours: combine their bits with a shuffle, lane j == 0 writes
-        const unsigned other = __shfl_down_sync(0xffffffffu, visible ? 1u : 0u, 1);
-        if (live && j == 0) b.vis[slot] = (visible ? 1u : 0u) | (other << 1);
+        if (R == 2u) {
+            // one light: the two lanes of a slot are neighbours; combine their bits with a shuffle, lane j == 0 writes
+            const unsigned other = __shfl_down_sync(0xffffffffu, visible ? 1u : 0u, 1);
+            if (live && j == 0) b.vis[slot] = (visible ? 1u : 0u) | (other << 1);
+        } else if (visible) {
+            atomicOr(&b.vis[slot], 1u << j);             // several lights: k_pt_shade cleared the word when it queued the rays
+        }
     }
     flush_stats(0, rays, 0, stats, rays);
 }
@@ -340,14 +354,15 @@ void pt_wavefront_destroy(TptScene* s) {
     s->ptwf = nullptr;
 }
 
-static int pt_alloc(PtPipe& w, int S) {
-    if (w.S == S && !w.allocs.empty()) return TPT_OK;
+static int pt_alloc(PtPipe& w, int S, int nl) {
+    if (w.S == S && w.b.nl == nl && !w.allocs.empty()) return TPT_OK;
     if (!w.allocs.empty()) cudaDeviceSynchronize();      // a different share: the previous one's launches may still be running
     pt_pipe_free(w);
     w.S = S;
     std::memset(&w.b, 0, sizeof w.b);
     PtBuffers& b = w.b;
     b.S = S;
+    b.nl = nl;
     auto get = [&](size_t bytes, void** out) -> bool {
         void* p = tpt_dev_alloc(bytes);
         if (!p) return false;
@@ -360,8 +375,8 @@ static int pt_alloc(PtPipe& w, int S) {
               get(F4, (void**)&b.alpha) && get(F4, (void**)&b.rad) &&
               get(F4, (void**)&b.acc) && get(F4, (void**)&b.prim_hit) && get(F4, (void**)&b.prim_dir) &&
               get(F4, (void**)&b.ray_o) && get(F4, (void**)&b.ray_d) && get(F4, (void**)&b.hit) &&
-              get(F4, (void**)&b.dl_alpha) && get(F4, (void**)&b.dl_e1) && get(F4, (void**)&b.dl_e2) &&
-              get(2 * F4, (void**)&b.sh_from) && get(F4, (void**)&b.sh_to) && get(U, (void**)&b.vis) &&
+              get(F4, (void**)&b.dl_alpha) && get(nl * F4, (void**)&b.dl_e1) && get(nl * F4, (void**)&b.dl_e2) &&
+              get(2 * nl * F4, (void**)&b.sh_from) && get(F4, (void**)&b.sh_to) && get(U, (void**)&b.vis) &&
               get(U, (void**)&b.active[0]) && get(U, (void**)&b.active[1]) && get(sizeof(PtCounters), (void**)&b.ctr);
     if (ok && !(w.h_flag = static_cast<unsigned*>(tpt_pinned_alloc(64)))) ok = false;
     if (!ok) { pt_pipe_free(w); return TPT_ERR_OOM; }
@@ -369,6 +384,7 @@ static int pt_alloc(PtPipe& w, int S) {
 }
 
 int pt_wavefront_render(TptScene* s, const RenderArgs& a0, float* d_radiance, cudaStream_t st, KernelTimer* tm) {
+    if (s->view.n_emissive > PT_MAX_LIGHTS) { tpt_set_error("PathTrace: more than 16 emissive objects"); return TPT_ERR_INVALID; }
     const int npix = s->view.width * s->view.height;
     if (!s->ptwf) s->ptwf = new PtWavefrontState;
     PtWavefrontState* W = s->ptwf;
@@ -391,7 +407,7 @@ int pt_wavefront_render(TptScene* s, const RenderArgs& a0, float* d_radiance, cu
         PtPipe& w = W->pipe[p];
         args[p] = a0; args[p].sub = p; args[p].nsub = npipes;
         const int S = tpt_part_slots(args[p], npix);
-        int rc = pt_alloc(w, S);
+        int rc = pt_alloc(w, S, s->view.n_emissive);
         if (rc != TPT_OK) return rc;
         if (two && !w.side) {
             TPT_CUDA(cudaStreamCreateWithFlags(&w.side, cudaStreamNonBlocking));
@@ -427,7 +443,7 @@ int pt_wavefront_render(TptScene* s, const RenderArgs& a0, float* d_radiance, cu
             if (two) TPT_CUDA(cudaEventRecord(w.ev_side, ss[p]));
             cur[p] ^= 1;
         }
-        if ((it & 7) == 7) {
+        if ((it & 7) == 7 || it + 1 == max_iters) {
             bool any = false;
             for (int p = 0; p < npipes; ++p)
                 if (live[p]) TPT_CUDA(cudaMemcpyAsync(W->pipe[p].h_flag, &W->pipe[p].b.ctr->n_active[cur[p]], sizeof(unsigned), cudaMemcpyDeviceToHost, ms[p]));
@@ -440,11 +456,14 @@ int pt_wavefront_render(TptScene* s, const RenderArgs& a0, float* d_radiance, cu
             if (!any) break;
         }
     }
+    bool unfinished = false;                 // only if max_iters ran out (never seen): an incomplete frame must not pass for a frame
+    for (int p = 0; p < npipes; ++p) unfinished = unfinished || live[p];
     for (int p = 0; p < npipes; ++p) {       // everything joins the caller's stream
         PtPipe& w = W->pipe[p];
         if (two) TPT_CUDA(cudaStreamWaitEvent(ms[p], w.ev_side, 0));
         if (p > 0) { TPT_CUDA(cudaEventRecord(w.ev_join, ms[p])); TPT_CUDA(cudaStreamWaitEvent(st, w.ev_join, 0)); }
     }
     TPT_CUDA(cudaGetLastError());
+    if (unfinished) { tpt_set_error("pt_wavefront_render: slots still had samples to draw when the iteration bound was reached"); return TPT_ERR_CUDA; }
     return TPT_OK;
 }

@@ -58,6 +58,7 @@ struct HostBuild {
             if (n.object >= d->n_objects) { err = "top-level leaf outside objects[]"; return false; }
             const TptObject& o = d->objects[n.object];
             DevObject& dev = objs[n.object];
+            if (dev.root >= 0) { err = "an object is referenced by two top-level leaves"; return false; }
             if (o.kind == TPT_OBJ_SPHERE) {
                 dev.root = push(n.bmin, n.bmax, d->n_tris + o.first_prim);
                 dev.end = dev.root + 1;
@@ -100,6 +101,13 @@ static int tpt_build_scene_blob(const TptSceneDesc* d, SceneBlob* out) {
     if (d->width <= 0 || d->height <= 0 || d->n_objects <= 0 || d->n_top_nodes <= 0 || d->n_materials <= 0 ||
         !d->objects || !d->top_nodes || !d->materials) {
         tpt_set_error("scene description is empty or incomplete");
+        return TPT_ERR_INVALID;
+    }
+    // every count non-negative, every array present when its count says it is read
+    if (d->n_mesh_nodes < 0 || d->n_tris < 0 || d->n_spheres < 0 || d->n_emissive < 0 ||
+        (d->n_mesh_nodes > 0 && !d->mesh_nodes) || (d->n_tris > 0 && !d->tris) || (d->n_spheres > 0 && !d->spheres) ||
+        (d->n_emissive > 0 && !d->emissive_objects)) {
+        tpt_set_error("scene description: a negative count, or a null array with a positive count");
         return TPT_ERR_INVALID;
     }
     HostBuild hb;

@@ -706,6 +706,7 @@ static int check_params(const TptScene* s, const TptRenderParams* p, RenderArgs*
     if (!s || !p) { tpt_set_error("null argument"); return TPT_ERR_INVALID; }
     if (p->mode < TPT_MODE_PT_SHIPPED || p->mode > TPT_MODE_BDPT) { tpt_set_error("unknown mode"); return TPT_ERR_INVALID; }
     if (p->spp <= 0) { tpt_set_error("spp must be positive"); return TPT_ERR_INVALID; }
+    if (p->spp_total > 0 && p->spp_total < p->spp) { tpt_set_error("spp_total (the 1/spp weight of the frame) is smaller than this call's spp"); return TPT_ERR_INVALID; }
     const int world = p->world > 0 ? p->world : 1;
     if (p->rank < 0 || p->rank >= world) { tpt_set_error("rank outside world"); return TPT_ERR_INVALID; }
     if (p->mode == TPT_MODE_BDPT && s->view.n_emissive == 0) { tpt_set_error("BDPT needs an emissive object (BDPT.cpp:287)"); return TPT_ERR_INVALID; }
@@ -720,11 +721,27 @@ static int check_params(const TptScene* s, const TptRenderParams* p, RenderArgs*
     return TPT_OK;
 }
 
+namespace {
+struct EventPair {       // destroyed on every return path
+    cudaEvent_t a = nullptr, b = nullptr;
+    bool create() { return cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess; }
+    ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+};
+// One render in flight per scene handle: the handle owns ONE set of work buffers (path store, queues, counters).
+struct RenderGuard {
+    TptScene* s; bool held;
+    explicit RenderGuard(TptScene* sc) : s(sc), held(!sc->rendering.exchange(true)) {}
+    ~RenderGuard() { if (held) s->rendering.store(false); }
+};
+}  // namespace
+
 extern "C" int tpt_render_device(TptScene* s, const TptRenderParams* p, float* d_accum, void* stream, TptStats* stats) {
     RenderArgs a;
     int rc = check_params(s, p, &a);
     if (rc != TPT_OK) return rc;
     if (!d_accum) { tpt_set_error("null accumulation buffer"); return TPT_ERR_INVALID; }
+    RenderGuard guard(s);
+    if (!guard.held) { tpt_set_error("tpt_render_device: another render is in flight on this scene handle (one at a time: the handle owns one set of work buffers)"); return TPT_ERR_INVALID; }
     TPT_CUDA(cudaSetDevice(s->device));
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n3 = (size_t)s->view.width * s->view.height * 3;
@@ -734,13 +751,11 @@ extern "C" int tpt_render_device(TptScene* s, const TptRenderParams* p, float* d
     KernelTimer timer;
     timer.on = a.kernel_times != 0 && stats != nullptr;
     timer.stream = st;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (stats) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
+    EventPair ev;
+    if (stats) { if (!ev.create()) { tpt_set_error("cudaEventCreate failed"); return TPT_ERR_CUDA; } cudaEventRecord(ev.a, st); }
     TPT_CUDA(cudaMemsetAsync(d_accum, 0, 2 * n3 * sizeof(float), st));
     TPT_CUDA(cudaMemsetAsync(s->d_stats, 0, STAT_COUNT * sizeof(unsigned long long), st));
-    // the PathTrace queue pipeline handles one emissive object; other light counts use the per-pixel kernel
-    const bool pt_queue_ok = s->view.n_emissive == 1;
-    if (p->pipeline == TPT_PIPE_MEGAKERNEL || (a.mode != TPT_MODE_BDPT && !pt_queue_ok)) {
+    if (p->pipeline == TPT_PIPE_MEGAKERNEL) {
         const int npix = s->view.width * s->view.height;
         const int slots = tpt_part_slots(a, npix);
         const int grid = (slots + 127) / 128;
@@ -751,7 +766,14 @@ extern "C" int tpt_render_device(TptScene* s, const TptRenderParams* p, float* d
     } else {
         rc = a.mode == TPT_MODE_BDPT ? wavefront_render(s, a, d_radiance, d_splat, st, &timer)
                                      : pt_wavefront_render(s, a, d_radiance, st, &timer);
-        if (rc != TPT_OK) return rc;
+        if (rc != TPT_OK) {
+            // launch chains may still be running on the pipeline's own streams: nothing may be reused or freed under them
+            const std::string why = tpt_last_error();
+            cudaDeviceSynchronize();
+            cudaGetLastError();
+            tpt_set_error(why);
+            return rc;
+        }
         for (int k = 0; k < 8; ++k) launches += timer.launches[k];
     }
     if (a.mode == TPT_MODE_BDPT) {
@@ -760,12 +782,11 @@ extern "C" int tpt_render_device(TptScene* s, const TptRenderParams* p, float* d
         launches += 1;
     }
     if (stats) {
-        cudaEventRecord(e1, st);
-        TPT_CUDA(cudaEventSynchronize(e1));
+        cudaEventRecord(ev.b, st);
+        TPT_CUDA(cudaEventSynchronize(ev.b));
         std::memset(stats, 0, sizeof *stats);
         float ms = 0;
-        cudaEventElapsedTime(&ms, e0, e1);
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        cudaEventElapsedTime(&ms, ev.a, ev.b);
         read_stats(s, stats);
         stats->device_ms = ms;
         stats->launches = launches;

@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -22,6 +23,7 @@ struct TptScene {
     unsigned long long* d_stats = nullptr;   // 8 counters, see STAT_*
     WavefrontState* wf = nullptr;   // lazily created work buffers of the BDPT wavefront pipeline
     PtWavefrontState* ptwf = nullptr;   // ... of the PathTrace wavefront pipeline
+    std::atomic<bool> rendering{false};  // one render in flight per handle (it owns ONE set of work buffers)
 };
 
 enum { STAT_REF_RAYS = 0, STAT_SCENE_RAYS, STAT_PROBE_RAYS, STAT_NODE_VISITS, STAT_PRIM_TESTS, STAT_SAMPLES, STAT_SHADOW_RAYS, STAT_COUNT = 8 };

@@ -871,6 +871,8 @@ int wavefront_render(TptScene* s, const RenderArgs& a, float* d_radiance, float*
     const char* env_two = getenv("TPT_WF_TWO_STREAMS");
     const bool two = !tm->on && !(env_two && atoi(env_two) == 0);
     if (two && !w->side[0]) {
+        // (measured, round 2: giving these streams a higher priority than k_path's costs 4 %, capping k_path's blocks
+        // per SM with shared memory to leave room for a strategy block 8-14 %: profiles/r02g_ab_schedule.log)
         for (int k = 0; k < WF_CHAINS; ++k) {
             TPT_CUDA(cudaStreamCreateWithFlags(&w->side[k], cudaStreamNonBlocking));
             TPT_CUDA(cudaEventCreateWithFlags(&w->ev_path[k], cudaEventDisableTiming));

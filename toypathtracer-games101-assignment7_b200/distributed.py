@@ -91,10 +91,18 @@ def pixels_of(share, npix):
     return range(npix)
 
 
-def reduce_frame(accum, dst=0, group=None):
-    """The one exchange step: sum the [radiance | splat] accumulators onto rank `dst`."""
+def reduce_frame(accum, dst=0, group=None, cuda_stream=None):
+    """The one exchange step: sum the [radiance | splat] accumulators onto rank `dst`.  The collective is ordered
+    against torch's CURRENT stream; when the render was queued on another stream (`cuda_stream`, a raw handle), the
+    reduce is issued with that stream current so that it follows the render and precedes the merge."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        if cuda_stream is not None and accum.is_cuda:
+            import torch
+            if torch.cuda.current_stream().cuda_stream != cuda_stream:
+                with torch.cuda.stream(torch.cuda.ExternalStream(cuda_stream)):
+                    dist.reduce(accum, dst=dst, op=dist.ReduceOp.SUM, group=group)
+                return accum
         dist.reduce(accum, dst=dst, op=dist.ReduceOp.SUM, group=group)
     return accum
 
@@ -108,12 +116,15 @@ def render_frame(scene, mode, spp_total, accum, out=None, strategy="spp", rank=0
     render  test hook: callable(share, accum) used instead of the GPU call
     Returns the stats dict of this rank's render (or None)."""
     share = plan(strategy, rank, world, spp_total, scene.width * scene.height)
+    if cuda_stream is None and render is None:
+        import torch
+        cuda_stream = torch.cuda.current_stream().cuda_stream      # never the legacy default stream behind torch's back
     if render is not None:
         st = render(share, accum)
     else:
         st = scene.render_device(mode, share.spp, accum.data_ptr(), cuda_stream=cuda_stream, want_stats=want_stats, flags=flags,
                                  **share.params())
-    reduce_frame(accum, dst=0)
+    reduce_frame(accum, dst=0, cuda_stream=cuda_stream if render is None else None)
     if rank == 0 and out is not None and render is None:
         scene.finalize_device(accum.data_ptr(), out.data_ptr(), cuda_stream=cuda_stream)
     return st

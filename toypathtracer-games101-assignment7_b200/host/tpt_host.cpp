@@ -448,7 +448,7 @@ TpthScene* tpth_scene_build(const char* sceneName, const char* modelsDir, int wi
         AddMesh(h, box + "right.obj", green);
         AddMesh(h, box + "light.obj", light);
     } else if (name == "standard" || name == "smooth" || name == "silver" || name == "refractive" ||
-               name == "occlusion") {
+               name == "occlusion" || name == "twolights") {
         AddMesh(h, box + "floor.obj", walls);
         AddMesh(h, box + "shortbox.obj", walls);
         AddMesh(h, box + "tallbox.obj", walls);
@@ -460,6 +460,12 @@ TpthScene* tpth_scene_build(const char* sceneName, const char* modelsDir, int wi
             scene.Add(h->objects.back().get());
         }
         if (name == "occlusion") AddMesh(h, box + "lightocculuder.obj", white);
+        if (name == "twolights") {   // a second emitter, a Sphere: PathTrace loops over every emissive object (PathTracer.cpp:82)
+            Material* lamp = AddMaterial(h, Dieletric, Vector3f(6.0f, 9.0f, 14.0f));
+            lamp->Kd = Vector3f(0.65f);
+            h->objects.emplace_back(new Sphere(Vector3f(400.0f, 90.0f, 120.0f), 40.0f, lamp));
+            scene.Add(h->objects.back().get());
+        }
     } else {
         h->error = "unknown scene '" + name + "'";
         return h;
