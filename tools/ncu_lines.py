@@ -36,7 +36,7 @@ def sass_lines(kernel):
                 cur_line = (os.path.basename(m.group(1)), int(m.group(2)))
                 continue
             m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", line)
-            if m and cur_fn and kernel in cur_fn:
+            if m and cur_fn and ("%d%s" % (len(kernel), kernel)) in cur_fn:      # the mangled name: k_path, not k_pathweight
                 out[int(m.group(1), 16)] = (cur_line, m.group(2).strip())
     return out
 

@@ -72,7 +72,7 @@ TPT_DEV void object_sample(const SceneView& sc, int obj, uint32_t& rng, LightPoi
         return;
     }
     const DevLightNode* nodes = sc.lnodes + o.lroot;
-    float p = sqrtf(rng_float(rng)) * nodes[0].area;   // sqrt here is the reference's (quirk Q13)
+    float p = s_sqrt(rng_float(rng)) * nodes[0].area;   // sqrt here is the reference's (quirk Q13)
     int idx = 0;
     while (!(nodes[idx].left == -1 || nodes[idx].right == -1)) {
         const float la = nodes[nodes[idx].left].area;
@@ -80,14 +80,14 @@ TPT_DEV void object_sample(const SceneView& sc, int obj, uint32_t& rng, LightPoi
         else { p = p - la; idx = nodes[idx].right; }
     }
     const int tri = nodes[idx].tri;
-    const float x = sqrtf(rng_float(rng)), y = rng_float(rng);
+    const float x = s_sqrt(rng_float(rng)), y = rng_float(rng);
     const f3 v0 = mk3(sc.tris[4 * tri]), v1 = mk3(sc.tverts[2 * tri]), v2 = mk3(sc.tverts[2 * tri + 1]);
     pos->coords = v0 * (1.0f - x) + v1 * (x * (1.0f - y)) + v2 * (x * y);
     pos->normal = mk3(sc.tris[4 * tri + 3]);
     pos->prim = tri;
 }
 // Object::pdf(): MeshTriangle 1/bvh-root area (Triangle.hpp:58-60), Sphere 1/area
-TPT_DEV float object_pdf(const SceneView& sc, int obj) { return 1.0f / sc.objs[obj].root_area; }
+TPT_DEV float object_pdf(const SceneView& sc, int obj) { return s_rcp(sc.objs[obj].root_area); }
 
 // ======================================================================= PathTrace
 // DirectLightSampler::pdf, PathTracer.cpp:14-24
@@ -195,7 +195,7 @@ TPT_DEV float srpdf_to_area(float srpdf, f3 x1, f3 N1, int type1, f3 x2, f3 N2, 
     const f3 w = s_normalize_len2(x2 - x1, &distSqr);
     const float cos1 = type1 == VT_CAMERA ? 1.0f : fabsf(dotf(w, N1));
     const float cos2 = type2 == VT_CAMERA ? 1.0f : fabsf(dotf(w, N2));
-    return srpdf * fabsf(cos1 * cos2 / distSqr);
+    return srpdf * fabsf(s_div(cos1 * cos2, distSqr));
 }
 
 TPT_DEV f3 vert_normal(const PVert& v) { return v.type == VT_CAMERA ? mk3(0.0f, 0.0f, 1.0f) : v.N; }   // BDPT.hpp:91-95
@@ -321,7 +321,7 @@ TPT_DEV float append_pdf_base(const SceneView& sc, const PVert& L, int Ltype, f3
     }
     const float cos1 = Ltype == VT_CAMERA ? 1.0f : cosine;
     const float cos2 = vtype == VT_CAMERA ? 1.0f : fabsf(dotf(w, vN));
-    return srpdf * fabsf(cos1 * cos2 / distSqr);
+    return srpdf * fabsf(s_div(cos1 * cos2, distSqr));
 }
 // ... and with it: vertex number `count` of the temporary path (BDPT.cpp:162-165).
 TPT_DEV float append_pdf(const SceneView& sc, const PVert& L, int Ltype, f3 pre_x, const PVert& v, int count) {
@@ -374,7 +374,7 @@ TPT_DEV f3 connect_unweighted(const SceneView& sc, const CamPath& cam, int s, co
     *needs_shadow = shadow_query_kind(sc, z1, y);
     const f3 fl = vertex_bsdf(sc, y, t >= 2 ? light.pos(t - 2) : mk3(0.0f), dir_ltoc);
     const f3 fc = vertex_bsdf(sc, z1, s >= 2 ? cam.pos(s - 2) : mk3(0.0f), -dir_ltoc);
-    const float g = fabsf(dotf(vert_normal(y), dir_ltoc) * dotf(vert_normal(z1), dir_ltoc) / distSqr);
+    const float g = fabsf(s_div(dotf(vert_normal(y), dir_ltoc) * dotf(vert_normal(z1), dir_ltoc), distSqr));
     const f3 c_st = (fl * fc) * g;
     return (y.alpha * z1.alpha) * c_st;
 }
@@ -466,7 +466,7 @@ TPT_DEV float mis_denominator_paired(const SceneView& sc, const CamPath& cam, in
     const f3 w_zp = s_normalize_len2(zp.x - z.x, &dzp2);          // unused for s == 1
     const float cos_zp = fabsf(dotf(w_zp, Nz));
     // area-measure factor of appending zp behind z: |cos at z| * |cos at zp| / dist^2 (SrpdfToAreaPdf)
-    const float g_zp = fabsf((z.type == VT_CAMERA ? 1.0f : cos_zp) * (zp.type == VT_CAMERA ? 1.0f : fabsf(dotf(w_zp, zp.N))) / dzp2);
+    const float g_zp = fabsf(s_div((z.type == VT_CAMERA ? 1.0f : cos_zp) * (zp.type == VT_CAMERA ? 1.0f : fabsf(dotf(w_zp, zp.N))), dzp2));
     if (t == 0) {
         // light subpath empty: cam[s-1] starts the path re-typed Light with its primitive's own 1/area (quirk Q15)
         float cur = safe_div(prim_pdf(sc, z.prim), z.pdf);
@@ -474,7 +474,7 @@ TPT_DEV float mis_denominator_paired(const SceneView& sc, const CamPath& cam, in
         int count = 1;
         if (cur != 0.0f && s >= 2) {
             const float sr = safe_div(cosine_pdf(Nz, w_zp), cos_zp);
-            cur *= safe_div(sr * fabsf(cos_zp * (zp.type == VT_CAMERA ? 1.0f : fabsf(dotf(w_zp, zp.N))) / dzp2) * (count > 4 ? .8f : 1.f), zp.pdf);
+            cur *= safe_div(sr * fabsf(s_div(cos_zp * (zp.type == VT_CAMERA ? 1.0f : fabsf(dotf(w_zp, zp.N))), dzp2)) * (count > 4 ? .8f : 1.f), zp.pdf);
             den += cur * cur;
             count++;
             for (int i = s - 3; i >= 0 && cur != 0.0f; --i) {
@@ -495,8 +495,8 @@ TPT_DEV float mis_denominator_paired(const SceneView& sc, const CamPath& cam, in
     const f3 w_yp = s_normalize_len2(yp.x - y.x, &dyp2);            // unused for t == 1
     const float cos_z = fabsf(dotf(w_zy, Nz)), cos_y = fabsf(dotf(w_zy, Ny));
     const float cos_yp = fabsf(dotf(w_yp, Ny));
-    const float g_zy = fabsf((z.type == VT_CAMERA ? 1.0f : cos_z) * (y.type == VT_CAMERA ? 1.0f : cos_y) / d2);
-    const float g_yp = fabsf((y.type == VT_CAMERA ? 1.0f : cos_yp) * (yp.type == VT_CAMERA ? 1.0f : fabsf(dotf(w_yp, yp.N))) / dyp2);
+    const float g_zy = fabsf(s_div((z.type == VT_CAMERA ? 1.0f : cos_z) * (y.type == VT_CAMERA ? 1.0f : cos_y), d2));
+    const float g_yp = fabsf(s_div((y.type == VT_CAMERA ? 1.0f : cos_yp) * (yp.type == VT_CAMERA ? 1.0f : fabsf(dotf(w_yp, yp.N))), dyp2));
     const SolidPair pz = vertex_pdf_pair(sc, z, z.type, w_zp, w_zy, cos_zp, cos_z);
     const SolidPair py = vertex_pdf_pair(sc, y, y.type, w_yp, -w_zy, cos_yp, cos_y);
     {   // camera subpath extended by light[t-1], ..., light[0]
@@ -556,8 +556,8 @@ TPT_DEV void splat_to_image(const SceneView& sc, f3 light_x, f3 value, float* sp
     if (value.x == 0.0f && value.y == 0.0f && value.z == 0.0f) return;   // adding zeros
     f3 d = s_normalize(light_x - mk3(sc.eye.x, sc.eye.y, sc.eye.z));
     d = d / d.z;
-    const float u = (-d.x / sc.scale / sc.aspect + 1.0f) * 0.5f;
-    const float v = (-d.y / sc.scale + 1.0f) * 0.5f;
+    const float u = (s_div(s_div(-d.x, sc.scale), sc.aspect) + 1.0f) * 0.5f;
+    const float v = (s_div(-d.y, sc.scale) + 1.0f) * 0.5f;
     const float sx = u * sc.width, sy = v * sc.height;
     if (!(fabsf(sx) < 1e9f && fabsf(sy) < 1e9f)) return;   // (int) of these is INT_MIN on the CPU: nothing drawn
     const int cx = (int)sx, cy = (int)sy;

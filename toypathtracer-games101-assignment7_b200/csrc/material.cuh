@@ -23,16 +23,16 @@ TPT_DEV f3 refract_dir(f3 I, f3 N, float ior) {           // Refract, .cpp:37-48
     float etai = 1, etat = ior;
     f3 n = N;
     if (cosi < 0) { cosi = -cosi; } else { float s = etai; etai = etat; etat = s; n = -N; }
-    const float eta = etai / etat;
+    const float eta = s_div(etai, etat);
     const float k = __fsub_rn(1.0f, __fmul_rn(__fmul_rn(eta, eta), __fsub_rn(1.0f, __fmul_rn(cosi, cosi))));
     if (k < 0) return mk3(0.0f);
-    return s_normalize_exact(eta * I + (eta * cosi - sqrtf(k)) * n);
+    return s_normalize_exact(eta * I + (eta * cosi - s_sqrt(k)) * n);
 }
 TPT_DEV f3 any_perpendicular(f3 i) {                       // AnyPerpendicular, .cpp:51-67
     // the three cases as selects and ONE normalisation: lanes shading walls with different normals stay
     // together ((0,1,0) normalises to itself, so the first case is unchanged)
     const bool z0 = i.z == 0.0f, y0 = i.y == 0.0f;
-    const float q = z0 ? -i.x / i.y : -1.0f * i.y / i.z;
+    const float q = z0 ? s_div(-i.x, i.y) : s_div(-1.0f * i.y, i.z);
     const f3 v = z0 ? (y0 ? mk3(0.0f, 1.0f, 0.0f) : mk3(1.0f, q, 0.0f)) : mk3(0.0f, 1.0f, q);
     return s_normalize(v);
 }
@@ -58,12 +58,12 @@ TPT_DEV f3 half_dir(f3 N, f3 wi, f3 wo, float matIor, float nl, float nv) {   //
 TPT_DEV float cosine_pdf(f3 N, f3 wi) { return saturate_f(dotf(wi, N)) / TPT_PI; }   // .hpp:118-120
 TPT_DEV f3 cosine_sample(uint32_t& rng, f3 N, float* pdf) {                            // .hpp:105-115
     const float u1 = rng_float(rng);
-    const float r = sqrtf(u1);
+    const float r = s_sqrt(u1);
     const float theta = 2 * TPT_PI * rng_float(rng);
     float sn, cs;
     sincosf(theta, &sn, &cs);
     const float x = r * cs, y = r * sn;
-    const f3 wi = s_normalize_exact(to_world(mk3(x, y, sqrtf(1.0f - u1)), N));
+    const f3 wi = s_normalize_exact(to_world(mk3(x, y, s_sqrt(1.0f - u1)), N));
     *pdf = dotf(wi, N) / TPT_PI;
     return wi;
 }
@@ -72,17 +72,17 @@ TPT_DEV f3 cosine_sample(uint32_t& rng, f3 N, float* pdf) {                     
 TPT_DEV float ggx_visibility(float vn, float vh, float roughness) {   // Visibility, :8-14
     if (vh * vn <= 0.0f) return 0.0f;
     const float vh2 = __fmul_rn(vh, vh);
-    const float tan2 = __fsub_rn(1.0f, vh2) / vh2;
-    return 2.0f / (1 + sqrtf(__fadd_rn(1.0f, __fmul_rn(__fmul_rn(roughness, roughness), tan2))));
+    const float tan2 = s_div(__fsub_rn(1.0f, vh2), vh2);
+    return s_div(2.0f, 1 + s_sqrt(__fadd_rn(1.0f, __fmul_rn(__fmul_rn(roughness, roughness), tan2))));
 }
 TPT_DEV float ggx_term(float ndoth, float roughness) {                 // GGXTerm, :17-30
     const float a2 = __fmul_rn(roughness, roughness);
     const float c2 = __fmul_rn(ndoth, ndoth);
     const float c4 = __fmul_rn(c2, c2);
-    const float tan2 = __fsub_rn(1.0f, c2) / c2;
+    const float tan2 = s_div(__fsub_rn(1.0f, c2), c2);
     float den = __fadd_rn(a2, tan2);
     den = __fmul_rn(den, den);
-    return a2 / __fmul_rn(__fmul_rn(TPT_PI, c4), den);
+    return s_div(a2, __fmul_rn(__fmul_rn(TPT_PI, c4), den));
 }
 TPT_DEV float ggx_half_pdf(f3 n, f3 h, float roughness) {              // GGXHalfPDF, :33-35
     const double a = fabs(dotd(n, h));
@@ -92,9 +92,9 @@ TPT_DEV f3 ggx_sample_h(uint32_t& rng, f3 N, float roughness) {        // Sample
     const float d1 = rng_float(rng), d2 = rng_float(rng);
     // theta = atan2(rough * sqrt(d1), sqrt(1 - d1)); only its sine and cosine are used, and those
     // are the two legs over the hypotenuse — no atan2 / sincos round trip (same values to an ulp)
-    const float ly = roughness * sqrtf(d1), lx = sqrtf(1.0f - d1);
-    const float hyp = sqrtf(lx * lx + ly * ly);
-    const float st = ly / hyp, ct = lx / hyp;
+    const float ly = roughness * s_sqrt(d1), lx = s_sqrt(1.0f - d1);
+    const float hyp = s_sqrt(lx * lx + ly * ly);
+    const float st = s_div(ly, hyp), ct = s_div(lx, hyp);
     const float phi = 2.0f * TPT_PI * d2;
     float sp, cp;
     sincosf(phi, &sp, &cp);
@@ -117,13 +117,13 @@ TPT_DEV f3 mat_fresnel(const Mat& m, f3 I, f3 N) {                     // fresne
     float cosi = std_clamp(dotf(I, N), -1.f, 1.f);
     float etai = 1, etat = m.ior_d;
     if (cosi > 0) { float s = etai; etai = etat; etat = s; }
-    const float sint = etai / etat * sqrtf(std_max(0.f, __fsub_rn(1.0f, __fmul_rn(cosi, cosi))));
+    const float sint = s_div(etai, etat) * s_sqrt(std_max(0.f, __fsub_rn(1.0f, __fmul_rn(cosi, cosi))));
     if (sint >= 1) return mk3(1.0f);
-    const float cost = sqrtf(std_max(0.f, __fsub_rn(1.0f, __fmul_rn(sint, sint))));
+    const float cost = s_sqrt(std_max(0.f, __fsub_rn(1.0f, __fmul_rn(sint, sint))));
     cosi = fabsf(cosi);
     const float tc = __fmul_rn(etat, cosi), ic = __fmul_rn(etai, cost), ii = __fmul_rn(etai, cosi), tt = __fmul_rn(etat, cost);
-    const float Rs = __fsub_rn(tc, ic) / __fadd_rn(tc, ic);
-    const float Rp = __fsub_rn(ii, tt) / __fadd_rn(ii, tt);
+    const float Rs = s_div(__fsub_rn(tc, ic), __fadd_rn(tc, ic));
+    const float Rp = s_div(__fsub_rn(ii, tt), __fadd_rn(ii, tt));
     return mk3((Rs * Rs + Rp * Rp) / 2);
 }
 
@@ -156,13 +156,13 @@ TPT_DEV f3 mat_eval(const Mat& m, f3 wo, f3 wi, f3 N, bool combineCosineTerm) {
     if (m.type != 2) return mk3(0.0f);   // refraction only through Transparent
     float ior_i, ior_o;
     if (nv < 0.0f) { ior_i = 1.0f; ior_o = m.ior_d; } else { ior_i = m.ior_d; ior_o = 1.0f; }
-    float partA = fabsf(vh) * fabsf(lh) / fabsf(nv);
-    if (!combineCosineTerm) partA /= fabsf(nl);
+    float partA = s_div(fabsf(vh) * fabsf(lh), fabsf(nv));
+    if (!combineCosineTerm) partA = s_div(partA, fabsf(nl));
     const float partB = ior_o * ior_o * (1.0f - f.x) * G * D;
     if (partA * partB == 0.0f) return mk3(0.0f);
     float partC = ior_i * lh + ior_o * vh;
     partC *= partC;
-    return mk3(partA * partB / partC);
+    return mk3(s_div(partA * partB, partC));
 }
 
 // pdf, :105-147

@@ -141,5 +141,5 @@ TPT_DEV int prim_object(const SceneView& sc, int prim) {
 }
 // pdf() of the primitive itself: Triangle::pdf (Triangle.hpp:38-40) / Sphere::pdf (Sphere.hpp:24-26)
 TPT_DEV float prim_pdf(const SceneView& sc, int prim) {
-    return prim < sc.n_tris ? 1.0f / sc.tris[4 * prim + 1].w : 1.0f / sc.spheres[2 * (prim - sc.n_tris) + 1].y;
+    return s_rcp(prim < sc.n_tris ? sc.tris[4 * prim + 1].w : sc.spheres[2 * (prim - sc.n_tris) + 1].y);
 }

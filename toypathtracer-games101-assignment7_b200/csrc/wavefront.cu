@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(256, PATH_MIN_BLOCKS) k_path(SceneView g, Rend
                 const f3 w = s_normalize_len2(prev_x - Vx, &d2);
                 const float cosine = fabsf(dotf(w, VN));
                 const float cosT = prev_type == VT_CAMERA ? 1.0f : fabsf(dotf(w, prev_N));
-                bk = make_float4(w.x, w.y, w.z, fabsf(cosine * cosT / d2));
+                bk = make_float4(w.x, w.y, w.z, fabsf(s_div(cosine * cosT, d2)));
             }
             const float rrProb = i > 4 ? .8f : 1.f;
             const bool rr_pass = !(rng_float(rng) > rrProb);      // drawn even when rrProb == 1 (quirk Q16)
