@@ -208,11 +208,19 @@ struct NextSample {
     f3 alpha;    // SafeDivide(bsdf, srpdf)
     int cull;
 };
-TPT_DEV NextSample sample_next_dir(const SceneView& sc, uint32_t& rng, f3 N, int prim, f3 w_o) {
+// ... in the three steps of mat_sample (material.cuh): the draws, the direction's tail, the rest.
+// (the material record is read again by the last step: a few shared-memory loads instead of 14 live registers)
+struct NextBegin { LocalDir local; bool diffuse; };
+TPT_DEV NextBegin sample_next_begin(const SceneView& sc, uint32_t& rng, int prim) {
+    NextBegin b;
+    b.local = mat_sample_begin(load_mat(sc, prim_material(sc, prim)), rng, &b.diffuse);
+    return b;
+}
+TPT_DEV NextSample sample_next_finish(const SceneView& sc, const NextBegin& b, uint32_t& rng, f3 N, int prim, f3 w_o, f3 w) {
     const Mat mat = load_mat(sc, prim_material(sc, prim));
     NextSample s;
     float rawpdf;
-    s.w_i = mat_sample(mat, rng, w_o, N, &rawpdf);
+    s.w_i = mat_sample_finish(mat, rng, w_o, N, w, b.diffuse, &rawpdf);
     const double nwi = dotd(N, s.w_i);
     const float costheta = (float)fabs(nwi);
     s.srpdf = safe_div(rawpdf, costheta);
@@ -220,6 +228,10 @@ TPT_DEV NextSample sample_next_dir(const SceneView& sc, uint32_t& rng, f3 N, int
     const f3 bsdf = mat_eval(mat, w_o, s.w_i, N, false);
     s.alpha = safe_div(bsdf, s.srpdf);
     return s;
+}
+TPT_DEV NextSample sample_next_dir(const SceneView& sc, uint32_t& rng, f3 N, int prim, f3 w_o) {
+    const NextBegin b = sample_next_begin(sc, rng, prim);
+    return sample_next_finish(sc, b, rng, N, prim, w_o, local_to_world(b.local, N));
 }
 // Deliberate deviations from the reference, both only where the reference itself produces NaN:
 //  * a subpath ends at a vertex whose area pdf is not a positive finite number.  BDPT.cpp:110 stops
@@ -278,19 +290,27 @@ TPT_DEV void camera_path_head(const SceneView& sc, const DHit& primary, PVert* v
 
 // BDPTPath::GenerateLightPath up to its first ray, BDPT.cpp:61-77
 struct LightStart { f3 w_i; float pdf1; };
-TPT_DEV LightStart light_path_head(const SceneView& sc, uint32_t& rng, int lightObj, PVert* verts) {
-    LightPoint t;
-    object_sample(sc, lightObj, rng, &t);
+// (the same three steps: the light point and the draws of the cosine sample, the direction's tail, the pdf)
+TPT_DEV LocalDir light_path_begin(const SceneView& sc, uint32_t& rng, int lightObj, LightPoint* t) {
+    object_sample(sc, lightObj, rng, t);
+    return cosine_local(rng);
+}
+TPT_DEV LightStart light_path_finish(const SceneView& sc, int lightObj, const LightPoint& t, f3 w, PVert* verts) {      // w: local_to_world(.., t.normal)
     verts[0].x = t.coords; verts[0].type = VT_LIGHT; verts[0].prim = t.prim; verts[0].N = t.normal;
     verts[0].pdf = object_pdf(sc, lightObj);
     const Mat lm = load_mat(sc, sc.objs[lightObj].material);
     verts[0].alpha = lm.emission / verts[0].pdf;
     LightStart s;
-    float pdf1;
-    s.w_i = cosine_sample(rng, t.normal, &pdf1);
+    s.w_i = w;
+    const float pdf1 = dotf(w, verts[0].N) / TPT_PI;              // cosine_sample's pdf
     const float costheta = dotf(verts[0].N, s.w_i);
     s.pdf1 = safe_div(pdf1, costheta);
     return s;
+}
+TPT_DEV LightStart light_path_head(const SceneView& sc, uint32_t& rng, int lightObj, PVert* verts) {
+    LightPoint t;
+    const LocalDir l = light_path_begin(sc, rng, lightObj, &t);
+    return light_path_finish(sc, lightObj, t, local_to_world(l, t.normal), verts);
 }
 // ... and after it, BDPT.cpp:79-90.  Returns false when the path stops at 2 vertices
 // without entering FillPathUsingRussianRoulette.

@@ -45,25 +45,35 @@ TPT_DEV f3 to_world(f3 a, f3 N) {                          // TransformVectorToW
 }
 TPT_DEV f3 half_dir(f3 N, f3 wi, f3 wo, float matIor, float nl, float nv) {   // GetHalfDir, .hpp:79-102
     if (nl == 0.0f || nv == 0.0f) return mk3(0.0f);
-    f3 h;
-    if (nl * nv > 0.0f) {
-        h = s_normalize_exact(wi + wo);
-        if (nv < 0.0f) h = -h;
-    } else {
-        if (nv < 0.0f) h = -s_normalize_exact(matIor * wo + wi);
-        else h = -s_normalize_exact(wo + wi * matIor);
-    }
-    return h;
+    // wi + wo (reflection), -(matIor * wo + wi) or -(wo + wi * matIor) (refraction): one expression k * p + q with
+    // selected operands (1 * p is exact), so there is ONE normalisation in the code and the lanes of a warp stay together
+    const bool refl = nl * nv > 0.0f;
+    const bool scale_wo = refl || nv < 0.0f;
+    const float k = refl ? 1.0f : matIor;
+    const f3 p = scale_wo ? wo : wi, q = scale_wo ? wi : wo;
+    const f3 h = s_normalize_exact(k * p + q);
+    return (refl && !(nv < 0.0f)) ? h : -h;
 }
 TPT_DEV float cosine_pdf(f3 N, f3 wi) { return saturate_f(dotf(wi, N)) / TPT_PI; }   // .hpp:118-120
-TPT_DEV f3 cosine_sample(uint32_t& rng, f3 N, float* pdf) {                            // .hpp:105-115
-    const float u1 = rng_float(rng);
-    const float r = s_sqrt(u1);
-    const float theta = 2 * TPT_PI * rng_float(rng);
+// A sampled direction before it is turned into world space: (rad cos(angle), rad sin(angle), z) around a normal.
+// Both samplers (cosine-weighted hemisphere, GGX half vector) end in the same sincos / TransformVectorToWorld /
+// normalisation; the wavefront kernel runs that tail ONCE for all lanes of a warp, whichever sampler they used.
+struct LocalDir { float rad, z, angle; };
+TPT_DEV f3 local_to_world(const LocalDir& l, f3 N) {
     float sn, cs;
-    sincosf(theta, &sn, &cs);
-    const float x = r * cs, y = r * sn;
-    const f3 wi = s_normalize_exact(to_world(mk3(x, y, s_sqrt(1.0f - u1)), N));
+    sincosf(l.angle, &sn, &cs);
+    return s_normalize_exact(to_world(mk3(l.rad * cs, l.rad * sn, l.z), N));
+}
+TPT_DEV LocalDir cosine_local(uint32_t& rng) {                                         // .hpp:105-115, the draws
+    LocalDir l;
+    const float u1 = rng_float(rng);
+    l.rad = s_sqrt(u1);
+    l.angle = 2 * TPT_PI * rng_float(rng);
+    l.z = s_sqrt(1.0f - u1);
+    return l;
+}
+TPT_DEV f3 cosine_sample(uint32_t& rng, f3 N, float* pdf) {                            // .hpp:105-115
+    const f3 wi = local_to_world(cosine_local(rng), N);
     *pdf = dotf(wi, N) / TPT_PI;
     return wi;
 }
@@ -88,17 +98,15 @@ TPT_DEV float ggx_half_pdf(f3 n, f3 h, float roughness) {              // GGXHal
     const double a = fabs(dotd(n, h));
     return (float)((double)ggx_term((float)a, roughness) * a);
 }
-TPT_DEV f3 ggx_sample_h(uint32_t& rng, f3 N, float roughness) {        // SampleGGXSpecularH, :46-59
-    const float d1 = rng_float(rng), d2 = rng_float(rng);
+TPT_DEV LocalDir ggx_local(float d1, float d2, float roughness) {     // SampleGGXSpecularH, :46-59, from its two draws
     // theta = atan2(rough * sqrt(d1), sqrt(1 - d1)); only its sine and cosine are used, and those
     // are the two legs over the hypotenuse — no atan2 / sincos round trip (same values to an ulp)
     const float ly = roughness * s_sqrt(d1), lx = s_sqrt(1.0f - d1);
     const float hyp = s_sqrt(lx * lx + ly * ly);
-    const float st = s_div(ly, hyp), ct = s_div(lx, hyp);
-    const float phi = 2.0f * TPT_PI * d2;
-    float sp, cp;
-    sincosf(phi, &sp, &cp);
-    return s_normalize_exact(to_world(mk3(st * cp, st * sp, ct), N));
+    LocalDir l;
+    l.rad = s_div(ly, hyp); l.z = s_div(lx, hyp);
+    l.angle = 2.0f * TPT_PI * d2;
+    return l;
 }
 
 // ---- Material.cpp -----------------------------------------------------------------
@@ -214,42 +222,52 @@ TPT_DEV void mat_pdf_pair(const Mat& m, f3 a, f3 n, f3 b, float* pab, float* pba
 
 // sample, :150-214.  RNG draws: 2 for H, then Dieletric 1 (+2 on the diffuse branch),
 // Transparent 1, Metal 0 — same order as the reference.
-TPT_DEV f3 mat_sample(const Mat& m, uint32_t& rng, f3 w_o, f3 n, float* pdf) {
-    f3 H = ggx_sample_h(rng, n, m.rough);
-    const f3 w_i_s = reflect_dir(w_o, H);
-    float pdf_h = ggx_half_pdf(n, H, m.rough);
+//
+// In three steps so that a kernel can run the middle one for a whole warp at once:
+//   mat_sample_begin   the draws that decide WHAT is sampled: the GGX half vector, or (Dieletric, coin >= 0.5) the
+//                      cosine-weighted direction — the reference computes H first in either case, but on the diffuse
+//                      branch only its two draws matter (H, w_i_s and pdf_h are overwritten or unused, :176-190)
+//   local_to_world     sincos, TransformVectorToWorld, normalisation
+//   mat_sample_finish  the lobe's direction and pdf
+TPT_DEV LocalDir mat_sample_begin(const Mat& m, uint32_t& rng, bool* diffuse) {
+    const float d1 = rng_float(rng), d2 = rng_float(rng);
+    *diffuse = m.type == 0 && !(rng_float(rng) < 0.5f);
+    if (*diffuse) return cosine_local(rng);
+    return ggx_local(d1, d2, m.rough);
+}
+// w: local_to_world of what mat_sample_begin returned, around n
+TPT_DEV f3 mat_sample_finish(const Mat& m, uint32_t& rng, f3 w_o, f3 n, f3 w, bool diffuse, float* pdf) {
     const float vn = dotf(w_o, n);
-    float vh = dotf(w_o, H);
-    float abs_vh = fabsf(vh);
-    float jaco_reflect = safe_div(1.0f, (4.0f * abs_vh));
+    f3 H, w_i;
+    float pdf_d = 0.0f;
+    if (diffuse) {                       // w is the cosine-sampled direction
+        w_i = w;
+        pdf_d = dotf(w_i, n) / TPT_PI;
+        H = s_normalize_exact(w_i + w_o);
+    } else {                             // w is the GGX half vector
+        H = w;
+        w_i = reflect_dir(w_o, H);
+        if (m.type == 0) pdf_d = cosine_pdf(n, w_i);
+    }
+    const float pdf_h = ggx_half_pdf(n, H, m.rough);
+    const float vh = dotf(w_o, H);
+    const float abs_vh = fabsf(vh);
+    const float jaco_reflect = safe_div(1.0f, (4.0f * abs_vh));
     if (m.type == 1) {
         *pdf = pdf_h * jaco_reflect;
-        if (vn * dotf(w_i_s, n) < 0.0f) *pdf = 0.0f;
-        return w_i_s;
+        if (vn * dotf(w_i, n) < 0.0f) *pdf = 0.0f;
+        return w_i;
     }
-    if (m.type == 0) {
-        if (rng_float(rng) < 0.5f) {   // specular lobe
-            const float pdf_d = cosine_pdf(n, w_i_s);
-            *pdf = (pdf_h * jaco_reflect + pdf_d) * 0.5f;
-            if (vn * dotf(w_i_s, n) < 0.0f) *pdf = 0.0f;
-            return w_i_s;
-        }
-        float pdf_d;
-        const f3 w_i_d = cosine_sample(rng, n, &pdf_d);
-        H = s_normalize_exact(w_i_d + w_o);
-        vh = dotf(w_o, H);
-        abs_vh = fabsf(vh);
-        pdf_h = ggx_half_pdf(n, H, m.rough);
-        jaco_reflect = safe_div(1.0f, (4.0f * abs_vh));
+    if (m.type == 0) {                   // specular lobe or diffuse lobe: the same mixture density
         *pdf = (pdf_h * jaco_reflect + pdf_d) * 0.5f;
-        if (vn * dotf(w_i_d, n) < 0.0f) *pdf = 0.0f;
-        return w_i_d;
+        if (vn * dotf(w_i, n) < 0.0f) *pdf = 0.0f;
+        return w_i;
     }
     const f3 f = mat_fresnel(m, w_o, H);
     if (rng_float(rng) < f.x) {
         *pdf = pdf_h * f.x * jaco_reflect;
-        if (vn * dotf(w_i_s, n) < 0.0f) *pdf = 0.0f;
-        return w_i_s;
+        if (vn * dotf(w_i, n) < 0.0f) *pdf = 0.0f;
+        return w_i;
     }
     const f3 w_i_refract = refract_dir(w_o, H, m.ior_d);
     const float nl = dotf(n, w_i_refract);
@@ -261,4 +279,9 @@ TPT_DEV f3 mat_sample(const Mat& m, uint32_t& rng, f3 w_o, f3 n, float* pdf) {
     *pdf = pdf_h * (1.0f - f.x) * jaco_refract;
     if (vn * dotf(w_i_refract, n) > 0.0f) *pdf = 0.0f;
     return w_i_refract;
+}
+TPT_DEV f3 mat_sample(const Mat& m, uint32_t& rng, f3 w_o, f3 n, float* pdf) {
+    bool diffuse;
+    const LocalDir l = mat_sample_begin(m, rng, &diffuse);
+    return mat_sample_finish(m, rng, w_o, n, local_to_world(l, n), diffuse, pdf);
 }

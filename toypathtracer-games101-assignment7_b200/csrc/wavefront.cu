@@ -491,14 +491,29 @@ __global__ void __launch_bounds__(256, PATH_MIN_BLOCKS) k_path(SceneView g, Rend
         }
         WF_TRACE_SHADE(action, alive);
 
-        // ---- phase 3: the one expensive shading step
+        // ---- phase 3: the one expensive shading step, in the three steps of mat_sample (material.cuh) so that the
+        // lanes sampling a BSDF and the lanes starting a light subpath run the sampled direction's tail together
         __syncwarp();
         float4 ro = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)), rd = make_float4(0.f, 0.f, 1.f, 0.f);   // cull < 0: no ray
+        NextBegin nb;
+        nb.local.rad = 0.0f; nb.local.z = 1.0f; nb.local.angle = 0.0f; nb.diffuse = false;
+        f3 frameN = mk3(0.0f, 0.0f, 1.0f), w_o = mk3(0.0f);
+        LightPoint lp;
+        lp.coords = lp.normal = mk3(0.0f); lp.prim = -1;
+        if (action == ACT_EXTEND) {
+            w_o = s_normalize(prev_x - mk3(cA));
+            nb = sample_next_begin(sc, rng, unpack_prim(__float_as_int(cB.w)));
+            frameN = mk3(cB);
+        } else if (action == ACT_LIGHT) {
+            // GenerateLightPath head (BDPT.cpp:61-77)
+            nb.local = light_path_begin(sc, rng, sc.emissive[0], &lp);
+            frameN = lp.normal;
+        }
+        f3 w_dir = mk3(0.0f);
+        if (action != ACT_NONE) w_dir = local_to_world(nb.local, frameN);
         if (action == ACT_EXTEND) {
             const f3 Vx = mk3(cA), VN = mk3(cB);
-            const int Vprim = unpack_prim(__float_as_int(cB.w));
-            const f3 w_o = s_normalize(prev_x - Vx);
-            const NextSample s = sample_next_dir(sc, rng, VN, Vprim, w_o);
+            const NextSample s = sample_next_finish(sc, nb, rng, VN, unpack_prim(__float_as_int(cB.w)), w_o, w_dir);
             {
                 // what the reverse pdf towards vertex i-1 needs from this side (phase 1 of the next step
                 // finishes it): unit vector to the predecessor and |cos cos'| / dist^2 as SrpdfToAreaPdf forms them
@@ -515,10 +530,9 @@ __global__ void __launch_bounds__(256, PATH_MIN_BLOCKS) k_path(SceneView g, Rend
             pa = make_float4(s.alpha.x, s.alpha.y, s.alpha.z, s.srpdf);
             flags |= INFO_PENDING | (rr_pass ? INFO_RR_PASS : 0u);
         } else if (action == ACT_LIGHT) {
-            // GenerateLightPath head (BDPT.cpp:61-77)
             nc = count;
             PVert v0[1];
-            const LightStart ls = light_path_head(sc, rng, sc.emissive[0], v0);
+            const LightStart ls = light_path_finish(sc, sc.emissive[0], lp, w_dir, v0);
             store_vertex(b.l0, l0_at((int)parity, slot), v0[0]);
             cA = make_float4(v0[0].x.x, v0[0].x.y, v0[0].x.z, v0[0].pdf);
             cB = make_float4(v0[0].N.x, v0[0].N.y, v0[0].N.z, __int_as_float(pack_pt(v0[0].prim, v0[0].type)));
