@@ -152,7 +152,11 @@ typedef struct TptRenderParams {
 enum {
     TPT_FLAG_REF_TRAVERSAL = 1, /* no t-pruning: visit exactly the nodes BVH.cpp:103-143 visits */
     TPT_FLAG_COUNT_VISITS  = 2, /* fill node_visits / prim_tests in TptStats (slower)           */
-    TPT_FLAG_KERNEL_TIMES  = 4  /* CUDA-event time of every launch, summed per kernel class     */
+    TPT_FLAG_KERNEL_TIMES  = 4, /* CUDA-event time of every launch, summed per kernel class     */
+    TPT_FLAG_BDPT_ALL_LIGHTS = 8 /* BDPT light subpaths start on ANY emissive object (uniform choice, its
+                                    probability in the pdf of light vertex 0) instead of the first one only as
+                                    BDPT.cpp:287 does — an extension; off by default, and a no-op
+                                    for scenes with one emissive object: every reference image is unchanged */
 };
 
 /* Kernel classes of the wavefront pipeline (indices into TptStats.kernel_ms). */

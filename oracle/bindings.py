@@ -211,6 +211,11 @@ class Checker:
         """Reference checker only: Scene::backgroundColor (and the flattened description's copy)."""
         self._fn("scene_set_background")(self.h, C.c_float(r), C.c_float(g), C.c_float(b))
 
+    def set_light_pick(self, on):
+        """The oracle port's extension (not in the reference): BDPT light subpaths start on any emissive object."""
+        assert self.prefix == "orc_", "the compiled reference has no such mode"
+        self._fn("set_light_pick")(self.h, C.c_int(1 if on else 0))
+
     def render(self, mode, spp, threads, w, h):
         out = np.empty((h * w, 3), np.float32); rays = C.c_longlong(0); sec = C.c_double(0)
         self._fn("render")(self.h, C.c_int(mode), C.c_int(spp), C.c_int(threads), _p(out), C.byref(rays), C.byref(sec))

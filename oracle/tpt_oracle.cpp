@@ -127,6 +127,8 @@ struct Scene {
     std::vector<TptMaterial> mats;
     std::vector<int> emissive;
     std::vector<int> primObject;         // global prim id -> object index
+    int lightPick = 0;                   // EXTENSION, not in the reference: 1 = BDPT light subpaths start on any
+                                         // emissive object, chosen uniformly; 0 = m_emissionObjects[0], BDPT.cpp:287
     int nTris() const { return (int)tris.size(); }
     const TptMaterial& primMat(int prim) const { return mats[objects[primObject[prim]].material]; }
 };
@@ -778,6 +780,18 @@ inline void GenerateCameraPath(const Scene& sc, Rng& rng, Path& p, const Ray& ca
     FillPath(sc, rng, p, 1);
 }
 
+// Extension (off by default): which emissive object the light subpath starts on, and the probability of that
+// choice — it multiplies the pdf of light vertex 0 in GenerateLightPath and in Append-to-an-empty-path.
+inline int PickLight(const Scene& sc, Rng& rng) {
+    if (!sc.lightPick || sc.emissive.size() < 2) return sc.emissive[0];
+    const int n = (int)sc.emissive.size();
+    const int k = (int)(rng.f() * (float)n);
+    return sc.emissive[k < n ? k : n - 1];
+}
+inline float LightPickPdf(const Scene& sc) {
+    return (sc.lightPick && sc.emissive.size() >= 2) ? 1.0f / (float)sc.emissive.size() : 1.0f;
+}
+
 // BDPTPath::GenerateLightPath, BDPT.cpp:61-90
 inline void GenerateLightPath(const Scene& sc, Rng& rng, Path& p, int lightObj) {
     LightSample t;
@@ -786,7 +800,7 @@ inline void GenerateLightPath(const Scene& sc, Rng& rng, Path& p, int lightObj) 
     p.verts[0].vertex.type = Light;
     p.verts[0].vertex.prim = t.prim;
     p.verts[0].vertex.N = t.normal;
-    p.verts[0].pdf = ObjectPdf(sc, lightObj);
+    p.verts[0].pdf = ObjectPdf(sc, lightObj) * LightPickPdf(sc);      // (factor 1 unless the extension is on)
     p.verts[0].alpha = V3(sc.mats[sc.objects[lightObj].material].emission) / p.verts[0].pdf;
     float pdf1;
     V3 w_i = GetCosineWeightedSample(rng, t.normal, pdf1);
@@ -804,7 +818,7 @@ inline void GenerateLightPath(const Scene& sc, Rng& rng, Path& p, int lightObj) 
 inline void Append(const Scene& sc, Path& p, const PTVertex& vertex) {
     if (p.count == 0) {
         p.verts[0].vertex = vertex;
-        p.verts[0].pdf = PrimPdf(sc, vertex.prim);   // vertex.obj->pdf(): the Triangle's / Sphere's
+        p.verts[0].pdf = PrimPdf(sc, vertex.prim) * LightPickPdf(sc);   // vertex.obj->pdf(): the Triangle's / Sphere's
         p.count++;
         return;
     }
@@ -885,7 +899,7 @@ V3 BDPT(const Scene& sc, Rng& rng, const Ray& ray, int& outBounces, V3* emission
     outBounces = 0;
     Path lightPath, camPath;
     GenerateCameraPath(sc, rng, camPath, ray);
-    GenerateLightPath(sc, rng, lightPath, sc.emissive[0]);
+    GenerateLightPath(sc, rng, lightPath, PickLight(sc, rng));
     outBounces += camPath.count + lightPath.count;
     V3 result;
     for (int s = 1; s <= camPath.count; s++) {
@@ -961,6 +975,8 @@ OrcScene* orc_scene_create(const TptSceneDesc* d) {
     return o;
 }
 void orc_scene_destroy(OrcScene* o) { delete o; }
+// the extension above: 0 (default) = the reference's m_emissionObjects[0]
+void orc_set_light_pick(OrcScene* o, int on) { o->sc.lightPick = on ? 1 : 0; }
 
 // counters since the last reset: scene_rays, probe_rays, node_visits, prim_tests, traversals
 void orc_stats(OrcScene* o, uint64_t* out5, int reset) {
@@ -1070,7 +1086,7 @@ uint32_t orc_bdpt_sample(OrcScene* o, int pixel, uint32_t seed, TptPathVertex* c
     V3 dir = PixelPosToRay(x, y, sc.width, sc.height, scale);
     Path camPath, lightPath;
     GenerateCameraPath(sc, rng, camPath, Ray(sc.eye, dir));
-    GenerateLightPath(sc, rng, lightPath, sc.emissive[0]);
+    GenerateLightPath(sc, rng, lightPath, PickLight(sc, rng));
     DumpPath(camPath, cam, camCount);
     DumpPath(lightPath, light, lightCount);
     if (weights) {

@@ -59,6 +59,22 @@ def desc_from_golden(scene, width=None, height=None):
     return d, keep
 
 
+def one_light_of(scene, which, width=None, height=None):
+    """The golden scene `scene` with only its which-th emissive object left emitting: the others keep their geometry
+    and material but emit nothing and leave the emissive list (their materials must not be shared).  Light transport
+    is linear in the emitters: the frames of these scenes add up to the frame of the scene with all of them."""
+    from oracle import bindings as B
+    d, keep = desc_from_golden(scene, width, height)
+    objs = [d.emissive_objects[i] for i in range(d.n_emissive)]
+    for i, o in enumerate(objs):
+        if i != which:
+            d.materials[d.objects[o].material].emission = B.Vec3(0.0, 0.0, 0.0)
+    buf = (C.c_int32 * 1)(objs[which])
+    keep["emissive_one"] = buf
+    d.n_emissive, d.emissive_objects = 1, C.cast(buf, C.POINTER(C.c_int32))
+    return d, keep
+
+
 def oracle_for(scene, width=None, height=None):
     from oracle import bindings as B
     d, keep = desc_from_golden(scene, width, height)

@@ -37,6 +37,37 @@ def test_every_emissive_object_lights_pathtrace(tpt, pipeline):
     s.close()
 
 
+def test_bdpt_light_subpaths_from_every_emissive_object(tpt):
+    """TPT_FLAG_BDPT_ALL_LIGHTS (the reference starts light subpaths on m_emissionObjects[0] only,
+    BDPT.cpp:287).  Pinned to the reference through the linearity of light transport: the frame of the two-light scene
+    must be the sum of the plain reference BDPT frames of its two one-emitter scenes (tests/golden/alllights.npz).
+    The queue pipeline and the per-pixel kernel agree pixel by pixel; the default mode is untouched by the code path
+    (the same frame as the compiled reference's, test_every_emissive_object_lights_pathtrace) and far from the sum;
+    on a scene with one emissive object the flag changes nothing."""
+    g = golden("alllights.npz")
+    target = g["only_0"] + g["only_1"]
+    s = gpu_scene("twolights", 64, 64)
+    img, st = s.render("bdpt", 256, flags=tpt.FLAG_BDPT_ALL_LIGHTS)
+    assert np.isfinite(img).all()
+    rel = np.abs(img.mean((0, 1)) - target.mean((0, 1))) / target.mean((0, 1))
+    assert (rel < 0.01).all(), rel
+    tiles = lambda x: x.reshape(8, 8, 8, 8, 3).mean((1, 3))
+    assert np.max(np.abs(tiles(img) - tiles(target)) / (tiles(target) + 1e-2)) < 0.08
+    a, sa = s.render("bdpt", 6, flags=tpt.FLAG_BDPT_ALL_LIGHTS)
+    b, sb = s.render("bdpt", 6, flags=tpt.FLAG_BDPT_ALL_LIGHTS, pipeline=tpt.PIPE_MEGAKERNEL)
+    assert sa["ref_rays"] == sb["ref_rays"]
+    err = np.abs(a - b) / (np.abs(b) + 1e-3)
+    assert np.percentile(err, 99.9) < 1e-3, np.percentile(err, 99.9)
+    default, _ = s.render("bdpt", 32)
+    assert np.abs(default.mean() - target.mean()) / target.mean() > 0.2
+    s.close()
+    s = gpu_scene("standard", 64, 64)
+    a, sa = s.render("bdpt", 4)
+    b, sb = s.render("bdpt", 4, flags=tpt.FLAG_BDPT_ALL_LIGHTS)
+    assert sa["ref_rays"] == sb["ref_rays"] and np.allclose(a, b, rtol=2e-4, atol=2e-5)
+    s.close()
+
+
 @pytest.mark.parametrize("scene,mode,spp", [("standard", "bdpt", 16), ("standard", "pt_full", 64),
                                             ("refractive", "bdpt", 16), ("smooth", "pt_full", 64)])
 def test_readme_images(tpt, scene, mode, spp):

@@ -6,7 +6,7 @@
 import numpy as np
 import pytest
 
-from conftest import golden, oracle_for
+from conftest import desc_from_golden, golden, oracle_for
 from oracle import bindings as B
 
 SCENES = ["standard", "smooth", "silver", "refractive", "occlusion", "bunny"]
@@ -191,3 +191,25 @@ def test_lit_background_restatement_equals_compiled_reference():
         b, rb, _ = orc.render(mode, spp, 1, 40, 40)
         assert (a.view(np.uint32) == b.view(np.uint32)).all() and ra == rb
     assert a[0, 0].sum() > 0.1            # the corner pixel looks past the box
+
+
+def test_all_lights_extension_adds_up():
+    """BDPT with light subpaths on EVERY emissive object (an extension; the reference starts them on
+    m_emissionObjects[0] only, BDPT.cpp:287) is pinned through the linearity of light transport: its frame must be the
+    SUM of the plain reference BDPT frames of the scenes with one emitter each (tests/golden/alllights.npz, made by
+    make_alllights.py from the reference's trees of the two-light scene).  The default mode stays far from that sum:
+    the second light is only ever found by camera subpaths."""
+    import os
+    g = golden("alllights.npz")
+    target = g["only_0"] + g["only_1"]
+    d, keep = desc_from_golden("twolights", 64, 64)
+    orc = B.oracle_scene(d, keep)
+    default, _, _ = orc.render(2, 32, os.cpu_count() or 1, 64, 64)
+    orc.set_light_pick(1)
+    img, _, _ = orc.render(2, 128, os.cpu_count() or 1, 64, 64)
+    assert np.isfinite(img).all()
+    rel = np.abs(img.mean((0, 1)) - target.mean((0, 1))) / target.mean((0, 1))
+    assert (rel < 0.01).all(), rel
+    tiles = lambda x: x.reshape(8, 8, 8, 8, 3).mean((1, 3))
+    assert np.max(np.abs(tiles(img) - tiles(target)) / (tiles(target) + 1e-2)) < 0.10
+    assert np.abs(default.mean() - target.mean()) / target.mean() > 0.2

@@ -27,7 +27,7 @@ CULL_BACK, CULL_FRONT, NO_CULL = 0, 1, 2
 SEED_REF, SEED_SPLIT = 0, 1
 PART_ALL, PART_INTERLEAVE, PART_BLOCK = 0, 1, 2
 PIPE_WAVEFRONT, PIPE_MEGAKERNEL = 0, 1
-FLAG_REF_TRAVERSAL, FLAG_COUNT_VISITS, FLAG_KERNEL_TIMES = 1, 2, 4
+FLAG_REF_TRAVERSAL, FLAG_COUNT_VISITS, FLAG_KERNEL_TIMES, FLAG_BDPT_ALL_LIGHTS = 1, 2, 4, 8
 KERNEL_NAMES = ("generate", "shade", "extend", "expand", "connect", "shadow", "mis", "accumulate")
 SCENES = ("standard", "smooth", "silver", "refractive", "occlusion", "bunny")
 

@@ -86,6 +86,17 @@ TPT_DEV void object_sample(const SceneView& sc, int obj, uint32_t& rng, LightPoi
     pos->normal = mk3(sc.tris[4 * tri + 3]);
     pos->prim = tri;
 }
+// The emissive object a BDPT light subpath starts on.  The reference always takes m_emissionObjects[0]
+// (BDPT.cpp:287); with SceneView::light_pick every emissive object is chosen with the same probability (one more
+// draw, only in that mode), and that probability multiplies the pdf of light vertex 0 wherever it appears: in
+// GenerateLightPath (BDPT.cpp:66) and in the density PathWeight gives a camera vertex that starts the temporary
+// path as a light (BDPT.cpp:127-139).  With one emissive object, or without the flag, the factor is exactly 1.
+TPT_DEV int pick_light(const SceneView& sc, uint32_t& rng) {
+    if (!sc.light_pick) return sc.emissive[0];
+    const int k = (int)(rng_float(rng) * (float)sc.n_emissive);
+    return sc.emissive[k < sc.n_emissive ? k : sc.n_emissive - 1];
+}
+TPT_DEV float light_pick_pdf(const SceneView& sc) { return sc.light_pick ? 1.0f / (float)sc.n_emissive : 1.0f; }
 // Object::pdf(): MeshTriangle 1/bvh-root area (Triangle.hpp:58-60), Sphere 1/area
 TPT_DEV float object_pdf(const SceneView& sc, int obj) { return s_rcp(sc.objs[obj].root_area); }
 
@@ -297,7 +308,7 @@ TPT_DEV LocalDir light_path_begin(const SceneView& sc, uint32_t& rng, int lightO
 }
 TPT_DEV LightStart light_path_finish(const SceneView& sc, int lightObj, const LightPoint& t, f3 w, PVert* verts) {      // w: local_to_world(.., t.normal)
     verts[0].x = t.coords; verts[0].type = VT_LIGHT; verts[0].prim = t.prim; verts[0].N = t.normal;
-    verts[0].pdf = object_pdf(sc, lightObj);
+    verts[0].pdf = object_pdf(sc, lightObj) * light_pick_pdf(sc);
     const Mat lm = load_mat(sc, sc.objs[lightObj].material);
     verts[0].alpha = lm.emission / verts[0].pdf;
     LightStart s;
@@ -432,7 +443,7 @@ TPT_DEV float mis_denominator(const SceneView& sc, const CamPath& cam, int s, co
                 // Append to an empty path (BDPT.cpp:127-139): the camera-path end re-typed Light,
                 // pdf = vertex.obj->pdf() — the Triangle's own 1/area (quirk Q15)
                 v.type = VT_LIGHT;
-                pdf = prim_pdf(sc, v.prim);
+                pdf = prim_pdf(sc, v.prim) * light_pick_pdf(sc);
             } else {
                 pdf = append_pdf(sc, L, L.type, P.x, v, count);
             }
@@ -489,7 +500,7 @@ TPT_DEV float mis_denominator_paired(const SceneView& sc, const CamPath& cam, in
     const float g_zp = fabsf(s_div((z.type == VT_CAMERA ? 1.0f : cos_zp) * (zp.type == VT_CAMERA ? 1.0f : fabsf(dotf(w_zp, zp.N))), dzp2));
     if (t == 0) {
         // light subpath empty: cam[s-1] starts the path re-typed Light with its primitive's own 1/area (quirk Q15)
-        float cur = safe_div(prim_pdf(sc, z.prim), z.pdf);
+        float cur = safe_div(prim_pdf(sc, z.prim) * light_pick_pdf(sc), z.pdf);
         den += cur * cur;
         int count = 1;
         if (cur != 0.0f && s >= 2) {

@@ -62,6 +62,8 @@ struct SceneView {
     const float4* uboxes;     // the DISTINCT leaf boxes: {bmin, asfloat(leaf mask bits 0-31)} {bmax, asfloat(bits 32-63)}
     int n_uboxes;
     int n_nodes, n_tris, n_spheres, n_mats, n_objs, n_lnodes, n_emissive;
+    int light_pick;           // BDPT light subpaths: 0 = start on emissive[0] only (BDPT.cpp:287), 1 = on any emissive object,
+                              // chosen uniformly (TPT_FLAG_BDPT_ALL_LIGHTS; set per render in the copy the kernels get)
     int width, height;
     float scale;              // CalculateScale(fov), computed on the host with the host libm
     float aspect;             // (float)(width / height): integer division, SceneRenderingHelper.cpp:17

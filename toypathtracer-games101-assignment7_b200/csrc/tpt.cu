@@ -650,7 +650,7 @@ __global__ void __launch_bounds__(128) k_render_mega(SceneView g, RenderArgs a, 
                 trace_scene<COUNT>(c, primary, 0, &h);
                 camera_path_head(sc, h, cam);
                 const int nc = fill_path<COUNT>(c, rng, cam);
-                const LightStart ls = light_path_head(sc, rng, sc.emissive[0], light);
+                const LightStart ls = light_path_head(sc, rng, pick_light(sc, rng), light);
                 trace_scene<COUNT>(c, make_ray(light[0].x, ls.w_i), 0, &h);
                 int nl = 2;
                 if (light_path_first_hit(ls, h, light)) nl = fill_path<COUNT>(c, rng, light);
@@ -718,6 +718,7 @@ static int check_params(const TptScene* s, const TptRenderParams* p, RenderArgs*
     a->prune = (p->flags & TPT_FLAG_REF_TRAVERSAL) ? 0 : 1;
     a->count_visits = (p->flags & TPT_FLAG_COUNT_VISITS) ? 1 : 0;
     a->kernel_times = (p->flags & TPT_FLAG_KERNEL_TIMES) ? 1 : 0;
+    a->all_lights = (p->flags & TPT_FLAG_BDPT_ALL_LIGHTS) ? 1 : 0;
     return TPT_OK;
 }
 
@@ -759,8 +760,10 @@ extern "C" int tpt_render_device(TptScene* s, const TptRenderParams* p, float* d
         const int npix = s->view.width * s->view.height;
         const int slots = tpt_part_slots(a, npix);
         const int grid = (slots + 127) / 128;
-        if (a.count_visits) k_render_mega<true><<<grid, 128, s->view.stage_bytes, st>>>(s->view, a, d_radiance, d_splat, s->d_stats);
-        else k_render_mega<false><<<grid, 128, s->view.stage_bytes, st>>>(s->view, a, d_radiance, d_splat, s->d_stats);
+        SceneView view = s->view;
+        view.light_pick = (a.all_lights && view.n_emissive > 1) ? 1 : 0;
+        if (a.count_visits) k_render_mega<true><<<grid, 128, s->view.stage_bytes, st>>>(view, a, d_radiance, d_splat, s->d_stats);
+        else k_render_mega<false><<<grid, 128, s->view.stage_bytes, st>>>(view, a, d_radiance, d_splat, s->d_stats);
         TPT_CUDA(cudaGetLastError());
         launches += 1;
     } else {

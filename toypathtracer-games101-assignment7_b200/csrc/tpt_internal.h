@@ -32,6 +32,7 @@ struct RenderArgs {
     int mode, spp, spp_total;
     int seed_mode, partition, rank, world, stream;
     int prune, count_visits, kernel_times;
+    int all_lights;     // TPT_FLAG_BDPT_ALL_LIGHTS
     int sub, nsub;      // this launch chain handles every nsub-th slot of the partition, starting at sub (1 chain: 0, 1)
 };
 

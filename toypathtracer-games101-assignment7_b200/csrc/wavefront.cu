@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(256, PATH_MIN_BLOCKS) k_path(SceneView g, Rend
             frameN = mk3(cB);
         } else if (action == ACT_LIGHT) {
             // GenerateLightPath head (BDPT.cpp:61-77)
-            nb.local = light_path_begin(sc, rng, sc.emissive[0], &lp);
+            nb.local = light_path_begin(sc, rng, pick_light(sc, rng), &lp);
             frameN = lp.normal;
         }
         f3 w_dir = mk3(0.0f);
@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(256, PATH_MIN_BLOCKS) k_path(SceneView g, Rend
         } else if (action == ACT_LIGHT) {
             nc = count;
             PVert v0[1];
-            const LightStart ls = light_path_finish(sc, sc.emissive[0], lp, w_dir, v0);
+            const LightStart ls = light_path_finish(sc, prim_object(sc, lp.prim), lp, w_dir, v0);
             store_vertex(b.l0, l0_at((int)parity, slot), v0[0]);
             cA = make_float4(v0[0].x.x, v0[0].x.y, v0[0].x.z, v0[0].pdf);
             cB = make_float4(v0[0].N.x, v0[0].N.y, v0[0].N.z, __int_as_float(pack_pt(v0[0].prim, v0[0].type)));
@@ -862,6 +862,8 @@ int wavefront_render(TptScene* s, const RenderArgs& a, float* d_radiance, float*
     if (rc != TPT_OK) return rc;
     WavefrontState* w = s->wf;
     WfBuffers& b = w->b;
+    SceneView view = s->view;                          // the kernels' copy, with this render's light choice
+    view.light_pick = (a.all_lights && view.n_emissive > 1) ? 1 : 0;
     const unsigned smem = s->view.stage_bytes;
     const unsigned tsmem = TPT_TRAV_SMEM(smem, 256);   // traversal kernels: + candidate columns + cooperative area
     if (tsmem > 48u * 1024u) {                         // mid-size staged scenes: opt in to more dynamic shared memory
@@ -875,7 +877,7 @@ int wavefront_render(TptScene* s, const RenderArgs& a, float* d_radiance, float*
     std::memset(&init, 0, sizeof init);
     init.n_active[0] = (unsigned)S;
     TPT_CUDA(cudaMemcpyAsync(b.ctr, &init, sizeof init, cudaMemcpyHostToDevice, st));
-    tm->begin(TPT_K_GENERATE); launch_pdl(k_generate, grid, tsmem, st, s->view, a, b, s->d_stats); tm->end();
+    tm->begin(TPT_K_GENERATE); launch_pdl(k_generate, grid, tsmem, st, view, a, b, s->d_stats); tm->end();
     int cur = 0;
     // Safety bound only (an incomplete frame must not pass for a frame): every round completes at least one waiting
     // sample per block, a sample takes at most 31 steps
@@ -902,12 +904,12 @@ int wavefront_render(TptScene* s, const RenderArgs& a, float* d_radiance, float*
         if (two && it >= WF_CHAINS) TPT_CUDA(cudaStreamWaitEvent(st, w->ev_side[e], 0));
         // one block per 256 slots of the frame (a block past the end of the active list exits at once): the blocks
         // are the regions of the done list
-        tm->begin(TPT_K_SHADE); launch_pdl(k_path, b.n_regions, tsmem, st, s->view, a, b, cur, par, s->d_stats); tm->end();
+        tm->begin(TPT_K_SHADE); launch_pdl(k_path, b.n_regions, tsmem, st, view, a, b, cur, par, s->d_stats); tm->end();
         if (two) { TPT_CUDA(cudaEventRecord(w->ev_path[e], st)); TPT_CUDA(cudaStreamWaitEvent(ss, w->ev_path[e], 0)); }
         tm->begin(TPT_K_EXPAND); launch_pdl(k_expand, b.n_regions, 0u, ss, bs, par); tm->end();
-        tm->begin(TPT_K_CONNECT); launch_pdl(k_connect, pgrid, smem, ss, s->view, bs, par); tm->end();
-        tm->begin(TPT_K_SHADOW); launch_pdl(k_shadow_q, pgrid, (unsigned)TPT_SHADOW_SMEM(smem, 256), ss, s->view, a, bs, par, s->d_stats); tm->end();
-        tm->begin(TPT_K_MIS); launch_pdl(k_mis, pgrid, smem, ss, s->view, a, bs, par, d_radiance, d_splat); tm->end();
+        tm->begin(TPT_K_CONNECT); launch_pdl(k_connect, pgrid, smem, ss, view, bs, par); tm->end();
+        tm->begin(TPT_K_SHADOW); launch_pdl(k_shadow_q, pgrid, (unsigned)TPT_SHADOW_SMEM(smem, 256), ss, view, a, bs, par, s->d_stats); tm->end();
+        tm->begin(TPT_K_MIS); launch_pdl(k_mis, pgrid, smem, ss, view, a, bs, par, d_radiance, d_splat); tm->end();
         if (two) TPT_CUDA(cudaEventRecord(w->ev_side[e], ss));
         cur ^= 1;
         if ((it & 3) == 3 || it + 1 == max_rounds) {

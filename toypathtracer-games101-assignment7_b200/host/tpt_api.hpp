@@ -297,6 +297,10 @@ public:
     // reference's seeds: the one-GPU image)
     int gpus = 1;
     int split = 0;
+    // Extension, off by default (TPT_FLAG_BDPT_ALL_LIGHTS of include/tpt.h; TPT_BDPT_ALL_LIGHTS=1 in the environment
+    // sets it for an unchanged main.cpp): BDPT light subpaths start on any emissive object of the scene instead of
+    // the first one added (BDPT.cpp:287).  No effect on scenes with one emissive object.
+    bool bdptAllLights = false;
     bool quiet = false;
     // filled by Render(): radiance + merged splats, width*height Vector3f
     std::vector<Vector3f> framebuffer;

@@ -349,6 +349,9 @@ void Renderer::Render(std::string outputFileName, const Scene& scene, int spp, i
     p.mode = bdpt ? TPT_MODE_BDPT : (pt_full ? TPT_MODE_PT_FULL : TPT_MODE_PT_SHIPPED);
     p.spp = spp;
     p.world = 1;
+    bool allLights = bdptAllLights;
+    if (const char* env = std::getenv("TPT_BDPT_ALL_LIGHTS")) allLights = std::atoi(env) != 0;
+    if (allLights) p.flags |= TPT_FLAG_BDPT_ALL_LIGHTS;
     TptStats st;
     std::memset(&st, 0, sizeof st);
     std::vector<float> rgb((size_t)scene.width * scene.height * 3);
