@@ -25,8 +25,19 @@ namespace {
 
 struct PtCounters {
     unsigned n_active[2];
-    unsigned pad[2];
+    unsigned n_long_ext, n_long_sh;    // walks parked by k_pt_extend / k_pt_shadow for the *_long kernels (large scenes)
 };
+
+// Large scenes (no flat leaf list: the bunny).  The average walk is short (13.5 nodes), but a tenth of the rays enter
+// the mesh and visit 100-280 nodes, and a warp takes as long as its slowest lane: with one such ray in nearly every
+// warp the traversal kernels ran at a fraction of their lanes.  The stackless walk can stop anywhere and go on later
+// (walk_resume / shadow_resume, traverse.cuh: the cursor is the node index and the best hit — the same sequence of
+// tests, so the same answer bit for bit), so k_pt_extend / k_pt_shadow give every ray PT_WALK_BUDGET node visits and
+// park what is not finished by then in a queue; k_pt_extend_long / k_pt_shadow_long finish the parked walks, one
+// per lane, dense: long walks run in warps of their own.
+#ifndef PT_WALK_BUDGET
+#define PT_WALK_BUDGET 24       /* bunny pt_full 32 spp at 784^2: 58.5 ms without parking; 57.4 / 58.4 / 51.5 / 53.7 / 59.1 ms with 12 / 16 / 24 / 32 / 48 */
+#endif
 
 // info bits: [0] extension ray pending  [1] direct-light record pending  [2] explicitLight
 //            [3] flip culling  [4] sample in progress  [8..31] bounces
@@ -51,6 +62,9 @@ struct PtBuffers {
     float4 *dl_alpha, *dl_e1, *dl_e2; // direct light of the last vertex: alpha; E1, E2 of light l at [l * S + s] (w = 1: shadow ray queued)
     float4 *sh_from, *sh_to;          // [2 * nl * S]: shadow ray j = 2 l + {0, 1} of slot s at [j * S + s]; from.w < 0: none
     unsigned* vis;                    // bit j: shadow ray j found the light visible
+    uint4* long_ext;                  // parked closest-hit walks {slot, next node, best primitive, -} ...
+    double* long_ext_t;               // ... and their best t
+    uint4* long_sh;                   // parked shadow walks {slot, ray j of the slot, next node, -}
     int* active[2];
     PtCounters* ctr;
 };
@@ -89,6 +103,7 @@ __global__ void __launch_bounds__(256, PT_SHADE_MIN_BLOCKS) k_pt_shade(SceneView
     pdl_wait();
     Ctx c;
     c.sc = sc; c.prune = true; c.cnt.node_visits = 0; c.cnt.prim_tests = 0; c.scene_rays = 0; c.probe_rays = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { b.ctr->n_long_ext = 0u; b.ctr->n_long_sh = 0u; }   // the *_long kernels of the last iteration are done
     const unsigned n = b.ctr->n_active[cur];
     const int* list = b.active[cur];
     int* next_list = b.active[cur ^ 1];
@@ -278,6 +293,78 @@ __global__ void __launch_bounds__(256) k_pt_extend(SceneView g, PtBuffers b, int
     flush_stats(0, rays, 0, stats);
 }
 
+// k_pt_extend for large scenes (a kernel of its own: the walk needs 72 registers, the flat-list kernel above runs at 64):
+// every ray gets PT_WALK_BUDGET node visits, what is not finished by then is parked for k_pt_extend_long
+__global__ void __launch_bounds__(256) k_pt_extend_budget(SceneView g, PtBuffers b, int cur, unsigned long long* stats) {
+    pdl_launch_dependents();
+    const SceneView sc = stage_scene(g, tpt_smem);
+    pdl_wait();
+    if (blockIdx.x == 0 && threadIdx.x == 0) b.ctr->n_active[cur ^ 1] = 0;   // the list k_pt_shade consumed: the next one is built there
+    const unsigned n = b.ctr->n_active[cur];
+    const int* list = b.active[cur];
+    unsigned long long rays = 0;
+    const unsigned total = (n + 31u) & ~31u;
+    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+        int slot = 0;
+        float4 o = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)), d = make_float4(0.f, 0.f, 1.f, 0.f);
+        if (q < n) { slot = list[q]; o = b.ray_o[slot]; d = b.ray_d[slot]; }
+        const bool has_ray = __float_as_int(o.w) >= 0;
+        const DRay r = make_ray(mk3(o), mk3(d));
+        WalkCursor c = walk_begin(0);
+        bool done = true;
+        if (has_ray) {
+            rays++;
+            done = walk_resume(sc, r, __float_as_int(o.w), sc.n_nodes, true, PT_WALK_BUDGET, c);
+            if (done) {
+                DHit h;
+                finish_hit(sc, r, c.best, c.best_t, &h);
+                b.hit[slot] = make_float4(h.coords.x, h.coords.y, h.coords.z, __int_as_float(h.prim));
+            }
+        }
+        const unsigned at = wf_append(&b.ctr->n_long_ext, !done);
+        if (!done) { b.long_ext[at] = make_uint4((unsigned)slot, (unsigned)c.i, (unsigned)c.best, 0u); b.long_ext_t[at] = c.best_t; }
+    }
+    flush_stats(0, rays, 0, stats);
+}
+
+// The walks k_pt_extend_budget parked, to their end.
+// (64 registers, 4 blocks per SM; compiled for 6 or 8 blocks they spill and the frame takes 55 / 56.5 ms instead of 51.5)
+__global__ void __launch_bounds__(256) k_pt_extend_long(SceneView g, PtBuffers b) {
+    pdl_launch_dependents();
+    const SceneView sc = stage_scene(g, tpt_smem);
+    pdl_wait();
+    const unsigned n = b.ctr->n_long_ext;
+    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const uint4 e = b.long_ext[q];
+        const int slot = (int)e.x;
+        const float4 o = b.ray_o[slot], d = b.ray_d[slot];
+        const DRay r = make_ray(mk3(o), mk3(d));
+        WalkCursor c;
+        c.i = (int)e.y; c.best = (int)e.z; c.best_t = b.long_ext_t[q];
+        walk_resume(sc, r, __float_as_int(o.w), sc.n_nodes, true, 0x7fffffff, c);
+        DHit h;
+        finish_hit(sc, r, c.best, c.best_t, &h);
+        b.hit[slot] = make_float4(h.coords.x, h.coords.y, h.coords.z, __int_as_float(h.prim));
+    }
+}
+// ... and k_pt_shadow's: a ray found visible sets its bit (k_pt_shadow left it clear)
+__global__ void __launch_bounds__(256) k_pt_shadow_long(SceneView g, PtBuffers b) {
+    pdl_launch_dependents();
+    const SceneView sc = stage_scene(g, tpt_smem);
+    pdl_wait();
+    const unsigned n = b.ctr->n_long_sh;
+    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const uint4 e = b.long_sh[q];
+        const int slot = (int)e.x;
+        const float4 from = b.sh_from[(size_t)e.y * b.S + slot], to = b.sh_to[slot];
+        const ShadowQuery sq = shadow_begin(mk3(from), mk3(to));
+        int cursor = (int)e.z;
+        bool found = false;
+        shadow_resume(sc, sq, 0, 0x7fffffff, cursor, &found);
+        if (!found) atomicOr(&b.vis[slot], 1u << e.y);
+    }
+}
+
 // Two shadow-ray slots per active slot: thread 2q+j handles ray j of queue entry q.
 __global__ void __launch_bounds__(256) k_pt_shadow(SceneView g, PtBuffers b, int cur, unsigned long long* stats) {
     pdl_launch_dependents();
@@ -299,7 +386,22 @@ __global__ void __launch_bounds__(256) k_pt_shadow(SceneView g, PtBuffers b, int
             from = b.sh_from[(size_t)j * b.S + slot];
             if (from.w > 0.0f) { to = b.sh_to[slot]; has_ray = true; rays++; }
         }
-        if (has_ray) visible = !shadow_check_deferred(sc, mk3(from), mk3(to), 0, cand, blockDim.x);   // Scene::ShadowCheck(inte.coords, x)
+        bool parked = false;
+        int cursor = 0;
+        if (has_ray) {
+            if (sc.n_leaves == 0) {                 // large scene: a budget of node visits, the rest parked for k_pt_shadow_long
+                const ShadowQuery sq = shadow_begin(mk3(from), mk3(to));
+                bool found = false;
+                parked = !shadow_resume(sc, sq, 0, PT_WALK_BUDGET, cursor, &found);
+                visible = !parked && !found;
+            } else {
+                visible = !shadow_check_deferred(sc, mk3(from), mk3(to), 0, cand, blockDim.x);   // Scene::ShadowCheck(inte.coords, x)
+            }
+        }
+        if (sc.n_leaves == 0) {
+            const unsigned at = wf_append(&b.ctr->n_long_sh, parked);
+            if (parked) b.long_sh[at] = make_uint4((unsigned)slot, j, (unsigned)cursor, 0u);
+        }
         if (R == 2u) {
             // one light: the two lanes of a slot are neighbours; combine their bits with a shuffle, lane j == 0 writes
             const unsigned other = __shfl_down_sync(0xffffffffu, visible ? 1u : 0u, 1);
@@ -377,7 +479,9 @@ static int pt_alloc(PtPipe& w, int S, int nl) {
               get(F4, (void**)&b.ray_o) && get(F4, (void**)&b.ray_d) && get(F4, (void**)&b.hit) &&
               get(F4, (void**)&b.dl_alpha) && get(nl * F4, (void**)&b.dl_e1) && get(nl * F4, (void**)&b.dl_e2) &&
               get(2 * nl * F4, (void**)&b.sh_from) && get(F4, (void**)&b.sh_to) && get(U, (void**)&b.vis) &&
-              get(U, (void**)&b.active[0]) && get(U, (void**)&b.active[1]) && get(sizeof(PtCounters), (void**)&b.ctr);
+              get(U, (void**)&b.active[0]) && get(U, (void**)&b.active[1]) && get(sizeof(PtCounters), (void**)&b.ctr) &&
+              get((size_t)S * sizeof(uint4), (void**)&b.long_ext) && get((size_t)S * sizeof(double), (void**)&b.long_ext_t) &&
+              get((size_t)2 * nl * S * sizeof(uint4), (void**)&b.long_sh);
     if (ok && !(w.h_flag = static_cast<unsigned*>(tpt_pinned_alloc(64)))) ok = false;
     if (!ok) { pt_pipe_free(w); return TPT_ERR_OOM; }
     return TPT_OK;
@@ -430,6 +534,7 @@ int pt_wavefront_render(TptScene* s, const RenderArgs& a0, float* d_radiance, cu
         TPT_CUDA(cudaMemcpyAsync(w.b.ctr, &init, sizeof init, cudaMemcpyHostToDevice, ms[p]));
         tm->begin(TPT_K_GENERATE); launch_pdl(k_pt_generate, grid[p], tsmem, ms[p], s->view, args[p], w.b, s->d_stats); tm->end();
     }
+    const bool large = s->view.n_leaves == 0;          // no flat leaf list: budgeted walks + the *_long kernels
     const long long max_iters = (long long)a0.spp * 4096 + 8;
     for (long long it = 0; it < max_iters; ++it) {
         for (int p = 0; p < npipes; ++p) {
@@ -438,8 +543,14 @@ int pt_wavefront_render(TptScene* s, const RenderArgs& a0, float* d_radiance, cu
             if (two && it > 0) TPT_CUDA(cudaStreamWaitEvent(ms[p], w.ev_side, 0));
             tm->begin(TPT_K_SHADE); launch_pdl(k_pt_shade, grid[p], smem, ms[p], s->view, args[p], w.b, cur[p], d_radiance, s->d_stats); tm->end();
             if (two) { TPT_CUDA(cudaEventRecord(w.ev_shade, ms[p])); TPT_CUDA(cudaStreamWaitEvent(ss[p], w.ev_shade, 0)); }
-            tm->begin(TPT_K_EXTEND); launch_pdl(k_pt_extend, grid[p], tsmem, ms[p], s->view, w.b, cur[p] ^ 1, s->d_stats); tm->end();
+            if (large) {
+                tm->begin(TPT_K_EXTEND); launch_pdl(k_pt_extend_budget, grid[p], smem, ms[p], s->view, w.b, cur[p] ^ 1, s->d_stats); tm->end();
+                tm->begin(TPT_K_EXTEND); launch_pdl(k_pt_extend_long, grid[p], smem, ms[p], s->view, w.b); tm->end();
+            } else {
+                tm->begin(TPT_K_EXTEND); launch_pdl(k_pt_extend, grid[p], tsmem, ms[p], s->view, w.b, cur[p] ^ 1, s->d_stats); tm->end();
+            }
             tm->begin(TPT_K_SHADOW); launch_pdl(k_pt_shadow, grid[p], (unsigned)TPT_SHADOW_SMEM(smem, 256), ss[p], s->view, w.b, cur[p] ^ 1, s->d_stats); tm->end();
+            if (large) { tm->begin(TPT_K_SHADOW); launch_pdl(k_pt_shadow_long, grid[p], smem, ss[p], s->view, w.b); tm->end(); }
             if (two) TPT_CUDA(cudaEventRecord(w.ev_side, ss[p]));
             cur[p] ^= 1;
         }
