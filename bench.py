@@ -20,8 +20,8 @@ render of that frame: 784*784*16 = 9 834 496 samples.  The metric is Msamples/s 
              (tpt_probe_fma_throughput: one instruction per scheduler per cycle, 148 SMs x 4 x clock).  Beside it
              `lane_efficiency` (thread instructions / 32 x warp instructions), the fp32 FLOP/s of the step against
              the probe's fp32 rate, and per kernel: live CUDA-event time, issue fraction, lanes, DRAM and L2 GB/s.
-             `hbm` is the same accounting for the kernel that moves the most DRAM bytes (k_shade: 324 B of slot
-             state per active slot and iteration, algorithmic) against the measured HBM peak.
+             `hbm` is the same accounting for k_path's slot state and path vertices (algorithmic: 256 B of slot
+             state per slot and launch + 52 B per new vertex) against the measured HBM peak.
   ceilings   SURVEY.md 8(d)'s three: traversal algorithmic bytes/s against measured L2 and HBM read bandwidth
              (tpt_probe_read_bandwidth), and the DRAM bytes of the WHOLE step (ncu) per second against the HBM peak.
   cpu_baseline  the compiled reference (oracle/_ref, kind "reference") or the restatement (oracle/liboracle.so,
@@ -54,8 +54,10 @@ SAMPLES_PER_STEP = W * H * SPP
 # 27.5 nodes x 32 B + 3.56 primitives x 64 B + 48 B ray/hit record
 BYTES_PER_RAY = 27.5 * 32 + 3.56 * 64 + 48
 CPU_SAMPLE_SPP = SPP          # the reference arm renders the same 16 spp as the GPU arm (same_config)
-# slot state k_shade loads + stores per active slot and iteration: the algorithmic DRAM bytes
-SHADE_STATE_BYTES = 144 + 180
+# k_path: slot state loaded + stored once per slot and LAUNCH (144 + 112 B), one path vertex
+# (3 x 16 B) and one reverse pdf (4 B) stored per traced extension ray: the algorithmic DRAM bytes
+PATH_STATE_BYTES = 144 + 112
+PATH_VERTEX_BYTES = 48 + 4
 
 
 def measured_peaks():
@@ -389,7 +391,9 @@ def main():
     if rank == 0:
         peaks, peak_src = measured_peaks()
         k_ms = st["kernel_ms"]
-        trav_ms = k_ms["extend"] + k_ms["shadow"] + k_ms["generate"]
+        # the kernels that trace: k_generate (primary rays), k_path (the extension rays — fused with the per-slot state
+        # machine and the BSDF sampling since round 2, so its time is more than traversal), k_shadow_q
+        trav_ms = k_ms["shade"] + k_ms["extend"] + k_ms["shadow"] + k_ms["generate"]
         rays = st["traced_rays"]
         trav_gbs = rays * BYTES_PER_RAY / (trav_ms * 1e-3) / 1e9 if trav_ms > 0 else 0.0
         total_k = sum(k_ms.values())
@@ -409,8 +413,9 @@ def main():
             "step_dram_bytes_ncu": dram,
             "step_dram_gbs": dram / (step_ms * 1e-3) / 1e9 if dram else None,
             "step_dram_frac_of_hbm": dram / (step_ms * 1e-3) / 1e9 / peaks["hbm_gbs"] if dram else None,
-            "note": "the scene (5.7 KB) is staged in shared memory: the traversal kernels read neither L2 nor HBM for it, so "
-                    "the algorithmic-bytes figure is above the HBM peak and below the L2 one; neither binds"}
+            "note": "the scene (5.7 KB) is staged in shared memory: the kernels that trace read neither L2 nor HBM for it; "
+                    "the time is that of k_generate + k_path + k_shadow_q (k_path also shades: a lower bound of the "
+                    "traversal rate); neither ceiling binds"}
         # the roofline that binds: instruction issue (counts: ncu over every launch of one step, committed profile)
         sc_ = step_counters()
         roofline = {"bound": "issue", "achieved": None, "peak": issue_peak, "unit": "Gwarp-inst/s", "frac": None,
@@ -420,7 +425,7 @@ def main():
             winst, tinst, flops = tot["warp_inst"], tot["thread_inst"], tot["fp32_flops"]
             achieved = winst / (step_ms * 1e-3) / 1e9
             kernels = {}
-            live = {"k_generate": "generate", "k_shade": "shade", "k_extend": "extend", "k_expand": "expand",
+            live = {"k_generate": "generate", "k_path": "shade", "k_expand": "expand",
                     "k_connect": "connect", "k_shadow_q": "shadow", "k_mis": "mis"}
             for kname, c in sc_["kernels"].items():
                 if kname not in live or k_ms.get(live[kname], 0) <= 0:
@@ -429,10 +434,11 @@ def main():
                 kernels[kname] = {"ms": k_ms[live[kname]], "issue_frac": c["warp_inst"] / t / 1e9 / issue_peak,
                                   "lanes": c["thread_inst"] / c["warp_inst"], "dram_gbs": c["dram_bytes"] / t / 1e9,
                                   "l2_gbs": c["l2_bytes"] / t / 1e9, "fp32_tflops": c["fp32_flops"] / t / 1e12}
-            shade = sc_["kernels"].get("k_shade")
+            shade = sc_["kernels"].get("k_path")
             roofline.update({
                 "achieved": achieved, "frac": achieved / issue_peak,
-                "kernel": "whole step (k_shade 29 % of the kernel time is the largest; three kernels are resident at a time)",
+                "kernel": "whole step (k_path, the per-slot state machine with its rays, is the largest at ~40 % of the kernel "
+                          "time; the strategy kernels of the previous two rounds run beside it)",
                 "warp_inst_per_step": winst, "lane_efficiency": tinst / (32.0 * winst),
                 "useful_lane_frac": achieved / issue_peak * tinst / (32.0 * winst),
                 "fp32": {"flops_per_step": flops, "achieved_tflops": flops / (step_ms * 1e-3) / 1e12,
@@ -440,15 +446,18 @@ def main():
                 "per_kernel_serialised": kernels,
                 "counts_source": "profiles/step_counters.json (%s)" % sc_.get("source", "ncu"),
                 "note": "per-kernel times are CUDA-event times of a serialised run (TPT_FLAG_KERNEL_TIMES); in the timed "
-                        "run the strategy kernels overlap k_shade / k_extend, which is what `frac` of the step shows"})
+                        "run the strategy kernels overlap k_path, which is what `frac` of the step shows"})
             if shade and k_ms.get("shade", 0) > 0:
-                # every slot-iteration of k_shade emits one ray (extension or light start) or retires the slot
-                slot_iters = int(st["extend_rays"]) + W * H
-                algo = SHADE_STATE_BYTES * slot_iters
+                # k_path: every slot still drawing samples is loaded and stored once per launch (all of them in nearly
+                # every launch: a slot completes at most one or two samples per launch), and every traced extension ray
+                # stores one vertex
+                n_launch = int(st["kernel_launches"]["shade"])
+                algo = PATH_STATE_BYTES * W * H * n_launch + PATH_VERTEX_BYTES * int(st["extend_rays"])
                 t = k_ms["shade"] * 1e-3
-                roofline["hbm"] = {"bound": "hbm", "kernel": "k_shade (largest DRAM mover: slot state in, slot state + path "
-                                   "vertices out)", "algorithmic_bytes_per_slot_iteration": SHADE_STATE_BYTES,
-                                   "slot_iterations_per_step": slot_iters,
+                roofline["hbm"] = {"bound": "hbm", "kernel": "k_path (slot state in and out once per launch, path vertices out)",
+                                   "algorithmic_bytes_per_slot_and_launch": PATH_STATE_BYTES,
+                                   "algorithmic_bytes_per_vertex": PATH_VERTEX_BYTES,
+                                   "algorithmic_bytes_per_step": algo,
                                    "achieved": algo / t / 1e9 if algo else None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                    "frac": algo / t / 1e9 / peaks["hbm_gbs"] if algo else None,
                                    "traffic": shade["dram_bytes"] / max(1, shade["launches"]), "peak_source": peak_src}

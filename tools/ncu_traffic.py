@@ -20,7 +20,7 @@ for r in rows[1:]:
     a[0] += float(r[iV].replace(",", "")) * scale.get(r[iU], 1)
     a[1].add(r[0])
 out = {k: {"launches": len(v[1]), "dram_bytes_per_launch": v[0] / max(len(v[1]), 1)} for k, v in agg.items()}
-trav = [k for k in out if k in ("k_extend", "k_shadow_q", "k_generate")]
+trav = [k for k in out if k in ("k_extend", "k_shadow_q", "k_generate")]      # the kernels that ONLY trace (k_path also shades)
 tl = sum(out[k]["launches"] for k in trav)
 tb = sum(out[k]["dram_bytes_per_launch"] * out[k]["launches"] for k in trav)
 res = {"source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum over one BDPT 784^2 16 spp frame",

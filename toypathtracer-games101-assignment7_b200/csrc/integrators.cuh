@@ -109,7 +109,7 @@ TPT_DEV float light_pdf_from_hit(const SceneView& sc, int light, const DHit& h, 
     const float rawpdf = object_pdf(sc, light);
     const float costhetap = dotf(h.normal, -w_i);
     if (costhetap == 0.0f) return 0.0f;
-    return (float)((double)rawpdf * lightDistanceSqr / fabsf(costhetap));
+    return s_div(rawpdf * lightDistanceSqr, fabsf(costhetap));      // (double in the reference: shading tier, <= 2 ulp)
 }
 template <bool COUNT> TPT_DEV float light_pdf(Ctx& c, int light, f3 x, f3 w_i) {
     DHit h;
@@ -125,7 +125,7 @@ TPT_DEV f3 light_sample_dir(Ctx& c, int light, uint32_t& rng, f3 x, float* pdf) 
     w_i = s_normalize(w_i);
     const float rawpdf = object_pdf(c.sc, light);
     const float costhetap = dotf(pos.normal, -w_i);
-    *pdf = (float)((double)rawpdf * lightDistanceSqr / fabsf(costhetap));
+    *pdf = s_div(rawpdf * lightDistanceSqr, fabsf(costhetap));
     return w_i;
 }
 
