@@ -185,7 +185,7 @@ def workload_config():
     return {"workload": "Cornell-Standard %dx%d BDPT %d spp" % (W, H, SPP), "scene": SCENE, "mode": MODE,
             "width": W, "height": H, "spp": SPP,
             "cache": "GPU arm: the working set of a step (path store %.0f MB) exceeds the 126 MB L2, no flush needed"
-                     % (W * H * 3 * 32 * 48 / 1e6)}
+                     % (W * H * 5 * 32 * 48 / 1e6)}      # 5 rotating copies x 2 x 16 vertices x 48 B per slot
 
 
 REFERENCE_BUDGET_S = 330.0     # the reference arm stops taking steps once it would run past this
@@ -380,9 +380,11 @@ def main():
                            "rank0_share": {"spp": share_n.spp, "pixel_sets": share_n.world},
                            "ms_1gpu": ms1, "ms": msn, "speedup": ms1 / msn, "n_gpus": world,
                            "launches_per_frame_rank0": int(stn["launches"]),
-                           "limiter": "the dependent launch chain: a frame is %d launches on rank 0 whatever the share (a "
-                                      "sample is a chain of ~11 shade/extend iterations; the strategy kernels of an "
-                                      "iteration follow it); %.1f us per launch" % (int(stn["launches"]), 1e3 * msn / max(1, int(stn["launches"])))}
+                           "limiter": "the dependent launch chain: a frame is %d launches on rank 0 (rounds of k_path, 8 path "
+                                      "steps each, every round followed by its four strategy kernels; a slot completes at "
+                                      "most two samples per round, so the rounds go with the samples per slot — with fewer "
+                                      "slots per GPU the rounds stay and the kernels get smaller); %.1f us per launch"
+                                      % (int(stn["launches"]), 1e3 * msn / max(1, int(stn["launches"])))}
             if sscene is not scene:
                 del sacc, sout
                 sscene.close()
