@@ -246,6 +246,8 @@ HostScene* th_scene_create(const TptSceneDesc* d) {
     return s;
 }
 void th_scene_destroy(HostScene* s) { delete s; }
+// TPT_FLAG_BDPT_ALL_LIGHTS for this scene's renders (the pixel loop here and the wavefront pipeline of wavefront_host.cu)
+void th_set_light_pick(HostScene* hs, int on) { hs->view.light_pick = (on && hs->view.n_emissive > 1) ? 1 : 0; }
 int th_scene_leaves(const HostScene* s) { return s->view.n_leaves; }
 int th_scene_nodes(const HostScene* s) { return s->view.n_nodes; }
 
@@ -468,7 +470,7 @@ static unsigned long long RenderAll(const HostScene* s, int mode, int spp, float
                 trace_scene<COUNT>(c, primary, 0, &h);
                 camera_path_head(sc, h, cam);
                 const int nc = fill_path<COUNT>(c, rng, cam);
-                const LightStart ls = light_path_head(sc, rng, sc.emissive[0], light);
+                const LightStart ls = light_path_head(sc, rng, pick_light(sc, rng), light);      // (emissive[0] unless th_set_light_pick)
                 trace_scene<COUNT>(c, make_ray(light[0].x, ls.w_i), 0, &h);
                 int nl = 2;
                 if (light_path_first_hit(ls, h, light)) nl = fill_path<COUNT>(c, rng, light);

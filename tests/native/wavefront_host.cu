@@ -123,6 +123,7 @@ static int RenderShare(HostScene* hs, int mode, int spp, int sms, int partition,
     a.mode = mode; a.spp = spp; a.spp_total = spp;
     a.seed_mode = TPT_SEED_REF; a.partition = partition; a.rank = rank; a.world = world; a.stream = 0;
     a.prune = 1; a.sub = 0; a.nsub = 1;
+    a.all_lights = hs->view.light_pick;            // th_set_light_pick
     const size_t n3 = (size_t)hs->view.width * hs->view.height * 3;
     float* radiance = static_cast<float*>(calloc(n3, sizeof(float)));
     float* splat = static_cast<float*>(calloc(n3, sizeof(float)));

@@ -457,9 +457,12 @@ def wf_experiment(request, tmp_path_factory):
     return build_wavefront_mirror(tmp_path_factory, request.param.split())
 
 
-def wavefront_vs_pixel_loop(lib, scene, mode, spp, size, sms=1):
+def wavefront_vs_pixel_loop(lib, scene, mode, spp, size, sms=1, all_lights=False):
     import tpt_b200 as T
     m = Mirror(lib, scene, size, size)
+    if all_lights:
+        lib.th_set_light_pick.argtypes = [C.c_void_p, C.c_int]
+        lib.th_set_light_pick(m.h, 1)
     img = np.zeros((size, size, 3), np.float32)
     stats = np.zeros(8, np.uint64)
     rc = lib.th_wavefront_render(m.h, T.MODES[mode], spp, sms, img.ctypes.data, stats.ctypes.data)
@@ -490,6 +493,17 @@ def test_bdpt_wavefront_is_the_pixel_loop(wfmirror, scene, spp, sms):
     assert np.isfinite(img).all()
     assert np.allclose(img, ref, rtol=2e-4, atol=2e-5), float(np.abs(img - ref).max())
     assert ref.mean() > 0.05
+
+
+def test_bdpt_all_lights_wavefront_is_the_pixel_loop(wfmirror):
+    """TPT_FLAG_BDPT_ALL_LIGHTS on the two-light scene (quad + emissive Sphere): k_path's light start on a chosen emissive
+    object and the t = 0 density of k_mis agree with the pixel loop's light_path_head / mis_denominator — and both light
+    the scene far more than the default mode, which starts light subpaths on the first emissive object only."""
+    img, ref = wavefront_vs_pixel_loop(wfmirror, "twolights", "bdpt", 3, 32, all_lights=True)
+    assert np.isfinite(img).all()
+    assert np.allclose(img, ref, rtol=2e-4, atol=2e-5), float(np.abs(img - ref).max())
+    default, _ = wavefront_vs_pixel_loop(wfmirror, "twolights", "bdpt", 3, 32)
+    assert img.mean() > 1.2 * default.mean()
 
 
 def test_bdpt_samples_that_find_no_strategy_room_wait_a_round(wfmirror, monkeypatch):
