@@ -524,9 +524,13 @@ TPT_DEV unsigned char* trav_coop(unsigned char* smem, unsigned stage_bytes) {
 
 // Scene::Intersect for a whole warp.  coop: this block's cooperative area (TPT_COOP_BYTES), cand: the
 // thread's candidate column for the fallback walk.
-TPT_DEV void closest_hit_warp(const SceneView& sc, const DRay& r, int cull, bool has_ray, unsigned char* coop, int* cand,
-                              int stride, DHit* hit) {
-    if (sc.n_leaves == 0) {                                   // large scene (uniform): the hierarchy walk
+// KIND: what the caller knows about the scene at compile time — 0: nothing (both paths compiled), 1: the scene has
+// the flat leaf list (n_leaves > 0), 2: it has not.  k_path exists in variants 1 and 2: each leaves out the other's
+// traversal code (a third of the kernel's instructions), which the warps otherwise step around in every path step.
+template <int KIND>
+TPT_DEV void closest_hit_warp_t(const SceneView& sc, const DRay& r, int cull, bool has_ray, unsigned char* coop, int* cand,
+                                int stride, DHit* hit) {
+    if (KIND == 2 || (KIND == 0 && sc.n_leaves == 0)) {       // large scene (uniform): the hierarchy walk
         if (has_ray) closest_hit_deferred(sc, r, cull, 0, sc.n_nodes, cand, stride, hit);
         return;
     }
@@ -536,7 +540,14 @@ TPT_DEV void closest_hit_warp(const SceneView& sc, const DRay& r, int cull, bool
     const CoopWarp cw = coop_warp(coop);
     unsigned base, cnt;
     const bool done = coop_test(sc, r, cull, m0, m1, cw, &base, &cnt);
-    if (has_ray && !flat) { closest_hit_deferred(sc, r, cull, 0, sc.n_nodes, cand, stride, hit); return; }
+    if (has_ray && !flat) {                                    // a ray that can produce NaNs: the literal walk (a handful per frame)
+        double best_t = 0.0;
+        int best = -1;
+        const int nc = walk_record<false>(sc, r, cull, 0, sc.n_nodes, cand, stride, best, best_t);
+        for (int k = 0; k < nc; ++k) settle_candidate(sc, r, cull, cand[k * stride], best, best_t);
+        finish_hit(sc, r, best, best_t, hit);
+        return;
+    }
     if (!has_ray) return;
     double best_t = 0.0;
     int best = -1;
@@ -551,6 +562,10 @@ TPT_DEV void closest_hit_warp(const SceneView& sc, const DRay& r, int cull, bool
         while (m0 | m1) settle_candidate(sc, r, cull, __float_as_int(sc.leaves[2 * flat_next(m0, m1)].w), best, best_t);
     }
     finish_hit(sc, r, best, best_t, hit);
+}
+TPT_DEV void closest_hit_warp(const SceneView& sc, const DRay& r, int cull, bool has_ray, unsigned char* coop, int* cand,
+                              int stride, DHit* hit) {
+    closest_hit_warp_t<0>(sc, r, cull, has_ray, coop, cand, stride, hit);
 }
 
 // Scene::Intersect, Scene.cpp:21-35

@@ -321,6 +321,7 @@ TPT_DEV PVert unpack_vertex(const float4 a, const float4 b, const float4 c) {
 #ifndef PATH_MIN_BLOCKS
 #define PATH_MIN_BLOCKS 3         /* 85 registers, no spills: 33.1 vs 33.4 ms (Cornell), 44.5 vs 48.3 ms (bunny) against 2 */
 #endif
+template <int KIND>      // 1: scenes with the flat leaf list, 2: large scenes (closest_hit_warp_t)
 __global__ void __launch_bounds__(256, PATH_MIN_BLOCKS) k_path(SceneView g, RenderArgs a, WfBuffers b, int cur, int par, unsigned long long* stats) {
     pdl_launch_dependents();
     const SceneView sc = stage_scene(g, tpt_smem);
@@ -549,7 +550,7 @@ __global__ void __launch_bounds__(256, PATH_MIN_BLOCKS) k_path(SceneView g, Rend
         // ---- phase 4: closest hit of the new ray (Scene::Intersect), the warp's 32 rays together
         const bool has_ray = __float_as_int(ro.w) >= 0;
         DHit h;
-        closest_hit_warp(sc, make_ray(mk3(ro), mk3(rd)), __float_as_int(ro.w), has_ray, coop, cand, blockDim.x, &h);
+        closest_hit_warp_t<KIND>(sc, make_ray(mk3(ro), mk3(rd)), __float_as_int(ro.w), has_ray, coop, cand, blockDim.x, &h);
         if (has_ray) {
             rays++;
             hr = make_float4(h.coords.x, h.coords.y, h.coords.z, __int_as_float(h.prim));
@@ -868,7 +869,8 @@ int wavefront_render(TptScene* s, const RenderArgs& a, float* d_radiance, float*
     const unsigned tsmem = TPT_TRAV_SMEM(smem, 256);   // traversal kernels: + candidate columns + cooperative area
     if (tsmem > 48u * 1024u) {                         // mid-size staged scenes: opt in to more dynamic shared memory
         TPT_CUDA(cudaFuncSetAttribute(k_generate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
-        TPT_CUDA(cudaFuncSetAttribute(k_path, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+        TPT_CUDA(cudaFuncSetAttribute(k_path<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+        TPT_CUDA(cudaFuncSetAttribute(k_path<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
         TPT_CUDA(cudaFuncSetAttribute(k_shadow_q, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
     }
     const int grid = std::max(1, std::min((S + 255) / 256, s->num_sms * 8));
@@ -904,7 +906,7 @@ int wavefront_render(TptScene* s, const RenderArgs& a, float* d_radiance, float*
         if (two && it >= WF_CHAINS) TPT_CUDA(cudaStreamWaitEvent(st, w->ev_side[e], 0));
         // one block per 256 slots of the frame (a block past the end of the active list exits at once): the blocks
         // are the regions of the done list
-        tm->begin(TPT_K_SHADE); launch_pdl(k_path, b.n_regions, tsmem, st, view, a, b, cur, par, s->d_stats); tm->end();
+        tm->begin(TPT_K_SHADE); launch_pdl(view.n_leaves > 0 ? k_path<1> : k_path<2>, b.n_regions, tsmem, st, view, a, b, cur, par, s->d_stats); tm->end();
         if (two) { TPT_CUDA(cudaEventRecord(w->ev_path[e], st)); TPT_CUDA(cudaStreamWaitEvent(ss, w->ev_path[e], 0)); }
         tm->begin(TPT_K_EXPAND); launch_pdl(k_expand, b.n_regions, 0u, ss, bs, par); tm->end();
         tm->begin(TPT_K_CONNECT); launch_pdl(k_connect, pgrid, smem, ss, view, bs, par); tm->end();
