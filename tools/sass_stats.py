@@ -2,7 +2,7 @@
 """Static view of a compile-time variant, without a GPU: registers, spills and the opcode mix of the hot kernels.
 
     python tools/sass_stats.py                       # the build as shipped
-    python tools/sass_stats.py -DTPT_WIDE_TRIS       # a variant (flags are passed to nvcc as NVEXTRA would)
+    python tools/sass_stats.py -DPATH_MIN_BLOCKS=2   # a variant (flags are passed to nvcc as NVEXTRA would)
 
 Compiles csrc/wavefront.cu and csrc/pt_wavefront.cu into a temporary directory with the Makefile's flags plus the
 given ones and prints, per kernel: registers, stack frame, spill bytes (ptxas -v) and how many SASS instructions of
