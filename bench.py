@@ -120,9 +120,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Samples received between t0 and t1 (host clock around the timed region).  The sampler is started before the
+        warm-up steps (nvidia-smi needs ~0.2 s to answer its first query); if a short timed region holds no sample, the
+        samples of the warm-up steps — the same work, directly before — are used and `window` says so."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -130,6 +133,11 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        window = "timed region"
+        rows = [r for t, r in self.rows if t0 is None or (t0 <= t <= t1 + 0.05)]
+        if not rows:
+            rows, window = [r for _, r in self.rows], "warm-up steps directly before the timed region (it was shorter than one sampling period)"
+        self.rows = rows
         sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
         mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
@@ -140,7 +148,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 class quiet_stdout:
@@ -277,23 +285,25 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 0)):
-        step()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 0)):
+        step()
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_region0 = time.time()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     barrier()
+    t_region1 = time.time()
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_region0, t_region1) if rank == 0 else None
 
     # one more step with per-launch CUDA events for the roofline + launch count (outside the timed region)
     st = step(flags=T.FLAG_KERNEL_TIMES, want_stats=True)
