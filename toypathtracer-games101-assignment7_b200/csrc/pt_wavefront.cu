@@ -419,8 +419,14 @@ __global__ void __launch_bounds__(256) k_pt_shadow(SceneView g, PtBuffers b, int
 // partition's slots, launched alternately from the one host thread: k_pt_shade of one half runs beside
 // k_pt_extend / k_pt_shadow of the other (a chain by itself is shade -> (extend || shadow) -> shade, strictly
 // serial).  Slots never interact and every pixel is written by its own slot, so the image is the same bit for bit.
+// Two chains for scenes with the flat leaf list (3 and 4 measured no better); three for large scenes, whose *_long kernels
+// are a few warps per SM waiting on L2 — another chain's kernels fill the machine meanwhile (bunny pt_full 32 spp:
+// 49.5 / 47.9 / 48.3 / 49.9 ms with 2 / 3 / 4 / 6 chains).
 #ifndef PT_PIPES
-#define PT_PIPES 2
+#define PT_PIPES 3          /* chains allocated */
+#endif
+#ifndef PT_PIPES_FLAT
+#define PT_PIPES_FLAT 2
 #endif
 struct PtPipe {
     int S = 0;
@@ -495,7 +501,7 @@ int pt_wavefront_render(TptScene* s, const RenderArgs& a0, float* d_radiance, cu
     const char* env_two = getenv("TPT_WF_TWO_STREAMS");
     const bool two = !tm->on && !(env_two && atoi(env_two) == 0);      // per-kernel timing needs one stream
     // small partitions stay one chain: half of them would not fill the machine
-    const int npipes = (two && tpt_part_slots(a0, npix) >= s->num_sms * 2048) ? PT_PIPES : 1;
+    const int npipes = (two && tpt_part_slots(a0, npix) >= s->num_sms * 2048) ? (s->view.n_leaves == 0 ? PT_PIPES : std::min(PT_PIPES, PT_PIPES_FLAT)) : 1;
     const unsigned smem = s->view.stage_bytes;
     const unsigned tsmem = TPT_TRAV_SMEM(smem, 256);
     if (tsmem > 48u * 1024u) {                         // mid-size staged scenes: opt in to more dynamic shared memory
