@@ -102,7 +102,7 @@ def test_device_code_is_sm100a_with_the_documented_resources(tpt):
             usage.setdefault(short.group(1), []).append((int(reg), int(stack)))
     limits = {"k_path": 88, "k_expand": 64, "k_connect": 64, "k_shadow_q": 64, "k_mis": 64,
               "k_pt_shade": 128, "k_pt_extend": 64, "k_pt_shadow": 64, "k_pt_extend_budget": 64, "k_pt_extend_long": 64,
-              "k_pt_shadow_long": 64}
+              "k_pt_shadow_long": 64, "k_shadow_q_long": 64}
     for k, lim in limits.items():
         assert k in usage, "kernel %s not found in libtpt.so" % k
         for reg, stack in usage[k]:

@@ -110,6 +110,21 @@ def test_pt_is_deterministic_and_pipelines_agree(tpt):
     s.close()
 
 
+def test_large_scene_parked_walks_give_the_pixel_loops_frame(tpt):
+    """The bunny scene has no flat leaf list: the PathTrace queue pipeline gives every walk a budget of node visits, parks
+    the unfinished ones and finishes them in k_pt_extend_long / k_pt_shadow_long (three interleaved launch chains).  A
+    parked walk resumes from its node index and best hit, i.e. performs the very same tests: the frame is the per-pixel
+    kernel's (which walks every ray to the end in one go), run to run bit for bit."""
+    s = gpu_scene("bunny", 256, 256)
+    a, sa = s.render("pt_full", 6)
+    b, _ = s.render("pt_full", 6)
+    assert (a.view(np.uint32) == b.view(np.uint32)).all()
+    c, sc = s.render("pt_full", 6, pipeline=tpt.PIPE_MEGAKERNEL)
+    assert sa["ref_rays"] == sc["ref_rays"]
+    assert np.allclose(a, c, rtol=1e-4, atol=1e-5)
+    s.close()
+
+
 @pytest.mark.parametrize("scene", ["standard", "refractive", "silver", "occlusion"])
 def test_bdpt_pipelines_agree_per_pixel(tpt, scene):
     """The wavefront pipeline (queues, shared-suffix MIS, atomics) and the per-pixel validation kernel

@@ -26,6 +26,9 @@
 
 #include "wf_common.cuh"
 
+#ifndef WF_WALK_BUDGET
+#define WF_WALK_BUDGET 24       /* large scenes: node visits a walk gets per turn before it is parked (pt_wavefront.cu: PT_WALK_BUDGET) */
+#endif
 #ifndef WF_MIN_BLOCKS
 #define WF_MIN_BLOCKS 4   // resident 256-thread CTAs per SM the shading kernels are compiled for
 #endif
@@ -61,12 +64,13 @@ struct WfCounters {
     // i clears the set of round i + 1 (no separate reset launch)
     unsigned long long done_pairs[ROUND_SETS];   // strategy records of the round (written by k_expand)
     unsigned long long shadow_mis[ROUND_SETS];   // low word: shadow queue length, high word: MIS queue length (appended together)
+    unsigned n_long[ROUND_SETS];                 // shadow walks parked by k_shadow_q for k_shadow_q_long (large scenes)
 };
 
 // ---- slot state ----------------------------------------------------------------------
 // info bits: [0] path (0 camera, 1 light)  [1..4] i = index of the last stored vertex
 //            [5..9] count  [10] pending ray  [11] light-first ray  [12] rr pass
-//            [13] waiting for pair space  [15] ray left from cam[1]
+//            [13] waiting for pair space  [14] walk parked (large scenes)  [15] ray left from cam[1]
 //            [16..20] nc of this sample  [21] camera subpath ended on a Background vertex  [22] light subpath did
 //            [23..25] which copy of the path store this sample writes (vtx_at)
 //            [26..28] samples the slot completed in the previous round (k_path: which copies are still being read)
@@ -79,6 +83,7 @@ struct WfCounters {
 #define INFO_WAIT (1u << 13)
 #define INFO_PARITY(i) (((i) >> 23) & 7u)
 #define INFO_UPREV(i) (((i) >> 26) & 7u)
+#define INFO_WALKING (1u << 14)       /* large scenes: the pending ray's walk is parked — `hit` holds its cursor, `walk_d` the ray */
 #define INFO_FROM_C1 (1u << 15)
 #define INFO_NC(i) (((i) >> 16) & 31u)
 #define INFO_CAM_BG (1u << 21)
@@ -108,6 +113,7 @@ struct WfBuffers {
     // the vertex the pending ray left from, indexed by slot alone (k_path keeps it in registers between its
     // steps and parks it here between launches)
     float4 *curA, *curB, *curC;
+    float4* walk_d;                    // large scenes: {direction, asfloat(cull)} of a ray whose walk is parked between launches
     float4* back;                      // {unit vector from that vertex to its predecessor, |cos cos'| / dist^2 between the two}
     int* active[2];
     // completed samples of a round, three buffers used in rotation like the counters.  Block r of k_path owns
@@ -127,6 +133,7 @@ struct WfBuffers {
     // chasing queue -> strategy record -> vertices:
     float4* shadow_q;                  // 2 per entry: {from, asfloat(strategy id)} {to, asfloat(cull)}
     uint4* mis_q;                      // {slot, s | t << 8 | parity << 16, strategy id, 0}
+    uint2* long_sh;                    // large scenes: parked shadow walks {shadow queue index, next node}
     WfCounters* ctr;
 };
 
@@ -345,11 +352,13 @@ __global__ void __launch_bounds__(256, PATH_MIN_BLOCKS) k_path(SceneView g, Rend
     unsigned info = 0, spp_seen = 0, emask = 0;
     uint32_t rng = 0;
     float4 hr = zero4, pa = zero4, cA = zero4, cB = zero4, cC = zero4, bk = zero4, c1A = zero4, c1B = zero4;
+    float4 wd = zero4;          // KIND 2: the ray of a parked walk
     if (live) {
         info = b.info[slot]; spp_seen = b.spp_done[slot]; emask = b.emask[slot]; rng = b.rng[slot];
         hr = b.hit[slot]; pa = b.pend[slot];
         cA = b.curA[slot]; cB = b.curB[slot]; cC = b.curC[slot]; bk = b.back[slot];
         c1A = b.c1A[slot]; c1B = b.c1B[slot];
+        if (KIND == 2 && (info & INFO_WALKING)) wd = b.walk_d[slot];
     }
     bool alive = live;          // still stepping in this launch
     bool keep = live;           // stays in the active queue
@@ -367,7 +376,10 @@ __global__ void __launch_bounds__(256, PATH_MIN_BLOCKS) k_path(SceneView g, Rend
         f3 prev_x = mk3(0.0f), prev_N = mk3(0.0f);
         int prev_type = VT_CAMERA;
         bool path_done = false, completing = false, fresh = false;
-        if (alive) {
+        // large scenes: a lane whose walk is parked (INFO_WALKING) only walks on in this step — the state machine sees the
+        // ray's hit once the walk is complete
+        const bool walking = KIND == 2 && alive && (info & INFO_WALKING) != 0;
+        if (alive && !walking) {
             const bool waiting = (info & INFO_WAIT) != 0;
             path_done = waiting;          // a waiting slot sits on a finished light subpath
             int cur_type = -1;            // type of vertex i, when known
@@ -545,15 +557,48 @@ __global__ void __launch_bounds__(256, PATH_MIN_BLOCKS) k_path(SceneView g, Rend
             path = 1; i = 0; count = 1;
             flags = INFO_PENDING | INFO_LIGHT_FIRST;
         }
-        if (stepping) info = make_info(path, i, count, flags | (parity << 23) | bgbits, nc);
+        if (stepping && !walking) info = make_info(path, i, count, flags | (parity << 23) | bgbits, nc);
 
         // ---- phase 4: closest hit of the new ray (Scene::Intersect), the warp's 32 rays together
         const bool has_ray = __float_as_int(ro.w) >= 0;
-        DHit h;
-        closest_hit_warp_t<KIND>(sc, make_ray(mk3(ro), mk3(rd)), __float_as_int(ro.w), has_ray, coop, cand, blockDim.x, &h);
-        if (has_ray) {
-            rays++;
-            hr = make_float4(h.coords.x, h.coords.y, h.coords.z, __int_as_float(h.prim));
+        if (KIND == 2) {
+            // large scene: the hierarchy walk, WF_WALK_BUDGET node visits per step.  A walk that is not finished by then is
+            // parked in the slot (cursor in `hit`, ray in `walk_d`) and goes on in the lane's next step, while the other
+            // lanes of the warp move on with their paths: a warp no longer waits for the one ray that enters the mesh
+            // (the same walk cut into pieces: walk_resume, traverse.cuh)
+            if (has_ray || walking) {
+                WalkCursor c;
+                f3 o3, d3;
+                int cull;
+                if (walking) {
+                    o3 = mk3(cA); d3 = mk3(wd); cull = __float_as_int(wd.w);
+                    c.i = __float_as_int(hr.x); c.best = __float_as_int(hr.y);
+                    memcpy(&c.best_t, &hr.z, 8);                      // (hr.z, hr.w: the double's two words)
+                } else {
+                    rays++;
+                    o3 = mk3(ro); d3 = mk3(rd); cull = __float_as_int(ro.w);
+                    c = walk_begin(0);
+                }
+                const DRay r = make_ray(o3, d3);
+                if (walk_resume(sc, r, cull, sc.n_nodes, true, WF_WALK_BUDGET, c)) {
+                    DHit h;
+                    finish_hit(sc, r, c.best, c.best_t, &h);
+                    hr = make_float4(h.coords.x, h.coords.y, h.coords.z, __int_as_float(h.prim));
+                    info &= ~INFO_WALKING;
+                } else {
+                    hr = make_float4(__int_as_float(c.i), __int_as_float(c.best), 0.0f, 0.0f);
+                    memcpy(&hr.z, &c.best_t, 8);
+                    if (!walking) wd = make_float4(d3.x, d3.y, d3.z, __int_as_float(cull));
+                    info |= INFO_WALKING;
+                }
+            }
+        } else {
+            DHit h;
+            closest_hit_warp_t<KIND>(sc, make_ray(mk3(ro), mk3(rd)), __float_as_int(ro.w), has_ray, coop, cand, blockDim.x, &h);
+            if (has_ray) {
+                rays++;
+                hr = make_float4(h.coords.x, h.coords.y, h.coords.z, __int_as_float(h.prim));
+            }
         }
     }
 
@@ -561,6 +606,7 @@ __global__ void __launch_bounds__(256, PATH_MIN_BLOCKS) k_path(SceneView g, Rend
         b.info[slot] = (info & ~(7u << 26)) | (u_now << 26); b.spp_done[slot] = spp_seen; b.emask[slot] = emask; b.rng[slot] = rng;
         b.hit[slot] = hr; b.pend[slot] = pa;
         b.curA[slot] = cA; b.curB[slot] = cB; b.curC[slot] = cC; b.back[slot] = bk;
+        if (KIND == 2 && (info & INFO_WALKING)) b.walk_d[slot] = wd;
     }
     const unsigned at = wf_append(&b.ctr->n_active[cur ^ 1], keep);
     if (keep) next_list[at] = slot;
@@ -575,6 +621,7 @@ __global__ void __launch_bounds__(256, PATH_MIN_BLOCKS) k_path(SceneView g, Rend
             b.ctr->ticket = 0u;
             b.ctr->n_active[cur] = 0u;                                   // the list just consumed: the next launch builds its successor there
             b.ctr->shadow_mis[(par + 1) % ROUND_SETS] = 0ull;         // (its last readers finished before this launch started)
+            b.ctr->n_long[(par + 1) % ROUND_SETS] = 0u;
         }
     }
 }
@@ -693,6 +740,7 @@ __global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_connect(SceneView g, WfB
 #ifndef SHADOW_MIN_BLOCKS
 #define SHADOW_MIN_BLOCKS 4
 #endif
+
 __global__ void __launch_bounds__(256, SHADOW_MIN_BLOCKS) k_shadow_q(SceneView g, RenderArgs a, WfBuffers b, int par, unsigned long long* stats) {
     pdl_launch_dependents();
     const SceneView sc = stage_scene(g, tpt_smem);
@@ -714,11 +762,53 @@ __global__ void __launch_bounds__(256, SHADOW_MIN_BLOCKS) k_shadow_q(SceneView g
             rays++;
         }
         // per-lane tests here: a shadow query stops at its first blocking hit, which sharing the tests would give up
-        if (live) visible = !shadow_check_deferred(sc, mk3(e0), mk3(e1), __float_as_int(e1.w), cand, blockDim.x);
+        bool parked = false;
+        int cursor = 0;
+        if (live) {
+            if (sc.n_leaves == 0) {      // large scene: WF_WALK_BUDGET node visits, the rest parked for k_shadow_q_long (as PathTrace does)
+                const ShadowQuery sq = shadow_begin(mk3(e0), mk3(e1));
+                bool found = false;
+                parked = !shadow_resume(sc, sq, __float_as_int(e1.w), WF_WALK_BUDGET, cursor, &found);
+                visible = !parked && !found;
+            } else {
+                visible = !shadow_check_deferred(sc, mk3(e0), mk3(e1), __float_as_int(e1.w), cand, blockDim.x);
+            }
+        }
+        if (sc.n_leaves == 0) {
+            const unsigned at = wf_append(&b.ctr->n_long[par], parked);
+            if (parked) b.long_sh[at] = make_uint2(q, (unsigned)cursor);
+        }
         const unsigned am = wf_append(reinterpret_cast<unsigned*>(&b.ctr->shadow_mis[par]) + 1, visible);   // the MIS word
         if (visible) b.mis_q[am] = out;
     }
     flush_stats(0, rays, 0, stats, rays);
+}
+
+// The shadow walks k_shadow_q parked (large scenes), to their end; survivors join the MIS queue.
+__global__ void __launch_bounds__(256) k_shadow_q_long(SceneView g, WfBuffers b, int par) {
+    pdl_launch_dependents();
+    const SceneView sc = stage_scene(g, tpt_smem);
+    pdl_wait();
+    const unsigned n = b.ctr->n_long[par];
+    const unsigned total = (n + 31u) & ~31u;
+    for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
+        bool visible = false;
+        uint4 out = make_uint4(0u, 0u, 0u, 0u);
+        if (k < n) {
+            const uint2 e = b.long_sh[k];
+            const float4 e0 = b.shadow_q[2 * (size_t)e.x], e1 = b.shadow_q[2 * (size_t)e.x + 1];
+            const unsigned p = __float_as_uint(e0.w);
+            const uint2 rec = b.pair_rec[p];
+            out = make_uint4(rec.x, rec.y, p, 0u);
+            const ShadowQuery sq = shadow_begin(mk3(e0), mk3(e1));
+            int cursor = (int)e.y;
+            bool found = false;
+            shadow_resume(sc, sq, __float_as_int(e1.w), 0x7fffffff, cursor, &found);
+            visible = !found;
+        }
+        const unsigned am = wf_append(reinterpret_cast<unsigned*>(&b.ctr->shadow_mis[par]) + 1, visible);   // the MIS word
+        if (visible) b.mis_q[am] = out;
+    }
 }
 
 // ---- mis + accumulate: power-heuristic weight of the surviving strategies, added to the
@@ -795,6 +885,7 @@ static unsigned long long wf_pair_cap(int S) {
 static int wf_alloc(TptScene* s, int S) {
     const int n_regions = (S + 255) / 256;
     const unsigned long long cap = wf_pair_cap(S);
+    const bool large = s->view.n_leaves == 0;          // no flat leaf list: the parked-walk queue of k_shadow_q_long
     if (s->wf && s->wf->S == S && s->wf->b.pair_cap == cap) return TPT_OK;
     if (s->wf) cudaDeviceSynchronize();      // a different share: the previous one's launches may still be running on its streams
     wavefront_destroy(s);
@@ -829,12 +920,13 @@ static int wf_alloc(TptScene* s, int S) {
               get(REG, (void**)&b.reg_pairs) && get(REG, (void**)&b.reg_done) &&
               get(b.pair_cap * sizeof(uint2), (void**)&b.pair_rec) && get(b.pair_cap * sizeof(float4), (void**)&b.pair_val) &&
               get(b.pair_cap * 2 * sizeof(float4), (void**)&b.shadow_q) && get(b.pair_cap * sizeof(uint4), (void**)&b.mis_q) &&
-              get(sizeof(WfCounters), (void**)&b.ctr);
+              get(sizeof(WfCounters), (void**)&b.ctr) && (!large || (get(b.pair_cap * sizeof(uint2), (void**)&b.long_sh) && get(F4, (void**)&b.walk_d)));
     for (int k = 0; k < WF_CHAINS; ++k) {
         w->bs[k] = b;
         if (k == 0) continue;
         ok = ok && get(b.pair_cap * sizeof(uint2), (void**)&w->bs[k].pair_rec) && get(b.pair_cap * sizeof(float4), (void**)&w->bs[k].pair_val) &&
-             get(b.pair_cap * 2 * sizeof(float4), (void**)&w->bs[k].shadow_q) && get(b.pair_cap * sizeof(uint4), (void**)&w->bs[k].mis_q);
+             get(b.pair_cap * 2 * sizeof(float4), (void**)&w->bs[k].shadow_q) && get(b.pair_cap * sizeof(uint4), (void**)&w->bs[k].mis_q) &&
+             (!large || get(b.pair_cap * sizeof(uint2), (void**)&w->bs[k].long_sh));
     }
     if (ok && !(w->h_flag = static_cast<unsigned*>(tpt_pinned_alloc(64)))) ok = false;
     if (!ok) { wavefront_destroy(s); return TPT_ERR_OOM; }
@@ -911,6 +1003,7 @@ int wavefront_render(TptScene* s, const RenderArgs& a, float* d_radiance, float*
         tm->begin(TPT_K_EXPAND); launch_pdl(k_expand, b.n_regions, 0u, ss, bs, par); tm->end();
         tm->begin(TPT_K_CONNECT); launch_pdl(k_connect, pgrid, smem, ss, view, bs, par); tm->end();
         tm->begin(TPT_K_SHADOW); launch_pdl(k_shadow_q, pgrid, (unsigned)TPT_SHADOW_SMEM(smem, 256), ss, view, a, bs, par, s->d_stats); tm->end();
+        if (view.n_leaves == 0) { tm->begin(TPT_K_SHADOW); launch_pdl(k_shadow_q_long, pgrid, smem, ss, view, bs, par); tm->end(); }
         tm->begin(TPT_K_MIS); launch_pdl(k_mis, pgrid, smem, ss, view, a, bs, par, d_radiance, d_splat); tm->end();
         if (two) TPT_CUDA(cudaEventRecord(w->ev_side[e], ss));
         cur ^= 1;
