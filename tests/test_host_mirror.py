@@ -262,7 +262,7 @@ def test_resumable_walk_is_the_walk(mirror, scene, budget):
 
 @pytest.mark.parametrize("scene", SCENES)
 def test_warp_cooperative_closest_hit(mirror, scene):
-    """closest_hit_warp (what k_extend / k_pt_extend / k_intersect call): the candidates of a warp's 32 rays pooled in
+    """closest_hit_warp (what k_path / k_pt_extend / k_intersect call): the candidates of a warp's 32 rays pooled in
     shared memory, dealt out 32 at a time, tested by whichever lane gets them with the owner's ray fetched by shuffles,
     and read back by the owner in visit order.  Run as 32 coroutines that meet at every warp collective."""
     m = Mirror(mirror, scene)
@@ -486,7 +486,7 @@ def test_pathtrace_wavefront_is_the_pixel_loop(wfmirror, scene, mode, spp):
 
 @pytest.mark.parametrize("scene,spp,sms", [("standard", 4, 1), ("refractive", 3, 2), ("occlusion", 3, 1), ("bunny", 2, 1)])
 def test_bdpt_wavefront_is_the_pixel_loop(wfmirror, scene, spp, sms):
-    """k_generate / k_shade / k_extend / k_expand / k_connect / k_shadow_q / k_mis with wavefront_render's loop (strategy
+    """k_generate / k_path / k_expand / k_connect / k_shadow_q / k_mis with wavefront_render's loop (strategy
     records, shadow and MIS queues, rotating path-store copies): every pixel within float addition order of the pixel
     loop, the same number of subpath vertices."""
     img, ref = wavefront_vs_pixel_loop(wfmirror, scene, "bdpt", spp, 32, sms)

@@ -103,7 +103,7 @@ struct WfBuffers {
     float4* verts;
     float4* l0;
     float4 *c1A, *c1B;                 // camera vertex 1 (the cached primary hit) once more, indexed by slot alone:
-                                       // k_shade reads it every iteration, coalesced
+                                       // k_path reads it at every launch, coalesced
     uint32_t* rng;
     unsigned* info;
     unsigned* spp_done;
@@ -137,10 +137,9 @@ struct WfBuffers {
     WfCounters* ctr;
 };
 
-// Three copies ("parities") of a slot's path store, used in rotation by its consecutive samples: the strategy
-// kernels of iteration i run beside k_shade / k_extend of iteration i + 1, a sample can complete one iteration
-// after the previous one (primary ray leaves the scene, light ray leaves the scene), so the sample after THAT
-// must not write where the first one is still being read.
+// PATH_COPIES copies ("parities") of a slot's path store, used in rotation by its consecutive samples: the strategy
+// kernels of a round run beside k_path of the next rounds and read the completed samples' copies, so the samples a
+// slot starts meanwhile must not write there (the rule is at the top of this file).
 TPT_DEV size_t vtx_at(int parity, int path, int k, int slot) { return ((((size_t)slot * PATH_COPIES + parity) * 2 + path) * MAX_BDPT_PATH_LENGTH + k) * 3; }
 TPT_DEV size_t l0_at(int parity, int slot) { return ((size_t)slot * PATH_COPIES + parity) * 3; }
 TPT_DEV void store_vertex(float4* w, size_t at, const PVert& v) {
@@ -148,7 +147,7 @@ TPT_DEV void store_vertex(float4* w, size_t at, const PVert& v) {
     w[at + 1] = make_float4(v.N.x, v.N.y, v.N.z, __int_as_float(pack_pt(v.prim, v.type)));
     w[at + 2] = make_float4(v.alpha.x, v.alpha.y, v.alpha.z, 0.0f);
 }
-// {original area pdf of vertex i, reverse pdf towards vertex i (C.w, written by k_shade)}
+// {original area pdf of vertex i, reverse pdf towards vertex i (C.w, written by k_path)}
 struct CamAux {
     const WfBuffers& b; int slot; int parity;
     TPT_DEV float2 operator()(int i) const {
@@ -234,7 +233,7 @@ template <class Fallback> struct AuxPair {
 // Of the nc * (nl + 1) - 1 strategies the reference loops over (BDPT.cpp:290-313), those with a
 // Background end contribute exactly zero (BDPT.cpp:180-187; (nc, 0) adds alpha * backgroundColor, zero
 // for a black background) and so do the t = 0 strategies whose camera vertex is not on an emitter
-// (BDPT.cpp:196-197).  k_shade knows both when the vertices are made, so those strategies are never
+// (BDPT.cpp:196-197).  k_path knows both when the vertices are made, so those strategies are never
 // enumerated: connections s = 1..nc', t = 1..nl' (primes: without a Background end), then (s, 0) for the
 // emitter vertices, then (nc, 0) if the background is lit.
 TPT_DEV bool prim_emissive(const SceneView& sc, int prim) {
