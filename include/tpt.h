@@ -332,6 +332,15 @@ int tpt_material_sample_batch(TptScene* scene, int32_t mat, const float* wo, con
                               const uint32_t* seeds, size_t n, float* out_wi, float* out_pdf,
                               uint32_t* out_state);
 
+/* DirectLightSampler (PathTracer.cpp:6-40) for emissive object `light_object` (an index into objects[]) at n shading
+ * points x:  op 0 = sample (PathTracer.cpp:26-40) from ResetRandom(seeds[i]): direction to the sampled light point, its
+ * solid-angle pdf, the RNG state after;  op 1 = pdf (PathTracer.cpp:14-24) of direction dirs[i]: the light object is
+ * probed along it without culling, 0 when it is missed.  seeds is read by op 0 only, dirs by op 1 only; out_dir and
+ * out_state are written by op 0 only (may be NULL for op 1). */
+enum { TPT_LIGHT_SAMPLE = 0, TPT_LIGHT_PDF = 1 };
+int tpt_light_sampler_batch(TptScene* scene, int32_t light_object, int32_t op, const float* x, const float* dirs,
+                            const uint32_t* seeds, size_t n, float* out_dir, float* out_pdf, uint32_t* out_state);
+
 /* A BDPT subpath vertex as the integrators store it (BDPT.hpp:16-21). */
 typedef struct TptPathVertex {
     TptVec3 x, N;

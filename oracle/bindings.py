@@ -177,6 +177,21 @@ class Checker:
                                           _p(wi), _p(pdf), _p(st))
         return wi, pdf, st
 
+    def light_sample(self, light_object, x, seeds):
+        x = _f3(x)
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        d = np.empty_like(x); pdf = np.empty(len(x), np.float32); st = np.empty(len(x), np.uint32)
+        self._fn("light_sampler_batch")(self.h, C.c_int(light_object), C.c_int(0), _p(x), None, _p(seeds), C.c_size_t(len(x)),
+                                        _p(d), _p(pdf), _p(st))
+        return d, pdf, st
+
+    def light_pdf(self, light_object, x, dirs):
+        x, dirs = _f3(x), _f3(dirs)
+        pdf = np.empty(len(x), np.float32)
+        self._fn("light_sampler_batch")(self.h, C.c_int(light_object), C.c_int(1), _p(x), _p(dirs), None, C.c_size_t(len(x)),
+                                        None, _p(pdf), None)
+        return pdf
+
     def helpers(self, a, b, ior):
         a = np.asarray(a, np.float32); b = np.asarray(b, np.float32)
         r = [np.empty(3, np.float32) for _ in range(3)]

@@ -1046,6 +1046,21 @@ void orc_material_sample_batch(OrcScene* o, int mat, const float* wo, const floa
         if (out_state) out_state[i] = r.s;
     }
 }
+// DirectLightSampler::sample (op 0) / ::pdf (op 1), PathTracer.cpp:14-40
+void orc_light_sampler_batch(OrcScene* o, int light, int op, const float* x, const float* dirs, const uint32_t* seeds, size_t n,
+                             float* out_dir, float* out_pdf, uint32_t* out_state) {
+    for (size_t i = 0; i < n; ++i) {
+        if (op == 0) {
+            Rng r{seeds[i]};
+            float pdf = 0;
+            S3(out_dir, i, LightSampleDir(o->sc, light, r, L3(x, i), &pdf));
+            out_pdf[i] = pdf;
+            if (out_state) out_state[i] = r.s;
+        } else {
+            out_pdf[i] = LightPdf(o->sc, light, L3(x, i), L3(dirs, i));
+        }
+    }
+}
 void orc_helpers(const float* a, const float* b, float ior, float* reflect, float* refract, float* perp) {
     S3(reflect, 0, Reflect(L3(a, 0), L3(b, 0)));
     S3(refract, 0, Refract(L3(a, 0), L3(b, 0), ior));

@@ -379,6 +379,26 @@ void th_material(const HostScene* s, int op, int mat, const float* a, const floa
 
 }  // extern "C"
 
+static Ctx MakeCtx(const SceneView& sc, bool prune);
+extern "C" {
+// DirectLightSampler::sample (op 0) / ::pdf (op 1) as k_light_sampler (tpt.cu) calls them
+void th_light_sampler(const HostScene* s, int light, int op, const float* x, const float* dirs, const uint32_t* seeds, size_t n,
+                      float* out_dir, float* out_pdf, uint32_t* out_state) {
+    Ctx c = MakeCtx(s->view, true);
+    for (size_t i = 0; i < n; ++i) {
+        if (op == 0) {
+            uint32_t st = seeds[i];
+            float pdf;
+            St3(out_dir, i, light_sample_dir(c, light, st, Ld3(x, i), &pdf));
+            out_pdf[i] = pdf;
+            if (out_state) out_state[i] = st;
+        } else {
+            out_pdf[i] = light_pdf<false>(c, light, Ld3(x, i), Ld3(dirs, i));
+        }
+    }
+}
+}  // extern "C"
+
 static Ctx MakeCtx(const SceneView& sc, bool prune) {
     Ctx c;
     c.sc = sc; c.prune = prune;

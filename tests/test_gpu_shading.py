@@ -54,3 +54,15 @@ def test_coincident_vertices_do_not_poison_the_pixel(tpt):
     cam, cc, light, lc, _ = s.subpaths([pixel], [3384471102])          # the stream state at that sample
     assert cc[0] == 5 and np.isfinite(cam[0]["pdf"][:5]).all() and np.isfinite(light[0]["pdf"][:lc[0]]).all()
     s.close()
+
+
+@pytest.mark.parametrize("scene", ["standard", "twolights"])
+def test_direct_light_sampler_matches_the_reference_functions(tpt, scene):
+    """SURVEY 8(a) row a15 at function level: DirectLightSampler::sample / ::pdf through tpt_light_sampler_batch against
+    the pinned restatement, for the quad light and (twolights) the emissive Sphere (Sphere::Sample, Sphere.cpp:48-55)."""
+    from conftest import gpu_scene, oracle_for
+    from shading_checks import check_light_sampler
+    orc, d = oracle_for(scene, 64, 64)
+    s = gpu_scene(scene, 64, 64)
+    check_light_sampler(s, orc, d)
+    s.close()

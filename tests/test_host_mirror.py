@@ -143,6 +143,20 @@ class Mirror:
     def mat_sample(self, mat, wo, nrm, seeds):
         return self._mat(3, mat, wo, nrm, seeds=seeds)
 
+    def light_sample(self, light_object, x, seeds):
+        x = np.ascontiguousarray(x, np.float32); seeds = np.ascontiguousarray(seeds, np.uint32)
+        d = np.empty_like(x); pdf = np.empty(len(x), np.float32); st = np.empty(len(x), np.uint32)
+        self.lib.th_light_sampler.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 3 + [C.c_size_t] + [C.c_void_p] * 3
+        self.lib.th_light_sampler(self.h, light_object, 0, x.ctypes.data, None, seeds.ctypes.data, len(x), d.ctypes.data, pdf.ctypes.data, st.ctypes.data)
+        return d, pdf, st
+
+    def light_pdf(self, light_object, x, dirs):
+        x = np.ascontiguousarray(x, np.float32); dirs = np.ascontiguousarray(dirs, np.float32)
+        pdf = np.empty(len(x), np.float32)
+        self.lib.th_light_sampler.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 3 + [C.c_size_t] + [C.c_void_p] * 3
+        self.lib.th_light_sampler(self.h, light_object, 1, x.ctypes.data, dirs.ctypes.data, None, len(x), None, pdf.ctypes.data, None)
+        return pdf
+
     def pathweights(self, cam, cam_count, light, light_count):
         import tpt_b200 as T
         cam = np.ascontiguousarray(cam, dtype=T.PATHVERTEX_DTYPE).reshape(-1, 16)
@@ -354,6 +368,18 @@ from shading_checks import (GLOSSY, RENDER_SCENES, ROUGH, check_glossy_material,
 def test_rough_materials_match_to_ulps(mirror, tag, scene, mat):
     m = Mirror(mirror, scene)
     check_rough_material(m, tag, mat)
+    m.close()
+
+
+@pytest.mark.parametrize("scene", ["standard", "twolights"])
+def test_direct_light_sampler_matches_the_reference_functions(mirror, scene):
+    """DirectLightSampler::sample / ::pdf (PathTracer.cpp:6-40) of the kernels' source against the pinned restatement, for
+    the quad light and the emissive Sphere — the assertions of the GPU test (tests/shading_checks.py)."""
+    from conftest import oracle_for
+    from shading_checks import check_light_sampler
+    orc, d = oracle_for(scene, 64, 64)
+    m = Mirror(mirror, scene, 64, 64)
+    check_light_sampler(m, orc, d, n=4000)
     m.close()
 
 

@@ -252,6 +252,23 @@ class Scene:
                                                _p(wi), _p(pdf), _p(st)))
         return wi, pdf, st
 
+    def light_sample(self, light_object, x, seeds):
+        """tpt_light_sampler_batch, op sample: (directions, pdfs, RNG states after)"""
+        x = _f3(x)
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        d = np.empty_like(x); pdf = np.empty(len(x), np.float32); st = np.empty(len(x), np.uint32)
+        _check(lib().tpt_light_sampler_batch(self.h, C.c_int32(light_object), C.c_int32(0), _p(x), None, _p(seeds), C.c_size_t(len(x)),
+                                             _p(d), _p(pdf), _p(st)))
+        return d, pdf, st
+
+    def light_pdf(self, light_object, x, dirs):
+        """tpt_light_sampler_batch, op pdf"""
+        x, dirs = _f3(x), _f3(dirs)
+        pdf = np.empty(len(x), np.float32)
+        _check(lib().tpt_light_sampler_batch(self.h, C.c_int32(light_object), C.c_int32(1), _p(x), _p(dirs), None, C.c_size_t(len(x)),
+                                             None, _p(pdf), None))
+        return pdf
+
     def pathweights(self, cam, cam_count, light, light_count):
         cam = np.ascontiguousarray(cam, dtype=PATHVERTEX_DTYPE).reshape(-1, 16)
         light = np.ascontiguousarray(light, dtype=PATHVERTEX_DTYPE).reshape(-1, 16)

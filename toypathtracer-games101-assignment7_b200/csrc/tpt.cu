@@ -459,6 +459,48 @@ extern "C" int tpt_rng_batch(uint32_t seed, size_t n, uint32_t* states, float* f
     return TPT_OK;
 }
 
+// DirectLightSampler::sample / ::pdf (PathTracer.cpp:14-40) as the PathTrace kernels call them
+__global__ void __launch_bounds__(256) k_light_sampler(SceneView g, int light, int op, const float* x, const float* dirs,
+                                                       const uint32_t* seeds, size_t n, float* out_dir, float* out_pdf, uint32_t* out_state) {
+    Ctx c = make_ctx(stage_scene(g, tpt_smem), true);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        if (op == TPT_LIGHT_SAMPLE) {
+            uint32_t s = seeds[i];
+            float pdf;
+            st3(out_dir, i, light_sample_dir(c, light, s, ld3(x, i), &pdf));
+            out_pdf[i] = pdf;
+            if (out_state) out_state[i] = s;
+        } else {
+            out_pdf[i] = light_pdf<false>(c, light, ld3(x, i), ld3(dirs, i));
+        }
+    }
+}
+extern "C" int tpt_light_sampler_batch(TptScene* s, int32_t light, int32_t op, const float* x, const float* dirs, const uint32_t* seeds,
+                                       size_t n, float* out_dir, float* out_pdf, uint32_t* out_state) {
+    if (!s) { tpt_set_error("null scene"); return TPT_ERR_INVALID; }
+    if (light < 0 || light >= s->view.n_objs) { tpt_set_error("light object index out of range"); return TPT_ERR_INVALID; }
+    if (op != TPT_LIGHT_SAMPLE && op != TPT_LIGHT_PDF) { tpt_set_error("tpt_light_sampler_batch: unknown op"); return TPT_ERR_INVALID; }
+    if (n > 0 && (!x || !out_pdf || (op == TPT_LIGHT_SAMPLE ? (!seeds || !out_dir) : !dirs))) { tpt_set_error("tpt_light_sampler_batch: null array"); return TPT_ERR_INVALID; }
+    TPT_CUDA(cudaSetDevice(s->device));
+    if (n == 0) return TPT_OK;
+    DevBuf dx, dd, dsd, dod, dop, dos;
+    int rc;
+    if ((rc = dx.from_host(x, n * 12))) return rc;
+    if (op == TPT_LIGHT_PDF && (rc = dd.from_host(dirs, n * 12))) return rc;
+    if (op == TPT_LIGHT_SAMPLE && (rc = dsd.from_host(seeds, n * 4))) return rc;
+    if ((rc = dod.alloc(n * 12)) || (rc = dop.alloc(n * 4)) || (rc = dos.alloc(n * 4))) return rc;
+    k_light_sampler<<<launch_grid(s, n), 256, s->view.stage_bytes>>>(s->view, light, op, dx.as<float>(), dd.as<float>(), dsd.as<uint32_t>(), n,
+                                                                  dod.as<float>(), dop.as<float>(), dos.as<uint32_t>());
+    TPT_CUDA(cudaGetLastError());
+    TPT_CUDA(cudaDeviceSynchronize());
+    TPT_CUDA(cudaMemcpy(out_pdf, dop.p, n * 4, cudaMemcpyDeviceToHost));
+    if (op == TPT_LIGHT_SAMPLE) {
+        TPT_CUDA(cudaMemcpy(out_dir, dod.p, n * 12, cudaMemcpyDeviceToHost));
+        if (out_state) TPT_CUDA(cudaMemcpy(out_state, dos.p, n * 4, cudaMemcpyDeviceToHost));
+    }
+    return TPT_OK;
+}
+
 enum { MATOP_EVAL = 0, MATOP_PDF = 1, MATOP_FRESNEL = 2, MATOP_SAMPLE = 3 };
 __global__ void __launch_bounds__(256) k_material(SceneView g, int op, int mat, const float* a, const float* b,
                                                   const float* c3, const uint32_t* seeds, int combine, size_t n,
