@@ -316,6 +316,11 @@ int tpt_render_multi(const TptSceneDesc* desc, const TptRenderParams* params, in
 
 /* ---- per-function entry points (parity tests against the oracle) --------- */
 
+/* PixelPosToRay (SceneRenderingHelper.cpp:16-22, with CalculateScale :12-14 and the integer aspect of :17) for n pixel
+ * indices of this scene's frame (index = y * width + x): the normalised camera ray directions, as the render kernels
+ * form them. */
+int tpt_pixel_rays_batch(TptScene* scene, const int32_t* pixels, size_t n, float* out_dir);
+
 /* XorShift32 / GetRandomFloat (global.cpp:5-22): n draws from ResetRandom(seed). */
 int tpt_rng_batch(uint32_t seed, size_t n, uint32_t* states, float* floats);
 

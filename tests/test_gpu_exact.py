@@ -62,6 +62,8 @@ def test_all_primary_rays_784(tpt):
     dirs = (v / nrm[:, None]).astype(np.float32)
     for p in (0, 392 * 784 + 392, 614655, 12345):
         assert (bits32(dirs[p]) == bits32(orc.pixel_ray(int(p % w), int(p // w), w, h, scale))).all()
+    # ... and the DEVICE's PixelPosToRay (tpt_pixel_rays_batch: what k_generate forms), every pixel, bit for bit
+    assert (bits32(s.pixel_rays(idx)) == bits32(dirs)).all()
     org = np.tile(np.array([278, 278, -800], np.float32), (w * h, 1))
     cull = np.zeros(w * h, np.uint8)
     prim, t, coords, normal = s.intersect(org, dirs, cull)

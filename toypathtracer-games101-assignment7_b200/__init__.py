@@ -252,6 +252,13 @@ class Scene:
                                                _p(wi), _p(pdf), _p(st)))
         return wi, pdf, st
 
+    def pixel_rays(self, pixels):
+        """tpt_pixel_rays_batch: camera ray directions of the given pixel indices"""
+        pixels = np.ascontiguousarray(pixels, dtype=np.int32)
+        d = np.empty((len(pixels), 3), np.float32)
+        _check(lib().tpt_pixel_rays_batch(self.h, _p(pixels), C.c_size_t(len(pixels)), _p(d)))
+        return d
+
     def light_sample(self, light_object, x, seeds):
         """tpt_light_sampler_batch, op sample: (directions, pdfs, RNG states after)"""
         x = _f3(x)

@@ -459,6 +459,28 @@ extern "C" int tpt_rng_batch(uint32_t seed, size_t n, uint32_t* states, float* f
     return TPT_OK;
 }
 
+// PixelPosToRay as k_generate / k_pt_generate / k_render_mega call it
+__global__ void __launch_bounds__(256) k_pixel_rays(SceneView g, const int32_t* pixels, size_t n, float* out_dir) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        st3(out_dir, i, pixel_ray(g, pixels[i] % g.width, pixels[i] / g.width));
+}
+extern "C" int tpt_pixel_rays_batch(TptScene* s, const int32_t* pixels, size_t n, float* out_dir) {
+    if (!s) { tpt_set_error("null scene"); return TPT_ERR_INVALID; }
+    if (n > 0 && (!pixels || !out_dir)) { tpt_set_error("tpt_pixel_rays_batch: null array"); return TPT_ERR_INVALID; }
+    for (size_t i = 0; i < n; ++i)
+        if (pixels[i] < 0 || pixels[i] >= s->view.width * s->view.height) { tpt_set_error("tpt_pixel_rays_batch: pixel outside the frame"); return TPT_ERR_INVALID; }
+    TPT_CUDA(cudaSetDevice(s->device));
+    if (n == 0) return TPT_OK;
+    DevBuf dp, dd;
+    int rc;
+    if ((rc = dp.from_host(pixels, n * 4)) || (rc = dd.alloc(n * 12))) return rc;
+    k_pixel_rays<<<launch_grid(s, n), 256>>>(s->view, dp.as<int32_t>(), n, dd.as<float>());
+    TPT_CUDA(cudaGetLastError());
+    TPT_CUDA(cudaDeviceSynchronize());
+    TPT_CUDA(cudaMemcpy(out_dir, dd.p, n * 12, cudaMemcpyDeviceToHost));
+    return TPT_OK;
+}
+
 // DirectLightSampler::sample / ::pdf (PathTracer.cpp:14-40) as the PathTrace kernels call them
 __global__ void __launch_bounds__(256) k_light_sampler(SceneView g, int light, int op, const float* x, const float* dirs,
                                                        const uint32_t* seeds, size_t n, float* out_dir, float* out_pdf, uint32_t* out_state) {
