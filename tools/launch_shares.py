@@ -13,7 +13,7 @@ agg = collections.defaultdict(lambda: [0, 0.0])
 for r in rows[1:]:
     if r[iM] != "gpu__time_duration.sum":
         continue
-    name = r[iK].split("(")[0].replace("<unnamed>::", "")
+    name = r[iK].split("(")[0].replace("<unnamed>::", "").replace("void ", "").split("<")[0]    # k_path<1> (a template instance) -> k_path
     agg[name][0] += 1
     agg[name][1] += float(r[iV].replace(",", "")) * scale.get(r[iU], 1.0)
 total = sum(v[1] for v in agg.values())

@@ -28,7 +28,7 @@ ids = collections.defaultdict(set)
 for r in rows[1:]:
     if r[iM] not in field:
         continue
-    name = r[iK].split("(")[0].replace("<unnamed>::", "")
+    name = r[iK].split("(")[0].replace("<unnamed>::", "").replace("void ", "").split("<")[0]    # k_path<1> (a template instance) -> k_path
     key, w = field[r[iM]]
     agg[name][key] += w * float(r[iV].replace(",", "")) * scale.get(r[iU], 1)
     ids[name].add(r[iI])

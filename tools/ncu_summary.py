@@ -32,4 +32,4 @@ w = csv.writer(out)
 w.writerow(keys)
 w.writerow([units[hdr.index(k)] for k in keys])
 for r in data:
-    w.writerow([r[hdr.index(k)].split("(")[0].replace("<unnamed>::", "") if k == "Kernel Name" else r[hdr.index(k)] for k in keys])
+    w.writerow([r[hdr.index(k)].split("(")[0].replace("<unnamed>::", "").replace("void ", "") if k == "Kernel Name" else r[hdr.index(k)] for k in keys])

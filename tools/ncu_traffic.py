@@ -15,7 +15,7 @@ agg = collections.defaultdict(lambda: [0.0, set()])
 for r in rows[1:]:
     if "dram__bytes" not in r[iM]:
         continue
-    name = r[iK].split("(")[0].replace("<unnamed>::", "")
+    name = r[iK].split("(")[0].replace("<unnamed>::", "").replace("void ", "").split("<")[0]    # k_path<1> (a template instance) -> k_path
     a = agg[name]
     a[0] += float(r[iV].replace(",", "")) * scale.get(r[iU], 1)
     a[1].add(r[0])
