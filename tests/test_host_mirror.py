@@ -578,3 +578,31 @@ def test_rank_shares_add_up_to_the_frame(wfmirror, partition, world):
             assert (total.view(np.uint32) == full.view(np.uint32)).all()
         else:
             assert np.allclose(total, full, rtol=2e-4, atol=2e-5)
+
+
+def test_wavefront_pipelines_under_address_sanitizer(tmp_path_factory):
+    """compute-sanitizer is closed on the GPU pool, so the bounds check of the wavefront kernels is this: the block
+    emulator build (kernels and host loops of csrc/wavefront.cu / pt_wavefront.cu as plain C++) compiled with
+    -fsanitize=address, every "device" buffer a calloc of its own, small frames of every pipeline and scene kind in a
+    child process with libasan preloaded.  An out-of-bounds queue, path-store or scene access aborts the child."""
+    import sys
+    gxx = shutil.which("g++")
+    cuda_inc = "/usr/local/cuda/include"
+    if not gxx or not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("g++ / CUDA headers not available")
+    asan = subprocess.run([gxx, "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("libasan not available")
+    so = str(tmp_path_factory.mktemp("asan") / "libwavefront_host_asan.so")
+    r = subprocess.run([gxx, "-std=c++17", "-O1", "-g", "-x", "c++", "-fPIC", "-ffp-contract=off", "-shared", "-w",
+                        "-fsanitize=address", "-fno-omit-frame-pointer",
+                        "-I", cuda_inc, "-I", os.path.join(ROOT, "include"), "-I", os.path.join(PKG, "csrc"),
+                        "-I", os.path.join(ROOT, "tests", "native"), os.path.join(ROOT, "tests", "native", "wavefront_host.cu"),
+                        "-o", so, "-Wl,-Bsymbolic", "-L/usr/local/cuda/lib64", "-lcudart_static", "-ldl", "-lrt", "-lpthread"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0:abort_on_error=0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "native", "asan_render.py"), so], env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "ASAN RUN DONE" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
+    assert "ERROR: AddressSanitizer" not in r.stderr
