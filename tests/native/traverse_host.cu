@@ -98,9 +98,25 @@ static void run_block(int nlanes, unsigned block_idx, unsigned grid_dim, const s
         w.ctx[l].uc_link = &w.sched;
         makecontext(&w.ctx[l], block_entry, 0);
     }
+    // The order in which the runnable threads get their turn between collectives is the emulator's choice, as it is the
+    // hardware's: TPT_EMU_ORDER=0 ascending, 1 descending, 2 a fresh pseudo-random permutation every sweep.  Code that
+    // hands data from one thread to another through shared or global memory without the __syncwarp / __syncthreads it
+    // needs gives different results under different orders (tests/test_host_mirror.py runs the pipelines under all three).
+    const char* env_order = getenv("TPT_EMU_ORDER");
+    const int order = env_order ? atoi(env_order) : 0;
+    static unsigned order_state = 0x9E3779B9u;
+    int ord[BlockEmu::MAX_LANES];
     for (;;) {
         int live = 0, at_barrier = 0;
-        for (int l = 0; l < nlanes; ++l) {
+        for (int k = 0; k < nlanes; ++k) ord[k] = order == 1 ? nlanes - 1 - k : k;
+        if (order == 2)
+            for (int k = nlanes - 1; k > 0; --k) {
+                order_state ^= order_state << 13; order_state ^= order_state >> 17; order_state ^= order_state << 5;
+                const int j = (int)(order_state % (unsigned)(k + 1));
+                const int t = ord[k]; ord[k] = ord[j]; ord[j] = t;
+            }
+        for (int k = 0; k < nlanes; ++k) {
+            const int l = ord[k];
             if (!w.finished[l] && !w.parked[l]) {
                 w.lane = l;
                 swapcontext(&w.sched, &w.ctx[l]);          // until its next collective or its end

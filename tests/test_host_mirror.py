@@ -606,3 +606,19 @@ def test_wavefront_pipelines_under_address_sanitizer(tmp_path_factory):
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "ASAN RUN DONE" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
     assert "ERROR: AddressSanitizer" not in r.stderr
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_wavefront_pipelines_do_not_depend_on_the_thread_schedule(wfmirror, order, monkeypatch):
+    """The race check the GPU pool does not offer (no compute-sanitizer --tool racecheck): between two collectives the
+    emulator may run the threads of a block in any order — ascending by default, here descending and freshly shuffled at
+    every sweep.  A hand-over through shared or global memory that lacks its __syncwarp / __syncthreads (the pooled
+    primitive tests of closest_hit_warp, the per-block done regions of k_path, the queue appends) shows as a different
+    frame.  PathTrace: bit for bit the per-pixel loop's; BDPT: within the float addition order, as under the default order."""
+    monkeypatch.setenv("TPT_EMU_ORDER", str(order))
+    for scene, mode, spp in (("standard", "pt_full", 3), ("bunny", "pt_full", 2), ("twolights", "pt_full", 2)):
+        img, ref = wavefront_vs_pixel_loop(wfmirror, scene, mode, spp, 32)
+        assert (img.view(np.uint32) == ref.view(np.uint32)).all(), (scene, order)
+    for scene, spp, sms in (("standard", 3, 1), ("refractive", 2, 2), ("bunny", 2, 1)):
+        img, ref = wavefront_vs_pixel_loop(wfmirror, scene, "bdpt", spp, 32, sms)
+        assert np.allclose(img, ref, rtol=2e-4, atol=2e-5), (scene, order, float(np.abs(img - ref).max()))
