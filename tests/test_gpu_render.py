@@ -249,3 +249,15 @@ def test_baseline_config5_4k_occlusion_tiles(tpt):
     assert np.percentile(err, 99.9) < 1e-3
     s.close()
     tpt.release_cached_memory()          # ~25 GB of 4K work buffers go back to the driver
+
+
+def test_soak_create_render_destroy(tpt):
+    """tools/soak.py, shortened: scenes of every kind created, rendered at changing sizes and destroyed 60 times in one
+    process.  Frames of one kind are reproduced (PathTrace bit for bit, BDPT within the addition order of the splats) and
+    the device memory in use returns to where it started once the work-buffer cache is released (no leak per scene)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "soak.py"), "12"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "soak ok" in r.stdout, (r.stdout[-1500:], r.stderr[-1500:])
