@@ -349,6 +349,31 @@ void th_shadow_budgeted(const HostScene* s, const float* from, const float* to, 
     }
 }
 
+// The walk over the wide tree (wide_closest_hit): plain rays over wnodes, the others (and a stack overflow)
+// over nodes[].  `taken` (optional): rays that took the wide walk.  th_intersect_wide with budget > 0 does what
+// k_pt_extend_budget + k_pt_extend_long do: `budget` steps of the threaded walk, then the wide tree from its root, seeded
+// with the best hit found so far and its visit rank.
+int th_scene_wnodes(const HostScene* s) { return s->view.n_wnodes; }
+void th_intersect_wide(const HostScene* s, const float* org, const float* dir, const uint8_t* cull, size_t n, int budget,
+                       int32_t* prim, double* t, float* coords, float* normal, unsigned* taken) {
+    const SceneView& sc = s->view;
+    unsigned nw = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const DRay r = make_ray(Ld3(org, i), Ld3(dir, i));
+        WalkCursor c = walk_begin(0);
+        const bool done = budget > 0 && walk_resume(sc, r, cull[i], sc.n_nodes, true, budget, c);
+        if (done) {}
+        else if (ray_is_plain(r) && wide_closest_hit(sc, r, cull[i], c.best, c.best_t, c.best >= 0 ? sc.prim_leaf[c.best] : 0x7fffffff)) ++nw;
+        else walk_resume(sc, r, cull[i], sc.n_nodes, true, 0x7fffffff, c);
+        DHit h;
+        finish_hit(sc, r, c.best, c.best_t, &h);
+        prim[i] = h.prim;
+        t[i] = h.prim >= 0 ? h.t : 0.0;
+        St3(coords, i, h.coords);
+        St3(normal, i, h.normal);
+    }
+    if (taken) *taken = nw;
+}
 // variant 0: shadow_check in the reference's closest-hit form; 1: as an any-hit query; 2: shadow_check_deferred
 void th_shadow(const HostScene* s, const float* from, const float* to, const uint8_t* cull, size_t n, int variant,
                uint8_t* out) {

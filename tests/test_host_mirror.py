@@ -62,6 +62,8 @@ def build_mirror(tmp_path_factory, defines=()):
     lib.th_intersect_warp.argtypes = [C.c_void_p] * 4 + [C.c_size_t] + [C.c_void_p] * 4
     lib.th_intersect_budgeted.argtypes = [C.c_void_p] * 4 + [C.c_size_t, C.c_int, C.c_int] + [C.c_void_p] * 5
     lib.th_shadow_budgeted.argtypes = [C.c_void_p] * 4 + [C.c_size_t, C.c_int, C.c_void_p]
+    lib.th_scene_wnodes.argtypes = [C.c_void_p]
+    lib.th_intersect_wide.argtypes = [C.c_void_p] * 4 + [C.c_size_t, C.c_int] + [C.c_void_p] * 5
     lib.th_render_counted.restype = C.c_uint64
     lib.th_render_counted.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     return lib
@@ -239,6 +241,36 @@ def test_pruning_only_removes_work_and_counts_follow_the_reference(mirror, scene
     assert int(full[1]) == st["prim_tests"]
     assert int(full[0]) == st["node_visits"] - mesh_entries
     assert pruned[0] <= full[0] and pruned[1] <= full[1] and pruned[0] < full[0]
+    m.close()
+
+
+@pytest.mark.parametrize("budget", [0, 3, 24])
+def test_wide_tree_walk_is_the_walk(mirror, budget):
+    """wide_closest_hit (traverse.cuh) over the four-children tree of the Cornell + bunny scene — nearest child first, leaf
+    or inner node, pruned by the best hit, ties by the reference's visit rank: every golden batch (primary, secondary,
+    random, adversarial) comes back as the reference has it, bit for bit.  Small scenes take the flat leaf list and have
+    no such tree.  With a budget the walk starts as the threaded walk over nodes[] and is finished in the wide tree, seeded
+    with the best hit so far and its visit rank (k_pt_extend_budget + k_pt_extend_long)."""
+    m = Mirror(mirror, "standard")
+    assert mirror.th_scene_wnodes(m.h) == 0
+    m.close()
+    m = Mirror(mirror, "bunny")
+    nw = mirror.th_scene_wnodes(m.h)
+    assert 0.2 * mirror.th_scene_nodes(m.h) < nw < 0.5 * mirror.th_scene_nodes(m.h)      # ~ (leaves - 1) / 3 inner nodes
+    g = golden("rays_bunny.npz")
+    for tag in ("P", "S", "R", "A"):
+        org, dirs = np.ascontiguousarray(g[tag + "_org"]), np.ascontiguousarray(g[tag + "_dir"])
+        cull = np.ascontiguousarray(g[tag + "_cull"])
+        n = len(cull)
+        prim, t = np.empty(n, np.int32), np.empty(n, np.float64)
+        coords, normal = np.empty((n, 3), np.float32), np.empty((n, 3), np.float32)
+        taken = C.c_uint(0)
+        mirror.th_intersect_wide(m.h, org.ctypes.data, dirs.ctypes.data, cull.ctypes.data, n, budget,
+                                 prim.ctypes.data, t.ctypes.data, coords.ctypes.data, normal.ctypes.data, C.byref(taken))
+        assert (prim == g[tag + "_prim"]).all(), (tag, int((prim != g[tag + "_prim"]).sum()))
+        assert (t.view(np.uint64) == g[tag + "_t"].view(np.uint64)).all()
+        assert (bits32(coords) == bits32(g[tag + "_coords"])).all() and (bits32(normal) == bits32(g[tag + "_normal"])).all()
+        assert taken.value > (0.9 if budget == 0 else 0.05 if budget == 24 else 0.5) * n or tag == "A"          # the wide walk is what ran (budget 24: for the long walks)
     m.close()
 
 

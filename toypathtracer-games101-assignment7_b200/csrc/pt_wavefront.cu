@@ -322,14 +322,19 @@ __global__ void __launch_bounds__(256) k_pt_extend_budget(SceneView g, PtBuffers
             }
         }
         const unsigned at = wf_append(&b.ctr->n_long_ext, !done);
-        if (!done) { b.long_ext[at] = make_uint4((unsigned)slot, (unsigned)c.i, (unsigned)c.best, 0u); b.long_ext_t[at] = c.best_t; }
+        if (!done) { b.long_ext[at] = make_uint4((unsigned)slot, (unsigned)c.i, (unsigned)c.best, c.best >= 0 && sc.n_wnodes > 0 ? (unsigned)sc.prim_leaf[c.best] : 0x7fffffffu); b.long_ext_t[at] = c.best_t; }
     }
     flush_stats(0, rays, 0, stats);
 }
 
 // The walks k_pt_extend_budget parked, to their end.
 // (64 registers, 4 blocks per SM; compiled for 6 or 8 blocks they spill and the frame takes 55 / 56.5 ms instead of 51.5)
-__global__ void __launch_bounds__(256) k_pt_extend_long(SceneView g, PtBuffers b) {
+// With the scene's wide tree (`wide`; traverse.cuh: wide_closest_hit) a plain ray's walk is finished THERE, from the root,
+// seeded with the best hit of the steps already taken and that leaf's visit rank (k_pt_extend_budget parks it): a fifth of
+// the dependent fetches of the threaded walk and, nearest child first, fewer primitive tests — what these few, long,
+// latency-bound walks consist of.  (Shadow queries are any-hit: every leaf in reach is tested whatever the order, and
+// k_pt_shadow_long over the wide tree measured 3 % slower than over nodes[].)
+__global__ void __launch_bounds__(256) k_pt_extend_long(SceneView g, PtBuffers b, int wide) {
     pdl_launch_dependents();
     const SceneView sc = stage_scene(g, tpt_smem);
     pdl_wait();
@@ -341,7 +346,8 @@ __global__ void __launch_bounds__(256) k_pt_extend_long(SceneView g, PtBuffers b
         const DRay r = make_ray(mk3(o), mk3(d));
         WalkCursor c;
         c.i = (int)e.y; c.best = (int)e.z; c.best_t = b.long_ext_t[q];
-        walk_resume(sc, r, __float_as_int(o.w), sc.n_nodes, true, 0x7fffffff, c);
+        if (!(wide && ray_is_plain(r) && wide_closest_hit(sc, r, __float_as_int(o.w), c.best, c.best_t, (int)e.w)))
+            walk_resume(sc, r, __float_as_int(o.w), sc.n_nodes, true, 0x7fffffff, c);
         DHit h;
         finish_hit(sc, r, c.best, c.best_t, &h);
         b.hit[slot] = make_float4(h.coords.x, h.coords.y, h.coords.z, __int_as_float(h.prim));
@@ -541,6 +547,8 @@ int pt_wavefront_render(TptScene* s, const RenderArgs& a0, float* d_radiance, cu
         tm->begin(TPT_K_GENERATE); launch_pdl(k_pt_generate, grid[p], tsmem, ms[p], s->view, args[p], w.b, s->d_stats); tm->end();
     }
     const bool large = s->view.n_leaves == 0;          // no flat leaf list: budgeted walks + the *_long kernels
+    const char* env_wide = getenv("TPT_WIDE");
+    const bool wide = large && s->view.n_wnodes > 0 && !(env_wide && atoi(env_wide) == 0);      // ... or the wide tree
     const long long max_iters = (long long)a0.spp * 4096 + 8;
     for (long long it = 0; it < max_iters; ++it) {
         for (int p = 0; p < npipes; ++p) {
@@ -551,7 +559,7 @@ int pt_wavefront_render(TptScene* s, const RenderArgs& a0, float* d_radiance, cu
             if (two) { TPT_CUDA(cudaEventRecord(w.ev_shade, ms[p])); TPT_CUDA(cudaStreamWaitEvent(ss[p], w.ev_shade, 0)); }
             if (large) {
                 tm->begin(TPT_K_EXTEND); launch_pdl(k_pt_extend_budget, grid[p], smem, ms[p], s->view, w.b, cur[p] ^ 1, s->d_stats); tm->end();
-                tm->begin(TPT_K_EXTEND); launch_pdl(k_pt_extend_long, grid[p], smem, ms[p], s->view, w.b); tm->end();
+                tm->begin(TPT_K_EXTEND); launch_pdl(k_pt_extend_long, grid[p], smem, ms[p], s->view, w.b, wide ? 1 : 0); tm->end();
             } else {
                 tm->begin(TPT_K_EXTEND); launch_pdl(k_pt_extend, grid[p], tsmem, ms[p], s->view, w.b, cur[p] ^ 1, s->d_stats); tm->end();
             }

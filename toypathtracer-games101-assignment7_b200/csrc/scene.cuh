@@ -69,6 +69,9 @@ struct SceneView {
     float aspect;             // (float)(width / height): integer division, SceneRenderingHelper.cpp:17
     float3 eye;
     float3 background;
+    const float4* wnodes;     // n_wnodes > 0 (large scenes): the hierarchy with four children per node, 8 words each, see scene_build.h
+    int n_wnodes;
+    const int* prim_leaf;     // (with wnodes) primitive -> its leaf's position in nodes[], the reference's visit rank
     const unsigned char* blob;   // the arrays above are sections of this one allocation, in this order
     unsigned blob_bytes;         // multiple of 16
     unsigned stage_bytes;        // = blob_bytes when the blob is staged in shared memory; 0 = too large
@@ -113,6 +116,8 @@ __device__ inline SceneView stage_scene(const SceneView& g, unsigned char* smem)
     s.emissive = reinterpret_cast<const int*>(move(g.emissive));
     s.leaves = reinterpret_cast<const float4*>(move(g.leaves));
     s.uboxes = reinterpret_cast<const float4*>(move(g.uboxes));
+    s.wnodes = reinterpret_cast<const float4*>(move(g.wnodes));
+    s.prim_leaf = reinterpret_cast<const int*>(move(g.prim_leaf));
     return s;
 }
 

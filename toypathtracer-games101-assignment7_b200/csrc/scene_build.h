@@ -5,6 +5,7 @@
 // traverse.cuh on the CPU against the oracle.  Host code only; included by exactly those two.
 #pragma once
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <string>
@@ -15,8 +16,9 @@
 struct SceneBlob {
     std::vector<unsigned char> bytes;      // the arrays in the order stage_scene expects, 16-byte granular
     size_t o_nodes = 0, o_tris = 0, o_tverts = 0, o_spheres = 0, o_mats = 0, o_objs = 0, o_lnodes = 0, o_emissive = 0,
-           o_leaves = 0, o_uboxes = 0;
+           o_leaves = 0, o_uboxes = 0, o_wnodes = 0, o_prim_leaf = 0;
     int n_nodes = 0, n_leaves = 0, n_uboxes = 0;
+    int n_wnodes = 0;                      // 0: no wide tree (small scene, or a box that does not contain its subtree)
 };
 
 namespace {
@@ -84,6 +86,83 @@ struct HostBuild {
         return true;
     }
 };
+
+// ---- wide tree (scene.cuh: wnodes) --------------------------------------------------------------------------
+// The hierarchy of nodes[] with up to four children per node and the children's boxes IN the node: every node of the
+// wide tree is a node of nodes[], its children are descendants of that node (a child that is an inner node with the
+// largest box is replaced by its own children while there is room), every box is the exact box of nodes[].  Leaves keep
+// their position in nodes[] as their visit rank.  false: some box does not contain the boxes of its subtree — the
+// argument that lets a walk take another route (traverse.cuh: wide_closest_hit) does not hold, nodes[] is walked.
+struct WideNode {
+    float lox[4], loy[4], loz[4], hix[4], hiy[4], hiz[4];
+    int ref[4];          // >= 0: wide node, WIDE_EMPTY: no child, else ~primitive (a leaf)
+    int rank[4];         // leaf: its index in nodes[] (the reference's visit order)
+};
+static_assert(sizeof(WideNode) == 128, "eight 128-bit words");
+enum { WIDE_EMPTY = (int)0x80000000 };
+inline bool build_wide_tree(const std::vector<float4>& nodes, std::vector<WideNode>* out) {
+    const int nn = (int)nodes.size() / 2;
+    if (nn <= 1) return false;
+    auto prim_of = [&](int i) { int p; std::memcpy(&p, &nodes[2 * i].w, 4); return p; };
+    auto miss_of = [&](int i) { int m; std::memcpy(&m, &nodes[2 * i + 1].w, 4); return m; };
+    for (int i = 0; i < nn; ++i) {          // finite, ordered boxes that contain their subtrees (what Union() builds; checked)
+        const int miss = miss_of(i);
+        if (miss <= i || miss > nn) return false;
+        const float4 lo = nodes[2 * i], hi = nodes[2 * i + 1];
+        if (!(std::isfinite(lo.x) && std::isfinite(lo.y) && std::isfinite(lo.z) && std::isfinite(hi.x) && std::isfinite(hi.y) &&
+              std::isfinite(hi.z) && lo.x <= hi.x && lo.y <= hi.y && lo.z <= hi.z)) return false;
+        if (prim_of(i) >= 0) { if (miss != i + 1) return false; continue; }
+        for (int c = i + 1; c < miss; c = miss_of(c)) {      // the direct children: containment is transitive
+            const float4 a = nodes[2 * c], b = nodes[2 * c + 1];
+            if (!(a.x >= lo.x && a.y >= lo.y && a.z >= lo.z && b.x <= hi.x && b.y <= hi.y && b.z <= hi.z)) return false;
+        }
+    }
+    if (prim_of(0) >= 0) return false;
+    auto area = [&](int i) {
+        const float4 lo = nodes[2 * i], hi = nodes[2 * i + 1];
+        const double dx = (double)hi.x - lo.x, dy = (double)hi.y - lo.y, dz = (double)hi.z - lo.z;
+        return dx * dy + dy * dz + dz * dx;
+    };
+    out->clear();
+    std::vector<int> todo{0}, slot_of{-1}, child_of{-1};      // nodes[] index to emit, and where its wide index goes
+    // breadth first: wide node k is made from todo[k]
+    for (size_t k = 0; k < todo.size(); ++k) {
+        const int i = todo[k];
+        std::vector<int> kids;
+        for (int c = i + 1; c < miss_of(i); c = miss_of(c)) kids.push_back(c);
+        for (;;) {                          // open the largest inner child while its children fit
+            int pick = -1;
+            double best = -1.0;
+            for (size_t j = 0; j < kids.size(); ++j)
+                if (prim_of(kids[j]) < 0 && area(kids[j]) > best) {
+                    int n = 0;
+                    for (int c = kids[j] + 1; c < miss_of(kids[j]); c = miss_of(c)) ++n;
+                    if ((int)kids.size() - 1 + n <= 4) { best = area(kids[j]); pick = (int)j; }
+                }
+            if (pick < 0) break;
+            const int open = kids[pick];
+            kids.erase(kids.begin() + pick);
+            for (int c = open + 1; c < miss_of(open); c = miss_of(c)) kids.push_back(c);
+        }
+        if (kids.empty() || kids.size() > 4) return false;
+        WideNode w;
+        for (int j = 0; j < 4; ++j) {
+            w.lox[j] = w.loy[j] = w.loz[j] = w.hix[j] = w.hiy[j] = w.hiz[j] = 0.0f;
+            w.ref[j] = WIDE_EMPTY; w.rank[j] = 0;
+        }
+        out->push_back(w);
+        if (slot_of[k] >= 0) (*out)[slot_of[k]].ref[child_of[k]] = (int)k;
+        for (size_t j = 0; j < kids.size(); ++j) {
+            const int c = kids[j];
+            WideNode& dst = (*out)[k];
+            dst.lox[j] = nodes[2 * c].x; dst.loy[j] = nodes[2 * c].y; dst.loz[j] = nodes[2 * c].z;
+            dst.hix[j] = nodes[2 * c + 1].x; dst.hiy[j] = nodes[2 * c + 1].y; dst.hiz[j] = nodes[2 * c + 1].z;
+            if (prim_of(c) >= 0) { dst.ref[j] = ~prim_of(c); dst.rank[j] = c; }
+            else { todo.push_back(c); slot_of.push_back((int)k); child_of.push_back((int)j); }
+        }
+    }
+    return true;
+}
 
 // Appends one array to the scene blob (16-byte granular) and returns its byte offset.
 template <class T> size_t blob_put(std::vector<unsigned char>& blob, const std::vector<T>& host) {
@@ -235,6 +314,20 @@ static int tpt_build_scene_blob(const TptSceneDesc* d, SceneBlob* out) {
     out->o_spheres = blob_put(blob, spheres); out->o_mats = blob_put(blob, mats); out->o_objs = blob_put(blob, hb.objs);
     out->o_lnodes = blob_put(blob, lnodes); out->o_emissive = blob_put(blob, emissive); out->o_leaves = blob_put(blob, leaves);
     out->o_uboxes = blob_put(blob, uboxes);
+    // large scenes (no flat leaf list): the wide tree, when the scene qualifies
+    std::vector<WideNode> wnodes;
+    if (!(leaves.empty() && build_wide_tree(hb.nodes, &wnodes))) wnodes.clear();
+    out->n_wnodes = (int)wnodes.size();
+    out->o_wnodes = blob_put(blob, wnodes);
+    std::vector<int> prim_leaf;
+    if (!wnodes.empty()) {
+        prim_leaf.assign((size_t)d->n_tris + d->n_spheres, 0x7fffffff);
+        for (int i = 0; i < (int)hb.nodes.size() / 2; ++i) {
+            int prim; std::memcpy(&prim, &hb.nodes[2 * i].w, 4);
+            if (prim >= 0 && prim < (int)prim_leaf.size()) prim_leaf[prim] = i;
+        }
+    }
+    out->o_prim_leaf = blob_put(blob, prim_leaf);
     out->n_nodes = (int)hb.nodes.size() / 2;
     out->n_leaves = (int)leaves.size() / 2;
     out->n_uboxes = (int)uboxes.size() / 2;
@@ -258,6 +351,9 @@ static void tpt_scene_view(const SceneBlob& b, const unsigned char* base, const 
     v->n_leaves = b.n_leaves;
     v->uboxes = reinterpret_cast<const float4*>(base + b.o_uboxes);
     v->n_uboxes = b.n_uboxes;
+    v->wnodes = reinterpret_cast<const float4*>(base + b.o_wnodes);
+    v->n_wnodes = b.n_wnodes;
+    v->prim_leaf = reinterpret_cast<const int*>(base + b.o_prim_leaf);
     v->n_nodes = b.n_nodes; v->n_tris = d->n_tris; v->n_spheres = d->n_spheres;
     v->n_mats = d->n_materials; v->n_objs = d->n_objects; v->n_lnodes = d->n_mesh_nodes; v->n_emissive = d->n_emissive;
     v->width = d->width; v->height = d->height;

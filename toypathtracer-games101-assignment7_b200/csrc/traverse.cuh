@@ -431,6 +431,85 @@ TPT_DEV bool shadow_resume(const SceneView& sc, const ShadowQuery& q, int cull, 
     return hit || i >= end;
 }
 
+// ---- wide tree (large scenes) ----------------------------------------------------------------------------------
+// For a plain ray (ray_is_plain) the slab test is monotone in the box, and every box of nodes[] contains the boxes of its
+// subtree (checked by build_wide_tree): the reference's walk tests a primitive iff its own LEAF box passes — the argument
+// of the flat leaf list, which does not depend on how the leaves are reached.  So the closest hit is
+//     min over { primitives whose leaf box passes and whose test succeeds } of (t, position of the leaf in nodes[])
+// — the strict first-visited-wins update of BVH.cpp:131 is a minimum by (t, visit rank) — and any hierarchy over the same
+// leaf boxes whose inner boxes contain their leaves may be walked, in any order, skipping what starts beyond the best hit
+// (same margin as closest_hit_range: nothing that could hold a hit at t <= best is skipped, ties included).  wnodes is
+// such a hierarchy: four children per node, their exact boxes in the node (one 128-byte fetch, four independent slab
+// tests), walked nearest child first with a short stack.  Half to a fifth of the dependent fetches of the threaded walk.
+// A ray that is not plain takes the walk over nodes[].
+#define TPT_WIDE_EMPTY ((int)0x80000000)
+#define TPT_WIDE_STACK 32
+TPT_DEV float4 wide_box(const float4& x, const float4& y, const float4& z, int k) {
+    return k == 0 ? make_float4(x.x, y.x, z.x, 0.f) : (k == 1 ? make_float4(x.y, y.y, z.y, 0.f) : (k == 2 ? make_float4(x.z, y.z, z.z, 0.f) : make_float4(x.w, y.w, z.w, 0.f)));
+}
+TPT_DEV int wide_pick(const float4& v, int k) { return __float_as_int(k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w))); }
+// (best_out, best_t_out, rank_in) on entry: a hit already known — the best of the leaves a threaded walk has visited, with
+// that leaf's position in nodes[] — or (-1, .., ..).  Leaves met again lose against it or are it.
+// false: the stack overflowed, nothing was written (the caller walks nodes[] instead).
+TPT_DEV bool wide_closest_hit(const SceneView& sc, const DRay& r, int cull, int& best_out, double& best_t_out, int rank_in) {
+    int s_ref[TPT_WIDE_STACK];
+    float s_nmin[TPT_WIDE_STACK];
+    int sp = 0, cur = 0, best = best_out, best_rank = rank_in;
+    double best_t = best_t_out;
+    float prune_t = best >= 0 ? (float)best_t * 1.0001f + 1e-3f : FLT_MAX;
+    for (;;) {
+        const float4* w = sc.wnodes + 8 * (size_t)cur;
+        const float4 lox = w[0], loy = w[1], loz = w[2], hix = w[3], hiy = w[4], hiz = w[5], refs = w[6], ranks = w[7];
+        float nm[4];
+        int ref[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            ref[k] = wide_pick(refs, k);
+            float e;
+            const bool in = ref[k] != TPT_WIDE_EMPTY && slab_test_plain(wide_box(lox, loy, loz, k), wide_box(hix, hiy, hiz, k), r, &e) && !(e > prune_t);
+            nm[k] = in ? e : INFINITY;
+        }
+        // leaves among the children: tested here, nearest first; a hit shortens the reach for what follows
+        for (;;) {
+            int k = -1;
+            float e = INFINITY;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (ref[j] < 0 && nm[j] < e) { e = nm[j]; k = j; }
+            if (k < 0 || e > prune_t) break;
+            const int rf = k == 0 ? ref[0] : (k == 1 ? ref[1] : (k == 2 ? ref[2] : ref[3]));
+            const int rank = wide_pick(ranks, k);
+            if (k == 0) nm[0] = INFINITY; else if (k == 1) nm[1] = INFINITY; else if (k == 2) nm[2] = INFINITY; else nm[3] = INFINITY;
+            int b = -1;
+            double t = 0.0;
+            settle_candidate(sc, r, cull, ~rf, b, t);
+            if (b >= 0 && (best < 0 || t < best_t || (t == best_t && rank < best_rank))) {      // minimum by (t, visit rank)
+                best = b; best_t = t; best_rank = rank;
+                prune_t = (float)best_t * 1.0001f + 1e-3f;
+            }
+        }
+        // inner children still in reach, nearest first: the nearest is the next node, the others wait on the stack
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (ref[k] < 0 || nm[k] > prune_t) nm[k] = INFINITY;
+#define TPT_WIDE_CSWAP(a, b) if (nm[b] < nm[a]) { const float tf = nm[a]; nm[a] = nm[b]; nm[b] = tf; const int ti = ref[a]; ref[a] = ref[b]; ref[b] = ti; }
+        TPT_WIDE_CSWAP(0, 1) TPT_WIDE_CSWAP(2, 3) TPT_WIDE_CSWAP(0, 2) TPT_WIDE_CSWAP(1, 3) TPT_WIDE_CSWAP(1, 2)
+#undef TPT_WIDE_CSWAP
+        if (sp + 3 > TPT_WIDE_STACK) return false;
+        if (nm[3] < INFINITY) { s_ref[sp] = ref[3]; s_nmin[sp] = nm[3]; ++sp; }
+        if (nm[2] < INFINITY) { s_ref[sp] = ref[2]; s_nmin[sp] = nm[2]; ++sp; }
+        if (nm[1] < INFINITY) { s_ref[sp] = ref[1]; s_nmin[sp] = nm[1]; ++sp; }
+        bool next = nm[0] < INFINITY;
+        cur = ref[0];
+        while (!next && sp > 0) {
+            --sp;
+            next = !(s_nmin[sp] > prune_t);
+            cur = s_ref[sp];
+        }
+        if (!next) break;
+    }
+    best_out = best; best_t_out = best_t;
+    return true;
+}
+
 // ---- warp-cooperative primitive tests -------------------------------------------------------------
 // After the flat leaf pass every lane holds a mask of candidates: 3.6 on average for Cornell, up to
 // ~10, so testing "the k-th candidate of every lane" keeps a third of the lanes busy.  Here the
