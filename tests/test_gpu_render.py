@@ -261,3 +261,19 @@ def test_soak_create_render_destroy(tpt):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "soak.py"), "12"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "soak ok" in r.stdout, (r.stdout[-1500:], r.stderr[-1500:])
+
+
+def test_wide_tree_walks_give_the_same_frame(tpt, monkeypatch):
+    """Large scenes: the parked closest-hit walks are finished over the four-wide tree (wide_closest_hit) — or, with
+    TPT_WIDE=0, over nodes[] like the walks that parked them.  Same primitives, same t: the PathTrace frame is the same bit
+    for bit; the per-pixel kernel (which only knows nodes[]) draws the same paths."""
+    s = gpu_scene("bunny", 160, 160)
+    wide, st = s.render("pt_full", 6)
+    monkeypatch.setenv("TPT_WIDE", "0")
+    plain, _ = s.render("pt_full", 6)
+    monkeypatch.delenv("TPT_WIDE")
+    mega, sm = s.render("pt_full", 6, pipeline=tpt.PIPE_MEGAKERNEL)
+    s.close()
+    assert st["samples"] == 160 * 160 * 6 and np.isfinite(wide).all() and wide.mean() > 0.1
+    assert (wide.view(np.uint32) == plain.view(np.uint32)).all()
+    assert st["ref_rays"] == sm["ref_rays"] and np.allclose(wide, mega, rtol=1e-4, atol=1e-5)      # (another kernel: the shading tier may contract differently)
