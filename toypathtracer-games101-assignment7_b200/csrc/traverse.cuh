@@ -84,20 +84,29 @@ template <bool PLAIN> TPT_DEV bool slab_test_t(const float4 lo, const float4 hi,
 
 // Triangle::GetIntersection, reference Triangle.cpp:77-118.  Returns true and fills
 // *t on a hit; the hit point / normal are produced by the caller for the winner only.
+// WHOLE: the 64-byte record is loaded in one go (two sectors in flight together).  The walks of large scenes ask for
+// that: their records come from L2, and a test that gets past the culling decision would otherwise wait a second time
+// (bunny pt_full 47.3 -> 46.9 ms).  Staged scenes read shared memory, where the eight extra live registers only cost
+// (Cornell BDPT 30.25 -> 30.60 ms with it).
+template <bool WHOLE = false>
 TPT_DEV bool triangle_test(const SceneView& sc, int prim, const DRay& r, int cull, double* t_out) {
+    float4 q0, q1, q2;
+    if (WHOLE) { q0 = sc.tris[4 * prim]; q1 = sc.tris[4 * prim + 1]; q2 = sc.tris[4 * prim + 2]; }
     const f3 normal = mk3(sc.tris[4 * prim + 3]);
     if (cull == 0) {            // CullBack
         if (dotd(r.d, normal) > 0) return false;
     } else if (cull == 1) {     // CullFront
         if (dotd(r.d, normal) < 0) return false;
     }
-    const f3 e2 = mk3(sc.tris[4 * prim + 2]);
-    const f3 e1 = mk3(sc.tris[4 * prim + 1]);
+    if (!WHOLE) { q2 = sc.tris[4 * prim + 2]; q1 = sc.tris[4 * prim + 1]; }
+    const f3 e2 = mk3(q2);
+    const f3 e1 = mk3(q1);
     const f3 pvec = x_cross(r.d, e2);
     const double det = dotd(e1, pvec);
     if (fabs(det) < (double)TPT_EPSILON) return false;
     const double det_inv = 1. / det;
-    const f3 tvec = x_sub(r.o, mk3(sc.tris[4 * prim]));
+    if (!WHOLE) q0 = sc.tris[4 * prim];
+    const f3 tvec = x_sub(r.o, mk3(q0));
     const double u = dotd(tvec, pvec) * det_inv;
     if (u < 0 || u > 1) return false;
     const f3 qvec = x_cross(tvec, e1);
@@ -202,11 +211,12 @@ TPT_DEV void closest_hit_range(const SceneView& sc, const DRay& r, int cull, int
 #endif
 #define TPT_CAND_BYTES(threads) ((threads) * TPT_CAND_MAX * 4)
 
+template <bool WHOLE = false>
 TPT_DEV void settle_candidate(const SceneView& sc, const DRay& r, int cull, int prim, int& best, double& best_t) {
     double t = 0.0;
     bool ok;
     if (prim < sc.n_tris) {
-        ok = triangle_test(sc, prim, r, cull, &t);
+        ok = triangle_test<WHOLE>(sc, prim, r, cull, &t);
     } else {
         float ts = 0.0f;
         ok = sphere_test(sc, prim - sc.n_tris, r, cull, &ts);
@@ -306,9 +316,10 @@ TPT_DEV void closest_hit_deferred(const SceneView& sc, const DRay& r, int cull, 
 
 // Scene::ShadowCheck in the same form: record the leaves in front of the target, then test them in
 // order until one hit lies inside the limit (the any-hit argument of shadow_check applies).
+template <bool WHOLE = false>
 TPT_DEV bool shadow_candidate(const SceneView& sc, const DRay& r, int cull, int prim, f3 from, double limit) {
     int b = -1; double t = 0.0;
-    settle_candidate(sc, r, cull, prim, b, t);
+    settle_candidate<WHOLE>(sc, r, cull, prim, b, t);
     if (b < 0) return false;
     const f3 d1 = x_sub(x_madd(r.o, r.d, (float)t), from);
     return dotd(d1, d1) < limit;
@@ -387,7 +398,7 @@ TPT_DEV bool walk_resume(const SceneView& sc, const DRay& r, int cull, int end, 
         const int prim = __float_as_int(n0.w);
         i = in ? i + 1 : __float_as_int(n1.w);
         if (in && prim >= 0) {
-            settle_candidate(sc, r, cull, prim, best, best_t);
+            settle_candidate<true>(sc, r, cull, prim, best, best_t);
             if (prune && best >= 0) prune_t = (float)best_t * 1.0001f + 1e-3f;
         }
     }
@@ -424,7 +435,7 @@ TPT_DEV bool shadow_resume(const SceneView& sc, const ShadowQuery& q, int cull, 
         const bool in = (plain ? slab_test_plain(n0, n1, q.r, &nmin) : slab_test(n0, n1, q.r, &nmin)) && !(nmin > q.reach);
         const int prim = __float_as_int(n0.w);
         i = in ? i + 1 : __float_as_int(n1.w);
-        if (in && prim >= 0) hit = shadow_candidate(sc, q.r, cull, prim, q.from, q.limit);
+        if (in && prim >= 0) hit = shadow_candidate<true>(sc, q.r, cull, prim, q.from, q.limit);
     }
     cursor = i;
     *found = hit;
@@ -481,7 +492,7 @@ TPT_DEV bool wide_closest_hit(const SceneView& sc, const DRay& r, int cull, int&
             if (k == 0) nm[0] = INFINITY; else if (k == 1) nm[1] = INFINITY; else if (k == 2) nm[2] = INFINITY; else nm[3] = INFINITY;
             int b = -1;
             double t = 0.0;
-            settle_candidate(sc, r, cull, ~rf, b, t);
+            settle_candidate<true>(sc, r, cull, ~rf, b, t);
             if (b >= 0 && (best < 0 || t < best_t || (t == best_t && rank < best_rank))) {      // minimum by (t, visit rank)
                 best = b; best_t = t; best_rank = rank;
                 prune_t = (float)best_t * 1.0001f + 1e-3f;
