@@ -127,6 +127,9 @@ __global__ void __launch_bounds__(256, PT_SHADE_MIN_BLOCKS) k_pt_shade(SceneView
             const float4 hr = b.hit[slot], rd = b.ray_d[slot], ph = b.prim_hit[slot], pd = b.prim_dir[slot];
             const float4 al = b.alpha[slot], ra = b.rad[slot], ac = b.acc[slot];
             const float4 da = b.dl_alpha[slot];
+            // (asked for with the rest, needed or not: every load of the slot's state is in flight at once)
+            const float4 e1_first = b.dl_e1[slot], e2_first = b.dl_e2[slot];
+            const unsigned spp_before = b.spp_done[slot];
             alpha = mk3(al); rad = mk3(ra); acc = mk3(ac);
             bounces = PT_BOUNCES(info);
             keep = true;
@@ -134,7 +137,7 @@ __global__ void __launch_bounds__(256, PT_SHADE_MIN_BLOCKS) k_pt_shade(SceneView
             // ---- the direct light of the previous vertex (PathTracer.cpp:90-105), in the reference's order
             if (info & PT_DIRECT)
                 for (int l = 0; l < b.nl; ++l) {                          // one `resultRadiance +=` per light (PathTracer.cpp:105)
-                    const float4 e1 = b.dl_e1[(size_t)l * b.S + slot], e2 = b.dl_e2[(size_t)l * b.S + slot];
+                    const float4 e1 = l == 0 ? e1_first : b.dl_e1[(size_t)l * b.S + slot], e2 = l == 0 ? e2_first : b.dl_e2[(size_t)l * b.S + slot];
                     f3 eval_result = mk3(0.0f);
                     if (e1.w != 0.0f && ((vis >> (2 * l)) & 1u)) eval_result += mk3(e1);
                     if (e2.w != 0.0f && ((vis >> (2 * l + 1)) & 1u)) eval_result += mk3(e2);
@@ -152,7 +155,7 @@ __global__ void __launch_bounds__(256, PT_SHADE_MIN_BLOCKS) k_pt_shade(SceneView
                 acc += inv_spp * rad;                                    // Renderer.cpp:51
                 ref_rays += bounces;                                     // PathTracer.cpp:126
                 samples++;
-                const unsigned d = b.spp_done[slot] + 1;
+                const unsigned d = spp_before + 1;
                 b.spp_done[slot] = d;
                 info = 0;
                 if ((int)d >= a.spp) {
@@ -174,6 +177,9 @@ __global__ void __launch_bounds__(256, PT_SHADE_MIN_BLOCKS) k_pt_shade(SceneView
             }
             shadeNow = keep && hprim >= 0;
         }
+
+        // the slot's place in the next list: the counter's answer is only needed at the end and travels while the vertex is shaded
+        const unsigned at = wf_append(&b.ctr->n_active[cur ^ 1], keep);
 
         // ---- shade the vertex (one call site for the whole warp)
         __syncwarp();
@@ -256,7 +262,6 @@ __global__ void __launch_bounds__(256, PT_SHADE_MIN_BLOCKS) k_pt_shade(SceneView
             b.acc[slot] = make_float4(acc.x, acc.y, acc.z, 0.0f);
             b.info[slot] = nflags | (bounces << 8);
         }
-        const unsigned at = wf_append(&b.ctr->n_active[cur ^ 1], keep);
         if (keep) next_list[at] = slot;
     }
     // light probes are counted here; scene rays by the traversal kernels
