@@ -726,9 +726,14 @@ __global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_connect(SceneView g, WfB
     const unsigned n = (unsigned)(np_all < b.pair_cap ? np_all : b.pair_cap);
     const unsigned total = (n + 31u) & ~31u;
     const ConnectOut nothing = {false, false, mk3(0.0f), mk3(0.0f), 0};
-    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
-        uint2 rec = make_uint2(0xffffffffu, 0u);
-        if (p < n) rec = b.pair_rec[p];
+    // the NEXT strategy's record is asked for before this one is worked on: its round trip runs beside the work
+    const unsigned first = blockIdx.x * blockDim.x + threadIdx.x;
+    uint2 rec_next = make_uint2(0xffffffffu, 0u);
+    if (first < n) rec_next = b.pair_rec[first];
+    for (unsigned p = first; p < total; p += gridDim.x * blockDim.x) {
+        const uint2 rec = rec_next;
+        rec_next = make_uint2(0xffffffffu, 0u);
+        if (p + gridDim.x * blockDim.x < n) rec_next = b.pair_rec[p + gridDim.x * blockDim.x];
         ConnectOut o = nothing;
         if (rec.x != 0xffffffffu) o = connect_one(b, sc, rec, p);
         connect_emit(b, par, o, rec, p);
@@ -820,8 +825,13 @@ __global__ void __launch_bounds__(256, WF_MIN_BLOCKS) k_mis(SceneView g, RenderA
     pdl_wait();
     const unsigned n = (unsigned)(b.ctr->shadow_mis[par] >> 32);
     const float inv_spp = 1.0f / a.spp_total;
-    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
-        const uint4 e = b.mis_q[q];
+    // the NEXT queue entry is asked for before this one is worked on: its round trip runs beside the work
+    const unsigned first = blockIdx.x * blockDim.x + threadIdx.x;
+    uint4 e_next = make_uint4(0u, 0u, 0u, 0u);
+    if (first < n) e_next = b.mis_q[first];
+    for (unsigned q = first; q < n; q += gridDim.x * blockDim.x) {
+        const uint4 e = e_next;
+        if (q + gridDim.x * blockDim.x < n) e_next = b.mis_q[q + gridDim.x * blockDim.x];
         const unsigned p = e.z;
         const uint2 rec = make_uint2(e.x, e.y);
         const int slot = (int)rec.x;
