@@ -209,6 +209,9 @@ __host__ __device__ inline HmDim hm_block_idx() { HmDim d = {0u, 0u, 0u}; HM_HOS
 __host__ __device__ inline HmDim hm_grid_dim() { HmDim d = {1u, 1u, 1u}; HM_HOST(d.x = g_blk.grid_dim;) return d; }
 template <class T, class U> __host__ __device__ inline T hm_atomic_add(T* p, U v) { const T old = *p; *p = old + (T)v; return old; }   // one host thread
 template <class T, class U> __host__ __device__ inline T hm_atomic_or(T* p, U v) { const T old = *p; *p = old | (T)v; return old; }
+__host__ __device__ inline int hm_float2int_rz(float f) { return (int)f; }
+#define __float2int_rz hm_float2int_rz
+#define __fdividef hm_div
 #define __fadd_rn hm_add
 #define __fsub_rn hm_sub
 #define __fmul_rn hm_mul

@@ -672,7 +672,12 @@ __global__ void __launch_bounds__(256) k_expand(WfBuffers b, int par) {
         const unsigned np = ss.grid + ss.ne + ss.bg;
         for (unsigned k = lane; k < np; k += 32) {
             unsigned s, t = 0u;
-            if (k < ss.grid) { s = k / ss.nlp + 1; t = k % ss.nlp + 1; }
+            if (k < ss.grid) {
+                // k / nlp without the integer division (k < 272, nlp <= 16: (k + 0.5) / nlp is at least 1/32 away from an
+                // integer, far beyond the error of the float quotient, so truncation gives the exact answer)
+                const unsigned qd = (unsigned)__float2int_rz(__fdividef((float)k + 0.5f, (float)ss.nlp));
+                s = qd + 1; t = k - qd * ss.nlp + 1;
+            }
             else if (k < ss.grid + ss.ne) s = __fns(ss.emitters, 0u, (int)(k - ss.grid) + 1) + 1;      // z = cam[s-1] on an emitter
             else s = nc;                                                                              // Background end, lit background
             b.pair_rec[base + off + k] = make_uint2((unsigned)slot, s | (t << 8) | (parity << 16));
