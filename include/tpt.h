@@ -211,6 +211,27 @@ int tpt_probe_read_bandwidth(int device, size_t bytes, int repeats, double* gb_p
  * the reference. */
 int tpt_probe_fma_throughput(int device, int iters, double* tflops, double* gwarp_inst_per_s);
 
+/* ---- scene preparation --------------------------------------------------- */
+
+/* One node of BVHAccel::nodes (reference BVH.hpp:46-61 BVHBuildNode): box, children (-1 at a leaf), the leaf's
+ * object as an index into the caller's object list (-1 at an inner node), area. */
+typedef struct TptBvhNode {
+    float   bmin[3], bmax[3];
+    int32_t left, right;
+    int32_t object;
+    float   area;
+} TptBvhNode;
+
+/* Replaces BVHAccel::recursiveBuild (BVH.cpp:30-99) for one list of n objects — a mesh's triangles
+ * (Triangle.cpp:69-74) or a scene's objects (Scene.cpp:11-19) — on `device`.  bounds: n * 6 floats, Object::GetBounds()
+ * as pMin.xyz pMax.xyz; areas: n floats, Object::getArea().  out_nodes: 2n - 1 nodes in the order the reference's
+ * recursion appends them (pre-order, left subtree first; node 0 is the root), each with the reference's child
+ * indices, leaf object, box and area bit for bit — including where std::sort leaves objects whose centroids tie on
+ * the split axis, which decides which of two hits at equal distance the traversal reports.  device_ms (may be NULL):
+ * CUDA-event time of the kernels.  Host buffers; NaN coordinates are outside the contract (the reference's comparator
+ * is not an ordering for them). */
+int tpt_bvh_build(const float* bounds, const float* areas, int n, int device, TptBvhNode* out_nodes, double* device_ms);
+
 /* Page-locked host memory for the frame tpt_render writes (a plain malloc'ed buffer works
  * too, through the driver's staging copy).  NULL on failure. */
 void* tpt_host_alloc(size_t bytes);

@@ -1,0 +1,67 @@
+"""SURVEY 8(f)2 on the GPU: the device BVH build (tpt_bvh_build, csrc/bvh_build.cu) against the reference recursion
+(BVHAccel::recursiveBuild = BVH.cpp:30-99 as written) — node arrays bit for bit — and a frame rendered from a scene whose
+trees were built on the device against the same frame from host-built trees."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def test_device_build_equals_the_reference_recursion(tpt, tmp_path):
+    """tests/native/bvh_build_device.cpp: tie-heavy synthetic lists from 1 to 300 000 objects (both sides of the
+    thread-per-range switch and of the shared-memory capacity) and the triangles of every fixture mesh."""
+    pkg = os.path.dirname(tpt.LIBTPT)
+    exe = str(tmp_path / "bvh_build_device")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(pkg, "host"), "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "native", "bvh_build_device.cpp"), "-o", exe,
+                        "-L", pkg, "-ltpt_host", "-ltpt", "-Wl,-rpath," + pkg], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    models = tpt.ensure_models()
+    meshes = [os.path.join(models, "bunny", "bunny_x1500.obj")] + \
+             [os.path.join(models, "cornellbox", m + ".obj") for m in ("floor", "shortbox", "tallbox", "lightocculuder")]
+    r = subprocess.run([exe, *meshes], capture_output=True, text=True, timeout=900)
+    print(r.stdout)
+    assert r.returncode == 0 and " 0 errors" in r.stdout, r.stdout + r.stderr
+
+
+def test_abi_entry_point_on_a_small_list(tpt):
+    """tpt_bvh_build directly: three boxes in a row — the root splits at the median of the x centroids."""
+    lib = tpt.lib()
+
+    class Node(C.Structure):
+        _fields_ = [("bmin", C.c_float * 3), ("bmax", C.c_float * 3), ("left", C.c_int32), ("right", C.c_int32),
+                    ("object", C.c_int32), ("area", C.c_float)]
+
+    bounds = np.array([[4, 0, 0, 5, 1, 1], [0, 0, 0, 1, 1, 1], [2, 0, 0, 3, 1, 1]], np.float32)
+    areas = np.array([1.0, 2.0, 4.0], np.float32)
+    nodes = (Node * 5)()
+    ms = C.c_double(-1)
+    lib.tpt_bvh_build.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
+    assert lib.tpt_bvh_build(bounds.ctypes.data, areas.ctypes.data, 3, 0, C.addressof(nodes), C.byref(ms)) == 0, lib.tpt_last_error()
+    # sorted by x centroid: objects 1, 2, 0; left = {1}, right = {2, 0}
+    assert (nodes[0].left, nodes[0].right, nodes[0].object) == (1, 2, -1)
+    assert nodes[1].object == 1 and nodes[2].object == -1 and nodes[3].object == 2 and nodes[4].object == 0
+    assert list(nodes[0].bmin) == [0, 0, 0] and list(nodes[0].bmax) == [5, 1, 1] and nodes[0].area == 7.0
+    assert ms.value >= 0
+    assert lib.tpt_bvh_build(bounds.ctypes.data, areas.ctypes.data, 0, 0, C.addressof(nodes), None) == 1
+
+
+def test_frame_from_device_built_trees(tpt, monkeypatch):
+    """The host scene API with every BVH built on the device: the bunny PathTrace frame is the host-built scene's frame
+    bit for bit (same trees, same kernels)."""
+    def frame():
+        s = tpt.Scene("bunny", 96, 96, device=0)
+        img, _ = s.render("pt_full", 4)
+        s.close()
+        return img
+    monkeypatch.delenv("TPT_BVH_BUILD", raising=False)
+    host_built = frame()
+    monkeypatch.setenv("TPT_BVH_BUILD", "device")
+    device_built = frame()
+    assert np.array_equal(host_built, device_built)

@@ -125,6 +125,45 @@ def test_in_place_bvh_build_equals_the_reference_recursion(tpt, tmp_path):
     assert r.returncode == 0 and " 0 errors" in r.stdout, r.stdout + r.stderr
 
 
+def test_restated_std_sort_moves_elements_as_libstdcxx_does(tmp_path):
+    """csrc/std_sort.cuh (what the device BVH build sorts with) against std::sort itself: tie-heavy inputs, sizes around
+    the insertion-sort threshold, killer inputs that reach the heap-sort fallback, and the round-based schedule the
+    CUDA block uses (tests/native/std_sort_check.cpp; host code only)."""
+    import subprocess
+    exe = str(tmp_path / "std_sort_check")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "toypathtracer-games101-assignment7_b200", "csrc"),
+                        os.path.join(ROOT, "tests", "native", "std_sort_check.cpp"), "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and " 0 errors" in r.stdout and " 0 heap-sort" not in r.stdout, r.stdout + r.stderr
+
+
+def test_device_bvh_build_on_the_block_emulator(tmp_path):
+    """csrc/bvh_build.cu (tpt_bvh_build: range table, per-level sort kernels with their task lists, emit passes) run on
+    the CPU block emulator against the reference recursion restated over indices — node arrays bit for bit, for
+    tie-heavy inputs, sizes on both sides of the thread-per-range switch, with the ranges staged in "shared memory" and
+    sorted in place in global memory (tests/native/bvh_build_host.cu).  The GPU run is tests/test_gpu_bvh_build.py."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    cuda_inc = "/usr/local/cuda/include"
+    if not shutil.which("g++") or not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("g++ / CUDA headers not available")
+    so = str(tmp_path / "libbvh_build_host.so")
+    r = subprocess.run(["g++", "-std=c++17", "-O2", "-x", "c++", "-fPIC", "-ffp-contract=off", "-shared", "-w", "-I", cuda_inc,
+                        "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "toypathtracer-games101-assignment7_b200", "csrc"),
+                        "-I", os.path.join(ROOT, "tests", "native"), os.path.join(ROOT, "tests", "native", "bvh_build_host.cu"), "-o", so,
+                        "-Wl,-Bsymbolic", "-L/usr/local/cuda/lib64", "-lcudart_static", "-ldl", "-lrt", "-lpthread"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lib = C.CDLL(so)
+    lib.bbh_case.argtypes = [C.c_int] * 3
+    for kind in range(5):
+        for n in (1, 2, 3, 4, 5, 7, 16, 17, 33, 48, 49, 50, 97, 100, 1000, 4980):
+            for smem in (200 * 1024, 4096 + 8 * 60):       # staged / in place
+                assert lib.bbh_case(kind, n, smem) == 0, (kind, n, smem)
+
+
 def test_mesh_placement_constructors(tpt, tmp_path):
     """MeshTriangle(path | xyz, material, scale, translate) (the reference has no transform): bit-identical
     to a mesh whose vertices the caller placed with the same float arithmetic (tests/native/mesh_place.cpp)."""

@@ -194,8 +194,13 @@ public:
     std::vector<Object*> primitives;
     std::vector<BVHBuildNode> nodes;
 
+    // lists of at least DeviceBuildMin() objects are built on the GPU (tpt_bvh_build); see tpt_host.cpp
+    static int DeviceBuildMin();
+    double deviceBuildMs = -1.0;       // CUDA-event time of the device build's kernels; -1 when built on the host
+
 private:
     void buildInPlace();
+    void buildOnDevice();
 };
 
 // ---- Triangle.hpp -----------------------------------------------------------

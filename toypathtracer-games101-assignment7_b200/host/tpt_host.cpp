@@ -25,7 +25,49 @@ const float EPSILON = 1e-4;
 // ---------------------------------------------------------------- BVH build
 BVHAccel::BVHAccel(std::vector<Object*> p, int maxPrims, SplitMethod method)
     : maxPrimsInNode(std::min(255, maxPrims)), splitMethod(method), primitives(std::move(p)) {
-    if (!primitives.empty()) buildInPlace();
+    if (primitives.empty()) return;
+    if (primitives.size() >= (size_t)DeviceBuildMin()) buildOnDevice();
+    else buildInPlace();
+}
+
+// Which lists are built on the GPU (tpt_bvh_build, csrc/bvh_build.cu) instead of by buildInPlace below: those with at
+// least TPT_BVH_BUILD_MIN objects; TPT_BVH_BUILD=device is short for a minimum of 1, and without either variable every
+// list is built on the host (for the meshes of BASELINE — 5 K triangles at most — the two take about as long, and
+// the host build needs no device).  Both produce the node array of the reference recursion.
+int BVHAccel::DeviceBuildMin() {
+    if (const char* e = std::getenv("TPT_BVH_BUILD_MIN")) return std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("TPT_BVH_BUILD")) if (std::string(e) == "device") return 1;
+    return std::numeric_limits<int>::max();
+}
+
+void BVHAccel::buildOnDevice() {
+    const size_t n = primitives.size();
+    std::vector<float> bounds(6 * n), areas(n);
+    for (size_t i = 0; i < n; ++i) {
+        const Bounds3 b = primitives[i]->GetBounds();
+        bounds[6 * i + 0] = b.pMin.x; bounds[6 * i + 1] = b.pMin.y; bounds[6 * i + 2] = b.pMin.z;
+        bounds[6 * i + 3] = b.pMax.x; bounds[6 * i + 4] = b.pMax.y; bounds[6 * i + 5] = b.pMax.z;
+        areas[i] = primitives[i]->getArea();
+    }
+    std::vector<TptBvhNode> flat(2 * n - 1);
+    int device = 0;
+    if (const char* e = std::getenv("TPT_DEVICE")) device = std::atoi(e);
+    if (tpt_bvh_build(bounds.data(), areas.data(), (int)n, device, flat.data(), &deviceBuildMs) != TPT_OK) {
+        // the reference has no error channel here (a constructor, no exceptions); a build that was asked to run on
+        // the device and cannot must not quietly become something else
+        std::fprintf(stderr, "BVHAccel: device build failed: %s\n", tpt_last_error());
+        std::abort();
+    }
+    nodes.assign(flat.size(), BVHBuildNode());
+    for (size_t i = 0; i < flat.size(); ++i) {
+        BVHBuildNode& nd = nodes[i];
+        nd.bounds.pMin = Vector3f(flat[i].bmin[0], flat[i].bmin[1], flat[i].bmin[2]);
+        nd.bounds.pMax = Vector3f(flat[i].bmax[0], flat[i].bmax[1], flat[i].bmax[2]);
+        nd.left = flat[i].left;
+        nd.right = flat[i].right;
+        nd.object = flat[i].object >= 0 ? primitives[flat[i].object] : nullptr;
+        nd.area = flat[i].area;
+    }
 }
 
 // ---- the same tree without the per-level copies (large meshes) -------------------------
