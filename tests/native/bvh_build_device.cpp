@@ -2,8 +2,8 @@
 // with TPT_BVH_BUILD=device against BVHAccel::recursiveBuild (reference BVH.cpp:30-99 as written) on the same
 // objects — child indices, leaf objects, bounds and areas bit for bit.  Inputs as in bvh_build.cpp (chosen for ties:
 // lattices, coincident centroids, flat sheets) plus an OBJ mesh when a path is given; sizes on both sides of the
-// thread-per-range / block-per-range switch (48) and of the shared-memory capacity (~28 K objects).  Above 40 K
-// objects the comparison is with the host's in-place build (which bvh_build.cpp pins to the recursion).
+// warp-per-range / block-per-range switch (48) and of the shared-memory capacity (~12 K objects).  Every list is
+// compared with the host's in-place build, and up to 40 K objects with the recursion itself.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -37,24 +37,22 @@ static int CompareBuilds(const std::vector<Object*>& objs, const char* what) {
     const double dev_wall = Ms(t0);
     unsetenv("TPT_BVH_BUILD");
     if (dev.deviceBuildMs < 0) { std::printf("%s: the device build did not run\n", what); return 1; }
-    int bad;
-    double host_ms;
+    t0 = std::chrono::steady_clock::now();
+    BVHAccel host(objs);                              // the host's in-place build (bvh_build.cpp pins it to the recursion)
+    const double host_ms = Ms(t0);
+    if (host.deviceBuildMs >= 0) { std::printf("%s: the host build ran on the device\n", what); return 1; }
+    int bad = Compare(dev.nodes, host.nodes);
+    double recursion_ms = -1.0;
     if (objs.size() <= 40001) {
         BVHAccel slow(std::vector<Object*>{});        // empty: the constructor builds nothing
         t0 = std::chrono::steady_clock::now();
         slow.recursiveBuild(objs);
-        host_ms = Ms(t0);
-        bad = Compare(dev.nodes, slow.nodes);
-    } else {
-        t0 = std::chrono::steady_clock::now();
-        BVHAccel host(objs);
-        host_ms = Ms(t0);
-        if (host.deviceBuildMs >= 0) { std::printf("%s: the host build ran on the device\n", what); return 1; }
-        bad = Compare(dev.nodes, host.nodes);
+        recursion_ms = Ms(t0);
+        bad += Compare(dev.nodes, slow.nodes);
     }
     if (bad || objs.size() >= 4000)
-        std::printf("%s n %zu: %d differing nodes; device kernels %.3f ms (call %.3f ms), host %s %.3f ms\n", what, objs.size(), bad,
-                    dev.deviceBuildMs, dev_wall, objs.size() <= 40001 ? "recursion" : "in-place build", host_ms);
+        std::printf("%s n %zu: %d differing nodes; device kernels %.3f ms (call %.3f ms), host in-place build %.3f ms, reference recursion %.3f ms\n",
+                    what, objs.size(), bad, dev.deviceBuildMs, dev_wall, host_ms, recursion_ms);
     return bad != 0;
 }
 

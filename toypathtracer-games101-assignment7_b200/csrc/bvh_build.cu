@@ -16,6 +16,9 @@
 // (host/tpt_host.cpp) bit for bit: tests/native/bvh_build_device.cpp compares them.
 #include <algorithm>
 #include <cfloat>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "std_sort.cuh"
@@ -31,8 +34,11 @@ struct BuildRange { int start, n, self; };
 #define BB_LAUNCH(kernel, grid, block, smem, ...) kernel<<<(grid), (block), (smem)>>>(__VA_ARGS__)
 #define BB_DYN_SHARED(type, name) extern __shared__ type name[]
 #endif
-#define BB_THREADS 128
-#define BB_SMALL_N 48            /* a level whose ranges are at most this long is sorted a thread per range */
+#define BB_THREADS 256           /* block of the block-per-range kernel */
+#define BB_SMALL_THREADS 256      /* ... by a warp: eight ranges per block */
+#define BB_SMALL_N 48            /* a level whose ranges are at most this long is sorted a warp per range ... */
+#define BB_COOP_MIN 2048         /* partition steps over more elements than this are done by the whole block ... */
+#define BB_WARP_MIN 64           /* ... over more than this by a warp, shorter ones by a thread */
 
 __device__ __forceinline__ uint32_t centroid_key(const float* cent, uint32_t obj, int dim) {
     // -0 and +0 compare equal in the reference's comparator: fold them before taking the order-preserving bits
@@ -54,12 +60,130 @@ __global__ void __launch_bounds__(256) k_bvh_centroids(const float* __restrict__
     order[i] = (ss_word)(unsigned)i;
 }
 
-// One level, a block per range.  `work` is the range's slice of `order`, or its copy in shared memory when it fits.
+// One step of the introsort loop (ss_step) by many threads.  __unguarded_partition swaps the k-th element from the
+// left that is not below the pivot with the k-th element from the right that is not above it, for as long as the former
+// lies left of the latter; neither scan ever returns to a position it has passed, so both sequences can be read off the
+// array as it stands after the median has been moved to the front.  The threads list the positions of the two
+// sequences (ascending for the left one, descending for the right one), K = the number of k with left[k] < right[k]
+// (a prefix: both lists are monotone) is the number of swaps, the swaps touch distinct positions, and the cut is where
+// the left scan of the serial loop stops next — at left[K], or at the element the K-th swap put in front of it.
+// The arrangement is the serial loop's (tests/native/bvh_build_host.cu compares whole trees).
+__device__ __forceinline__ int partition_cut(const int* lpos, const int* rpos, int tot_l, int K, int last) {
+    if (K < tot_l && (K == 0 || lpos[K] < rpos[K - 1])) return lpos[K];
+    return K > 0 ? rpos[K - 1] : last;
+}
+__device__ __forceinline__ void finish_step(ss_word* v, SsRange T, int cut, SsRange* next, int* sh_next) {      // one thread
+    const SsRange parts[2] = {{T.first, cut, T.depth - 1}, {cut, T.last, T.depth - 1}};
+    for (int p = 0; p < 2; ++p) {
+        if (parts[p].last - parts[p].first > SS_THRESHOLD) next[atomicAdd(sh_next, 1)] = parts[p];
+        else ss_insertion_sort(v, parts[p].first, parts[p].last);
+    }
+}
+
+// ... by the whole block (long ranges): a chunk of positions per thread, the list offsets from a block scan over the
+// per-thread counts.  sh_warp: 2 x 8 warp totals; sh_k: the swap count.
+__device__ void coop_step(ss_word* v, SsRange T, SsRange* next, int* sh_next, int* lpos, int* rpos, int* sh_warp, int* sh_k) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (T.depth == 0) {                       // depth limit reached: heap sort, as the serial step does
+        if (tid == 0) ss_heap_sort(v + T.first, T.last - T.first);
+        __syncthreads();
+        return;
+    }
+    if (tid == 0) { ss_median_to_first(v, T.first, T.first + 1, T.first + (T.last - T.first) / 2, T.last - 1); *sh_k = 0; }
+    __syncthreads();
+    const ss_word pivot = v[T.first];
+    const int m = T.last - T.first - 1;       // the scans run over first + 1 .. last - 1
+    const int chunk = (m + BB_THREADS - 1) / BB_THREADS;
+    const int p0 = T.first + 1 + min(m, tid * chunk), p1 = T.first + 1 + min(m, (tid + 1) * chunk);
+    int cl = 0, cr = 0;
+    for (int p = p0; p < p1; ++p) {
+        const ss_word w = v[p];
+        cl += !ss_less(w, pivot);
+        cr += !ss_less(pivot, w);
+    }
+    int il = cl, ir = cr;                     // inclusive scans inside the warp, warp totals through shared memory
+    for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, il, o), b = __shfl_up_sync(0xffffffffu, ir, o);
+        if (lane >= o) { il += a; ir += b; }
+    }
+    if (lane == 31) { sh_warp[warp] = il; sh_warp[BB_THREADS / 32 + warp] = ir; }
+    __syncthreads();
+    int ol = il - cl, orr = ir - cr, tot_l = 0, tot_r = 0;
+    for (int w = 0; w < BB_THREADS / 32; ++w) {
+        const int a = sh_warp[w], b = sh_warp[BB_THREADS / 32 + w];
+        if (w < warp) { ol += a; orr += b; }
+        tot_l += a; tot_r += b;
+    }
+    for (int p = p0; p < p1; ++p) {
+        const ss_word w = v[p];
+        if (!ss_less(w, pivot)) lpos[ol++] = p;
+        if (!ss_less(pivot, w)) rpos[tot_r - 1 - orr++] = p;
+    }
+    __syncthreads();
+    const int len = min(tot_l, tot_r);
+    int cnt = 0;
+    for (int k = tid; k < len; k += BB_THREADS) cnt += lpos[k] < rpos[k];
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0 && cnt) atomicAdd(sh_k, cnt);
+    __syncthreads();
+    const int K = *sh_k;
+    const int cut = partition_cut(lpos, rpos, tot_l, K, T.last);
+    for (int k = tid; k < K; k += BB_THREADS) ss_swap(v, lpos[k], rpos[k]);
+    __syncthreads();
+    if (tid == 0) finish_step(v, T, cut, next, sh_next);
+    __syncthreads();                          // the lists, the warp totals and the counter are free again
+}
+
+// ... by one warp (ranges of a few hundred elements; the warps of the block work on different ranges): 32 positions of
+// each scan per iteration, placed by ballots.
+__device__ void warp_step(ss_word* v, SsRange T, SsRange* next, int* sh_next, int* lpos, int* rpos) {
+    const int lane = threadIdx.x & 31;
+    const unsigned below = (1u << lane) - 1u;
+    if (T.depth == 0) {
+        if (lane == 0) ss_heap_sort(v + T.first, T.last - T.first);
+        __syncwarp();
+        return;
+    }
+    if (lane == 0) ss_median_to_first(v, T.first, T.first + 1, T.first + (T.last - T.first) / 2, T.last - 1);
+    __syncwarp();
+    const ss_word pivot = v[T.first];
+    const int m = T.last - T.first - 1;
+    int tot_l = 0, tot_r = 0;
+    for (int base = 0; base < m; base += 32) {
+        const int i = base + lane;
+        const bool in = i < m;
+        const int pl = T.first + 1 + i, pr = T.last - 1 - i;
+        const bool fl = in && !ss_less(v[in ? pl : T.first], pivot), fr = in && !ss_less(pivot, v[in ? pr : T.first]);
+        const unsigned ml = __ballot_sync(0xffffffffu, fl), mr = __ballot_sync(0xffffffffu, fr);
+        if (fl) lpos[tot_l + __popc(ml & below)] = pl;
+        if (fr) rpos[tot_r + __popc(mr & below)] = pr;
+        tot_l += __popc(ml);
+        tot_r += __popc(mr);
+    }
+    __syncwarp();
+    const int len = min(tot_l, tot_r);
+    int K = 0;
+    for (int k = lane; k < len; k += 32) K += lpos[k] < rpos[k];
+    for (int o = 16; o > 0; o >>= 1) K += __shfl_xor_sync(0xffffffffu, K, o);
+    const int cut = partition_cut(lpos, rpos, tot_l, K, T.last);
+    __syncwarp();
+    for (int k = lane; k < K; k += 32) ss_swap(v, lpos[k], rpos[k]);
+    __syncwarp();
+    if (lane == 0) finish_step(v, T, cut, next, sh_next);
+    __syncwarp();
+}
+
+// One level, a block per range.  A range of at most `smem_elems` objects is sorted in shared memory together with
+// everything the sort needs (the words, the two position lists of the partition steps, the two task lists:
+// bb_smem_bytes); a longer one in place in global memory with its lists in the scratch arrays.
+__host__ __device__ inline size_t bb_smem_bytes(int n) { return (size_t)n * 16 + 2 * ((size_t)n / 16 + 1) * sizeof(SsRange); }
+
 __global__ void __launch_bounds__(BB_THREADS) k_bvh_sort_level(const BuildRange* __restrict__ ranges, int count, const float* __restrict__ cent,
-                                                               ss_word* order, SsRange* tasks, int smem_words) {
+                                                               ss_word* order, SsRange* tasks, int* lists, int smem_elems) {
     BB_DYN_SHARED(ss_word, sh_words);
     __shared__ float red[6][BB_THREADS / 32];
-    __shared__ int sh_dim, sh_count, sh_next;
+    __shared__ int sh_dim, sh_count, sh_next, sh_k, sh_long;
+    __shared__ int sh_warp[2 * BB_THREADS / 32];
     const int tid = threadIdx.x;
     for (int r = blockIdx.x; r < count; r += gridDim.x) {
         const BuildRange R = ranges[r];
@@ -90,28 +214,52 @@ __global__ void __launch_bounds__(BB_THREADS) k_bvh_sort_level(const BuildRange*
         }
         __syncthreads();
         const int dim = sh_dim;
-        ss_word* work = R.n <= smem_words ? sh_words : slice;
+        const bool staged = R.n <= smem_elems;
+        ss_word* work = staged ? sh_words : slice;
         for (int i = tid; i < R.n; i += BB_THREADS) {
             const uint32_t obj = (uint32_t)slice[i];
             work[i] = ((ss_word)centroid_key(cent, obj, dim) << 32) | obj;
         }
-        // std::sort of the range: the partition tree a round per level, a thread per range of the round
-        // (std_sort.cuh).  The two task lists of this range sit at 2 * (start / 16 + r): n / 16 + 1 entries each.
+        // std::sort of the range: the partition tree a round per level — the whole block on each long range of the
+        // round (coop_step), a warp on each middle one (warp_step), a thread per short one (std_sort.cuh).  A step's two
+        // position lists take 2 ints per element of ITS range; the two task lists of this range n / 16 + 1 entries each
+        // (in global memory at 2 * (start / 16 + r)).
         const int cap = R.n / 16 + 1;
-        SsRange* cur = tasks + 2 * ((size_t)R.start / 16 + r);
+        int* lists_r = staged ? reinterpret_cast<int*>(sh_words + R.n) : lists + 2 * (size_t)R.start;
+        SsRange* cur = staged ? reinterpret_cast<SsRange*>(lists_r + 2 * (size_t)R.n) : tasks + 2 * ((size_t)R.start / 16 + r);
         SsRange* next = cur + cap;
         if (tid == 0) {
             if (R.n <= SS_THRESHOLD) { sh_count = 0; }
             else { cur[0] = SsRange{0, R.n, 2 * ss_lg(R.n)}; sh_count = 1; }
             sh_next = 0;
+            sh_long = R.n > BB_COOP_MIN;
         }
         __syncthreads();
         if (R.n <= SS_THRESHOLD && tid == 0) ss_insertion_sort(work, 0, R.n);
         while (sh_count > 0) {
             const int n_tasks = sh_count;
-            for (int t = tid; t < n_tasks; t += BB_THREADS) {
+            if (sh_long) {                                // the long ones first, the whole block on each
+                int still = 0;
+                for (int t = 0; t < n_tasks; ++t) {
+                    const SsRange T = cur[t];
+                    if (T.last - T.first <= BB_COOP_MIN) continue;
+                    coop_step(work, T, next, &sh_next, lists_r + 2 * T.first, lists_r + 2 * T.first + (T.last - T.first), sh_warp, &sh_k);
+                    still = 1;
+                }
+                if (tid == 0) sh_long = still;            // read again after the barriers that end the round
+            }
+            for (int t = tid >> 5; t < n_tasks; t += BB_THREADS / 32) {      // a warp on each of the middle ones
+                const SsRange T = cur[t];
+                const int len = T.last - T.first;
+                if (len > BB_WARP_MIN && len <= BB_COOP_MIN) warp_step(work, T, next, &sh_next, lists_r + 2 * T.first, lists_r + 2 * T.first + len);
+            }
+            // a thread on each of the short ones — neighbouring tasks to different WARPS: every lane walks its own
+            // data-dependent loops, and the lanes of one warp take turns on them
+            for (int t = (tid >> 5) + (BB_THREADS / 32) * (tid & 31); t < n_tasks; t += BB_THREADS) {
+                const SsRange T = cur[t];
+                if (T.last - T.first > BB_WARP_MIN) continue;
                 SsRange out[2];
-                const int k = ss_step(work, cur[t], out);
+                const int k = ss_step(work, T, out);
                 for (int i = 0; i < k; ++i) next[atomicAdd(&sh_next, 1)] = out[i];
             }
             __syncthreads();
@@ -125,28 +273,43 @@ __global__ void __launch_bounds__(BB_THREADS) k_bvh_sort_level(const BuildRange*
     }
 }
 
-// One level of short ranges, a thread per range, in place.
-__global__ void __launch_bounds__(BB_THREADS) k_bvh_sort_level_small(const BuildRange* __restrict__ ranges, int count, const float* __restrict__ cent,
-                                                                     ss_word* order) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= count) return;
+// One level of short ranges, a warp per range: the lanes gather the centroids and form the keys together (a thread on
+// its own waits for every one of these loads in turn), lane 0 sorts the words in shared memory (a serial sort in place
+// in global memory reloads every line it has just written from L2), the lanes write them back.
+__global__ void __launch_bounds__(BB_SMALL_THREADS) k_bvh_sort_level_small(const BuildRange* __restrict__ ranges, int count, const float* __restrict__ cent,
+                                                                           ss_word* order) {
+    __shared__ ss_word sh_slices[(BB_SMALL_THREADS / 32) * BB_SMALL_N];
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= count) return;               // whole warps
     const BuildRange R = ranges[r];
     if (R.n <= 2) return;
     ss_word* slice = order + R.start;
+    ss_word* mine = sh_slices + (threadIdx.x >> 5) * BB_SMALL_N;
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-    for (int i = 0; i < R.n; ++i) {
-        const uint32_t obj = (uint32_t)slice[i];
-        for (int c = 0; c < 3; ++c) {
-            const float v = cent[3 * (size_t)obj + c];
-            lo[c] = fminf(lo[c], v); hi[c] = fmaxf(hi[c], v);
+    uint32_t objs[(BB_SMALL_N + 31) / 32];
+    for (int k = 0; k < (BB_SMALL_N + 31) / 32; ++k) {
+        const int i = lane + 32 * k;
+        objs[k] = i < R.n ? (uint32_t)slice[i] : 0u;
+        if (i < R.n)
+            for (int c = 0; c < 3; ++c) {
+                const float v = cent[3 * (size_t)objs[k] + c];
+                lo[c] = fminf(lo[c], v); hi[c] = fmaxf(hi[c], v);
+            }
+    }
+    for (int c = 0; c < 3; ++c)
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+            hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
         }
-    }
     const int dim = widest_axis(lo, hi);
-    for (int i = 0; i < R.n; ++i) {
-        const uint32_t obj = (uint32_t)slice[i];
-        slice[i] = ((ss_word)centroid_key(cent, obj, dim) << 32) | obj;
+    for (int k = 0; k < (BB_SMALL_N + 31) / 32; ++k) {
+        const int i = lane + 32 * k;
+        if (i < R.n) mine[i] = ((ss_word)centroid_key(cent, objs[k], dim) << 32) | objs[k];
     }
-    ss_sort_serial(slice, R.n);
+    __syncwarp();
+    if (lane == 0) ss_sort_serial(mine, R.n);
+    __syncwarp();
+    for (int i = lane; i < R.n; i += 32) slice[i] = mine[i];
 }
 
 // The nodes of one level, deepest level first: a leaf takes its object's box and area, an inner node the Union of its
@@ -217,13 +380,14 @@ extern "C" int tpt_bvh_build(const float* bounds, const float* areas, int n, int
 
     int smem_optin = 0;
     TPT_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-    const int smem_words = std::max(0, (smem_optin - 4096) / 8);
-    TPT_CUDA(cudaFuncSetAttribute(k_bvh_sort_level, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_words * 8));
+    int smem_elems = std::max(0, (smem_optin - 4096) / 18);     // the longest range bb_smem_bytes() of which fit
+    while (smem_elems > 0 && bb_smem_bytes(smem_elems) > (size_t)std::max(0, smem_optin - 4096)) --smem_elems;
+    TPT_CUDA(cudaFuncSetAttribute(k_bvh_sort_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bb_smem_bytes(smem_elems)));
 
     DevBlock d_bounds(sizeof(float) * 6 * n), d_areas(sizeof(float) * n), d_cent(sizeof(float) * 3 * n), d_order(sizeof(ss_word) * n),
         d_table(sizeof(BuildRange) * table.size()), d_nodes(sizeof(TptBvhNode) * (2 * (size_t)n - 1)),
-        d_tasks(sizeof(SsRange) * 2 * ((size_t)n / 16 + widest + 2));
-    for (const DevBlock* b : {&d_bounds, &d_areas, &d_cent, &d_order, &d_table, &d_nodes, &d_tasks})
+        d_tasks(sizeof(SsRange) * 2 * ((size_t)n / 16 + widest + 2)), d_lists(sizeof(int) * 2 * (size_t)n);
+    for (const DevBlock* b : {&d_bounds, &d_areas, &d_cent, &d_order, &d_table, &d_nodes, &d_tasks, &d_lists})
         if (!b->p) return TPT_ERR_OOM;
     TPT_CUDA(cudaMemcpy(d_bounds.p, bounds, sizeof(float) * 6 * n, cudaMemcpyHostToDevice));
     TPT_CUDA(cudaMemcpy(d_areas.p, areas, sizeof(float) * n, cudaMemcpyHostToDevice));
@@ -232,7 +396,18 @@ extern "C" int tpt_bvh_build(const float* bounds, const float* areas, int n, int
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     TPT_CUDA(cudaEventCreate(&e0));
     TPT_CUDA(cudaEventCreate(&e1));
+    // TPT_BVH_BUILD_TRACE=1: an event after every launch, the per-launch times on stderr (a measurement aid)
+    const bool trace = std::getenv("TPT_BVH_BUILD_TRACE") != nullptr;
+    std::vector<cudaEvent_t> marks;
+    std::vector<std::string> labels;
+    auto mark = [&](const char* what, size_t lv, int longest) {
+        if (!trace) return;
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, 0);
+        marks.push_back(e);
+        labels.push_back(std::string(what) + " level " + std::to_string(lv) + " longest " + std::to_string(longest));
+    };
     cudaEventRecord(e0, 0);
+    mark("start", 0, n);
     BB_LAUNCH(k_bvh_centroids, (n + 255) / 256, 256, 0, d_bounds.as<float>(), n, d_cent.as<float>(), d_order.as<ss_word>());
     for (size_t lv = 0; lv < levels; ++lv) {
         const BuildRange* lr = d_table.as<BuildRange>() + level_at[lv];
@@ -241,22 +416,31 @@ extern "C" int tpt_bvh_build(const float* bounds, const float* areas, int n, int
         for (size_t i = level_at[lv]; i < level_at[lv + 1]; ++i) longest = std::max(longest, table[i].n);
         if (longest <= 2) continue;
         if (longest <= BB_SMALL_N) {
-            BB_LAUNCH(k_bvh_sort_level_small, (count + BB_THREADS - 1) / BB_THREADS, BB_THREADS, 0, lr, count, d_cent.as<float>(), d_order.as<ss_word>());
+            const int per_block = BB_SMALL_THREADS / 32;
+            BB_LAUNCH(k_bvh_sort_level_small, (count + per_block - 1) / per_block, BB_SMALL_THREADS, 0, lr, count, d_cent.as<float>(), d_order.as<ss_word>());
         } else {
-            const bool staged = longest <= smem_words;      // the level's ranges fit shared memory (they differ by one element at most)
-            BB_LAUNCH(k_bvh_sort_level, std::min(count, 65535), BB_THREADS, staged ? (size_t)longest * 8 : 0, lr, count, d_cent.as<float>(),
-                      d_order.as<ss_word>(), d_tasks.as<SsRange>(), staged ? smem_words : 0);
+            const bool staged = longest <= smem_elems;      // the level's ranges fit shared memory (they differ by one element at most)
+            BB_LAUNCH(k_bvh_sort_level, std::min(count, 65535), BB_THREADS, staged ? bb_smem_bytes(longest) : 0, lr, count, d_cent.as<float>(),
+                      d_order.as<ss_word>(), d_tasks.as<SsRange>(), d_lists.as<int>(), staged ? smem_elems : 0);
         }
+        mark(longest <= BB_SMALL_N ? "sort (thread per range)" : "sort (block per range)", lv, longest);
     }
     for (size_t lv = levels; lv-- > 0;) {
         const int count = (int)(level_at[lv + 1] - level_at[lv]);
         BB_LAUNCH(k_bvh_emit_level, (count + 255) / 256, 256, 0, d_table.as<BuildRange>() + level_at[lv], count, d_order.as<ss_word>(), d_bounds.as<float>(),
                   d_areas.as<float>(), d_nodes.as<TptBvhNode>());
     }
+    mark("emit, all levels", 0, n);
     cudaEventRecord(e1, 0);
     int rc = TPT_OK;
     if (!tpt_cuda_ok(cudaDeviceSynchronize(), "tpt_bvh_build kernels")) rc = TPT_ERR_CUDA;
     if (rc == TPT_OK && device_ms) { float ms = 0; cudaEventElapsedTime(&ms, e0, e1); *device_ms = ms; }
+    for (size_t i = 1; i < marks.size() && rc == TPT_OK; ++i) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, marks[i - 1], marks[i]);
+        std::fprintf(stderr, "tpt_bvh_build n %d: %-28s %8.3f ms\n", n, labels[i].c_str(), ms);
+    }
+    for (cudaEvent_t e : marks) cudaEventDestroy(e);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     if (rc == TPT_OK && !tpt_cuda_ok(cudaMemcpy(out_nodes, d_nodes.p, sizeof(TptBvhNode) * (2 * (size_t)n - 1), cudaMemcpyDeviceToHost), "cudaMemcpy(nodes)"))
