@@ -53,6 +53,21 @@ def test_invalid_arguments_are_reported(tpt):
     assert lib.tpt_scene_destroy(None) == 0
 
 
+def test_bvh_build_argument_checks_and_no_cpu_path(tpt):
+    """tpt_bvh_build: null arrays / an empty list are refused; with valid arguments and no GPU it reports
+    TPT_ERR_NO_DEVICE (the host build lives in libtpt_host.so, this library has no CPU path)."""
+    lib = tpt.lib()
+    lib.tpt_bvh_build.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    bounds = np.zeros((2, 6), np.float32)
+    areas = np.ones(2, np.float32)
+    nodes = np.zeros((3, 10), np.float32)
+    assert lib.tpt_bvh_build(None, areas.ctypes.data, 2, 0, nodes.ctypes.data, None) == 1
+    assert lib.tpt_bvh_build(bounds.ctypes.data, areas.ctypes.data, 0, 0, nodes.ctypes.data, None) == 1
+    if lib.tpt_device_count() == 0:
+        assert lib.tpt_bvh_build(bounds.ctypes.data, areas.ctypes.data, 2, 0, nodes.ctypes.data, None) == 2
+        assert b"no CUDA device" in lib.tpt_last_error()
+
+
 def test_unknown_scene_and_missing_models(tpt, tmp_path):
     with pytest.raises(tpt.TptError):
         tpt.HostScene("no-such-scene", 16, 16)

@@ -159,7 +159,8 @@ def test_device_bvh_build_on_the_block_emulator(tmp_path):
     lib = C.CDLL(so)
     lib.bbh_case.argtypes = [C.c_int] * 3
     for kind in range(5):
-        for n in (1, 2, 3, 4, 5, 7, 16, 17, 33, 48, 49, 64, 65, 66, 130, 1000, 2048, 2049, 4980):     # steps by a thread (<= 64), a warp, the block (> 2048)
+        sizes = (1, 2, 3, 4, 5, 7, 16, 17, 33, 48, 49, 64, 65, 66, 130, 1000, 2049)     # steps by a thread (<= 64), a warp, ...
+        for n in sizes + ((4980,) if kind < 2 else ()):                                  # ... the whole block (> 2048)
             for smem in (200 * 1024, 4096 + 8 * 60):       # staged / in place
                 assert lib.bbh_case(kind, n, smem) == 0, (kind, n, smem)
 
