@@ -22,10 +22,12 @@ static unsigned long long g_dyn_shared[32 * 1024];
         const unsigned g_ = (unsigned)(grid);                                                                  \
         for (unsigned b_ = 0; b_ < g_; ++b_) run_block((int)(block), b_, g_, [&] { kernel(__VA_ARGS__); });    \
     } while (0)
-static int g_smem_bytes = 200 * 1024;       // the opt-in shared memory the build is told about (a case shrinks it)
+static int g_smem_bytes = 200 * 1024;       // the opt-in shared memory the build is told about (a case shrinks it: longer ranges then sort in
+                                            // "global memory" and hand their short tasks to k_bvh_finish_tasks)
 #define cudaMemcpy(dst, src, n, kind) (memcpy((dst), (src), (n)), cudaSuccess)
 #define cudaSetDevice(d) (cudaSuccess)
-#define cudaDeviceGetAttribute(p, a, d) (*(p) = g_smem_bytes, cudaSuccess)
+#define cudaDeviceGetAttribute(p, a, d) (*(p) = (a) == cudaDevAttrMultiProcessorCount ? 2 : g_smem_bytes, cudaSuccess)
+#define cudaMemsetAsync(p, v, n, st) (memset((p), (v), (n)), cudaSuccess)
 #define cudaFuncSetAttribute(f, a, v) (cudaSuccess)
 #define cudaEventCreate(p) (*(p) = reinterpret_cast<cudaEvent_t>(1), cudaSuccess)
 #define cudaEventRecord(e, s) (cudaSuccess)

@@ -60,7 +60,7 @@ def test_frame_from_device_built_trees(tpt, monkeypatch):
         img, _ = s.render("pt_full", 4)
         s.close()
         return img
-    monkeypatch.delenv("TPT_BVH_BUILD", raising=False)
+    monkeypatch.setenv("TPT_BVH_BUILD", "host")
     host_built = frame()
     monkeypatch.setenv("TPT_BVH_BUILD", "device")
     device_built = frame()

@@ -173,17 +173,82 @@ __device__ void warp_step(ss_word* v, SsRange T, SsRange* next, int* sh_next, in
     __syncwarp();
 }
 
-// One level, a block per range.  A range of at most `smem_elems` objects is sorted in shared memory together with
-// everything the sort needs (the words, the two position lists of the partition steps, the two task lists:
-// bb_smem_bytes); a longer one in place in global memory with its lists in the scratch arrays.
+// std::sort of work[0, len) by the block, starting from one introsort task with `depth` splits left: the partition
+// tree a round per level — the whole block on each long range of the round (coop_step), a warp on each middle one
+// (warp_step), a thread per short one (std_sort.cuh).  A step's two position lists take 2 ints per element of ITS
+// range (lists: 2 * len ints); cur / next: the two task lists, len / 16 + 1 entries each.
+// FORWARD (ranges too long for shared memory, sorted in place in global memory): only the steps over more than
+// `local_max` elements are done here; the shorter tasks are handed to k_bvh_finish_tasks, which sorts each of them in
+// the shared memory of a block of its own — on as many SMs as there are tasks instead of this one.
+struct SortShared { int count, next, k, is_long; int warp[2 * BB_THREADS / 32]; };
+struct LeftTask { int start, len, depth; };        // start: index into the order array
+
 __host__ __device__ inline size_t bb_smem_bytes(int n) { return (size_t)n * 16 + 2 * ((size_t)n / 16 + 1) * sizeof(SsRange); }
 
+template <bool FORWARD>
+__device__ void block_sort(ss_word* work, int len, int depth, int* lists, SsRange* cur, SsRange* next, SortShared* sh,
+                           int local_max, int base, LeftTask* left, int* n_left) {
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        if (len <= SS_THRESHOLD) sh->count = 0;
+        else { cur[0] = SsRange{0, len, depth}; sh->count = 1; }
+        sh->next = 0;
+        sh->is_long = len > BB_COOP_MIN;
+    }
+    __syncthreads();
+    if (len <= SS_THRESHOLD && tid == 0) ss_insertion_sort(work, 0, len);
+    while (sh->count > 0) {
+        const int n_tasks = sh->count;
+        if (sh->is_long) {                            // the long ones first, the whole block on each
+            int still = 0;
+            for (int t = 0; t < n_tasks; ++t) {
+                const SsRange T = cur[t];
+                if (T.last - T.first <= (FORWARD ? local_max : BB_COOP_MIN)) continue;
+                coop_step(work, T, next, &sh->next, lists + 2 * T.first, lists + 2 * T.first + (T.last - T.first), sh->warp, &sh->k);
+                still = 1;
+            }
+            if (tid == 0) sh->is_long = still;        // read again after the barriers that end the round
+        }
+        if (FORWARD) {
+            for (int t = tid; t < n_tasks; t += BB_THREADS) {
+                const SsRange T = cur[t];
+                if (T.last - T.first <= local_max) left[atomicAdd(n_left, 1)] = LeftTask{base + T.first, T.last - T.first, T.depth};
+            }
+        } else {
+            for (int t = tid >> 5; t < n_tasks; t += BB_THREADS / 32) {      // a warp on each of the middle ones
+                const SsRange T = cur[t];
+                const int l = T.last - T.first;
+                if (l > BB_WARP_MIN && l <= BB_COOP_MIN) warp_step(work, T, next, &sh->next, lists + 2 * T.first, lists + 2 * T.first + l);
+            }
+            // a thread on each of the short ones — neighbouring tasks to different WARPS: every lane walks its own
+            // data-dependent loops, and the lanes of one warp take turns on them
+            for (int t = (tid >> 5) + (BB_THREADS / 32) * (tid & 31); t < n_tasks; t += BB_THREADS) {
+                const SsRange T = cur[t];
+                if (T.last - T.first > BB_WARP_MIN) continue;
+                SsRange out[2];
+                const int k = ss_step(work, T, out);
+                for (int i = 0; i < k; ++i) next[atomicAdd(&sh->next, 1)] = out[i];
+            }
+        }
+        __syncthreads();
+        if (tid == 0) { sh->count = sh->next; sh->next = 0; }
+        SsRange* t = cur; cur = next; next = t;
+        __syncthreads();
+    }
+    __syncthreads();
+}
+
+// One level, a block per range.  A range of at most `smem_elems` objects is sorted in shared memory together with
+// everything the sort needs (the words, the two position lists of the partition steps, the two task lists:
+// bb_smem_bytes); a longer one in place in global memory with its lists in the scratch arrays — its long partition
+// steps only, the rest by k_bvh_finish_tasks.
 __global__ void __launch_bounds__(BB_THREADS) k_bvh_sort_level(const BuildRange* __restrict__ ranges, int count, const float* __restrict__ cent,
-                                                               ss_word* order, SsRange* tasks, int* lists, int smem_elems) {
+                                                               ss_word* order, SsRange* tasks, int* lists, int smem_elems, int local_max,
+                                                               LeftTask* left, int* n_left) {
     BB_DYN_SHARED(ss_word, sh_words);
     __shared__ float red[6][BB_THREADS / 32];
-    __shared__ int sh_dim, sh_count, sh_next, sh_k, sh_long;
-    __shared__ int sh_warp[2 * BB_THREADS / 32];
+    __shared__ int sh_dim;
+    __shared__ SortShared sh;
     const int tid = threadIdx.x;
     for (int r = blockIdx.x; r < count; r += gridDim.x) {
         const BuildRange R = ranges[r];
@@ -203,7 +268,7 @@ __global__ void __launch_bounds__(BB_THREADS) k_bvh_sort_level(const BuildRange*
                 lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
                 hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
             }
-        __syncthreads();                  // the previous range of this block is done with `red` and the task lists
+        __syncthreads();                  // the previous range of this block is done with `red`
         if ((tid & 31) == 0)
             for (int c = 0; c < 3; ++c) { red[c][tid >> 5] = lo[c]; red[3 + c][tid >> 5] = hi[c]; }
         __syncthreads();
@@ -220,56 +285,35 @@ __global__ void __launch_bounds__(BB_THREADS) k_bvh_sort_level(const BuildRange*
             const uint32_t obj = (uint32_t)slice[i];
             work[i] = ((ss_word)centroid_key(cent, obj, dim) << 32) | obj;
         }
-        // std::sort of the range: the partition tree a round per level — the whole block on each long range of the
-        // round (coop_step), a warp on each middle one (warp_step), a thread per short one (std_sort.cuh).  A step's two
-        // position lists take 2 ints per element of ITS range; the two task lists of this range n / 16 + 1 entries each
-        // (in global memory at 2 * (start / 16 + r)).
-        const int cap = R.n / 16 + 1;
-        int* lists_r = staged ? reinterpret_cast<int*>(sh_words + R.n) : lists + 2 * (size_t)R.start;
-        SsRange* cur = staged ? reinterpret_cast<SsRange*>(lists_r + 2 * (size_t)R.n) : tasks + 2 * ((size_t)R.start / 16 + r);
-        SsRange* next = cur + cap;
-        if (tid == 0) {
-            if (R.n <= SS_THRESHOLD) { sh_count = 0; }
-            else { cur[0] = SsRange{0, R.n, 2 * ss_lg(R.n)}; sh_count = 1; }
-            sh_next = 0;
-            sh_long = R.n > BB_COOP_MIN;
-        }
-        __syncthreads();
-        if (R.n <= SS_THRESHOLD && tid == 0) ss_insertion_sort(work, 0, R.n);
-        while (sh_count > 0) {
-            const int n_tasks = sh_count;
-            if (sh_long) {                                // the long ones first, the whole block on each
-                int still = 0;
-                for (int t = 0; t < n_tasks; ++t) {
-                    const SsRange T = cur[t];
-                    if (T.last - T.first <= BB_COOP_MIN) continue;
-                    coop_step(work, T, next, &sh_next, lists_r + 2 * T.first, lists_r + 2 * T.first + (T.last - T.first), sh_warp, &sh_k);
-                    still = 1;
-                }
-                if (tid == 0) sh_long = still;            // read again after the barriers that end the round
-            }
-            for (int t = tid >> 5; t < n_tasks; t += BB_THREADS / 32) {      // a warp on each of the middle ones
-                const SsRange T = cur[t];
-                const int len = T.last - T.first;
-                if (len > BB_WARP_MIN && len <= BB_COOP_MIN) warp_step(work, T, next, &sh_next, lists_r + 2 * T.first, lists_r + 2 * T.first + len);
-            }
-            // a thread on each of the short ones — neighbouring tasks to different WARPS: every lane walks its own
-            // data-dependent loops, and the lanes of one warp take turns on them
-            for (int t = (tid >> 5) + (BB_THREADS / 32) * (tid & 31); t < n_tasks; t += BB_THREADS) {
-                const SsRange T = cur[t];
-                if (T.last - T.first > BB_WARP_MIN) continue;
-                SsRange out[2];
-                const int k = ss_step(work, T, out);
-                for (int i = 0; i < k; ++i) next[atomicAdd(&sh_next, 1)] = out[i];
-            }
-            __syncthreads();
-            if (tid == 0) { sh_count = sh_next; sh_next = 0; }
-            SsRange* t = cur; cur = next; next = t;
-            __syncthreads();
-        }
-        __syncthreads();
-        if (work != slice)
+        const int cap = R.n / 16 + 1;      // in global memory the two task lists of this range sit at 2 * (start / 16 + r)
+        if (staged) {
+            int* lists_r = reinterpret_cast<int*>(sh_words + R.n);
+            SsRange* cur = reinterpret_cast<SsRange*>(lists_r + 2 * (size_t)R.n);
+            block_sort<false>(work, R.n, 2 * ss_lg(R.n), lists_r, cur, cur + cap, &sh, 0, 0, nullptr, nullptr);
             for (int i = tid; i < R.n; i += BB_THREADS) slice[i] = work[i];
+        } else {
+            SsRange* cur = tasks + 2 * ((size_t)R.start / 16 + r);
+            block_sort<true>(work, R.n, 2 * ss_lg(R.n), lists + 2 * (size_t)R.start, cur, cur + cap, &sh, local_max, R.start, left, n_left);
+        }
+    }
+}
+
+// The tasks k_bvh_sort_level handed on (at most `smem_elems` elements each, with the depth their introsort loop had
+// left): a block per task, sorted in shared memory.
+__global__ void __launch_bounds__(BB_THREADS) k_bvh_finish_tasks(const LeftTask* __restrict__ left, const int* __restrict__ n_left, ss_word* order) {
+    BB_DYN_SHARED(ss_word, sh_words);
+    __shared__ SortShared sh;
+    const int tid = threadIdx.x;
+    const int count = *n_left;
+    for (int t = blockIdx.x; t < count; t += gridDim.x) {
+        const LeftTask T = left[t];
+        ss_word* slice = order + T.start;
+        __syncthreads();                  // the previous task of this block has been written back
+        for (int i = tid; i < T.len; i += BB_THREADS) sh_words[i] = slice[i];
+        int* lists_r = reinterpret_cast<int*>(sh_words + T.len);
+        SsRange* cur = reinterpret_cast<SsRange*>(lists_r + 2 * (size_t)T.len);
+        block_sort<false>(sh_words, T.len, T.depth, lists_r, cur, cur + T.len / 16 + 1, &sh, 0, 0, nullptr, nullptr);
+        for (int i = tid; i < T.len; i += BB_THREADS) slice[i] = sh_words[i];
     }
 }
 
@@ -383,11 +427,18 @@ extern "C" int tpt_bvh_build(const float* bounds, const float* areas, int n, int
     int smem_elems = std::max(0, (smem_optin - 4096) / 18);     // the longest range bb_smem_bytes() of which fit
     while (smem_elems > 0 && bb_smem_bytes(smem_elems) > (size_t)std::max(0, smem_optin - 4096)) --smem_elems;
     TPT_CUDA(cudaFuncSetAttribute(k_bvh_sort_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bb_smem_bytes(smem_elems)));
+    TPT_CUDA(cudaFuncSetAttribute(k_bvh_finish_tasks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bb_smem_bytes(smem_elems)));
+    if (smem_elems < BB_COOP_MIN) { tpt_set_error("tpt_bvh_build: less shared memory per block than the sort is written for"); return TPT_ERR_INVALID; }
+    // tasks of a long range that go to k_bvh_finish_tasks: short enough for several blocks per SM
+    const int local_max = std::min(smem_elems, 4096);
+    int num_sms = 1;
+    TPT_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
 
     DevBlock d_bounds(sizeof(float) * 6 * n), d_areas(sizeof(float) * n), d_cent(sizeof(float) * 3 * n), d_order(sizeof(ss_word) * n),
         d_table(sizeof(BuildRange) * table.size()), d_nodes(sizeof(TptBvhNode) * (2 * (size_t)n - 1)),
-        d_tasks(sizeof(SsRange) * 2 * ((size_t)n / 16 + widest + 2)), d_lists(sizeof(int) * 2 * (size_t)n);
-    for (const DevBlock* b : {&d_bounds, &d_areas, &d_cent, &d_order, &d_table, &d_nodes, &d_tasks, &d_lists})
+        d_tasks(sizeof(SsRange) * 2 * ((size_t)n / 16 + widest + 2)), d_lists(sizeof(int) * 2 * (size_t)n),
+        d_left(sizeof(LeftTask) * ((size_t)n / 16 + 2)), d_n_left(sizeof(int));
+    for (const DevBlock* b : {&d_bounds, &d_areas, &d_cent, &d_order, &d_table, &d_nodes, &d_tasks, &d_lists, &d_left, &d_n_left})
         if (!b->p) return TPT_ERR_OOM;
     TPT_CUDA(cudaMemcpy(d_bounds.p, bounds, sizeof(float) * 6 * n, cudaMemcpyHostToDevice));
     TPT_CUDA(cudaMemcpy(d_areas.p, areas, sizeof(float) * n, cudaMemcpyHostToDevice));
@@ -420,8 +471,12 @@ extern "C" int tpt_bvh_build(const float* bounds, const float* areas, int n, int
             BB_LAUNCH(k_bvh_sort_level_small, (count + per_block - 1) / per_block, BB_SMALL_THREADS, 0, lr, count, d_cent.as<float>(), d_order.as<ss_word>());
         } else {
             const bool staged = longest <= smem_elems;      // the level's ranges fit shared memory (they differ by one element at most)
+            if (!staged) cudaMemsetAsync(d_n_left.p, 0, sizeof(int), 0);
             BB_LAUNCH(k_bvh_sort_level, std::min(count, 65535), BB_THREADS, staged ? bb_smem_bytes(longest) : 0, lr, count, d_cent.as<float>(),
-                      d_order.as<ss_word>(), d_tasks.as<SsRange>(), d_lists.as<int>(), staged ? smem_elems : 0);
+                      d_order.as<ss_word>(), d_tasks.as<SsRange>(), d_lists.as<int>(), staged ? smem_elems : 0, local_max, d_left.as<LeftTask>(),
+                      d_n_left.as<int>());
+            if (!staged)
+                BB_LAUNCH(k_bvh_finish_tasks, 4 * num_sms, BB_THREADS, bb_smem_bytes(local_max), d_left.as<LeftTask>(), d_n_left.as<int>(), d_order.as<ss_word>());
         }
         mark(longest <= BB_SMALL_N ? "sort (thread per range)" : "sort (block per range)", lv, longest);
     }

@@ -31,13 +31,20 @@ BVHAccel::BVHAccel(std::vector<Object*> p, int maxPrims, SplitMethod method)
 }
 
 // Which lists are built on the GPU (tpt_bvh_build, csrc/bvh_build.cu) instead of by buildInPlace below: those with at
-// least TPT_BVH_BUILD_MIN objects; TPT_BVH_BUILD=device is short for a minimum of 1, and without either variable every
-// list is built on the host (for the meshes of BASELINE — 5 K triangles at most — the two take about as long, and
-// the host build needs no device).  Both produce the node array of the reference recursion.
+// least DeviceBuildMin() objects.  Both produce the node array of the reference recursion, so this is a question of
+// time only (B200 + 16 host cores, profiles/r05i_bvh_build.log: 5 K objects 0.74 ms of kernels against 1.8 ms, 28 K
+// 1.6 against 8.3, 300 K 10.6 against 77; the call adds the copies of the boxes and the nodes): without a setting,
+// lists of 16 384 objects and more go to the device when there is one — every BASELINE mesh (5 K triangles at most)
+// stays on the host, which needs no device to construct a scene.  TPT_BVH_BUILD=device / host forces one side for
+// every list, TPT_BVH_BUILD_MIN=<objects> moves the threshold.
 int BVHAccel::DeviceBuildMin() {
     if (const char* e = std::getenv("TPT_BVH_BUILD_MIN")) return std::max(1, std::atoi(e));
-    if (const char* e = std::getenv("TPT_BVH_BUILD")) if (std::string(e) == "device") return 1;
-    return std::numeric_limits<int>::max();
+    if (const char* e = std::getenv("TPT_BVH_BUILD")) {
+        if (std::string(e) == "device") return 1;
+        if (std::string(e) == "host") return std::numeric_limits<int>::max();
+    }
+    static const bool have_device = tpt_device_count() > 0;
+    return have_device ? 16384 : std::numeric_limits<int>::max();
 }
 
 void BVHAccel::buildOnDevice() {
