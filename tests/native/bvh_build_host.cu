@@ -86,6 +86,11 @@ float Rnd() { g_rng ^= g_rng << 13; g_rng ^= g_rng >> 17; g_rng ^= g_rng << 5; r
 // equal extents: the maxExtent tie rule); 4: coordinates on a coarse grid with zeros of both signs
 extern "C" int bbh_case(int kind, int n, int smem_bytes) {
     g_smem_bytes = smem_bytes;
+    // the larger setting also lifts the build's own limits, so that whole ranges of several thousand objects are sorted
+    // by one block in "shared memory" (block-wide partition steps there); the smaller one runs the defaults: ranges
+    // above 1 024 objects in place in global memory, their tasks handed to k_bvh_finish_tasks
+    if (smem_bytes >= 200 * 1024) { setenv("TPT_BVH_STAGE_MAX", "11000", 1); setenv("TPT_BVH_LOCAL_MAX", "4096", 1); }
+    else { unsetenv("TPT_BVH_STAGE_MAX"); unsetenv("TPT_BVH_LOCAL_MAX"); }
     std::vector<float> bounds(6 * (size_t)n), areas(n);
     for (int i = 0; i < n; ++i) {
         float c[3], h[3] = {1.0f, 1.0f, 0.5f};

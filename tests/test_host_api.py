@@ -161,7 +161,7 @@ def test_device_bvh_build_on_the_block_emulator(tmp_path):
     for kind in range(5):
         sizes = (1, 2, 3, 4, 5, 7, 16, 17, 33, 48, 49, 64, 65, 66, 130, 1000, 2049)     # steps by a thread (<= 64), a warp, ...
         for n in sizes + ((4980,) if kind < 2 else ()):                                  # ... the whole block (> 2048)
-            for smem in (200 * 1024, 4096 + 18 * 2100):    # every range in shared memory / those above 2 090 objects in place
+            for smem in (200 * 1024, 4096 + 18 * 2100):    # every range in shared memory / the defaults: above 1 024 objects in place
                 assert lib.bbh_case(kind, n, smem) == 0, (kind, n, smem)
 
 

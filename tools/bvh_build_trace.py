@@ -8,7 +8,8 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ["TPT_BVH_BUILD_TRACE"] = "1"
+if not os.environ.get("TPT_BVH_NO_TRACE"):
+    os.environ["TPT_BVH_BUILD_TRACE"] = "1"
 import tpt_b200 as T  # noqa: E402
 
 lib = T.lib()
@@ -21,7 +22,7 @@ for n in [int(a) for a in sys.argv[1:]] or [4968]:
     areas = rng.rand(n).astype(np.float32)
     nodes = np.zeros((2 * n - 1, 10), np.float32)
     ms = C.c_double(-1)
-    for rep in range(2):          # the second call has its work buffers from the cache
+    for rep in range(3):          # the later calls have their work buffers from the cache
         sys.stderr.write("-- n %d, call %d\n" % (n, rep))
         assert lib.tpt_bvh_build(bounds.ctypes.data, areas.ctypes.data, n, 0, nodes.ctypes.data, C.byref(ms)) == 0
-    print("n", n, "kernels %.3f ms" % ms.value)
+    print("n", n, "kernels %.3f ms" % ms.value, "STAGE_MAX", os.environ.get("TPT_BVH_STAGE_MAX"), "LOCAL_MAX", os.environ.get("TPT_BVH_LOCAL_MAX"))

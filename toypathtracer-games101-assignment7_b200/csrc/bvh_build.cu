@@ -193,7 +193,7 @@ __device__ void block_sort(ss_word* work, int len, int depth, int* lists, SsRang
         if (len <= SS_THRESHOLD) sh->count = 0;
         else { cur[0] = SsRange{0, len, depth}; sh->count = 1; }
         sh->next = 0;
-        sh->is_long = len > BB_COOP_MIN;
+        sh->is_long = FORWARD || len > BB_COOP_MIN;     // FORWARD: len > smem_elems >= local_max
     }
     __syncthreads();
     if (len <= SS_THRESHOLD && tid == 0) ss_insertion_sort(work, 0, len);
@@ -429,8 +429,16 @@ extern "C" int tpt_bvh_build(const float* bounds, const float* areas, int n, int
     TPT_CUDA(cudaFuncSetAttribute(k_bvh_sort_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bb_smem_bytes(smem_elems)));
     TPT_CUDA(cudaFuncSetAttribute(k_bvh_finish_tasks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bb_smem_bytes(smem_elems)));
     if (smem_elems < BB_COOP_MIN) { tpt_set_error("tpt_bvh_build: less shared memory per block than the sort is written for"); return TPT_ERR_INVALID; }
-    // tasks of a long range that go to k_bvh_finish_tasks: short enough for several blocks per SM
-    const int local_max = std::min(smem_elems, 4096);
+    // How long a range one block still sorts on its own, and how long a task a longer range hands to k_bvh_finish_tasks.
+    // Shared memory would take ~12 K elements, but a block is one SM: splitting earlier puts the levels of a mesh on
+    // more SMs at the price of a few partition steps in global memory (profiles/r05j_stage_sweep.log: 5 K objects
+    // 0.72 ms at 12 K / 4 K, 0.59 at 1 K / 1 K, 0.55 at 1 K / 512; 300 K objects 10.2 ms at 4 K / 4 K, 12.5 at 1 K / 1 K).
+    int local_max = n >= (1 << 16) ? 4096 : 1024;     // 131 K objects: 4.8 ms at 4 K, 5.6 at 1 K (r05k_sizes.log); 28 K: 1.56 / 1.41
+    smem_elems = std::min(smem_elems, local_max);
+    // measurement aids: TPT_BVH_STAGE_MAX (longest range one block sorts on its own), TPT_BVH_LOCAL_MAX (longest task handed on)
+    if (const char* e = std::getenv("TPT_BVH_STAGE_MAX")) smem_elems = std::max(BB_SMALL_N, std::min(smem_optin / 18 - 256, std::atoi(e)));
+    if (const char* e = std::getenv("TPT_BVH_LOCAL_MAX")) local_max = std::max(BB_SMALL_N, std::atoi(e));
+    local_max = std::min(local_max, smem_elems);
     int num_sms = 1;
     TPT_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
 

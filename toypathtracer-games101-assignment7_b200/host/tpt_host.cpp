@@ -32,8 +32,8 @@ BVHAccel::BVHAccel(std::vector<Object*> p, int maxPrims, SplitMethod method)
 
 // Which lists are built on the GPU (tpt_bvh_build, csrc/bvh_build.cu) instead of by buildInPlace below: those with at
 // least DeviceBuildMin() objects.  Both produce the node array of the reference recursion, so this is a question of
-// time only (B200 + 16 host cores, profiles/r05i_bvh_build.log: 5 K objects 0.74 ms of kernels against 1.8 ms, 28 K
-// 1.6 against 8.3, 300 K 10.6 against 77; the call adds the copies of the boxes and the nodes): without a setting,
+// time only (B200 + 16 host cores, profiles/r05k_bvh_build.log: 5 K objects 0.60 ms of kernels against 1.8 ms, 28 K
+// 1.5 against 7.5, 300 K 10.5 against 75; the call adds the copies of the boxes and the nodes): without a setting,
 // lists of 16 384 objects and more go to the device when there is one — every BASELINE mesh (5 K triangles at most)
 // stays on the host, which needs no device to construct a scene.  TPT_BVH_BUILD=device / host forces one side for
 // every list, TPT_BVH_BUILD_MIN=<objects> moves the threshold.
