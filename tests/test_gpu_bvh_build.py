@@ -8,9 +8,26 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import ROOT
+from conftest import ROOT, desc_from_golden
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("scene", ["standard", "smooth", "silver", "refractive", "occlusion", "bunny"])
+def test_device_built_scenes_are_the_compiled_references_trees(tpt, scene, monkeypatch):
+    """Every BVH of the fixture scenes (top level and meshes) built on the device through the host API
+    (TPT_BVH_BUILD=device), flattened, against the golden flat files written from the COMPILED REFERENCE's own trees:
+    node for node, bit for bit — the check tests/test_host_api.py makes for the host build."""
+    from oracle import bindings as B
+    monkeypatch.setenv("TPT_BVH_BUILD", "device")
+    hs = tpt.HostScene(scene, 784, 784)
+    mine = B.desc_arrays(B.SceneDesc.from_buffer_copy(bytes(hs.desc)))
+    theirs = B.desc_arrays(desc_from_golden(scene)[0])
+    assert mine["header"] == theirs["header"]
+    for key in ("objects", "top_nodes", "mesh_nodes", "tris", "spheres", "materials", "emissive"):
+        assert mine[key].shape == theirs[key].shape, key
+        assert (mine[key] == theirs[key]).all(), key
+    hs.close()
 
 
 def test_device_build_equals_the_reference_recursion(tpt, tmp_path):
