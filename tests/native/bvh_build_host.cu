@@ -39,6 +39,7 @@ bool tpt_cuda_ok(cudaError_t e, const char* what) { if (e != cudaSuccess) tpt_se
 void* tpt_dev_alloc(size_t bytes) { return calloc(1, bytes ? bytes : 1); }
 void tpt_dev_free(void* p) { free(p); }
 
+#define BB_LONG_THREADS 256                 /* the emulator runs blocks of at most 256 threads; the product launches 1024 here */
 #include "bvh_build.cu"
 
 // ---- the reference recursion over indices ---------------------------------------------------------------

@@ -34,7 +34,11 @@ struct BuildRange { int start, n, self; };
 #define BB_LAUNCH(kernel, grid, block, smem, ...) kernel<<<(grid), (block), (smem)>>>(__VA_ARGS__)
 #define BB_DYN_SHARED(type, name) extern __shared__ type name[]
 #endif
-#define BB_THREADS 256           /* block of the block-per-range kernel */
+#define BB_THREADS 256           /* block of the block-per-range kernels: ranges sorted in shared memory ... */
+#ifndef BB_LONG_THREADS
+#define BB_LONG_THREADS 1024     /* ... and ranges whose long partition steps run in global memory (more loads in flight) */
+#endif
+#define BB_MAX_WARPS 32
 #define BB_SMALL_THREADS 256      /* ... by a warp: eight ranges per block */
 #define BB_SMALL_N 48            /* a level whose ranges are at most this long is sorted a warp per range ... */
 #define BB_COOP_MIN 2048         /* partition steps over more elements than this are done by the whole block ... */
@@ -83,7 +87,7 @@ __device__ __forceinline__ void finish_step(ss_word* v, SsRange T, int cut, SsRa
 // ... by the whole block (long ranges): a chunk of positions per thread, the list offsets from a block scan over the
 // per-thread counts.  sh_warp: 2 x 8 warp totals; sh_k: the swap count.
 __device__ void coop_step(ss_word* v, SsRange T, SsRange* next, int* sh_next, int* lpos, int* rpos, int* sh_warp, int* sh_k) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x;
     if (T.depth == 0) {                       // depth limit reached: heap sort, as the serial step does
         if (tid == 0) ss_heap_sort(v + T.first, T.last - T.first);
         __syncthreads();
@@ -93,7 +97,7 @@ __device__ void coop_step(ss_word* v, SsRange T, SsRange* next, int* sh_next, in
     __syncthreads();
     const ss_word pivot = v[T.first];
     const int m = T.last - T.first - 1;       // the scans run over first + 1 .. last - 1
-    const int chunk = (m + BB_THREADS - 1) / BB_THREADS;
+    const int chunk = (m + nt - 1) / nt;
     const int p0 = T.first + 1 + min(m, tid * chunk), p1 = T.first + 1 + min(m, (tid + 1) * chunk);
     int cl = 0, cr = 0;
     for (int p = p0; p < p1; ++p) {
@@ -106,11 +110,11 @@ __device__ void coop_step(ss_word* v, SsRange T, SsRange* next, int* sh_next, in
         const int a = __shfl_up_sync(0xffffffffu, il, o), b = __shfl_up_sync(0xffffffffu, ir, o);
         if (lane >= o) { il += a; ir += b; }
     }
-    if (lane == 31) { sh_warp[warp] = il; sh_warp[BB_THREADS / 32 + warp] = ir; }
+    if (lane == 31) { sh_warp[warp] = il; sh_warp[BB_MAX_WARPS + warp] = ir; }
     __syncthreads();
     int ol = il - cl, orr = ir - cr, tot_l = 0, tot_r = 0;
-    for (int w = 0; w < BB_THREADS / 32; ++w) {
-        const int a = sh_warp[w], b = sh_warp[BB_THREADS / 32 + w];
+    for (int w = 0; w < nt / 32; ++w) {
+        const int a = sh_warp[w], b = sh_warp[BB_MAX_WARPS + w];
         if (w < warp) { ol += a; orr += b; }
         tot_l += a; tot_r += b;
     }
@@ -122,13 +126,13 @@ __device__ void coop_step(ss_word* v, SsRange T, SsRange* next, int* sh_next, in
     __syncthreads();
     const int len = min(tot_l, tot_r);
     int cnt = 0;
-    for (int k = tid; k < len; k += BB_THREADS) cnt += lpos[k] < rpos[k];
+    for (int k = tid; k < len; k += nt) cnt += lpos[k] < rpos[k];
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if (lane == 0 && cnt) atomicAdd(sh_k, cnt);
     __syncthreads();
     const int K = *sh_k;
     const int cut = partition_cut(lpos, rpos, tot_l, K, T.last);
-    for (int k = tid; k < K; k += BB_THREADS) ss_swap(v, lpos[k], rpos[k]);
+    for (int k = tid; k < K; k += nt) ss_swap(v, lpos[k], rpos[k]);
     __syncthreads();
     if (tid == 0) finish_step(v, T, cut, next, sh_next);
     __syncthreads();                          // the lists, the warp totals and the counter are free again
@@ -180,7 +184,7 @@ __device__ void warp_step(ss_word* v, SsRange T, SsRange* next, int* sh_next, in
 // FORWARD (ranges too long for shared memory, sorted in place in global memory): only the steps over more than
 // `local_max` elements are done here; the shorter tasks are handed to k_bvh_finish_tasks, which sorts each of them in
 // the shared memory of a block of its own — on as many SMs as there are tasks instead of this one.
-struct SortShared { int count, next, k, is_long; int warp[2 * BB_THREADS / 32]; };
+struct SortShared { int count, next, k, is_long; int warp[2 * BB_MAX_WARPS]; };
 struct LeftTask { int start, len, depth; };        // start: index into the order array
 
 __host__ __device__ inline size_t bb_smem_bytes(int n) { return (size_t)n * 16 + 2 * ((size_t)n / 16 + 1) * sizeof(SsRange); }
@@ -188,7 +192,7 @@ __host__ __device__ inline size_t bb_smem_bytes(int n) { return (size_t)n * 16 +
 template <bool FORWARD>
 __device__ void block_sort(ss_word* work, int len, int depth, int* lists, SsRange* cur, SsRange* next, SortShared* sh,
                            int local_max, int base, LeftTask* left, int* n_left) {
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, nt = blockDim.x;
     if (tid == 0) {
         if (len <= SS_THRESHOLD) sh->count = 0;
         else { cur[0] = SsRange{0, len, depth}; sh->count = 1; }
@@ -210,19 +214,19 @@ __device__ void block_sort(ss_word* work, int len, int depth, int* lists, SsRang
             if (tid == 0) sh->is_long = still;        // read again after the barriers that end the round
         }
         if (FORWARD) {
-            for (int t = tid; t < n_tasks; t += BB_THREADS) {
+            for (int t = tid; t < n_tasks; t += nt) {
                 const SsRange T = cur[t];
                 if (T.last - T.first <= local_max) left[atomicAdd(n_left, 1)] = LeftTask{base + T.first, T.last - T.first, T.depth};
             }
         } else {
-            for (int t = tid >> 5; t < n_tasks; t += BB_THREADS / 32) {      // a warp on each of the middle ones
+            for (int t = tid >> 5; t < n_tasks; t += nt / 32) {      // a warp on each of the middle ones
                 const SsRange T = cur[t];
                 const int l = T.last - T.first;
                 if (l > BB_WARP_MIN && l <= BB_COOP_MIN) warp_step(work, T, next, &sh->next, lists + 2 * T.first, lists + 2 * T.first + l);
             }
             // a thread on each of the short ones — neighbouring tasks to different WARPS: every lane walks its own
             // data-dependent loops, and the lanes of one warp take turns on them
-            for (int t = (tid >> 5) + (BB_THREADS / 32) * (tid & 31); t < n_tasks; t += BB_THREADS) {
+            for (int t = (tid >> 5) + (nt / 32) * (tid & 31); t < n_tasks; t += nt) {
                 const SsRange T = cur[t];
                 if (T.last - T.first > BB_WARP_MIN) continue;
                 SsRange out[2];
@@ -242,21 +246,21 @@ __device__ void block_sort(ss_word* work, int len, int depth, int* lists, SsRang
 // everything the sort needs (the words, the two position lists of the partition steps, the two task lists:
 // bb_smem_bytes); a longer one in place in global memory with its lists in the scratch arrays — its long partition
 // steps only, the rest by k_bvh_finish_tasks.
-__global__ void __launch_bounds__(BB_THREADS) k_bvh_sort_level(const BuildRange* __restrict__ ranges, int count, const float* __restrict__ cent,
+__global__ void __launch_bounds__(BB_LONG_THREADS > BB_THREADS ? BB_LONG_THREADS : BB_THREADS) k_bvh_sort_level(const BuildRange* __restrict__ ranges, int count, const float* __restrict__ cent,
                                                                ss_word* order, SsRange* tasks, int* lists, int smem_elems, int local_max,
                                                                LeftTask* left, int* n_left) {
     BB_DYN_SHARED(ss_word, sh_words);
-    __shared__ float red[6][BB_THREADS / 32];
+    __shared__ float red[6][BB_MAX_WARPS];
     __shared__ int sh_dim;
     __shared__ SortShared sh;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, nt = blockDim.x;
     for (int r = blockIdx.x; r < count; r += gridDim.x) {
         const BuildRange R = ranges[r];
         if (R.n <= 2) continue;           // two objects are split as they stand (BVH.cpp:46-50)
         ss_word* slice = order + R.start;
         // centroid bounds of the range -> the axis it sorts by
         float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-        for (int i = tid; i < R.n; i += BB_THREADS) {
+        for (int i = tid; i < R.n; i += nt) {
             const uint32_t obj = (uint32_t)slice[i];
             for (int c = 0; c < 3; ++c) {
                 const float v = cent[3 * (size_t)obj + c];
@@ -273,7 +277,7 @@ __global__ void __launch_bounds__(BB_THREADS) k_bvh_sort_level(const BuildRange*
             for (int c = 0; c < 3; ++c) { red[c][tid >> 5] = lo[c]; red[3 + c][tid >> 5] = hi[c]; }
         __syncthreads();
         if (tid == 0) {
-            for (int w = 1; w < BB_THREADS / 32; ++w)
+            for (int w = 1; w < nt / 32; ++w)
                 for (int c = 0; c < 3; ++c) { lo[c] = fminf(lo[c], red[c][w]); hi[c] = fmaxf(hi[c], red[3 + c][w]); }
             sh_dim = widest_axis(lo, hi);
         }
@@ -281,7 +285,7 @@ __global__ void __launch_bounds__(BB_THREADS) k_bvh_sort_level(const BuildRange*
         const int dim = sh_dim;
         const bool staged = R.n <= smem_elems;
         ss_word* work = staged ? sh_words : slice;
-        for (int i = tid; i < R.n; i += BB_THREADS) {
+        for (int i = tid; i < R.n; i += nt) {
             const uint32_t obj = (uint32_t)slice[i];
             work[i] = ((ss_word)centroid_key(cent, obj, dim) << 32) | obj;
         }
@@ -290,7 +294,7 @@ __global__ void __launch_bounds__(BB_THREADS) k_bvh_sort_level(const BuildRange*
             int* lists_r = reinterpret_cast<int*>(sh_words + R.n);
             SsRange* cur = reinterpret_cast<SsRange*>(lists_r + 2 * (size_t)R.n);
             block_sort<false>(work, R.n, 2 * ss_lg(R.n), lists_r, cur, cur + cap, &sh, 0, 0, nullptr, nullptr);
-            for (int i = tid; i < R.n; i += BB_THREADS) slice[i] = work[i];
+            for (int i = tid; i < R.n; i += nt) slice[i] = work[i];
         } else {
             SsRange* cur = tasks + 2 * ((size_t)R.start / 16 + r);
             block_sort<true>(work, R.n, 2 * ss_lg(R.n), lists + 2 * (size_t)R.start, cur, cur + cap, &sh, local_max, R.start, left, n_left);
@@ -480,7 +484,9 @@ extern "C" int tpt_bvh_build(const float* bounds, const float* areas, int n, int
         } else {
             const bool staged = longest <= smem_elems;      // the level's ranges fit shared memory (they differ by one element at most)
             if (!staged) cudaMemsetAsync(d_n_left.p, 0, sizeof(int), 0);
-            BB_LAUNCH(k_bvh_sort_level, std::min(count, 65535), BB_THREADS, staged ? bb_smem_bytes(longest) : 0, lr, count, d_cent.as<float>(),
+            // 1024 threads where a block walks a long range in global memory (more loads in flight: 300 K objects 10.4 -> 8.8 ms;
+            // a 5 K range is no faster for it, r05o_sizes.log)
+            BB_LAUNCH(k_bvh_sort_level, std::min(count, 65535), !staged && longest >= 16384 ? BB_LONG_THREADS : BB_THREADS, staged ? bb_smem_bytes(longest) : 0, lr, count, d_cent.as<float>(),
                       d_order.as<ss_word>(), d_tasks.as<SsRange>(), d_lists.as<int>(), staged ? smem_elems : 0, local_max, d_left.as<LeftTask>(),
                       d_n_left.as<int>());
             if (!staged)
