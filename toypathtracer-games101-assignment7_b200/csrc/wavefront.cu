@@ -979,6 +979,22 @@ int wavefront_render(TptScene* s, const RenderArgs& a, float* d_radiance, float*
         TPT_CUDA(cudaFuncSetAttribute(k_path<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
         TPT_CUDA(cudaFuncSetAttribute(k_shadow_q, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
     }
+    // measurement aid: TPT_WF_CARVEOUT="<k_path %>,<strategy kernels %>" — preferred shared-memory carveout of the unified
+    // L1 / shared memory, in percent of the largest one (left to the driver otherwise: DESIGN.md section 10)
+    if (const char* e = getenv("TPT_WF_CARVEOUT")) {
+        int cp = -1, cs = -1;
+        sscanf(e, "%d,%d", &cp, &cs);
+        if (cp >= 0) {
+            TPT_CUDA(cudaFuncSetAttribute(k_path<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cp));
+            TPT_CUDA(cudaFuncSetAttribute(k_path<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cp));
+        }
+        if (cs >= 0) {
+            TPT_CUDA(cudaFuncSetAttribute(k_expand, cudaFuncAttributePreferredSharedMemoryCarveout, cs));
+            TPT_CUDA(cudaFuncSetAttribute(k_connect, cudaFuncAttributePreferredSharedMemoryCarveout, cs));
+            TPT_CUDA(cudaFuncSetAttribute(k_shadow_q, cudaFuncAttributePreferredSharedMemoryCarveout, cs));
+            TPT_CUDA(cudaFuncSetAttribute(k_mis, cudaFuncAttributePreferredSharedMemoryCarveout, cs));
+        }
+    }
     const int grid = std::max(1, std::min((S + 255) / 256, s->num_sms * 8));
     const int pgrid = s->num_sms * 8;      // strategy kernels: persistent, sized to the machine
     WfCounters init;
