@@ -227,7 +227,8 @@ typedef struct TptBvhNode {
  * as pMin.xyz pMax.xyz; areas: n floats, Object::getArea().  out_nodes: 2n - 1 nodes in the order the reference's
  * recursion appends them (pre-order, left subtree first; node 0 is the root), each with the reference's child
  * indices, leaf object, box and area bit for bit — including where std::sort leaves objects whose centroids tie on
- * the split axis, which decides which of two hits at equal distance the traversal reports.  device_ms (may be NULL):
+ * the split axis, which decides which of two hits at equal distance the traversal reports.  device < 0: the calling
+ * thread's current CUDA device.  device_ms (may be NULL):
  * CUDA-event time of the kernels.  Host buffers; NaN coordinates are outside the contract (the reference's comparator
  * is not an ordering for them). */
 int tpt_bvh_build(const float* bounds, const float* areas, int n, int device, TptBvhNode* out_nodes, double* device_ms);

@@ -403,6 +403,7 @@ extern "C" int tpt_bvh_build(const float* bounds, const float* areas, int n, int
     if (!bounds || !areas || !out_nodes || n < 1 || n > (1 << 28)) { tpt_set_error("tpt_bvh_build: null array or object count outside [1, 2^28]"); return TPT_ERR_INVALID; }
     const int n_dev = tpt_device_count();
     if (n_dev <= 0) { tpt_set_error("tpt_bvh_build: no CUDA device (there is no CPU path in this library)"); return TPT_ERR_NO_DEVICE; }
+    if (device < 0) TPT_CUDA(cudaGetDevice(&device));       // the calling thread's current device
     if (device < 0 || device >= n_dev) { tpt_set_error("tpt_bvh_build: device index out of range"); return TPT_ERR_INVALID; }
     TPT_CUDA(cudaSetDevice(device));
 

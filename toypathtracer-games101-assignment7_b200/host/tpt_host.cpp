@@ -33,10 +33,11 @@ BVHAccel::BVHAccel(std::vector<Object*> p, int maxPrims, SplitMethod method)
 // Which lists are built on the GPU (tpt_bvh_build, csrc/bvh_build.cu) instead of by buildInPlace below: those with at
 // least DeviceBuildMin() objects.  Both produce the node array of the reference recursion, so this is a question of
 // time only (B200 + 16 host cores, profiles/r05k_bvh_build.log: 5 K objects 0.60 ms of kernels against 1.8 ms, 28 K
-// 1.5 against 7.5, 300 K 10.5 against 75; the call adds the copies of the boxes and the nodes): without a setting,
-// lists of 16 384 objects and more go to the device when there is one — every BASELINE mesh (5 K triangles at most)
-// stays on the host, which needs no device to construct a scene.  TPT_BVH_BUILD=device / host forces one side for
-// every list, TPT_BVH_BUILD_MIN=<objects> moves the threshold.
+// 1.5 against 7.5, 300 K 8.8 against 75; the call adds the copies of the boxes and the nodes, 1.4-1.7 ms in all at
+// 5 K): without a setting, lists of 4 096 objects and more go to the device when there is one — of the BASELINE
+// scenes that is the bunny; the Cornell meshes (12 triangles at most) and every scene constructed on a machine
+// without a GPU are built on the host.  TPT_BVH_BUILD=device / host forces one side for every list,
+// TPT_BVH_BUILD_MIN=<objects> moves the threshold.
 int BVHAccel::DeviceBuildMin() {
     if (const char* e = std::getenv("TPT_BVH_BUILD_MIN")) return std::max(1, std::atoi(e));
     if (const char* e = std::getenv("TPT_BVH_BUILD")) {
@@ -44,7 +45,7 @@ int BVHAccel::DeviceBuildMin() {
         if (std::string(e) == "host") return std::numeric_limits<int>::max();
     }
     static const bool have_device = tpt_device_count() > 0;
-    return have_device ? 16384 : std::numeric_limits<int>::max();
+    return have_device ? 4096 : std::numeric_limits<int>::max();
 }
 
 void BVHAccel::buildOnDevice() {
@@ -57,7 +58,7 @@ void BVHAccel::buildOnDevice() {
         areas[i] = primitives[i]->getArea();
     }
     std::vector<TptBvhNode> flat(2 * n - 1);
-    int device = 0;
+    int device = -1;                                   // the calling thread's current device (a rank of a multi-GPU job has set its own)
     if (const char* e = std::getenv("TPT_DEVICE")) device = std::atoi(e);
     if (tpt_bvh_build(bounds.data(), areas.data(), (int)n, device, flat.data(), &deviceBuildMs) != TPT_OK) {
         // the reference has no error channel here (a constructor, no exceptions); a build that was asked to run on
