@@ -42,7 +42,7 @@ struct BuildRange { int start, n, self; };
 #define BB_SMALL_THREADS 256      /* ... by a warp: eight ranges per block */
 #define BB_SMALL_N 48            /* a level whose ranges are at most this long is sorted a warp per range ... */
 #define BB_COOP_MIN 2048         /* partition steps over more elements than this are done by the whole block ... */
-#define BB_WARP_MIN 64           /* ... over more than this by a warp, shorter ones by a thread */
+                                 /* ... every shorter one by a warp (a task has more than SS_THRESHOLD elements) */
 
 __device__ __forceinline__ uint32_t centroid_key(const float* cent, uint32_t obj, int dim) {
     // -0 and +0 compare equal in the reference's comparator: fold them before taking the order-preserving bits
@@ -173,13 +173,31 @@ __device__ void warp_step(ss_word* v, SsRange T, SsRange* next, int* sh_next, in
     __syncwarp();
     for (int k = lane; k < K; k += 32) ss_swap(v, lpos[k], rpos[k]);
     __syncwarp();
-    if (lane == 0) finish_step(v, T, cut, next, sh_next);
+    // The two parts, a half-warp each: a part of more than SS_THRESHOLD elements is a task of the next round; a shorter
+    // one is finished here.  Insertion sort with a strict comparison is a stable sort, so every element's place is the
+    // number of smaller elements plus the number of equal ones before it: one lane per element ranks it.
+    const int j = lane & 15;
+    const int pf = (lane >> 4) ? cut : T.first, pl = (lane >> 4) ? T.last : cut;
+    const int plen = pl - pf;
+    const bool ranked = plen <= SS_THRESHOLD && j < plen;
+    ss_word mine = 0;
+    int rank = 0;
+    if (ranked) {
+        mine = v[pf + j];
+        for (int i = 0; i < plen; ++i) {
+            const ss_word o = v[pf + i];
+            rank += ss_less(o, mine) || (!ss_less(mine, o) && i < j);
+        }
+    }
+    __syncwarp();
+    if (ranked) v[pf + rank] = mine;
+    if (plen > SS_THRESHOLD && j == 0) next[atomicAdd(sh_next, 1)] = SsRange{pf, pl, T.depth - 1};
     __syncwarp();
 }
 
 // std::sort of work[0, len) by the block, starting from one introsort task with `depth` splits left: the partition
-// tree a round per level — the whole block on each long range of the round (coop_step), a warp on each middle one
-// (warp_step), a thread per short one (std_sort.cuh).  A step's two position lists take 2 ints per element of ITS
+// tree a round per level — the whole block on each long range of the round (coop_step), a warp on each shorter one
+// (warp_step, which also finishes the parts of at most SS_THRESHOLD elements).  A step's two position lists take 2 ints per element of ITS
 // range (lists: 2 * len ints); cur / next: the two task lists, len / 16 + 1 entries each.
 // FORWARD (ranges too long for shared memory, sorted in place in global memory): only the steps over more than
 // `local_max` elements are done here; the shorter tasks are handed to k_bvh_finish_tasks, which sorts each of them in
@@ -222,16 +240,7 @@ __device__ void block_sort(ss_word* work, int len, int depth, int* lists, SsRang
             for (int t = tid >> 5; t < n_tasks; t += nt / 32) {      // a warp on each of the middle ones
                 const SsRange T = cur[t];
                 const int l = T.last - T.first;
-                if (l > BB_WARP_MIN && l <= BB_COOP_MIN) warp_step(work, T, next, &sh->next, lists + 2 * T.first, lists + 2 * T.first + l);
-            }
-            // a thread on each of the short ones — neighbouring tasks to different WARPS: every lane walks its own
-            // data-dependent loops, and the lanes of one warp take turns on them
-            for (int t = (tid >> 5) + (nt / 32) * (tid & 31); t < n_tasks; t += nt) {
-                const SsRange T = cur[t];
-                if (T.last - T.first > BB_WARP_MIN) continue;
-                SsRange out[2];
-                const int k = ss_step(work, T, out);
-                for (int i = 0; i < k; ++i) next[atomicAdd(&sh->next, 1)] = out[i];
+                if (l <= BB_COOP_MIN) warp_step(work, T, next, &sh->next, lists + 2 * T.first, lists + 2 * T.first + l);
             }
         }
         __syncthreads();

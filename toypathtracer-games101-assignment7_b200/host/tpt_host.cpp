@@ -32,8 +32,8 @@ BVHAccel::BVHAccel(std::vector<Object*> p, int maxPrims, SplitMethod method)
 
 // Which lists are built on the GPU (tpt_bvh_build, csrc/bvh_build.cu) instead of by buildInPlace below: those with at
 // least DeviceBuildMin() objects.  Both produce the node array of the reference recursion, so this is a question of
-// time only (B200 + 16 host cores, profiles/r05k_bvh_build.log: 5 K objects 0.60 ms of kernels against 1.8 ms, 28 K
-// 1.5 against 7.5, 300 K 8.8 against 75; the call adds the copies of the boxes and the nodes, 1.4-1.7 ms in all at
+// time only (B200 + 16 host cores, profiles/r05s_bvh_build.log: 5 K objects 0.4 ms of kernels against 1.8 ms, 28 K
+// 1.1 against 7.5, 300 K 8.0 against 75; the call adds the copies of the boxes and the nodes, 1.4-1.7 ms in all at
 // 5 K): without a setting, lists of 4 096 objects and more go to the device when there is one — of the BASELINE
 // scenes that is the bunny; the Cornell meshes (12 triangles at most) and every scene constructed on a machine
 // without a GPU are built on the host.  TPT_BVH_BUILD=device / host forces one side for every list,
