@@ -39,6 +39,7 @@ struct BuildRange { int start, n, self; };
 #define BB_LONG_THREADS 1024     /* ... and ranges whose long partition steps run in global memory (more loads in flight) */
 #endif
 #define BB_MAX_WARPS 32
+#define BB_TOP_LEVELS 12         /* levels k_bvh_emit_top can take in its one launch */
 #define BB_SMALL_THREADS 256      /* ... by a warp: eight ranges per block */
 #define BB_SMALL_N 48            /* a level whose ranges are at most this long is sorted a warp per range ... */
 #define BB_COOP_MIN 2048         /* partition steps over more elements than this are done by the whole block ... */
@@ -372,11 +373,8 @@ __global__ void __launch_bounds__(BB_SMALL_THREADS) k_bvh_sort_level_small(const
 // The nodes of one level, deepest level first: a leaf takes its object's box and area, an inner node the Union of its
 // children's boxes (Bounds3.hpp:117-123: std::min / std::max with the left child as first argument) and the float sum
 // of their areas (BVH.cpp:44,50,97).
-__global__ void __launch_bounds__(256) k_bvh_emit_level(const BuildRange* __restrict__ ranges, int count, const ss_word* __restrict__ order,
-                                                        const float* __restrict__ bounds, const float* __restrict__ areas, TptBvhNode* nodes) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= count) return;
-    const BuildRange R = ranges[r];
+__device__ __forceinline__ void emit_node(const BuildRange R, const ss_word* __restrict__ order, const float* __restrict__ bounds,
+                                          const float* __restrict__ areas, TptBvhNode* nodes) {
     TptBvhNode nd;
     if (R.n == 1) {
         const uint32_t obj = (uint32_t)order[R.start];
@@ -397,6 +395,22 @@ __global__ void __launch_bounds__(256) k_bvh_emit_level(const BuildRange* __rest
         nd.area = __fadd_rn(a.area, b.area);
     }
     nodes[R.self] = nd;
+}
+__global__ void __launch_bounds__(256) k_bvh_emit_level(const BuildRange* __restrict__ ranges, int count, const ss_word* __restrict__ order,
+                                                        const float* __restrict__ bounds, const float* __restrict__ areas, TptBvhNode* nodes) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < count) emit_node(ranges[r], order, bounds, areas, nodes);
+}
+// The levels near the root (a few hundred ranges at most) in ONE launch: a block walks them upwards, a barrier between
+// levels (what a thread wrote to global memory is visible to its block after the barrier).
+struct LevelOffsets { int at[BB_TOP_LEVELS + 2]; };
+__global__ void __launch_bounds__(256) k_bvh_emit_top(const BuildRange* __restrict__ table, LevelOffsets lv, int top, const ss_word* __restrict__ order,
+                                                      const float* __restrict__ bounds, const float* __restrict__ areas, TptBvhNode* nodes) {
+    for (int l = top; l >= 0; --l) {
+        const int count = lv.at[l + 1] - lv.at[l];
+        for (int r = threadIdx.x; r < count; r += blockDim.x) emit_node(table[lv.at[l] + r], order, bounds, areas, nodes);
+        __syncthreads();
+    }
 }
 
 struct DevBlock {      // a work buffer from the caching allocator, returned when the build is over
@@ -504,11 +518,19 @@ extern "C" int tpt_bvh_build(const float* bounds, const float* areas, int n, int
         }
         mark(longest <= BB_SMALL_N ? "sort (thread per range)" : "sort (block per range)", lv, longest);
     }
-    for (size_t lv = levels; lv-- > 0;) {
+    // the levels of up to 1024 ranges (the first ten or eleven) in one launch, the wider ones a launch each
+    int top = -1;
+    LevelOffsets lo{};
+    for (size_t lv = 0; lv < levels && lv <= BB_TOP_LEVELS && level_at[lv + 1] - level_at[lv] <= 1024; ++lv) top = (int)lv;
+    for (int l = 0; l <= top + 1; ++l) lo.at[l] = (int)level_at[l];
+    for (size_t lv = levels; lv-- > (size_t)(top + 1);) {
         const int count = (int)(level_at[lv + 1] - level_at[lv]);
         BB_LAUNCH(k_bvh_emit_level, (count + 255) / 256, 256, 0, d_table.as<BuildRange>() + level_at[lv], count, d_order.as<ss_word>(), d_bounds.as<float>(),
                   d_areas.as<float>(), d_nodes.as<TptBvhNode>());
     }
+    if (top >= 0)
+        BB_LAUNCH(k_bvh_emit_top, 1, 256, 0, d_table.as<BuildRange>(), lo, top, d_order.as<ss_word>(), d_bounds.as<float>(), d_areas.as<float>(),
+                  d_nodes.as<TptBvhNode>());
     mark("emit, all levels", 0, n);
     cudaEventRecord(e1, 0);
     int rc = TPT_OK;
