@@ -8,10 +8,12 @@
 //    is known from n alone.  The host tabulates the ranges per level; no tree is discovered on the device.
 //  * a level only re-orders objects INSIDE its ranges.  One array of {key, object} words holds the order; a level
 //    rewrites the key halves (the centroid coordinate its range sorts by) and sorts each range in place, all ranges of
-//    the level in one launch — a block per range, or a thread per range once the ranges are small.
+//    the level in one launch — a block per range (a range too long for the block's shared memory does its long
+//    partition steps in place and hands the rest to a block per task), or a warp per range once the ranges are small.
 //  * the sort has to leave equal keys where libstdc++'s std::sort leaves them (std_sort.cuh): the leaf order is the
 //    tie order of the closest-hit contract.
-// Bounds and areas are formed afterwards, level by level from the leaves up, with the reference's expressions
+// Bounds and areas are formed afterwards, level by level from the leaves up (the levels near the root in one launch),
+// with the reference's expressions
 // (Union's std::min / std::max argument order, area = left + right in float), so the node array is the host build's
 // (host/tpt_host.cpp) bit for bit: tests/native/bvh_build_device.cpp compares them.
 #include <algorithm>
@@ -40,10 +42,10 @@ struct BuildRange { int start, n, self; };
 #endif
 #define BB_MAX_WARPS 32
 #define BB_TOP_LEVELS 12         /* levels k_bvh_emit_top can take in its one launch */
-#define BB_SMALL_THREADS 256      /* ... by a warp: eight ranges per block */
-#define BB_SMALL_N 48            /* a level whose ranges are at most this long is sorted a warp per range ... */
-#define BB_COOP_MIN 2048         /* partition steps over more elements than this are done by the whole block ... */
-                                 /* ... every shorter one by a warp (a task has more than SS_THRESHOLD elements) */
+#define BB_SMALL_N 48            /* a level whose ranges are at most this long is sorted a warp per range, ... */
+#define BB_SMALL_THREADS 256     /* ... eight ranges per block */
+#define BB_COOP_MIN 2048         /* partition steps over more elements than this are done by the whole block, every shorter
+                                    one by a warp (a task has more than SS_THRESHOLD elements) */
 
 __device__ __forceinline__ uint32_t centroid_key(const float* cent, uint32_t obj, int dim) {
     // -0 and +0 compare equal in the reference's comparator: fold them before taking the order-preserving bits
@@ -516,7 +518,7 @@ extern "C" int tpt_bvh_build(const float* bounds, const float* areas, int n, int
             if (!staged)
                 BB_LAUNCH(k_bvh_finish_tasks, 4 * num_sms, BB_THREADS, bb_smem_bytes(local_max), d_left.as<LeftTask>(), d_n_left.as<int>(), d_order.as<ss_word>());
         }
-        mark(longest <= BB_SMALL_N ? "sort (thread per range)" : "sort (block per range)", lv, longest);
+        mark(longest <= BB_SMALL_N ? "sort (warp per range)" : "sort (block per range)", lv, longest);
     }
     // the levels of up to 1024 ranges (the first ten or eleven) in one launch, the wider ones a launch each
     int top = -1;

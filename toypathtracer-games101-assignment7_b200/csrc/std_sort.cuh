@@ -10,11 +10,14 @@
 //
 // Two facts make the algorithm parallel without changing its result:
 //  * the introsort loop is a tree of partition steps over disjoint ranges; what a step does depends on its range
-//    alone, so the steps can run in any order (here: one round per tree level, one thread per range);
+//    alone, so the steps can run in any order (bvh_build.cu: one round per tree level, a warp or the whole block on
+//    a step — a step's swap sequence can be read off the array, see coop_step there; this header has the step as one
+//    thread performs it, which the warp-per-range kernel and the host check use);
 //  * the closing __final_insertion_sort is an insertion sort with a strict comparison, i.e. a STABLE sort of the
 //    arrangement the partition steps leave; since every element of a left part is <= every element of the right
-//    part, it never moves an element out of its <= 16-element piece, so each piece is insertion-sorted where its
-//    chain ends (a heap-sorted range — depth limit reached — is sorted already: a no-op).
+//    part, it never moves an element out of its <= 16-element piece, so each piece is sorted where its chain ends —
+//    by insertion here, by ranking in bvh_build.cu's warp_step: a stable sort has one result — (a heap-sorted range,
+//    depth limit reached, is sorted already: a no-op).
 // tests/native/std_sort_check.cpp compiles this header for the host and compares with std::sort itself.
 #pragma once
 #include <stdint.h>
